@@ -1,0 +1,207 @@
+/* vkhr_b200.h -- C ABI of the B200-native strand voxeliser.
+ *
+ * Drop-in boundary for ONE path of CaffeineViking/vkhr: voxelising hair strand
+ * vertices/segments into the 8-bit density volume (reference
+ * `vkhr::HairStyle::voxelize_vertices` / `voxelize_segments` returning a
+ * `vkhr::HairStyle::Volume`).  Plain C types only: no STL, GLM or torch types
+ * cross this boundary.  Paths below are relative to the reference tree.
+ *
+ * Data contract (identical to the reference):
+ *   vertices    V x 3 float32, 12-byte stride          (HairStyle::vertices, hair_style.hh:126)
+ *   indices     2 per segment, uint32 vertex ids       (HairStyle::indices,  hair_style.hh:139)
+ *   AABB        origin = bbox_min, size = max - min    (HairStyle::get_bounding_box, hair_style.cc:236-255)
+ *   densities   W*H*D uint8, x fastest, then y, then z (Volume::densities, hair_style.hh:93;
+ *               uploaded as VK_FORMAT_R8_UNORM by rasterizer/hair_style.cc:94-101)
+ *   tangents    W*H*D x int8[4], w = 0                 (Volume::tangents, hair_style.hh:94; R8G8B8A8_SNORM)
+ *   density     = min(number of samples landing in the voxel, 255)  (hair_style.cc:277-280, :322-325)
+ *
+ * Numerics: fp32 IEEE, the exact operation order of hair_style.cc:257-281 and
+ * :296-329, including the fp32 linear index of :276/:321 (which rounds for
+ * grids above 2^24 voxels).  Densities are bit-exact with the reference built
+ * with strict IEEE flags.  Where the reference is undefined this library
+ * defines: samples whose fp32 index is NaN/negative/>= W*H*D are dropped;
+ * segments whose step count is not < 2^24 are skipped; normalize with
+ * max == min leaves the grid unchanged; fewer than 2 indices => empty volume.
+ *
+ * Threading: one context = one device + one internal stream.  Calls on one
+ * context must be serialised by the caller; distinct contexts are independent.
+ * Host-pointer entry points are synchronous.  `_dev` entry points take device
+ * pointers, enqueue on the given stream (NULL = the context's stream) and
+ * return without synchronising.
+ *
+ * Errors: every call returns 0 or a negative vkhr_b200_status; nothing throws.
+ * There is no CPU fallback: without a usable sm_100 device vkhr_b200_create fails.
+ */
+#ifndef VKHR_B200_H
+#define VKHR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define VKHR_B200_API __declspec(dllexport)
+#else
+#define VKHR_B200_API __attribute__((visibility("default")))
+#endif
+
+typedef struct vkhr_b200_ctx vkhr_b200_ctx;
+
+typedef enum vkhr_b200_status {
+    VKHR_B200_OK = 0,
+    VKHR_B200_ERR_INVALID_ARGUMENT = -1,
+    VKHR_B200_ERR_CUDA = -2,
+    VKHR_B200_ERR_OUT_OF_MEMORY = -3,
+    VKHR_B200_ERR_NO_DEVICE = -4,
+    VKHR_B200_ERR_UNSUPPORTED = -5
+} vkhr_b200_status;
+
+/* flags (bitwise or) */
+enum {
+    /* Linear voxel index computed in exact integers instead of the reference's
+     * fp32 expression (hair_style.cc:276,:321).  Differs from the reference
+     * only for grids above 2^24 voxels.  Default (0) = reference behaviour. */
+    VKHR_B200_INDEX_EXACT = 1u << 0,
+    /* Apply Volume::normalize() (hair_style.cc:344-357) to the densities, as
+     * the only caller does (rasterizer/hair_style.cc:77). */
+    VKHR_B200_NORMALIZE = 1u << 1,
+    /* Kernel strategy override (default: chosen from the grid size).
+     * COUNT32: u32 hit counts in context scratch, then clamp to u8.
+     * PACKED8: saturating counts kept directly in the u8 output grid
+     *          (byte-packed 32-bit atomics, exact overflow repair). */
+    VKHR_B200_STRATEGY_COUNT32 = 1u << 8,
+    VKHR_B200_STRATEGY_PACKED8 = 1u << 9
+};
+
+/* 2x2x2 reduction functors for vkhr_b200_downsample (Volume::downsample takes
+ * an arbitrary functor over the 8 texels ordered x + 2y + 4z, hair_style.hh:228-257). */
+enum { VKHR_B200_DOWNSAMPLE_MAX = 0, VKHR_B200_DOWNSAMPLE_MEAN = 1,
+       VKHR_B200_DOWNSAMPLE_SUM = 2, VKHR_B200_DOWNSAMPLE_MIN = 3 };
+
+/* ---- context ---------------------------------------------------------- */
+VKHR_B200_API int vkhr_b200_create(int device, vkhr_b200_ctx** out);
+VKHR_B200_API void vkhr_b200_destroy(vkhr_b200_ctx* ctx);
+/* Message of the last failing call on this context (ctx may be NULL for create failures). */
+VKHR_B200_API const char* vkhr_b200_last_error(const vkhr_b200_ctx* ctx);
+VKHR_B200_API const char* vkhr_b200_version(void);
+/* The context's internal stream, as a cudaStream_t. */
+VKHR_B200_API void* vkhr_b200_stream(vkhr_b200_ctx* ctx);
+VKHR_B200_API int vkhr_b200_synchronize(vkhr_b200_ctx* ctx);
+/* Number of kernels this context has launched so far. */
+VKHR_B200_API uint64_t vkhr_b200_launch_count(const vkhr_b200_ctx* ctx);
+
+/* ---- host-pointer API: replaces HairStyle::voxelize_segments ----------
+ * (hair_style.hh:104, hair_style.cc:296-342).
+ * indices == NULL with segs_per_strand > 0 means uniform strands: the implicit
+ * pairs generate_indices() (hair_style.cc:196-213) would produce.
+ * tangents_in / tangents_out may be NULL (density only). */
+VKHR_B200_API int vkhr_b200_voxelize_segments(
+    vkhr_b200_ctx* ctx, const float* vertices, uint32_t n_vertices,
+    const uint32_t* indices, uint64_t n_indices, uint32_t segs_per_strand,
+    const float* tangents_in, const float aabb_origin[3], const float aabb_size[3],
+    uint32_t W, uint32_t H, uint32_t D, uint32_t flags,
+    uint8_t* densities_out, int8_t* tangents_out);
+
+/* Replaces HairStyle::voxelize_vertices (hair_style.hh:103, hair_style.cc:257-294). */
+VKHR_B200_API int vkhr_b200_voxelize_vertices(
+    vkhr_b200_ctx* ctx, const float* vertices, uint32_t n_vertices,
+    const float* tangents_in, const float aabb_origin[3], const float aabb_size[3],
+    uint32_t W, uint32_t H, uint32_t D, uint32_t flags,
+    uint8_t* densities_out, int8_t* tangents_out);
+
+/* ---- device-pointer API (per-frame path: no host<->device copies) ----- */
+VKHR_B200_API int vkhr_b200_voxelize_segments_dev(
+    vkhr_b200_ctx* ctx, const float* d_vertices, uint32_t n_vertices,
+    const uint32_t* d_indices, uint64_t n_indices, uint32_t segs_per_strand,
+    const float* d_tangents_in, const float aabb_origin[3], const float aabb_size[3],
+    uint32_t W, uint32_t H, uint32_t D, uint32_t flags,
+    uint8_t* d_densities_out, int8_t* d_tangents_out, void* stream);
+
+VKHR_B200_API int vkhr_b200_voxelize_vertices_dev(
+    vkhr_b200_ctx* ctx, const float* d_vertices, uint32_t n_vertices,
+    const float* d_tangents_in, const float aabb_origin[3], const float aabb_size[3],
+    uint32_t W, uint32_t H, uint32_t D, uint32_t flags,
+    uint8_t* d_densities_out, int8_t* d_tangents_out, void* stream);
+
+/* One crowd member: its own strands, AABB and output volume
+ * (the reference keeps one Volume per vulkan::HairStyle, rasterizer.cc:148-151). */
+typedef struct vkhr_b200_instance {
+    const float*    d_vertices;       /* device, V x 3 float32 */
+    const uint32_t* d_indices;        /* device or NULL (uniform strands) */
+    uint64_t        n_indices;
+    uint32_t        n_vertices;
+    uint32_t        segs_per_strand;
+    float           aabb_origin[3];
+    float           aabb_size[3];
+    uint8_t*        d_densities_out;  /* device, W*H*D */
+} vkhr_b200_instance;
+
+/* voxelize_segments for `n` independent instances (host array of descriptors,
+ * device pointers inside), all at the same resolution. */
+VKHR_B200_API int vkhr_b200_voxelize_segments_batch_dev(
+    vkhr_b200_ctx* ctx, const vkhr_b200_instance* instances, uint32_t n,
+    uint32_t W, uint32_t H, uint32_t D, uint32_t flags, void* stream);
+
+/* ---- multi-GPU building blocks ---------------------------------------- *
+ * A rank ADDS the hits of its shard of segments (vertices) into a W*H*D u32
+ * grid it owns (not cleared here); the shards' grids are summed (NCCL
+ * allreduce, integer) and clamped: density = min(sum, 255) -- exact for any
+ * partition because the reference counter saturates (hair_style.cc:322-325). */
+VKHR_B200_API int vkhr_b200_count_segments_dev(
+    vkhr_b200_ctx* ctx, const float* d_vertices, uint32_t n_vertices,
+    const uint32_t* d_indices, uint64_t n_indices, uint32_t segs_per_strand,
+    const float aabb_origin[3], const float aabb_size[3],
+    uint32_t W, uint32_t H, uint32_t D, uint32_t flags,
+    uint32_t* d_counts_inout, void* stream);
+
+VKHR_B200_API int vkhr_b200_count_vertices_dev(
+    vkhr_b200_ctx* ctx, const float* d_vertices, uint32_t n_vertices,
+    const float aabb_origin[3], const float aabb_size[3],
+    uint32_t W, uint32_t H, uint32_t D, uint32_t flags,
+    uint32_t* d_counts_inout, void* stream);
+
+/* densities = min(counts, 255), optionally followed by normalize (flags). */
+VKHR_B200_API int vkhr_b200_clamp_counts_dev(
+    vkhr_b200_ctx* ctx, const uint32_t* d_counts, uint64_t n_voxels, uint32_t flags,
+    uint8_t* d_densities_out, void* stream);
+
+/* ---- Volume operations -------------------------------------------------- */
+/* Volume::normalize (hair_style.cc:344-357), in place. */
+VKHR_B200_API int vkhr_b200_normalize_dev(vkhr_b200_ctx* ctx, uint8_t* d_densities, uint64_t n_voxels, void* stream);
+VKHR_B200_API int vkhr_b200_normalize(vkhr_b200_ctx* ctx, uint8_t* densities, uint64_t n_voxels);
+/* Volume::downsample (hair_style.hh:228-257): (W/2)*(H/2)*(D/2) texels out. */
+VKHR_B200_API int vkhr_b200_downsample_dev(vkhr_b200_ctx* ctx, const uint8_t* d_densities,
+    uint32_t W, uint32_t H, uint32_t D, int filter, uint8_t* d_out, void* stream);
+VKHR_B200_API int vkhr_b200_downsample(vkhr_b200_ctx* ctx, const uint8_t* densities,
+    uint32_t W, uint32_t H, uint32_t D, int filter, uint8_t* out);
+/* HairStyle::generate_bounding_box (hair_style.cc:215-234): min/max folded from
+ * (0,0,0).  d_aabb_out / aabb_out = min.xyz, max.xyz (6 floats). */
+VKHR_B200_API int vkhr_b200_generate_bounding_box_dev(vkhr_b200_ctx* ctx, const float* d_vertices,
+    uint32_t n_vertices, float* d_aabb_out, void* stream);
+VKHR_B200_API int vkhr_b200_generate_bounding_box(vkhr_b200_ctx* ctx, const float* vertices,
+    uint32_t n_vertices, float aabb_out[6]);
+
+/* ---- device memory helpers (so a C/C++ caller needs no CUDA headers) ----- */
+VKHR_B200_API int vkhr_b200_malloc(vkhr_b200_ctx* ctx, size_t bytes, void** d_ptr);
+VKHR_B200_API int vkhr_b200_free(vkhr_b200_ctx* ctx, void* d_ptr);
+VKHR_B200_API int vkhr_b200_memset(vkhr_b200_ctx* ctx, void* d_ptr, int value, size_t bytes, void* stream);
+VKHR_B200_API int vkhr_b200_upload(vkhr_b200_ctx* ctx, void* d_dst, const void* src, size_t bytes, void* stream);
+VKHR_B200_API int vkhr_b200_download(vkhr_b200_ctx* ctx, void* dst, const void* d_src, size_t bytes, void* stream);
+
+/* ---- harness helpers (host side; inputs only, not part of parity) ------- *
+ * The reference's .hair assets are Git-LFS pointers in the checkout, so the
+ * named workloads are generated: seeded random-walk strands of the named
+ * shape (xorshift64 of hair_style.cc:679-685, one stream per strand). */
+VKHR_B200_API int vkhr_b200_synth_strands(uint32_t n_strands, uint32_t segs_per_strand, uint64_t seed,
+    const float root_min[3], const float root_max[3], float seg_len, float curl, float gravity, float gather,
+    float* xyz_out);
+VKHR_B200_API int vkhr_b200_synth_sway(const float* xyz_in, uint32_t n_strands, uint32_t segs_per_strand,
+    float t, float amplitude, float omega, float* xyz_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VKHR_B200_H */

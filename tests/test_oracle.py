@@ -1,0 +1,179 @@
+"""The CPU restatement (oracle/voxel_oracle.c) against the pins: golden vectors generated from the
+unmodified reference (tests/golden/make_golden.py) and, where the reference driver is available,
+the reference itself on fresh inputs.  No GPU involved."""
+import numpy as np
+import pytest
+
+from conftest import dense
+
+from vkhr_b200 import synth
+
+
+def _fnv(port, a):
+    return f"{port.fnv1a64(a):016x}"
+
+
+def test_kat4_appendix_b(port, golden):
+    k = golden["kat4"]
+    v = np.array(k["vertices"], dtype=np.float32)
+    lo, hi = port.generate_bounding_box(v)
+    bb = port.get_bounding_box(lo, hi)
+    assert np.allclose(bb, k["aabb"], rtol=0, atol=0)
+    idx = port.generate_indices(k["strands"], k["segments_per_strand"])
+    assert idx.tolist() == k["indices"]
+    tg = port.generate_tangents(v, k["strands"], k["segments_per_strand"])
+    assert np.array_equal(tg, np.array(k["tangents_in"], dtype=np.float32), equal_nan=True)
+    d, t = port.voxelize_segments(v, idx, bb[:3], bb[4:7], 4, 4, 4, tangents=tg)
+    assert np.array_equal(d, dense(k["voxelize_segments"], 64))
+    # the hand-verified table of SURVEY.md Appendix B
+    assert {i: int(d[i]) for i in np.nonzero(d)[0]} == {0: 1, 12: 1, 13: 1, 14: 1, 21: 1, 42: 1, 63: 3}
+    for i, tv in k["voxelize_segments_tangents"].items():
+        assert t[int(i)].tolist() == tv
+    dv, tv_ = port.voxelize_vertices(v, bb[:3], bb[4:7], 4, 4, 4, tangents=tg)
+    assert np.array_equal(dv, dense(k["voxelize_vertices"], 64))
+    assert {i: int(dv[i]) for i in np.nonzero(dv)[0]} == {0: 1, 12: 1, 15: 1, 21: 2, 47: 1, 63: 2}
+    for i, tv in k["voxelize_vertices_tangents"].items():
+        assert tv_[int(i)].tolist() == tv
+    assert np.array_equal(port.normalize(d), dense(k["normalize_segments"], 64))
+    assert port.downsample(d, 4, 4, 4, 2).tolist() == k["downsample_sum_segments"] == [2, 0, 2, 1, 0, 0, 0, 4]
+    assert port.downsample(d, 4, 4, 4, 0).tolist() == k["downsample_max_segments"]
+
+
+@pytest.mark.parametrize("res", [(64, 64, 64), (64, 32, 16), (16, 16, 16), (30, 20, 10)])
+def test_small_sets(port, small_sets, res):
+    W, H, D = res
+    tag = f"{W}x{H}x{D}"
+    v = small_sets["in_vertices"]
+    n, s = [int(x) for x in small_sets["in_meta"]]
+    bb = small_sets["aabb_generated"]
+    lo, hi = port.generate_bounding_box(v)
+    assert np.array_equal(port.get_bounding_box(lo, hi), bb)
+    idx = port.generate_indices(n, s)
+    tg = port.generate_tangents(v, n, s)
+    d, t = port.voxelize_segments(v, idx, bb[:3], bb[4:7], W, H, D, tangents=tg)
+    assert np.array_equal(d, small_sets[f"seg_{tag}"])
+    # tangents: the reference's fp32 sum is reproduced op for op on one thread => exact here
+    assert np.array_equal(t, small_sets[f"segtan_{tag}"])
+    assert np.array_equal(port.voxelize_segments(v, idx, bb[:3], bb[4:7], W, H, D), d)   # density-only walk
+    assert np.array_equal(port.voxelize_vertices(v, bb[:3], bb[4:7], W, H, D), small_sets[f"ver_{tag}"])
+    assert np.array_equal(port.normalize(d), small_sets[f"segnorm_{tag}"])
+    if f"segdown0_{tag}" in small_sets:
+        for f in range(4):
+            assert np.array_equal(port.downsample(d, W, H, D, f), small_sets[f"segdown{f}_{tag}"])
+    # counts before the clamp: min(count, 255) == density
+    c = port.count_segments(v, idx, bb[:3], bb[4:7], W, H, D)
+    assert np.array_equal(np.minimum(c, 255).astype(np.uint8), d)
+    assert int(c.sum()) <= port.count_samples(v, idx, bb[:3], bb[4:7], W, H, D)
+
+
+def test_small_header_aabb_and_variable_strands(port, small_sets):
+    v = small_sets["in_vertices"]
+    n, s = [int(x) for x in small_sets["in_meta"]]
+    bb = small_sets["aabb_header"]
+    idx = port.generate_indices(n, s)
+    assert np.array_equal(port.voxelize_segments(v, idx, bb[:3], bb[4:7], 64, 64, 64), small_sets["seg_header_64x64x64"])
+    assert np.array_equal(port.voxelize_vertices(v, bb[:3], bb[4:7], 64, 64, 64), small_sets["ver_header_64x64x64"])
+    vv, segs, vbb = small_sets["var_vertices"], small_sets["var_segments"], small_sets["var_aabb"]
+    vidx = port.generate_indices(len(segs), 0, segments=segs)
+    assert np.array_equal(vidx, small_sets["var_indices"])
+    assert np.array_equal(port.voxelize_segments(vv, vidx, vbb[:3], vbb[4:7], 32, 32, 32), small_sets["var_seg_32x32x32"])
+
+
+@pytest.mark.parametrize("name", ["ponytail_256", "ponytail_long_256", "ponytail_sat_32", "ponytail_noncubic", "straight_512"])
+def test_full_size_fingerprints(port, golden, name):
+    e = golden["fingerprints"][name]
+    v, n, s = synth.shape(e["shape"], seed=e["seed"], seg_len=e["seg_len"], scale=e["scale"])
+    assert _fnv(port, v) == e["input_fnv"], "synthetic generator output changed: regenerate tests/golden"
+    W, H, D = e["resolution"]
+    bb = np.array(e["aabb"], dtype=np.float32)
+    idx = port.generate_indices(n, s)
+    d = port.voxelize_segments(v, idx, bb[:3], bb[4:7], W, H, D)
+    st = e["segments"]
+    assert (_fnv(port, d), int(d.astype(np.int64).sum()), int(np.count_nonzero(d)), int((d == 255).sum())) == \
+           (st["fnv"], st["sum"], st["nonzero"], st["saturated"])
+    assert _fnv(port, port.normalize(d)) == e["normalize_segments"]["fnv"]
+    dv = port.voxelize_vertices(v, bb[:3], bb[4:7], W, H, D)
+    assert _fnv(port, dv) == e["vertices"]["fnv"]
+    if name == "ponytail_sat_32":
+        assert st["saturated"] > 0 and st["max"] == 255
+    if name == "straight_512":
+        # an exact integer index differs from the reference's fp32 index above 2^24 voxels
+        de = port.voxelize_segments(v, idx, bb[:3], bb[4:7], W, H, D, flags=1)
+        assert not np.array_equal(de, d)
+        assert int(np.minimum(port.count_segments(v, idx, bb[:3], bb[4:7], W, H, D, flags=1), 255).sum()) == int(de.astype(np.int64).sum())
+
+
+def _random_case(rng, n_strands, segs, spread):
+    v = synth.strands(n_strands, segs, seed=int(rng.integers(1, 2**31)), seg_len=float(spread),
+                      curl=float(rng.uniform(0.1, 2.0)), gravity=float(rng.uniform(0, 0.6)))
+    return v
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_port_matches_live_reference(port, ref, seed):
+    """Fresh seeded inputs through the unmodified reference and through the restatement."""
+    rng = np.random.default_rng(100 + seed)
+    n, s = int(rng.integers(50, 600)), int(rng.integers(1, 20))
+    v = _random_case(rng, n, s, rng.uniform(0.2, 6.0))
+    W, H, D = [int(x) for x in rng.choice([4, 7, 16, 33, 64, 100], size=3)]
+    if seed % 2:
+        hs = ref.create(v, n, s)
+    else:                                   # header AABB slightly larger than the data
+        lo, hi = v.min(axis=0) - 0.5, v.max(axis=0) + 0.25
+        hs = ref.create(v, n, s, aabb_min=lo, aabb_max=hi)
+    bb = hs.aabb
+    idx, tg = hs.indices, hs.tangents
+    assert np.array_equal(port.generate_indices(n, s), idx)
+    assert np.array_equal(port.generate_tangents(v, n, s), tg, equal_nan=True)
+    d_ref, t_ref, _ = hs.voxelize("segments", W, H, D, want_tangents=True)
+    d, t = port.voxelize_segments(v, idx, bb[:3], bb[4:7], W, H, D, tangents=tg)
+    assert np.array_equal(d, d_ref)
+    assert np.array_equal(t, t_ref)
+    dv_ref, tv_ref, _ = hs.voxelize("vertices", W, H, D, want_tangents=True)
+    dv, tv = port.voxelize_vertices(v, bb[:3], bb[4:7], W, H, D, tangents=tg)
+    assert np.array_equal(dv, dv_ref) and np.array_equal(tv, tv_ref)
+    assert np.array_equal(port.normalize(d), ref.normalize(d_ref))
+    if W % 2 == 0 and H % 2 == 0 and D % 2 == 0:
+        for f in range(4):
+            assert np.array_equal(port.downsample(d, W, H, D, f), ref.downsample(d_ref, W, H, D, f))
+
+
+def test_edge_cases_against_reference(port, ref):
+    """Max-corner clamp, zero-length segments, vertices on voxel faces, a saturating clump."""
+    rng = np.random.default_rng(5)
+    clump = np.tile(np.array([[1.25, 1.25, 1.25], [1.75, 2.6, 1.3]], dtype=np.float32), (400, 1))   # 400 x same segment
+    faces = np.array([[0, 0, 0], [8, 8, 8], [8, 8, 8], [8, 0, 8], [2, 2, 2], [2, 2, 2], [3, 3, 3], [3, 4, 3],
+                      [7.999999, 7.999999, 7.999999], [8, 8, 8], [0, 8, 0], [8, 8, 0]], dtype=np.float32)
+    jitter = rng.uniform(0, 8, size=(200, 3)).astype(np.float32)
+    v = np.concatenate([clump, faces, jitter], axis=0)
+    n = v.shape[0] // 2
+    hs = ref.create(v, n, 1)
+    bb = hs.aabb
+    for res in [(8, 8, 8), (4, 4, 4), (5, 3, 2)]:
+        d_ref, t_ref, _ = hs.voxelize("segments", *res, want_tangents=True)
+        d, t = port.voxelize_segments(v, hs.indices, bb[:3], bb[4:7], *res, tangents=hs.tangents)
+        assert np.array_equal(d, d_ref) and d.max() == 255
+        sat = d == 255
+        assert np.array_equal(t[~sat], t_ref[~sat])
+        assert np.array_equal(port.voxelize_vertices(v, bb[:3], bb[4:7], *res), hs.voxelize("vertices", *res)[0])
+
+
+def test_defined_extensions(port):
+    """Inputs on which the reference is undefined: the rules both the oracle and the CUDA path implement."""
+    origin, size = np.zeros(3, np.float32), np.full(3, 4.0, np.float32)
+    # a vertex outside the box: index out of range => dropped; in-range wrap-around is kept like the reference
+    v = np.array([[9, 9, 9], [9.5, 9, 9], [1, 1, 1], [1, 1, 1]], dtype=np.float32)
+    idx = np.array([0, 1, 2, 3], dtype=np.uint32)
+    assert port.voxelize_segments(v, idx, origin, size, 4, 4, 4).sum() == 1      # (9,9,9) clamps to voxel 63
+    v = np.array([[-9, -9, -9], [-9.5, -9, -9]], dtype=np.float32)
+    assert port.voxelize_segments(v, idx[:2], origin, size, 4, 4, 4).sum() == 0  # negative index: dropped
+    v = np.array([[np.nan, 0, 0], [1, 1, 1]], dtype=np.float32)
+    assert port.voxelize_segments(v, idx[:2], origin, size, 4, 4, 4).sum() == 0
+    assert port.voxelize_vertices(v, origin, size, 4, 4, 4).sum() == 1
+    # fewer than two indices => empty volume; odd trailing index ignored
+    v = np.array([[0, 0, 0], [3, 0, 0], [0, 3, 0]], dtype=np.float32)
+    assert port.voxelize_segments(v, np.array([0], np.uint32), origin, size, 4, 4, 4).sum() == 0
+    assert port.voxelize_segments(v, np.array([0, 1, 2], np.uint32), origin, size, 4, 4, 4).sum() == 3
+    # normalize with max == min leaves the grid unchanged
+    flat = np.full(64, 7, dtype=np.uint8)
+    assert np.array_equal(port.normalize(flat), flat)

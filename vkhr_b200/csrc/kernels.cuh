@@ -1,0 +1,340 @@
+// kernels.cuh -- sm_100a kernels of the strand-voxelisation path.
+//
+// Reference behaviour being replaced (paths relative to the reference tree):
+//   segment walk + saturating u8 count   src/vkhr/scene_graph/hair_style.cc:311-329
+//   vertex splat                          src/vkhr/scene_graph/hair_style.cc:272-281
+//   Volume::normalize                     src/vkhr/scene_graph/hair_style.cc:344-357
+//   Volume::downsample                    include/vkhr/scene_graph/hair_style.hh:228-257
+//   generate_bounding_box                 src/vkhr/scene_graph/hair_style.cc:215-234
+#pragma once
+#include "walk.cuh"
+
+namespace vkhr_b200 {
+
+constexpr int kWalkThreads = 256;
+
+// Device-side description of one instance of a batch.
+struct InstanceDev {
+    const float*    vertices;
+    const uint32_t* indices;        // nullptr => uniform strands
+    uint64_t        n_segments;
+    uint32_t        n_vertices;
+    uint32_t        segs_per_strand;
+    GridParams      grid;
+    uint8_t*        densities;      // W*H*D u8 (PACKED8: counted in place)
+    uint32_t*       counts;         // W*H*D u32 (COUNT32) or nullptr
+    uint32_t*       ovf_bitmap;     // PACKED8: 1 bit per 32-bit word of `densities`
+    uint32_t*       ovf_flag;       // PACKED8: != 0 when any word overflowed
+    uint32_t        first_tile;     // first CTA tile of this instance in the flat batch grid
+    uint32_t        pad;
+};
+
+// ---------------------------------------------------------------------------
+// Sinks: what one sample does to the grid.
+// ---------------------------------------------------------------------------
+
+// COUNT32: plain u32 hit counter, clamped later.  `red.global.add.u32` (no return).
+struct SinkCount32 {
+    uint32_t* counts;
+    __device__ __forceinline__ void operator()(uint32_t idx) const { atomicAdd(counts + idx, 1u); }
+};
+
+// PACKED8: the u8 output grid itself is the counter; four voxels share one
+// 32-bit word and a hit adds 1 << (8 * byte).  The returned old word tells
+// the adding thread whether ITS add carried out of the byte (old field ==
+// 255).  The first carry in a word is always seen on a clean word, so a word
+// is flagged in the bitmap if and only if one of its voxels received more
+// than 255 hits; flagged words are recounted exactly by k_repair_*.
+struct SinkPacked8 {
+    uint32_t* words;
+    uint32_t* ovf_bitmap;
+    uint32_t* ovf_flag;
+    __device__ __forceinline__ void operator()(uint32_t idx) const {
+        const uint32_t w = idx >> 2, sh = (idx & 3u) * 8u;
+        const uint32_t old = atomicAdd(words + w, 1u << sh);
+        if (((old >> sh) & 0xFFu) == 0xFFu) {
+            atomicOr(ovf_bitmap + (w >> 5), 1u << (w & 31u));
+            *ovf_flag = 1u;
+        }
+    }
+};
+
+// Recount pass of PACKED8: only samples landing in flagged words are counted,
+// into the u32 scratch grid.
+struct SinkRecount {
+    const uint32_t* ovf_bitmap;
+    uint32_t* counts;
+    __device__ __forceinline__ void operator()(uint32_t idx) const {
+        const uint32_t w = idx >> 2;
+        if ((__ldg(ovf_bitmap + (w >> 5)) >> (w & 31u)) & 1u) atomicAdd(counts + idx, 1u);
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Walk kernels.  One thread per segment (or per vertex); consecutive threads
+// take consecutive segments of the same strand, so a warp reads a contiguous
+// span of the vertex array.
+// ---------------------------------------------------------------------------
+template <class Sink>
+__device__ __forceinline__ void walk_one_segment(const float* __restrict__ vertices,
+                                                 const uint32_t* __restrict__ indices,
+                                                 uint32_t segs, uint64_t s,
+                                                 const GridParams& g, Sink&& sink) {
+    uint32_t i0, i1;
+    segment_vertices(indices, segs, s, i0, i1);
+    const float* a = vertices + 3ull * i0;
+    const float* b = vertices + 3ull * i1;
+    walk_segment(g, __ldg(a), __ldg(a + 1), __ldg(a + 2), __ldg(b), __ldg(b + 1), __ldg(b + 2), sink);
+}
+
+// Batched walk: a flat grid of tiles over all instances; each CTA finds its
+// instance by binary search over first_tile.  MODE 0 = COUNT32, 1 = PACKED8,
+// 2 = recount of flagged words (only instances whose ovf_flag is set).
+template <int MODE>
+__global__ void __launch_bounds__(kWalkThreads)
+k_walk_batch(const InstanceDev* __restrict__ inst, uint32_t n_inst) {
+    uint32_t lo = 0, hi = n_inst - 1;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi + 1) >> 1;
+        if (inst[mid].first_tile <= blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const InstanceDev& I = inst[lo];
+    if (MODE == 2 && *I.ovf_flag == 0u) return;
+    const uint64_t s = (uint64_t)(blockIdx.x - I.first_tile) * kWalkThreads + threadIdx.x;
+    if (s >= I.n_segments) return;
+    if (MODE == 0)
+        walk_one_segment(I.vertices, I.indices, I.segs_per_strand, s, I.grid, SinkCount32{I.counts});
+    else if (MODE == 1)
+        walk_one_segment(I.vertices, I.indices, I.segs_per_strand, s, I.grid,
+                         SinkPacked8{reinterpret_cast<uint32_t*>(I.densities), I.ovf_bitmap, I.ovf_flag});
+    else
+        walk_one_segment(I.vertices, I.indices, I.segs_per_strand, s, I.grid,
+                         SinkRecount{I.ovf_bitmap, I.counts});
+}
+
+// Same for the vertex splat (instances reuse n_vertices; indices unused).
+template <int MODE>
+__global__ void __launch_bounds__(kWalkThreads)
+k_splat_batch(const InstanceDev* __restrict__ inst, uint32_t n_inst) {
+    uint32_t lo = 0, hi = n_inst - 1;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi + 1) >> 1;
+        if (inst[mid].first_tile <= blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const InstanceDev& I = inst[lo];
+    if (MODE == 2 && *I.ovf_flag == 0u) return;
+    const uint32_t i = (blockIdx.x - I.first_tile) * kWalkThreads + threadIdx.x;
+    if (i >= I.n_vertices) return;
+    const float* v = I.vertices + 3ull * i;
+    const GridParams& g = I.grid;
+    uint32_t idx;
+    if (!voxel_index(g, to_voxel_space(__ldg(v), g.ox, g.vsx), to_voxel_space(__ldg(v + 1), g.oy, g.vsy),
+                     to_voxel_space(__ldg(v + 2), g.oz, g.vsz), idx))
+        return;
+    if (MODE == 0) SinkCount32{I.counts}(idx);
+    else if (MODE == 1) SinkPacked8{reinterpret_cast<uint32_t*>(I.densities), I.ovf_bitmap, I.ovf_flag}(idx);
+    else SinkRecount{I.ovf_bitmap, I.counts}(idx);
+}
+
+// ---------------------------------------------------------------------------
+// Grid-stride helpers: clear, clamp, repair.
+// ---------------------------------------------------------------------------
+
+// Zero `n16` 16-byte words (grid-stride, st.global.v4).
+__global__ void __launch_bounds__(256) k_zero16(uint4* __restrict__ p, uint64_t n16) {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16;
+         i += (uint64_t)gridDim.x * blockDim.x)
+        p[i] = z;
+}
+
+// PACKED8 clear for a batch: densities, overflow bitmap and flag of every instance.
+// blockIdx.y = instance.  n_voxels % 16 == 0 is guaranteed by the host (else COUNT32).
+__global__ void __launch_bounds__(256) k_clear_packed_batch(const InstanceDev* __restrict__ inst) {
+    const InstanceDev& I = inst[blockIdx.y];
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    uint4* d = reinterpret_cast<uint4*>(I.densities);
+    const uint32_t n16 = I.grid.n_voxels >> 4;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t i = t; i < n16; i += stride) d[i] = z;
+    const uint32_t n_bm = (I.grid.n_voxels / 4 + 31) / 32;          // bitmap words
+    for (uint32_t i = t; i < n_bm; i += stride) I.ovf_bitmap[i] = 0u;
+    if (t == 0) *I.ovf_flag = 0u;
+}
+
+// densities = min(counts, 255)  (hair_style.cc:322: `if (d != 255) d += 1`),
+// 16 voxels per thread-iteration: 4 x ld.v4.u32 -> 1 x st.v4.u32.
+// ZERO: also write zeros back over the counts (leaves the scratch clean for the next frame).
+__device__ __forceinline__ uint32_t clamp4(uint4 c) {
+    return min(c.x, 255u) | (min(c.y, 255u) << 8) | (min(c.z, 255u) << 16) | (min(c.w, 255u) << 24);
+}
+
+template <bool ZERO>
+__global__ void __launch_bounds__(256)
+k_clamp_counts(uint32_t* __restrict__ counts, uint64_t n, uint8_t* __restrict__ dens) {
+    const uint64_t n16 = n >> 4;
+    uint4* c4 = reinterpret_cast<uint4*>(counts);
+    uint4* d4 = reinterpret_cast<uint4*>(dens);
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 a = c4[4 * i], b = c4[4 * i + 1], c = c4[4 * i + 2], d = c4[4 * i + 3];
+        d4[i] = make_uint4(clamp4(a), clamp4(b), clamp4(c), clamp4(d));
+        if (ZERO) { c4[4 * i] = z; c4[4 * i + 1] = z; c4[4 * i + 2] = z; c4[4 * i + 3] = z; }
+    }
+    // tail (n % 16 voxels), first threads of block 0
+    if (blockIdx.x == 0) {
+        for (uint64_t i = (n16 << 4) + threadIdx.x; i < n; i += blockDim.x) {
+            dens[i] = (uint8_t)min(counts[i], 255u);
+            if (ZERO) counts[i] = 0u;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Volume::normalize (hair_style.cc:344-357): min/max, then a 256-entry map
+//   d -> (uchar)(float(uchar(d - lo)) * (255.0f / float(hi - lo))).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_minmax_u8(const uint8_t* __restrict__ dens, uint64_t n, uint32_t* __restrict__ lohi /* [0]=min, [1]=max */) {
+    uint32_t lo = 255u, hi = 0u;
+    const uint64_t n16 = n >> 4;
+    const uint4* d4 = reinterpret_cast<const uint4*>(dens);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 v = d4[i];
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            // per-byte min/max of one word against the running values
+            uint32_t x = w[k];
+            uint32_t b0 = x & 0xFFu, b1 = (x >> 8) & 0xFFu, b2 = (x >> 16) & 0xFFu, b3 = x >> 24;
+            lo = min(lo, min(min(b0, b1), min(b2, b3)));
+            hi = max(hi, max(max(b0, b1), max(b2, b3)));
+        }
+    }
+    if (blockIdx.x == 0)
+        for (uint64_t i = (n16 << 4) + threadIdx.x; i < n; i += blockDim.x) {
+            lo = min(lo, (uint32_t)dens[i]);
+            hi = max(hi, (uint32_t)dens[i]);
+        }
+    lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+    hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+    if ((threadIdx.x & 31) == 0) {
+        if (lo != 255u) atomicMin(lohi, lo);
+        if (hi != 0u) atomicMax(lohi + 1, hi);
+    }
+}
+
+__global__ void k_minmax_init(uint32_t* lohi) { lohi[0] = 255u; lohi[1] = 0u; }
+
+__global__ void __launch_bounds__(256)
+k_normalize_apply(uint8_t* __restrict__ dens, uint64_t n, const uint32_t* __restrict__ lohi) {
+    __shared__ uint8_t lut[256];
+    const uint32_t lo = lohi[0], hi = lohi[1];
+    if (hi == lo) return;                                  // 255/0 in the reference: leave unchanged
+    const float scaling = __fdiv_rn(255.0f, (float)(int)(hi - lo));
+    for (uint32_t v = threadIdx.x; v < 256; v += blockDim.x) {
+        const uint32_t d = (v - lo) & 0xFFu;                // unsigned char wrap of `d -= min`
+        lut[v] = (uint8_t)__float2int_rz(__fmul_rn((float)d, scaling));
+    }
+    __syncthreads();
+    const uint64_t n16 = n >> 4;
+    uint4* d4 = reinterpret_cast<uint4*>(dens);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 v = d4[i];
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t x = w[k];
+            w[k] = (uint32_t)lut[x & 0xFFu] | ((uint32_t)lut[(x >> 8) & 0xFFu] << 8) |
+                   ((uint32_t)lut[(x >> 16) & 0xFFu] << 16) | ((uint32_t)lut[x >> 24] << 24);
+        }
+        d4[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    if (blockIdx.x == 0)
+        for (uint64_t i = (n16 << 4) + threadIdx.x; i < n; i += blockDim.x) dens[i] = lut[dens[i]];
+}
+
+// ---------------------------------------------------------------------------
+// Volume::downsample (hair_style.hh:228-257): 2x2x2 -> 1, output (W/2,H/2,D/2).
+// filter: 0 max, 1 sum/8, 2 (uchar)sum, 3 min.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_downsample(const uint8_t* __restrict__ in, uint32_t W, uint32_t H, uint32_t w, uint32_t h, uint32_t d,
+             int filter, uint8_t* __restrict__ out) {
+    const uint64_t n = (uint64_t)w * h * d;
+    for (uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n;
+         o += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t i = (uint32_t)(o % w), j = (uint32_t)((o / w) % h), k = (uint32_t)(o / ((uint64_t)w * h));
+        uint32_t s = 0, mx = 0, mn = 255;
+#pragma unroll
+        for (int z = 0; z < 2; ++z)
+#pragma unroll
+            for (int y = 0; y < 2; ++y) {
+                const uint8_t* p = in + (2ull * i) + (uint64_t)(2 * j + y) * W + (uint64_t)(2 * k + z) * W * H;
+                uint32_t a = p[0], b = p[1];
+                s += a + b;
+                mx = max(mx, max(a, b));
+                mn = min(mn, min(a, b));
+            }
+        out[o] = (uint8_t)(filter == 0 ? mx : filter == 1 ? s / 8 : filter == 2 ? s : mn);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// HairStyle::generate_bounding_box (hair_style.cc:215-234): min/max folded
+// from (0,0,0).  Floats are mapped to order-preserving u32 keys so the fold is
+// an integer atomicMin/Max; out[0..2] = min keys, out[3..5] = max keys,
+// initialised to key(0.0f) by k_aabb_init and decoded by k_aabb_decode.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t f2key(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+__global__ void k_aabb_init(uint32_t* keys) {
+    if (threadIdx.x < 6) keys[threadIdx.x] = f2key(0.0f);
+}
+__global__ void __launch_bounds__(256)
+k_aabb_reduce(const float* __restrict__ xyz, uint32_t n_vertices, uint32_t* __restrict__ keys) {
+    // A block-iteration covers 768 consecutive floats (a multiple of 3), so the
+    // float at base + 256*r + t is component (t + r) % 3: each thread keeps three
+    // running (min,max) pairs, one per r, with fully coalesced loads.
+    __shared__ uint32_t s_keys[6];
+    const uint32_t z = f2key(0.0f);
+    if (threadIdx.x < 6) s_keys[threadIdx.x] = z;
+    __syncthreads();
+    const uint64_t n = 3ull * n_vertices;
+    uint32_t lo[3] = {z, z, z}, hi[3] = {z, z, z};
+    const uint64_t stride = (uint64_t)gridDim.x * 768ull;
+    for (uint64_t base = (uint64_t)blockIdx.x * 768ull; base < n; base += stride) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const uint64_t i = base + r * 256 + threadIdx.x;
+            if (i < n) {
+                const uint32_t k = f2key(xyz[i]);
+                lo[r] = min(lo[r], k);
+                hi[r] = max(hi[r], k);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int comp = (threadIdx.x + r) % 3;
+        if (lo[r] != z) atomicMin(&s_keys[comp], lo[r]);
+        if (hi[r] != z) atomicMax(&s_keys[3 + comp], hi[r]);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) atomicMin(keys + threadIdx.x, s_keys[threadIdx.x]);
+    else if (threadIdx.x < 6) atomicMax(keys + threadIdx.x, s_keys[threadIdx.x]);
+}
+__global__ void k_aabb_decode(const uint32_t* keys, float* out6) {
+    if (threadIdx.x < 6) out6[threadIdx.x] = key2f(keys[threadIdx.x]);
+}
+
+}  // namespace vkhr_b200

@@ -1,0 +1,701 @@
+// vkhr_b200.cu -- the C ABI of include/vkhr_b200.h over the sm_100a kernels.
+//
+// Replaces, behind plain C entry points, the reference's
+//   HairStyle::voxelize_segments   (src/vkhr/scene_graph/hair_style.cc:296-342)
+//   HairStyle::voxelize_vertices   (src/vkhr/scene_graph/hair_style.cc:257-294)
+//   Volume::normalize / downsample (hair_style.cc:344-357, hair_style.hh:228-257)
+//   HairStyle::generate_bounding_box (hair_style.cc:215-234)
+// There is no CPU fallback anywhere in this file: every entry point either
+// runs the CUDA kernels or returns an error.
+#include "../../include/vkhr_b200.h"
+#include "kernels.cuh"
+
+#include <cooperative_groups.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace cg = cooperative_groups;
+using namespace vkhr_b200;
+
+// ---------------------------------------------------------------------------
+// PACKED8 repair: one persistent cooperative kernel.  Instances whose overflow
+// flag is set (some voxel received more than 255 hits) are handled one after
+// the other on a single shared u32 scratch grid:
+//   zero the scratch entries of flagged words -> grid barrier ->
+//   re-walk the instance, counting only samples that land in flagged words ->
+//   grid barrier -> rewrite the flagged words as min(count, 255).
+// With no flag set (the common case) every CTA returns after reading n flags.
+// ---------------------------------------------------------------------------
+template <bool VERTICES>
+__global__ void __launch_bounds__(kWalkThreads)
+k_repair_packed(const InstanceDev* __restrict__ inst, uint32_t n_inst, uint32_t* __restrict__ scratch) {
+    cg::grid_group grid = cg::this_grid();
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nthreads = gridDim.x * blockDim.x;
+    for (uint32_t k = 0; k < n_inst; ++k) {
+        const InstanceDev& I = inst[k];
+        if (*I.ovf_flag == 0u) continue;                       // uniform across the grid
+        const uint32_t n_words = I.grid.n_voxels >> 2;
+        const uint32_t n_bm = (n_words + 31) / 32;
+        uint32_t* words = reinterpret_cast<uint32_t*>(I.densities);
+        uint4* counts4 = reinterpret_cast<uint4*>(scratch);
+        for (uint32_t b = tid; b < n_bm; b += nthreads) {
+            uint32_t m = I.ovf_bitmap[b];
+            while (m) {
+                const uint32_t w = b * 32 + (__ffs(m) - 1);
+                m &= m - 1;
+                if (w < n_words) counts4[w] = make_uint4(0, 0, 0, 0);
+            }
+        }
+        grid.sync();
+        const SinkRecount sink{I.ovf_bitmap, scratch};
+        if (VERTICES) {
+            for (uint32_t i = tid; i < I.n_vertices; i += nthreads) {
+                const float* v = I.vertices + 3ull * i;
+                const GridParams& g = I.grid;
+                uint32_t idx;
+                if (voxel_index(g, to_voxel_space(__ldg(v), g.ox, g.vsx), to_voxel_space(__ldg(v + 1), g.oy, g.vsy),
+                                to_voxel_space(__ldg(v + 2), g.oz, g.vsz), idx))
+                    sink(idx);
+            }
+        } else {
+            for (uint64_t s = tid; s < I.n_segments; s += nthreads)
+                walk_one_segment(I.vertices, I.indices, I.segs_per_strand, s, I.grid, sink);
+        }
+        grid.sync();
+        for (uint32_t b = tid; b < n_bm; b += nthreads) {
+            uint32_t m = I.ovf_bitmap[b];
+            while (m) {
+                const uint32_t w = b * 32 + (__ffs(m) - 1);
+                m &= m - 1;
+                if (w < n_words) words[w] = clamp4(counts4[w]);
+            }
+        }
+        grid.sync();                                           // scratch is reused by the next flagged instance
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Context
+// ---------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct vkhr_b200_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    DevBuf counts;        // u32 scratch grid(s)
+    size_t counts_clean_bytes = 0;   // leading bytes of `counts` known to be zero
+    DevBuf bitmap;        // PACKED8 overflow bitmaps (+ flags at the front)
+    DevBuf table;         // InstanceDev[]
+    DevBuf small;         // lohi[2] + aabb keys[6] + aabb floats[6]
+    DevBuf st_vertices, st_indices, st_tangents, st_dens, st_tang_out;   // host-API staging
+    int repair_blocks[2] = {0, 0};
+    std::vector<InstanceDev> host_table;
+};
+
+static thread_local std::string g_create_error;
+
+namespace {
+
+int fail(vkhr_b200_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CU_CHECK(ctx, expr)                                                                      \
+    do {                                                                                         \
+        cudaError_t e_ = (expr);                                                                 \
+        if (e_ != cudaSuccess) {                                                                 \
+            int code_ = (e_ == cudaErrorMemoryAllocation) ? VKHR_B200_ERR_OUT_OF_MEMORY          \
+                                                          : VKHR_B200_ERR_CUDA;                  \
+            return fail(ctx, code_, std::string(#expr) + ": " + cudaGetErrorString(e_));         \
+        }                                                                                        \
+    } while (0)
+
+#define RET_IF(expr)                     \
+    do {                                 \
+        int rc_ = (expr);                \
+        if (rc_ != VKHR_B200_OK) return rc_; \
+    } while (0)
+
+int bind(vkhr_b200_ctx* ctx) {
+    if (!ctx) return fail(nullptr, VKHR_B200_ERR_INVALID_ARGUMENT, "null context");
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    return VKHR_B200_OK;
+}
+
+int reserve(vkhr_b200_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return VKHR_B200_OK;
+    if (b.p) {
+        CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        CU_CHECK(ctx, cudaFree(b.p));
+        b.p = nullptr; b.cap = 0;
+    }
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); want = bytes; e = cudaMalloc(&b.p, want); }
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        b.p = nullptr;
+        return fail(ctx, VKHR_B200_ERR_OUT_OF_MEMORY, "cudaMalloc of " + std::to_string(bytes) + " bytes failed");
+    }
+    b.cap = want;
+    return VKHR_B200_OK;
+}
+
+inline cudaStream_t pick(vkhr_b200_ctx* ctx, void* stream) {
+    return stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+}
+
+inline unsigned stride_blocks(vkhr_b200_ctx* ctx, uint64_t items, unsigned per_block, unsigned waves) {
+    uint64_t need = (items + per_block - 1) / per_block;
+    uint64_t cap = (uint64_t)ctx->sm_count * waves;
+    uint64_t g = need < cap ? need : cap;
+    return (unsigned)(g ? g : 1);
+}
+
+int make_grid(vkhr_b200_ctx* ctx, const float origin[3], const float size[3],
+              uint32_t W, uint32_t H, uint32_t D, uint32_t flags, GridParams& g) {
+    if (!origin || !size) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null AABB");
+    if (W == 0 || H == 0 || D == 0) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "zero resolution");
+    const unsigned long long n = (unsigned long long)W * H * D;
+    if (n >= (1ull << 32)) return fail(ctx, VKHR_B200_ERR_UNSUPPORTED, "W*H*D must be < 2^32");
+    for (int c = 0; c < 3; ++c)
+        if (!std::isfinite(origin[c]) || !std::isfinite(size[c]) || !(size[c] > 0.0f))
+            return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "AABB must be finite with size > 0");
+    // hair_style.cc:297-307: resolution is a glm::vec3 of floats, voxel_size = size / resolution
+    const float rx = (float)(size_t)W, ry = (float)(size_t)H, rz = (float)(size_t)D;
+    g.ox = origin[0]; g.oy = origin[1]; g.oz = origin[2];
+    g.vsx = size[0] / rx; g.vsy = size[1] / ry; g.vsz = size[2] / rz;
+    g.rx1 = rx - 1.0f; g.ry1 = ry - 1.0f; g.rz1 = rz - 1.0f;
+    g.Wf = rx; g.Hf = ry;
+    g.W = W; g.H = H; g.D = D;
+    g.n_voxels = (uint32_t)n;
+    g.index_exact = (flags & VKHR_B200_INDEX_EXACT) ? 1u : 0u;
+    return VKHR_B200_OK;
+}
+
+// Number of segments described by (indices, n_indices) or by uniform strands.
+int segment_count(vkhr_b200_ctx* ctx, const uint32_t* d_indices, uint64_t n_indices, uint32_t n_vertices,
+                  uint32_t segs, uint64_t& n_segments) {
+    if (d_indices) {
+        if (reinterpret_cast<uintptr_t>(d_indices) & 7u)
+            return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "indices must be 8-byte aligned");
+        n_segments = n_indices / 2;      // the reference loop `i < size()-1; i += 2` (hair_style.cc:311)
+    } else {
+        if (segs == 0) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "indices == NULL needs segs_per_strand > 0");
+        if (n_vertices % (segs + 1) != 0)
+            return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "n_vertices is not a multiple of segs_per_strand + 1");
+        n_segments = (uint64_t)(n_vertices / (segs + 1)) * segs;
+    }
+    return VKHR_B200_OK;
+}
+
+enum Strategy { COUNT32 = 0, PACKED8 = 1 };
+
+struct Job {                 // one instance, host side
+    const float* d_vertices;
+    const uint32_t* d_indices;
+    uint64_t n_segments;
+    uint32_t n_vertices;
+    uint32_t segs;
+    GridParams grid;
+    uint8_t* d_dens;
+};
+
+bool packed_ok(const Job& j) {
+    return (j.grid.n_voxels % 16u) == 0 && (reinterpret_cast<uintptr_t>(j.d_dens) & 15u) == 0;
+}
+
+int upload_table(vkhr_b200_ctx* ctx, cudaStream_t s) {
+    const size_t bytes = ctx->host_table.size() * sizeof(InstanceDev);
+    RET_IF(reserve(ctx, ctx->table, bytes));
+    // pageable source: the runtime stages it before returning, so host_table may be reused at once
+    CU_CHECK(ctx, cudaMemcpyAsync(ctx->table.p, ctx->host_table.data(), bytes, cudaMemcpyHostToDevice, s));
+    return VKHR_B200_OK;
+}
+
+// Fill host_table for `jobs`; returns the total number of walk tiles.
+uint32_t fill_table(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_mode) {
+    ctx->host_table.resize(n);
+    uint64_t tile = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        InstanceDev& I = ctx->host_table[k];
+        std::memset(&I, 0, sizeof I);
+        I.vertices = jobs[k].d_vertices;
+        I.indices = jobs[k].d_indices;
+        I.n_segments = jobs[k].n_segments;
+        I.n_vertices = jobs[k].n_vertices;
+        I.segs_per_strand = jobs[k].segs;
+        I.grid = jobs[k].grid;
+        I.densities = jobs[k].d_dens;
+        I.first_tile = (uint32_t)tile;
+        const uint64_t items = vertices_mode ? jobs[k].n_vertices : jobs[k].n_segments;
+        tile += (items + kWalkThreads - 1) / kWalkThreads;
+    }
+    return (uint32_t)tile;
+}
+
+template <bool VERTICES>
+int launch_repair(vkhr_b200_ctx* ctx, uint32_t n, uint32_t* scratch, cudaStream_t s) {
+    int& blocks = ctx->repair_blocks[VERTICES ? 1 : 0];
+    if (blocks == 0) {
+        int per_sm = 0;
+        CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_repair_packed<VERTICES>, kWalkThreads, 0));
+        if (per_sm < 1) return fail(ctx, VKHR_B200_ERR_CUDA, "repair kernel does not fit on an SM");
+        blocks = per_sm * ctx->sm_count;
+    }
+    const InstanceDev* table = static_cast<const InstanceDev*>(ctx->table.p);
+    void* args[] = {(void*)&table, (void*)&n, (void*)&scratch};
+    CU_CHECK(ctx, cudaLaunchCooperativeKernel((void*)k_repair_packed<VERTICES>, dim3(blocks), dim3(kWalkThreads), args, 0, s));
+    ctx->launches++;
+    return VKHR_B200_OK;
+}
+
+// The voxelisation of `n` instances at one resolution into their u8 grids.
+int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_mode, uint32_t flags, cudaStream_t s) {
+    if (n == 0) return VKHR_B200_OK;
+    const uint64_t nv = jobs[0].grid.n_voxels;
+    bool packed = true;
+    for (uint32_t k = 0; k < n; ++k) packed = packed && packed_ok(jobs[k]);
+    if (flags & VKHR_B200_STRATEGY_COUNT32) packed = false;
+    if ((flags & VKHR_B200_STRATEGY_PACKED8) && !packed)
+        return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "PACKED8 needs W*H*D % 16 == 0 and 16-byte aligned densities");
+
+    if (packed) {
+        // scratch: per-instance overflow bitmap + flag, one shared u32 recount grid
+        const size_t bm_words = ((nv / 4 + 31) / 32 + 3) & ~size_t(3);
+        RET_IF(reserve(ctx, ctx->bitmap, (size_t)n * (bm_words + 4) * 4));
+        RET_IF(reserve(ctx, ctx->counts, nv * 4));
+        ctx->counts_clean_bytes = 0;                   // the recount may leave entries behind
+        const uint32_t tiles = fill_table(ctx, jobs, n, vertices_mode);
+        uint32_t* base = static_cast<uint32_t*>(ctx->bitmap.p);
+        for (uint32_t k = 0; k < n; ++k) {
+            ctx->host_table[k].ovf_flag = base + (size_t)k * (bm_words + 4);
+            ctx->host_table[k].ovf_bitmap = base + (size_t)k * (bm_words + 4) + 4;
+            ctx->host_table[k].counts = static_cast<uint32_t*>(ctx->counts.p);
+        }
+        RET_IF(upload_table(ctx, s));
+        const InstanceDev* table = static_cast<const InstanceDev*>(ctx->table.p);
+        const unsigned gx = stride_blocks(ctx, nv / 16, 256, n >= 8 ? 2 : 8);
+        k_clear_packed_batch<<<dim3(gx, n), 256, 0, s>>>(table);
+        if (tiles) {
+            if (vertices_mode) k_splat_batch<1><<<tiles, kWalkThreads, 0, s>>>(table, n);
+            else               k_walk_batch<1><<<tiles, kWalkThreads, 0, s>>>(table, n);
+        }
+        ctx->launches += tiles ? 2 : 1;
+        CU_CHECK(ctx, cudaGetLastError());
+        if (tiles) {
+            if (vertices_mode) RET_IF(launch_repair<true>(ctx, n, static_cast<uint32_t*>(ctx->counts.p), s));
+            else               RET_IF(launch_repair<false>(ctx, n, static_cast<uint32_t*>(ctx->counts.p), s));
+        }
+    } else {
+        // COUNT32 in chunks of instances bounded by a 1 GiB scratch budget
+        const size_t per = nv * 4;
+        uint32_t chunk = (uint32_t)std::max<size_t>(1, (size_t(1) << 30) / per);
+        if (chunk > n) chunk = n;
+        const size_t need = per * chunk;
+        if (need > ctx->counts.cap) ctx->counts_clean_bytes = 0;
+        RET_IF(reserve(ctx, ctx->counts, need));
+        for (uint32_t first = 0; first < n; first += chunk) {
+            const uint32_t m = std::min(chunk, n - first);
+            if (ctx->counts_clean_bytes < per * m) {
+                CU_CHECK(ctx, cudaMemsetAsync(ctx->counts.p, 0, per * m, s));
+                ctx->counts_clean_bytes = 0;           // until the ZERO clamp below has run
+            }
+            const uint32_t tiles = fill_table(ctx, jobs + first, m, vertices_mode);
+            for (uint32_t k = 0; k < m; ++k)
+                ctx->host_table[k].counts = static_cast<uint32_t*>(ctx->counts.p) + (size_t)k * nv;
+            RET_IF(upload_table(ctx, s));
+            const InstanceDev* table = static_cast<const InstanceDev*>(ctx->table.p);
+            if (tiles) {
+                if (vertices_mode) k_splat_batch<0><<<tiles, kWalkThreads, 0, s>>>(table, m);
+                else               k_walk_batch<0><<<tiles, kWalkThreads, 0, s>>>(table, m);
+                ctx->launches++;
+            }
+            for (uint32_t k = 0; k < m; ++k) {
+                k_clamp_counts<true><<<stride_blocks(ctx, nv / 16 + 1, 256, 8), 256, 0, s>>>(
+                    static_cast<uint32_t*>(ctx->counts.p) + (size_t)k * nv, nv, jobs[first + k].d_dens);
+                ctx->launches++;
+            }
+            CU_CHECK(ctx, cudaGetLastError());
+            ctx->counts_clean_bytes = std::max(ctx->counts_clean_bytes, per * m);   // ZERO clamp restored the invariant
+        }
+    }
+    if (flags & VKHR_B200_NORMALIZE)
+        for (uint32_t k = 0; k < n; ++k) RET_IF(vkhr_b200_normalize_dev(ctx, jobs[k].d_dens, nv, s));
+    return VKHR_B200_OK;
+}
+
+int stage_in(vkhr_b200_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
+    RET_IF(reserve(ctx, b, bytes ? bytes : 16));
+    if (bytes) CU_CHECK(ctx, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return VKHR_B200_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// exported functions
+// ---------------------------------------------------------------------------
+extern "C" {
+
+const char* vkhr_b200_version(void) { return "vkhr_b200 0.1.0 (sm_100a)"; }
+
+int vkhr_b200_create(int device, vkhr_b200_ctx** out) {
+    if (!out) return fail(nullptr, VKHR_B200_ERR_INVALID_ARGUMENT, "null out pointer");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        (void)cudaGetLastError();
+        return fail(nullptr, VKHR_B200_ERR_NO_DEVICE,
+                    std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                        " (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= count) return fail(nullptr, VKHR_B200_ERR_INVALID_ARGUMENT, "device index out of range");
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+        return fail(nullptr, VKHR_B200_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return fail(nullptr, VKHR_B200_ERR_NO_DEVICE,
+                    std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                        "; this library carries sm_100a code only");
+    vkhr_b200_ctx* ctx = new vkhr_b200_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaSetDevice(device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, VKHR_B200_ERR_CUDA, "cannot create a stream on the device");
+    }
+    if (reserve(ctx, ctx->small, 256) != VKHR_B200_OK) {
+        g_create_error = ctx->err;
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return VKHR_B200_ERR_OUT_OF_MEMORY;
+    }
+    *out = ctx;
+    return VKHR_B200_OK;
+}
+
+void vkhr_b200_destroy(vkhr_b200_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = {&ctx->counts, &ctx->bitmap, &ctx->table, &ctx->small, &ctx->st_vertices,
+                      &ctx->st_indices, &ctx->st_tangents, &ctx->st_dens, &ctx->st_tang_out};
+    for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* vkhr_b200_last_error(const vkhr_b200_ctx* ctx) {
+    return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+void* vkhr_b200_stream(vkhr_b200_ctx* ctx) { return ctx ? ctx->stream : nullptr; }
+
+int vkhr_b200_synchronize(vkhr_b200_ctx* ctx) {
+    RET_IF(bind(ctx));
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return VKHR_B200_OK;
+}
+
+uint64_t vkhr_b200_launch_count(const vkhr_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- device-pointer API -----------------------------------------------------
+int vkhr_b200_voxelize_segments_dev(vkhr_b200_ctx* ctx, const float* d_vertices, uint32_t n_vertices,
+                                    const uint32_t* d_indices, uint64_t n_indices, uint32_t segs_per_strand,
+                                    const float* d_tangents_in, const float aabb_origin[3], const float aabb_size[3],
+                                    uint32_t W, uint32_t H, uint32_t D, uint32_t flags,
+                                    uint8_t* d_densities_out, int8_t* d_tangents_out, void* stream) {
+    RET_IF(bind(ctx));
+    if (!d_vertices || !d_densities_out) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null vertices or densities");
+    if (d_tangents_out || d_tangents_in)
+        return fail(ctx, VKHR_B200_ERR_UNSUPPORTED, "tangent volume not built yet (density only)");
+    Job j{};
+    RET_IF(make_grid(ctx, aabb_origin, aabb_size, W, H, D, flags, j.grid));
+    RET_IF(segment_count(ctx, d_indices, n_indices, n_vertices, segs_per_strand, j.n_segments));
+    j.d_vertices = d_vertices; j.d_indices = d_indices; j.n_vertices = n_vertices;
+    j.segs = segs_per_strand; j.d_dens = d_densities_out;
+    return run_voxelize(ctx, &j, 1, false, flags, pick(ctx, stream));
+}
+
+int vkhr_b200_voxelize_vertices_dev(vkhr_b200_ctx* ctx, const float* d_vertices, uint32_t n_vertices,
+                                    const float* d_tangents_in, const float aabb_origin[3], const float aabb_size[3],
+                                    uint32_t W, uint32_t H, uint32_t D, uint32_t flags,
+                                    uint8_t* d_densities_out, int8_t* d_tangents_out, void* stream) {
+    RET_IF(bind(ctx));
+    if (!d_vertices || !d_densities_out) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null vertices or densities");
+    if (d_tangents_out || d_tangents_in)
+        return fail(ctx, VKHR_B200_ERR_UNSUPPORTED, "tangent volume not built yet (density only)");
+    Job j{};
+    RET_IF(make_grid(ctx, aabb_origin, aabb_size, W, H, D, flags, j.grid));
+    j.d_vertices = d_vertices; j.n_vertices = n_vertices; j.d_dens = d_densities_out;
+    return run_voxelize(ctx, &j, 1, true, flags, pick(ctx, stream));
+}
+
+int vkhr_b200_voxelize_segments_batch_dev(vkhr_b200_ctx* ctx, const vkhr_b200_instance* instances, uint32_t n,
+                                          uint32_t W, uint32_t H, uint32_t D, uint32_t flags, void* stream) {
+    RET_IF(bind(ctx));
+    if (n == 0) return VKHR_B200_OK;
+    if (!instances) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null instance array");
+    std::vector<Job> jobs(n);
+    for (uint32_t k = 0; k < n; ++k) {
+        const vkhr_b200_instance& in = instances[k];
+        if (!in.d_vertices || !in.d_densities_out)
+            return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "instance " + std::to_string(k) + ": null vertices or densities");
+        Job& j = jobs[k];
+        RET_IF(make_grid(ctx, in.aabb_origin, in.aabb_size, W, H, D, flags, j.grid));
+        RET_IF(segment_count(ctx, in.d_indices, in.n_indices, in.n_vertices, in.segs_per_strand, j.n_segments));
+        j.d_vertices = in.d_vertices; j.d_indices = in.d_indices; j.n_vertices = in.n_vertices;
+        j.segs = in.segs_per_strand; j.d_dens = in.d_densities_out;
+    }
+    return run_voxelize(ctx, jobs.data(), n, false, flags, pick(ctx, stream));
+}
+
+// ---- multi-GPU building blocks -----------------------------------------------
+int vkhr_b200_count_segments_dev(vkhr_b200_ctx* ctx, const float* d_vertices, uint32_t n_vertices,
+                                 const uint32_t* d_indices, uint64_t n_indices, uint32_t segs_per_strand,
+                                 const float aabb_origin[3], const float aabb_size[3],
+                                 uint32_t W, uint32_t H, uint32_t D, uint32_t flags,
+                                 uint32_t* d_counts_inout, void* stream) {
+    RET_IF(bind(ctx));
+    if (!d_counts_inout) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null counts");
+    if (n_vertices == 0) return VKHR_B200_OK;
+    if (!d_vertices) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null vertices");
+    Job j{};
+    RET_IF(make_grid(ctx, aabb_origin, aabb_size, W, H, D, flags, j.grid));
+    RET_IF(segment_count(ctx, d_indices, n_indices, n_vertices, segs_per_strand, j.n_segments));
+    j.d_vertices = d_vertices; j.d_indices = d_indices; j.n_vertices = n_vertices; j.segs = segs_per_strand;
+    cudaStream_t s = pick(ctx, stream);
+    const uint32_t tiles = fill_table(ctx, &j, 1, false);
+    if (!tiles) return VKHR_B200_OK;
+    ctx->host_table[0].counts = d_counts_inout;
+    RET_IF(upload_table(ctx, s));
+    k_walk_batch<0><<<tiles, kWalkThreads, 0, s>>>(static_cast<const InstanceDev*>(ctx->table.p), 1);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return VKHR_B200_OK;
+}
+
+int vkhr_b200_count_vertices_dev(vkhr_b200_ctx* ctx, const float* d_vertices, uint32_t n_vertices,
+                                 const float aabb_origin[3], const float aabb_size[3],
+                                 uint32_t W, uint32_t H, uint32_t D, uint32_t flags,
+                                 uint32_t* d_counts_inout, void* stream) {
+    RET_IF(bind(ctx));
+    if (!d_counts_inout) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null counts");
+    if (n_vertices == 0) return VKHR_B200_OK;
+    if (!d_vertices) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null vertices");
+    Job j{};
+    RET_IF(make_grid(ctx, aabb_origin, aabb_size, W, H, D, flags, j.grid));
+    j.d_vertices = d_vertices; j.n_vertices = n_vertices;
+    cudaStream_t s = pick(ctx, stream);
+    const uint32_t tiles = fill_table(ctx, &j, 1, true);
+    ctx->host_table[0].counts = d_counts_inout;
+    RET_IF(upload_table(ctx, s));
+    k_splat_batch<0><<<tiles, kWalkThreads, 0, s>>>(static_cast<const InstanceDev*>(ctx->table.p), 1);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return VKHR_B200_OK;
+}
+
+int vkhr_b200_clamp_counts_dev(vkhr_b200_ctx* ctx, const uint32_t* d_counts, uint64_t n_voxels, uint32_t flags,
+                               uint8_t* d_densities_out, void* stream) {
+    RET_IF(bind(ctx));
+    if (!d_counts || !d_densities_out) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null pointer");
+    if ((reinterpret_cast<uintptr_t>(d_counts) & 15u) || (reinterpret_cast<uintptr_t>(d_densities_out) & 15u))
+        return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "counts and densities must be 16-byte aligned");
+    cudaStream_t s = pick(ctx, stream);
+    k_clamp_counts<false><<<stride_blocks(ctx, n_voxels / 16 + 1, 256, 8), 256, 0, s>>>(
+        const_cast<uint32_t*>(d_counts), n_voxels, d_densities_out);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    if (flags & VKHR_B200_NORMALIZE) RET_IF(vkhr_b200_normalize_dev(ctx, d_densities_out, n_voxels, s));
+    return VKHR_B200_OK;
+}
+
+// ---- Volume operations ---------------------------------------------------------
+int vkhr_b200_normalize_dev(vkhr_b200_ctx* ctx, uint8_t* d_densities, uint64_t n_voxels, void* stream) {
+    RET_IF(bind(ctx));
+    if (!d_densities) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null densities");
+    if (reinterpret_cast<uintptr_t>(d_densities) & 15u)
+        return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "densities must be 16-byte aligned");
+    if (n_voxels == 0) return VKHR_B200_OK;
+    cudaStream_t s = pick(ctx, stream);
+    uint32_t* lohi = static_cast<uint32_t*>(ctx->small.p);
+    const unsigned g = stride_blocks(ctx, n_voxels / 16 + 1, 256, 8);
+    k_minmax_init<<<1, 32, 0, s>>>(lohi);
+    k_minmax_u8<<<g, 256, 0, s>>>(d_densities, n_voxels, lohi);
+    k_normalize_apply<<<g, 256, 0, s>>>(d_densities, n_voxels, lohi);
+    ctx->launches += 3;
+    CU_CHECK(ctx, cudaGetLastError());
+    return VKHR_B200_OK;
+}
+
+int vkhr_b200_downsample_dev(vkhr_b200_ctx* ctx, const uint8_t* d_densities, uint32_t W, uint32_t H, uint32_t D,
+                             int filter, uint8_t* d_out, void* stream) {
+    RET_IF(bind(ctx));
+    if (!d_densities || !d_out) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null pointer");
+    if (filter < 0 || filter > 3) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "unknown downsample filter");
+    const uint32_t w = W / 2, h = H / 2, d = D / 2;
+    const uint64_t n = (uint64_t)w * h * d;
+    if (n == 0) return VKHR_B200_OK;
+    cudaStream_t s = pick(ctx, stream);
+    k_downsample<<<stride_blocks(ctx, n, 256, 16), 256, 0, s>>>(d_densities, W, H, w, h, d, filter, d_out);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return VKHR_B200_OK;
+}
+
+int vkhr_b200_generate_bounding_box_dev(vkhr_b200_ctx* ctx, const float* d_vertices, uint32_t n_vertices,
+                                        float* d_aabb_out, void* stream) {
+    RET_IF(bind(ctx));
+    if (!d_aabb_out || (n_vertices && !d_vertices)) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null pointer");
+    cudaStream_t s = pick(ctx, stream);
+    uint32_t* keys = static_cast<uint32_t*>(ctx->small.p) + 8;
+    k_aabb_init<<<1, 32, 0, s>>>(keys);
+    ctx->launches++;
+    if (n_vertices) {
+        k_aabb_reduce<<<stride_blocks(ctx, 3ull * n_vertices, 768, 8), 256, 0, s>>>(d_vertices, n_vertices, keys);
+        ctx->launches++;
+    }
+    k_aabb_decode<<<1, 32, 0, s>>>(keys, d_aabb_out);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return VKHR_B200_OK;
+}
+
+// ---- host-pointer API ------------------------------------------------------------
+int vkhr_b200_voxelize_segments(vkhr_b200_ctx* ctx, const float* vertices, uint32_t n_vertices,
+                                const uint32_t* indices, uint64_t n_indices, uint32_t segs_per_strand,
+                                const float* tangents_in, const float aabb_origin[3], const float aabb_size[3],
+                                uint32_t W, uint32_t H, uint32_t D, uint32_t flags,
+                                uint8_t* densities_out, int8_t* tangents_out) {
+    RET_IF(bind(ctx));
+    if (!densities_out || (n_vertices && !vertices)) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null vertices or densities");
+    if (tangents_out || tangents_in)
+        return fail(ctx, VKHR_B200_ERR_UNSUPPORTED, "tangent volume not built yet (density only)");
+    GridParams g;
+    RET_IF(make_grid(ctx, aabb_origin, aabb_size, W, H, D, flags, g));
+    const size_t nv = g.n_voxels;
+    RET_IF(reserve(ctx, ctx->st_dens, nv));
+    // fewer than two indices: the reference underflows size()-1; defined here as an empty volume
+    const bool empty = n_vertices == 0 || (indices && n_indices < 2);
+    if (empty) {
+        CU_CHECK(ctx, cudaMemsetAsync(ctx->st_dens.p, 0, nv, ctx->stream));
+    } else {
+        RET_IF(stage_in(ctx, ctx->st_vertices, vertices, (size_t)n_vertices * 12));
+        if (indices) RET_IF(stage_in(ctx, ctx->st_indices, indices, (size_t)(n_indices / 2) * 8));
+        RET_IF(vkhr_b200_voxelize_segments_dev(ctx, static_cast<const float*>(ctx->st_vertices.p), n_vertices,
+                                               indices ? static_cast<const uint32_t*>(ctx->st_indices.p) : nullptr,
+                                               n_indices, segs_per_strand, nullptr, aabb_origin, aabb_size,
+                                               W, H, D, flags, static_cast<uint8_t*>(ctx->st_dens.p), nullptr, ctx->stream));
+    }
+    CU_CHECK(ctx, cudaMemcpyAsync(densities_out, ctx->st_dens.p, nv, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return VKHR_B200_OK;
+}
+
+int vkhr_b200_voxelize_vertices(vkhr_b200_ctx* ctx, const float* vertices, uint32_t n_vertices,
+                                const float* tangents_in, const float aabb_origin[3], const float aabb_size[3],
+                                uint32_t W, uint32_t H, uint32_t D, uint32_t flags,
+                                uint8_t* densities_out, int8_t* tangents_out) {
+    RET_IF(bind(ctx));
+    if (!densities_out || (n_vertices && !vertices)) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null vertices or densities");
+    if (tangents_out || tangents_in)
+        return fail(ctx, VKHR_B200_ERR_UNSUPPORTED, "tangent volume not built yet (density only)");
+    GridParams g;
+    RET_IF(make_grid(ctx, aabb_origin, aabb_size, W, H, D, flags, g));
+    const size_t nv = g.n_voxels;
+    RET_IF(reserve(ctx, ctx->st_dens, nv));
+    if (n_vertices == 0) {
+        CU_CHECK(ctx, cudaMemsetAsync(ctx->st_dens.p, 0, nv, ctx->stream));
+    } else {
+        RET_IF(stage_in(ctx, ctx->st_vertices, vertices, (size_t)n_vertices * 12));
+        RET_IF(vkhr_b200_voxelize_vertices_dev(ctx, static_cast<const float*>(ctx->st_vertices.p), n_vertices, nullptr,
+                                               aabb_origin, aabb_size, W, H, D, flags,
+                                               static_cast<uint8_t*>(ctx->st_dens.p), nullptr, ctx->stream));
+    }
+    CU_CHECK(ctx, cudaMemcpyAsync(densities_out, ctx->st_dens.p, nv, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return VKHR_B200_OK;
+}
+
+int vkhr_b200_normalize(vkhr_b200_ctx* ctx, uint8_t* densities, uint64_t n_voxels) {
+    RET_IF(bind(ctx));
+    if (!densities) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null densities");
+    if (n_voxels == 0) return VKHR_B200_OK;
+    RET_IF(stage_in(ctx, ctx->st_dens, densities, n_voxels));
+    RET_IF(vkhr_b200_normalize_dev(ctx, static_cast<uint8_t*>(ctx->st_dens.p), n_voxels, ctx->stream));
+    CU_CHECK(ctx, cudaMemcpyAsync(densities, ctx->st_dens.p, n_voxels, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return VKHR_B200_OK;
+}
+
+int vkhr_b200_downsample(vkhr_b200_ctx* ctx, const uint8_t* densities, uint32_t W, uint32_t H, uint32_t D,
+                         int filter, uint8_t* out) {
+    RET_IF(bind(ctx));
+    if (!densities || !out) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null pointer");
+    const size_t n_in = (size_t)W * H * D, n_out = (size_t)(W / 2) * (H / 2) * (D / 2);
+    if (n_out == 0) return VKHR_B200_OK;
+    RET_IF(stage_in(ctx, ctx->st_dens, densities, n_in));
+    RET_IF(reserve(ctx, ctx->st_tang_out, n_out));
+    RET_IF(vkhr_b200_downsample_dev(ctx, static_cast<const uint8_t*>(ctx->st_dens.p), W, H, D, filter,
+                                    static_cast<uint8_t*>(ctx->st_tang_out.p), ctx->stream));
+    CU_CHECK(ctx, cudaMemcpyAsync(out, ctx->st_tang_out.p, n_out, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return VKHR_B200_OK;
+}
+
+int vkhr_b200_generate_bounding_box(vkhr_b200_ctx* ctx, const float* vertices, uint32_t n_vertices, float aabb_out[6]) {
+    RET_IF(bind(ctx));
+    if (!aabb_out || (n_vertices && !vertices)) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null pointer");
+    RET_IF(stage_in(ctx, ctx->st_vertices, vertices, (size_t)n_vertices * 12));
+    float* d_out = reinterpret_cast<float*>(static_cast<uint32_t*>(ctx->small.p) + 16);
+    RET_IF(vkhr_b200_generate_bounding_box_dev(ctx, static_cast<const float*>(ctx->st_vertices.p), n_vertices, d_out, ctx->stream));
+    CU_CHECK(ctx, cudaMemcpyAsync(aabb_out, d_out, 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return VKHR_B200_OK;
+}
+
+// ---- device memory helpers --------------------------------------------------------
+int vkhr_b200_malloc(vkhr_b200_ctx* ctx, size_t bytes, void** d_ptr) {
+    RET_IF(bind(ctx));
+    if (!d_ptr) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null out pointer");
+    CU_CHECK(ctx, cudaMalloc(d_ptr, bytes ? bytes : 16));
+    return VKHR_B200_OK;
+}
+int vkhr_b200_free(vkhr_b200_ctx* ctx, void* d_ptr) {
+    RET_IF(bind(ctx));
+    CU_CHECK(ctx, cudaFree(d_ptr));
+    return VKHR_B200_OK;
+}
+int vkhr_b200_memset(vkhr_b200_ctx* ctx, void* d_ptr, int value, size_t bytes, void* stream) {
+    RET_IF(bind(ctx));
+    CU_CHECK(ctx, cudaMemsetAsync(d_ptr, value, bytes, pick(ctx, stream)));
+    return VKHR_B200_OK;
+}
+int vkhr_b200_upload(vkhr_b200_ctx* ctx, void* d_dst, const void* src, size_t bytes, void* stream) {
+    RET_IF(bind(ctx));
+    CU_CHECK(ctx, cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, pick(ctx, stream)));
+    return VKHR_B200_OK;
+}
+int vkhr_b200_download(vkhr_b200_ctx* ctx, void* dst, const void* d_src, size_t bytes, void* stream) {
+    RET_IF(bind(ctx));
+    CU_CHECK(ctx, cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, pick(ctx, stream)));
+    return VKHR_B200_OK;
+}
+
+}  // extern "C"

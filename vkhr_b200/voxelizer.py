@@ -1,0 +1,280 @@
+"""``Voxelizer`` -- one native context (one GPU + one stream) behind the C ABI.
+
+Host-pointer methods take numpy arrays and are synchronous; ``*_dev`` methods
+take torch CUDA tensors (torch is used for device memory and streams only),
+enqueue on torch's current stream and do not synchronise.  All compute happens
+in libvkhr_b200.so; nothing here touches voxels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import capi
+from .capi import lib
+
+
+def _np(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class Voxelizer:
+    def __init__(self, device: int = 0):
+        h = capi.c_ctx()
+        rc = lib.vkhr_b200_create(int(device), C.byref(h))
+        if rc != capi.OK:
+            raise capi.VkhrB200Error(rc, capi.last_error(None))
+        self._h = h
+        self.device = int(device)
+
+    # ---- lifetime ---------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib.vkhr_b200_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib.vkhr_b200_launch_count(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(lib.vkhr_b200_stream(self._h) or 0)
+
+    def synchronize(self) -> None:
+        capi.check(self._h, lib.vkhr_b200_synchronize(self._h))
+
+    @staticmethod
+    def version() -> str:
+        return lib.vkhr_b200_version().decode()
+
+    # ---- host-pointer API (numpy) ------------------------------------------
+    def voxelize_segments(self, vertices, indices, aabb_origin, aabb_size, W, H, D,
+                          segs_per_strand: int = 0, flags: int = 0) -> np.ndarray:
+        """Replaces ``HairStyle::voxelize_segments`` (reference hair_style.cc:296-342); returns W*H*D uint8."""
+        v = _np(vertices, np.float32).reshape(-1, 3)
+        idx = None if indices is None else _np(indices, np.uint32).reshape(-1)
+        out = np.empty(int(W) * int(H) * int(D), dtype=np.uint8)
+        rc = lib.vkhr_b200_voxelize_segments(self._h, _p(v), v.shape[0], _p(idx),
+                                             0 if idx is None else idx.size, int(segs_per_strand), None,
+                                             capi.vec3(aabb_origin), capi.vec3(aabb_size),
+                                             int(W), int(H), int(D), int(flags), _p(out), None)
+        capi.check(self._h, rc)
+        return out
+
+    def voxelize_vertices(self, vertices, aabb_origin, aabb_size, W, H, D, flags: int = 0) -> np.ndarray:
+        """Replaces ``HairStyle::voxelize_vertices`` (reference hair_style.cc:257-294)."""
+        v = _np(vertices, np.float32).reshape(-1, 3)
+        out = np.empty(int(W) * int(H) * int(D), dtype=np.uint8)
+        rc = lib.vkhr_b200_voxelize_vertices(self._h, _p(v), v.shape[0], None,
+                                             capi.vec3(aabb_origin), capi.vec3(aabb_size),
+                                             int(W), int(H), int(D), int(flags), _p(out), None)
+        capi.check(self._h, rc)
+        return out
+
+    def normalize(self, densities) -> np.ndarray:
+        """``Volume::normalize`` (reference hair_style.cc:344-357) on a host grid; returns a new array."""
+        d = np.array(densities, dtype=np.uint8, copy=True).reshape(-1)
+        capi.check(self._h, lib.vkhr_b200_normalize(self._h, _p(d), d.size))
+        return d
+
+    def downsample(self, densities, W, H, D, filter: int = capi.DOWNSAMPLE_MAX) -> np.ndarray:
+        """``Volume::downsample`` (reference hair_style.hh:228-257)."""
+        d = _np(densities, np.uint8).reshape(-1)
+        if d.size != W * H * D:
+            raise ValueError("densities does not match W*H*D")
+        out = np.empty((W // 2) * (H // 2) * (D // 2), dtype=np.uint8)
+        capi.check(self._h, lib.vkhr_b200_downsample(self._h, _p(d), int(W), int(H), int(D), int(filter), _p(out)))
+        return out
+
+    def generate_bounding_box(self, vertices) -> tuple[np.ndarray, np.ndarray]:
+        """``HairStyle::generate_bounding_box`` (reference hair_style.cc:215-234): (min, max) folded from (0,0,0)."""
+        v = _np(vertices, np.float32).reshape(-1, 3)
+        out = (C.c_float * 6)()
+        capi.check(self._h, lib.vkhr_b200_generate_bounding_box(self._h, _p(v), v.shape[0], out))
+        a = np.array(out, dtype=np.float32)
+        return a[:3].copy(), a[3:].copy()
+
+    # ---- device-pointer API (torch CUDA tensors) ----------------------------
+    def _torch_stream(self, stream):
+        import torch
+        if stream is None:
+            return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return C.c_void_p(int(stream))
+
+    def _check_dev(self, t, dtype, name):
+        import torch
+        if not isinstance(t, torch.Tensor) or not t.is_cuda or t.device.index != self.device:
+            raise ValueError(f"{name} must be a CUDA tensor on cuda:{self.device}")
+        if t.dtype != dtype or not t.is_contiguous():
+            raise ValueError(f"{name} must be contiguous {dtype}")
+
+    def voxelize_segments_dev(self, vertices, indices, aabb_origin, aabb_size, W, H, D,
+                              segs_per_strand: int = 0, flags: int = 0, out=None, stream=None):
+        import torch
+        self._check_dev(vertices, torch.float32, "vertices")
+        if indices is not None:
+            self._check_dev(indices, torch.int32, "indices")
+        n = int(W) * int(H) * int(D)
+        if out is None:
+            out = torch.empty(n, dtype=torch.uint8, device=vertices.device)
+        self._check_dev(out, torch.uint8, "out")
+        rc = lib.vkhr_b200_voxelize_segments_dev(
+            self._h, C.c_void_p(vertices.data_ptr()), vertices.numel() // 3,
+            None if indices is None else C.c_void_p(indices.data_ptr()),
+            0 if indices is None else indices.numel(), int(segs_per_strand), None,
+            capi.vec3(aabb_origin), capi.vec3(aabb_size), int(W), int(H), int(D), int(flags),
+            C.c_void_p(out.data_ptr()), None, self._torch_stream(stream))
+        capi.check(self._h, rc)
+        return out
+
+    def voxelize_vertices_dev(self, vertices, aabb_origin, aabb_size, W, H, D, flags: int = 0, out=None, stream=None):
+        import torch
+        self._check_dev(vertices, torch.float32, "vertices")
+        n = int(W) * int(H) * int(D)
+        if out is None:
+            out = torch.empty(n, dtype=torch.uint8, device=vertices.device)
+        self._check_dev(out, torch.uint8, "out")
+        rc = lib.vkhr_b200_voxelize_vertices_dev(
+            self._h, C.c_void_p(vertices.data_ptr()), vertices.numel() // 3, None,
+            capi.vec3(aabb_origin), capi.vec3(aabb_size), int(W), int(H), int(D), int(flags),
+            C.c_void_p(out.data_ptr()), None, self._torch_stream(stream))
+        capi.check(self._h, rc)
+        return out
+
+    def make_batch(self, instances: Sequence[dict]):
+        """Build the ``vkhr_b200_instance[]`` array once (per-frame calls then reuse it).
+
+        Each dict: vertices (cuda f32), out (cuda u8), aabb_origin, aabb_size,
+        and either indices (cuda i32) or segs_per_strand.
+        """
+        import torch
+        arr = (capi.Instance * len(instances))()
+        keep = []
+        for k, ins in enumerate(instances):
+            v, o = ins["vertices"], ins["out"]
+            self._check_dev(v, torch.float32, "vertices")
+            self._check_dev(o, torch.uint8, "out")
+            idx = ins.get("indices")
+            if idx is not None:
+                self._check_dev(idx, torch.int32, "indices")
+            arr[k].d_vertices = v.data_ptr()
+            arr[k].d_indices = None if idx is None else idx.data_ptr()
+            arr[k].n_indices = 0 if idx is None else idx.numel()
+            arr[k].n_vertices = v.numel() // 3
+            arr[k].segs_per_strand = int(ins.get("segs_per_strand", 0))
+            arr[k].aabb_origin = capi.vec3(ins["aabb_origin"])
+            arr[k].aabb_size = capi.vec3(ins["aabb_size"])
+            arr[k].d_densities_out = o.data_ptr()
+            keep.append((v, o, idx))
+        return arr, keep
+
+    def voxelize_segments_batch_dev(self, batch, W, H, D, flags: int = 0, stream=None) -> None:
+        """``voxelize_segments`` for a crowd: ``batch`` from :meth:`make_batch` (or a list of dicts)."""
+        if isinstance(batch, (list, tuple)) and batch and isinstance(batch[0], dict):
+            batch = self.make_batch(batch)
+        arr = batch[0] if isinstance(batch, tuple) else batch
+        rc = lib.vkhr_b200_voxelize_segments_batch_dev(self._h, arr, len(arr), int(W), int(H), int(D),
+                                                       int(flags), self._torch_stream(stream))
+        capi.check(self._h, rc)
+
+    def count_segments_dev(self, vertices, indices, aabb_origin, aabb_size, W, H, D, counts,
+                           segs_per_strand: int = 0, flags: int = 0, stream=None):
+        """ADD this shard's hits into ``counts`` (cuda int32, W*H*D) -- the multi-GPU partial."""
+        import torch
+        self._check_dev(vertices, torch.float32, "vertices")
+        self._check_dev(counts, torch.int32, "counts")
+        if indices is not None:
+            self._check_dev(indices, torch.int32, "indices")
+        if counts.numel() != int(W) * int(H) * int(D):
+            raise ValueError("counts does not match W*H*D")
+        rc = lib.vkhr_b200_count_segments_dev(
+            self._h, C.c_void_p(vertices.data_ptr()), vertices.numel() // 3,
+            None if indices is None else C.c_void_p(indices.data_ptr()),
+            0 if indices is None else indices.numel(), int(segs_per_strand),
+            capi.vec3(aabb_origin), capi.vec3(aabb_size), int(W), int(H), int(D), int(flags),
+            C.c_void_p(counts.data_ptr()), self._torch_stream(stream))
+        capi.check(self._h, rc)
+        return counts
+
+    def count_vertices_dev(self, vertices, aabb_origin, aabb_size, W, H, D, counts, flags: int = 0, stream=None):
+        import torch
+        self._check_dev(vertices, torch.float32, "vertices")
+        self._check_dev(counts, torch.int32, "counts")
+        rc = lib.vkhr_b200_count_vertices_dev(
+            self._h, C.c_void_p(vertices.data_ptr()), vertices.numel() // 3,
+            capi.vec3(aabb_origin), capi.vec3(aabb_size), int(W), int(H), int(D), int(flags),
+            C.c_void_p(counts.data_ptr()), self._torch_stream(stream))
+        capi.check(self._h, rc)
+        return counts
+
+    def clamp_counts_dev(self, counts, flags: int = 0, out=None, stream=None):
+        """densities = min(counts, 255) [+ normalize]."""
+        import torch
+        self._check_dev(counts, torch.int32, "counts")
+        if out is None:
+            out = torch.empty(counts.numel(), dtype=torch.uint8, device=counts.device)
+        self._check_dev(out, torch.uint8, "out")
+        rc = lib.vkhr_b200_clamp_counts_dev(self._h, C.c_void_p(counts.data_ptr()), counts.numel(), int(flags),
+                                            C.c_void_p(out.data_ptr()), self._torch_stream(stream))
+        capi.check(self._h, rc)
+        return out
+
+    def normalize_dev(self, densities, stream=None):
+        import torch
+        self._check_dev(densities, torch.uint8, "densities")
+        capi.check(self._h, lib.vkhr_b200_normalize_dev(self._h, C.c_void_p(densities.data_ptr()),
+                                                        densities.numel(), self._torch_stream(stream)))
+        return densities
+
+    def downsample_dev(self, densities, W, H, D, filter: int = capi.DOWNSAMPLE_MAX, out=None, stream=None):
+        import torch
+        self._check_dev(densities, torch.uint8, "densities")
+        if out is None:
+            out = torch.empty((W // 2) * (H // 2) * (D // 2), dtype=torch.uint8, device=densities.device)
+        capi.check(self._h, lib.vkhr_b200_downsample_dev(self._h, C.c_void_p(densities.data_ptr()), int(W), int(H), int(D),
+                                                         int(filter), C.c_void_p(out.data_ptr()), self._torch_stream(stream)))
+        return out
+
+    def generate_bounding_box_dev(self, vertices, out=None, stream=None):
+        import torch
+        self._check_dev(vertices, torch.float32, "vertices")
+        if out is None:
+            out = torch.empty(6, dtype=torch.float32, device=vertices.device)
+        capi.check(self._h, lib.vkhr_b200_generate_bounding_box_dev(self._h, C.c_void_p(vertices.data_ptr()),
+                                                                    vertices.numel() // 3, C.c_void_p(out.data_ptr()),
+                                                                    self._torch_stream(stream)))
+        return out
+
+
+_default: dict[int, Voxelizer] = {}
+
+
+def default_voxelizer(device: int = 0) -> Voxelizer:
+    """Process-wide context per device (what ``HairStyle.voxelize_*`` uses)."""
+    v = _default.get(device)
+    if v is None or v.handle is None:
+        v = _default[device] = Voxelizer(device)
+    return v
