@@ -93,6 +93,14 @@ VKHR_B200_API int vkhr_b200_synchronize(vkhr_b200_ctx* ctx);
 /* Number of kernels this context has launched so far. */
 VKHR_B200_API uint64_t vkhr_b200_launch_count(const vkhr_b200_ctx* ctx);
 
+/* Per-phase device timing.  While enabled, every voxelize call records CUDA
+ * events on its launching stream around its phases; profile_read waits for
+ * them and returns, since the previous read, the summed milliseconds and the
+ * number of spans of: [0] grid clear, [1] strand walk (the dominant kernel),
+ * [2] finish (overflow repair or u32->u8 clamp), [3] normalize. */
+VKHR_B200_API int vkhr_b200_profile_enable(vkhr_b200_ctx* ctx, int enable);
+VKHR_B200_API int vkhr_b200_profile_read(vkhr_b200_ctx* ctx, double ms_out[4], uint32_t spans_out[4]);
+
 /* ---- host-pointer API: replaces HairStyle::voxelize_segments ----------
  * (hair_style.hh:104, hair_style.cc:296-342).
  * indices == NULL with segs_per_strand > 0 means uniform strands: the implicit

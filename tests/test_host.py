@@ -1,0 +1,147 @@
+"""Host logic and the C-ABI boundary, without a GPU: symbol export, struct layout, .hair I/O,
+the generators of the HairStyle mirror, and loud failure when no device is present."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import vkhr_b200
+from vkhr_b200 import HairStyle, capi, synth
+
+
+def test_library_exports_every_declared_symbol():
+    names = capi.header_symbols()
+    assert len(names) >= 28
+    out = subprocess.check_output(["nm", "-D", "--defined-only", capi.LIB_PATH], text=True)
+    exported = {line.split()[-1] for line in out.splitlines() if line.strip()}
+    missing = [n for n in names if n not in exported]
+    assert not missing, f"declared in include/vkhr_b200.h but not exported: {missing}"
+    for n in names:
+        assert n in capi._PROTOTYPES, f"{n} has no ctypes prototype"
+        getattr(capi.lib, n)
+    # nothing but the C ABI leaks out of the shared object
+    leaked = [e for e in exported if not e.startswith("vkhr_b200_") and not e.startswith("_")]
+    assert not leaked, leaked
+
+
+def test_library_is_sm100a_and_links_no_oracle():
+    sass = subprocess.run(["cuobjdump", "-lelf", capi.LIB_PATH], capture_output=True, text=True)
+    if sass.returncode == 0:
+        assert "sm_100a" in sass.stdout
+    deps = subprocess.check_output(["ldd", capi.LIB_PATH], text=True)
+    assert "oracle" not in deps and "vkhr_ref" not in deps
+
+
+def test_no_product_file_touches_the_oracle():
+    root = os.path.dirname(os.path.abspath(vkhr_b200.__file__))
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cc", ".h")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "import oracle" not in text and "from oracle" not in text and "oracle/" not in text, f
+
+
+def test_instance_struct_layout_matches_header():
+    # typedef struct vkhr_b200_instance { ptr, ptr, u64, u32, u32, float[3], float[3], ptr }
+    assert C.sizeof(capi.Instance) == 64
+    assert capi.Instance.d_densities_out.offset == 56
+    assert capi.Instance.aabb_origin.offset == 32
+
+
+def test_create_fails_loudly_without_a_device():
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    with pytest.raises(vkhr_b200.VkhrB200Error) as e:
+        vkhr_b200.Voxelizer(0)
+    assert e.value.code == capi.ERR_NO_DEVICE
+    assert "no CPU fallback" in str(e.value)
+
+
+def _style(n=40, s=5, seed=3):
+    hs = HairStyle()
+    hs.vertices = synth.strands(n, s, seed=seed, seg_len=1.1)
+    hs.set_strand_count(n)
+    hs.set_default_segment_count(s)
+    return hs
+
+
+def test_generators_match_oracle(port):
+    hs = _style()
+    hs.generate_indices()
+    hs.generate_tangents()
+    hs.generate_thickness(0.042)
+    assert np.array_equal(hs.indices, port.generate_indices(40, 5))
+    assert np.array_equal(hs.tangents, port.generate_tangents(hs.vertices, 40, 5))
+    assert hs.get_segment_count() == 200 and hs.get_vertex_count() == 240
+    assert hs.thickness[5] == 0 and hs.thickness[4] == np.float32(0.042)
+    # variable strand lengths (has_segments route)
+    segs = np.array([1, 4, 2, 7, 3], dtype=np.uint16)
+    v = np.concatenate([synth.strands(1, int(c), seed=9 + k) for k, c in enumerate(segs)])
+    hs2 = HairStyle()
+    hs2.vertices, hs2.segments = v, segs
+    hs2.generate_indices()
+    hs2.generate_tangents()
+    assert hs2.get_strand_count() == 5
+    assert np.array_equal(hs2.indices, port.generate_indices(5, 0, segments=segs))
+    assert np.array_equal(hs2.tangents, port.generate_tangents(v, 5, 0, segments=segs))
+    lo, hi = synth.host_bounding_box(v)
+    plo, phi = port.generate_bounding_box(v)
+    assert np.array_equal(lo, plo) and np.array_equal(hi, phi)
+    hs2.set_bounding_box(lo, hi)
+    b = hs2.get_bounding_box()
+    assert np.array_equal(np.concatenate([b.origin, [b.radius], b.size, [b.volume]]).astype(np.float32),
+                          port.get_bounding_box(lo, hi))
+
+
+def test_hair_file_roundtrip_with_reference_loader(tmp_path, ref):
+    """A .hair written by the mirror loads in the unmodified reference and vice versa (Appendix C)."""
+    hs = _style(30, 4)
+    hs.generate_indices()
+    hs.generate_tangents()
+    lo, hi = synth.host_bounding_box(hs.vertices)
+    hs.set_bounding_box(lo, hi)
+    p = str(tmp_path / "a.hair")
+    assert hs.save(p)
+    assert os.path.getsize(p) == 128 + 150 * 12 * 2 + 120 * 2 * 4
+    r = ref.load(p)
+    assert r.vertex_count == 150 and r.strand_count == 30 and r.segment_count == 120 and r.has_bounding_box
+    assert np.array_equal(r.vertices, hs.vertices) and np.array_equal(r.indices, hs.indices)
+    assert np.array_equal(r.tangents, hs.tangents)
+    b = hs.get_bounding_box()
+    assert np.array_equal(r.aabb, np.concatenate([b.origin, [b.radius], b.size, [b.volume]]).astype(np.float32))
+    q = str(tmp_path / "b.hair")
+    r.save(q)
+    back = HairStyle(q)
+    assert np.array_equal(back.vertices, hs.vertices) and np.array_equal(back.indices, hs.indices)
+    assert back.has_bounding_box() and back.get_default_segment_count() == 4
+    # variable segments survive too
+    segs = np.array([2, 3, 1], dtype=np.uint16)
+    hv = HairStyle()
+    hv.vertices = np.concatenate([synth.strands(1, int(c), seed=k + 1) for k, c in enumerate(segs)])
+    hv.segments = segs
+    hv.generate_indices()
+    assert hv.save(p)
+    r2 = ref.load(p)
+    assert r2.segments.tolist() == [2, 3, 1] and np.array_equal(r2.indices, hv.indices)
+    assert not HairStyle().load(str(tmp_path / "missing.hair"))
+    with open(p, "wb") as f:
+        f.write(b"NOPE" + bytes(124))
+    assert not HairStyle().load(p)
+
+
+def test_synth_shapes():
+    v, n, s = synth.shape("ponytail", scale=0.01)
+    assert v.shape == (n * (s + 1), 3) and s == 12 and v.dtype == np.float32
+    v2, _, _ = synth.shape("ponytail", scale=0.01)
+    assert np.array_equal(v, v2)                               # deterministic
+    d = np.linalg.norm(np.diff(v.reshape(n, s + 1, 3), axis=1), axis=2)
+    assert np.allclose(d, 0.5, atol=1e-4)                      # fixed segment length
+    w = synth.sway(v, n, s, t=3.0)
+    assert np.array_equal(w.reshape(n, s + 1, 3)[:, 0], v.reshape(n, s + 1, 3)[:, 0])   # roots stay
+    assert not np.array_equal(w, v)

@@ -1,0 +1,288 @@
+"""GPU parity: the CUDA path, called through the C ABI (ctypes), against the golden vectors generated
+from the unmodified reference, against the CPU oracle on seeded inputs, and -- at BASELINE.json's
+full sizes -- through size-independent properties.  Densities are compared BIT-EXACT."""
+import numpy as np
+import pytest
+
+from conftest import dense
+
+pytestmark = pytest.mark.gpu
+
+import vkhr_b200
+from vkhr_b200 import HairStyle, capi, synth
+
+STRATEGIES = [0, capi.STRATEGY_COUNT32, capi.STRATEGY_PACKED8]
+
+
+def _fnv(port, a):
+    return f"{port.fnv1a64(a):016x}"
+
+
+def test_native_library_is_loaded():
+    # the tests below would be meaningless on a fallback: assert the native .so is the one in use
+    with open("/proc/self/maps") as f:
+        assert "libvkhr_b200.so" in f.read()
+    assert "sm_100a" in vkhr_b200.Voxelizer.version()
+
+
+def test_kat4_through_hairstyle_mirror(vox, golden):
+    """The reference's own call sequence (SceneGraph::add_style + voxelize_segments + normalize)."""
+    k = golden["kat4"]
+    hs = HairStyle(voxelizer=vox)
+    hs.vertices = np.array(k["vertices"], dtype=np.float32)
+    hs.set_strand_count(k["strands"])
+    hs.set_default_segment_count(k["segments_per_strand"])
+    hs.generate_tangents()
+    hs.generate_indices()
+    hs.generate_bounding_box()
+    b = hs.get_bounding_box()
+    assert np.array_equal(np.concatenate([b.origin, [b.radius], b.size, [b.volume]]).astype(np.float32),
+                          np.array(k["aabb"], dtype=np.float32))
+    assert hs.indices.tolist() == k["indices"]
+    assert np.array_equal(hs.tangents, np.array(k["tangents_in"], dtype=np.float32), equal_nan=True)
+    vol = hs.voxelize_segments(4, 4, 4)
+    assert np.array_equal(vol.densities, dense(k["voxelize_segments"], 64))
+    assert np.array_equal(hs.voxelize_vertices(4, 4, 4).densities, dense(k["voxelize_vertices"], 64))
+    assert vol.downsample(capi.DOWNSAMPLE_SUM).densities.tolist() == k["downsample_sum_segments"]
+    assert vol.downsample(capi.DOWNSAMPLE_MAX).densities.tolist() == k["downsample_max_segments"]
+    vol.normalize()
+    assert np.array_equal(vol.densities, dense(k["normalize_segments"], 64))
+
+
+@pytest.mark.parametrize("strategy", STRATEGIES)
+@pytest.mark.parametrize("res", [(64, 64, 64), (64, 32, 16), (16, 16, 16), (30, 20, 10)])
+def test_small_sets_golden(vox, small_sets, res, strategy):
+    W, H, D = res
+    if strategy == capi.STRATEGY_PACKED8 and (W * H * D) % 16:
+        pytest.skip("PACKED8 needs W*H*D % 16 == 0")
+    tag = f"{W}x{H}x{D}"
+    v = small_sets["in_vertices"]
+    n, s = [int(x) for x in small_sets["in_meta"]]
+    bb = small_sets["aabb_generated"]
+    lo, hi = vox.generate_bounding_box(v)
+    assert np.array_equal(lo, bb[:3]) and np.array_equal(hi - lo, bb[4:7])
+    hs = HairStyle(voxelizer=vox)
+    hs.vertices = v
+    hs.set_strand_count(n)
+    hs.set_default_segment_count(s)
+    hs.generate_indices()
+    # explicit index buffer and implicit uniform strands must agree with the reference
+    d = vox.voxelize_segments(v, hs.indices, bb[:3], bb[4:7], W, H, D, flags=strategy)
+    assert np.array_equal(d, small_sets[f"seg_{tag}"])
+    d2 = vox.voxelize_segments(v, None, bb[:3], bb[4:7], W, H, D, segs_per_strand=s, flags=strategy)
+    assert np.array_equal(d2, small_sets[f"seg_{tag}"])
+    assert np.array_equal(vox.voxelize_vertices(v, bb[:3], bb[4:7], W, H, D, flags=strategy), small_sets[f"ver_{tag}"])
+    dn = vox.voxelize_segments(v, hs.indices, bb[:3], bb[4:7], W, H, D, flags=strategy | capi.NORMALIZE)
+    assert np.array_equal(dn, small_sets[f"segnorm_{tag}"])
+    assert np.array_equal(vox.normalize(d), small_sets[f"segnorm_{tag}"])
+    if f"segdown0_{tag}" in small_sets:
+        for f in range(4):
+            assert np.array_equal(vox.downsample(d, W, H, D, f), small_sets[f"segdown{f}_{tag}"])
+
+
+def test_small_header_aabb_and_variable_strands(vox, small_sets):
+    v = small_sets["in_vertices"]
+    n, s = [int(x) for x in small_sets["in_meta"]]
+    bb = small_sets["aabb_header"]
+    d = vox.voxelize_segments(v, None, bb[:3], bb[4:7], 64, 64, 64, segs_per_strand=s)
+    assert np.array_equal(d, small_sets["seg_header_64x64x64"])
+    assert np.array_equal(vox.voxelize_vertices(v, bb[:3], bb[4:7], 64, 64, 64), small_sets["ver_header_64x64x64"])
+    hs = HairStyle(voxelizer=vox)
+    hs.vertices = small_sets["var_vertices"]
+    hs.segments = small_sets["var_segments"]
+    hs.generate_indices()
+    assert np.array_equal(hs.indices, small_sets["var_indices"])
+    vbb = small_sets["var_aabb"]
+    hs.set_bounding_box(vbb[:3], vbb[:3] + vbb[4:7])
+    assert np.array_equal(hs.voxelize_segments(32, 32, 32).densities, small_sets["var_seg_32x32x32"])
+
+
+@pytest.mark.parametrize("strategy", STRATEGIES)
+@pytest.mark.parametrize("name", ["ponytail_256", "ponytail_long_256", "ponytail_sat_32", "ponytail_noncubic", "straight_512"])
+def test_full_size_fingerprints(vox, port, golden, name, strategy):
+    """BASELINE.json configs 1/2 sizes: fingerprints of the unmodified reference's output."""
+    e = golden["fingerprints"][name]
+    v, n, s = synth.shape(e["shape"], seed=e["seed"], seg_len=e["seg_len"], scale=e["scale"])
+    assert _fnv(port, v) == e["input_fnv"], "synthetic generator output changed: regenerate tests/golden"
+    W, H, D = e["resolution"]
+    bb = np.array(e["aabb"], dtype=np.float32)
+    d = vox.voxelize_segments(v, None, bb[:3], bb[4:7], W, H, D, segs_per_strand=s, flags=strategy)
+    st = e["segments"]
+    assert (_fnv(port, d), int(d.astype(np.int64).sum()), int(np.count_nonzero(d)), int((d == 255).sum())) == \
+           (st["fnv"], st["sum"], st["nonzero"], st["saturated"])
+    dv = vox.voxelize_vertices(v, bb[:3], bb[4:7], W, H, D, flags=strategy)
+    assert _fnv(port, dv) == e["vertices"]["fnv"]
+    assert _fnv(port, vox.normalize(d)) == e["normalize_segments"]["fnv"]
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_sets_against_oracle(vox, port, seed):
+    rng = np.random.default_rng(1000 + seed)
+    n, s = int(rng.integers(50, 3000)), int(rng.integers(1, 24))
+    v = synth.strands(n, s, seed=int(rng.integers(1, 2**31)), seg_len=float(rng.uniform(0.2, 6.0)),
+                      curl=float(rng.uniform(0.1, 2.0)), gravity=float(rng.uniform(0, 0.6)))
+    W, H, D = [int(x) for x in rng.choice([4, 8, 16, 33, 64, 100, 128], size=3)]
+    lo, hi = port.generate_bounding_box(v)
+    if seed % 2:
+        lo, hi = v.min(axis=0) - np.float32(0.5), v.max(axis=0) + np.float32(0.25)
+    size = (hi - lo).astype(np.float32)
+    idx = port.generate_indices(n, s)
+    for flags in (0, capi.INDEX_EXACT):
+        want = port.voxelize_segments(v, idx, lo, size, W, H, D, flags=flags)
+        for strat in STRATEGIES:
+            if strat == capi.STRATEGY_PACKED8 and (W * H * D) % 16:
+                continue
+            got = vox.voxelize_segments(v, idx, lo, size, W, H, D, flags=flags | strat)
+            assert np.array_equal(got, want), (seed, flags, strat)
+        assert np.array_equal(vox.voxelize_vertices(v, lo, size, W, H, D, flags=flags),
+                              port.voxelize_vertices(v, lo, size, W, H, D, flags=flags))
+
+
+def test_edge_cases(vox, port):
+    """Saturating clump, max-corner clamp, zero-length segments, out-of-box and NaN vertices, tiny inputs."""
+    rng = np.random.default_rng(5)
+    clump = np.tile(np.array([[1.25, 1.25, 1.25], [1.75, 2.6, 1.3]], dtype=np.float32), (400, 1))
+    faces = np.array([[0, 0, 0], [8, 8, 8], [8, 8, 8], [8, 0, 8], [2, 2, 2], [2, 2, 2], [3, 3, 3], [3, 4, 3],
+                      [7.999999, 7.999999, 7.999999], [8, 8, 8], [0, 8, 0], [8, 8, 0],
+                      [9, 9, 9], [12, 9, 9], [-3, 1, 1], [2, 1, 1], [np.nan, 1, 1], [1, 1, 1]], dtype=np.float32)
+    jitter = rng.uniform(0, 8, size=(200, 3)).astype(np.float32)
+    v = np.concatenate([clump, faces, jitter], axis=0)
+    idx = np.arange(v.shape[0], dtype=np.uint32)
+    origin, size = np.zeros(3, np.float32), np.full(3, 8.0, np.float32)
+    for res in [(8, 8, 8), (4, 4, 4), (5, 3, 2), (16, 4, 2)]:
+        want = port.voxelize_segments(v, idx, origin, size, *res)
+        assert want.max() == 255
+        for strat in STRATEGIES:
+            if strat == capi.STRATEGY_PACKED8 and np.prod(res) % 16:
+                continue
+            assert np.array_equal(vox.voxelize_segments(v, idx, origin, size, *res, flags=strat), want), (res, strat)
+            assert np.array_equal(vox.voxelize_vertices(v, origin, size, *res, flags=strat),
+                                  port.voxelize_vertices(v, origin, size, *res))
+    # empty / ragged inputs
+    z = np.zeros(64, dtype=np.uint8)
+    assert np.array_equal(vox.voxelize_segments(v[:3], np.array([0], np.uint32), origin, size, 4, 4, 4), z)
+    assert np.array_equal(vox.voxelize_segments(np.zeros((0, 3), np.float32), None, origin, size, 4, 4, 4,
+                                                segs_per_strand=3), z)
+    assert np.array_equal(vox.voxelize_vertices(np.zeros((0, 3), np.float32), origin, size, 4, 4, 4), z)
+    odd = np.array([0, 1, 2], dtype=np.uint32)          # trailing lone index is ignored (reference loop bound)
+    assert np.array_equal(vox.voxelize_segments(v, odd, origin, size, 4, 4, 4),
+                          port.voxelize_segments(v, odd, origin, size, 4, 4, 4))
+    flat = np.full(64, 7, dtype=np.uint8)
+    assert np.array_equal(vox.normalize(flat), flat)     # max == min: unchanged
+
+
+def test_error_behaviour(vox):
+    v = np.zeros((4, 3), dtype=np.float32)
+    o, s = np.zeros(3, np.float32), np.ones(3, np.float32)
+    with pytest.raises(vkhr_b200.VkhrB200Error) as e:
+        vox.voxelize_segments(v, None, o, s, 4, 4, 4, segs_per_strand=0)
+    assert e.value.code == capi.ERR_INVALID_ARGUMENT
+    with pytest.raises(vkhr_b200.VkhrB200Error):
+        vox.voxelize_segments(v, None, o, s, 4, 4, 4, segs_per_strand=2)       # 4 % 3 != 0
+    with pytest.raises(vkhr_b200.VkhrB200Error):
+        vox.voxelize_segments(v, None, o, np.zeros(3, np.float32), 4, 4, 4, segs_per_strand=1)
+    with pytest.raises(vkhr_b200.VkhrB200Error):
+        vox.voxelize_vertices(v, o, s, 0, 4, 4)
+    with pytest.raises(vkhr_b200.VkhrB200Error) as e:
+        vox.voxelize_vertices(v, o, s, 2048, 2048, 2048)
+    assert e.value.code == capi.ERR_UNSUPPORTED
+    with pytest.raises(vkhr_b200.VkhrB200Error):
+        vox.voxelize_vertices(v, o, s, 5, 3, 2, flags=capi.STRATEGY_PACKED8)
+
+
+def test_device_api_batch_and_shards(vox, port):
+    """Device-pointer API: the crowd batch, and fake ranks -- k partial u32 grids summed then clamped
+    must be byte-identical to the single-rank volume."""
+    import torch
+    dev = torch.device("cuda", 0)
+    W = H = D = 64
+    insts, wants = [], []
+    for k in range(5):
+        v, n, s = synth.shape("ponytail", seed=77 + k, seg_len=0.6 + 0.3 * k, scale=0.01 + 0.002 * k)
+        lo, hi = port.generate_bounding_box(v)
+        size = (hi - lo).astype(np.float32)
+        wants.append(port.voxelize_segments(v, port.generate_indices(n, s), lo, size, W, H, D))
+        insts.append({"vertices": torch.from_numpy(v).to(dev).reshape(-1), "segs_per_strand": s,
+                      "aabb_origin": lo, "aabb_size": size,
+                      "out": torch.full((W * H * D,), 9, dtype=torch.uint8, device=dev)})
+    for strat in (0, capi.STRATEGY_COUNT32):
+        for ins in insts:
+            ins["out"].fill_(9)
+        vox.voxelize_segments_batch_dev(insts, W, H, D, flags=strat)
+        torch.cuda.synchronize()
+        for ins, want in zip(insts, wants):
+            assert np.array_equal(ins["out"].cpu().numpy(), want)
+    # strand shards -> partial counts -> sum -> clamp
+    v, n, s = synth.shape("ponytail", seed=5, seg_len=1.0, scale=0.03)
+    lo, hi = port.generate_bounding_box(v)
+    size = (hi - lo).astype(np.float32)
+    W, H, D = 32, 32, 16                                    # coarse: many saturated voxels
+    want = port.voxelize_segments(v, port.generate_indices(n, s), lo, size, W, H, D)
+    assert (want == 255).sum() > 0
+    vt = torch.from_numpy(v).to(dev)
+    for world in (1, 2, 4, 8):
+        total = torch.zeros(W * H * D, dtype=torch.int32, device=dev)
+        for rank in range(world):
+            a, b = (n * rank) // world, (n * (rank + 1)) // world
+            part = torch.zeros(W * H * D, dtype=torch.int32, device=dev)
+            shard = vt[a * (s + 1): b * (s + 1)].contiguous().reshape(-1)
+            if shard.numel():
+                vox.count_segments_dev(shard, None, lo, size, W, H, D, part, segs_per_strand=s)
+            total += part
+        got = vox.clamp_counts_dev(total)
+        torch.cuda.synchronize()
+        assert np.array_equal(got.cpu().numpy(), want), world
+    # the same through vertex counts
+    part = torch.zeros(W * H * D, dtype=torch.int32, device=dev)
+    vox.count_vertices_dev(vt.reshape(-1), lo, size, W, H, D, part)
+    assert np.array_equal(part.cpu().numpy().astype(np.uint32), port.count_vertices(v, lo, size, W, H, D))
+
+
+def test_full_size_properties(vox, port):
+    """Config-1 size (1.64 M segments, 256^3) and 512^3: properties that need no CPU run of the full job."""
+    import torch
+    dev = torch.device("cuda", 0)
+    v, n, s = synth.shape("ponytail", seed=0xBEEF, seg_len=1.5)
+    lo, hi = port.generate_bounding_box(v)
+    size = (hi - lo).astype(np.float32)
+    idx = port.generate_indices(n, s)
+    vt = torch.from_numpy(v).to(dev).reshape(-1)
+    for (W, H, D) in [(256, 256, 256), (512, 512, 512)]:
+        nvox = W * H * D
+        counts = torch.zeros(nvox, dtype=torch.int32, device=dev)
+        vox.count_segments_dev(vt, None, lo, size, W, H, D, counts, segs_per_strand=s)
+        # (1) unclamped hit counts == the oracle's (its walk alone takes about a second at these sizes),
+        #     and no sample is lost: every sample of the reference walk is in the grid or dropped by rule
+        want_counts = port.count_segments(v, idx, lo, size, W, H, D)
+        assert np.array_equal(counts.cpu().numpy().astype(np.uint32), want_counts)
+        assert int(counts.sum(dtype=torch.int64)) <= port.count_samples(v, idx, lo, size, W, H, D)
+        del want_counts
+        # (2) clamp of the counts == the direct u8 volume, for both strategies
+        clamped = vox.clamp_counts_dev(counts)
+        for strat in (capi.STRATEGY_PACKED8, capi.STRATEGY_COUNT32):
+            d = vox.voxelize_segments_dev(vt, None, lo, size, W, H, D, segs_per_strand=s, flags=strat)
+            assert torch.equal(d, clamped)
+        # (3) additivity over a strand partition (what the multi-GPU sum relies on)
+        half = (n // 2) * (s + 1) * 3
+        c2 = torch.zeros(nvox, dtype=torch.int32, device=dev)
+        vox.count_segments_dev(vt[:half].contiguous(), None, lo, size, W, H, D, c2, segs_per_strand=s)
+        vox.count_segments_dev(vt[half:].contiguous(), None, lo, size, W, H, D, c2, segs_per_strand=s)
+        assert torch.equal(c2, counts)
+        # (4) explicit indices == implicit uniform strands
+        it = torch.from_numpy(idx.astype(np.int32)).to(dev)
+        d_idx = vox.voxelize_segments_dev(vt, it, lo, size, W, H, D)
+        assert torch.equal(d_idx, clamped)
+        # (5) normalize is idempotent once max == 255 and min == 0, and keeps zeros
+        nrm = vox.normalize_dev(d_idx.clone())
+        assert int(nrm.max()) in (254, 255) and int(nrm.min()) == 0
+        assert torch.equal((nrm == 0), (d_idx == 0))
+        # (6) downsample(max) of the volume dominates downsample(min); sum of MEAN*8 <= total
+        if W == 256:
+            mx = vox.downsample_dev(d_idx, W, H, D, capi.DOWNSAMPLE_MAX)
+            mn = vox.downsample_dev(d_idx, W, H, D, capi.DOWNSAMPLE_MIN)
+            assert bool((mx >= mn).all())
+            # oracle on the full grid is cheap for downsample/normalize (no walk)
+            dh = d_idx.cpu().numpy()
+            assert np.array_equal(mx.cpu().numpy(), port.downsample(dh, W, H, D, 0))
+            assert np.array_equal(nrm.cpu().numpy(), port.normalize(dh))
+        torch.cuda.synchronize()

@@ -101,7 +101,15 @@ struct vkhr_b200_ctx {
     DevBuf st_vertices, st_indices, st_tangents, st_dens, st_tang_out;   // host-API staging
     int repair_blocks[2] = {0, 0};
     std::vector<InstanceDev> host_table;
+    // optional per-phase device timing (vkhr_b200_profile_*): CUDA events recorded on the
+    // launching stream around each phase of run_voxelize
+    bool profiling = false;
+    struct Span { cudaEvent_t a, b; int phase; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> event_pool;
 };
+
+enum Phase { PH_CLEAR = 0, PH_WALK = 1, PH_FINISH = 2, PH_NORMALIZE = 3, PH_COUNT = 4 };
 
 static thread_local std::string g_create_error;
 
@@ -156,6 +164,24 @@ int reserve(vkhr_b200_ctx* ctx, DevBuf& b, size_t bytes) {
 inline cudaStream_t pick(vkhr_b200_ctx* ctx, void* stream) {
     return stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
 }
+
+cudaEvent_t take_event(vkhr_b200_ctx* ctx) {
+    if (!ctx->event_pool.empty()) { cudaEvent_t e = ctx->event_pool.back(); ctx->event_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+// Scoped phase marker: records an event pair on `s` when profiling is on, else does nothing.
+struct PhaseMark {
+    vkhr_b200_ctx* ctx; cudaStream_t s; cudaEvent_t a = nullptr; int phase;
+    PhaseMark(vkhr_b200_ctx* c, cudaStream_t st, int ph) : ctx(c), s(st), phase(ph) {
+        if (ctx->profiling) { a = take_event(ctx); cudaEventRecord(a, s); }
+    }
+    ~PhaseMark() {
+        if (a) { cudaEvent_t b = take_event(ctx); cudaEventRecord(b, s); ctx->spans.push_back({a, b, phase}); }
+    }
+};
 
 inline unsigned stride_blocks(vkhr_b200_ctx* ctx, uint64_t items, unsigned per_block, unsigned waves) {
     uint64_t need = (items + per_block - 1) / per_block;
@@ -288,14 +314,19 @@ int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_
         RET_IF(upload_table(ctx, s));
         const InstanceDev* table = static_cast<const InstanceDev*>(ctx->table.p);
         const unsigned gx = stride_blocks(ctx, nv / 16, 256, n >= 8 ? 2 : 8);
-        k_clear_packed_batch<<<dim3(gx, n), 256, 0, s>>>(table);
+        {
+            PhaseMark m(ctx, s, PH_CLEAR);
+            k_clear_packed_batch<<<dim3(gx, n), 256, 0, s>>>(table);
+        }
         if (tiles) {
+            PhaseMark m(ctx, s, PH_WALK);
             if (vertices_mode) k_splat_batch<1><<<tiles, kWalkThreads, 0, s>>>(table, n);
             else               k_walk_batch<1><<<tiles, kWalkThreads, 0, s>>>(table, n);
         }
         ctx->launches += tiles ? 2 : 1;
         CU_CHECK(ctx, cudaGetLastError());
         if (tiles) {
+            PhaseMark m(ctx, s, PH_FINISH);
             if (vertices_mode) RET_IF(launch_repair<true>(ctx, n, static_cast<uint32_t*>(ctx->counts.p), s));
             else               RET_IF(launch_repair<false>(ctx, n, static_cast<uint32_t*>(ctx->counts.p), s));
         }
@@ -310,6 +341,7 @@ int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_
         for (uint32_t first = 0; first < n; first += chunk) {
             const uint32_t m = std::min(chunk, n - first);
             if (ctx->counts_clean_bytes < per * m) {
+                PhaseMark mk(ctx, s, PH_CLEAR);
                 CU_CHECK(ctx, cudaMemsetAsync(ctx->counts.p, 0, per * m, s));
                 ctx->counts_clean_bytes = 0;           // until the ZERO clamp below has run
             }
@@ -319,10 +351,12 @@ int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_
             RET_IF(upload_table(ctx, s));
             const InstanceDev* table = static_cast<const InstanceDev*>(ctx->table.p);
             if (tiles) {
+                PhaseMark mk(ctx, s, PH_WALK);
                 if (vertices_mode) k_splat_batch<0><<<tiles, kWalkThreads, 0, s>>>(table, m);
                 else               k_walk_batch<0><<<tiles, kWalkThreads, 0, s>>>(table, m);
                 ctx->launches++;
             }
+            PhaseMark mk(ctx, s, PH_FINISH);
             for (uint32_t k = 0; k < m; ++k) {
                 k_clamp_counts<true><<<stride_blocks(ctx, nv / 16 + 1, 256, 8), 256, 0, s>>>(
                     static_cast<uint32_t*>(ctx->counts.p) + (size_t)k * nv, nv, jobs[first + k].d_dens);
@@ -332,8 +366,10 @@ int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_
             ctx->counts_clean_bytes = std::max(ctx->counts_clean_bytes, per * m);   // ZERO clamp restored the invariant
         }
     }
-    if (flags & VKHR_B200_NORMALIZE)
+    if (flags & VKHR_B200_NORMALIZE) {
+        PhaseMark mk(ctx, s, PH_NORMALIZE);
         for (uint32_t k = 0; k < n; ++k) RET_IF(vkhr_b200_normalize_dev(ctx, jobs[k].d_dens, nv, s));
+    }
     return VKHR_B200_OK;
 }
 
@@ -396,6 +432,8 @@ void vkhr_b200_destroy(vkhr_b200_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->counts, &ctx->bitmap, &ctx->table, &ctx->small, &ctx->st_vertices,
                       &ctx->st_indices, &ctx->st_tangents, &ctx->st_dens, &ctx->st_tang_out};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+    for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -413,6 +451,29 @@ int vkhr_b200_synchronize(vkhr_b200_ctx* ctx) {
 }
 
 uint64_t vkhr_b200_launch_count(const vkhr_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int vkhr_b200_profile_enable(vkhr_b200_ctx* ctx, int enable) {
+    RET_IF(bind(ctx));
+    ctx->profiling = enable != 0;
+    return VKHR_B200_OK;
+}
+
+int vkhr_b200_profile_read(vkhr_b200_ctx* ctx, double ms_out[4], uint32_t spans_out[4]) {
+    RET_IF(bind(ctx));
+    if (!ms_out || !spans_out) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null output");
+    for (int k = 0; k < PH_COUNT; ++k) { ms_out[k] = 0.0; spans_out[k] = 0; }
+    for (auto& sp : ctx->spans) {
+        CU_CHECK(ctx, cudaEventSynchronize(sp.b));
+        float ms = 0.0f;
+        CU_CHECK(ctx, cudaEventElapsedTime(&ms, sp.a, sp.b));
+        ms_out[sp.phase] += ms;
+        spans_out[sp.phase] += 1;
+        ctx->event_pool.push_back(sp.a);
+        ctx->event_pool.push_back(sp.b);
+    }
+    ctx->spans.clear();
+    return VKHR_B200_OK;
+}
 
 // ---- device-pointer API -----------------------------------------------------
 int vkhr_b200_voxelize_segments_dev(vkhr_b200_ctx* ctx, const float* d_vertices, uint32_t n_vertices,

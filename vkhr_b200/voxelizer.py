@@ -63,6 +63,16 @@ class Voxelizer:
     def stream(self) -> int:
         return int(lib.vkhr_b200_stream(self._h) or 0)
 
+    def profile_enable(self, on: bool = True) -> None:
+        capi.check(self._h, lib.vkhr_b200_profile_enable(self._h, int(bool(on))))
+
+    def profile_read(self) -> dict:
+        """Summed device milliseconds / span counts per phase since the last read."""
+        ms, n = (C.c_double * 4)(), (C.c_uint32 * 4)()
+        capi.check(self._h, lib.vkhr_b200_profile_read(self._h, ms, n))
+        names = ("clear", "walk", "finish", "normalize")
+        return {k: {"ms": ms[i], "spans": int(n[i])} for i, k in enumerate(names)}
+
     def synchronize(self) -> None:
         capi.check(self._h, lib.vkhr_b200_synchronize(self._h))
 
