@@ -26,8 +26,9 @@
  * Threading: one context = one device + one internal stream.  Calls on one
  * context must be serialised by the caller; distinct contexts are independent.
  * Host-pointer entry points are synchronous.  `_dev` entry points take device
- * pointers, enqueue on the given stream (NULL = the context's stream) and
- * return without synchronising.
+ * pointers, enqueue on the given cudaStream_t (NULL = the context's own stream;
+ * pass cudaStreamLegacy, (void*)1, for the legacy default stream) and return
+ * without synchronising.
  *
  * Errors: every call returns 0 or a negative vkhr_b200_status; nothing throws.
  * There is no CPU fallback: without a usable sm_100 device vkhr_b200_create fails.
@@ -100,6 +101,12 @@ VKHR_B200_API uint64_t vkhr_b200_launch_count(const vkhr_b200_ctx* ctx);
  * [2] finish (overflow repair or u32->u8 clamp), [3] normalize. */
 VKHR_B200_API int vkhr_b200_profile_enable(vkhr_b200_ctx* ctx, int enable);
 VKHR_B200_API int vkhr_b200_profile_read(vkhr_b200_ctx* ctx, double ms_out[4], uint32_t spans_out[4]);
+
+/* Self test of the kernels' fast exact division (walk.cuh div_exact): compares it
+ * bit for bit with the IEEE division instruction sequence on n_trials
+ * pseudo-random numerators for one divisor; *mismatches must come back 0. */
+VKHR_B200_API int vkhr_b200_selftest_division(vkhr_b200_ctx* ctx, float divisor, uint64_t n_trials,
+                                              uint64_t seed, uint64_t* mismatches);
 
 /* ---- host-pointer API: replaces HairStyle::voxelize_segments ----------
  * (hair_style.hh:104, hair_style.cc:296-342).

@@ -25,6 +25,41 @@ def test_native_library_is_loaded():
     assert "sm_100a" in vkhr_b200.Voxelizer.version()
 
 
+def test_fast_division_is_exact(vox):
+    """The kernels replace `a / d` by an FMA sequence with a precomputed reciprocal (walk.cuh div_exact);
+    it must equal the IEEE division bit for bit, including operands on both sides of its range guard."""
+    rng = np.random.default_rng(3)
+    divisors = [1.0, 0.21861044, 0.39062497, 1.9999999, 1.0000001, 3.0, 0.1, 7.0, 1.5, 0.75, 255.0, 1e-3, 1e4,
+                float(np.float32(100.0) / np.float32(256.0)), float(np.float32(56.558083) / np.float32(256.0))]
+    divisors += [float(x) for x in np.exp(rng.uniform(np.log(1e-4), np.log(1e4), 25)).astype(np.float32)]
+    divisors += [float(np.frombuffer(np.uint32(0x3F7FFFFF + k).tobytes(), dtype=np.float32)[0]) for k in (0, 1, 2)]
+    divisors += [1e-13, 1e13]            # outside the fast range: must still be exact (plain division)
+    total = 0
+    for i, d in enumerate(divisors):
+        assert vox.selftest_division(d, n_trials=1 << 26, seed=1000 + i) == 0, d
+        total += 1 << 26
+    assert total > 2_000_000_000
+
+
+def test_unaligned_and_offset_device_buffers(vox, port):
+    """Device pointers that are only 4-byte aligned (a view into a larger buffer)."""
+    import torch
+    dev = torch.device("cuda", 0)
+    v, n, s = synth.shape("ponytail", seed=21, seg_len=1.0, scale=0.02)
+    lo, hi = port.generate_bounding_box(v)
+    size = (hi - lo).astype(np.float32)
+    want = port.voxelize_segments(v, port.generate_indices(n, s), lo, size, 64, 64, 64)
+    big = torch.zeros(v.size + 8, dtype=torch.float32, device=dev)
+    for off in (0, 1, 2, 3):
+        big[off:off + v.size] = torch.from_numpy(v.reshape(-1)).to(dev)
+        view = big[off:off + v.size]
+        got = vox.voxelize_segments_dev(view, None, lo, size, 64, 64, 64, segs_per_strand=s)
+        assert np.array_equal(got.cpu().numpy(), want), off
+        outbuf = torch.zeros(64 ** 3 + 16, dtype=torch.uint8, device=dev)
+        got2 = vox.voxelize_segments_dev(view, None, lo, size, 64, 64, 64, segs_per_strand=s, out=outbuf[off + 1:off + 1 + 64 ** 3])
+        assert np.array_equal(got2.cpu().numpy(), want), off
+
+
 def test_kat4_through_hairstyle_mirror(vox, golden):
     """The reference's own call sequence (SceneGraph::add_style + voxelize_segments + normalize)."""
     k = golden["kat4"]
@@ -216,7 +251,7 @@ def test_device_api_batch_and_shards(vox, port):
     v, n, s = synth.shape("ponytail", seed=5, seg_len=1.0, scale=0.03)
     lo, hi = port.generate_bounding_box(v)
     size = (hi - lo).astype(np.float32)
-    W, H, D = 32, 32, 16                                    # coarse: many saturated voxels
+    W, H, D = 8, 8, 4                                       # coarse: many saturated voxels
     want = port.voxelize_segments(v, port.generate_indices(n, s), lo, size, W, H, D)
     assert (want == 255).sum() > 0
     vt = torch.from_numpy(v).to(dev)

@@ -36,7 +36,8 @@ struct InstanceDev {
 // COUNT32: plain u32 hit counter, clamped later.  `red.global.add.u32` (no return).
 struct SinkCount32 {
     uint32_t* counts;
-    __device__ __forceinline__ void operator()(uint32_t idx) const { atomicAdd(counts + idx, 1u); }
+    __device__ __forceinline__ void operator()(uint32_t idx) { atomicAdd(counts + idx, 1u); }
+    __device__ __forceinline__ void finish() {}
 };
 
 // PACKED8: the u8 output grid itself is the counter; four voxels share one
@@ -44,19 +45,28 @@ struct SinkCount32 {
 // the adding thread whether ITS add carried out of the byte (old field ==
 // 255).  The first carry in a word is always seen on a clean word, so a word
 // is flagged in the bitmap if and only if one of its voxels received more
-// than 255 hits; flagged words are recounted exactly by k_repair_*.
+// than 255 hits; flagged words are recounted exactly by k_repair_packed.
+// The returned word is examined one sample later, just before the next atomic
+// is issued, so the round trip overlaps the next sample's arithmetic.
 struct SinkPacked8 {
     uint32_t* words;
     uint32_t* ovf_bitmap;
     uint32_t* ovf_flag;
-    __device__ __forceinline__ void operator()(uint32_t idx) const {
-        const uint32_t w = idx >> 2, sh = (idx & 3u) * 8u;
-        const uint32_t old = atomicAdd(words + w, 1u << sh);
-        if (((old >> sh) & 0xFFu) == 0xFFu) {
-            atomicOr(ovf_bitmap + (w >> 5), 1u << (w & 31u));
+    uint32_t pend_old = 0, pend_sh = 0, pend_w = 0;
+    __device__ __forceinline__ void check() {
+        if (((pend_old >> pend_sh) & 0xFFu) == 0xFFu) {
+            atomicOr(ovf_bitmap + (pend_w >> 5), 1u << (pend_w & 31u));
             *ovf_flag = 1u;
         }
     }
+    __device__ __forceinline__ void operator()(uint32_t idx) {
+        const uint32_t w = idx >> 2, sh = (idx & 3u) * 8u;
+        check();
+        pend_old = atomicAdd(words + w, 1u << sh);
+        pend_sh = sh;
+        pend_w = w;
+    }
+    __device__ __forceinline__ void finish() { check(); }
 };
 
 // Recount pass of PACKED8: only samples landing in flagged words are counted,
@@ -64,76 +74,146 @@ struct SinkPacked8 {
 struct SinkRecount {
     const uint32_t* ovf_bitmap;
     uint32_t* counts;
-    __device__ __forceinline__ void operator()(uint32_t idx) const {
+    __device__ __forceinline__ void operator()(uint32_t idx) {
         const uint32_t w = idx >> 2;
         if ((__ldg(ovf_bitmap + (w >> 5)) >> (w & 31u)) & 1u) atomicAdd(counts + idx, 1u);
     }
+    __device__ __forceinline__ void finish() {}
 };
 
-// ---------------------------------------------------------------------------
-// Walk kernels.  One thread per segment (or per vertex); consecutive threads
-// take consecutive segments of the same strand, so a warp reads a contiguous
-// span of the vertex array.
-// ---------------------------------------------------------------------------
-template <class Sink>
-__device__ __forceinline__ void walk_one_segment(const float* __restrict__ vertices,
-                                                 const uint32_t* __restrict__ indices,
-                                                 uint32_t segs, uint64_t s,
-                                                 const GridParams& g, Sink&& sink) {
-    uint32_t i0, i1;
-    segment_vertices(indices, segs, s, i0, i1);
-    const float* a = vertices + 3ull * i0;
-    const float* b = vertices + 3ull * i1;
-    walk_segment(g, __ldg(a), __ldg(a + 1), __ldg(a + 2), __ldg(b), __ldg(b + 1), __ldg(b + 2), sink);
-}
+template <int MODE> struct SinkOf;
+template <> struct SinkOf<0> { using type = SinkCount32;
+    __device__ static type make(const InstanceDev& I) { return SinkCount32{I.counts}; } };
+template <> struct SinkOf<1> { using type = SinkPacked8;
+    __device__ static type make(const InstanceDev& I) { return SinkPacked8{reinterpret_cast<uint32_t*>(I.densities), I.ovf_bitmap, I.ovf_flag}; } };
+template <> struct SinkOf<2> { using type = SinkRecount;
+    __device__ static type make(const InstanceDev& I) { return SinkRecount{I.ovf_bitmap, I.counts}; } };
 
-// Batched walk: a flat grid of tiles over all instances; each CTA finds its
-// instance by binary search over first_tile.  MODE 0 = COUNT32, 1 = PACKED8,
-// 2 = recount of flagged words (only instances whose ovf_flag is set).
-template <int MODE>
-__global__ void __launch_bounds__(kWalkThreads)
-k_walk_batch(const InstanceDev* __restrict__ inst, uint32_t n_inst) {
+// Instance owning flat tile `tile` (binary search over first_tile; n_inst is small).
+__device__ __forceinline__ uint32_t find_instance(const InstanceDev* __restrict__ inst, uint32_t n_inst, uint32_t tile) {
     uint32_t lo = 0, hi = n_inst - 1;
     while (lo < hi) {
-        uint32_t mid = (lo + hi + 1) >> 1;
-        if (inst[mid].first_tile <= blockIdx.x) lo = mid; else hi = mid - 1;
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (__ldg(&inst[mid].first_tile) <= tile) lo = mid; else hi = mid - 1;
     }
-    const InstanceDev& I = inst[lo];
+    return lo;
+}
+
+// ---------------------------------------------------------------------------
+// Walk kernel for uniform strands (no index buffer): the hot kernel.
+//
+// A CTA owns 256 consecutive vertex slots of one instance.  Its 257 vertices
+// (3084 contiguous bytes) are fetched with 193 coalesced 16-byte loads into
+// shared memory; thread t moves vertex t to voxel space ONCE (three exact
+// divisions), publishes it through shared memory, and walks the segment
+// (vertex t, vertex t+1) unless vertex t is the last of its strand.  Vertices
+// are read from HBM exactly once and no per-thread strided global loads or
+// per-iteration parameter loads remain on the L1TEX path -- only the atomics.
+// MODE 0 = COUNT32, 1 = PACKED8, 2 = recount of flagged words.
+// ---------------------------------------------------------------------------
+template <int MODE, int EXACT>
+__global__ void __launch_bounds__(kWalkThreads)
+k_walk_uniform(const InstanceDev* __restrict__ inst, uint32_t n_inst) {
+    __shared__ __align__(16) float s_raw[4 * 194];
+    __shared__ float s_pos[3 * 257 + 3];
+    const uint32_t t = threadIdx.x;
+    const InstanceDev& I = inst[find_instance(inst, n_inst, blockIdx.x)];
+    if (MODE == 2 && *I.ovf_flag == 0u) return;
+    const GridParams g = I.grid;                                  // by value: stays in registers
+    const uint32_t n_vertices = I.n_vertices;
+    const uint32_t v0 = (blockIdx.x - I.first_tile) * kWalkThreads;   // first vertex slot of this tile
+    const uint32_t cnt = min(257u, n_vertices - v0);              // vertices this tile can see
+    const uint32_t n_floats = 3u * cnt;
+    const float* __restrict__ src = I.vertices + 3ull * v0;       // tile stride 3072 B: aligned iff the base is
+    if ((reinterpret_cast<uintptr_t>(I.vertices) & 15u) == 0) {
+        if (t < 193u) {
+            if (4u * t + 4u <= n_floats) {
+                reinterpret_cast<uint4*>(s_raw)[t] = __ldg(reinterpret_cast<const uint4*>(src) + t);
+            } else {
+                for (uint32_t k = 4u * t; k < n_floats; ++k) s_raw[k] = __ldg(src + k);
+            }
+        }
+    } else {                                                      // unaligned vertex buffer: scalar, still coalesced
+        for (uint32_t k = t; k < n_floats; k += kWalkThreads) s_raw[k] = __ldg(src + k);
+    }
+    __syncthreads();
+    float px = 0.f, py = 0.f, pz = 0.f;
+    if (t < cnt) {
+        px = to_voxel_space(s_raw[3 * t + 0], g.ox, g.vsx, g.rvx);
+        py = to_voxel_space(s_raw[3 * t + 1], g.oy, g.vsy, g.rvy);
+        pz = to_voxel_space(s_raw[3 * t + 2], g.oz, g.vsz, g.rvz);
+        s_pos[3 * t + 0] = px; s_pos[3 * t + 1] = py; s_pos[3 * t + 2] = pz;
+    }
+    if (t == 0 && cnt == 257u) {                                  // the tile's last tip vertex
+        s_pos[768] = to_voxel_space(s_raw[768], g.ox, g.vsx, g.rvx);
+        s_pos[769] = to_voxel_space(s_raw[769], g.oy, g.vsy, g.rvy);
+        s_pos[770] = to_voxel_space(s_raw[770], g.oz, g.vsz, g.rvz);
+    }
+    __syncthreads();
+    // vertex v0+t starts a segment unless it is the last vertex of its strand
+    const uint32_t vps = I.segs_per_strand + 1u;
+    const bool starts_segment = (t + 1u < cnt) && ((v0 + t) % vps != vps - 1u);
+    if (!starts_segment) return;
+    auto sink = SinkOf<MODE>::make(I);
+    walk_voxel_space<EXACT>(g, px, py, pz, s_pos[3 * t + 3], s_pos[3 * t + 4], s_pos[3 * t + 5], sink);
+    sink.finish();
+}
+
+// ---------------------------------------------------------------------------
+// Generic walk: explicit index buffer (arbitrary vertex pairs), one thread per
+// segment, gathered vertex loads.
+// ---------------------------------------------------------------------------
+template <int MODE, int EXACT>
+__global__ void __launch_bounds__(kWalkThreads)
+k_walk_indexed(const InstanceDev* __restrict__ inst, uint32_t n_inst) {
+    const InstanceDev& I = inst[find_instance(inst, n_inst, blockIdx.x)];
     if (MODE == 2 && *I.ovf_flag == 0u) return;
     const uint64_t s = (uint64_t)(blockIdx.x - I.first_tile) * kWalkThreads + threadIdx.x;
     if (s >= I.n_segments) return;
-    if (MODE == 0)
-        walk_one_segment(I.vertices, I.indices, I.segs_per_strand, s, I.grid, SinkCount32{I.counts});
-    else if (MODE == 1)
-        walk_one_segment(I.vertices, I.indices, I.segs_per_strand, s, I.grid,
-                         SinkPacked8{reinterpret_cast<uint32_t*>(I.densities), I.ovf_bitmap, I.ovf_flag});
-    else
-        walk_one_segment(I.vertices, I.indices, I.segs_per_strand, s, I.grid,
-                         SinkRecount{I.ovf_bitmap, I.counts});
+    const GridParams g = I.grid;
+    const uint2 pr = __ldg(reinterpret_cast<const uint2*>(I.indices) + s);
+    const float* a = I.vertices + 3ull * pr.x;
+    const float* b = I.vertices + 3ull * pr.y;
+    auto sink = SinkOf<MODE>::make(I);
+    walk_segment<EXACT>(g, __ldg(a), __ldg(a + 1), __ldg(a + 2), __ldg(b), __ldg(b + 1), __ldg(b + 2), sink);
+    sink.finish();
 }
 
-// Same for the vertex splat (instances reuse n_vertices; indices unused).
-template <int MODE>
+// Vertex splat (voxelize_vertices): one thread per vertex.
+template <int MODE, int EXACT>
 __global__ void __launch_bounds__(kWalkThreads)
 k_splat_batch(const InstanceDev* __restrict__ inst, uint32_t n_inst) {
-    uint32_t lo = 0, hi = n_inst - 1;
-    while (lo < hi) {
-        uint32_t mid = (lo + hi + 1) >> 1;
-        if (inst[mid].first_tile <= blockIdx.x) lo = mid; else hi = mid - 1;
-    }
-    const InstanceDev& I = inst[lo];
+    const InstanceDev& I = inst[find_instance(inst, n_inst, blockIdx.x)];
     if (MODE == 2 && *I.ovf_flag == 0u) return;
     const uint32_t i = (blockIdx.x - I.first_tile) * kWalkThreads + threadIdx.x;
     if (i >= I.n_vertices) return;
+    const GridParams g = I.grid;
     const float* v = I.vertices + 3ull * i;
-    const GridParams& g = I.grid;
     uint32_t idx;
-    if (!voxel_index(g, to_voxel_space(__ldg(v), g.ox, g.vsx), to_voxel_space(__ldg(v + 1), g.oy, g.vsy),
-                     to_voxel_space(__ldg(v + 2), g.oz, g.vsz), idx))
+    if (!voxel_index<EXACT>(g, to_voxel_space(__ldg(v), g.ox, g.vsx, g.rvx), to_voxel_space(__ldg(v + 1), g.oy, g.vsy, g.rvy),
+                            to_voxel_space(__ldg(v + 2), g.oz, g.vsz, g.rvz), idx))
         return;
-    if (MODE == 0) SinkCount32{I.counts}(idx);
-    else if (MODE == 1) SinkPacked8{reinterpret_cast<uint32_t*>(I.densities), I.ovf_bitmap, I.ovf_flag}(idx);
-    else SinkRecount{I.ovf_bitmap, I.counts}(idx);
+    auto sink = SinkOf<MODE>::make(I);
+    sink(idx);
+    sink.finish();
+}
+
+// Bitwise comparison of div_exact against the IEEE division on pseudo-random
+// operands (self test of the fast exact division; see walk.cuh).
+__global__ void __launch_bounds__(256)
+k_selftest_division(float d, float y, uint64_t seed, uint32_t per_thread, unsigned long long* mismatches) {
+    uint64_t x = seed ^ (0x9E3779B97F4A7C15ull * ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 1));
+    uint32_t bad = 0;
+    for (uint32_t i = 0; i < per_thread; ++i) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        // random sign and mantissa, exponent spread over [2^-70, 2^70] (both sides of the guard)
+        const uint32_t e = 127u - 70u + (uint32_t)((x >> 40) % 141u);
+        const float a = __uint_as_float(((uint32_t)x & 0x807FFFFFu) | (e << 23));
+        const float q = div_exact(a, d, y);
+        const float want = __fdiv_rn(a, d);
+        bad += (__float_as_uint(q) != __float_as_uint(want));
+    }
+    if (bad) atomicAdd(mismatches, (unsigned long long)bad);
 }
 
 // ---------------------------------------------------------------------------
@@ -189,6 +269,16 @@ k_clamp_counts(uint32_t* __restrict__ counts, uint64_t n, uint8_t* __restrict__ 
             dens[i] = (uint8_t)min(counts[i], 255u);
             if (ZERO) counts[i] = 0u;
         }
+    }
+}
+
+// Same for an output grid that is not 16-byte aligned (a view into a caller's buffer): one voxel per thread.
+template <bool ZERO>
+__global__ void __launch_bounds__(256)
+k_clamp_counts_unaligned(uint32_t* __restrict__ counts, uint64_t n, uint8_t* __restrict__ dens) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        dens[i] = (uint8_t)min(counts[i], 255u);
+        if (ZERO) counts[i] = 0u;
     }
 }
 

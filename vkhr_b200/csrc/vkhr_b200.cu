@@ -33,13 +33,18 @@ using namespace vkhr_b200;
 template <bool VERTICES>
 __global__ void __launch_bounds__(kWalkThreads)
 k_repair_packed(const InstanceDev* __restrict__ inst, uint32_t n_inst, uint32_t* __restrict__ scratch) {
+    // common case first: no instance overflowed -> one parallel look at the flags and out
+    int any = 0;
+    for (uint32_t k = threadIdx.x; k < n_inst; k += blockDim.x) any |= (*inst[k].ovf_flag != 0u);
+    if (!__syncthreads_or(any)) return;                        // same answer in every CTA
     cg::grid_group grid = cg::this_grid();
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t nthreads = gridDim.x * blockDim.x;
     for (uint32_t k = 0; k < n_inst; ++k) {
         const InstanceDev& I = inst[k];
         if (*I.ovf_flag == 0u) continue;                       // uniform across the grid
-        const uint32_t n_words = I.grid.n_voxels >> 2;
+        const GridParams g = I.grid;
+        const uint32_t n_words = g.n_voxels >> 2;
         const uint32_t n_bm = (n_words + 31) / 32;
         uint32_t* words = reinterpret_cast<uint32_t*>(I.densities);
         uint4* counts4 = reinterpret_cast<uint4*>(scratch);
@@ -52,19 +57,29 @@ k_repair_packed(const InstanceDev* __restrict__ inst, uint32_t n_inst, uint32_t*
             }
         }
         grid.sync();
-        const SinkRecount sink{I.ovf_bitmap, scratch};
+        SinkRecount sink{I.ovf_bitmap, scratch};
         if (VERTICES) {
             for (uint32_t i = tid; i < I.n_vertices; i += nthreads) {
                 const float* v = I.vertices + 3ull * i;
-                const GridParams& g = I.grid;
                 uint32_t idx;
-                if (voxel_index(g, to_voxel_space(__ldg(v), g.ox, g.vsx), to_voxel_space(__ldg(v + 1), g.oy, g.vsy),
-                                to_voxel_space(__ldg(v + 2), g.oz, g.vsz), idx))
+                if (voxel_index(g, to_voxel_space(__ldg(v), g.ox, g.vsx, g.rvx), to_voxel_space(__ldg(v + 1), g.oy, g.vsy, g.rvy),
+                                to_voxel_space(__ldg(v + 2), g.oz, g.vsz, g.rvz), idx))
                     sink(idx);
             }
+        } else if (I.indices) {
+            for (uint64_t s = tid; s < I.n_segments; s += nthreads) {
+                const uint2 pr = __ldg(reinterpret_cast<const uint2*>(I.indices) + s);
+                const float* a = I.vertices + 3ull * pr.x;
+                const float* b = I.vertices + 3ull * pr.y;
+                walk_segment(g, __ldg(a), __ldg(a + 1), __ldg(a + 2), __ldg(b), __ldg(b + 1), __ldg(b + 2), sink);
+            }
         } else {
-            for (uint64_t s = tid; s < I.n_segments; s += nthreads)
-                walk_one_segment(I.vertices, I.indices, I.segs_per_strand, s, I.grid, sink);
+            const uint32_t vps = I.segs_per_strand + 1u;
+            for (uint32_t v = tid; v + 1u < I.n_vertices; v += nthreads) {
+                if (v % vps == vps - 1u) continue;             // last vertex of a strand starts no segment
+                const float* a = I.vertices + 3ull * v;
+                walk_segment(g, __ldg(a), __ldg(a + 1), __ldg(a + 2), __ldg(a + 3), __ldg(a + 4), __ldg(a + 5), sink);
+            }
         }
         grid.sync();
         for (uint32_t b = tid; b < n_bm; b += nthreads) {
@@ -208,6 +223,9 @@ int make_grid(vkhr_b200_ctx* ctx, const float origin[3], const float size[3],
     g.W = W; g.H = H; g.D = D;
     g.n_voxels = (uint32_t)n;
     g.index_exact = (flags & VKHR_B200_INDEX_EXACT) ? 1u : 0u;
+    // RN(1/voxel_size) for div_exact (walk.cuh); outside [2^-40, 2^40] the kernels use the plain IEEE division
+    auto recip = [](float vs) { return (vs >= 9.094947e-13f && vs <= 1.0995116e12f) ? 1.0f / vs : 0.0f; };
+    g.rvx = recip(g.vsx); g.rvy = recip(g.vsy); g.rvz = recip(g.vsz);
     return VKHR_B200_OK;
 }
 
@@ -251,25 +269,75 @@ int upload_table(vkhr_b200_ctx* ctx, cudaStream_t s) {
     return VKHR_B200_OK;
 }
 
-// Fill host_table for `jobs`; returns the total number of walk tiles.
-uint32_t fill_table(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_mode) {
+// How one instance's work is tiled over CTAs.
+enum WalkKind { WK_UNIFORM = 0, WK_INDEXED = 1, WK_SPLAT = 2 };
+
+WalkKind kind_of(const Job& j, bool vertices_mode) {
+    if (vertices_mode) return WK_SPLAT;
+    return j.d_indices ? WK_INDEXED : WK_UNIFORM;
+}
+
+struct TablePlan {
+    uint32_t first[2] = {0, 0};     // table slice [first, first+count) of the uniform / indexed (or splat) group
+    uint32_t count[2] = {0, 0};
+    uint32_t tiles[2] = {0, 0};
+    std::vector<uint32_t> order;    // table slot -> job index
+};
+
+// Fill host_table for `jobs`: instances walked by the uniform-strand kernel first, then the rest
+// (explicit indices, or every instance in vertex mode); first_tile restarts per group.
+TablePlan fill_table(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_mode) {
+    TablePlan plan;
     ctx->host_table.resize(n);
-    uint64_t tile = 0;
-    for (uint32_t k = 0; k < n; ++k) {
-        InstanceDev& I = ctx->host_table[k];
-        std::memset(&I, 0, sizeof I);
-        I.vertices = jobs[k].d_vertices;
-        I.indices = jobs[k].d_indices;
-        I.n_segments = jobs[k].n_segments;
-        I.n_vertices = jobs[k].n_vertices;
-        I.segs_per_strand = jobs[k].segs;
-        I.grid = jobs[k].grid;
-        I.densities = jobs[k].d_dens;
-        I.first_tile = (uint32_t)tile;
-        const uint64_t items = vertices_mode ? jobs[k].n_vertices : jobs[k].n_segments;
-        tile += (items + kWalkThreads - 1) / kWalkThreads;
+    for (int grp = 0; grp < 2; ++grp) {
+        plan.first[grp] = (uint32_t)plan.order.size();
+        uint64_t tile = 0;
+        for (uint32_t k = 0; k < n; ++k) {
+            const WalkKind kind = kind_of(jobs[k], vertices_mode);
+            if ((kind == WK_UNIFORM ? 0 : 1) != grp) continue;
+            InstanceDev& I = ctx->host_table[plan.order.size()];
+            plan.order.push_back(k);
+            std::memset(&I, 0, sizeof I);
+            I.vertices = jobs[k].d_vertices;
+            I.indices = jobs[k].d_indices;
+            I.n_segments = jobs[k].n_segments;
+            I.n_vertices = jobs[k].n_vertices;
+            I.segs_per_strand = jobs[k].segs;
+            I.grid = jobs[k].grid;
+            I.densities = jobs[k].d_dens;
+            I.first_tile = (uint32_t)tile;
+            const uint64_t items = (kind == WK_INDEXED) ? jobs[k].n_segments : jobs[k].n_vertices;
+            tile += (items + kWalkThreads - 1) / kWalkThreads;
+        }
+        plan.count[grp] = (uint32_t)plan.order.size() - plan.first[grp];
+        plan.tiles[grp] = (uint32_t)tile;
     }
-    return (uint32_t)tile;
+    return plan;
+}
+
+// Launch the walk (or splat) of every instance in the uploaded table.  MODE as in kernels.cuh.
+template <int MODE>
+int launch_walk(vkhr_b200_ctx* ctx, const TablePlan& plan, bool vertices_mode, bool exact, cudaStream_t s) {
+    const InstanceDev* table = static_cast<const InstanceDev*>(ctx->table.p);
+    if (plan.tiles[0]) {
+        const InstanceDev* t0 = table + plan.first[0];
+        if (exact) k_walk_uniform<MODE, 1><<<plan.tiles[0], kWalkThreads, 0, s>>>(t0, plan.count[0]);
+        else       k_walk_uniform<MODE, 0><<<plan.tiles[0], kWalkThreads, 0, s>>>(t0, plan.count[0]);
+        ctx->launches++;
+    }
+    if (plan.tiles[1]) {
+        const InstanceDev* t1 = table + plan.first[1];
+        if (vertices_mode) {
+            if (exact) k_splat_batch<MODE, 1><<<plan.tiles[1], kWalkThreads, 0, s>>>(t1, plan.count[1]);
+            else       k_splat_batch<MODE, 0><<<plan.tiles[1], kWalkThreads, 0, s>>>(t1, plan.count[1]);
+        } else {
+            if (exact) k_walk_indexed<MODE, 1><<<plan.tiles[1], kWalkThreads, 0, s>>>(t1, plan.count[1]);
+            else       k_walk_indexed<MODE, 0><<<plan.tiles[1], kWalkThreads, 0, s>>>(t1, plan.count[1]);
+        }
+        ctx->launches++;
+    }
+    CU_CHECK(ctx, cudaGetLastError());
+    return VKHR_B200_OK;
 }
 
 template <bool VERTICES>
@@ -292,6 +360,7 @@ int launch_repair(vkhr_b200_ctx* ctx, uint32_t n, uint32_t* scratch, cudaStream_
 int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_mode, uint32_t flags, cudaStream_t s) {
     if (n == 0) return VKHR_B200_OK;
     const uint64_t nv = jobs[0].grid.n_voxels;
+    const bool exact = (flags & VKHR_B200_INDEX_EXACT) != 0;
     bool packed = true;
     for (uint32_t k = 0; k < n; ++k) packed = packed && packed_ok(jobs[k]);
     if (flags & VKHR_B200_STRATEGY_COUNT32) packed = false;
@@ -304,7 +373,7 @@ int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_
         RET_IF(reserve(ctx, ctx->bitmap, (size_t)n * (bm_words + 4) * 4));
         RET_IF(reserve(ctx, ctx->counts, nv * 4));
         ctx->counts_clean_bytes = 0;                   // the recount may leave entries behind
-        const uint32_t tiles = fill_table(ctx, jobs, n, vertices_mode);
+        const TablePlan plan = fill_table(ctx, jobs, n, vertices_mode);
         uint32_t* base = static_cast<uint32_t*>(ctx->bitmap.p);
         for (uint32_t k = 0; k < n; ++k) {
             ctx->host_table[k].ovf_flag = base + (size_t)k * (bm_words + 4);
@@ -317,19 +386,18 @@ int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_
         {
             PhaseMark m(ctx, s, PH_CLEAR);
             k_clear_packed_batch<<<dim3(gx, n), 256, 0, s>>>(table);
+            ctx->launches++;
         }
-        if (tiles) {
-            PhaseMark m(ctx, s, PH_WALK);
-            if (vertices_mode) k_splat_batch<1><<<tiles, kWalkThreads, 0, s>>>(table, n);
-            else               k_walk_batch<1><<<tiles, kWalkThreads, 0, s>>>(table, n);
-        }
-        ctx->launches += tiles ? 2 : 1;
-        CU_CHECK(ctx, cudaGetLastError());
-        if (tiles) {
+        if (plan.tiles[0] + plan.tiles[1]) {
+            {
+                PhaseMark m(ctx, s, PH_WALK);
+                RET_IF(launch_walk<1>(ctx, plan, vertices_mode, exact, s));
+            }
             PhaseMark m(ctx, s, PH_FINISH);
             if (vertices_mode) RET_IF(launch_repair<true>(ctx, n, static_cast<uint32_t*>(ctx->counts.p), s));
             else               RET_IF(launch_repair<false>(ctx, n, static_cast<uint32_t*>(ctx->counts.p), s));
         }
+        CU_CHECK(ctx, cudaGetLastError());
     } else {
         // COUNT32 in chunks of instances bounded by a 1 GiB scratch budget
         const size_t per = nv * 4;
@@ -345,21 +413,22 @@ int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_
                 CU_CHECK(ctx, cudaMemsetAsync(ctx->counts.p, 0, per * m, s));
                 ctx->counts_clean_bytes = 0;           // until the ZERO clamp below has run
             }
-            const uint32_t tiles = fill_table(ctx, jobs + first, m, vertices_mode);
+            const TablePlan plan = fill_table(ctx, jobs + first, m, vertices_mode);
             for (uint32_t k = 0; k < m; ++k)
                 ctx->host_table[k].counts = static_cast<uint32_t*>(ctx->counts.p) + (size_t)k * nv;
             RET_IF(upload_table(ctx, s));
-            const InstanceDev* table = static_cast<const InstanceDev*>(ctx->table.p);
-            if (tiles) {
+            {
                 PhaseMark mk(ctx, s, PH_WALK);
-                if (vertices_mode) k_splat_batch<0><<<tiles, kWalkThreads, 0, s>>>(table, m);
-                else               k_walk_batch<0><<<tiles, kWalkThreads, 0, s>>>(table, m);
-                ctx->launches++;
+                RET_IF(launch_walk<0>(ctx, plan, vertices_mode, exact, s));
             }
             PhaseMark mk(ctx, s, PH_FINISH);
-            for (uint32_t k = 0; k < m; ++k) {
-                k_clamp_counts<true><<<stride_blocks(ctx, nv / 16 + 1, 256, 8), 256, 0, s>>>(
-                    static_cast<uint32_t*>(ctx->counts.p) + (size_t)k * nv, nv, jobs[first + k].d_dens);
+            for (uint32_t k = 0; k < m; ++k) {          // table slot k holds job plan.order[k]
+                uint32_t* c = static_cast<uint32_t*>(ctx->counts.p) + (size_t)k * nv;
+                uint8_t* d = jobs[first + plan.order[k]].d_dens;
+                if ((reinterpret_cast<uintptr_t>(d) & 15u) == 0 && ((size_t)k * nv) % 4 == 0)
+                    k_clamp_counts<true><<<stride_blocks(ctx, nv / 16 + 1, 256, 8), 256, 0, s>>>(c, nv, d);
+                else
+                    k_clamp_counts_unaligned<true><<<stride_blocks(ctx, nv, 256, 16), 256, 0, s>>>(c, nv, d);
                 ctx->launches++;
             }
             CU_CHECK(ctx, cudaGetLastError());
@@ -371,6 +440,16 @@ int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_
         for (uint32_t k = 0; k < n; ++k) RET_IF(vkhr_b200_normalize_dev(ctx, jobs[k].d_dens, nv, s));
     }
     return VKHR_B200_OK;
+}
+
+// ADD the hits of one shard into a caller-owned u32 grid (the multi-GPU partial).
+int run_count(vkhr_b200_ctx* ctx, const Job& j, bool vertices_mode, uint32_t flags, uint32_t* d_counts, cudaStream_t s) {
+    const TablePlan plan = fill_table(ctx, &j, 1, vertices_mode);
+    if (plan.tiles[0] + plan.tiles[1] == 0) return VKHR_B200_OK;
+    ctx->host_table[0].counts = d_counts;
+    RET_IF(upload_table(ctx, s));
+    PhaseMark mk(ctx, s, PH_WALK);
+    return launch_walk<0>(ctx, plan, vertices_mode, (flags & VKHR_B200_INDEX_EXACT) != 0, s);
 }
 
 int stage_in(vkhr_b200_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
@@ -475,6 +554,24 @@ int vkhr_b200_profile_read(vkhr_b200_ctx* ctx, double ms_out[4], uint32_t spans_
     return VKHR_B200_OK;
 }
 
+int vkhr_b200_selftest_division(vkhr_b200_ctx* ctx, float divisor, uint64_t n_trials, uint64_t seed, uint64_t* mismatches) {
+    RET_IF(bind(ctx));
+    if (!mismatches || !(divisor > 0.0f) || !std::isfinite(divisor))
+        return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "divisor must be finite and > 0");
+    unsigned long long* d_bad = reinterpret_cast<unsigned long long*>(static_cast<uint32_t*>(ctx->small.p) + 32);
+    CU_CHECK(ctx, cudaMemsetAsync(d_bad, 0, 8, ctx->stream));
+    const float y = (divisor >= 9.094947e-13f && divisor <= 1.0995116e12f) ? 1.0f / divisor : 0.0f;
+    const unsigned blocks = ctx->sm_count * 16, threads = 256;
+    const uint64_t per = (n_trials + (uint64_t)blocks * threads - 1) / ((uint64_t)blocks * threads);
+    k_selftest_division<<<blocks, threads, 0, ctx->stream>>>(divisor, y, seed, (uint32_t)per, d_bad);
+    ctx->launches++;
+    unsigned long long bad = 0;
+    CU_CHECK(ctx, cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    *mismatches = bad;
+    return VKHR_B200_OK;
+}
+
 // ---- device-pointer API -----------------------------------------------------
 int vkhr_b200_voxelize_segments_dev(vkhr_b200_ctx* ctx, const float* d_vertices, uint32_t n_vertices,
                                     const uint32_t* d_indices, uint64_t n_indices, uint32_t segs_per_strand,
@@ -540,15 +637,7 @@ int vkhr_b200_count_segments_dev(vkhr_b200_ctx* ctx, const float* d_vertices, ui
     RET_IF(make_grid(ctx, aabb_origin, aabb_size, W, H, D, flags, j.grid));
     RET_IF(segment_count(ctx, d_indices, n_indices, n_vertices, segs_per_strand, j.n_segments));
     j.d_vertices = d_vertices; j.d_indices = d_indices; j.n_vertices = n_vertices; j.segs = segs_per_strand;
-    cudaStream_t s = pick(ctx, stream);
-    const uint32_t tiles = fill_table(ctx, &j, 1, false);
-    if (!tiles) return VKHR_B200_OK;
-    ctx->host_table[0].counts = d_counts_inout;
-    RET_IF(upload_table(ctx, s));
-    k_walk_batch<0><<<tiles, kWalkThreads, 0, s>>>(static_cast<const InstanceDev*>(ctx->table.p), 1);
-    ctx->launches++;
-    CU_CHECK(ctx, cudaGetLastError());
-    return VKHR_B200_OK;
+    return run_count(ctx, j, false, flags, d_counts_inout, pick(ctx, stream));
 }
 
 int vkhr_b200_count_vertices_dev(vkhr_b200_ctx* ctx, const float* d_vertices, uint32_t n_vertices,
@@ -562,14 +651,7 @@ int vkhr_b200_count_vertices_dev(vkhr_b200_ctx* ctx, const float* d_vertices, ui
     Job j{};
     RET_IF(make_grid(ctx, aabb_origin, aabb_size, W, H, D, flags, j.grid));
     j.d_vertices = d_vertices; j.n_vertices = n_vertices;
-    cudaStream_t s = pick(ctx, stream);
-    const uint32_t tiles = fill_table(ctx, &j, 1, true);
-    ctx->host_table[0].counts = d_counts_inout;
-    RET_IF(upload_table(ctx, s));
-    k_splat_batch<0><<<tiles, kWalkThreads, 0, s>>>(static_cast<const InstanceDev*>(ctx->table.p), 1);
-    ctx->launches++;
-    CU_CHECK(ctx, cudaGetLastError());
-    return VKHR_B200_OK;
+    return run_count(ctx, j, true, flags, d_counts_inout, pick(ctx, stream));
 }
 
 int vkhr_b200_clamp_counts_dev(vkhr_b200_ctx* ctx, const uint32_t* d_counts, uint64_t n_voxels, uint32_t flags,

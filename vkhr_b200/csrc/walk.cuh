@@ -24,7 +24,33 @@ struct GridParams {
     uint32_t W, H, D;
     uint32_t n_voxels;         // W*H*D  (< 2^32, checked on the host)
     uint32_t index_exact;      // VKHR_B200_INDEX_EXACT
+    float rvx, rvy, rvz;       // RN(1 / voxel_size), or 0 when the fast exact division must not be used
 };
+
+// Correctly rounded a / d for d > 0, given y = RN(1/d) (0 = not available).
+//
+// Markstein's sequence: q0 = RN(a*y); r0 = a - q0*d (FMA); q1 = RN(q0 + r0*y)
+// is a faithful quotient, and one more exact-remainder correction
+// q2 = RN(q1 + (a - q1*d)*y) is then the correctly rounded quotient RN(a/d)
+// (Markstein 1990; Muller et al., Handbook of Floating-Point Arithmetic,
+// "division with an FMA") whenever y is the correctly rounded reciprocal and
+// nothing over/underflows.  The guard keeps |a| in [2^-60, 2^60] (the host
+// keeps d in [2^-40, 2^40]), zero keeps its sign (d > 0), and everything else
+// -- NaN, infinities, tiny values -- takes the IEEE division instruction
+// sequence.  tests/test_parity_gpu.py::test_fast_division_is_exact compares
+// this bit for bit with __fdiv_rn on billions of operands.
+__device__ __forceinline__ float div_exact(float a, float d, float y) {
+    const float aa = fabsf(a);
+    if (y != 0.0f && aa >= 8.6736174e-19f && aa <= 1.1529215e18f) {
+        const float q0 = __fmul_rn(a, y);
+        const float r0 = __fmaf_rn(-q0, d, a);
+        const float q1 = __fmaf_rn(r0, y, q0);
+        const float r1 = __fmaf_rn(-q1, d, a);
+        return __fmaf_rn(r1, y, q1);
+    }
+    if (a == 0.0f) return a;
+    return __fdiv_rn(a, d);
+}
 
 // glm::max(a,b) = (a < b) ? b : a ; glm::min(a,b) = (b < a) ? b : a
 // (foreign/glm/glm/detail/func_common.inl:16-29) -- NaN behaviour included.
@@ -34,12 +60,13 @@ __device__ __forceinline__ float glm_min(float a, float b) { return (b < a) ? b 
 // Voxel of a point already in voxel space: min(floor(p), res-1), then the
 // linear index.  Returns false when the sample must be dropped (index NaN,
 // negative or >= W*H*D: undefined behaviour in the reference).
+template <int EXACT = -1>      // -1: decided at run time from g.index_exact
 __device__ __forceinline__ bool voxel_index(const GridParams& g, float px, float py, float pz,
                                             uint32_t& idx) {
     float vx = glm_min(floorf(px), g.rx1);
     float vy = glm_min(floorf(py), g.ry1);
     float vz = glm_min(floorf(pz), g.rz1);
-    if (!g.index_exact) {
+    if (EXACT == 0 || (EXACT < 0 && !g.index_exact)) {
         // voxel.x + voxel.y*width + voxel.z*width*height, all in fp32 (hair_style.cc:276,:321)
         float a = __fmul_rn(vy, g.Wf);
         float b = __fmul_rn(vz, g.Wf);
@@ -60,35 +87,46 @@ __device__ __forceinline__ bool voxel_index(const GridParams& g, float px, float
 }
 
 // (v - origin) / voxel_size, per component (hair_style.cc:274, :312-313).
-__device__ __forceinline__ float to_voxel_space(float v, float o, float vs) {
-    return __fdiv_rn(__fsub_rn(v, o), vs);
+__device__ __forceinline__ float to_voxel_space(float v, float o, float vs, float rvs) {
+    return div_exact(__fsub_rn(v, o), vs, rvs);
 }
 
-// The sampled line walk of one segment (hair_style.cc:312-328).  `sink(idx)` is
-// called once per sample that lands inside the grid.
-template <class Sink>
-__device__ __forceinline__ void walk_segment(const GridParams& g,
-                                             float ax, float ay, float az,
-                                             float bx, float by, float bz, Sink&& sink) {
-    float rx = to_voxel_space(ax, g.ox, g.vsx);
-    float ry = to_voxel_space(ay, g.oy, g.vsy);
-    float rz = to_voxel_space(az, g.oz, g.vsz);
-    float dx = __fsub_rn(to_voxel_space(bx, g.ox, g.vsx), rx);
-    float dy = __fsub_rn(to_voxel_space(by, g.oy, g.vsy), ry);
-    float dz = __fsub_rn(to_voxel_space(bz, g.oz, g.vsz), rz);
+// The sampled line walk of one segment whose end points are already in voxel
+// space (hair_style.cc:315-328).  `sink(idx)` is called once per sample that
+// lands inside the grid.
+template <int EXACT = -1, class Sink>
+__device__ __forceinline__ void walk_voxel_space(const GridParams& g,
+                                                 float rx, float ry, float rz,
+                                                 float tx, float ty, float tz, Sink&& sink) {
+    float dx = __fsub_rn(tx, rx);
+    float dy = __fsub_rn(ty, ry);
+    float dz = __fsub_rn(tz, rz);
     float steps = glm_max(glm_max(fabsf(dx), fabsf(dy)), fabsf(dz));     // compMax(abs(direction))
     if (!(steps > 0.0f) || !(steps < 16777216.0f)) return;               // 0 / NaN: no samples; >= 2^24: reference never ends
-    dx = __fdiv_rn(dx, steps);
-    dy = __fdiv_rn(dy, steps);
-    dz = __fdiv_rn(dz, steps);
+    // direction /= steps: three IEEE divisions by the same divisor (hair_style.cc:317)
+    const float y = (steps >= 9.094947e-13f) ? __frcp_rn(steps) : 0.0f;   // RN(1/steps); tiny steps: plain division
+    dx = div_exact(dx, steps, y);
+    dy = div_exact(dy, steps, y);
+    dz = div_exact(dz, steps, y);
     do {                                                                  // while (steps-- > 0.0f)
         uint32_t idx;
-        if (voxel_index(g, rx, ry, rz, idx)) sink(idx);
+        if (voxel_index<EXACT>(g, rx, ry, rz, idx)) sink(idx);
         rx = __fadd_rn(rx, dx);
         ry = __fadd_rn(ry, dy);
         rz = __fadd_rn(rz, dz);
         steps = __fsub_rn(steps, 1.0f);
     } while (steps > 0.0f);
+}
+
+// The same from world-space vertices (hair_style.cc:312-313 first).
+template <int EXACT = -1, class Sink>
+__device__ __forceinline__ void walk_segment(const GridParams& g,
+                                             float ax, float ay, float az,
+                                             float bx, float by, float bz, Sink&& sink) {
+    walk_voxel_space<EXACT>(g,
+        to_voxel_space(ax, g.ox, g.vsx, g.rvx), to_voxel_space(ay, g.oy, g.vsy, g.rvy), to_voxel_space(az, g.oz, g.vsz, g.rvz),
+        to_voxel_space(bx, g.ox, g.vsx, g.rvx), to_voxel_space(by, g.oy, g.vsy, g.rvy), to_voxel_space(bz, g.oz, g.vsz, g.rvz),
+        sink);
 }
 
 // Vertex pair of segment `s`.  indices == nullptr => uniform strands of

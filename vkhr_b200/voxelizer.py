@@ -73,6 +73,12 @@ class Voxelizer:
         names = ("clear", "walk", "finish", "normalize")
         return {k: {"ms": ms[i], "spans": int(n[i])} for i, k in enumerate(names)}
 
+    def selftest_division(self, divisor: float, n_trials: int = 1 << 26, seed: int = 1) -> int:
+        """Mismatches between the kernels' fast exact division and the IEEE division (must be 0)."""
+        bad = C.c_uint64(0)
+        capi.check(self._h, lib.vkhr_b200_selftest_division(self._h, float(divisor), int(n_trials), int(seed), C.byref(bad)))
+        return int(bad.value)
+
     def synchronize(self) -> None:
         capi.check(self._h, lib.vkhr_b200_synchronize(self._h))
 
@@ -131,8 +137,10 @@ class Voxelizer:
     def _torch_stream(self, stream):
         import torch
         if stream is None:
-            return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        return C.c_void_p(int(stream))
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        # handle 0 is torch's legacy default stream; the C ABI reads NULL as "the context's own stream",
+        # so name the legacy stream explicitly (cudaStreamLegacy == 1)
+        return C.c_void_p(int(stream) or 1)
 
     def _check_dev(self, t, dtype, name):
         import torch
