@@ -12,7 +12,7 @@ timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.json 2> gpu
 if [ "$1" = "ncu" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 2 --warmup 3 --instances 8 --no-e2e --no-cpu > gpurun_out/ncu_bench.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_walk_batch -s 2 -c 2 -o gpurun_out/prof_walk -f \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_walk_uniform -s 2 -c 2 -o gpurun_out/prof_walk -f \
       python bench.py --steps 1 --warmup 3 --instances 8 --no-e2e --no-cpu > gpurun_out/ncu_full.log 2>&1
 fi
 ls -la gpurun_out

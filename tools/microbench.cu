@@ -31,6 +31,47 @@ __global__ void k_atomics(uint32_t* grid, uint32_t mask, uint32_t per_thread, ui
     if (acc == 0xDEADBEEF) *sink = acc;
 }
 
+// Atomic throughput when only `active` of the 32 lanes of each warp take part (divergent sample loops).
+__global__ void k_atomics_partial(uint32_t* grid, uint32_t mask, uint32_t per_thread, uint32_t active, uint32_t* sink) {
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((threadIdx.x & 31u) >= active) return;
+    uint32_t acc = 0;
+    for (uint32_t i = 0; i < per_thread; ++i) {
+        uint32_t h = hash32(tid * 0x9E3779B9u + i * 0x85EBCA6Bu) & mask;
+        uint32_t sh = (h & 3u) * 8u; uint32_t old = atomicAdd(grid + (h >> 2), 1u << sh); if (((old >> sh) & 0xFF) == 0xFF) acc |= 1u;
+    }
+    if (acc == 0xDEADBEEF) *sink = acc;
+}
+
+// Same total work, but each atomic is separated by `pad` dependent FMAs (models the per-sample arithmetic).
+__global__ void k_atomics_padded(uint32_t* grid, uint32_t mask, uint32_t per_thread, uint32_t pad, uint32_t* sink) {
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t acc = 0; float f = (float)tid;
+    for (uint32_t i = 0; i < per_thread; ++i) {
+        for (uint32_t k = 0; k < pad; ++k) f = f * 1.0000001f + 0.5f;
+        uint32_t h = hash32(tid * 0x9E3779B9u + i * 0x85EBCA6Bu + (uint32_t)f) & mask;
+        uint32_t sh = (h & 3u) * 8u; uint32_t old = atomicAdd(grid + (h >> 2), 1u << sh); if (((old >> sh) & 0xFF) == 0xFF) acc |= 1u;
+    }
+    if (acc == 0xDEADBEEF) *sink = acc;
+}
+
+// Sector locality: the 32 lanes of a warp instruction hit 32/K random 32-byte sectors, K lanes per sector
+// (distinct words for K <= 8; K = 16/32 put 2/4 lanes on each word, different bytes).
+__global__ void k_atomics_grouped(uint32_t* grid, uint32_t mask_sectors, uint32_t per_thread, uint32_t K, uint32_t* sink) {
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t lane = threadIdx.x & 31u, warp = tid >> 5;
+    uint32_t acc = 0;
+    for (uint32_t i = 0; i < per_thread; ++i) {
+        uint32_t sector = hash32((warp * 32u + lane / K) * 0x9E3779B9u + i * 0x85EBCA6Bu) & mask_sectors;
+        uint32_t slot = lane % K;                       // position inside the sector
+        uint32_t word = sector * 8u + (slot & 7u);
+        uint32_t sh = ((slot >> 3) & 3u) * 8u;
+        uint32_t old = atomicAdd(grid + word, 1u << sh);
+        if (((old >> sh) & 0xFF) == 0xFF) acc |= 1u;
+    }
+    if (acc == 0xDEADBEEF) *sink = acc;
+}
+
 __global__ void k_smem_atomics(uint32_t per_thread, uint32_t words, uint32_t* sink) {
     extern __shared__ uint32_t s[];
     for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) s[i] = 0;
@@ -83,6 +124,25 @@ int main() {
         float l2 = time_ms([&] { k_atomics<2, 1><<<blocks, threads>>>(grid, mask, per, sink); }, 5);
         printf(" \"atomics_%s\": {\"red_random_Gops\": %.2f, \"atom_random_Gops\": %.2f, \"atom_packed8_random_Gops\": %.2f, \"red_local_Gops\": %.2f, \"atom_packed8_local_Gops\": %.2f},\n",
                sz.name, nops / r0 / 1e6, nops / r1 / 1e6, nops / r2 / 1e6, nops / l0 / 1e6, nops / l2 / 1e6);
+    }
+    {
+        uint32_t mask = (uint32_t)((16u << 20) - 1);   // 16 MiB of packed bytes
+        for (uint32_t active : {32u, 24u, 16u, 8u, 4u, 1u}) {
+            float r = time_ms([&] { k_atomics_partial<<<blocks, threads>>>(grid, mask, per, active, sink); }, 5);
+            printf(" \"atom_packed8_active%u_of_32\": {\"Gops\": %.2f, \"Ginstr\": %.3f},\n", active, nops * active / 32 / r / 1e6, nops / 32 / r / 1e6);
+        }
+        for (uint32_t K : {1u, 2u, 4u, 8u, 16u, 32u}) {
+            float r = time_ms([&] { k_atomics_grouped<<<blocks, threads>>>(grid, (16u << 20) / 32 - 1, per, K, sink); }, 5);
+            printf(" \"atom_packed8_%u_lanes_per_sector\": {\"Gops\": %.2f},\n", K, nops / r / 1e6);
+        }
+        for (uint32_t pad : {0u, 32u}) {
+            float r = time_ms([&] { k_atomics_padded<<<blocks, threads>>>(grid, mask, per, pad, sink); }, 5);
+            printf(" \"atom_packed8_pad%u_fma\": {\"Gops\": %.2f},\n", pad, nops / r / 1e6);
+        }
+        for (int bl : {148 * 2, 148 * 4, 148 * 8, 148 * 16, 148 * 32}) {
+            float r = time_ms([&] { k_atomics<2, 0><<<bl, threads>>>(grid, mask, per * 4, sink); }, 5);
+            printf(" \"atom_packed8_blocks%d\": {\"Gops\": %.2f},\n", bl, (double)threads * bl * per * 4 / r / 1e6);
+        }
     }
     {
         const uint32_t words = 8192;   // 32 KB

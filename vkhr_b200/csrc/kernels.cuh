@@ -13,6 +13,9 @@ namespace vkhr_b200 {
 
 constexpr int kWalkThreads = 256;
 
+// How an instance's work is tiled over CTAs.
+enum WalkKind : uint32_t { WK_UNIFORM = 0, WK_INDEXED = 1, WK_SPLAT = 2 };
+
 // Device-side description of one instance of a batch.
 struct InstanceDev {
     const float*    vertices;
@@ -22,12 +25,25 @@ struct InstanceDev {
     uint32_t        segs_per_strand;
     GridParams      grid;
     uint8_t*        densities;      // W*H*D u8 (PACKED8: counted in place)
-    uint32_t*       counts;         // W*H*D u32 (COUNT32) or nullptr
+    uint32_t*       counts;         // W*H*D u32 (COUNT32 / recount scratch) or nullptr
     uint32_t*       ovf_bitmap;     // PACKED8: 1 bit per 32-bit word of `densities`
     uint32_t*       ovf_flag;       // PACKED8: != 0 when any word overflowed
-    uint32_t        first_tile;     // first CTA tile of this instance in the flat batch grid
+    uint32_t        n_tiles;        // CTAs (of kWalkThreads items) this instance needs
+    uint32_t        kind;           // WalkKind
+    uint32_t        vps_magic;      // floor(2^32 / (segs_per_strand + 1)) + 1   (strand-end test without a division)
     uint32_t        pad;
 };
+
+// A batch travels to the kernels as a __grid_constant__ parameter: every per-instance constant is then
+// read through the constant cache, not through L1TEX (which the atomics need), and no table upload
+// precedes the launch.  blockIdx.y selects the instance.
+constexpr uint32_t kMaxBatch = 64;
+struct Batch {
+    uint32_t n;
+    uint32_t pad[3];
+    InstanceDev inst[kMaxBatch];
+};
+static_assert(sizeof(Batch) <= 16 * 1024, "kernel parameter space");
 
 // ---------------------------------------------------------------------------
 // Sinks: what one sample does to the grid.
@@ -36,7 +52,8 @@ struct InstanceDev {
 // COUNT32: plain u32 hit counter, clamped later.  `red.global.add.u32` (no return).
 struct SinkCount32 {
     uint32_t* counts;
-    __device__ __forceinline__ void operator()(uint32_t idx) { atomicAdd(counts + idx, 1u); }
+    template <int SLOT = 0>
+    __device__ __forceinline__ void put(uint32_t idx) { atomicAdd(counts + idx, 1u); }
     __device__ __forceinline__ void finish() {}
 };
 
@@ -46,27 +63,33 @@ struct SinkCount32 {
 // 255).  The first carry in a word is always seen on a clean word, so a word
 // is flagged in the bitmap if and only if one of its voxels received more
 // than 255 hits; flagged words are recounted exactly by k_repair_packed.
-// The returned word is examined one sample later, just before the next atomic
-// is issued, so the round trip overlaps the next sample's arithmetic.
+// Returned words are examined kDepth samples later (a ring of kDepth pending
+// results in registers, slot chosen at compile time by the unrolled walk), so
+// up to kDepth atomics of a thread are in flight and their round trips overlap
+// the arithmetic of the following samples.
 struct SinkPacked8 {
+    static constexpr int kDepth = 4;
     uint32_t* words;
     uint32_t* ovf_bitmap;
     uint32_t* ovf_flag;
-    uint32_t pend_old = 0, pend_sh = 0, pend_w = 0;
+    uint32_t pend_old[kDepth] = {0, 0, 0, 0};
+    uint32_t pend_idx[kDepth] = {0, 0, 0, 0};
+    template <int SLOT>
     __device__ __forceinline__ void check() {
-        if (((pend_old >> pend_sh) & 0xFFu) == 0xFFu) {
-            atomicOr(ovf_bitmap + (pend_w >> 5), 1u << (pend_w & 31u));
+        // byte (idx & 3) of the word as it was before this thread's add
+        if (__byte_perm(pend_old[SLOT], 0u, 0x4440u | (pend_idx[SLOT] & 3u)) == 0xFFu) {
+            const uint32_t w = pend_idx[SLOT] >> 2;
+            atomicOr(ovf_bitmap + (w >> 5), 1u << (w & 31u));
             *ovf_flag = 1u;
         }
     }
-    __device__ __forceinline__ void operator()(uint32_t idx) {
-        const uint32_t w = idx >> 2, sh = (idx & 3u) * 8u;
-        check();
-        pend_old = atomicAdd(words + w, 1u << sh);
-        pend_sh = sh;
-        pend_w = w;
+    template <int SLOT = 0>
+    __device__ __forceinline__ void put(uint32_t idx) {
+        check<SLOT>();
+        pend_old[SLOT] = atomicAdd(words + (idx >> 2), 1u << ((idx & 3u) * 8u));
+        pend_idx[SLOT] = idx;
     }
-    __device__ __forceinline__ void finish() { check(); }
+    __device__ __forceinline__ void finish() { check<0>(); check<1>(); check<2>(); check<3>(); }
 };
 
 // Recount pass of PACKED8: only samples landing in flagged words are counted,
@@ -74,7 +97,8 @@ struct SinkPacked8 {
 struct SinkRecount {
     const uint32_t* ovf_bitmap;
     uint32_t* counts;
-    __device__ __forceinline__ void operator()(uint32_t idx) {
+    template <int SLOT = 0>
+    __device__ __forceinline__ void put(uint32_t idx) {
         const uint32_t w = idx >> 2;
         if ((__ldg(ovf_bitmap + (w >> 5)) >> (w & 31u)) & 1u) atomicAdd(counts + idx, 1u);
     }
@@ -85,77 +109,82 @@ template <int MODE> struct SinkOf;
 template <> struct SinkOf<0> { using type = SinkCount32;
     __device__ static type make(const InstanceDev& I) { return SinkCount32{I.counts}; } };
 template <> struct SinkOf<1> { using type = SinkPacked8;
-    __device__ static type make(const InstanceDev& I) { return SinkPacked8{reinterpret_cast<uint32_t*>(I.densities), I.ovf_bitmap, I.ovf_flag}; } };
+    __device__ static type make(const InstanceDev& I) { SinkPacked8 k; k.words = reinterpret_cast<uint32_t*>(I.densities); k.ovf_bitmap = I.ovf_bitmap; k.ovf_flag = I.ovf_flag; return k; } };
 template <> struct SinkOf<2> { using type = SinkRecount;
     __device__ static type make(const InstanceDev& I) { return SinkRecount{I.ovf_bitmap, I.counts}; } };
-
-// Instance owning flat tile `tile` (binary search over first_tile; n_inst is small).
-__device__ __forceinline__ uint32_t find_instance(const InstanceDev* __restrict__ inst, uint32_t n_inst, uint32_t tile) {
-    uint32_t lo = 0, hi = n_inst - 1;
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi + 1) >> 1;
-        if (__ldg(&inst[mid].first_tile) <= tile) lo = mid; else hi = mid - 1;
-    }
-    return lo;
-}
 
 // ---------------------------------------------------------------------------
 // Walk kernel for uniform strands (no index buffer): the hot kernel.
 //
-// A CTA owns 256 consecutive vertex slots of one instance.  Its 257 vertices
-// (3084 contiguous bytes) are fetched with 193 coalesced 16-byte loads into
-// shared memory; thread t moves vertex t to voxel space ONCE (three exact
-// divisions), publishes it through shared memory, and walks the segment
-// (vertex t, vertex t+1) unless vertex t is the last of its strand.  Vertices
-// are read from HBM exactly once and no per-thread strided global loads or
-// per-iteration parameter loads remain on the L1TEX path -- only the atomics.
+// Warp-autonomous and barrier-free.  A warp-tile is 32 consecutive vertices
+// (96 floats, three fully coalesced 128-byte requests); lane t moves vertex t to
+// voxel space ONCE (three exact divisions), receives vertex t+1 from lane t+1
+// by shuffle and walks the segment (t, t+1) unless t is the last vertex of its
+// strand; lane 31 only supplies the tip of lane 30, so consecutive tiles overlap
+// by one vertex (tile stride 31).  Each warp walks kTilesPerWarp tiles and
+// fetches the next tile's floats into registers before walking the current one,
+// so the HBM latency of the vertex stream hides behind the walk.  Vertices are
+// read from HBM once (1/31 twice); per-instance constants come from the constant
+// bank (the batch is a __grid_constant__ parameter); the L1TEX path carries only
+// the vertex stream and the atomics.  blockIdx.y = instance.
 // MODE 0 = COUNT32, 1 = PACKED8, 2 = recount of flagged words.
 // ---------------------------------------------------------------------------
+constexpr uint32_t kTilesPerWarp = 8;
+constexpr uint32_t kWarpsPerBlock = kWalkThreads / 32;
+constexpr uint32_t kTileStride = 31;          // segments (= new vertices) per warp-tile
+
 template <int MODE, int EXACT>
 __global__ void __launch_bounds__(kWalkThreads)
-k_walk_uniform(const InstanceDev* __restrict__ inst, uint32_t n_inst) {
-    __shared__ __align__(16) float s_raw[4 * 194];
-    __shared__ float s_pos[3 * 257 + 3];
-    const uint32_t t = threadIdx.x;
-    const InstanceDev& I = inst[find_instance(inst, n_inst, blockIdx.x)];
+k_walk_uniform(const __grid_constant__ Batch B) {
+    __shared__ float s_raw[kWarpsPerBlock][96];
+    const InstanceDev& I = B.inst[blockIdx.y];
+    if (blockIdx.x >= I.n_tiles || I.kind != WK_UNIFORM) return;   // n_tiles counts CTAs
     if (MODE == 2 && *I.ovf_flag == 0u) return;
-    const GridParams g = I.grid;                                  // by value: stays in registers
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const GridParams& g = I.grid;
     const uint32_t n_vertices = I.n_vertices;
-    const uint32_t v0 = (blockIdx.x - I.first_tile) * kWalkThreads;   // first vertex slot of this tile
-    const uint32_t cnt = min(257u, n_vertices - v0);              // vertices this tile can see
-    const uint32_t n_floats = 3u * cnt;
-    const float* __restrict__ src = I.vertices + 3ull * v0;       // tile stride 3072 B: aligned iff the base is
-    if ((reinterpret_cast<uintptr_t>(I.vertices) & 15u) == 0) {
-        if (t < 193u) {
-            if (4u * t + 4u <= n_floats) {
-                reinterpret_cast<uint4*>(s_raw)[t] = __ldg(reinterpret_cast<const uint4*>(src) + t);
-            } else {
-                for (uint32_t k = 4u * t; k < n_floats; ++k) s_raw[k] = __ldg(src + k);
-            }
-        }
-    } else {                                                      // unaligned vertex buffer: scalar, still coalesced
-        for (uint32_t k = t; k < n_floats; k += kWalkThreads) s_raw[k] = __ldg(src + k);
-    }
-    __syncthreads();
-    float px = 0.f, py = 0.f, pz = 0.f;
-    if (t < cnt) {
-        px = to_voxel_space(s_raw[3 * t + 0], g.ox, g.vsx, g.rvx);
-        py = to_voxel_space(s_raw[3 * t + 1], g.oy, g.vsy, g.rvy);
-        pz = to_voxel_space(s_raw[3 * t + 2], g.oz, g.vsz, g.rvz);
-        s_pos[3 * t + 0] = px; s_pos[3 * t + 1] = py; s_pos[3 * t + 2] = pz;
-    }
-    if (t == 0 && cnt == 257u) {                                  // the tile's last tip vertex
-        s_pos[768] = to_voxel_space(s_raw[768], g.ox, g.vsx, g.rvx);
-        s_pos[769] = to_voxel_space(s_raw[769], g.oy, g.vsy, g.rvy);
-        s_pos[770] = to_voxel_space(s_raw[770], g.oz, g.vsz, g.rvz);
-    }
-    __syncthreads();
-    // vertex v0+t starts a segment unless it is the last vertex of its strand
+    const uint32_t n_floats = 3u * n_vertices;
+    const uint32_t n_warp_tiles = (n_vertices + kTileStride - 1u) / kTileStride;
     const uint32_t vps = I.segs_per_strand + 1u;
-    const bool starts_segment = (t + 1u < cnt) && ((v0 + t) % vps != vps - 1u);
-    if (!starts_segment) return;
+    const float* __restrict__ verts = I.vertices;
+    float* raw = s_raw[warp];
     auto sink = SinkOf<MODE>::make(I);
-    walk_voxel_space<EXACT>(g, px, py, pz, s_pos[3 * t + 3], s_pos[3 * t + 4], s_pos[3 * t + 5], sink);
+
+    uint32_t tile = (blockIdx.x * kWarpsPerBlock + warp) * kTilesPerWarp;
+    const uint32_t tile_end = min(tile + kTilesPerWarp, n_warp_tiles);
+    if (tile >= tile_end) return;
+    // this lane's three floats of the current tile (float f of the tile lives in lane f % 32, register f / 32)
+    float f0 = 0.f, f1 = 0.f, f2 = 0.f;
+    {
+        const uint32_t base = 3u * kTileStride * tile + lane;
+        if (base < n_floats) f0 = __ldg(verts + base);
+        if (base + 32u < n_floats) f1 = __ldg(verts + base + 32u);
+        if (base + 64u < n_floats) f2 = __ldg(verts + base + 64u);
+    }
+    for (; tile < tile_end; ++tile) {
+        raw[lane] = f0; raw[lane + 32u] = f1; raw[lane + 64u] = f2;
+        if (tile + 1u < tile_end) {                               // prefetch the next tile into registers
+            const uint32_t base = 3u * kTileStride * (tile + 1u) + lane;
+            f0 = (base < n_floats) ? __ldg(verts + base) : 0.f;
+            f1 = (base + 32u < n_floats) ? __ldg(verts + base + 32u) : 0.f;
+            f2 = (base + 64u < n_floats) ? __ldg(verts + base + 64u) : 0.f;
+        }
+        __syncwarp();
+        const float px = to_voxel_space(raw[3u * lane + 0u], g.ox, g.vsx, g.rvx);
+        const float py = to_voxel_space(raw[3u * lane + 1u], g.oy, g.vsy, g.rvy);
+        const float pz = to_voxel_space(raw[3u * lane + 2u], g.oz, g.vsz, g.rvz);
+        __syncwarp();                                             // raw[] is rewritten by the next iteration
+        const float tx = __shfl_down_sync(0xFFFFFFFFu, px, 1);
+        const float ty = __shfl_down_sync(0xFFFFFFFFu, py, 1);
+        const float tz = __shfl_down_sync(0xFFFFFFFFu, pz, 1);
+        // vertex x starts a segment unless it is the last of its strand: x mod vps by multiply-high
+        // (the quotient estimate is exact or one too large)
+        const uint32_t x = kTileStride * tile + lane;
+        uint32_t r = x - __umulhi(x, I.vps_magic) * vps;
+        if ((int32_t)r < 0) r += vps;
+        if (lane < kTileStride && x + 1u < n_vertices && r != vps - 1u)
+            walk_voxel_space<EXACT>(g, px, py, pz, tx, ty, tz, sink);
+    }
     sink.finish();
 }
 
@@ -165,12 +194,13 @@ k_walk_uniform(const InstanceDev* __restrict__ inst, uint32_t n_inst) {
 // ---------------------------------------------------------------------------
 template <int MODE, int EXACT>
 __global__ void __launch_bounds__(kWalkThreads)
-k_walk_indexed(const InstanceDev* __restrict__ inst, uint32_t n_inst) {
-    const InstanceDev& I = inst[find_instance(inst, n_inst, blockIdx.x)];
+k_walk_indexed(const __grid_constant__ Batch B) {
+    const InstanceDev& I = B.inst[blockIdx.y];
+    if (blockIdx.x >= I.n_tiles || I.kind != WK_INDEXED) return;
     if (MODE == 2 && *I.ovf_flag == 0u) return;
-    const uint64_t s = (uint64_t)(blockIdx.x - I.first_tile) * kWalkThreads + threadIdx.x;
+    const uint64_t s = (uint64_t)blockIdx.x * kWalkThreads + threadIdx.x;
     if (s >= I.n_segments) return;
-    const GridParams g = I.grid;
+    const GridParams& g = I.grid;
     const uint2 pr = __ldg(reinterpret_cast<const uint2*>(I.indices) + s);
     const float* a = I.vertices + 3ull * pr.x;
     const float* b = I.vertices + 3ull * pr.y;
@@ -182,19 +212,20 @@ k_walk_indexed(const InstanceDev* __restrict__ inst, uint32_t n_inst) {
 // Vertex splat (voxelize_vertices): one thread per vertex.
 template <int MODE, int EXACT>
 __global__ void __launch_bounds__(kWalkThreads)
-k_splat_batch(const InstanceDev* __restrict__ inst, uint32_t n_inst) {
-    const InstanceDev& I = inst[find_instance(inst, n_inst, blockIdx.x)];
+k_splat_batch(const __grid_constant__ Batch B) {
+    const InstanceDev& I = B.inst[blockIdx.y];
+    if (blockIdx.x >= I.n_tiles || I.kind != WK_SPLAT) return;
     if (MODE == 2 && *I.ovf_flag == 0u) return;
-    const uint32_t i = (blockIdx.x - I.first_tile) * kWalkThreads + threadIdx.x;
+    const uint32_t i = blockIdx.x * kWalkThreads + threadIdx.x;
     if (i >= I.n_vertices) return;
-    const GridParams g = I.grid;
+    const GridParams& g = I.grid;
     const float* v = I.vertices + 3ull * i;
     uint32_t idx;
     if (!voxel_index<EXACT>(g, to_voxel_space(__ldg(v), g.ox, g.vsx, g.rvx), to_voxel_space(__ldg(v + 1), g.oy, g.vsy, g.rvy),
                             to_voxel_space(__ldg(v + 2), g.oz, g.vsz, g.rvz), idx))
         return;
     auto sink = SinkOf<MODE>::make(I);
-    sink(idx);
+    sink.template put<0>(idx);
     sink.finish();
 }
 
@@ -230,8 +261,8 @@ __global__ void __launch_bounds__(256) k_zero16(uint4* __restrict__ p, uint64_t 
 
 // PACKED8 clear for a batch: densities, overflow bitmap and flag of every instance.
 // blockIdx.y = instance.  n_voxels % 16 == 0 is guaranteed by the host (else COUNT32).
-__global__ void __launch_bounds__(256) k_clear_packed_batch(const InstanceDev* __restrict__ inst) {
-    const InstanceDev& I = inst[blockIdx.y];
+__global__ void __launch_bounds__(256) k_clear_packed_batch(const __grid_constant__ Batch B) {
+    const InstanceDev& I = B.inst[blockIdx.y];
     const uint4 z = make_uint4(0, 0, 0, 0);
     uint4* d = reinterpret_cast<uint4*>(I.densities);
     const uint32_t n16 = I.grid.n_voxels >> 4;

@@ -32,8 +32,10 @@ using namespace vkhr_b200;
 // ---------------------------------------------------------------------------
 template <bool VERTICES>
 __global__ void __launch_bounds__(kWalkThreads)
-k_repair_packed(const InstanceDev* __restrict__ inst, uint32_t n_inst, uint32_t* __restrict__ scratch) {
+k_repair_packed(const __grid_constant__ Batch B, uint32_t* __restrict__ scratch) {
     // common case first: no instance overflowed -> one parallel look at the flags and out
+    const uint32_t n_inst = B.n;
+    const InstanceDev* inst = B.inst;
     int any = 0;
     for (uint32_t k = threadIdx.x; k < n_inst; k += blockDim.x) any |= (*inst[k].ovf_flag != 0u);
     if (!__syncthreads_or(any)) return;                        // same answer in every CTA
@@ -64,7 +66,7 @@ k_repair_packed(const InstanceDev* __restrict__ inst, uint32_t n_inst, uint32_t*
                 uint32_t idx;
                 if (voxel_index(g, to_voxel_space(__ldg(v), g.ox, g.vsx, g.rvx), to_voxel_space(__ldg(v + 1), g.oy, g.vsy, g.rvy),
                                 to_voxel_space(__ldg(v + 2), g.oz, g.vsz, g.rvz), idx))
-                    sink(idx);
+                    sink.put<0>(idx);
             }
         } else if (I.indices) {
             for (uint64_t s = tid; s < I.n_segments; s += nthreads) {
@@ -111,11 +113,10 @@ struct vkhr_b200_ctx {
     DevBuf counts;        // u32 scratch grid(s)
     size_t counts_clean_bytes = 0;   // leading bytes of `counts` known to be zero
     DevBuf bitmap;        // PACKED8 overflow bitmaps (+ flags at the front)
-    DevBuf table;         // InstanceDev[]
     DevBuf small;         // lohi[2] + aabb keys[6] + aabb floats[6]
     DevBuf st_vertices, st_indices, st_tangents, st_dens, st_tang_out;   // host-API staging
     int repair_blocks[2] = {0, 0};
-    std::vector<InstanceDev> host_table;
+    Batch batch;          // host copy of the kernel-parameter batch being launched
     // optional per-phase device timing (vkhr_b200_profile_*): CUDA events recorded on the
     // launching stream around each phase of run_voxelize
     bool profiling = false;
@@ -261,79 +262,62 @@ bool packed_ok(const Job& j) {
     return (j.grid.n_voxels % 16u) == 0 && (reinterpret_cast<uintptr_t>(j.d_dens) & 15u) == 0;
 }
 
-int upload_table(vkhr_b200_ctx* ctx, cudaStream_t s) {
-    const size_t bytes = ctx->host_table.size() * sizeof(InstanceDev);
-    RET_IF(reserve(ctx, ctx->table, bytes));
-    // pageable source: the runtime stages it before returning, so host_table may be reused at once
-    CU_CHECK(ctx, cudaMemcpyAsync(ctx->table.p, ctx->host_table.data(), bytes, cudaMemcpyHostToDevice, s));
-    return VKHR_B200_OK;
-}
-
-// How one instance's work is tiled over CTAs.
-enum WalkKind { WK_UNIFORM = 0, WK_INDEXED = 1, WK_SPLAT = 2 };
-
-WalkKind kind_of(const Job& j, bool vertices_mode) {
-    if (vertices_mode) return WK_SPLAT;
-    return j.d_indices ? WK_INDEXED : WK_UNIFORM;
-}
-
-struct TablePlan {
-    uint32_t first[2] = {0, 0};     // table slice [first, first+count) of the uniform / indexed (or splat) group
-    uint32_t count[2] = {0, 0};
-    uint32_t tiles[2] = {0, 0};
-    std::vector<uint32_t> order;    // table slot -> job index
+// Fill ctx->batch with `n` (<= kMaxBatch) jobs.
+struct BatchPlan {
+    uint32_t max_tiles[3] = {0, 0, 0};      // per WalkKind: grid.x of that kernel (0 = not needed)
 };
 
-// Fill host_table for `jobs`: instances walked by the uniform-strand kernel first, then the rest
-// (explicit indices, or every instance in vertex mode); first_tile restarts per group.
-TablePlan fill_table(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_mode) {
-    TablePlan plan;
-    ctx->host_table.resize(n);
-    for (int grp = 0; grp < 2; ++grp) {
-        plan.first[grp] = (uint32_t)plan.order.size();
-        uint64_t tile = 0;
-        for (uint32_t k = 0; k < n; ++k) {
-            const WalkKind kind = kind_of(jobs[k], vertices_mode);
-            if ((kind == WK_UNIFORM ? 0 : 1) != grp) continue;
-            InstanceDev& I = ctx->host_table[plan.order.size()];
-            plan.order.push_back(k);
-            std::memset(&I, 0, sizeof I);
-            I.vertices = jobs[k].d_vertices;
-            I.indices = jobs[k].d_indices;
-            I.n_segments = jobs[k].n_segments;
-            I.n_vertices = jobs[k].n_vertices;
-            I.segs_per_strand = jobs[k].segs;
-            I.grid = jobs[k].grid;
-            I.densities = jobs[k].d_dens;
-            I.first_tile = (uint32_t)tile;
+BatchPlan fill_batch(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_mode) {
+    BatchPlan plan;
+    Batch& B = ctx->batch;
+    B.n = n;
+    for (uint32_t k = 0; k < n; ++k) {
+        InstanceDev& I = B.inst[k];
+        std::memset(&I, 0, sizeof I);
+        const uint32_t kind = vertices_mode ? WK_SPLAT : (jobs[k].d_indices ? WK_INDEXED : WK_UNIFORM);
+        I.vertices = jobs[k].d_vertices;
+        I.indices = jobs[k].d_indices;
+        I.n_segments = jobs[k].n_segments;
+        I.n_vertices = jobs[k].n_vertices;
+        I.segs_per_strand = jobs[k].segs;
+        I.grid = jobs[k].grid;
+        I.densities = jobs[k].d_dens;
+        I.kind = kind;
+        if (kind == WK_UNIFORM) {
+            // warp-tiles of kTileStride vertices, kTilesPerWarp per warp, kWarpsPerBlock warps per CTA
+            const uint64_t warp_tiles = ((uint64_t)jobs[k].n_vertices + kTileStride - 1) / kTileStride;
+            const uint64_t per_cta = (uint64_t)kWarpsPerBlock * kTilesPerWarp;
+            I.n_tiles = (uint32_t)((warp_tiles + per_cta - 1) / per_cta);
+        } else {
             const uint64_t items = (kind == WK_INDEXED) ? jobs[k].n_segments : jobs[k].n_vertices;
-            tile += (items + kWalkThreads - 1) / kWalkThreads;
+            I.n_tiles = (uint32_t)((items + kWalkThreads - 1) / kWalkThreads);
         }
-        plan.count[grp] = (uint32_t)plan.order.size() - plan.first[grp];
-        plan.tiles[grp] = (uint32_t)tile;
+        I.vps_magic = (uint32_t)((1ull << 32) / (uint64_t)(jobs[k].segs + 1u)) + 1u;
+        plan.max_tiles[kind] = std::max(plan.max_tiles[kind], I.n_tiles);
     }
     return plan;
 }
 
-// Launch the walk (or splat) of every instance in the uploaded table.  MODE as in kernels.cuh.
+// Launch the walk (or splat) of every instance of ctx->batch.  MODE as in kernels.cuh.
 template <int MODE>
-int launch_walk(vkhr_b200_ctx* ctx, const TablePlan& plan, bool vertices_mode, bool exact, cudaStream_t s) {
-    const InstanceDev* table = static_cast<const InstanceDev*>(ctx->table.p);
-    if (plan.tiles[0]) {
-        const InstanceDev* t0 = table + plan.first[0];
-        if (exact) k_walk_uniform<MODE, 1><<<plan.tiles[0], kWalkThreads, 0, s>>>(t0, plan.count[0]);
-        else       k_walk_uniform<MODE, 0><<<plan.tiles[0], kWalkThreads, 0, s>>>(t0, plan.count[0]);
+int launch_walk(vkhr_b200_ctx* ctx, const BatchPlan& plan, bool exact, cudaStream_t s) {
+    const Batch& B = ctx->batch;
+    if (plan.max_tiles[WK_UNIFORM]) {
+        const dim3 grid(plan.max_tiles[WK_UNIFORM], B.n);
+        if (exact) k_walk_uniform<MODE, 1><<<grid, kWalkThreads, 0, s>>>(B);
+        else       k_walk_uniform<MODE, 0><<<grid, kWalkThreads, 0, s>>>(B);
         ctx->launches++;
     }
-    if (plan.tiles[1]) {
-        const InstanceDev* t1 = table + plan.first[1];
-        if (vertices_mode) {
-            if (exact) k_splat_batch<MODE, 1><<<plan.tiles[1], kWalkThreads, 0, s>>>(t1, plan.count[1]);
-            else       k_splat_batch<MODE, 0><<<plan.tiles[1], kWalkThreads, 0, s>>>(t1, plan.count[1]);
-        } else {
-            if (exact) k_walk_indexed<MODE, 1><<<plan.tiles[1], kWalkThreads, 0, s>>>(t1, plan.count[1]);
-            else       k_walk_indexed<MODE, 0><<<plan.tiles[1], kWalkThreads, 0, s>>>(t1, plan.count[1]);
-        }
+    if (plan.max_tiles[WK_INDEXED]) {
+        const dim3 grid(plan.max_tiles[WK_INDEXED], B.n);
+        if (exact) k_walk_indexed<MODE, 1><<<grid, kWalkThreads, 0, s>>>(B);
+        else       k_walk_indexed<MODE, 0><<<grid, kWalkThreads, 0, s>>>(B);
+        ctx->launches++;
+    }
+    if (plan.max_tiles[WK_SPLAT]) {
+        const dim3 grid(plan.max_tiles[WK_SPLAT], B.n);
+        if (exact) k_splat_batch<MODE, 1><<<grid, kWalkThreads, 0, s>>>(B);
+        else       k_splat_batch<MODE, 0><<<grid, kWalkThreads, 0, s>>>(B);
         ctx->launches++;
     }
     CU_CHECK(ctx, cudaGetLastError());
@@ -341,7 +325,7 @@ int launch_walk(vkhr_b200_ctx* ctx, const TablePlan& plan, bool vertices_mode, b
 }
 
 template <bool VERTICES>
-int launch_repair(vkhr_b200_ctx* ctx, uint32_t n, uint32_t* scratch, cudaStream_t s) {
+int launch_repair(vkhr_b200_ctx* ctx, uint32_t* scratch, cudaStream_t s) {
     int& blocks = ctx->repair_blocks[VERTICES ? 1 : 0];
     if (blocks == 0) {
         int per_sm = 0;
@@ -349,14 +333,13 @@ int launch_repair(vkhr_b200_ctx* ctx, uint32_t n, uint32_t* scratch, cudaStream_
         if (per_sm < 1) return fail(ctx, VKHR_B200_ERR_CUDA, "repair kernel does not fit on an SM");
         blocks = per_sm * ctx->sm_count;
     }
-    const InstanceDev* table = static_cast<const InstanceDev*>(ctx->table.p);
-    void* args[] = {(void*)&table, (void*)&n, (void*)&scratch};
+    void* args[] = {(void*)&ctx->batch, (void*)&scratch};
     CU_CHECK(ctx, cudaLaunchCooperativeKernel((void*)k_repair_packed<VERTICES>, dim3(blocks), dim3(kWalkThreads), args, 0, s));
     ctx->launches++;
     return VKHR_B200_OK;
 }
 
-// The voxelisation of `n` instances at one resolution into their u8 grids.
+// The voxelisation of `n` instances at one resolution into their u8 grids, kMaxBatch at a time.
 int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_mode, uint32_t flags, cudaStream_t s) {
     if (n == 0) return VKHR_B200_OK;
     const uint64_t nv = jobs[0].grid.n_voxels;
@@ -370,39 +353,41 @@ int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_
     if (packed) {
         // scratch: per-instance overflow bitmap + flag, one shared u32 recount grid
         const size_t bm_words = ((nv / 4 + 31) / 32 + 3) & ~size_t(3);
-        RET_IF(reserve(ctx, ctx->bitmap, (size_t)n * (bm_words + 4) * 4));
+        const uint32_t chunk = std::min<uint32_t>(n, kMaxBatch);
+        RET_IF(reserve(ctx, ctx->bitmap, (size_t)chunk * (bm_words + 4) * 4));
         RET_IF(reserve(ctx, ctx->counts, nv * 4));
         ctx->counts_clean_bytes = 0;                   // the recount may leave entries behind
-        const TablePlan plan = fill_table(ctx, jobs, n, vertices_mode);
         uint32_t* base = static_cast<uint32_t*>(ctx->bitmap.p);
-        for (uint32_t k = 0; k < n; ++k) {
-            ctx->host_table[k].ovf_flag = base + (size_t)k * (bm_words + 4);
-            ctx->host_table[k].ovf_bitmap = base + (size_t)k * (bm_words + 4) + 4;
-            ctx->host_table[k].counts = static_cast<uint32_t*>(ctx->counts.p);
-        }
-        RET_IF(upload_table(ctx, s));
-        const InstanceDev* table = static_cast<const InstanceDev*>(ctx->table.p);
-        const unsigned gx = stride_blocks(ctx, nv / 16, 256, n >= 8 ? 2 : 8);
-        {
-            PhaseMark m(ctx, s, PH_CLEAR);
-            k_clear_packed_batch<<<dim3(gx, n), 256, 0, s>>>(table);
-            ctx->launches++;
-        }
-        if (plan.tiles[0] + plan.tiles[1]) {
-            {
-                PhaseMark m(ctx, s, PH_WALK);
-                RET_IF(launch_walk<1>(ctx, plan, vertices_mode, exact, s));
+        for (uint32_t first = 0; first < n; first += chunk) {
+            const uint32_t m = std::min(chunk, n - first);
+            const BatchPlan plan = fill_batch(ctx, jobs + first, m, vertices_mode);
+            for (uint32_t k = 0; k < m; ++k) {
+                ctx->batch.inst[k].ovf_flag = base + (size_t)k * (bm_words + 4);
+                ctx->batch.inst[k].ovf_bitmap = base + (size_t)k * (bm_words + 4) + 4;
+                ctx->batch.inst[k].counts = static_cast<uint32_t*>(ctx->counts.p);
             }
-            PhaseMark m(ctx, s, PH_FINISH);
-            if (vertices_mode) RET_IF(launch_repair<true>(ctx, n, static_cast<uint32_t*>(ctx->counts.p), s));
-            else               RET_IF(launch_repair<false>(ctx, n, static_cast<uint32_t*>(ctx->counts.p), s));
+            const unsigned gx = stride_blocks(ctx, nv / 16, 256, m >= 8 ? 2 : 8);
+            {
+                PhaseMark mk(ctx, s, PH_CLEAR);
+                k_clear_packed_batch<<<dim3(gx, m), 256, 0, s>>>(ctx->batch);
+                ctx->launches++;
+            }
+            if (plan.max_tiles[0] + plan.max_tiles[1] + plan.max_tiles[2]) {
+                {
+                    PhaseMark mk(ctx, s, PH_WALK);
+                    RET_IF(launch_walk<1>(ctx, plan, exact, s));
+                }
+                PhaseMark mk(ctx, s, PH_FINISH);
+                if (vertices_mode) RET_IF(launch_repair<true>(ctx, static_cast<uint32_t*>(ctx->counts.p), s));
+                else               RET_IF(launch_repair<false>(ctx, static_cast<uint32_t*>(ctx->counts.p), s));
+            }
+            CU_CHECK(ctx, cudaGetLastError());
         }
-        CU_CHECK(ctx, cudaGetLastError());
     } else {
         // COUNT32 in chunks of instances bounded by a 1 GiB scratch budget
         const size_t per = nv * 4;
         uint32_t chunk = (uint32_t)std::max<size_t>(1, (size_t(1) << 30) / per);
-        if (chunk > n) chunk = n;
+        chunk = std::min(std::min(chunk, n), kMaxBatch);
         const size_t need = per * chunk;
         if (need > ctx->counts.cap) ctx->counts_clean_bytes = 0;
         RET_IF(reserve(ctx, ctx->counts, need));
@@ -413,18 +398,17 @@ int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_
                 CU_CHECK(ctx, cudaMemsetAsync(ctx->counts.p, 0, per * m, s));
                 ctx->counts_clean_bytes = 0;           // until the ZERO clamp below has run
             }
-            const TablePlan plan = fill_table(ctx, jobs + first, m, vertices_mode);
+            const BatchPlan plan = fill_batch(ctx, jobs + first, m, vertices_mode);
             for (uint32_t k = 0; k < m; ++k)
-                ctx->host_table[k].counts = static_cast<uint32_t*>(ctx->counts.p) + (size_t)k * nv;
-            RET_IF(upload_table(ctx, s));
+                ctx->batch.inst[k].counts = static_cast<uint32_t*>(ctx->counts.p) + (size_t)k * nv;
             {
                 PhaseMark mk(ctx, s, PH_WALK);
-                RET_IF(launch_walk<0>(ctx, plan, vertices_mode, exact, s));
+                RET_IF(launch_walk<0>(ctx, plan, exact, s));
             }
             PhaseMark mk(ctx, s, PH_FINISH);
-            for (uint32_t k = 0; k < m; ++k) {          // table slot k holds job plan.order[k]
+            for (uint32_t k = 0; k < m; ++k) {
                 uint32_t* c = static_cast<uint32_t*>(ctx->counts.p) + (size_t)k * nv;
-                uint8_t* d = jobs[first + plan.order[k]].d_dens;
+                uint8_t* d = jobs[first + k].d_dens;
                 if ((reinterpret_cast<uintptr_t>(d) & 15u) == 0 && ((size_t)k * nv) % 4 == 0)
                     k_clamp_counts<true><<<stride_blocks(ctx, nv / 16 + 1, 256, 8), 256, 0, s>>>(c, nv, d);
                 else
@@ -444,12 +428,11 @@ int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_
 
 // ADD the hits of one shard into a caller-owned u32 grid (the multi-GPU partial).
 int run_count(vkhr_b200_ctx* ctx, const Job& j, bool vertices_mode, uint32_t flags, uint32_t* d_counts, cudaStream_t s) {
-    const TablePlan plan = fill_table(ctx, &j, 1, vertices_mode);
-    if (plan.tiles[0] + plan.tiles[1] == 0) return VKHR_B200_OK;
-    ctx->host_table[0].counts = d_counts;
-    RET_IF(upload_table(ctx, s));
+    const BatchPlan plan = fill_batch(ctx, &j, 1, vertices_mode);
+    if (plan.max_tiles[0] + plan.max_tiles[1] + plan.max_tiles[2] == 0) return VKHR_B200_OK;
+    ctx->batch.inst[0].counts = d_counts;
     PhaseMark mk(ctx, s, PH_WALK);
-    return launch_walk<0>(ctx, plan, vertices_mode, (flags & VKHR_B200_INDEX_EXACT) != 0, s);
+    return launch_walk<0>(ctx, plan, (flags & VKHR_B200_INDEX_EXACT) != 0, s);
 }
 
 int stage_in(vkhr_b200_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
@@ -508,7 +491,7 @@ void vkhr_b200_destroy(vkhr_b200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->counts, &ctx->bitmap, &ctx->table, &ctx->small, &ctx->st_vertices,
+    DevBuf* bufs[] = {&ctx->counts, &ctx->bitmap, &ctx->small, &ctx->st_vertices,
                       &ctx->st_indices, &ctx->st_tangents, &ctx->st_dens, &ctx->st_tang_out};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }

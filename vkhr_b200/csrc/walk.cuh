@@ -10,6 +10,7 @@
 // strict-IEEE x86-64 build of the reference computes.
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 namespace vkhr_b200 {
@@ -108,9 +109,47 @@ __device__ __forceinline__ void walk_voxel_space(const GridParams& g,
     dx = div_exact(dx, steps, y);
     dy = div_exact(dy, steps, y);
     dz = div_exact(dz, steps, y);
+    // All six finite (the only case in-AABB data produces): every later position is finite as well
+    // (|root| + 2^24 * |dir|), so glm::min(floor(p), res-1) == fminf(floor(p), res-1) and the loop can
+    // use the single-instruction min.  Anything else takes the literal loop below.
+    if (fabsf(__fadd_rn(__fadd_rn(fabsf(rx), fabsf(ry)), fabsf(rz))) < 3.0e38f &&
+        fabsf(__fadd_rn(__fadd_rn(fabsf(dx), fabsf(dy)), fabsf(dz))) < 3.0e38f) {
+        // one sample; SLOT names the sink's pending-result register for this position of the unrolled loop
+        auto sample = [&](auto slot) {
+            const float vx = fminf(floorf(rx), g.rx1);
+            const float vy = fminf(floorf(ry), g.ry1);
+            const float vz = fminf(floorf(rz), g.rz1);
+            uint32_t idx;
+            bool ok;
+            if (EXACT == 0 || (EXACT < 0 && !g.index_exact)) {
+                const float f = __fadd_rn(__fadd_rn(vx, __fmul_rn(vy, g.Wf)), __fmul_rn(__fmul_rn(vz, g.Wf), g.Hf));
+                idx = __float2uint_rz(f);                                 // negative -> 0, checked through f
+                ok = (f >= 0.0f) && (f < 4294967296.0f) && idx < g.n_voxels;
+            } else {
+                const long long li = (long long)__float2int_rz(vx) + (long long)__float2int_rz(vy) * (long long)g.W +
+                                     (long long)__float2int_rz(vz) * ((long long)g.W * (long long)g.H);
+                idx = (uint32_t)li;
+                ok = (fabsf(vx) < 2147483648.0f) && (fabsf(vy) < 2147483648.0f) && (fabsf(vz) < 2147483648.0f) &&
+                     li >= 0 && li < (long long)g.n_voxels;
+            }
+            if (ok) sink.template put<decltype(slot)::value>(idx);
+            rx = __fadd_rn(rx, dx);
+            ry = __fadd_rn(ry, dy);
+            rz = __fadd_rn(rz, dz);
+            steps = __fsub_rn(steps, 1.0f);
+            return steps > 0.0f;
+        };
+        for (;;) {
+            if (!sample(std::integral_constant<int, 0>{})) break;
+            if (!sample(std::integral_constant<int, 1>{})) break;
+            if (!sample(std::integral_constant<int, 2>{})) break;
+            if (!sample(std::integral_constant<int, 3>{})) break;
+        }
+        return;
+    }
     do {                                                                  // while (steps-- > 0.0f)
         uint32_t idx;
-        if (voxel_index<EXACT>(g, rx, ry, rz, idx)) sink(idx);
+        if (voxel_index<EXACT>(g, rx, ry, rz, idx)) sink.template put<0>(idx);
         rx = __fadd_rn(rx, dx);
         ry = __fadd_rn(ry, dy);
         rz = __fadd_rn(rz, dz);
