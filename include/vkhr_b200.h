@@ -108,6 +108,12 @@ VKHR_B200_API int vkhr_b200_profile_read(vkhr_b200_ctx* ctx, double ms_out[4], u
 VKHR_B200_API int vkhr_b200_selftest_division(vkhr_b200_ctx* ctx, float divisor, uint64_t n_trials,
                                               uint64_t seed, uint64_t* mismatches);
 
+/* Measurement only: while enabled, every CTA of the uniform walk kernel records
+ * {SM id, start ns, end ns, (instance << 32) | block} (4 x u64 per record).
+ * enable = 1 arms the trace; enable = 0 disarms it and copies up to max_records out. */
+VKHR_B200_API int vkhr_b200_debug_trace(vkhr_b200_ctx* ctx, int enable, unsigned long long* host_out,
+                                        uint32_t max_records, uint32_t* n_records);
+
 /* ---- host-pointer API: replaces HairStyle::voxelize_segments ----------
  * (hair_style.hh:104, hair_style.cc:296-342).
  * indices == NULL with segs_per_strand > 0 means uniform strands: the implicit

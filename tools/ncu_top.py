@@ -15,7 +15,12 @@ want = ['gpu__time_duration.sum', 'l1tex__throughput.avg.pct_of_peak_sustained_e
 for h, u, v in zip(hdr, units, row):
     if h in want: print(f'{h:88s} {u:10s} {v}')
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(src))); hdr = rows[1]; data = rows[2:]
+rows = list(csv.reader(io.StringIO(src)))
+starts = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name']        # one section per captured launch
+sec = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+end = starts[sec + 1] if sec + 1 < len(starts) else len(rows)
+print(rows[starts[sec]][1])
+hdr = rows[starts[sec] + 1]; data = [r for r in rows[starts[sec] + 2:end] if len(r) == len(hdr)]
 iS, iI, iSrc = hdr.index('# Samples'), hdr.index('Instructions Executed'), hdr.index('Source')
 stall_cols = [i for i, h in enumerate(hdr) if h.startswith('stall_') and 'Not Issued' not in h]
 tot = sum(int(r[iS]) for r in data)

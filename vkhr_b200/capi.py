@@ -83,6 +83,7 @@ _PROTOTYPES = {
     "vkhr_b200_profile_enable": (_int, [c_ctx, _int]),
     "vkhr_b200_profile_read": (_int, [c_ctx, C.c_double * 4, C.c_uint32 * 4]),
     "vkhr_b200_selftest_division": (_int, [c_ctx, C.c_float, _u64, _u64, C.POINTER(_u64)]),
+    "vkhr_b200_debug_trace": (_int, [c_ctx, _int, _P, _u32, C.POINTER(_u32)]),
     "vkhr_b200_voxelize_segments": (_int, [c_ctx, _P, _u32, _P, _u64, _u32, _P, _vec3, _vec3, _u32, _u32, _u32, _u32, _P, _P]),
     "vkhr_b200_voxelize_vertices": (_int, [c_ctx, _P, _u32, _P, _vec3, _vec3, _u32, _u32, _u32, _u32, _P, _P]),
     "vkhr_b200_voxelize_segments_dev": (_int, [c_ctx, _P, _u32, _P, _u64, _u32, _P, _vec3, _vec3, _u32, _u32, _u32, _u32, _P, _P, _P]),

@@ -16,6 +16,13 @@ constexpr int kWalkThreads = 256;
 // How an instance's work is tiled over CTAs.
 enum WalkKind : uint32_t { WK_UNIFORM = 0, WK_INDEXED = 1, WK_SPLAT = 2 };
 
+// Per-instance bookkeeping of the PACKED8 strategy (device memory, zeroed by the clear kernel).
+struct PackedHeader {
+    unsigned long long samples;     // samples the walk added to the grid
+    unsigned long long byte_sum;    // sum of the grid's bytes after the walk (k_verify_packed_batch)
+    uint32_t pad[4];
+};
+
 // Device-side description of one instance of a batch.
 struct InstanceDev {
     const float*    vertices;
@@ -26,9 +33,8 @@ struct InstanceDev {
     GridParams      grid;
     uint8_t*        densities;      // W*H*D u8 (PACKED8: counted in place)
     uint32_t*       counts;         // W*H*D u32 (COUNT32 / recount scratch) or nullptr
-    uint32_t*       ovf_bitmap;     // PACKED8: 1 bit per 32-bit word of `densities`
-    uint32_t*       ovf_flag;       // PACKED8: != 0 when any word overflowed
-    uint32_t        n_tiles;        // CTAs (of kWalkThreads items) this instance needs
+    PackedHeader*   header;         // PACKED8 only
+    uint32_t        n_tiles;        // CTAs this instance needs in its walk kernel
     uint32_t        kind;           // WalkKind
     uint32_t        vps_magic;      // floor(2^32 / (segs_per_strand + 1)) + 1   (strand-end test without a division)
     uint32_t        pad;
@@ -36,7 +42,7 @@ struct InstanceDev {
 
 // A batch travels to the kernels as a __grid_constant__ parameter: every per-instance constant is then
 // read through the constant cache, not through L1TEX (which the atomics need), and no table upload
-// precedes the launch.  blockIdx.y selects the instance.
+// precedes the launch.  blockIdx.y + first selects the instance.
 constexpr uint32_t kMaxBatch = 64;
 struct Batch {
     uint32_t n;
@@ -57,61 +63,77 @@ struct SinkCount32 {
     __device__ __forceinline__ void finish() {}
 };
 
-// PACKED8: the u8 output grid itself is the counter; four voxels share one
-// 32-bit word and a hit adds 1 << (8 * byte).  The returned old word tells
-// the adding thread whether ITS add carried out of the byte (old field ==
-// 255).  The first carry in a word is always seen on a clean word, so a word
-// is flagged in the bitmap if and only if one of its voxels received more
-// than 255 hits; flagged words are recounted exactly by k_repair_packed.
-// Returned words are examined kDepth samples later (a ring of kDepth pending
-// results in registers, slot chosen at compile time by the unrolled walk), so
-// up to kDepth atomics of a thread are in flight and their round trips overlap
-// the arithmetic of the following samples.
+// PACKED8: the u8 output grid itself is the counter.  Four voxels share one 32-bit
+// word and a hit adds 1 << (8 * byte) with a fire-and-forget `red.global.add.u32`:
+// nothing returns to the SM, so a sample costs one L1TEX wavefront instead of the
+// request + reply of an `atom`.  A byte that receives more than 255 hits carries
+// into its neighbour, which no thread can see -- but the grid can prove afterwards
+// that it did not happen: the sum of all bytes of a word equals the number of hits
+// the word received if and only if no byte carried (every carry lowers the digit sum
+// by 255, a carry out of the word by 256, nothing raises it).  So each warp counts
+// the samples it adds (one u64 atomic per warp per kernel), k_verify_packed_batch
+// sums the bytes, and an instance whose two numbers differ is recounted exactly in
+// u32 by k_repair_packed.  With no voxel above 255 -- every hair style at a useful
+// resolution -- the volume is final after the verify pass.
 struct SinkPacked8 {
-    static constexpr int kDepth = 4;
     uint32_t* words;
-    uint32_t* ovf_bitmap;
-    uint32_t* ovf_flag;
-    uint32_t pend_old[kDepth] = {0, 0, 0, 0};
-    uint32_t pend_idx[kDepth] = {0, 0, 0, 0};
-    template <int SLOT>
-    __device__ __forceinline__ void check() {
-        // byte (idx & 3) of the word as it was before this thread's add
-        if (__byte_perm(pend_old[SLOT], 0u, 0x4440u | (pend_idx[SLOT] & 3u)) == 0xFFu) {
-            const uint32_t w = pend_idx[SLOT] >> 2;
-            atomicOr(ovf_bitmap + (w >> 5), 1u << (w & 31u));
-            *ovf_flag = 1u;
-        }
-    }
+    unsigned long long* samples;
+    uint32_t n_put = 0;
     template <int SLOT = 0>
     __device__ __forceinline__ void put(uint32_t idx) {
-        check<SLOT>();
-        pend_old[SLOT] = atomicAdd(words + (idx >> 2), 1u << ((idx & 3u) * 8u));
-        pend_idx[SLOT] = idx;
+        atomicAdd(words + (idx >> 2), 1u << ((idx & 3u) * 8u));      // result unused: RED.E.ADD
+        ++n_put;
     }
-    __device__ __forceinline__ void finish() { check<0>(); check<1>(); check<2>(); check<3>(); }
+    // all 32 lanes of the warp, converged
+    __device__ __forceinline__ void finish() {
+        const uint32_t n = __reduce_add_sync(kFullWarp, n_put);
+        if ((threadIdx.x & 31u) == 0u && n) atomicAdd(samples, (unsigned long long)n);
+    }
 };
 
-// Recount pass of PACKED8: only samples landing in flagged words are counted,
-// into the u32 scratch grid.
-struct SinkRecount {
-    const uint32_t* ovf_bitmap;
-    uint32_t* counts;
+// Measurement only (VKHR_B200_DEBUG_SINK=null): counts samples, touches no grid -- the walk without its reds.
+struct SinkNull {
+    unsigned long long* samples;
+    uint32_t n_put = 0;
+    template <int SLOT = 0>
+    __device__ __forceinline__ void put(uint32_t idx) { n_put += (idx & 1u) + 1u; }
+    __device__ __forceinline__ void finish() {
+        const uint32_t n = __reduce_add_sync(kFullWarp, n_put);
+        if ((threadIdx.x & 31u) == 0u && n) atomicAdd(samples, (unsigned long long)n);
+    }
+};
+
+// Measurement only: VARIANT 0 = every red lands in a 4 KB window (lanes coalesce), 1 = only every 4th sample is added.
+template <int VARIANT>
+struct SinkProbe {
+    uint32_t* words;
+    unsigned long long* samples;
+    uint32_t n_put = 0;
     template <int SLOT = 0>
     __device__ __forceinline__ void put(uint32_t idx) {
-        const uint32_t w = idx >> 2;
-        if ((__ldg(ovf_bitmap + (w >> 5)) >> (w & 31u)) & 1u) atomicAdd(counts + idx, 1u);
+        if (VARIANT == 0) atomicAdd(words + ((idx >> 2) & 1023u), 1u << ((idx & 3u) * 8u));
+        else if ((n_put & 3u) == 0u) atomicAdd(words + (idx >> 2), 1u << ((idx & 3u) * 8u));
+        ++n_put;
     }
-    __device__ __forceinline__ void finish() {}
+    __device__ __forceinline__ void finish() {
+        const uint32_t n = __reduce_add_sync(kFullWarp, n_put);
+        if ((threadIdx.x & 31u) == 0u && n) atomicAdd(samples, (unsigned long long)n);
+    }
 };
 
 template <int MODE> struct SinkOf;
 template <> struct SinkOf<0> { using type = SinkCount32;
     __device__ static type make(const InstanceDev& I) { return SinkCount32{I.counts}; } };
 template <> struct SinkOf<1> { using type = SinkPacked8;
-    __device__ static type make(const InstanceDev& I) { SinkPacked8 k; k.words = reinterpret_cast<uint32_t*>(I.densities); k.ovf_bitmap = I.ovf_bitmap; k.ovf_flag = I.ovf_flag; return k; } };
-template <> struct SinkOf<2> { using type = SinkRecount;
-    __device__ static type make(const InstanceDev& I) { return SinkRecount{I.ovf_bitmap, I.counts}; } };
+    __device__ static type make(const InstanceDev& I) { SinkPacked8 k; k.words = reinterpret_cast<uint32_t*>(I.densities); k.samples = &I.header->samples; return k; } };
+
+template <> struct SinkOf<2> { using type = SinkNull;
+    __device__ static type make(const InstanceDev& I) { SinkNull k; k.samples = &I.header->samples; return k; } };
+
+template <> struct SinkOf<3> { using type = SinkProbe<0>;
+    __device__ static type make(const InstanceDev& I) { SinkProbe<0> k; k.words = reinterpret_cast<uint32_t*>(I.densities); k.samples = &I.header->samples; return k; } };
+template <> struct SinkOf<4> { using type = SinkProbe<1>;
+    __device__ static type make(const InstanceDev& I) { SinkProbe<1> k; k.words = reinterpret_cast<uint32_t*>(I.densities); k.samples = &I.header->samples; return k; } };
 
 // ---------------------------------------------------------------------------
 // Walk kernel for uniform strands (no index buffer): the hot kernel.
@@ -126,66 +148,134 @@ template <> struct SinkOf<2> { using type = SinkRecount;
 // so the HBM latency of the vertex stream hides behind the walk.  Vertices are
 // read from HBM once (1/31 twice); per-instance constants come from the constant
 // bank (the batch is a __grid_constant__ parameter); the L1TEX path carries only
-// the vertex stream and the atomics.  blockIdx.y = instance.
-// MODE 0 = COUNT32, 1 = PACKED8, 2 = recount of flagged words.
+// the vertex stream and the reds.  blockIdx.y + first = instance.
+// MODE 0 = COUNT32, 1 = PACKED8.
 // ---------------------------------------------------------------------------
 constexpr uint32_t kTilesPerWarp = 8;
 constexpr uint32_t kWarpsPerBlock = kWalkThreads / 32;
 constexpr uint32_t kTileStride = 31;          // segments (= new vertices) per warp-tile
+constexpr uint32_t kRangeFloats = 3u * kTileStride * kTilesPerWarp;   // 744 floats = 2976 bytes (a multiple of 16)
+constexpr uint32_t kNeedFloats = kRangeFloats + 3u;                   // + the tip vertex of the range's last segment
+constexpr uint32_t kBulkBytes = ((kNeedFloats * 4u + 15u) / 16u) * 16u;   // 3008: what one bulk copy moves
+constexpr uint32_t kStageFloats = 768u;       // shared-memory slot of one warp (>= kBulkBytes / 4, 24 x 32)
+static_assert(kRangeFloats * 4u % 16u == 0 && kBulkBytes <= kStageFloats * 4u, "bulk copy geometry");
+
+// mbarrier + 1-D bulk copy (TMA unit, `cp.async.bulk`, SASS UBLKCP): global -> shared without passing
+// through the LSU queue the reds occupy.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (spin > (1u << 24)) __trap();                           // a lost copy must fail, not hang the device
+    }
+}
+
+// Measurement only: when non-null, every CTA of k_walk_uniform records {smid, start ns, end ns, instance}.
+__device__ unsigned long long* g_cta_trace = nullptr;
+__device__ unsigned int g_cta_trace_count = 0;
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
 
 template <int MODE, int EXACT>
 __global__ void __launch_bounds__(kWalkThreads)
-k_walk_uniform(const __grid_constant__ Batch B) {
-    __shared__ float s_raw[kWarpsPerBlock][96];
-    const InstanceDev& I = B.inst[blockIdx.y];
+k_walk_uniform(const __grid_constant__ Batch B, uint32_t first) {
+    __shared__ __align__(128) float s_stage[kWarpsPerBlock][kStageFloats];
+    const unsigned long long t_start = g_cta_trace ? globaltimer_ns() : 0ull;
+    __shared__ __align__(8) unsigned long long s_bar[kWarpsPerBlock];
+    const InstanceDev& I = B.inst[first + blockIdx.y];
     if (blockIdx.x >= I.n_tiles || I.kind != WK_UNIFORM) return;   // n_tiles counts CTAs
-    if (MODE == 2 && *I.ovf_flag == 0u) return;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const GridParams& g = I.grid;
-    const uint32_t n_vertices = I.n_vertices;
+    const GridParams g = pin(I.grid);                              // registers, not indexed constant loads
+    const uint32_t n_vertices = pin(I.n_vertices);
     const uint32_t n_floats = 3u * n_vertices;
     const uint32_t n_warp_tiles = (n_vertices + kTileStride - 1u) / kTileStride;
-    const uint32_t vps = I.segs_per_strand + 1u;
+    const uint32_t vps = pin(I.segs_per_strand + 1u);
+    const uint32_t vps_magic = pin(I.vps_magic);
     const float* __restrict__ verts = I.vertices;
-    float* raw = s_raw[warp];
+    float* stage = s_stage[warp];
     auto sink = SinkOf<MODE>::make(I);
 
-    uint32_t tile = (blockIdx.x * kWarpsPerBlock + warp) * kTilesPerWarp;
-    const uint32_t tile_end = min(tile + kTilesPerWarp, n_warp_tiles);
-    if (tile >= tile_end) return;
-    // this lane's three floats of the current tile (float f of the tile lives in lane f % 32, register f / 32)
-    float f0 = 0.f, f1 = 0.f, f2 = 0.f;
+    const uint32_t range = blockIdx.x * kWarpsPerBlock + warp;     // this warp's range of kTilesPerWarp tiles
+    const uint32_t tile0 = range * kTilesPerWarp;
+    const uint32_t n_tiles = min(kTilesPerWarp, n_warp_tiles - min(tile0, n_warp_tiles));
+    if (n_tiles == 0) return;                                      // whole warps only
+
+    // ---- stage the warp's vertex range (8 tiles + one tip vertex, 3 KB) into shared memory -----------------
+    // 16-byte aligned vertex buffers: ONE bulk copy issued by lane 0, completion on the warp's own mbarrier.
+    // Anything else (a 4-byte aligned view, the last bytes of the buffer): coalesced 32-bit loads.
     {
-        const uint32_t base = 3u * kTileStride * tile + lane;
-        if (base < n_floats) f0 = __ldg(verts + base);
-        if (base + 32u < n_floats) f1 = __ldg(verts + base + 32u);
-        if (base + 64u < n_floats) f2 = __ldg(verts + base + 64u);
-    }
-    for (; tile < tile_end; ++tile) {
-        raw[lane] = f0; raw[lane + 32u] = f1; raw[lane + 64u] = f2;
-        if (tile + 1u < tile_end) {                               // prefetch the next tile into registers
-            const uint32_t base = 3u * kTileStride * (tile + 1u) + lane;
-            f0 = (base < n_floats) ? __ldg(verts + base) : 0.f;
-            f1 = (base + 32u < n_floats) ? __ldg(verts + base + 32u) : 0.f;
-            f2 = (base + 64u < n_floats) ? __ldg(verts + base + 64u) : 0.f;
+        const uint32_t start = kRangeFloats * range;                // first float of the range
+        const uint32_t need = min(kNeedFloats, n_floats - start);   // floats this warp reads from `stage`
+        uint32_t bulk = 0;                                          // floats that arrive by bulk copy
+        if ((reinterpret_cast<uintptr_t>(verts) & 15u) == 0u)
+            bulk = min(kBulkBytes, ((n_floats - start) * 4u) & ~15u) / 4u;
+        const uint32_t bar = smem_u32(&s_bar[warp]);
+        if (bulk) {
+            if (lane == 0) mbar_init(bar, 1);
+            __syncwarp();
+            if (lane == 0) bulk_load(smem_u32(stage), verts + start, bulk * 4u, bar);
         }
+        for (uint32_t j = bulk + lane; j < need; j += 32u) stage[j] = __ldg(verts + start + j);
+        if (bulk) mbar_wait(bar, 0);
         __syncwarp();
-        const float px = to_voxel_space(raw[3u * lane + 0u], g.ox, g.vsx, g.rvx);
-        const float py = to_voxel_space(raw[3u * lane + 1u], g.oy, g.vsy, g.rvy);
-        const float pz = to_voxel_space(raw[3u * lane + 2u], g.oz, g.vsz, g.rvz);
-        __syncwarp();                                             // raw[] is rewritten by the next iteration
-        const float tx = __shfl_down_sync(0xFFFFFFFFu, px, 1);
-        const float ty = __shfl_down_sync(0xFFFFFFFFu, py, 1);
-        const float tz = __shfl_down_sync(0xFFFFFFFFu, pz, 1);
+    }
+
+    // ---- software-pipelined tile loop ------------------------------------------------------------------
+    // Shared-memory loads and shuffles share the SM's memory-instruction queue with the reds; behind a burst
+    // of reds each round trip takes as long as the queue is deep.  So nothing in a tile's walk waits for a
+    // round trip issued in the same iteration: the raw floats of tile k+2 and the transformed + shuffled end
+    // points of tile k+1 are requested BEFORE tile k is walked.
+    auto load_raw = [&](uint32_t k, float& a, float& b, float& c) {
+        const float* r = stage + 3u * kTileStride * k + 3u * lane;
+        a = r[0]; b = r[1]; c = r[2];
+    };
+    float r0, r1, r2, px, py, pz, tx, ty, tz;
+    load_raw(0, r0, r1, r2);
+    to_voxel_space_warp(g, r0, r1, r2, px, py, pz);
+    tx = __shfl_down_sync(kFullWarp, px, 1);
+    ty = __shfl_down_sync(kFullWarp, py, 1);
+    tz = __shfl_down_sync(kFullWarp, pz, 1);
+    if (n_tiles > 1u) load_raw(1, r0, r1, r2);
+    for (uint32_t k = 0; k < n_tiles; ++k) {
+        float npx = 0.f, npy = 0.f, npz = 0.f, ntx = 0.f, nty = 0.f, ntz = 0.f;
+        if (k + 1u < n_tiles) {                                    // warp-uniform
+            to_voxel_space_warp(g, r0, r1, r2, npx, npy, npz);
+            ntx = __shfl_down_sync(kFullWarp, npx, 1);
+            nty = __shfl_down_sync(kFullWarp, npy, 1);
+            ntz = __shfl_down_sync(kFullWarp, npz, 1);
+            if (k + 2u < n_tiles) load_raw(k + 2u, r0, r1, r2);
+        }
         // vertex x starts a segment unless it is the last of its strand: x mod vps by multiply-high
         // (the quotient estimate is exact or one too large)
-        const uint32_t x = kTileStride * tile + lane;
-        uint32_t r = x - __umulhi(x, I.vps_magic) * vps;
+        const uint32_t x = kTileStride * (tile0 + k) + lane;
+        uint32_t r = x - __umulhi(x, vps_magic) * vps;
         if ((int32_t)r < 0) r += vps;
-        if (lane < kTileStride && x + 1u < n_vertices && r != vps - 1u)
-            walk_voxel_space<EXACT>(g, px, py, pz, tx, ty, tz, sink);
+        const bool active = lane < kTileStride && x + 1u < n_vertices && r != vps - 1u;
+        walk_voxel_space_warp<EXACT>(g, active, px, py, pz, tx, ty, tz, sink);
+        px = npx; py = npy; pz = npz; tx = ntx; ty = nty; tz = ntz;
     }
     sink.finish();
+    if (g_cta_trace && threadIdx.x == 0) {                         // warp 0's own duration (no CTA barrier here)
+        const unsigned int slot = atomicAdd(&g_cta_trace_count, 1u);
+        if (slot < (1u << 20)) {
+            g_cta_trace[4ull * slot + 0] = smid();
+            g_cta_trace[4ull * slot + 1] = t_start;
+            g_cta_trace[4ull * slot + 2] = globaltimer_ns();
+            g_cta_trace[4ull * slot + 3] = ((unsigned long long)(first + blockIdx.y) << 32) | blockIdx.x;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -194,38 +284,47 @@ k_walk_uniform(const __grid_constant__ Batch B) {
 // ---------------------------------------------------------------------------
 template <int MODE, int EXACT>
 __global__ void __launch_bounds__(kWalkThreads)
-k_walk_indexed(const __grid_constant__ Batch B) {
-    const InstanceDev& I = B.inst[blockIdx.y];
+k_walk_indexed(const __grid_constant__ Batch B, uint32_t first) {
+    const InstanceDev& I = B.inst[first + blockIdx.y];
     if (blockIdx.x >= I.n_tiles || I.kind != WK_INDEXED) return;
-    if (MODE == 2 && *I.ovf_flag == 0u) return;
     const uint64_t s = (uint64_t)blockIdx.x * kWalkThreads + threadIdx.x;
-    if (s >= I.n_segments) return;
+    const bool active = s < I.n_segments;
     const GridParams& g = I.grid;
-    const uint2 pr = __ldg(reinterpret_cast<const uint2*>(I.indices) + s);
-    const float* a = I.vertices + 3ull * pr.x;
-    const float* b = I.vertices + 3ull * pr.y;
+    float ax = 0.f, ay = 0.f, az = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
+    if (active) {
+        const uint2 pr = __ldg(reinterpret_cast<const uint2*>(I.indices) + s);
+        const float* a = I.vertices + 3ull * pr.x;
+        const float* b = I.vertices + 3ull * pr.y;
+        ax = __ldg(a); ay = __ldg(a + 1); az = __ldg(a + 2);
+        bx = __ldg(b); by = __ldg(b + 1); bz = __ldg(b + 2);
+    }
     auto sink = SinkOf<MODE>::make(I);
-    walk_segment<EXACT>(g, __ldg(a), __ldg(a + 1), __ldg(a + 2), __ldg(b), __ldg(b + 1), __ldg(b + 2), sink);
+    float px, py, pz, tx, ty, tz;
+    to_voxel_space_warp(g, ax, ay, az, px, py, pz);
+    to_voxel_space_warp(g, bx, by, bz, tx, ty, tz);
+    walk_voxel_space_warp<EXACT>(g, active, px, py, pz, tx, ty, tz, sink);
     sink.finish();
 }
 
 // Vertex splat (voxelize_vertices): one thread per vertex.
 template <int MODE, int EXACT>
 __global__ void __launch_bounds__(kWalkThreads)
-k_splat_batch(const __grid_constant__ Batch B) {
-    const InstanceDev& I = B.inst[blockIdx.y];
+k_splat_batch(const __grid_constant__ Batch B, uint32_t first) {
+    const InstanceDev& I = B.inst[first + blockIdx.y];
     if (blockIdx.x >= I.n_tiles || I.kind != WK_SPLAT) return;
-    if (MODE == 2 && *I.ovf_flag == 0u) return;
     const uint32_t i = blockIdx.x * kWalkThreads + threadIdx.x;
-    if (i >= I.n_vertices) return;
+    const bool active = i < I.n_vertices;
     const GridParams& g = I.grid;
-    const float* v = I.vertices + 3ull * i;
-    uint32_t idx;
-    if (!voxel_index<EXACT>(g, to_voxel_space(__ldg(v), g.ox, g.vsx, g.rvx), to_voxel_space(__ldg(v + 1), g.oy, g.vsy, g.rvy),
-                            to_voxel_space(__ldg(v + 2), g.oz, g.vsz, g.rvz), idx))
-        return;
+    float wx = 0.f, wy = 0.f, wz = 0.f;
+    if (active) {
+        const float* v = I.vertices + 3ull * i;
+        wx = __ldg(v); wy = __ldg(v + 1); wz = __ldg(v + 2);
+    }
+    float px, py, pz;
+    to_voxel_space_warp(g, wx, wy, wz, px, py, pz);
     auto sink = SinkOf<MODE>::make(I);
-    sink.template put<0>(idx);
+    uint32_t idx;
+    if (active && voxel_index<EXACT>(g, px, py, pz, idx)) sink.template put<0>(idx);
     sink.finish();
 }
 
@@ -259,19 +358,41 @@ __global__ void __launch_bounds__(256) k_zero16(uint4* __restrict__ p, uint64_t 
         p[i] = z;
 }
 
-// PACKED8 clear for a batch: densities, overflow bitmap and flag of every instance.
-// blockIdx.y = instance.  n_voxels % 16 == 0 is guaranteed by the host (else COUNT32).
-__global__ void __launch_bounds__(256) k_clear_packed_batch(const __grid_constant__ Batch B) {
-    const InstanceDev& I = B.inst[blockIdx.y];
+// PACKED8 clear for a batch: densities and header of every instance.
+// blockIdx.y + first = instance.  n_voxels % 16 == 0 is guaranteed by the host (else COUNT32).
+__global__ void __launch_bounds__(256) k_clear_packed_batch(const __grid_constant__ Batch B, uint32_t first) {
+    const InstanceDev& I = B.inst[first + blockIdx.y];
     const uint4 z = make_uint4(0, 0, 0, 0);
     uint4* d = reinterpret_cast<uint4*>(I.densities);
     const uint32_t n16 = I.grid.n_voxels >> 4;
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     for (uint32_t i = t; i < n16; i += stride) d[i] = z;
-    const uint32_t n_bm = (I.grid.n_voxels / 4 + 31) / 32;          // bitmap words
-    for (uint32_t i = t; i < n_bm; i += stride) I.ovf_bitmap[i] = 0u;
-    if (t == 0) *I.ovf_flag = 0u;
+    if (t < 2) reinterpret_cast<uint4*>(I.header)[t] = z;
+}
+
+// PACKED8 verify: header.byte_sum = sum of all bytes of the instance's grid (see SinkPacked8).
+// Reads go to L2 only (ld.global.cg): the grid was just written there by the reds.
+__global__ void __launch_bounds__(256) k_verify_packed_batch(const __grid_constant__ Batch B, uint32_t first) {
+    const InstanceDev& I = B.inst[first + blockIdx.y];
+    const uint4* d = reinterpret_cast<const uint4*>(I.densities);
+    const uint32_t n16 = I.grid.n_voxels >> 4;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t a0 = 0, a1 = 0;                               // <= 2^28 * 255 / (threads >= 256) each: no overflow
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        const uint4 v = __ldcg(d + i);
+        a0 = __dp4a(v.x, 0x01010101u, a0);
+        a1 = __dp4a(v.y, 0x01010101u, a1);
+        a0 = __dp4a(v.z, 0x01010101u, a0);
+        a1 = __dp4a(v.w, 0x01010101u, a1);
+    }
+    __shared__ unsigned long long s_sum;
+    if (threadIdx.x == 0) s_sum = 0ull;
+    __syncthreads();
+    const unsigned long long w = (unsigned long long)__reduce_add_sync(kFullWarp, a0) + __reduce_add_sync(kFullWarp, a1);
+    if ((threadIdx.x & 31u) == 0u && w) atomicAdd(&s_sum, w);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_sum) atomicAdd(&I.header->byte_sum, s_sum);
 }
 
 // densities = min(counts, 255)  (hair_style.cc:322: `if (d != 255) d += 1`),

@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -22,44 +23,39 @@ namespace cg = cooperative_groups;
 using namespace vkhr_b200;
 
 // ---------------------------------------------------------------------------
-// PACKED8 repair: one persistent cooperative kernel.  Instances whose overflow
-// flag is set (some voxel received more than 255 hits) are handled one after
-// the other on a single shared u32 scratch grid:
-//   zero the scratch entries of flagged words -> grid barrier ->
-//   re-walk the instance, counting only samples that land in flagged words ->
-//   grid barrier -> rewrite the flagged words as min(count, 255).
-// With no flag set (the common case) every CTA returns after reading n flags.
+// PACKED8 repair: one persistent cooperative kernel.  An instance whose verify
+// pass found sum(bytes) != samples had a voxel above 255 hits (see SinkPacked8);
+// such instances are recounted exactly, one after the other, on a shared u32
+// scratch grid:
+//   zero the scratch -> grid barrier -> re-walk the instance into it ->
+//   grid barrier -> rewrite the u8 grid as min(count, 255).
+// With no mismatch (the common case) every CTA returns after reading n headers.
 // ---------------------------------------------------------------------------
 template <bool VERTICES>
 __global__ void __launch_bounds__(kWalkThreads)
 k_repair_packed(const __grid_constant__ Batch B, uint32_t* __restrict__ scratch) {
-    // common case first: no instance overflowed -> one parallel look at the flags and out
+    // common case first: nothing overflowed -> one parallel look at the headers and out
     const uint32_t n_inst = B.n;
     const InstanceDev* inst = B.inst;
     int any = 0;
-    for (uint32_t k = threadIdx.x; k < n_inst; k += blockDim.x) any |= (*inst[k].ovf_flag != 0u);
+    for (uint32_t k = threadIdx.x; k < n_inst; k += blockDim.x) {
+        const PackedHeader h = *inst[k].header;
+        any |= (h.samples != h.byte_sum);
+    }
     if (!__syncthreads_or(any)) return;                        // same answer in every CTA
     cg::grid_group grid = cg::this_grid();
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t nthreads = gridDim.x * blockDim.x;
     for (uint32_t k = 0; k < n_inst; ++k) {
         const InstanceDev& I = inst[k];
-        if (*I.ovf_flag == 0u) continue;                       // uniform across the grid
+        if (I.header->samples == I.header->byte_sum) continue; // uniform across the grid
         const GridParams g = I.grid;
         const uint32_t n_words = g.n_voxels >> 2;
-        const uint32_t n_bm = (n_words + 31) / 32;
         uint32_t* words = reinterpret_cast<uint32_t*>(I.densities);
         uint4* counts4 = reinterpret_cast<uint4*>(scratch);
-        for (uint32_t b = tid; b < n_bm; b += nthreads) {
-            uint32_t m = I.ovf_bitmap[b];
-            while (m) {
-                const uint32_t w = b * 32 + (__ffs(m) - 1);
-                m &= m - 1;
-                if (w < n_words) counts4[w] = make_uint4(0, 0, 0, 0);
-            }
-        }
+        for (uint32_t w = tid; w < n_words; w += nthreads) counts4[w] = make_uint4(0, 0, 0, 0);
         grid.sync();
-        SinkRecount sink{I.ovf_bitmap, scratch};
+        SinkCount32 sink{scratch};
         if (VERTICES) {
             for (uint32_t i = tid; i < I.n_vertices; i += nthreads) {
                 const float* v = I.vertices + 3ull * i;
@@ -84,14 +80,7 @@ k_repair_packed(const __grid_constant__ Batch B, uint32_t* __restrict__ scratch)
             }
         }
         grid.sync();
-        for (uint32_t b = tid; b < n_bm; b += nthreads) {
-            uint32_t m = I.ovf_bitmap[b];
-            while (m) {
-                const uint32_t w = b * 32 + (__ffs(m) - 1);
-                m &= m - 1;
-                if (w < n_words) words[w] = clamp4(counts4[w]);
-            }
-        }
+        for (uint32_t w = tid; w < n_words; w += nthreads) words[w] = clamp4(counts4[w]);
         grid.sync();                                           // scratch is reused by the next flagged instance
     }
 }
@@ -112,7 +101,9 @@ struct vkhr_b200_ctx {
     uint64_t launches = 0;
     DevBuf counts;        // u32 scratch grid(s)
     size_t counts_clean_bytes = 0;   // leading bytes of `counts` known to be zero
-    DevBuf bitmap;        // PACKED8 overflow bitmaps (+ flags at the front)
+    DevBuf headers;       // PACKED8 per-instance PackedHeader
+    int debug_sink = 0;               // measurement only (VKHR_B200_DEBUG_SINK): results are wrong by design
+    size_t group_bytes = 64u << 20;   // PACKED8: volumes cleared + walked + verified together (kept L2-resident)
     DevBuf small;         // lohi[2] + aabb keys[6] + aabb floats[6]
     DevBuf st_vertices, st_indices, st_tangents, st_dens, st_tang_out;   // host-API staging
     int repair_blocks[2] = {0, 0};
@@ -227,6 +218,7 @@ int make_grid(vkhr_b200_ctx* ctx, const float origin[3], const float size[3],
     // RN(1/voxel_size) for div_exact (walk.cuh); outside [2^-40, 2^40] the kernels use the plain IEEE division
     auto recip = [](float vs) { return (vs >= 9.094947e-13f && vs <= 1.0995116e12f) ? 1.0f / vs : 0.0f; };
     g.rvx = recip(g.vsx); g.rvy = recip(g.vsy); g.rvz = recip(g.vsz);
+    g.fast_div = (g.rvx != 0.0f && g.rvy != 0.0f && g.rvz != 0.0f) ? 1u : 0u;
     return VKHR_B200_OK;
 }
 
@@ -298,26 +290,29 @@ BatchPlan fill_batch(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool verti
     return plan;
 }
 
-// Launch the walk (or splat) of every instance of ctx->batch.  MODE as in kernels.cuh.
+// Launch the walk (or splat) of instances [first, first + count) of ctx->batch.  MODE as in kernels.cuh.
 template <int MODE>
-int launch_walk(vkhr_b200_ctx* ctx, const BatchPlan& plan, bool exact, cudaStream_t s) {
+int launch_walk(vkhr_b200_ctx* ctx, const BatchPlan& plan, bool exact, uint32_t first, uint32_t count, cudaStream_t s) {
     const Batch& B = ctx->batch;
-    if (plan.max_tiles[WK_UNIFORM]) {
-        const dim3 grid(plan.max_tiles[WK_UNIFORM], B.n);
-        if (exact) k_walk_uniform<MODE, 1><<<grid, kWalkThreads, 0, s>>>(B);
-        else       k_walk_uniform<MODE, 0><<<grid, kWalkThreads, 0, s>>>(B);
+    uint32_t tiles[3] = {0, 0, 0};
+    for (uint32_t k = first; k < first + count; ++k) tiles[B.inst[k].kind] = std::max(tiles[B.inst[k].kind], B.inst[k].n_tiles);
+    (void)plan;
+    if (tiles[WK_UNIFORM]) {
+        const dim3 grid(tiles[WK_UNIFORM], count);
+        if (exact) k_walk_uniform<MODE, 1><<<grid, kWalkThreads, 0, s>>>(B, first);
+        else       k_walk_uniform<MODE, 0><<<grid, kWalkThreads, 0, s>>>(B, first);
         ctx->launches++;
     }
-    if (plan.max_tiles[WK_INDEXED]) {
-        const dim3 grid(plan.max_tiles[WK_INDEXED], B.n);
-        if (exact) k_walk_indexed<MODE, 1><<<grid, kWalkThreads, 0, s>>>(B);
-        else       k_walk_indexed<MODE, 0><<<grid, kWalkThreads, 0, s>>>(B);
+    if (tiles[WK_INDEXED]) {
+        const dim3 grid(tiles[WK_INDEXED], count);
+        if (exact) k_walk_indexed<MODE, 1><<<grid, kWalkThreads, 0, s>>>(B, first);
+        else       k_walk_indexed<MODE, 0><<<grid, kWalkThreads, 0, s>>>(B, first);
         ctx->launches++;
     }
-    if (plan.max_tiles[WK_SPLAT]) {
-        const dim3 grid(plan.max_tiles[WK_SPLAT], B.n);
-        if (exact) k_splat_batch<MODE, 1><<<grid, kWalkThreads, 0, s>>>(B);
-        else       k_splat_batch<MODE, 0><<<grid, kWalkThreads, 0, s>>>(B);
+    if (tiles[WK_SPLAT]) {
+        const dim3 grid(tiles[WK_SPLAT], count);
+        if (exact) k_splat_batch<MODE, 1><<<grid, kWalkThreads, 0, s>>>(B, first);
+        else       k_splat_batch<MODE, 0><<<grid, kWalkThreads, 0, s>>>(B, first);
         ctx->launches++;
     }
     CU_CHECK(ctx, cudaGetLastError());
@@ -351,32 +346,44 @@ int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_
         return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "PACKED8 needs W*H*D % 16 == 0 and 16-byte aligned densities");
 
     if (packed) {
-        // scratch: per-instance overflow bitmap + flag, one shared u32 recount grid
-        const size_t bm_words = ((nv / 4 + 31) / 32 + 3) & ~size_t(3);
+        // scratch: one PackedHeader per instance, one shared u32 recount grid (touched only after an overflow)
         const uint32_t chunk = std::min<uint32_t>(n, kMaxBatch);
-        RET_IF(reserve(ctx, ctx->bitmap, (size_t)chunk * (bm_words + 4) * 4));
+        RET_IF(reserve(ctx, ctx->headers, (size_t)chunk * sizeof(PackedHeader)));
         RET_IF(reserve(ctx, ctx->counts, nv * 4));
         ctx->counts_clean_bytes = 0;                   // the recount may leave entries behind
-        uint32_t* base = static_cast<uint32_t*>(ctx->bitmap.p);
+        PackedHeader* hdr = static_cast<PackedHeader*>(ctx->headers.p);
+        // instances are cleared, walked and verified in groups whose volumes fit in L2 together, so a
+        // volume goes to HBM once (when it is evicted, final) instead of after the clear AND after the walk
+        const uint32_t group = (uint32_t)std::max<size_t>(1, ctx->group_bytes / (size_t)nv);
         for (uint32_t first = 0; first < n; first += chunk) {
             const uint32_t m = std::min(chunk, n - first);
             const BatchPlan plan = fill_batch(ctx, jobs + first, m, vertices_mode);
             for (uint32_t k = 0; k < m; ++k) {
-                ctx->batch.inst[k].ovf_flag = base + (size_t)k * (bm_words + 4);
-                ctx->batch.inst[k].ovf_bitmap = base + (size_t)k * (bm_words + 4) + 4;
+                ctx->batch.inst[k].header = hdr + k;
                 ctx->batch.inst[k].counts = static_cast<uint32_t*>(ctx->counts.p);
             }
-            const unsigned gx = stride_blocks(ctx, nv / 16, 256, m >= 8 ? 2 : 8);
-            {
-                PhaseMark mk(ctx, s, PH_CLEAR);
-                k_clear_packed_batch<<<dim3(gx, m), 256, 0, s>>>(ctx->batch);
-                ctx->launches++;
-            }
-            if (plan.max_tiles[0] + plan.max_tiles[1] + plan.max_tiles[2]) {
+            const bool work = plan.max_tiles[0] + plan.max_tiles[1] + plan.max_tiles[2] != 0;
+            for (uint32_t g0 = 0; g0 < m; g0 += group) {
+                const uint32_t gc = std::min(group, m - g0);
+                const unsigned gx = stride_blocks(ctx, nv / 16, 256, gc >= 8 ? 2 : 8);
+                {
+                    PhaseMark mk(ctx, s, PH_CLEAR);
+                    k_clear_packed_batch<<<dim3(gx, gc), 256, 0, s>>>(ctx->batch, g0);
+                    ctx->launches++;
+                }
+                if (!work) continue;
                 {
                     PhaseMark mk(ctx, s, PH_WALK);
-                    RET_IF(launch_walk<1>(ctx, plan, exact, s));
+                    if (ctx->debug_sink == 2) RET_IF(launch_walk<2>(ctx, plan, exact, g0, gc, s));
+                    else if (ctx->debug_sink == 3) RET_IF(launch_walk<3>(ctx, plan, exact, g0, gc, s));
+                    else if (ctx->debug_sink == 4) RET_IF(launch_walk<4>(ctx, plan, exact, g0, gc, s));
+                    else RET_IF(launch_walk<1>(ctx, plan, exact, g0, gc, s));
                 }
+                PhaseMark mk(ctx, s, PH_FINISH);
+                k_verify_packed_batch<<<dim3(gx, gc), 256, 0, s>>>(ctx->batch, g0);
+                ctx->launches++;
+            }
+            if (work) {
                 PhaseMark mk(ctx, s, PH_FINISH);
                 if (vertices_mode) RET_IF(launch_repair<true>(ctx, static_cast<uint32_t*>(ctx->counts.p), s));
                 else               RET_IF(launch_repair<false>(ctx, static_cast<uint32_t*>(ctx->counts.p), s));
@@ -403,7 +410,7 @@ int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_
                 ctx->batch.inst[k].counts = static_cast<uint32_t*>(ctx->counts.p) + (size_t)k * nv;
             {
                 PhaseMark mk(ctx, s, PH_WALK);
-                RET_IF(launch_walk<0>(ctx, plan, exact, s));
+                RET_IF(launch_walk<0>(ctx, plan, exact, 0, m, s));
             }
             PhaseMark mk(ctx, s, PH_FINISH);
             for (uint32_t k = 0; k < m; ++k) {
@@ -432,7 +439,7 @@ int run_count(vkhr_b200_ctx* ctx, const Job& j, bool vertices_mode, uint32_t fla
     if (plan.max_tiles[0] + plan.max_tiles[1] + plan.max_tiles[2] == 0) return VKHR_B200_OK;
     ctx->batch.inst[0].counts = d_counts;
     PhaseMark mk(ctx, s, PH_WALK);
-    return launch_walk<0>(ctx, plan, (flags & VKHR_B200_INDEX_EXACT) != 0, s);
+    return launch_walk<0>(ctx, plan, (flags & VKHR_B200_INDEX_EXACT) != 0, 0, 1, s);
 }
 
 int stage_in(vkhr_b200_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
@@ -472,6 +479,11 @@ int vkhr_b200_create(int device, vkhr_b200_ctx** out) {
     vkhr_b200_ctx* ctx = new vkhr_b200_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char* e = std::getenv("VKHR_B200_DEBUG_SINK")) ctx->debug_sink = std::string(e) == "null" ? 2 : std::string(e) == "compact" ? 3 : std::string(e) == "quarter" ? 4 : 0;
+    if (const char* e = std::getenv("VKHR_B200_GROUP_MIB")) {      // tuning knob for experiments
+        const long v = std::atol(e);
+        if (v > 0) ctx->group_bytes = (size_t)v << 20;
+    }
     if (cudaSetDevice(device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx;
@@ -491,7 +503,7 @@ void vkhr_b200_destroy(vkhr_b200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->counts, &ctx->bitmap, &ctx->small, &ctx->st_vertices,
+    DevBuf* bufs[] = {&ctx->counts, &ctx->headers, &ctx->small, &ctx->st_vertices,
                       &ctx->st_indices, &ctx->st_tangents, &ctx->st_dens, &ctx->st_tang_out};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -793,6 +805,30 @@ int vkhr_b200_generate_bounding_box(vkhr_b200_ctx* ctx, const float* vertices, u
     RET_IF(vkhr_b200_generate_bounding_box_dev(ctx, static_cast<const float*>(ctx->st_vertices.p), n_vertices, d_out, ctx->stream));
     CU_CHECK(ctx, cudaMemcpyAsync(aabb_out, d_out, 24, cudaMemcpyDeviceToHost, ctx->stream));
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return VKHR_B200_OK;
+}
+
+// ---- measurement only: per-CTA trace of the walk kernel ------------------------------
+int vkhr_b200_debug_trace(vkhr_b200_ctx* ctx, int enable, unsigned long long* host_out, uint32_t max_records, uint32_t* n_records) {
+    RET_IF(bind(ctx));
+    static unsigned long long* d_buf = nullptr;
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    CU_CHECK(ctx, cudaDeviceSynchronize());
+    if (enable) {
+        if (!d_buf) CU_CHECK(ctx, cudaMalloc(&d_buf, (size_t)(1u << 20) * 32));
+        unsigned int zero = 0;
+        CU_CHECK(ctx, cudaMemcpyToSymbol(g_cta_trace_count, &zero, 4));
+        CU_CHECK(ctx, cudaMemcpyToSymbol(g_cta_trace, &d_buf, 8));
+        return VKHR_B200_OK;
+    }
+    unsigned long long* null = nullptr;
+    unsigned int n = 0;
+    CU_CHECK(ctx, cudaMemcpyToSymbol(g_cta_trace, &null, 8));
+    CU_CHECK(ctx, cudaMemcpyFromSymbol(&n, g_cta_trace_count, 4));
+    if (n > max_records) n = max_records;
+    if (n > (1u << 20)) n = 1u << 20;
+    if (host_out && n && d_buf) CU_CHECK(ctx, cudaMemcpy(host_out, d_buf, (size_t)n * 32, cudaMemcpyDeviceToHost));
+    if (n_records) *n_records = n;
     return VKHR_B200_OK;
 }
 

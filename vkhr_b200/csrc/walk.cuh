@@ -26,6 +26,7 @@ struct GridParams {
     uint32_t n_voxels;         // W*H*D  (< 2^32, checked on the host)
     uint32_t index_exact;      // VKHR_B200_INDEX_EXACT
     float rvx, rvy, rvz;       // RN(1 / voxel_size), or 0 when the fast exact division must not be used
+    uint32_t fast_div;         // all three reciprocals are usable (warp-cooperative fast path)
 };
 
 // Correctly rounded a / d for d > 0, given y = RN(1/d) (0 = not available).
@@ -166,6 +167,121 @@ __device__ __forceinline__ void walk_segment(const GridParams& g,
         to_voxel_space(ax, g.ox, g.vsx, g.rvx), to_voxel_space(ay, g.oy, g.vsy, g.rvy), to_voxel_space(az, g.oz, g.vsz, g.rvz),
         to_voxel_space(bx, g.ox, g.vsx, g.rvx), to_voxel_space(by, g.oy, g.vsy, g.rvy), to_voxel_space(bz, g.oz, g.vsz, g.rvz),
         sink);
+}
+
+// ---------------------------------------------------------------------------
+// Warp-cooperative fast path.
+//
+// The per-operand range guards of div_exact cost two compares and a divergent
+// branch per division, six divisions per segment.  The hot kernels instead
+// evaluate the guards of all operands of a warp at once, vote, and take ONE
+// warp-uniform branch: either every lane runs the branch-free FMA division
+// (div_fast) and the single-instruction fminf clamp, or the whole warp runs the
+// literal IEEE code above.  Both sides compute the same bits; only the cost
+// differs.  All 32 lanes must call these functions together.
+// ---------------------------------------------------------------------------
+constexpr unsigned kFullWarp = 0xFFFFFFFFu;
+
+// Pin a kernel-parameter value into a register.  The batch is a dynamically indexed __grid_constant__
+// array, so every use of a per-instance constant is otherwise an indexed constant load (LDC c[0][R+imm]),
+// re-issued inside the loops and tracked on the long scoreboard like a memory operation.
+__device__ __forceinline__ float pin(float v) { asm volatile("" : "+f"(v)); return v; }
+__device__ __forceinline__ uint32_t pin(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
+__device__ __forceinline__ GridParams pin(const GridParams& c) {
+    GridParams g;
+    g.ox = pin(c.ox); g.oy = pin(c.oy); g.oz = pin(c.oz);
+    g.vsx = pin(c.vsx); g.vsy = pin(c.vsy); g.vsz = pin(c.vsz);
+    g.rx1 = pin(c.rx1); g.ry1 = pin(c.ry1); g.rz1 = pin(c.rz1);
+    g.Wf = pin(c.Wf); g.Hf = pin(c.Hf);
+    g.W = c.W; g.H = c.H; g.D = c.D;                       // exact-index mode only
+    g.n_voxels = pin(c.n_voxels);
+    g.index_exact = c.index_exact;
+    g.rvx = pin(c.rvx); g.rvy = pin(c.rvy); g.rvz = pin(c.rvz);
+    g.fast_div = pin(c.fast_div);
+    return g;
+}
+
+// |a| in [2^-60, 2^60], or zero.  (A zero numerator gives +-0 on either path; the sign of a
+// zero coordinate never reaches the voxel index: floor, min and the index sum map both to 0.)
+__device__ __forceinline__ bool div_fast_ok(float a) {
+    const float aa = fabsf(a);
+    return (aa <= 1.1529215e18f) && (aa >= 8.6736174e-19f || aa == 0.0f);
+}
+// The Markstein sequence of div_exact without its guard.
+__device__ __forceinline__ float div_fast(float a, float d, float y) {
+    const float q0 = __fmul_rn(a, y);
+    const float r0 = __fmaf_rn(-q0, d, a);
+    const float q1 = __fmaf_rn(r0, y, q0);
+    const float r1 = __fmaf_rn(-q1, d, a);
+    return __fmaf_rn(r1, y, q1);
+}
+
+// (v - origin) / voxel_size for one vertex per lane (hair_style.cc:274, :312-313).
+__device__ __forceinline__ void to_voxel_space_warp(const GridParams& g, float wx, float wy, float wz,
+                                                    float& px, float& py, float& pz) {
+    const float ax = __fsub_rn(wx, g.ox), ay = __fsub_rn(wy, g.oy), az = __fsub_rn(wz, g.oz);
+    const bool ok = div_fast_ok(ax) && div_fast_ok(ay) && div_fast_ok(az);
+    if (g.fast_div && __all_sync(kFullWarp, ok)) {
+        px = div_fast(ax, g.vsx, g.rvx);
+        py = div_fast(ay, g.vsy, g.rvy);
+        pz = div_fast(az, g.vsz, g.rvz);
+    } else {
+        px = __fdiv_rn(ax, g.vsx);
+        py = __fdiv_rn(ay, g.vsy);
+        pz = __fdiv_rn(az, g.vsz);
+    }
+}
+
+// One sample of the walk for finite positions: voxel, fp32 (or exact) linear index, range test.
+template <int EXACT>
+__device__ __forceinline__ bool sample_index(const GridParams& g, float rx, float ry, float rz, uint32_t& idx) {
+    const float vx = fminf(floorf(rx), g.rx1);
+    const float vy = fminf(floorf(ry), g.ry1);
+    const float vz = fminf(floorf(rz), g.rz1);
+    if (EXACT == 0 || (EXACT < 0 && !g.index_exact)) {
+        const float f = __fadd_rn(__fadd_rn(vx, __fmul_rn(vy, g.Wf)), __fmul_rn(__fmul_rn(vz, g.Wf), g.Hf));
+        idx = __float2uint_rz(f);                       // NaN and negatives -> 0 (caught by f >= 0), >= 2^32 -> 0xFFFFFFFF
+        return (f >= 0.0f) && idx < g.n_voxels;
+    } else {
+        const long long li = (long long)__float2int_rz(vx) + (long long)__float2int_rz(vy) * (long long)g.W +
+                             (long long)__float2int_rz(vz) * ((long long)g.W * (long long)g.H);
+        idx = (uint32_t)li;
+        return (fabsf(vx) < 2147483648.0f) && (fabsf(vy) < 2147483648.0f) && (fabsf(vz) < 2147483648.0f) &&
+               li >= 0 && li < (long long)g.n_voxels;
+    }
+}
+
+// The sampled walk of one segment per lane, end points in voxel space (hair_style.cc:315-328).
+// `active` = this lane has a segment.
+template <int EXACT, class Sink>
+__device__ __forceinline__ void walk_voxel_space_warp(const GridParams& g, bool active,
+                                                      float rx, float ry, float rz,
+                                                      float tx, float ty, float tz, Sink& sink) {
+    float dx = __fsub_rn(tx, rx), dy = __fsub_rn(ty, ry), dz = __fsub_rn(tz, rz);
+    float steps = glm_max(glm_max(fabsf(dx), fabsf(dy)), fabsf(dz));          // compMax(abs(direction))
+    const bool go = active && (steps > 0.0f) && (steps < 16777216.0f);        // 0 / NaN: no samples; >= 2^24: never ends
+    // fast when the root is finite (then every later position is finite too: |root| + 2^24 |dir|, so
+    // glm::min == fminf) and the three divisions by `steps` are inside the FMA division's range
+    const bool fast = !go || ((steps >= 9.094947e-13f) && div_fast_ok(dx) && div_fast_ok(dy) && div_fast_ok(dz) &&
+                              (__fadd_rn(__fadd_rn(fabsf(rx), fabsf(ry)), fabsf(rz)) < 3.0e38f));
+    if (__all_sync(kFullWarp, fast)) {
+        if (go) {
+            const float y = __frcp_rn(steps);                                 // RN(1/steps)
+            dx = div_fast(dx, steps, y);
+            dy = div_fast(dy, steps, y);
+            dz = div_fast(dz, steps, y);
+            do {                                                              // while (steps-- > 0.0f)
+                uint32_t idx;
+                if (sample_index<EXACT>(g, rx, ry, rz, idx)) sink.template put<0>(idx);
+                rx = __fadd_rn(rx, dx);
+                ry = __fadd_rn(ry, dy);
+                rz = __fadd_rn(rz, dz);
+                steps = __fsub_rn(steps, 1.0f);
+            } while (steps > 0.0f);
+        }
+    } else if (go) {
+        walk_voxel_space<EXACT>(g, rx, ry, rz, tx, ty, tz, sink);             // the literal code, any input
+    }
 }
 
 // Vertex pair of segment `s`.  indices == nullptr => uniform strands of
