@@ -42,5 +42,9 @@ T = t1.max() - base
 edges = np.linspace(0, T, 21)
 for a, b in zip(edges[:-1], edges[1:]):
     running = ((t0 - base < b) & (t1 - base > a)).sum()
-    print("  %6.1f-%6.1f us: %d CTAs alive" % (a / 1e3, b / 1e3, running))
+    pass
+cls = {}
+for i in range(148):
+    cls.setdefault(int(round(per_sm_dur[i])), []).append(i)
+print("duration classes (us: #SMs):", {k: len(v) for k, v in sorted(cls.items())})
 json.dump({"n": int(n.value), "sm": sm.tolist(), "t0": (t0 - base).tolist(), "t1": (t1 - base).tolist()}, open("gpurun_out/cta_trace.json", "w"))

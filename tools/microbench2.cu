@@ -101,6 +101,59 @@ __global__ void k_nored_mio(const float* table, uint32_t per_thread, float* out)
     if (f == 12345.678f) *out = f;
 }
 
+// A synthetic copy of the walk kernel's control structure: per "tile" a block of arithmetic with LDS + SHFL + VOTE,
+// then a per-lane sample loop with a data-dependent trip count (DIVERGE) whose body ends in a predicated red.
+// RED 0 = no red (index folded into a register), 1 = red.  UNIFORM trip count = 2 when DIVERGE == 0.
+template <int RED, int DIVERGE, int VOTE, int STAGE = 0>
+__global__ void k_mimic(uint32_t* grid, uint32_t tiles, float* out, const float* stream = nullptr) {
+    __shared__ float s[256 * 3];
+    __shared__ float st[8][768];
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u, warp = tid >> 5;
+    for (uint32_t i = threadIdx.x; i < 768; i += blockDim.x) s[i] = (float)i * 1e-3f;
+    __syncthreads();
+    if (STAGE) {                                   // every warp first streams its own 3 KB from HBM (as the walk kernel does)
+        float v[24];
+#pragma unroll
+        for (int j = 0; j < 24; ++j) v[j] = __ldg(stream + (size_t)warp * 768 + lane + 32 * j);
+#pragma unroll
+        for (int j = 0; j < 24; ++j) st[threadIdx.x >> 5][lane + 32 * j] = v[j];
+        __syncwarp();
+    }
+    float f = (float)tid * 1e-3f;
+    uint32_t acc = 0;
+    for (uint32_t t = 0; t < tiles; ++t) {
+        const uint32_t h = hash32(warp * 0x9E3779B9u + t * 0x85EBCA6Bu);
+        const uint32_t j = (h + lane) & 255u;
+        float a = s[3 * j], b = s[3 * j + 1], c = s[3 * j + 2];
+        if (STAGE) { a += st[threadIdx.x >> 5][93 * (t & 7u) + 3 * lane]; b += st[threadIdx.x >> 5][93 * (t & 7u) + 3 * lane + 1]; c += st[threadIdx.x >> 5][93 * (t & 7u) + 3 * lane + 2]; }
+#pragma unroll
+        for (int k = 0; k < 20; ++k) { a = __fmaf_rn(a, 1.0000001f, f); b = __fmaf_rn(b, 1.0000001f, a); c = __fmaf_rn(c, 1.0000001f, b); }
+        if (VOTE) { if (!__all_sync(0xFFFFFFFFu, a == a)) c += 1.0f; }
+        const float ta = __shfl_down_sync(0xFFFFFFFFu, a, 1), tb = __shfl_down_sync(0xFFFFFFFFu, b, 1), tc = __shfl_down_sync(0xFFFFFFFFu, c, 1);
+        float da = ta - a, db = tb - b, dc = tc - c;
+#pragma unroll
+        for (int k = 0; k < 15; ++k) { da = __fmaf_rn(da, 0.999f, dc); db = __fmaf_rn(db, 0.999f, da); dc = __fmaf_rn(dc, 0.999f, db); }
+        if (VOTE) { if (!__all_sync(0xFFFFFFFFu, da == da)) dc += 1.0f; }
+        const uint32_t hh = hash32(tid * 0x9E3779B9u + t);
+        const bool active = (hh & 7u) != 0u;                                   // 28 of 32 lanes
+        uint32_t n = DIVERGE ? (1u + ((hh >> 3) & 1u) + (((hh >> 4) & 15u) == 0u ? 1u : 0u) + ((hh >> 8) & 1u)) : 2u;   // mean ~2.06
+        uint32_t x = hh & 255u, y = (hh >> 8) & 255u, z = (hh >> 16) & 255u;
+        if (active) {
+            do {
+                const float fx = fminf(floorf(a), 255.0f), fy = fminf(floorf(b), 255.0f), fz = fminf(floorf(c), 255.0f);
+                const float fi = __fadd_rn(__fadd_rn(fx, __fmul_rn(fy, 256.0f)), __fmul_rn(__fmul_rn(fz, 256.0f), 256.0f));
+                uint32_t idx = (__float2uint_rz(fi) & 1u) ^ (x + (y << 8) + (z << 16));
+                if (fi >= 0.0f && idx < (1u << 24)) {
+                    if (RED) atomicAdd(grid + (idx >> 2), 1u << ((idx & 3u) * 8u)); else acc += idx;
+                }
+                a += da; b += db; c += dc; y = (y + 1u) & 255u;
+            } while (--n);
+        }
+        f = a * 1e-9f;
+    }
+    if (f == 12345.678f || acc == 0xDEADBEEF) *out = f;
+}
+
 __global__ void k_fill(uint4* p, uint64_t n16) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) p[i] = make_uint4(0, 0, 0, 0);
 }
@@ -184,6 +237,24 @@ int main() {
         RUNP("balance_fma192_lds3", 96)
         RUNP("balance_fma256_lds3", 128)
         RUNP("balance_fma384_lds3", 192)
+    }
+    {
+        const int blocks = 148 * 6 * 4, threads = 256; const uint32_t tiles = 8;     // ~4 waves of 6 CTAs/SM
+        const double lanes = (double)blocks * threads * tiles * 0.875 * 2.06;
+#define RUNK(name, D, V) { \
+            float w = time_ms([&] { k_mimic<1, D, V><<<blocks, threads>>>(grid, tiles, out); }, 5); \
+            float n = time_ms([&] { k_mimic<0, D, V><<<blocks, threads>>>(grid, tiles, out); }, 5); \
+            printf(" \"%s\": {\"with_red_us\": %.1f, \"without_red_us\": %.1f, \"red_alone_at_220G_us\": %.1f},\n", name, w * 1e3, n * 1e3, lanes / 220e3); }
+        RUNK("mimic_uniform_novote", 0, 0)
+        RUNK("mimic_uniform_vote", 0, 1)
+        RUNK("mimic_diverge_novote", 1, 0)
+        RUNK("mimic_diverge_vote", 1, 1)
+        {
+            const float* stream = (const float*)flush;      // 512 MiB, far larger than what one launch reads (87 MB)
+            float w = time_ms([&] { k_mimic<1, 1, 1, 1><<<blocks, threads>>>(grid, tiles, out, stream); }, 5);
+            float n = time_ms([&] { k_mimic<0, 1, 1, 1><<<blocks, threads>>>(grid, tiles, out, stream); }, 5);
+            printf(" \"mimic_diverge_vote_staged\": {\"with_red_us\": %.1f, \"without_red_us\": %.1f, \"red_alone_at_220G_us\": %.1f},\n", w * 1e3, n * 1e3, lanes / 220e3);
+        }
     }
     printf(" \"sm_clock_max_mhz\": %.0f\n}\n", clk / 1e6);
     return 0;

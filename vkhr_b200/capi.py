@@ -13,7 +13,7 @@ import re
 
 from . import build as _build
 
-LIB_PATH = _build.LIB
+LIB_PATH = os.environ.get("VKHR_B200_LIB") or _build.LIB      # override: A/B builds of the same ABI (measurement)
 HEADER_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "include", "vkhr_b200.h")
 
 # status codes / flags (include/vkhr_b200.h)

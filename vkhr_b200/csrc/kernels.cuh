@@ -12,16 +12,12 @@
 namespace vkhr_b200 {
 
 constexpr int kWalkThreads = 256;
+#ifndef VKHR_WALK_MIN_CTAS
+#define VKHR_WALK_MIN_CTAS 5
+#endif
 
 // How an instance's work is tiled over CTAs.
 enum WalkKind : uint32_t { WK_UNIFORM = 0, WK_INDEXED = 1, WK_SPLAT = 2 };
-
-// Per-instance bookkeeping of the PACKED8 strategy (device memory, zeroed by the clear kernel).
-struct PackedHeader {
-    unsigned long long samples;     // samples the walk added to the grid
-    unsigned long long byte_sum;    // sum of the grid's bytes after the walk (k_verify_packed_batch)
-    uint32_t pad[4];
-};
 
 // Device-side description of one instance of a batch.
 struct InstanceDev {
@@ -33,7 +29,8 @@ struct InstanceDev {
     GridParams      grid;
     uint8_t*        densities;      // W*H*D u8 (PACKED8: counted in place)
     uint32_t*       counts;         // W*H*D u32 (COUNT32 / recount scratch) or nullptr
-    PackedHeader*   header;         // PACKED8 only
+    uint32_t*       ovf_bitmap;     // PACKED8: 1 bit per 32-bit word of `densities`
+    uint32_t*       ovf_flag;       // PACKED8: != 0 when any word overflowed
     uint32_t        n_tiles;        // CTAs this instance needs in its walk kernel
     uint32_t        kind;           // WalkKind
     uint32_t        vps_magic;      // floor(2^32 / (segs_per_strand + 1)) + 1   (strand-end test without a division)
@@ -63,77 +60,63 @@ struct SinkCount32 {
     __device__ __forceinline__ void finish() {}
 };
 
-// PACKED8: the u8 output grid itself is the counter.  Four voxels share one 32-bit
-// word and a hit adds 1 << (8 * byte) with a fire-and-forget `red.global.add.u32`:
-// nothing returns to the SM, so a sample costs one L1TEX wavefront instead of the
-// request + reply of an `atom`.  A byte that receives more than 255 hits carries
-// into its neighbour, which no thread can see -- but the grid can prove afterwards
-// that it did not happen: the sum of all bytes of a word equals the number of hits
-// the word received if and only if no byte carried (every carry lowers the digit sum
-// by 255, a carry out of the word by 256, nothing raises it).  So each warp counts
-// the samples it adds (one u64 atomic per warp per kernel), k_verify_packed_batch
-// sums the bytes, and an instance whose two numbers differ is recounted exactly in
-// u32 by k_repair_packed.  With no voxel above 255 -- every hair style at a useful
-// resolution -- the volume is final after the verify pass.
+// PACKED8: the u8 output grid itself is the counter; four voxels share one
+// 32-bit word and a hit adds 1 << (8 * byte).  The returned old word tells
+// the adding thread whether ITS add carried out of the byte (old field ==
+// 255).  The first carry in a word is always seen on a clean word, so a word
+// is flagged in the bitmap if and only if one of its voxels received more
+// than 255 hits; flagged words are recounted exactly by k_repair_packed.
+// Returned words are examined kDepth samples later (a ring of kDepth pending
+// results in registers, slot chosen at compile time by the unrolled walk), so
+// up to kDepth atomics of a thread are in flight and their round trips overlap
+// the arithmetic of the following samples.
+// (A fire-and-forget `red` with a byte-sum verification pass was measured as
+// well -- DESIGN.md "what was tried": the walk is no faster, because the cost
+// of a sample is its 32-byte request packet to L2 either way, and the extra
+// pass over the grid is not free.)
 struct SinkPacked8 {
+    static constexpr int kDepth = 4;
     uint32_t* words;
-    unsigned long long* samples;
-    uint32_t n_put = 0;
-    template <int SLOT = 0>
+    uint32_t* ovf_bitmap;
+    uint32_t* ovf_flag;
+    uint32_t pend_old[kDepth] = {0, 0, 0, 0};
+    uint32_t pend_idx[kDepth] = {0, 0, 0, 0};
+    template <int SLOT>
+    __device__ __forceinline__ void check() {
+        // byte (idx & 3) of the word as it was before this thread's add
+        if (__byte_perm(pend_old[SLOT], 0u, 0x4440u | (pend_idx[SLOT] & 3u)) == 0xFFu) {
+            const uint32_t w = pend_idx[SLOT] >> 2;
+            atomicOr(ovf_bitmap + (w >> 5), 1u << (w & 31u));
+            *ovf_flag = 1u;
+        }
+    }
+    template <int SLOT>
     __device__ __forceinline__ void put(uint32_t idx) {
-        atomicAdd(words + (idx >> 2), 1u << ((idx & 3u) * 8u));      // result unused: RED.E.ADD
-        ++n_put;
+        check<SLOT>();
+        pend_old[SLOT] = atomicAdd(words + (idx >> 2), 1u << ((idx & 3u) * 8u));
+        pend_idx[SLOT] = idx;
     }
-    // all 32 lanes of the warp, converged
-    __device__ __forceinline__ void finish() {
-        const uint32_t n = __reduce_add_sync(kFullWarp, n_put);
-        if ((threadIdx.x & 31u) == 0u && n) atomicAdd(samples, (unsigned long long)n);
-    }
+    __device__ __forceinline__ void finish() { check<0>(); check<1>(); check<2>(); check<3>(); }
 };
 
-// Measurement only (VKHR_B200_DEBUG_SINK=null): counts samples, touches no grid -- the walk without its reds.
-struct SinkNull {
-    unsigned long long* samples;
-    uint32_t n_put = 0;
-    template <int SLOT = 0>
-    __device__ __forceinline__ void put(uint32_t idx) { n_put += (idx & 1u) + 1u; }
-    __device__ __forceinline__ void finish() {
-        const uint32_t n = __reduce_add_sync(kFullWarp, n_put);
-        if ((threadIdx.x & 31u) == 0u && n) atomicAdd(samples, (unsigned long long)n);
-    }
-};
-
-// Measurement only: VARIANT 0 = every red lands in a 4 KB window (lanes coalesce), 1 = only every 4th sample is added.
-template <int VARIANT>
-struct SinkProbe {
-    uint32_t* words;
-    unsigned long long* samples;
-    uint32_t n_put = 0;
+// Recount pass of PACKED8: only samples landing in flagged words are counted,
+// into the u32 scratch grid.
+struct SinkRecount {
+    const uint32_t* ovf_bitmap;
+    uint32_t* counts;
     template <int SLOT = 0>
     __device__ __forceinline__ void put(uint32_t idx) {
-        if (VARIANT == 0) atomicAdd(words + ((idx >> 2) & 1023u), 1u << ((idx & 3u) * 8u));
-        else if ((n_put & 3u) == 0u) atomicAdd(words + (idx >> 2), 1u << ((idx & 3u) * 8u));
-        ++n_put;
+        const uint32_t w = idx >> 2;
+        if ((__ldg(ovf_bitmap + (w >> 5)) >> (w & 31u)) & 1u) atomicAdd(counts + idx, 1u);
     }
-    __device__ __forceinline__ void finish() {
-        const uint32_t n = __reduce_add_sync(kFullWarp, n_put);
-        if ((threadIdx.x & 31u) == 0u && n) atomicAdd(samples, (unsigned long long)n);
-    }
+    __device__ __forceinline__ void finish() {}
 };
 
 template <int MODE> struct SinkOf;
 template <> struct SinkOf<0> { using type = SinkCount32;
     __device__ static type make(const InstanceDev& I) { return SinkCount32{I.counts}; } };
 template <> struct SinkOf<1> { using type = SinkPacked8;
-    __device__ static type make(const InstanceDev& I) { SinkPacked8 k; k.words = reinterpret_cast<uint32_t*>(I.densities); k.samples = &I.header->samples; return k; } };
-
-template <> struct SinkOf<2> { using type = SinkNull;
-    __device__ static type make(const InstanceDev& I) { SinkNull k; k.samples = &I.header->samples; return k; } };
-
-template <> struct SinkOf<3> { using type = SinkProbe<0>;
-    __device__ static type make(const InstanceDev& I) { SinkProbe<0> k; k.words = reinterpret_cast<uint32_t*>(I.densities); k.samples = &I.header->samples; return k; } };
-template <> struct SinkOf<4> { using type = SinkProbe<1>;
-    __device__ static type make(const InstanceDev& I) { SinkProbe<1> k; k.words = reinterpret_cast<uint32_t*>(I.densities); k.samples = &I.header->samples; return k; } };
+    __device__ static type make(const InstanceDev& I) { SinkPacked8 k; k.words = reinterpret_cast<uint32_t*>(I.densities); k.ovf_bitmap = I.ovf_bitmap; k.ovf_flag = I.ovf_flag; return k; } };
 
 // ---------------------------------------------------------------------------
 // Walk kernel for uniform strands (no index buffer): the hot kernel.
@@ -189,7 +172,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long l
 __device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
 
 template <int MODE, int EXACT>
-__global__ void __launch_bounds__(kWalkThreads)
+__global__ void __launch_bounds__(kWalkThreads, VKHR_WALK_MIN_CTAS)
 k_walk_uniform(const __grid_constant__ Batch B, uint32_t first) {
     __shared__ __align__(128) float s_stage[kWarpsPerBlock][kStageFloats];
     const unsigned long long t_start = g_cta_trace ? globaltimer_ns() : 0ull;
@@ -358,7 +341,7 @@ __global__ void __launch_bounds__(256) k_zero16(uint4* __restrict__ p, uint64_t 
         p[i] = z;
 }
 
-// PACKED8 clear for a batch: densities and header of every instance.
+// PACKED8 clear for a batch: densities, overflow bitmap and flag of every instance.
 // blockIdx.y + first = instance.  n_voxels % 16 == 0 is guaranteed by the host (else COUNT32).
 __global__ void __launch_bounds__(256) k_clear_packed_batch(const __grid_constant__ Batch B, uint32_t first) {
     const InstanceDev& I = B.inst[first + blockIdx.y];
@@ -368,31 +351,9 @@ __global__ void __launch_bounds__(256) k_clear_packed_batch(const __grid_constan
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     for (uint32_t i = t; i < n16; i += stride) d[i] = z;
-    if (t < 2) reinterpret_cast<uint4*>(I.header)[t] = z;
-}
-
-// PACKED8 verify: header.byte_sum = sum of all bytes of the instance's grid (see SinkPacked8).
-// Reads go to L2 only (ld.global.cg): the grid was just written there by the reds.
-__global__ void __launch_bounds__(256) k_verify_packed_batch(const __grid_constant__ Batch B, uint32_t first) {
-    const InstanceDev& I = B.inst[first + blockIdx.y];
-    const uint4* d = reinterpret_cast<const uint4*>(I.densities);
-    const uint32_t n16 = I.grid.n_voxels >> 4;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    uint32_t a0 = 0, a1 = 0;                               // <= 2^28 * 255 / (threads >= 256) each: no overflow
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
-        const uint4 v = __ldcg(d + i);
-        a0 = __dp4a(v.x, 0x01010101u, a0);
-        a1 = __dp4a(v.y, 0x01010101u, a1);
-        a0 = __dp4a(v.z, 0x01010101u, a0);
-        a1 = __dp4a(v.w, 0x01010101u, a1);
-    }
-    __shared__ unsigned long long s_sum;
-    if (threadIdx.x == 0) s_sum = 0ull;
-    __syncthreads();
-    const unsigned long long w = (unsigned long long)__reduce_add_sync(kFullWarp, a0) + __reduce_add_sync(kFullWarp, a1);
-    if ((threadIdx.x & 31u) == 0u && w) atomicAdd(&s_sum, w);
-    __syncthreads();
-    if (threadIdx.x == 0 && s_sum) atomicAdd(&I.header->byte_sum, s_sum);
+    const uint32_t n_bm = (I.grid.n_voxels / 4 + 31) / 32;          // bitmap words
+    for (uint32_t i = t; i < n_bm; i += stride) I.ovf_bitmap[i] = 0u;
+    if (t == 0) *I.ovf_flag = 0u;
 }
 
 // densities = min(counts, 255)  (hair_style.cc:322: `if (d != 255) d += 1`),

@@ -23,39 +23,44 @@ namespace cg = cooperative_groups;
 using namespace vkhr_b200;
 
 // ---------------------------------------------------------------------------
-// PACKED8 repair: one persistent cooperative kernel.  An instance whose verify
-// pass found sum(bytes) != samples had a voxel above 255 hits (see SinkPacked8);
-// such instances are recounted exactly, one after the other, on a shared u32
-// scratch grid:
-//   zero the scratch -> grid barrier -> re-walk the instance into it ->
-//   grid barrier -> rewrite the u8 grid as min(count, 255).
-// With no mismatch (the common case) every CTA returns after reading n headers.
+// PACKED8 repair: one persistent cooperative kernel.  Instances whose overflow
+// flag is set (some voxel received more than 255 hits) are handled one after
+// the other on a single shared u32 scratch grid:
+//   zero the scratch entries of flagged words -> grid barrier ->
+//   re-walk the instance, counting only samples that land in flagged words ->
+//   grid barrier -> rewrite the flagged words as min(count, 255).
+// With no flag set (the common case) every CTA returns after reading n flags.
 // ---------------------------------------------------------------------------
 template <bool VERTICES>
 __global__ void __launch_bounds__(kWalkThreads)
 k_repair_packed(const __grid_constant__ Batch B, uint32_t* __restrict__ scratch) {
-    // common case first: nothing overflowed -> one parallel look at the headers and out
+    // common case first: no instance overflowed -> one parallel look at the flags and out
     const uint32_t n_inst = B.n;
     const InstanceDev* inst = B.inst;
     int any = 0;
-    for (uint32_t k = threadIdx.x; k < n_inst; k += blockDim.x) {
-        const PackedHeader h = *inst[k].header;
-        any |= (h.samples != h.byte_sum);
-    }
+    for (uint32_t k = threadIdx.x; k < n_inst; k += blockDim.x) any |= (*inst[k].ovf_flag != 0u);
     if (!__syncthreads_or(any)) return;                        // same answer in every CTA
     cg::grid_group grid = cg::this_grid();
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t nthreads = gridDim.x * blockDim.x;
     for (uint32_t k = 0; k < n_inst; ++k) {
         const InstanceDev& I = inst[k];
-        if (I.header->samples == I.header->byte_sum) continue; // uniform across the grid
+        if (*I.ovf_flag == 0u) continue;                       // uniform across the grid
         const GridParams g = I.grid;
         const uint32_t n_words = g.n_voxels >> 2;
+        const uint32_t n_bm = (n_words + 31) / 32;
         uint32_t* words = reinterpret_cast<uint32_t*>(I.densities);
         uint4* counts4 = reinterpret_cast<uint4*>(scratch);
-        for (uint32_t w = tid; w < n_words; w += nthreads) counts4[w] = make_uint4(0, 0, 0, 0);
+        for (uint32_t b = tid; b < n_bm; b += nthreads) {
+            uint32_t m = I.ovf_bitmap[b];
+            while (m) {
+                const uint32_t w = b * 32 + (__ffs(m) - 1);
+                m &= m - 1;
+                if (w < n_words) counts4[w] = make_uint4(0, 0, 0, 0);
+            }
+        }
         grid.sync();
-        SinkCount32 sink{scratch};
+        SinkRecount sink{I.ovf_bitmap, scratch};
         if (VERTICES) {
             for (uint32_t i = tid; i < I.n_vertices; i += nthreads) {
                 const float* v = I.vertices + 3ull * i;
@@ -80,7 +85,14 @@ k_repair_packed(const __grid_constant__ Batch B, uint32_t* __restrict__ scratch)
             }
         }
         grid.sync();
-        for (uint32_t w = tid; w < n_words; w += nthreads) words[w] = clamp4(counts4[w]);
+        for (uint32_t b = tid; b < n_bm; b += nthreads) {
+            uint32_t m = I.ovf_bitmap[b];
+            while (m) {
+                const uint32_t w = b * 32 + (__ffs(m) - 1);
+                m &= m - 1;
+                if (w < n_words) words[w] = clamp4(counts4[w]);
+            }
+        }
         grid.sync();                                           // scratch is reused by the next flagged instance
     }
 }
@@ -101,9 +113,7 @@ struct vkhr_b200_ctx {
     uint64_t launches = 0;
     DevBuf counts;        // u32 scratch grid(s)
     size_t counts_clean_bytes = 0;   // leading bytes of `counts` known to be zero
-    DevBuf headers;       // PACKED8 per-instance PackedHeader
-    int debug_sink = 0;               // measurement only (VKHR_B200_DEBUG_SINK): results are wrong by design
-    size_t group_bytes = 64u << 20;   // PACKED8: volumes cleared + walked + verified together (kept L2-resident)
+    DevBuf bitmap;        // PACKED8 overflow bitmaps (+ flags at the front)
     DevBuf small;         // lohi[2] + aabb keys[6] + aabb floats[6]
     DevBuf st_vertices, st_indices, st_tangents, st_dens, st_tang_out;   // host-API staging
     int repair_blocks[2] = {0, 0};
@@ -346,44 +356,32 @@ int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_
         return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "PACKED8 needs W*H*D % 16 == 0 and 16-byte aligned densities");
 
     if (packed) {
-        // scratch: one PackedHeader per instance, one shared u32 recount grid (touched only after an overflow)
+        // scratch: per-instance overflow bitmap + flag, one shared u32 recount grid
+        const size_t bm_words = ((nv / 4 + 31) / 32 + 3) & ~size_t(3);
         const uint32_t chunk = std::min<uint32_t>(n, kMaxBatch);
-        RET_IF(reserve(ctx, ctx->headers, (size_t)chunk * sizeof(PackedHeader)));
+        RET_IF(reserve(ctx, ctx->bitmap, (size_t)chunk * (bm_words + 4) * 4));
         RET_IF(reserve(ctx, ctx->counts, nv * 4));
         ctx->counts_clean_bytes = 0;                   // the recount may leave entries behind
-        PackedHeader* hdr = static_cast<PackedHeader*>(ctx->headers.p);
-        // instances are cleared, walked and verified in groups whose volumes fit in L2 together, so a
-        // volume goes to HBM once (when it is evicted, final) instead of after the clear AND after the walk
-        const uint32_t group = (uint32_t)std::max<size_t>(1, ctx->group_bytes / (size_t)nv);
+        uint32_t* base = static_cast<uint32_t*>(ctx->bitmap.p);
         for (uint32_t first = 0; first < n; first += chunk) {
             const uint32_t m = std::min(chunk, n - first);
             const BatchPlan plan = fill_batch(ctx, jobs + first, m, vertices_mode);
             for (uint32_t k = 0; k < m; ++k) {
-                ctx->batch.inst[k].header = hdr + k;
+                ctx->batch.inst[k].ovf_flag = base + (size_t)k * (bm_words + 4);
+                ctx->batch.inst[k].ovf_bitmap = base + (size_t)k * (bm_words + 4) + 4;
                 ctx->batch.inst[k].counts = static_cast<uint32_t*>(ctx->counts.p);
             }
-            const bool work = plan.max_tiles[0] + plan.max_tiles[1] + plan.max_tiles[2] != 0;
-            for (uint32_t g0 = 0; g0 < m; g0 += group) {
-                const uint32_t gc = std::min(group, m - g0);
-                const unsigned gx = stride_blocks(ctx, nv / 16, 256, gc >= 8 ? 2 : 8);
-                {
-                    PhaseMark mk(ctx, s, PH_CLEAR);
-                    k_clear_packed_batch<<<dim3(gx, gc), 256, 0, s>>>(ctx->batch, g0);
-                    ctx->launches++;
-                }
-                if (!work) continue;
-                {
-                    PhaseMark mk(ctx, s, PH_WALK);
-                    if (ctx->debug_sink == 2) RET_IF(launch_walk<2>(ctx, plan, exact, g0, gc, s));
-                    else if (ctx->debug_sink == 3) RET_IF(launch_walk<3>(ctx, plan, exact, g0, gc, s));
-                    else if (ctx->debug_sink == 4) RET_IF(launch_walk<4>(ctx, plan, exact, g0, gc, s));
-                    else RET_IF(launch_walk<1>(ctx, plan, exact, g0, gc, s));
-                }
-                PhaseMark mk(ctx, s, PH_FINISH);
-                k_verify_packed_batch<<<dim3(gx, gc), 256, 0, s>>>(ctx->batch, g0);
+            const unsigned gx = stride_blocks(ctx, nv / 16, 256, m >= 8 ? 2 : 8);
+            {
+                PhaseMark mk(ctx, s, PH_CLEAR);
+                k_clear_packed_batch<<<dim3(gx, m), 256, 0, s>>>(ctx->batch, 0u);
                 ctx->launches++;
             }
-            if (work) {
+            if (plan.max_tiles[0] + plan.max_tiles[1] + plan.max_tiles[2]) {
+                {
+                    PhaseMark mk(ctx, s, PH_WALK);
+                    RET_IF(launch_walk<1>(ctx, plan, exact, 0, m, s));
+                }
                 PhaseMark mk(ctx, s, PH_FINISH);
                 if (vertices_mode) RET_IF(launch_repair<true>(ctx, static_cast<uint32_t*>(ctx->counts.p), s));
                 else               RET_IF(launch_repair<false>(ctx, static_cast<uint32_t*>(ctx->counts.p), s));
@@ -479,11 +477,6 @@ int vkhr_b200_create(int device, vkhr_b200_ctx** out) {
     vkhr_b200_ctx* ctx = new vkhr_b200_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    if (const char* e = std::getenv("VKHR_B200_DEBUG_SINK")) ctx->debug_sink = std::string(e) == "null" ? 2 : std::string(e) == "compact" ? 3 : std::string(e) == "quarter" ? 4 : 0;
-    if (const char* e = std::getenv("VKHR_B200_GROUP_MIB")) {      // tuning knob for experiments
-        const long v = std::atol(e);
-        if (v > 0) ctx->group_bytes = (size_t)v << 20;
-    }
     if (cudaSetDevice(device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx;
@@ -503,7 +496,7 @@ void vkhr_b200_destroy(vkhr_b200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->counts, &ctx->headers, &ctx->small, &ctx->st_vertices,
+    DevBuf* bufs[] = {&ctx->counts, &ctx->bitmap, &ctx->small, &ctx->st_vertices,
                       &ctx->st_indices, &ctx->st_tangents, &ctx->st_dens, &ctx->st_tang_out};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }

@@ -270,14 +270,22 @@ __device__ __forceinline__ void walk_voxel_space_warp(const GridParams& g, bool 
             dx = div_fast(dx, steps, y);
             dy = div_fast(dy, steps, y);
             dz = div_fast(dz, steps, y);
-            do {                                                              // while (steps-- > 0.0f)
+            // while (steps-- > 0.0f); unrolled by four so that a sink may keep one pending result per position
+            auto sample = [&](auto slot) {
                 uint32_t idx;
-                if (sample_index<EXACT>(g, rx, ry, rz, idx)) sink.template put<0>(idx);
+                if (sample_index<EXACT>(g, rx, ry, rz, idx)) sink.template put<decltype(slot)::value>(idx);
                 rx = __fadd_rn(rx, dx);
                 ry = __fadd_rn(ry, dy);
                 rz = __fadd_rn(rz, dz);
                 steps = __fsub_rn(steps, 1.0f);
-            } while (steps > 0.0f);
+                return steps > 0.0f;
+            };
+            for (;;) {
+                if (!sample(std::integral_constant<int, 0>{})) break;
+                if (!sample(std::integral_constant<int, 1>{})) break;
+                if (!sample(std::integral_constant<int, 2>{})) break;
+                if (!sample(std::integral_constant<int, 3>{})) break;
+            }
         }
     } else if (go) {
         walk_voxel_space<EXACT>(g, rx, ry, rz, tx, ty, tz, sink);             // the literal code, any input
