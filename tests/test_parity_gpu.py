@@ -321,3 +321,100 @@ def test_full_size_properties(vox, port):
             assert np.array_equal(mx.cpu().numpy(), port.downsample(dh, W, H, D, 0))
             assert np.array_equal(nrm.cpu().numpy(), port.normalize(dh))
         torch.cuda.synchronize()
+
+
+def _assert_tangents_close(got, want, dens, what):
+    """Volume::tangents: the reference sums fp32 tangents in strand order, the GPU sums integers (order-free):
+    within 1 LSB wherever the reference is defined and order-independent (0 < density < 255), w == 0 everywhere,
+    and exactly 0 in empty voxels (0/0 -> NaN -> 0 on x86-64 in the reference)."""
+    got, want = got.reshape(-1, 4).astype(np.int32), want.reshape(-1, 4).astype(np.int32)
+    assert np.all(got[:, 3] == 0), what
+    assert np.all(got[dens == 0] == 0), what
+    m = (dens > 0) & (dens < 255)
+    diff = np.abs(got[m, :3] - want[m, :3])
+    assert diff.max(initial=0) <= 1, f"{what}: tangent off by {diff.max()} LSB"
+    assert (diff == 0).mean() > 0.9, f"{what}: only {(diff == 0).mean():.3f} of the components identical"
+
+
+@pytest.mark.parametrize("res", [(64, 64, 64), (64, 32, 16), (16, 16, 16), (30, 20, 10)])
+def test_tangent_volume_golden(vox, port, small_sets, res):
+    """Tangent volumes against the ones the unmodified reference produced (tests/golden/small_sets.npz)."""
+    W, H, D = res
+    tag = f"{W}x{H}x{D}"
+    v = small_sets["in_vertices"]
+    n, s = [int(x) for x in small_sets["in_meta"]]
+    bb = small_sets["aabb_generated"]
+    hs = HairStyle(voxelizer=vox)
+    hs.vertices = v
+    hs.set_strand_count(n)
+    hs.set_default_segment_count(s)
+    hs.generate_indices()
+    hs.generate_tangents()
+    hs.generate_bounding_box()
+    want_d, want_t = small_sets[f"seg_{tag}"], small_sets[f"segtan_{tag}"]
+    # explicit indices + explicit tangents (what HairStyle::voxelize_segments reads)
+    d, t = vox.voxelize_segments(v, hs.indices, bb[:3], bb[4:7], W, H, D, tangents=hs.tangents)
+    assert np.array_equal(d, want_d)
+    _assert_tangents_close(t, want_t, want_d, f"indexed {tag}")
+    # uniform strands, tangents derived on the fly from the segment direction
+    d2, t2 = vox.voxelize_segments(v, None, bb[:3], bb[4:7], W, H, D, segs_per_strand=s, want_tangents=True)
+    assert np.array_equal(d2, want_d)
+    _assert_tangents_close(t2, want_t, want_d, f"uniform {tag}")
+    # order independence: reversing the strand order must not change a single byte
+    order = np.arange(n)[::-1]
+    vr = v.reshape(n, s + 1, 3)[order].reshape(-1, 3)
+    d3, t3 = vox.voxelize_segments(vr, None, bb[:3], bb[4:7], W, H, D, segs_per_strand=s, want_tangents=True)
+    assert np.array_equal(d3, d2) and np.array_equal(t3, t2)
+    # vertices, against the CPU oracle
+    wd, wt = port.voxelize_vertices(v, bb[:3], bb[4:7], W, H, D, tangents=hs.tangents)
+    gd, gt = vox.voxelize_vertices(v, bb[:3], bb[4:7], W, H, D, tangents=hs.tangents)
+    assert np.array_equal(gd, wd)
+    _assert_tangents_close(gt, wt, wd, f"vertices {tag}")
+    # through the HairStyle mirror, normalised densities as the caller uploads them
+    vol = hs.voxelize_segments(W, H, D, flags=capi.NORMALIZE)
+    assert np.array_equal(vol.densities, small_sets[f"segnorm_{tag}"])
+    _assert_tangents_close(vol.tangents, want_t, want_d, f"mirror {tag}")
+
+
+def test_kat4_tangents(vox, golden):
+    k = golden["kat4"]
+    hs = HairStyle(voxelizer=vox)
+    hs.vertices = np.array(k["vertices"], dtype=np.float32)
+    hs.set_strand_count(k["strands"])
+    hs.set_default_segment_count(k["segments_per_strand"])
+    hs.generate_tangents()
+    hs.generate_indices()
+    hs.generate_bounding_box()
+    vol = hs.voxelize_segments(4, 4, 4)
+    for idx, want in k["voxelize_segments_tangents"].items():
+        got = vol.tangents[int(idx)].astype(int)
+        assert np.abs(got - np.array(want)).max() <= 1, (idx, got, want)
+    assert np.all(vol.tangents[vol.densities == 0] == 0)
+
+
+def test_tangent_volume_full_size(vox, port):
+    """Ponytail-shaped set at 256^3: densities bit-exact with the density-only path, tangents within 1 LSB of the oracle."""
+    v, n, s = synth.shape("ponytail", seed=0x5EED, seg_len=0.5)
+    lo, hi = port.generate_bounding_box(v)
+    size = (hi - lo).astype(np.float32)
+    tin = port.generate_tangents(v, n, s)
+    idx = port.generate_indices(n, s)
+    wd, wt = port.voxelize_segments(v, idx, lo, size, 256, 256, 256, tangents=tin)
+    d, t = vox.voxelize_segments(v, None, lo, size, 256, 256, 256, segs_per_strand=s, tangents=tin)
+    assert np.array_equal(d, wd)
+    assert np.array_equal(d, vox.voxelize_segments(v, None, lo, size, 256, 256, 256, segs_per_strand=s))
+    _assert_tangents_close(t, wt, wd, "ponytail 256^3")
+
+
+def test_cpp_dropin_against_linked_reference():
+    """adapter/_build/dropin_test links the UNMODIFIED reference hair_style.cc and libvkhr_b200.so and runs the
+    caller's sequence (voxelize_segments(256^3) + normalize) through both; built by __graft_entry__.build()."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "adapter", "_build", "dropin_test")
+    if not os.path.exists(exe):
+        pytest.skip("adapter/_build/dropin_test not built (needs the reference tree at build time)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "drop-in test ok" in r.stdout
+    assert r.stdout.count("bit-exact") == 5 and "MISMATCH" not in r.stdout

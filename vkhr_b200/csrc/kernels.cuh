@@ -311,6 +311,106 @@ k_splat_batch(const __grid_constant__ Batch B, uint32_t first) {
     sink.finish();
 }
 
+// ---------------------------------------------------------------------------
+// Tangent volume (Volume::tangents, hair_style.cc:309,:323,:331-339): per voxel the
+// mean of the tangents of the samples that hit it, times 127, truncated to int8.
+//
+// The reference adds fp32 tangents in strand order (and shuffles the strands with a
+// random seed first, scene_graph.cc:233), so its result is order-dependent; here
+// the sum is an INTEGER sum of tangents quantised to 1/8192, which is the same for
+// any order and any sharding.  Accumulator: 16 bytes per voxel, two u64 words
+//   w0 = count | (sum_x << 32)            w1 = (sum_y + 8192*count) | (sum_z << 32)
+// so a sample is two 64-bit reds (the high fields wrap modulo 2^32, which is exact
+// for signed sums; the low field of w1 is biased to stay non-negative so that it
+// never borrows from sum_z).  Exact up to 262,143 hits per voxel.
+// ---------------------------------------------------------------------------
+constexpr int kTangentScale = 8192;
+
+struct SinkTangent {
+    unsigned long long* acc;
+    unsigned long long w0 = 0, w1 = 0;
+    __device__ __forceinline__ void set(float tx, float ty, float tz) {
+        auto q = [](float t) { return max(-kTangentScale, min(kTangentScale, __float2int_rn(t * (float)kTangentScale))); };   // NaN -> 0
+        const int qx = q(tx), qy = q(ty), qz = q(tz);
+        w0 = 1ull | ((unsigned long long)(uint32_t)qx << 32);
+        w1 = (unsigned long long)(uint32_t)(qy + kTangentScale) | ((unsigned long long)(uint32_t)qz << 32);
+    }
+    template <int SLOT = 0>
+    __device__ __forceinline__ void put(uint32_t idx) {
+        atomicAdd(acc + 2ull * idx, w0);
+        atomicAdd(acc + 2ull * idx + 1ull, w1);
+    }
+    __device__ __forceinline__ void finish() {}
+};
+
+// glm::normalize(v) = v * inversesqrt(dot(v, v)), what HairStyle::generate_tangents stores (hair_style.cc:171-194).
+__device__ __forceinline__ void glm_normalize(float& x, float& y, float& z) {
+    const float d = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+    const float r = __fdiv_rn(1.0f, __fsqrt_rn(d));
+    x = __fmul_rn(x, r); y = __fmul_rn(y, r); z = __fmul_rn(z, r);
+}
+
+// One thread per segment (KIND uniform / indexed) or per vertex (splat); counts and tangent sums into `acc`.
+// tangents == nullptr (segments only): the tangent of a segment's root vertex is normalize(tip - root), which is
+// what generate_tangents produces for every vertex that starts a segment.
+template <int KIND, int EXACT>
+__global__ void __launch_bounds__(kWalkThreads)
+k_walk_tangent(const float* __restrict__ vertices, const uint32_t* __restrict__ indices, const float* __restrict__ tangents,
+               uint64_t n_items, uint32_t segs, const __grid_constant__ GridParams g, unsigned long long* __restrict__ acc) {
+    const uint64_t s = (uint64_t)blockIdx.x * kWalkThreads + threadIdx.x;
+    const bool active = s < n_items;
+    uint32_t i0 = 0, i1 = 0;
+    if (active) {
+        if (KIND == WK_SPLAT) i0 = i1 = (uint32_t)s;
+        else segment_vertices(KIND == WK_INDEXED ? indices : nullptr, segs, s, i0, i1);
+    }
+    float ax = 0.f, ay = 0.f, az = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
+    SinkTangent sink{acc};
+    if (active) {
+        const float* a = vertices + 3ull * i0;
+        ax = __ldg(a); ay = __ldg(a + 1); az = __ldg(a + 2);
+        if (KIND != WK_SPLAT) { const float* b = vertices + 3ull * i1; bx = __ldg(b); by = __ldg(b + 1); bz = __ldg(b + 2); }
+        float tx, ty, tz;
+        if (tangents) { const float* t = tangents + 3ull * i0; tx = __ldg(t); ty = __ldg(t + 1); tz = __ldg(t + 2); }
+        else { tx = __fsub_rn(bx, ax); ty = __fsub_rn(by, ay); tz = __fsub_rn(bz, az); glm_normalize(tx, ty, tz); }
+        sink.set(tx, ty, tz);
+    }
+    float px, py, pz;
+    to_voxel_space_warp(g, ax, ay, az, px, py, pz);
+    if (KIND == WK_SPLAT) {
+        uint32_t idx;
+        if (active && voxel_index<EXACT>(g, px, py, pz, idx)) sink.put(idx);
+    } else {
+        float qx, qy, qz;
+        to_voxel_space_warp(g, bx, by, bz, qx, qy, qz);
+        walk_voxel_space_warp<EXACT>(g, active, px, py, pz, qx, qy, qz, sink);
+    }
+}
+
+// acc -> densities (min(count, 255)) and tangents (int8 x 4, w = 0); zeroes acc behind itself.
+// tangent component = (int8) trunc( (sum / count) * 127 ), the expression of hair_style.cc:336-338 on the exact mean.
+// Empty voxels: the reference divides 0/0 and converts NaN (0 on x86-64); here 0.
+__global__ void __launch_bounds__(256)
+k_finish_tangent(unsigned long long* __restrict__ acc, uint64_t n_voxels, uint8_t* __restrict__ dens, uint32_t* __restrict__ tang) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_voxels; i += (uint64_t)gridDim.x * blockDim.x) {
+        ulonglong2* a = reinterpret_cast<ulonglong2*>(acc) + i;
+        const ulonglong2 w = *a;
+        const uint32_t count = (uint32_t)w.x;
+        uint32_t t = 0;
+        if (count) {
+            const float fc = (float)count, inv = 1.0f / (float)kTangentScale;
+            const int sx = (int)(uint32_t)(w.x >> 32);
+            const int sy = (int)((uint32_t)w.y - (uint32_t)kTangentScale * count);
+            const int sz = (int)(uint32_t)(w.y >> 32);
+            auto q = [&](int sum) { return (uint32_t)(uint8_t)(int8_t)__float2int_rz(__fmul_rn(__fdiv_rn(__fmul_rn((float)sum, inv), fc), 127.0f)); };
+            t = q(sx) | (q(sy) << 8) | (q(sz) << 16);
+            *a = make_ulonglong2(0ull, 0ull);
+        }
+        dens[i] = (uint8_t)min(count, 255u);
+        if (tang) tang[i] = t;
+    }
+}
+
 // Bitwise comparison of div_exact against the IEEE division on pseudo-random
 // operands (self test of the fast exact division; see walk.cuh).
 __global__ void __launch_bounds__(256)

@@ -115,6 +115,8 @@ struct vkhr_b200_ctx {
     size_t counts_clean_bytes = 0;   // leading bytes of `counts` known to be zero
     DevBuf bitmap;        // PACKED8 overflow bitmaps (+ flags at the front)
     DevBuf small;         // lohi[2] + aabb keys[6] + aabb floats[6]
+    DevBuf tacc;          // tangent mode: 16-byte accumulator per voxel
+    size_t tacc_clean_bytes = 0;     // leading bytes of `tacc` known to be zero
     DevBuf st_vertices, st_indices, st_tangents, st_dens, st_tang_out;   // host-API staging
     int repair_blocks[2] = {0, 0};
     Batch batch;          // host copy of the kernel-parameter batch being launched
@@ -440,6 +442,55 @@ int run_count(vkhr_b200_ctx* ctx, const Job& j, bool vertices_mode, uint32_t fla
     return launch_walk<0>(ctx, plan, (flags & VKHR_B200_INDEX_EXACT) != 0, 0, 1, s);
 }
 
+// Densities AND the tangent volume of one instance (Volume::tangents): counts and integer tangent sums in a
+// 16-byte-per-voxel accumulator, then one pass that writes both outputs and leaves the accumulator zeroed.
+int run_tangent(vkhr_b200_ctx* ctx, const Job& j, const float* d_tangents_in, bool vertices_mode, uint32_t flags,
+                int8_t* d_tangents_out, cudaStream_t s) {
+    if (reinterpret_cast<uintptr_t>(d_tangents_out) & 3u)
+        return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "tangents_out must be 4-byte aligned");
+    if (vertices_mode && !d_tangents_in)
+        return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "voxelize_vertices needs tangents_in to produce tangents_out");
+    const uint64_t nv = j.grid.n_voxels;
+    const size_t need = (size_t)nv * 16;
+    if (need > ctx->tacc.cap) ctx->tacc_clean_bytes = 0;
+    RET_IF(reserve(ctx, ctx->tacc, need));
+    unsigned long long* acc = static_cast<unsigned long long*>(ctx->tacc.p);
+    if (ctx->tacc_clean_bytes < need) {
+        PhaseMark mk(ctx, s, PH_CLEAR);
+        CU_CHECK(ctx, cudaMemsetAsync(acc, 0, need, s));
+    }
+    ctx->tacc_clean_bytes = 0;
+    const bool exact = (flags & VKHR_B200_INDEX_EXACT) != 0;
+    const uint64_t items = vertices_mode ? j.n_vertices : j.n_segments;
+    if (items) {
+        PhaseMark mk(ctx, s, PH_WALK);
+        const unsigned blocks = (unsigned)((items + kWalkThreads - 1) / kWalkThreads);
+#define VKHR_LAUNCH_TANGENT(KIND)                                                                                      \
+        do {                                                                                                           \
+            if (exact) k_walk_tangent<KIND, 1><<<blocks, kWalkThreads, 0, s>>>(j.d_vertices, j.d_indices, d_tangents_in, items, j.segs, j.grid, acc); \
+            else       k_walk_tangent<KIND, 0><<<blocks, kWalkThreads, 0, s>>>(j.d_vertices, j.d_indices, d_tangents_in, items, j.segs, j.grid, acc); \
+        } while (0)
+        if (vertices_mode) VKHR_LAUNCH_TANGENT(WK_SPLAT);
+        else if (j.d_indices) VKHR_LAUNCH_TANGENT(WK_INDEXED);
+        else VKHR_LAUNCH_TANGENT(WK_UNIFORM);
+#undef VKHR_LAUNCH_TANGENT
+        ctx->launches++;
+        CU_CHECK(ctx, cudaGetLastError());
+    }
+    {
+        PhaseMark mk(ctx, s, PH_FINISH);
+        k_finish_tangent<<<stride_blocks(ctx, nv, 256, 16), 256, 0, s>>>(acc, nv, j.d_dens, reinterpret_cast<uint32_t*>(d_tangents_out));
+        ctx->launches++;
+        CU_CHECK(ctx, cudaGetLastError());
+    }
+    ctx->tacc_clean_bytes = need;                       // the finish pass zeroed every entry it found non-empty
+    if (flags & VKHR_B200_NORMALIZE) {
+        PhaseMark mk(ctx, s, PH_NORMALIZE);
+        RET_IF(vkhr_b200_normalize_dev(ctx, j.d_dens, nv, s));
+    }
+    return VKHR_B200_OK;
+}
+
 int stage_in(vkhr_b200_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
     RET_IF(reserve(ctx, b, bytes ? bytes : 16));
     if (bytes) CU_CHECK(ctx, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -496,7 +547,7 @@ void vkhr_b200_destroy(vkhr_b200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->counts, &ctx->bitmap, &ctx->small, &ctx->st_vertices,
+    DevBuf* bufs[] = {&ctx->counts, &ctx->bitmap, &ctx->small, &ctx->tacc, &ctx->st_vertices,
                       &ctx->st_indices, &ctx->st_tangents, &ctx->st_dens, &ctx->st_tang_out};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -568,13 +619,12 @@ int vkhr_b200_voxelize_segments_dev(vkhr_b200_ctx* ctx, const float* d_vertices,
                                     uint8_t* d_densities_out, int8_t* d_tangents_out, void* stream) {
     RET_IF(bind(ctx));
     if (!d_vertices || !d_densities_out) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null vertices or densities");
-    if (d_tangents_out || d_tangents_in)
-        return fail(ctx, VKHR_B200_ERR_UNSUPPORTED, "tangent volume not built yet (density only)");
     Job j{};
     RET_IF(make_grid(ctx, aabb_origin, aabb_size, W, H, D, flags, j.grid));
     RET_IF(segment_count(ctx, d_indices, n_indices, n_vertices, segs_per_strand, j.n_segments));
     j.d_vertices = d_vertices; j.d_indices = d_indices; j.n_vertices = n_vertices;
     j.segs = segs_per_strand; j.d_dens = d_densities_out;
+    if (d_tangents_out) return run_tangent(ctx, j, d_tangents_in, false, flags, d_tangents_out, pick(ctx, stream));
     return run_voxelize(ctx, &j, 1, false, flags, pick(ctx, stream));
 }
 
@@ -584,11 +634,10 @@ int vkhr_b200_voxelize_vertices_dev(vkhr_b200_ctx* ctx, const float* d_vertices,
                                     uint8_t* d_densities_out, int8_t* d_tangents_out, void* stream) {
     RET_IF(bind(ctx));
     if (!d_vertices || !d_densities_out) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null vertices or densities");
-    if (d_tangents_out || d_tangents_in)
-        return fail(ctx, VKHR_B200_ERR_UNSUPPORTED, "tangent volume not built yet (density only)");
     Job j{};
     RET_IF(make_grid(ctx, aabb_origin, aabb_size, W, H, D, flags, j.grid));
     j.d_vertices = d_vertices; j.n_vertices = n_vertices; j.d_dens = d_densities_out;
+    if (d_tangents_out) return run_tangent(ctx, j, d_tangents_in, true, flags, d_tangents_out, pick(ctx, stream));
     return run_voxelize(ctx, &j, 1, true, flags, pick(ctx, stream));
 }
 
@@ -716,25 +765,29 @@ int vkhr_b200_voxelize_segments(vkhr_b200_ctx* ctx, const float* vertices, uint3
                                 uint8_t* densities_out, int8_t* tangents_out) {
     RET_IF(bind(ctx));
     if (!densities_out || (n_vertices && !vertices)) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null vertices or densities");
-    if (tangents_out || tangents_in)
-        return fail(ctx, VKHR_B200_ERR_UNSUPPORTED, "tangent volume not built yet (density only)");
     GridParams g;
     RET_IF(make_grid(ctx, aabb_origin, aabb_size, W, H, D, flags, g));
     const size_t nv = g.n_voxels;
     RET_IF(reserve(ctx, ctx->st_dens, nv));
+    if (tangents_out) RET_IF(reserve(ctx, ctx->st_tang_out, nv * 4));
     // fewer than two indices: the reference underflows size()-1; defined here as an empty volume
     const bool empty = n_vertices == 0 || (indices && n_indices < 2);
     if (empty) {
         CU_CHECK(ctx, cudaMemsetAsync(ctx->st_dens.p, 0, nv, ctx->stream));
+        if (tangents_out) CU_CHECK(ctx, cudaMemsetAsync(ctx->st_tang_out.p, 0, nv * 4, ctx->stream));
     } else {
         RET_IF(stage_in(ctx, ctx->st_vertices, vertices, (size_t)n_vertices * 12));
         if (indices) RET_IF(stage_in(ctx, ctx->st_indices, indices, (size_t)(n_indices / 2) * 8));
+        if (tangents_out && tangents_in) RET_IF(stage_in(ctx, ctx->st_tangents, tangents_in, (size_t)n_vertices * 12));
         RET_IF(vkhr_b200_voxelize_segments_dev(ctx, static_cast<const float*>(ctx->st_vertices.p), n_vertices,
                                                indices ? static_cast<const uint32_t*>(ctx->st_indices.p) : nullptr,
-                                               n_indices, segs_per_strand, nullptr, aabb_origin, aabb_size,
-                                               W, H, D, flags, static_cast<uint8_t*>(ctx->st_dens.p), nullptr, ctx->stream));
+                                               n_indices, segs_per_strand,
+                                               (tangents_out && tangents_in) ? static_cast<const float*>(ctx->st_tangents.p) : nullptr,
+                                               aabb_origin, aabb_size, W, H, D, flags, static_cast<uint8_t*>(ctx->st_dens.p),
+                                               tangents_out ? static_cast<int8_t*>(ctx->st_tang_out.p) : nullptr, ctx->stream));
     }
     CU_CHECK(ctx, cudaMemcpyAsync(densities_out, ctx->st_dens.p, nv, cudaMemcpyDeviceToHost, ctx->stream));
+    if (tangents_out) CU_CHECK(ctx, cudaMemcpyAsync(tangents_out, ctx->st_tang_out.p, nv * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     return VKHR_B200_OK;
 }
@@ -745,21 +798,27 @@ int vkhr_b200_voxelize_vertices(vkhr_b200_ctx* ctx, const float* vertices, uint3
                                 uint8_t* densities_out, int8_t* tangents_out) {
     RET_IF(bind(ctx));
     if (!densities_out || (n_vertices && !vertices)) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null vertices or densities");
-    if (tangents_out || tangents_in)
-        return fail(ctx, VKHR_B200_ERR_UNSUPPORTED, "tangent volume not built yet (density only)");
+    if (tangents_out && !tangents_in)
+        return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "voxelize_vertices needs tangents_in to produce tangents_out");
     GridParams g;
     RET_IF(make_grid(ctx, aabb_origin, aabb_size, W, H, D, flags, g));
     const size_t nv = g.n_voxels;
     RET_IF(reserve(ctx, ctx->st_dens, nv));
+    if (tangents_out) RET_IF(reserve(ctx, ctx->st_tang_out, nv * 4));
     if (n_vertices == 0) {
         CU_CHECK(ctx, cudaMemsetAsync(ctx->st_dens.p, 0, nv, ctx->stream));
+        if (tangents_out) CU_CHECK(ctx, cudaMemsetAsync(ctx->st_tang_out.p, 0, nv * 4, ctx->stream));
     } else {
         RET_IF(stage_in(ctx, ctx->st_vertices, vertices, (size_t)n_vertices * 12));
-        RET_IF(vkhr_b200_voxelize_vertices_dev(ctx, static_cast<const float*>(ctx->st_vertices.p), n_vertices, nullptr,
+        if (tangents_out) RET_IF(stage_in(ctx, ctx->st_tangents, tangents_in, (size_t)n_vertices * 12));
+        RET_IF(vkhr_b200_voxelize_vertices_dev(ctx, static_cast<const float*>(ctx->st_vertices.p), n_vertices,
+                                               tangents_out ? static_cast<const float*>(ctx->st_tangents.p) : nullptr,
                                                aabb_origin, aabb_size, W, H, D, flags,
-                                               static_cast<uint8_t*>(ctx->st_dens.p), nullptr, ctx->stream));
+                                               static_cast<uint8_t*>(ctx->st_dens.p),
+                                               tangents_out ? static_cast<int8_t*>(ctx->st_tang_out.p) : nullptr, ctx->stream));
     }
     CU_CHECK(ctx, cudaMemcpyAsync(densities_out, ctx->st_dens.p, nv, cudaMemcpyDeviceToHost, ctx->stream));
+    if (tangents_out) CU_CHECK(ctx, cudaMemcpyAsync(tangents_out, ctx->st_tang_out.p, nv * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     return VKHR_B200_OK;
 }

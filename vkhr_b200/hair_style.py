@@ -254,12 +254,21 @@ class HairStyle:
         """``HairStyle::voxelize_segments`` (hair_style.cc:296-342) on the GPU."""
         vox = self._vox or default_voxelizer()
         b = self.get_bounding_box()
-        d = vox.voxelize_segments(self.vertices, self.indices, b.origin, b.size, width, height, depth, flags=flags)
-        return Volume(np.array([width, height, depth], dtype=np.float32), b, d, None, vox)
+        # the reference always fills Volume::tangents from this->tangents (hair_style.cc:309,:323)
+        tin = self.tangents if self.has_tangents() and self.tangents.shape == self.vertices.shape else None
+        if tin is not None:
+            d, t = vox.voxelize_segments(self.vertices, self.indices, b.origin, b.size, width, height, depth, flags=flags, tangents=tin)
+        else:
+            d, t = vox.voxelize_segments(self.vertices, self.indices, b.origin, b.size, width, height, depth, flags=flags), None
+        return Volume(np.array([width, height, depth], dtype=np.float32), b, d, t, vox)
 
     def voxelize_vertices(self, width: int, height: int, depth: int, flags: int = 0) -> Volume:
         """``HairStyle::voxelize_vertices`` (hair_style.cc:257-294) on the GPU."""
         vox = self._vox or default_voxelizer()
         b = self.get_bounding_box()
-        d = vox.voxelize_vertices(self.vertices, b.origin, b.size, width, height, depth, flags=flags)
-        return Volume(np.array([width, height, depth], dtype=np.float32), b, d, None, vox)
+        tin = self.tangents if self.has_tangents() and self.tangents.shape == self.vertices.shape else None
+        if tin is not None:
+            d, t = vox.voxelize_vertices(self.vertices, b.origin, b.size, width, height, depth, flags=flags, tangents=tin)
+        else:
+            d, t = vox.voxelize_vertices(self.vertices, b.origin, b.size, width, height, depth, flags=flags), None
+        return Volume(np.array([width, height, depth], dtype=np.float32), b, d, t, vox)

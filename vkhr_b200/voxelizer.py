@@ -88,27 +88,40 @@ class Voxelizer:
 
     # ---- host-pointer API (numpy) ------------------------------------------
     def voxelize_segments(self, vertices, indices, aabb_origin, aabb_size, W, H, D,
-                          segs_per_strand: int = 0, flags: int = 0) -> np.ndarray:
-        """Replaces ``HairStyle::voxelize_segments`` (reference hair_style.cc:296-342); returns W*H*D uint8."""
+                          segs_per_strand: int = 0, flags: int = 0, tangents=None, want_tangents: bool = False):
+        """Replaces ``HairStyle::voxelize_segments`` (reference hair_style.cc:296-342); returns W*H*D uint8.
+
+        ``want_tangents`` (or ``tangents`` given): also returns the int8 (W*H*D, 4) tangent volume
+        (``Volume::tangents``); without ``tangents`` the tangent of a segment is normalize(tip - root).
+        """
         v = _np(vertices, np.float32).reshape(-1, 3)
         idx = None if indices is None else _np(indices, np.uint32).reshape(-1)
+        tin = None if tangents is None else _np(tangents, np.float32).reshape(-1, 3)
+        if tin is not None and tin.shape != v.shape:
+            raise ValueError("tangents must have one row per vertex")
+        want = want_tangents or tin is not None
         out = np.empty(int(W) * int(H) * int(D), dtype=np.uint8)
+        tout = np.empty((out.size, 4), dtype=np.int8) if want else None
         rc = lib.vkhr_b200_voxelize_segments(self._h, _p(v), v.shape[0], _p(idx),
-                                             0 if idx is None else idx.size, int(segs_per_strand), None,
+                                             0 if idx is None else idx.size, int(segs_per_strand), _p(tin),
                                              capi.vec3(aabb_origin), capi.vec3(aabb_size),
-                                             int(W), int(H), int(D), int(flags), _p(out), None)
+                                             int(W), int(H), int(D), int(flags), _p(out), _p(tout))
         capi.check(self._h, rc)
-        return out
+        return (out, tout) if want else out
 
-    def voxelize_vertices(self, vertices, aabb_origin, aabb_size, W, H, D, flags: int = 0) -> np.ndarray:
-        """Replaces ``HairStyle::voxelize_vertices`` (reference hair_style.cc:257-294)."""
+    def voxelize_vertices(self, vertices, aabb_origin, aabb_size, W, H, D, flags: int = 0, tangents=None):
+        """Replaces ``HairStyle::voxelize_vertices`` (reference hair_style.cc:257-294); with ``tangents`` also the tangent volume."""
         v = _np(vertices, np.float32).reshape(-1, 3)
+        tin = None if tangents is None else _np(tangents, np.float32).reshape(-1, 3)
+        if tin is not None and tin.shape != v.shape:
+            raise ValueError("tangents must have one row per vertex")
         out = np.empty(int(W) * int(H) * int(D), dtype=np.uint8)
-        rc = lib.vkhr_b200_voxelize_vertices(self._h, _p(v), v.shape[0], None,
+        tout = np.empty((out.size, 4), dtype=np.int8) if tin is not None else None
+        rc = lib.vkhr_b200_voxelize_vertices(self._h, _p(v), v.shape[0], _p(tin),
                                              capi.vec3(aabb_origin), capi.vec3(aabb_size),
-                                             int(W), int(H), int(D), int(flags), _p(out), None)
+                                             int(W), int(H), int(D), int(flags), _p(out), _p(tout))
         capi.check(self._h, rc)
-        return out
+        return (out, tout) if tin is not None else out
 
     def normalize(self, densities) -> np.ndarray:
         """``Volume::normalize`` (reference hair_style.cc:344-357) on a host grid; returns a new array."""
