@@ -52,6 +52,7 @@ def parse_args():
     p.add_argument("--strategy", default="auto", choices=["auto", "packed8", "count32"])
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--no-others", action="store_true", help="skip the short device-resident timings of the other BASELINE configs")
     p.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
     return p.parse_args()
@@ -135,6 +136,44 @@ def make_instance(seed: int, seg_len: float):
     v, n, s = synth.shape("ponytail", seed=seed, seg_len=seg_len)
     lo, hi = synth.host_bounding_box(v)
     return v, n, s, lo, (hi - lo).astype(np.float32)
+
+
+def other_configs(vox, dev, args):
+    """Short device-resident timings (CUDA events, 20 reps after 3 warm-ups) of the other BASELINE.json configs that
+    fit one GPU; inputs are rotated over 8 copies (> L2) for the small sets.  Parity for these lives in tests/."""
+    import torch
+    from vkhr_b200 import synth
+    out = {}
+    cases = [("configs[0] ponytail 256^3, one instance", "ponytail", 0.5, 256, 8),
+             ("configs[1] Yuksel-straight-shaped 50,000 x 65 at 512^3", "straight", 0.5, 512, 2),
+             ("configs[2] 1M strands x 32 segments at 512^3 (one GPU)", "big", 0.5, 512, 1),
+             ("configs[4] animated ponytail frame at 1024^3 (voxelise only)", "ponytail", 0.5, 1024, 1)]
+    for name, shape, seg_len, W, copies in cases:
+        try:
+            v, n, s = synth.shape(shape, seed=0x5EED, seg_len=seg_len)
+            lo, hi = synth.host_bounding_box(v)
+            size = (hi - lo).astype(np.float32)
+            vt = [torch.from_numpy(v).to(dev).reshape(-1).clone() for _ in range(copies)]
+            o = [torch.empty(W ** 3, dtype=torch.uint8, device=dev) for _ in range(copies)]
+            reps = 20
+            for r in range(3):
+                vox.voxelize_segments_dev(vt[r % copies], None, lo, size, W, W, W, segs_per_strand=s, out=o[r % copies])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for r in range(reps):
+                vox.voxelize_segments_dev(vt[r % copies], None, lo, size, W, W, W, segs_per_strand=s, out=o[r % copies])
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            alg = 12 * v.shape[0] + W ** 3
+            out[name] = {"segments": n * s, "ms": ms, "value": n * s / ms / 1e3, "unit": UNIT,
+                         "hbm_frac_whole_path": alg / (ms * 1e-3) / 1e9 / hbm_peak()[0]}
+            del vt, o
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            out[name] = {"error": str(e)[:200]}
+    return out
 
 
 # --------------------------------------------------------------------------------------
@@ -271,8 +310,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     step_ms = ms / args.steps
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": ncu_traffic("k_walk_batch<1>" if args.strategy != "count32" else "k_walk_batch<0>"),
-        "kernel": "k_walk_batch (strand walk + packed u8 atomics)", "kernel_ms_per_launch": walk_ms,
+        "traffic": ncu_traffic(f"k_walk_uniform<{0 if args.strategy == 'count32' else 1}>@{I}x{W}^3"),
+        "kernel": "k_walk_uniform (strand walk + packed u8 atomics)", "kernel_ms_per_launch": walk_ms,
         "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
         "phase_ms_per_step": phases_ms, "kernel_share_of_step": (phases_ms["walk"] / (ms_instr / args.steps)) if ms_instr else None,
         "whole_path_frac": (alg_bytes / (step_ms * 1e-3) / 1e9) / peak,
@@ -344,6 +383,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             cpu = {"value": n_seg * reps / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
                    "sample": f"instance 0 of the crowd ({n_seg} segments, {W}^3), C port density-only walk, {reps} runs"}
 
+    others = None
+    if rank == 0 and world == 1 and not args.no_others:
+        others = other_configs(vox, dev, args)
     if rank == 0:
         sigma = None
         try:
@@ -352,6 +394,12 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             sigma = oracle.port().count_samples(v0, idx0, aabbs[0][0], aabbs[0][1], W, W, W) / n_seg
         except Exception:  # noqa: BLE001
             pass
+        if sigma:
+            # secondary bound: one 32-byte atomic request packet per sample; the measured ceiling of
+            # packed atomics with one lane per sector on this part is 220 G/s (profiles/r01_microbench.json)
+            roofline["atomic"] = {"samples_per_launch": sigma * n_seg * I, "achieved_Gsamples_s": sigma * n_seg * I / (walk_ms * 1e-3) / 1e9,
+                                  "peak_Gsamples_s": 220.0, "frac": sigma * n_seg * I / (walk_ms * 1e-3) / 1e9 / 220.0,
+                                  "peak_source": "tools/microbench.cu on this pool (profiles/r01_microbench.json)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
@@ -366,6 +414,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                 "cache": f"inputs {I * V * 12 / 1e6:.0f} MB + outputs {I * nvox / 1e6:.0f} MB per rank per step, larger than the 126 MB L2; no flush needed",
             },
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "other_configs": others,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -1,0 +1,144 @@
+"""Strand sharding across the GPUs of one box (BASELINE.json configs[2]): one process per GPU.
+
+Each rank voxelises a contiguous range of whole strands into a partial u32 hit-count grid; the
+partials are summed with ONE integer collective over NVLink and clamped:
+``density = min(sum_r count_r, 255)``.  That equals the single-GPU (and the reference's sequential)
+result for every partition because the reference's counter only saturates
+(``if (d != 255) d += 1``, hair_style.cc:277-280, :322-325).
+
+Two exchange schedules:
+
+* ``"allreduce"``  -- ``all_reduce(u32 grid, SUM)`` then a local clamp: 2(n-1)/n * 4 N^3 bytes per GPU.
+* ``"rs_ag"``      -- ``reduce_scatter(u32)`` -> the owner clamps its slab -> ``all_gather(u8)``:
+  (n-1)/n * (4 + 1) N^3 bytes per GPU, 37.5 % less NVLink traffic, and the clamp touches 1/n of the grid.
+
+torch.distributed is the plumbing (NCCL on the GPUs; gloo in the CPU tests of this module's host
+logic).  Counting and clamping run in libvkhr_b200.so; ``count_fn`` / ``clamp_fn`` exist so that the
+world_size-2 gloo tests can drive the exchange logic with the CPU oracle standing in for the kernels --
+nothing in the package passes them.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+
+
+def strand_range(n_strands: int, world: int, rank: int) -> Tuple[int, int]:
+    """(first strand, strand count) of ``rank``: contiguous, sizes differ by at most one."""
+    if not 0 <= rank < world:
+        raise ValueError("rank out of range")
+    base, extra = divmod(int(n_strands), int(world))
+    first = rank * base + min(rank, extra)
+    return first, base + (1 if rank < extra else 0)
+
+
+def shard_vertices(vertices: np.ndarray, n_strands: int, segs_per_strand: int, world: int, rank: int) -> np.ndarray:
+    """This rank's rows of a strand-major (n_strands * (segs + 1), 3) vertex array (a view, whole strands)."""
+    v = np.asarray(vertices).reshape(-1, 3)
+    vps = segs_per_strand + 1
+    if v.shape[0] != n_strands * vps:
+        raise ValueError("vertices do not match n_strands * (segs_per_strand + 1)")
+    first, count = strand_range(n_strands, world, rank)
+    return v[first * vps:(first + count) * vps]
+
+
+def padded_voxels(n_voxels: int, world: int) -> int:
+    """Grid length rounded up so that every rank owns an equal, 16-byte aligned slab (reduce-scatter layout)."""
+    q = 16 * world
+    return (n_voxels + q - 1) // q * q
+
+
+class ShardedVoxelizer:
+    """voxelize_segments / voxelize_vertices over the ranks of a torch.distributed group."""
+
+    def __init__(self, voxelizer=None, group=None, count_fn: Optional[Callable] = None,
+                 clamp_fn: Optional[Callable] = None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.vox = voxelizer
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self._count = count_fn or self._count_cuda
+        self._clamp = clamp_fn or self._clamp_cuda
+        self._counts = None
+
+    # ---- the CUDA path (the only one the package uses) -------------------------------------------
+    def _count_cuda(self, mode, vertices, indices, segs, origin, size, W, H, D, counts, flags):
+        if self.vox is None:
+            raise RuntimeError("ShardedVoxelizer needs a Voxelizer: there is no CPU fallback")
+        if mode == "segments":
+            self.vox.count_segments_dev(vertices, indices, origin, size, W, H, D, counts[:W * H * D],
+                                        segs_per_strand=segs, flags=flags)
+        else:
+            self.vox.count_vertices_dev(vertices, origin, size, W, H, D, counts[:W * H * D], flags=flags)
+
+    def _clamp_cuda(self, counts, out, flags=0):
+        self.vox.clamp_counts_dev(counts, flags=flags, out=out)
+
+    # ---- AABB: every rank must voxelise into the same box ------------------------------------------
+    def global_bounding_box(self, local_min, local_max):
+        """HairStyle::generate_bounding_box (hair_style.cc:215-234) over all shards: elementwise min / max of the
+        per-rank boxes (each already folded from (0,0,0))."""
+        import torch
+        lo = torch.as_tensor(np.asarray(local_min, dtype=np.float32)).clone()
+        hi = torch.as_tensor(np.asarray(local_max, dtype=np.float32)).clone()
+        dev = self._collective_device()
+        lo, hi = lo.to(dev), hi.to(dev)
+        self.dist.all_reduce(lo, op=self.dist.ReduceOp.MIN, group=self.group)
+        self.dist.all_reduce(hi, op=self.dist.ReduceOp.MAX, group=self.group)
+        return lo.cpu().numpy(), hi.cpu().numpy()
+
+    def _collective_device(self):
+        import torch
+        backend = self.dist.get_backend(self.group)
+        return torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+
+    # ---- the sharded voxelisation --------------------------------------------------------------------
+    def voxelize(self, mode: str, vertices, indices, segs_per_strand: int, aabb_origin, aabb_size,
+                 W: int, H: int, D: int, flags: int = 0, out=None, schedule: str = "rs_ag"):
+        """All ranks call this with THEIR shard (torch tensors on the collective's device); every rank returns the
+        complete W*H*D uint8 volume.  ``mode``: "segments" | "vertices"."""
+        import torch
+        if schedule not in ("allreduce", "rs_ag"):
+            raise ValueError("schedule must be 'allreduce' or 'rs_ag'")
+        nv = W * H * D
+        nvp = padded_voxels(nv, self.world)
+        dev = vertices.device
+        if self._counts is None or self._counts.numel() != nvp or self._counts.device != dev:
+            self._counts = torch.zeros(nvp, dtype=torch.int32, device=dev)
+        else:
+            self._counts.zero_()
+        counts = self._counts
+        if vertices.numel():
+            self._count(mode, vertices, indices, segs_per_strand, aabb_origin, aabb_size, W, H, D, counts, flags & 1)
+        norm = flags & 2                                  # NORMALIZE needs the whole grid: applied after the exchange
+        if out is None:
+            out = torch.empty(nvp, dtype=torch.uint8, device=dev)
+        elif out.numel() < nvp:
+            raise ValueError(f"out must hold the padded grid ({nvp} bytes)")
+        if self.world == 1:
+            self._clamp(counts, out[:nvp], 0)
+        elif schedule == "allreduce":
+            self.dist.all_reduce(counts, op=self.dist.ReduceOp.SUM, group=self.group)
+            self._clamp(counts, out[:nvp], 0)
+        else:
+            slab = nvp // self.world
+            mine = torch.empty(slab, dtype=torch.int32, device=dev)
+            self.dist.reduce_scatter_tensor(mine, counts, op=self.dist.ReduceOp.SUM, group=self.group)
+            mine_u8 = torch.empty(slab, dtype=torch.uint8, device=dev)
+            self._clamp(mine, mine_u8, 0)
+            self.dist.all_gather_into_tensor(out[:nvp], mine_u8, group=self.group)
+        vol = out[:nv]
+        if norm:
+            if self.vox is None:
+                raise RuntimeError("NORMALIZE needs the CUDA library")
+            self.vox.normalize_dev(vol)
+        return vol
+
+    def voxelize_segments(self, vertices, indices, segs_per_strand, aabb_origin, aabb_size, W, H, D, **kw):
+        return self.voxelize("segments", vertices, indices, segs_per_strand, aabb_origin, aabb_size, W, H, D, **kw)
+
+    def voxelize_vertices(self, vertices, aabb_origin, aabb_size, W, H, D, **kw):
+        return self.voxelize("vertices", vertices, None, 0, aabb_origin, aabb_size, W, H, D, **kw)
