@@ -166,6 +166,35 @@ VKHR_B200_API int vkhr_b200_voxelize_segments_batch_dev(
     vkhr_b200_ctx* ctx, const vkhr_b200_instance* instances, uint32_t n,
     uint32_t W, uint32_t H, uint32_t D, uint32_t flags, void* stream);
 
+/* ---- host-pointer crowd API (pipelined) ----------------------------------- *
+ * voxelize_segments for `n` independent instances whose strands and output
+ * volumes live in HOST memory (one vkhr::HairStyle + one Volume each, as the
+ * reference keeps them: rasterizer.cc:148-151).  The upload of instance k+1,
+ * the kernels of instance k and the download of instance k-1 run concurrently
+ * on separate streams / copy engines (PCIe is full duplex), so a crowd costs
+ * about max(H2D, D2H) instead of their sum.  Synchronous: returns when every
+ * volume is in host memory.  Host buffers should be page-locked
+ * (vkhr_b200_host_register) -- pageable memory works but serialises the copies. */
+typedef struct vkhr_b200_host_instance {
+    const float*    vertices;         /* host, V x 3 float32 */
+    const uint32_t* indices;          /* host or NULL (uniform strands) */
+    uint64_t        n_indices;
+    uint32_t        n_vertices;
+    uint32_t        segs_per_strand;
+    float           aabb_origin[3];
+    float           aabb_size[3];
+    uint8_t*        densities_out;    /* host, W*H*D */
+} vkhr_b200_host_instance;
+
+VKHR_B200_API int vkhr_b200_voxelize_segments_batch(
+    vkhr_b200_ctx* ctx, const vkhr_b200_host_instance* instances, uint32_t n,
+    uint32_t W, uint32_t H, uint32_t D, uint32_t flags);
+
+/* Page-lock / unlock a caller-owned host range (e.g. the storage of a std::vector)
+ * so that copies to and from it are asynchronous DMA transfers. */
+VKHR_B200_API int vkhr_b200_host_register(vkhr_b200_ctx* ctx, void* ptr, size_t bytes);
+VKHR_B200_API int vkhr_b200_host_unregister(vkhr_b200_ctx* ctx, void* ptr);
+
 /* ---- multi-GPU building blocks ---------------------------------------- *
  * A rank ADDS the hits of its shard of segments (vertices) into a W*H*D u32
  * grid it owns (not cleared here); the shards' grids are summed (NCCL

@@ -273,6 +273,49 @@ def test_device_api_batch_and_shards(vox, port):
     assert np.array_equal(part.cpu().numpy().astype(np.uint32), port.count_vertices(v, lo, size, W, H, D))
 
 
+def test_host_crowd_pipelined(vox, port):
+    """vkhr_b200_voxelize_segments_batch: more instances than staging slots, mixed uniform / indexed / empty members,
+    pinned and pageable host buffers -- every volume must equal the oracle's."""
+    import torch
+    rng = np.random.default_rng(5)
+    W, H, D = 64, 32, 16
+    inst, want = [], []
+    for k in range(8):
+        v, n, s = synth.shape("ponytail", seed=100 + k, seg_len=0.8 + 0.1 * k, scale=0.01 + 0.002 * k)
+        lo, hi = port.generate_bounding_box(v)
+        size = (hi - lo).astype(np.float32)
+        idx = port.generate_indices(n, s)
+        if k % 2 == 0:                                       # pinned through torch
+            vbuf = torch.from_numpy(v.reshape(-1).copy()).pin_memory().numpy()
+            obuf = torch.empty(W * H * D, dtype=torch.uint8).pin_memory().numpy()
+        else:                                                # pageable
+            vbuf, obuf = v.reshape(-1).copy(), np.empty(W * H * D, dtype=np.uint8)
+        obuf[:] = 0xAB
+        d = {"vertices": vbuf, "out": obuf, "aabb_origin": lo, "aabb_size": size}
+        if k % 3 == 1:
+            perm = rng.permutation(idx.reshape(-1, 2)).reshape(-1).astype(np.uint32)
+            d["indices"] = perm
+            want.append(port.voxelize_segments(v, perm, lo, size, W, H, D))
+        elif k == 5:
+            d["indices"] = np.zeros(1, dtype=np.uint32)      # fewer than two indices: empty volume
+            want.append(np.zeros(W * H * D, dtype=np.uint8))
+        else:
+            d["segs_per_strand"] = s
+            want.append(port.voxelize_segments(v, idx, lo, size, W, H, D))
+        inst.append(d)
+    for rep in range(2):                                     # second call reuses slots and events
+        vox.voxelize_segments_batch(inst, W, H, D)
+        for k in range(8):
+            assert np.array_equal(inst[k]["out"], want[k]), (rep, k)
+    # host_register on a caller-owned numpy buffer
+    reg = np.empty(W * H * D, dtype=np.uint8)
+    vox.host_register(reg)
+    inst[0]["out"] = reg
+    vox.voxelize_segments_batch(inst[:1], W, H, D, flags=capi.NORMALIZE)
+    vox.host_unregister(reg)
+    assert np.array_equal(reg, port.normalize(want[0]))
+
+
 def test_full_size_properties(vox, port):
     """Config-1 size (1.64 M segments, 256^3) and 512^3: properties that need no CPU run of the full job."""
     import torch

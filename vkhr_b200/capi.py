@@ -50,6 +50,20 @@ class Instance(C.Structure):
     ]
 
 
+class HostInstance(C.Structure):
+    """``vkhr_b200_host_instance``."""
+    _fields_ = [
+        ("vertices", C.c_void_p),
+        ("indices", C.c_void_p),
+        ("n_indices", C.c_uint64),
+        ("n_vertices", C.c_uint32),
+        ("segs_per_strand", C.c_uint32),
+        ("aabb_origin", C.c_float * 3),
+        ("aabb_size", C.c_float * 3),
+        ("densities_out", C.c_void_p),
+    ]
+
+
 class VkhrB200Error(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"vkhr_b200 error {code}: {message}")
@@ -89,6 +103,9 @@ _PROTOTYPES = {
     "vkhr_b200_voxelize_segments_dev": (_int, [c_ctx, _P, _u32, _P, _u64, _u32, _P, _vec3, _vec3, _u32, _u32, _u32, _u32, _P, _P, _P]),
     "vkhr_b200_voxelize_vertices_dev": (_int, [c_ctx, _P, _u32, _P, _vec3, _vec3, _u32, _u32, _u32, _u32, _P, _P, _P]),
     "vkhr_b200_voxelize_segments_batch_dev": (_int, [c_ctx, C.POINTER(Instance), _u32, _u32, _u32, _u32, _u32, _P]),
+    "vkhr_b200_voxelize_segments_batch": (_int, [c_ctx, C.POINTER(HostInstance), _u32, _u32, _u32, _u32, _u32]),
+    "vkhr_b200_host_register": (_int, [c_ctx, _P, _sz]),
+    "vkhr_b200_host_unregister": (_int, [c_ctx, _P]),
     "vkhr_b200_count_segments_dev": (_int, [c_ctx, _P, _u32, _P, _u64, _u32, _vec3, _vec3, _u32, _u32, _u32, _u32, _P, _P]),
     "vkhr_b200_count_vertices_dev": (_int, [c_ctx, _P, _u32, _vec3, _vec3, _u32, _u32, _u32, _u32, _P, _P]),
     "vkhr_b200_clamp_counts_dev": (_int, [c_ctx, _P, _u64, _u32, _P, _P]),

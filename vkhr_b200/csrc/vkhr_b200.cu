@@ -118,6 +118,11 @@ struct vkhr_b200_ctx {
     DevBuf tacc;          // tangent mode: 16-byte accumulator per voxel
     size_t tacc_clean_bytes = 0;     // leading bytes of `tacc` known to be zero
     DevBuf st_vertices, st_indices, st_tangents, st_dens, st_tang_out;   // host-API staging
+    // pipelined host crowd API: a ring of staging slots and two copy streams (one per PCIe direction)
+    static constexpr int kSlots = 3;
+    struct Slot { DevBuf vertices, indices, dens; cudaEvent_t uploaded = nullptr, computed = nullptr, downloaded = nullptr; };
+    Slot slots[kSlots];
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     int repair_blocks[2] = {0, 0};
     Batch batch;          // host copy of the kernel-parameter batch being launched
     // optional per-phase device timing (vkhr_b200_profile_*): CUDA events recorded on the
@@ -550,6 +555,14 @@ void vkhr_b200_destroy(vkhr_b200_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->counts, &ctx->bitmap, &ctx->small, &ctx->tacc, &ctx->st_vertices,
                       &ctx->st_indices, &ctx->st_tangents, &ctx->st_dens, &ctx->st_tang_out};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+    for (auto& sl : ctx->slots) {
+        DevBuf* sb[] = {&sl.vertices, &sl.indices, &sl.dens};
+        for (DevBuf* b : sb) if (b->p) cudaFree(b->p);
+        cudaEvent_t ev[] = {sl.uploaded, sl.computed, sl.downloaded};
+        for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e);
+    }
+    if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
@@ -857,6 +870,90 @@ int vkhr_b200_generate_bounding_box(vkhr_b200_ctx* ctx, const float* vertices, u
     RET_IF(vkhr_b200_generate_bounding_box_dev(ctx, static_cast<const float*>(ctx->st_vertices.p), n_vertices, d_out, ctx->stream));
     CU_CHECK(ctx, cudaMemcpyAsync(aabb_out, d_out, 24, cudaMemcpyDeviceToHost, ctx->stream));
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return VKHR_B200_OK;
+}
+
+// ---- host-pointer crowd API: upload / kernels / download of consecutive instances overlap ----------
+int vkhr_b200_voxelize_segments_batch(vkhr_b200_ctx* ctx, const vkhr_b200_host_instance* instances, uint32_t n,
+                                      uint32_t W, uint32_t H, uint32_t D, uint32_t flags) {
+    RET_IF(bind(ctx));
+    if (n == 0) return VKHR_B200_OK;
+    if (!instances) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null instance array");
+    // validate everything and size the slots before anything is enqueued
+    std::vector<Job> jobs(n);
+    size_t max_v = 16, max_i = 16;
+    for (uint32_t k = 0; k < n; ++k) {
+        const vkhr_b200_host_instance& in = instances[k];
+        if (!in.densities_out || (in.n_vertices && !in.vertices))
+            return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "instance " + std::to_string(k) + ": null vertices or densities");
+        Job& j = jobs[k];
+        RET_IF(make_grid(ctx, in.aabb_origin, in.aabb_size, W, H, D, flags, j.grid));
+        j.n_vertices = in.n_vertices; j.segs = in.segs_per_strand; j.n_segments = 0;
+        const bool empty = in.n_vertices == 0 || (in.indices && in.n_indices < 2);
+        if (!empty) {
+            if (in.indices) j.n_segments = in.n_indices / 2;
+            else RET_IF(segment_count(ctx, nullptr, 0, in.n_vertices, in.segs_per_strand, j.n_segments));
+        }
+        max_v = std::max(max_v, (size_t)in.n_vertices * 12);
+        if (in.indices) max_i = std::max(max_i, (size_t)(in.n_indices / 2) * 8);
+    }
+    const size_t nv = jobs[0].grid.n_voxels;
+    if (!ctx->h2d_stream) CU_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+    if (!ctx->d2h_stream) CU_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    const uint32_t n_slots = std::min<uint32_t>(n, vkhr_b200_ctx::kSlots);
+    for (uint32_t s = 0; s < n_slots; ++s) {
+        auto& sl = ctx->slots[s];
+        RET_IF(reserve(ctx, sl.vertices, max_v));
+        RET_IF(reserve(ctx, sl.indices, max_i));
+        RET_IF(reserve(ctx, sl.dens, nv));
+        if (!sl.uploaded) {
+            CU_CHECK(ctx, cudaEventCreateWithFlags(&sl.uploaded, cudaEventDisableTiming));
+            CU_CHECK(ctx, cudaEventCreateWithFlags(&sl.computed, cudaEventDisableTiming));
+            CU_CHECK(ctx, cudaEventCreateWithFlags(&sl.downloaded, cudaEventDisableTiming));
+        }
+    }
+    cudaStream_t up = ctx->h2d_stream, run = ctx->stream, down = ctx->d2h_stream;
+    for (uint32_t k = 0; k < n; ++k) {
+        const vkhr_b200_host_instance& in = instances[k];
+        auto& sl = ctx->slots[k % n_slots];
+        Job& j = jobs[k];
+        const bool reuse = k >= n_slots;
+        // upload: the slot's input buffers are free once the kernels of its previous tenant have run
+        if (reuse) CU_CHECK(ctx, cudaStreamWaitEvent(up, sl.computed, 0));
+        if (j.n_segments) {
+            CU_CHECK(ctx, cudaMemcpyAsync(sl.vertices.p, in.vertices, (size_t)in.n_vertices * 12, cudaMemcpyHostToDevice, up));
+            if (in.indices) CU_CHECK(ctx, cudaMemcpyAsync(sl.indices.p, in.indices, (size_t)j.n_segments * 8, cudaMemcpyHostToDevice, up));
+        }
+        CU_CHECK(ctx, cudaEventRecord(sl.uploaded, up));
+        // kernels: need the upload, and the slot's volume buffer back from the previous download
+        CU_CHECK(ctx, cudaStreamWaitEvent(run, sl.uploaded, 0));
+        if (reuse) CU_CHECK(ctx, cudaStreamWaitEvent(run, sl.downloaded, 0));
+        j.d_vertices = static_cast<const float*>(sl.vertices.p);
+        j.d_indices = in.indices ? static_cast<const uint32_t*>(sl.indices.p) : nullptr;
+        j.d_dens = static_cast<uint8_t*>(sl.dens.p);
+        if (j.n_segments) RET_IF(run_voxelize(ctx, &j, 1, false, flags, run));
+        else CU_CHECK(ctx, cudaMemsetAsync(sl.dens.p, 0, nv, run));
+        CU_CHECK(ctx, cudaEventRecord(sl.computed, run));
+        // download
+        CU_CHECK(ctx, cudaStreamWaitEvent(down, sl.computed, 0));
+        CU_CHECK(ctx, cudaMemcpyAsync(in.densities_out, sl.dens.p, nv, cudaMemcpyDeviceToHost, down));
+        CU_CHECK(ctx, cudaEventRecord(sl.downloaded, down));
+    }
+    CU_CHECK(ctx, cudaStreamSynchronize(down));
+    CU_CHECK(ctx, cudaStreamSynchronize(run));
+    CU_CHECK(ctx, cudaStreamSynchronize(up));
+    return VKHR_B200_OK;
+}
+
+int vkhr_b200_host_register(vkhr_b200_ctx* ctx, void* ptr, size_t bytes) {
+    RET_IF(bind(ctx));
+    if (!ptr || !bytes) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null range");
+    CU_CHECK(ctx, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return VKHR_B200_OK;
+}
+int vkhr_b200_host_unregister(vkhr_b200_ctx* ctx, void* ptr) {
+    RET_IF(bind(ctx));
+    CU_CHECK(ctx, cudaHostUnregister(ptr));
     return VKHR_B200_OK;
 }
 

@@ -123,6 +123,41 @@ class Voxelizer:
         capi.check(self._h, rc)
         return (out, tout) if tin is not None else out
 
+    def make_host_batch(self, instances: Sequence[dict]):
+        """``vkhr_b200_host_instance[]`` from dicts of numpy arrays: vertices (f32), out (u8, W*H*D),
+        aabb_origin, aabb_size and either indices (u32) or segs_per_strand."""
+        arr = (capi.HostInstance * len(instances))()
+        keep = []
+        for k, ins in enumerate(instances):
+            v, o, idx = ins["vertices"], ins["out"], ins.get("indices")
+            if v.dtype != np.float32 or o.dtype != np.uint8 or not v.flags.c_contiguous or not o.flags.c_contiguous:
+                raise ValueError("vertices must be contiguous float32 and out contiguous uint8")
+            if idx is not None and (idx.dtype != np.uint32 or not idx.flags.c_contiguous):
+                raise ValueError("indices must be contiguous uint32")
+            arr[k].vertices = v.ctypes.data
+            arr[k].indices = None if idx is None else idx.ctypes.data
+            arr[k].n_indices = 0 if idx is None else idx.size
+            arr[k].n_vertices = v.size // 3
+            arr[k].segs_per_strand = int(ins.get("segs_per_strand", 0))
+            arr[k].aabb_origin = capi.vec3(ins["aabb_origin"])
+            arr[k].aabb_size = capi.vec3(ins["aabb_size"])
+            arr[k].densities_out = o.ctypes.data
+            keep.append((v, o, idx))
+        return arr, keep
+
+    def voxelize_segments_batch(self, batch, W, H, D, flags: int = 0) -> None:
+        """``voxelize_segments`` of a crowd held in host memory (pipelined upload / kernels / download)."""
+        if isinstance(batch, (list, tuple)) and batch and isinstance(batch[0], dict):
+            batch = self.make_host_batch(batch)
+        arr = batch[0] if isinstance(batch, tuple) else batch
+        capi.check(self._h, lib.vkhr_b200_voxelize_segments_batch(self._h, arr, len(arr), int(W), int(H), int(D), int(flags)))
+
+    def host_register(self, array: np.ndarray) -> None:
+        capi.check(self._h, lib.vkhr_b200_host_register(self._h, C.c_void_p(array.ctypes.data), array.nbytes))
+
+    def host_unregister(self, array: np.ndarray) -> None:
+        capi.check(self._h, lib.vkhr_b200_host_unregister(self._h, C.c_void_p(array.ctypes.data)))
+
     def normalize(self, densities) -> np.ndarray:
         """``Volume::normalize`` (reference hair_style.cc:344-357) on a host grid; returns a new array."""
         d = np.array(densities, dtype=np.uint8, copy=True).reshape(-1)
