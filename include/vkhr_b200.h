@@ -98,9 +98,11 @@ VKHR_B200_API uint64_t vkhr_b200_launch_count(const vkhr_b200_ctx* ctx);
  * events on its launching stream around its phases; profile_read waits for
  * them and returns, since the previous read, the summed milliseconds and the
  * number of spans of: [0] grid clear, [1] strand walk (the dominant kernel),
- * [2] finish (overflow repair or u32->u8 clamp), [3] normalize. */
+ * [2] finish (overflow repair or u32->u8 clamp), [3] normalize.
+ * profile_read_ex also returns [4] prefilter (n_phases = 5). */
 VKHR_B200_API int vkhr_b200_profile_enable(vkhr_b200_ctx* ctx, int enable);
 VKHR_B200_API int vkhr_b200_profile_read(vkhr_b200_ctx* ctx, double ms_out[4], uint32_t spans_out[4]);
+VKHR_B200_API int vkhr_b200_profile_read_ex(vkhr_b200_ctx* ctx, double* ms_out, uint32_t* spans_out, uint32_t n_phases);
 
 /* Self test of the kernels' fast exact division (walk.cuh div_exact): compares it
  * bit for bit with the IEEE division instruction sequence on n_trials
@@ -233,6 +235,43 @@ VKHR_B200_API int vkhr_b200_generate_bounding_box_dev(vkhr_b200_ctx* ctx, const 
     uint32_t n_vertices, float* d_aabb_out, void* stream);
 VKHR_B200_API int vkhr_b200_generate_bounding_box(vkhr_b200_ctx* ctx, const float* vertices,
     uint32_t n_vertices, float aabb_out[6]);
+
+/* ---- density -> AO / opacity / Gaussian prefilter -------------------------- *
+ * What the reference's fragment shaders derive from the density volume at every
+ * shaded point, precomputed once per voxel centre into float32 W*H*D volumes
+ * (x fastest, like the densities):
+ *   ao       local_ambient_occlusion(density, centre, ..., 2, ao_radius, ao_exponent, ao_max)
+ *            (share/shaders/volumes/local_ambient_occlusion.glsl:9-30; call sites
+ *            strands/strand.frag:69-74, volumes/volume.frag:82-87)
+ *   opacity  pow(1 - strand_alpha, density * thickness): one raymarch step of
+ *            volume_approximated_deep_shadows (self-shadowing/approximate_deep_shadows.glsl:24-36,
+ *            thickness 11.0 at volumes/volume.frag:72-78); a ray's visibility is the product
+ *   gauss    filter_volume(density, gauss_width, centre, ...).r (volumes/sample_volume.glsl:12-35)
+ * with the density sampled as the reference samples it: R8_UNORM, LINEAR,
+ * CLAMP_TO_BORDER / opaque black (rasterizer/hair_style.cc:79-85).  Any output
+ * pointer may be NULL.  Results are within 1e-6 relative of the CPU restatement
+ * of the GLSL (oracle/prefilter_oracle.c holds the arithmetic contract).
+ * Defaults = include/vkhr/rasterizer/interface.hh:101-105. */
+typedef struct vkhr_b200_prefilter_params {
+    float ao_radius;       /* occlusion_radius, in voxels      (2.5)  */
+    float ao_exponent;     /* ao_exponent                      (10)   */
+    float ao_max;          /* ao_clamp                         (0.16) */
+    float strand_alpha;    /* hair_alpha = the style's default_transparency (caller supplied; 0.3) */
+    float thickness;       /* volume.frag:78                   (11)   */
+    float gauss_width;     /* kernel_width of filter_volume, odd, 1..9 (3) */
+    uint32_t flags;        /* VKHR_B200_PREFILTER_* */
+} vkhr_b200_prefilter_params;
+enum { VKHR_B200_PREFILTER_GENERIC = 1u << 0 };   /* force the untiled kernel (testing) */
+
+VKHR_B200_API void vkhr_b200_prefilter_defaults(vkhr_b200_prefilter_params* params);
+VKHR_B200_API int vkhr_b200_prefilter_dev(
+    vkhr_b200_ctx* ctx, const uint8_t* d_densities, uint32_t W, uint32_t H, uint32_t D,
+    const vkhr_b200_prefilter_params* params /* NULL = defaults */,
+    float* d_ao_out, float* d_opacity_out, float* d_gauss_out, void* stream);
+VKHR_B200_API int vkhr_b200_prefilter(
+    vkhr_b200_ctx* ctx, const uint8_t* densities, uint32_t W, uint32_t H, uint32_t D,
+    const vkhr_b200_prefilter_params* params,
+    float* ao_out, float* opacity_out, float* gauss_out);
 
 /* ---- device memory helpers (so a C/C++ caller needs no CUDA headers) ----- */
 VKHR_B200_API int vkhr_b200_malloc(vkhr_b200_ctx* ctx, size_t bytes, void** d_ptr);

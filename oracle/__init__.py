@@ -160,6 +160,28 @@ class _Port:
                                    C.c_int(filter), _ptr(out, _u8p))
         return out
 
+    # ---- prefilter (oracle/prefilter_oracle.c: restatement of the GLSL consumers at voxel centres) ----
+    def prefilter_ao(self, densities, W, H, D, radius=2.5, exponent=10.0, ao_max=0.16):
+        d = np.ascontiguousarray(densities, dtype=np.uint8).reshape(-1)
+        out = np.empty(W * H * D, dtype=np.float32)
+        self.lib.oracle_prefilter_ao(_ptr(d, _u8p), C.c_uint32(W), C.c_uint32(H), C.c_uint32(D),
+                                     C.c_float(radius), C.c_float(exponent), C.c_float(ao_max), _ptr(out, _f32p))
+        return out
+
+    def prefilter_opacity(self, densities, strand_alpha=0.3, thickness=11.0):
+        d = np.ascontiguousarray(densities, dtype=np.uint8).reshape(-1)
+        out = np.empty(d.size, dtype=np.float32)
+        self.lib.oracle_prefilter_opacity(_ptr(d, _u8p), C.c_uint64(d.size), C.c_float(strand_alpha), C.c_float(thickness),
+                                          _ptr(out, _f32p))
+        return out
+
+    def prefilter_gauss(self, densities, W, H, D, kernel_width=3.0):
+        d = np.ascontiguousarray(densities, dtype=np.uint8).reshape(-1)
+        out = np.empty(W * H * D, dtype=np.float32)
+        self.lib.oracle_prefilter_gauss(_ptr(d, _u8p), C.c_uint32(W), C.c_uint32(H), C.c_uint32(D), C.c_float(kernel_width),
+                                        _ptr(out, _f32p))
+        return out
+
     def fnv1a64(self, buf):
         b = np.ascontiguousarray(buf).view(np.uint8).reshape(-1)
         return int(self.lib.oracle_fnv1a64(_ptr(b, _u8p), C.c_uint64(b.size)))

@@ -177,3 +177,76 @@ def test_defined_extensions(port):
     # normalize with max == min leaves the grid unchanged
     flat = np.full(64, 7, dtype=np.uint8)
     assert np.array_equal(port.normalize(flat), flat)
+
+
+# ---- prefilter oracle (oracle/prefilter_oracle.c) -------------------------------------------------------------
+def _shader_lao_f64(d, W, H, D, origin, size, radius, exponent, ao_max):
+    """local_ambient_occlusion.glsl:9-30 + sample_volume.glsl:7-9 written out literally in float64 THROUGH WORLD
+    SPACE (fragment_position = voxel centre), with LINEAR / CLAMP_TO_BORDER(0) / R8_UNORM sampling per the Vulkan
+    spec (unnormalised coordinate u*size - 0.5, floor + fraction).  Independent of the oracle's texel-space shortcut."""
+    vol = np.zeros((D + 2, H + 2, W + 2))
+    vol[1:-1, 1:-1, 1:-1] = d.reshape(D, H, W) / 255.0                      # one texel of black border
+    res = np.array([W, H, D], dtype=np.float64)
+    origin, size = np.asarray(origin, np.float64), np.asarray(size, np.float64)
+    k, j, i = np.meshgrid(np.arange(D), np.arange(H), np.arange(W), indexing="ij")
+    centre = origin + (np.stack([i, j, k], -1) + 0.5) * (size / res)
+    kernel_size = 2.0
+    kernel_radius = (kernel_size - 1.0) / 2.0
+    voxel_sample_scaling = (radius / kernel_radius) * (size / res)
+
+    def texture(pos):
+        t = (pos - origin) / size * res - 0.5
+        t0 = np.floor(t)
+        f = t - t0
+        out = np.zeros(pos.shape[:-1])
+        for cz in (0, 1):
+            for cy in (0, 1):
+                for cx in (0, 1):
+                    x = np.clip(t0[..., 0] + cx, -1, W).astype(int) + 1
+                    y = np.clip(t0[..., 1] + cy, -1, H).astype(int) + 1
+                    z = np.clip(t0[..., 2] + cz, -1, D).astype(int) + 1
+                    w = (f[..., 0] if cx else 1 - f[..., 0]) * (f[..., 1] if cy else 1 - f[..., 1]) * (f[..., 2] if cz else 1 - f[..., 2])
+                    out += w * vol[z, y, x]
+        return out
+
+    density = np.zeros((D, H, W))
+    for z in (-kernel_radius, kernel_radius):
+        for y in (-kernel_radius, kernel_radius):
+            for x in (-kernel_radius, kernel_radius):
+                density += np.minimum(texture(centre + np.array([x, y, z]) * voxel_sample_scaling), ao_max)
+    return (1.0 - density / kernel_size ** 3) ** exponent
+
+
+@pytest.mark.parametrize("radius", [2.5, 1.25, 3.0, 0.75])
+def test_prefilter_ao_oracle_matches_the_shader_text(port, radius):
+    rng = np.random.default_rng(int(radius * 8))
+    W, H, D = 12, 10, 9
+    d = ((rng.random(W * H * D) < 0.3) * rng.integers(1, 256, W * H * D)).astype(np.uint8)
+    got = port.prefilter_ao(d, W, H, D, radius=radius, exponent=10.0, ao_max=0.16).reshape(D, H, W)
+    # power-of-two voxel size and origin: the world-space detour is exact in float64 and even integer radii
+    # (a tap exactly on a texel centre) land on the same side as the oracle's texel-space rule
+    want = _shader_lao_f64(d, W, H, D, origin=(-4.0, 8.0, 16.0), size=(W * 0.25, H * 0.5, D * 0.125), radius=radius,
+                           exponent=10.0, ao_max=0.16)
+    assert np.allclose(got, want, rtol=2e-5, atol=0)
+
+
+def test_prefilter_gauss_and_opacity_oracle(port):
+    rng = np.random.default_rng(4)
+    W, H, D = 9, 8, 7
+    d = ((rng.random(W * H * D) < 0.4) * rng.integers(1, 256, W * H * D)).astype(np.uint8)
+    for N in (1, 3, 5):
+        got = port.prefilter_gauss(d, W, H, D, float(N)).reshape(D, H, W)
+        R = (N - 1) // 2
+        sigma2 = ((N / 2.0) / 2.4) ** 2
+        pad = np.zeros((D + 2 * R, H + 2 * R, W + 2 * R))
+        pad[R:R + D, R:R + H, R:R + W] = d.reshape(D, H, W) / 255.0
+        acc, tot = np.zeros((D, H, W)), 0.0
+        for z in range(-R, R + 1):
+            for y in range(-R, R + 1):
+                for x in range(-R, R + 1):
+                    w = 1.0 / (2.0 * np.pi * sigma2) * np.e ** (-1.0 * (x * x + y * y + z * z) / 2.0 * sigma2)   # the quirk: * sigma2
+                    acc += w * pad[R + z:R + z + D, R + y:R + y + H, R + x:R + x + W]
+                    tot += w
+        assert np.allclose(got, acc / tot, rtol=2e-5, atol=1e-7)
+    op = port.prefilter_opacity(d, 0.3, 11.0)
+    assert np.allclose(op, (1 - 0.3) ** (d / 255.0 * 11.0), rtol=2e-6)

@@ -1,0 +1,116 @@
+"""GPU parity of the density -> AO / opacity / Gaussian prefilter (TMA-staged 3-D stencil) against the CPU restatement
+of the reference's GLSL (oracle/prefilter_oracle.c).  Tolerance: 1e-6 relative (BASELINE.json north_star: "derived
+float volumes must match within 1e-6 relative"); everything before the final powf is the same fp32 operation sequence."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from vkhr_b200 import capi, synth
+
+REL_TOL = 1e-6
+
+
+def _close(got, want, what):
+    assert got.shape == want.shape
+    assert np.all(np.isfinite(got)), what
+    err = np.abs(got.astype(np.float64) - want.astype(np.float64))
+    rel = err / np.maximum(np.abs(want.astype(np.float64)), 1e-30)
+    bad = (rel > REL_TOL) & (err > 1e-37)
+    assert not bad.any(), f"{what}: {bad.sum()} voxels off, worst rel {rel[bad].max():.3e}"
+    return float(rel[err > 0].max()) if (err > 0).any() else 0.0
+
+
+def _noise(rng, n, fill):
+    d = (rng.random(n) < fill) * rng.integers(1, 256, n)
+    return d.astype(np.uint8)
+
+
+def _hair(vox, port, W, H, D, seed=3):
+    v, n, s = synth.shape("ponytail", seed=seed, seg_len=1.0, scale=0.03)
+    lo, hi = port.generate_bounding_box(v)
+    return vox.voxelize_segments(v, None, lo, (hi - lo).astype(np.float32), W, H, D, segs_per_strand=s)
+
+
+@pytest.mark.parametrize("res", [(64, 32, 16), (32, 32, 32), (48, 40, 24), (16, 8, 8), (30, 20, 10), (4, 4, 4), (33, 7, 5)])
+@pytest.mark.parametrize("radius", [2.5, 2.0, 1.3, 0.0, 0.5])
+def test_ao_against_oracle(vox, port, res, radius):
+    W, H, D = res
+    rng = np.random.default_rng(W * 131 + int(radius * 10))
+    for d in (_noise(rng, W * H * D, 0.15), _noise(rng, W * H * D, 0.9), _hair(vox, port, W, H, D)):
+        want = port.prefilter_ao(d, W, H, D, radius=radius)
+        got = vox.prefilter(d, W, H, D, ao=True, ao_radius=radius)["ao"]
+        _close(got, want, f"ao {res} r={radius}")
+        gen = vox.prefilter(d, W, H, D, ao=True, ao_radius=radius, flags=capi.PREFILTER_GENERIC)["ao"]
+        assert np.array_equal(gen, got), "tiled and generic kernels must agree bit for bit"
+
+
+@pytest.mark.parametrize("radius,exponent,ao_max", [(5.75, 10.0, 0.16), (7.25, 3.0, 0.4), (8.0, 32.0, 0.05), (8.5, 1.0, 0.2), (12.0, 10.0, 0.16)])
+def test_ao_large_radii_and_ui_ranges(vox, port, radius, exponent, ao_max):
+    """The UI ranges (interface.cc:291-293): radius 0..8, exponent 0..32, clamp 0..0.4; halo > 8 takes the generic kernel."""
+    W, H, D = 48, 24, 24
+    rng = np.random.default_rng(int(radius * 100))
+    d = _noise(rng, W * H * D, 0.3)
+    want = port.prefilter_ao(d, W, H, D, radius=radius, exponent=exponent, ao_max=ao_max)
+    got = vox.prefilter(d, W, H, D, ao=True, ao_radius=radius, ao_exponent=exponent, ao_max=ao_max)["ao"]
+    _close(got, want, f"ao r={radius}")
+
+
+@pytest.mark.parametrize("res", [(64, 32, 16), (30, 20, 10), (4, 4, 4)])
+@pytest.mark.parametrize("width", [1, 3, 5, 7, 9])
+def test_gauss_and_opacity_against_oracle(vox, port, res, width):
+    W, H, D = res
+    rng = np.random.default_rng(W + width)
+    d = _noise(rng, W * H * D, 0.3)
+    out = vox.prefilter(d, W, H, D, ao=True, opacity=True, gauss=True, gauss_width=float(width), strand_alpha=0.35, thickness=11.0)
+    _close(out["gauss"], port.prefilter_gauss(d, W, H, D, float(width)), f"gauss {res} N={width}")
+    _close(out["opacity"], port.prefilter_opacity(d, 0.35, 11.0), f"opacity {res}")
+    _close(out["ao"], port.prefilter_ao(d, W, H, D), f"ao {res} (all three outputs in one launch)")
+    # opacity is a per-density table: exactly 256 distinct values at most, 1.0 where empty
+    assert np.all(out["opacity"][d == 0] == 1.0)
+
+
+def test_prefilter_errors(vox):
+    d = np.zeros(64, dtype=np.uint8)
+    with pytest.raises(capi.VkhrB200Error) as e:
+        vox.prefilter(d, 4, 4, 4, gauss=True, gauss_width=4.0)
+    assert e.value.code == capi.ERR_INVALID_ARGUMENT
+    with pytest.raises(capi.VkhrB200Error):
+        vox.prefilter(d, 4, 4, 4, ao=True, ao_radius=-1.0)
+    with pytest.raises(capi.VkhrB200Error):
+        vox.prefilter(d, 4, 4, 4, ao=True, ao_radius=float("nan"))
+    # empty volume: AO is exactly 1, Gaussian exactly 0
+    out = vox.prefilter(d, 4, 4, 4, ao=True, gauss=True)
+    assert np.all(out["ao"] == 1.0) and np.all(out["gauss"] == 0.0)
+
+
+def test_prefilter_full_size_device_path(vox, port):
+    """256^3 (the reference's resolution) on the device API: a slab is checked against the oracle, the whole volume
+    against the generic kernel bit for bit, and empty space must come out as exactly 1."""
+    import torch
+    dev = torch.device("cuda", 0)
+    W = H = D = 256
+    v, n, s = synth.shape("ponytail", seed=0x5EED, seg_len=0.5)
+    lo, hi = synth.host_bounding_box(v)
+    size = (hi - lo).astype(np.float32)
+    dens = vox.voxelize_segments_dev(torch.from_numpy(v).to(dev).reshape(-1), None, lo, size, W, H, D, segs_per_strand=s)
+    ao = torch.empty(W * H * D, dtype=torch.float32, device=dev)
+    op = torch.empty_like(ao)
+    ao2 = torch.empty_like(ao)
+    vox.prefilter_dev(dens, W, H, D, ao=ao, opacity=op)
+    vox.prefilter_dev(dens, W, H, D, ao=ao2, flags=capi.PREFILTER_GENERIC)
+    torch.cuda.synchronize()
+    assert torch.equal(ao, ao2)
+    dh = dens.cpu().numpy()
+    # oracle on a z-slab with its halo (the slab's interior does not see the cut)
+    z0, z1, hz = 120, 136, 3
+    sub = dh.reshape(D, H, W)[z0 - hz:z1 + hz].reshape(-1)
+    want = port.prefilter_ao(sub, W, H, z1 - z0 + 2 * hz).reshape(-1, H, W)[hz:-hz]
+    got = ao.cpu().numpy().reshape(D, H, W)[z0:z1]
+    _close(got, want, "ao 256^3 slab")
+    _close(op.cpu().numpy(), port.prefilter_opacity(dh), "opacity 256^3")
+    a = ao.cpu().numpy()
+    assert a.max() == 1.0 and a.min() > 0.17            # (1 - 0.16)^10 is the floor
+    # a voxel whose whole footprint is empty is exactly 1
+    occ = torch.nn.functional.max_pool3d((dens.reshape(1, 1, D, H, W) > 0).float(), 7, 1, 3).reshape(-1) > 0
+    assert torch.all(ao[~occ] == 1.0)

@@ -64,6 +64,18 @@ class HostInstance(C.Structure):
     ]
 
 
+class PrefilterParams(C.Structure):
+    """``vkhr_b200_prefilter_params``."""
+    _fields_ = [
+        ("ao_radius", C.c_float), ("ao_exponent", C.c_float), ("ao_max", C.c_float),
+        ("strand_alpha", C.c_float), ("thickness", C.c_float), ("gauss_width", C.c_float),
+        ("flags", C.c_uint32),
+    ]
+
+
+PREFILTER_GENERIC = 1 << 0
+
+
 class VkhrB200Error(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"vkhr_b200 error {code}: {message}")
@@ -115,6 +127,10 @@ _PROTOTYPES = {
     "vkhr_b200_downsample": (_int, [c_ctx, _P, _u32, _u32, _u32, _int, _P]),
     "vkhr_b200_generate_bounding_box_dev": (_int, [c_ctx, _P, _u32, _P, _P]),
     "vkhr_b200_generate_bounding_box": (_int, [c_ctx, _P, _u32, C.c_float * 6]),
+    "vkhr_b200_profile_read_ex": (_int, [c_ctx, C.POINTER(C.c_double), C.POINTER(C.c_uint32), _u32]),
+    "vkhr_b200_prefilter_defaults": (None, [C.POINTER(PrefilterParams)]),
+    "vkhr_b200_prefilter_dev": (_int, [c_ctx, _P, _u32, _u32, _u32, C.POINTER(PrefilterParams), _P, _P, _P, _P]),
+    "vkhr_b200_prefilter": (_int, [c_ctx, _P, _u32, _u32, _u32, C.POINTER(PrefilterParams), _P, _P, _P]),
     "vkhr_b200_malloc": (_int, [c_ctx, _sz, C.POINTER(_P)]),
     "vkhr_b200_free": (_int, [c_ctx, _P]),
     "vkhr_b200_memset": (_int, [c_ctx, _P, _int, _sz, _P]),

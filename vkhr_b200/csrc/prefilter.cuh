@@ -1,0 +1,294 @@
+// prefilter.cuh -- density -> ambient-occlusion / opacity / Gaussian prefilter: a TMA-staged 3-D stencil pass.
+//
+// What the reference's fragment shaders compute from the density volume at every shaded point, evaluated
+// once per voxel centre (paths relative to the reference tree):
+//   local_ambient_occlusion            share/shaders/volumes/local_ambient_occlusion.glsl:9-30
+//   volume_approximated_deep_shadows   share/shaders/self-shadowing/approximate_deep_shadows.glsl:24-36 (one step)
+//   filter_volume                      share/shaders/volumes/sample_volume.glsl:12-35
+//   sample_volume / sampler            sample_volume.glsl:7-9; R8_UNORM, LINEAR, CLAMP_TO_BORDER (black):
+//                                      src/vkhr/rasterizer/hair_style.cc:79-85,:94-101
+// The arithmetic contract (texel decode, tap geometry, nested x-y-z weighted sums, accumulation order) is the
+// one written out in oracle/prefilter_oracle.c; every fp32 operation below is a separately rounded
+// __f*_rn intrinsic in that order, so everything up to the final powf is bit-identical to the oracle.
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace vkhr_b200 {
+
+constexpr int kPfTX = 32, kPfTY = 8, kPfTZ = 8;      // output voxels per tile
+// The staged box starts kPfLead texels left of the tile: the innermost TMA coordinate must be a multiple of 16 BYTES
+// (measured: tools/tma_probe.cu -- x = -16, 16, 48 load, x = -3, 4, 29 raise "illegal instruction"), so the halo
+// cannot start at x0 - halo; the box is [x0 - 16, x0 + 48) and the kernel uses [x0 - halo, x0 + 32 + halo) of it.
+constexpr int kPfLead = 16;
+constexpr int kPfBX = kPfTX + 2 * kPfLead;           // 64 bytes per staged row (TMA inner box extent)
+constexpr int kPfMaxHalo = 8;                        // shared-memory budget (the float tile grows with halo^3)
+constexpr int kPfThreads = 256;
+constexpr int kPfMaxGauss = 9;                       // largest Gaussian kernel width
+
+struct AxisTaps { int o0, o1; float w0, w1; };       // texels i + o0, i + o1 and their weights
+
+struct PrefilterArgs {
+    const uint8_t* dens;
+    int W, H, D;
+    int halo;                  // texels needed on each side of a tile
+    float* ao;                 // outputs (nullptr = not wanted)
+    float* opacity;
+    float* gauss;
+    AxisTaps neg, pos;         // LAO taps at -radius / +radius voxels
+    float ao_max, ao_exponent;
+    float one_minus_alpha, thickness;
+    int g_range;               // (kernel_width - 1) / 2
+    float g_sigma2;
+    uint32_t tiles_x, tiles_y, tiles_z;
+};
+
+// ---- the arithmetic, shared by the tiled and the generic kernel ---------------------------------------------
+// fetch(ox, oy, oz) = tau of the texel displaced by (ox, oy, oz) from this thread's voxel (0 outside the grid).
+
+template <class Fetch>
+__device__ __forceinline__ float lao_at(const PrefilterArgs& A, Fetch&& fetch) {
+    const AxisTaps ax[2] = {A.neg, A.pos};
+    // X-lerps for the 4 x 4 (y,z) rows of the footprint, Y-lerps kept per z row
+    float yl[2][2][4];                                   // [sx][sy][z row]
+#pragma unroll
+    for (int zr = 0; zr < 4; ++zr) {
+        const int oz = (zr & 1) ? ax[zr >> 1].o1 : ax[zr >> 1].o0;
+        float xl[2][4];                                  // [sx][y row]
+#pragma unroll
+        for (int yr = 0; yr < 4; ++yr) {
+            const int oy = (yr & 1) ? ax[yr >> 1].o1 : ax[yr >> 1].o0;
+#pragma unroll
+            for (int sx = 0; sx < 2; ++sx) {
+                const float t0 = fetch(ax[sx].o0, oy, oz), t1 = fetch(ax[sx].o1, oy, oz);
+                xl[sx][yr] = __fadd_rn(__fmul_rn(t0, ax[sx].w0), __fmul_rn(t1, ax[sx].w1));
+            }
+        }
+#pragma unroll
+        for (int sx = 0; sx < 2; ++sx)
+#pragma unroll
+            for (int sy = 0; sy < 2; ++sy)
+                yl[sx][sy][zr] = __fadd_rn(__fmul_rn(xl[sx][2 * sy], ax[sy].w0), __fmul_rn(xl[sx][2 * sy + 1], ax[sy].w1));
+    }
+    float density = 0.0f;
+#pragma unroll
+    for (int sz = 0; sz < 2; ++sz)
+#pragma unroll
+        for (int sy = 0; sy < 2; ++sy)
+#pragma unroll
+            for (int sx = 0; sx < 2; ++sx) {
+                const float s = __fadd_rn(__fmul_rn(yl[sx][sy][2 * sz], ax[sz].w0), __fmul_rn(yl[sx][sy][2 * sz + 1], ax[sz].w1));
+                density = __fadd_rn(density, (A.ao_max < s) ? A.ao_max : s);
+            }
+    return powf(__fsub_rn(1.0f, __fdiv_rn(density, 8.0f)), A.ao_exponent);    // pow(kernel_size = 2, 3) = 8
+}
+
+// Gaussian weight of tap (x,y,z) (sample_volume.glsl:26-27, precedence quirk kept).
+__device__ __forceinline__ float gauss_weight(float x, float y, float z, float sigma2) {
+    const float e = __fmul_rn(__fdiv_rn(__fmul_rn(-1.0f, __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z))), 2.0f), sigma2);
+    const float pi = 3.14159265358979323846f, euler = 2.71828182845904523536f;
+    return __fmul_rn(__fdiv_rn(1.0f, __fmul_rn(__fmul_rn(2.0f, pi), sigma2)), powf(euler, e));
+}
+
+template <class Fetch>
+__device__ __forceinline__ float gauss_at(const PrefilterArgs& A, const float* __restrict__ w, Fetch&& fetch) {
+    const int R = A.g_range, N = 2 * R + 1;
+    float density = 0.0f, total = 0.0f;
+    for (int z = -R; z <= R; ++z)
+        for (int y = -R; y <= R; ++y)
+            for (int x = -R; x <= R; ++x) {
+                const float lw = w[((z + R) * N + (y + R)) * N + (x + R)];
+                density = __fadd_rn(density, __fmul_rn(fetch(x, y, z), lw));
+                total = __fadd_rn(total, lw);
+            }
+    return __fdiv_rn(density, total);
+}
+
+__device__ __forceinline__ float opacity_of(const PrefilterArgs& A, uint32_t d) {
+    return powf(A.one_minus_alpha, __fmul_rn(__fdiv_rn((float)d, 255.0f), A.thickness));
+}
+
+// ---- generic kernel: any grid size / alignment / radius; one thread per voxel, texels straight from global ----
+__global__ void __launch_bounds__(256)
+k_prefilter_generic(const __grid_constant__ PrefilterArgs A) {
+    __shared__ float s_gw[kPfMaxGauss * kPfMaxGauss * kPfMaxGauss];
+    if (A.gauss) {
+        const int N = 2 * A.g_range + 1;
+        for (int t = threadIdx.x; t < N * N * N; t += blockDim.x)
+            s_gw[t] = gauss_weight((float)(t % N - A.g_range), (float)((t / N) % N - A.g_range), (float)(t / (N * N) - A.g_range), A.g_sigma2);
+        __syncthreads();
+    }
+    const uint64_t n = (uint64_t)A.W * A.H * A.D;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (uint64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(v % A.W), j = (int)((v / A.W) % A.H), k = (int)(v / ((uint64_t)A.W * A.H));
+        auto fetch = [&](int ox, int oy, int oz) -> float {
+            const int x = i + ox, y = j + oy, z = k + oz;
+            if (x < 0 || y < 0 || z < 0 || x >= A.W || y >= A.H || z >= A.D) return 0.0f;
+            return __fdiv_rn((float)__ldg(A.dens + (size_t)x + (size_t)y * A.W + (size_t)z * A.W * A.H), 255.0f);
+        };
+        if (A.ao) A.ao[v] = lao_at(A, fetch);
+        if (A.opacity) A.opacity[v] = opacity_of(A, __ldg(A.dens + v));
+        if (A.gauss) A.gauss[v] = gauss_at(A, s_gw, fetch);
+    }
+}
+
+// ---- tiled kernel: persistent CTAs, 3-D TMA box loads (zero fill outside the grid = the black border) ----------
+__device__ __forceinline__ uint32_t pf_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void pf_tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int y, int z, uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void pf_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (spin > (1u << 24)) __trap();                 // a lost copy must fail, not hang the device
+    }
+}
+
+// Shared-memory plan (dynamic): [stage 0][stage 1][float tile][row flags][decode LUT][opacity LUT][gauss weights][2 mbarriers]
+struct PfSmemPlan {
+    uint32_t stage_bytes, stage1, ftile, flags, lut, oplut, gw, bars, total;
+};
+__host__ __device__ inline PfSmemPlan pf_plan(int halo, int g_range) {
+    PfSmemPlan p;
+    const uint32_t BY = kPfTY + 2 * halo, BZ = kPfTZ + 2 * halo, FX = kPfTX + 2 * halo;
+    p.stage_bytes = (kPfBX * BY * BZ + 127u) & ~127u;
+    p.stage1 = p.stage_bytes;
+    p.ftile = 2 * p.stage_bytes;
+    p.flags = p.ftile + FX * BY * BZ * 4u;
+    p.lut = p.flags + ((BY * BZ * 4u + 15u) & ~15u);
+    p.oplut = p.lut + 1024u;
+    p.gw = p.oplut + 1024u;
+    const uint32_t N = 2 * g_range + 1;
+    p.bars = p.gw + ((N * N * N * 4u + 15u) & ~15u);
+    p.total = p.bars + 16u;
+    return p;
+}
+
+__global__ void __launch_bounds__(kPfThreads)
+k_prefilter_tiled(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ PrefilterArgs A) {
+    extern __shared__ __align__(128) unsigned char pf_smem[];
+    const int h = A.halo, BY = kPfTY + 2 * h, BZ = kPfTZ + 2 * h, FX = kPfTX + 2 * h;
+    const PfSmemPlan P = pf_plan(h, A.g_range);
+    float* ftile = reinterpret_cast<float*>(pf_smem + P.ftile);
+    uint32_t* rowflag = reinterpret_cast<uint32_t*>(pf_smem + P.flags);
+    float* lut = reinterpret_cast<float*>(pf_smem + P.lut);
+    float* oplut = reinterpret_cast<float*>(pf_smem + P.oplut);
+    float* gw = reinterpret_cast<float*>(pf_smem + P.gw);
+    const uint32_t bar0 = pf_smem_u32(pf_smem + P.bars);
+    const uint32_t box_bytes = (uint32_t)(kPfBX * BY * BZ);
+    const uint32_t n_tiles = A.tiles_x * A.tiles_y * A.tiles_z;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    auto tile_origin = [&](uint32_t t, int& x0, int& y0, int& z0) {
+        x0 = (int)(t % A.tiles_x) * kPfTX;
+        y0 = (int)((t / A.tiles_x) % A.tiles_y) * kPfTY;
+        z0 = (int)(t / (A.tiles_x * A.tiles_y)) * kPfTZ;
+    };
+    auto issue = [&](uint32_t t, uint32_t buf) {
+        int x0, y0, z0;
+        tile_origin(t, x0, y0, z0);
+        pf_tma_load_3d(pf_smem_u32(pf_smem + buf * P.stage_bytes), &tmap, x0 - kPfLead, y0 - h, z0 - h, bar0 + 8u * buf, box_bytes);
+    };
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    // per-CTA tables: R8_UNORM decode, opacity of each of the 256 densities, Gaussian weights
+    lut[tid] = __fdiv_rn((float)tid, 255.0f);
+    if (A.opacity) oplut[tid] = opacity_of(A, (uint32_t)tid);
+    if (A.gauss) {
+        const int N = 2 * A.g_range + 1;
+        for (int t = tid; t < N * N * N; t += kPfThreads)
+            gw[t] = gauss_weight((float)(t % N - A.g_range), (float)((t / N) % N - A.g_range), (float)(t / (N * N) - A.g_range), A.g_sigma2);
+    }
+    for (int r = tid; r < BY * BZ; r += kPfThreads) rowflag[r] = 0u;
+    // constants of empty space
+    const float ao_empty = powf(__fsub_rn(1.0f, __fdiv_rn(0.0f, 8.0f)), A.ao_exponent);
+    __syncthreads();
+    if (blockIdx.x < n_tiles && tid == 0) issue(blockIdx.x, 0);
+
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t buf = it & 1u;
+        if (tid == 0 && tile + gridDim.x < n_tiles) issue(tile + gridDim.x, buf ^ 1u);   // prefetch the next tile
+        pf_mbar_wait(bar0 + 8u * buf, (it >> 1) & 1u);
+        const unsigned char* stage = pf_smem + buf * P.stage_bytes;
+
+        // ---- u8 rows -> float rows (+ which rows hold anything) --------------------------------------------
+        int mine = 0;
+        constexpr int kParts = kPfBX / 16;
+        for (int c = tid; c < kParts * BY * BZ; c += kPfThreads) {
+            const int row = c / kParts, part = c - kParts * row;
+            const int f0 = part * 16 - (kPfLead - h);                        // float-tile x of this chunk's first byte
+            if (f0 + 16 <= 0 || f0 >= FX) continue;                          // chunk entirely outside the used span
+            const uint4 q = *reinterpret_cast<const uint4*>(stage + row * kPfBX + part * 16);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+            float* dst = ftile + row * FX + f0;
+            if ((q.x | q.y | q.z | q.w) != 0u) {
+                bool used = false;
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                    if (f0 + e >= 0 && f0 + e < FX) { const uint32_t b = (w[e >> 2] >> (8 * (e & 3))) & 0xFFu; dst[e] = lut[b]; used |= (b != 0u); }
+                if (used) { rowflag[row] = 1u; mine = 1; }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) if (f0 + e >= 0 && f0 + e < FX) dst[e] = 0.0f;
+            }
+        }
+        const int tile_any = __syncthreads_or(mine);
+
+        // ---- one output row (32 voxels along x) per warp-iteration ---------------------------------------------
+        int x0, y0, z0;
+        tile_origin(tile, x0, y0, z0);
+        for (int rr = warp; rr < kPfTY * kPfTZ; rr += kPfThreads / 32) {
+            const int jy = rr % kPfTY, kz = rr / kPfTY;
+            const int X = x0 + lane, Y = y0 + jy, Z = z0 + kz;
+            if (Y >= A.H || Z >= A.D) continue;                               // warp-uniform
+            const size_t v = (size_t)X + (size_t)Y * A.W + (size_t)Z * A.W * A.H;
+            const bool inside = X < A.W;
+            const float* centre = ftile + ((kz + h) * BY + (jy + h)) * FX + (lane + h);
+            auto fetch = [&](int ox, int oy, int oz) -> float { return centre[(oz * BY + oy) * FX + ox]; };
+            auto flag = [&](int oy, int oz) -> uint32_t { return rowflag[(kz + h + oz) * BY + (jy + h + oy)]; };
+            if (A.ao) {
+                float r = ao_empty;
+                uint32_t any = 0u;
+                if (tile_any) {
+                    const int o[4] = {A.neg.o0, A.neg.o1, A.pos.o0, A.pos.o1};
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) any |= flag(o[a], o[b]);
+                }
+                if (any) r = lao_at(A, fetch);
+                if (inside) __stcs(A.ao + v, r);
+            }
+            if (A.opacity) {
+                const uint32_t d = stage[((kz + h) * BY + (jy + h)) * kPfBX + (lane + kPfLead)];
+                if (inside) __stcs(A.opacity + v, oplut[d]);
+            }
+            if (A.gauss) {
+                float r = 0.0f;                                               // 0 / total_weight
+                uint32_t any = 0u;
+                if (tile_any)
+                    for (int b = -A.g_range; b <= A.g_range; ++b)
+                        for (int a = -A.g_range; a <= A.g_range; ++a) any |= flag(a, b);
+                if (any) r = gauss_at(A, gw, fetch);
+                if (inside) __stcs(A.gauss + v, r);
+            }
+        }
+        __syncthreads();                                   // everyone is done with ftile / flags / this stage buffer
+        if (tile_any) for (int r = tid; r < BY * BZ; r += kPfThreads) rowflag[r] = 0u;
+        __syncthreads();                                   // flags are clean before the next tile's conversion sets them
+    }
+}
+
+}  // namespace vkhr_b200

@@ -9,6 +9,7 @@
 // runs the CUDA kernels or returns an error.
 #include "../../include/vkhr_b200.h"
 #include "kernels.cuh"
+#include "prefilter.cuh"
 
 #include <cooperative_groups.h>
 #include <algorithm>
@@ -124,6 +125,7 @@ struct vkhr_b200_ctx {
     Slot slots[kSlots];
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     int repair_blocks[2] = {0, 0};
+    uint32_t pf_smem_opted = 0;   // dynamic shared memory the tiled prefilter kernel has been opted into
     Batch batch;          // host copy of the kernel-parameter batch being launched
     // optional per-phase device timing (vkhr_b200_profile_*): CUDA events recorded on the
     // launching stream around each phase of run_voxelize
@@ -133,7 +135,7 @@ struct vkhr_b200_ctx {
     std::vector<cudaEvent_t> event_pool;
 };
 
-enum Phase { PH_CLEAR = 0, PH_WALK = 1, PH_FINISH = 2, PH_NORMALIZE = 3, PH_COUNT = 4 };
+enum Phase { PH_CLEAR = 0, PH_WALK = 1, PH_FINISH = 2, PH_NORMALIZE = 3, PH_PREFILTER = 4, PH_COUNT = 5 };
 
 static thread_local std::string g_create_error;
 
@@ -589,21 +591,24 @@ int vkhr_b200_profile_enable(vkhr_b200_ctx* ctx, int enable) {
     return VKHR_B200_OK;
 }
 
-int vkhr_b200_profile_read(vkhr_b200_ctx* ctx, double ms_out[4], uint32_t spans_out[4]) {
+int vkhr_b200_profile_read_ex(vkhr_b200_ctx* ctx, double* ms_out, uint32_t* spans_out, uint32_t n_phases) {
     RET_IF(bind(ctx));
     if (!ms_out || !spans_out) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null output");
-    for (int k = 0; k < PH_COUNT; ++k) { ms_out[k] = 0.0; spans_out[k] = 0; }
+    for (uint32_t k = 0; k < n_phases; ++k) { ms_out[k] = 0.0; spans_out[k] = 0; }
     for (auto& sp : ctx->spans) {
         CU_CHECK(ctx, cudaEventSynchronize(sp.b));
         float ms = 0.0f;
         CU_CHECK(ctx, cudaEventElapsedTime(&ms, sp.a, sp.b));
-        ms_out[sp.phase] += ms;
-        spans_out[sp.phase] += 1;
+        if ((uint32_t)sp.phase < n_phases) { ms_out[sp.phase] += ms; spans_out[sp.phase] += 1; }
         ctx->event_pool.push_back(sp.a);
         ctx->event_pool.push_back(sp.b);
     }
     ctx->spans.clear();
     return VKHR_B200_OK;
+}
+
+int vkhr_b200_profile_read(vkhr_b200_ctx* ctx, double ms_out[4], uint32_t spans_out[4]) {
+    return vkhr_b200_profile_read_ex(ctx, ms_out, spans_out, 4);
 }
 
 int vkhr_b200_selftest_division(vkhr_b200_ctx* ctx, float divisor, uint64_t n_trials, uint64_t seed, uint64_t* mismatches) {
@@ -954,6 +959,141 @@ int vkhr_b200_host_register(vkhr_b200_ctx* ctx, void* ptr, size_t bytes) {
 int vkhr_b200_host_unregister(vkhr_b200_ctx* ctx, void* ptr) {
     RET_IF(bind(ctx));
     CU_CHECK(ctx, cudaHostUnregister(ptr));
+    return VKHR_B200_OK;
+}
+
+// ---- density -> AO / opacity / Gaussian prefilter ------------------------------------------------------------
+void vkhr_b200_prefilter_defaults(vkhr_b200_prefilter_params* p) {
+    if (!p) return;
+    p->ao_radius = 2.5f; p->ao_exponent = 10.0f; p->ao_max = 0.16f;      // interface.hh:101-105
+    p->strand_alpha = 0.3f; p->thickness = 11.0f;                         // volume.frag:78
+    p->gauss_width = 3.0f; p->flags = 0;
+}
+
+namespace {
+// texels and weights of a LINEAR sample displaced by +-r voxels from a voxel centre (oracle/prefilter_oracle.c)
+AxisTaps axis_taps(float r, bool positive) {
+    AxisTaps a;
+    const float fl = std::floor(r), fp = r - fl;
+    const int ifl = (int)fl;
+    if (positive) { a.o0 = ifl; a.o1 = ifl + 1; a.w0 = 1.0f - fp; a.w1 = fp; }
+    else if (fp != 0.0f) { a.o0 = -ifl - 1; a.o1 = -ifl; a.w0 = fp; a.w1 = 1.0f - fp; }
+    else { a.o0 = -ifl; a.o1 = -ifl + 1; a.w0 = 1.0f; a.w1 = 0.0f; }
+    return a;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else (void)cudaGetLastError();
+    }
+    return fn;
+}
+}  // namespace
+
+int vkhr_b200_prefilter_dev(vkhr_b200_ctx* ctx, const uint8_t* d_densities, uint32_t W, uint32_t H, uint32_t D,
+                            const vkhr_b200_prefilter_params* params, float* d_ao, float* d_opacity, float* d_gauss, void* stream) {
+    RET_IF(bind(ctx));
+    if (!d_densities) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null densities");
+    if (W == 0 || H == 0 || D == 0) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "zero resolution");
+    if ((unsigned long long)W * H * D >= (1ull << 32)) return fail(ctx, VKHR_B200_ERR_UNSUPPORTED, "W*H*D must be < 2^32");
+    if (!d_ao && !d_opacity && !d_gauss) return VKHR_B200_OK;
+    vkhr_b200_prefilter_params P;
+    if (params) P = *params; else vkhr_b200_prefilter_defaults(&P);
+    PrefilterArgs A{};
+    A.dens = d_densities; A.W = (int)W; A.H = (int)H; A.D = (int)D;
+    A.ao = d_ao; A.opacity = d_opacity; A.gauss = d_gauss;
+    int halo = 0;
+    if (d_ao) {
+        if (!(P.ao_radius >= 0.0f) || !(P.ao_radius <= 64.0f) || !std::isfinite(P.ao_exponent) || !std::isfinite(P.ao_max))
+            return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "ao_radius must be in [0, 64] voxels and ao_exponent / ao_max finite");
+        // local_ambient_occlusion.glsl:15-18 with kernel_size = 2: the taps sit kernel_radius * voxel_scaling voxels away
+        const float kernel_radius = (2.0f - 1.0f) / 2.0f, voxel_scaling = P.ao_radius / kernel_radius;
+        const float r = kernel_radius * voxel_scaling;
+        A.neg = axis_taps(r, false); A.pos = axis_taps(r, true);
+        A.ao_max = P.ao_max; A.ao_exponent = P.ao_exponent;
+        halo = std::max(halo, std::max(A.pos.o1, -A.neg.o0));
+    }
+    if (d_opacity) {
+        if (!std::isfinite(P.strand_alpha) || !std::isfinite(P.thickness))
+            return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "strand_alpha and thickness must be finite");
+        A.one_minus_alpha = 1.0f - P.strand_alpha; A.thickness = P.thickness;
+    }
+    if (d_gauss) {
+        const int n = (int)P.gauss_width;
+        if ((float)n != P.gauss_width || n < 1 || n > kPfMaxGauss || (n & 1) == 0)
+            return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "gauss_width must be an odd integer in [1, 9]");
+        // sample_volume.glsl:17-19
+        const float sigma_stddev = (P.gauss_width / 2.0f) / 2.4f;
+        A.g_range = (n - 1) / 2; A.g_sigma2 = sigma_stddev * sigma_stddev;
+        halo = std::max(halo, A.g_range);
+    }
+    A.halo = halo;
+    A.tiles_x = (W + kPfTX - 1) / kPfTX; A.tiles_y = (H + kPfTY - 1) / kPfTY; A.tiles_z = (D + kPfTZ - 1) / kPfTZ;
+    cudaStream_t s = pick(ctx, stream);
+    PhaseMark mk(ctx, s, PH_PREFILTER);
+    const bool tiled = !(P.flags & VKHR_B200_PREFILTER_GENERIC) && halo <= kPfMaxHalo && (W % 16u) == 0 &&
+                       (reinterpret_cast<uintptr_t>(d_densities) & 15u) == 0;
+    if (!tiled) {
+        const uint64_t n = (uint64_t)W * H * D;
+        k_prefilter_generic<<<stride_blocks(ctx, n, 256, 32), 256, 0, s>>>(A);
+        ctx->launches++;
+        CU_CHECK(ctx, cudaGetLastError());
+        return VKHR_B200_OK;
+    }
+    EncodeTiledFn encode = encode_tiled_fn();
+    if (!encode) return fail(ctx, VKHR_B200_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    CUtensorMap tmap;
+    const cuuint64_t gdim[3] = {W, H, D};
+    const cuuint64_t gstride[2] = {(cuuint64_t)W, (cuuint64_t)W * H};                 // bytes, dims 1 and 2
+    const cuuint32_t box[3] = {(cuuint32_t)kPfBX, (cuuint32_t)(kPfTY + 2 * halo), (cuuint32_t)(kPfTZ + 2 * halo)};
+    const cuuint32_t estride[3] = {1, 1, 1};
+    const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(d_densities), gdim, gstride, box, estride,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(ctx, VKHR_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)cr));
+    const PfSmemPlan plan = pf_plan(halo, A.g_range);
+    if (plan.total > ctx->pf_smem_opted) {
+        CU_CHECK(ctx, cudaFuncSetAttribute(k_prefilter_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total));
+        ctx->pf_smem_opted = plan.total;
+    }
+    int per_sm = 0;
+    CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_prefilter_tiled, kPfThreads, plan.total));
+    if (per_sm < 1) return fail(ctx, VKHR_B200_ERR_CUDA, "prefilter kernel does not fit on an SM");
+    const uint64_t n_tiles = (uint64_t)A.tiles_x * A.tiles_y * A.tiles_z;
+    const unsigned blocks = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)per_sm * ctx->sm_count);
+    k_prefilter_tiled<<<blocks, kPfThreads, plan.total, s>>>(tmap, A);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return VKHR_B200_OK;
+}
+
+int vkhr_b200_prefilter(vkhr_b200_ctx* ctx, const uint8_t* densities, uint32_t W, uint32_t H, uint32_t D,
+                        const vkhr_b200_prefilter_params* params, float* ao_out, float* opacity_out, float* gauss_out) {
+    RET_IF(bind(ctx));
+    if (!densities) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null densities");
+    const size_t n = (size_t)W * H * D;
+    if (n == 0) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "zero resolution");
+    float* outs[3] = {ao_out, opacity_out, gauss_out};
+    int wanted = 0;
+    for (float* o : outs) wanted += o != nullptr;
+    if (!wanted) return VKHR_B200_OK;
+    RET_IF(stage_in(ctx, ctx->st_dens, densities, n));
+    RET_IF(reserve(ctx, ctx->st_tang_out, n * 4 * wanted));
+    float* d_out[3] = {nullptr, nullptr, nullptr};
+    int slot = 0;
+    for (int k = 0; k < 3; ++k) if (outs[k]) d_out[k] = static_cast<float*>(ctx->st_tang_out.p) + n * (slot++);
+    RET_IF(vkhr_b200_prefilter_dev(ctx, static_cast<const uint8_t*>(ctx->st_dens.p), W, H, D, params, d_out[0], d_out[1], d_out[2], ctx->stream));
+    for (int k = 0; k < 3; ++k)
+        if (outs[k]) CU_CHECK(ctx, cudaMemcpyAsync(outs[k], d_out[k], n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     return VKHR_B200_OK;
 }
 

@@ -68,9 +68,9 @@ class Voxelizer:
 
     def profile_read(self) -> dict:
         """Summed device milliseconds / span counts per phase since the last read."""
-        ms, n = (C.c_double * 4)(), (C.c_uint32 * 4)()
-        capi.check(self._h, lib.vkhr_b200_profile_read(self._h, ms, n))
-        names = ("clear", "walk", "finish", "normalize")
+        ms, n = (C.c_double * 5)(), (C.c_uint32 * 5)()
+        capi.check(self._h, lib.vkhr_b200_profile_read_ex(self._h, ms, n, 5))
+        names = ("clear", "walk", "finish", "normalize", "prefilter")
         return {k: {"ms": ms[i], "spans": int(n[i])} for i, k in enumerate(names)}
 
     def selftest_division(self, divisor: float, n_trials: int = 1 << 26, seed: int = 1) -> int:
@@ -171,6 +171,29 @@ class Voxelizer:
             raise ValueError("densities does not match W*H*D")
         out = np.empty((W // 2) * (H // 2) * (D // 2), dtype=np.uint8)
         capi.check(self._h, lib.vkhr_b200_downsample(self._h, _p(d), int(W), int(H), int(D), int(filter), _p(out)))
+        return out
+
+    @staticmethod
+    def prefilter_params(**kw) -> "capi.PrefilterParams":
+        """``vkhr_b200_prefilter_params`` with the reference's defaults (interface.hh:101-105), overridden by ``kw``."""
+        p = capi.PrefilterParams()
+        lib.vkhr_b200_prefilter_defaults(C.byref(p))
+        for k, v in kw.items():
+            if not hasattr(p, k):
+                raise TypeError(f"unknown prefilter parameter {k}")
+            setattr(p, k, v)
+        return p
+
+    def prefilter(self, densities, W, H, D, ao=True, opacity=False, gauss=False, **params) -> dict:
+        """Density -> AO / opacity / Gaussian float volumes (the shaders' local_ambient_occlusion,
+        volume_approximated_deep_shadows step and filter_volume at every voxel centre), host arrays."""
+        d = _np(densities, np.uint8).reshape(-1)
+        if d.size != W * H * D:
+            raise ValueError("densities does not match W*H*D")
+        p = self.prefilter_params(**params)
+        out = {k: np.empty(d.size, dtype=np.float32) for k, on in (("ao", ao), ("opacity", opacity), ("gauss", gauss)) if on}
+        capi.check(self._h, lib.vkhr_b200_prefilter(self._h, _p(d), int(W), int(H), int(D), C.byref(p),
+                                                    _p(out.get("ao")), _p(out.get("opacity")), _p(out.get("gauss"))))
         return out
 
     def generate_bounding_box(self, vertices) -> tuple[np.ndarray, np.ndarray]:
@@ -323,6 +346,22 @@ class Voxelizer:
         capi.check(self._h, lib.vkhr_b200_downsample_dev(self._h, C.c_void_p(densities.data_ptr()), int(W), int(H), int(D),
                                                          int(filter), C.c_void_p(out.data_ptr()), self._torch_stream(stream)))
         return out
+
+    def prefilter_dev(self, densities, W, H, D, ao=None, opacity=None, gauss=None, stream=None, **params):
+        """Device-resident prefilter: ``ao`` / ``opacity`` / ``gauss`` are cuda float32 tensors of W*H*D (or None)."""
+        import torch
+        self._check_dev(densities, torch.uint8, "densities")
+        if densities.numel() != int(W) * int(H) * int(D):
+            raise ValueError("densities does not match W*H*D")
+        for name, t in (("ao", ao), ("opacity", opacity), ("gauss", gauss)):
+            if t is not None:
+                self._check_dev(t, torch.float32, name)
+                if t.numel() != densities.numel():
+                    raise ValueError(f"{name} does not match W*H*D")
+        p = self.prefilter_params(**params)
+        ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())   # noqa: E731
+        capi.check(self._h, lib.vkhr_b200_prefilter_dev(self._h, C.c_void_p(densities.data_ptr()), int(W), int(H), int(D),
+                                                        C.byref(p), ptr(ao), ptr(opacity), ptr(gauss), self._torch_stream(stream)))
 
     def generate_bounding_box_dev(self, vertices, out=None, stream=None):
         import torch
