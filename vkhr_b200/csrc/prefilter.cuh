@@ -8,7 +8,7 @@
 //   sample_volume / sampler            sample_volume.glsl:7-9; R8_UNORM, LINEAR, CLAMP_TO_BORDER (black):
 //                                      src/vkhr/rasterizer/hair_style.cc:79-85,:94-101
 // The arithmetic contract (texel decode, tap geometry, nested x-y-z weighted sums, accumulation order) is the
-// one written out in oracle/prefilter_oracle.c; every fp32 operation below is a separately rounded
+// one written out in prefilter_oracle.c of the test infrastructure; every fp32 operation below is a separately rounded
 // __f*_rn intrinsic in that order, so everything up to the final powf is bit-identical to the oracle.
 #pragma once
 #include <cstdint>

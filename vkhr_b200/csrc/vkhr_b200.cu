@@ -971,7 +971,7 @@ void vkhr_b200_prefilter_defaults(vkhr_b200_prefilter_params* p) {
 }
 
 namespace {
-// texels and weights of a LINEAR sample displaced by +-r voxels from a voxel centre (oracle/prefilter_oracle.c)
+// texels and weights of a LINEAR sample displaced by +-r voxels from a voxel centre (prefilter_oracle.c of the test infrastructure)
 AxisTaps axis_taps(float r, bool positive) {
     AxisTaps a;
     const float fl = std::floor(r), fp = r - fl;
