@@ -147,7 +147,8 @@ def other_configs(vox, dev, args):
     cases = [("configs[0] ponytail 256^3, one instance", "ponytail", 0.5, 256, 8),
              ("configs[1] Yuksel-straight-shaped 50,000 x 65 at 512^3", "straight", 0.5, 512, 2),
              ("configs[2] 1M strands x 32 segments at 512^3 (one GPU)", "big", 0.5, 512, 1),
-             ("configs[4] animated ponytail frame at 1024^3 (voxelise only)", "ponytail", 0.5, 1024, 1)]
+             ("configs[4] animated ponytail frame at 1024^3 (voxelise only)", "ponytail", 0.5, 1024, 1),
+             ("configs[4] animated ponytail frame at 1024^3 (voxelise + AO/opacity prefilter)", "ponytail", 0.5, 1024, 1)]
     for name, shape, seg_len, W, copies in cases:
         try:
             v, n, s = synth.shape(shape, seed=0x5EED, seg_len=seg_len)
@@ -155,21 +156,28 @@ def other_configs(vox, dev, args):
             size = (hi - lo).astype(np.float32)
             vt = [torch.from_numpy(v).to(dev).reshape(-1).clone() for _ in range(copies)]
             o = [torch.empty(W ** 3, dtype=torch.uint8, device=dev) for _ in range(copies)]
-            reps = 20
-            for r in range(3):
+            prefilter = "prefilter" in name
+            reps = 5 if prefilter else 20
+            pf = [torch.empty(W ** 3, dtype=torch.float32, device=dev) for _ in range(2)] if prefilter else None
+
+            def once(r):
                 vox.voxelize_segments_dev(vt[r % copies], None, lo, size, W, W, W, segs_per_strand=s, out=o[r % copies])
+                if prefilter:
+                    vox.prefilter_dev(o[r % copies], W, W, W, ao=pf[0], opacity=pf[1])
+            for r in range(3):
+                once(r)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for r in range(reps):
-                vox.voxelize_segments_dev(vt[r % copies], None, lo, size, W, W, W, segs_per_strand=s, out=o[r % copies])
+                once(r)
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / reps
-            alg = 12 * v.shape[0] + W ** 3
+            alg = 12 * v.shape[0] + W ** 3 + (W ** 3 * (1 + 4 * 2) if prefilter else 0)      # prefilter N^3 (1 + 4k)
             out[name] = {"segments": n * s, "ms": ms, "value": n * s / ms / 1e3, "unit": UNIT,
                          "hbm_frac_whole_path": alg / (ms * 1e-3) / 1e9 / hbm_peak()[0]}
-            del vt, o
+            del vt, o, pf
             torch.cuda.empty_cache()
         except Exception as e:  # noqa: BLE001
             out[name] = {"error": str(e)[:200]}

@@ -273,6 +273,29 @@ VKHR_B200_API int vkhr_b200_prefilter(
     const vkhr_b200_prefilter_params* params,
     float* ao_out, float* opacity_out, float* gauss_out);
 
+/* ---- volumetric ADSM transmittance volume ---------------------------------- *
+ * volume_approximated_deep_shadows(density, centre, light, steps, strand_alpha,
+ * origin, size, thickness) of share/shaders/self-shadowing/approximate_deep_shadows.glsl:24-36
+ * (call site volumes/volume.frag:72-78: steps = raycast_steps = 1024, thickness 11.0)
+ * evaluated at every voxel centre: out[x + y*W + z*W*H] = visibility of the light from
+ * that voxel, pow(1 - strand_alpha, sum over the shader's own samples of density * thickness).
+ * The density is sampled as the reference samples it (R8_UNORM, LINEAR, CLAMP_TO_BORDER /
+ * opaque black).  Within 1e-6 relative of the CPU restatement (oracle/prefilter_oracle.c). */
+typedef struct vkhr_b200_adsm_params {
+    float light[3];        /* lights[0].origin, world space */
+    float steps;           /* raycast_steps                    (1024) */
+    float strand_alpha;    /* hair_alpha                       (0.3)  */
+    float thickness;       /* volume.frag:78                   (11)   */
+} vkhr_b200_adsm_params;
+VKHR_B200_API int vkhr_b200_adsm_dev(
+    vkhr_b200_ctx* ctx, const uint8_t* d_densities, uint32_t W, uint32_t H, uint32_t D,
+    const float aabb_origin[3], const float aabb_size[3], const vkhr_b200_adsm_params* params,
+    float* d_visibility_out, void* stream);
+VKHR_B200_API int vkhr_b200_adsm(
+    vkhr_b200_ctx* ctx, const uint8_t* densities, uint32_t W, uint32_t H, uint32_t D,
+    const float aabb_origin[3], const float aabb_size[3], const vkhr_b200_adsm_params* params,
+    float* visibility_out);
+
 /* ---- device memory helpers (so a C/C++ caller needs no CUDA headers) ----- */
 VKHR_B200_API int vkhr_b200_malloc(vkhr_b200_ctx* ctx, size_t bytes, void** d_ptr);
 VKHR_B200_API int vkhr_b200_free(vkhr_b200_ctx* ctx, void* d_ptr);

@@ -182,6 +182,20 @@ class _Port:
                                         _ptr(out, _f32p))
         return out
 
+    def adsm_t_table(self, steps=1024.0):
+        n = int(self.lib.oracle_adsm_t_table(C.c_float(steps), None, C.c_uint32(0)))
+        t = np.empty(n, dtype=np.float32)
+        self.lib.oracle_adsm_t_table(C.c_float(steps), _ptr(t, _f32p), C.c_uint32(n))
+        return t
+
+    def prefilter_adsm(self, densities, W, H, D, origin, size, light, steps=1024.0, strand_alpha=0.3, thickness=11.0):
+        d = np.ascontiguousarray(densities, dtype=np.uint8).reshape(-1)
+        out = np.empty(W * H * D, dtype=np.float32)
+        o, s, l = (np.ascontiguousarray(a, dtype=np.float32) for a in (origin, size, light))
+        self.lib.oracle_prefilter_adsm(_ptr(d, _u8p), C.c_uint32(W), C.c_uint32(H), C.c_uint32(D), _ptr(o, _f32p), _ptr(s, _f32p),
+                                       _ptr(l, _f32p), C.c_float(steps), C.c_float(strand_alpha), C.c_float(thickness), _ptr(out, _f32p))
+        return out
+
     def fnv1a64(self, buf):
         b = np.ascontiguousarray(buf).view(np.uint8).reshape(-1)
         return int(self.lib.oracle_fnv1a64(_ptr(b, _u8p), C.c_uint64(b.size)))

@@ -134,3 +134,77 @@ void oracle_prefilter_gauss(const uint8_t* dens, uint32_t W, uint32_t H, uint32_
                 out[(size_t)i + (size_t)j * W + (size_t)k * W * H] = density / total_weight;
             }
 }
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Volumetric ADSM transmittance volume: volume_approximated_deep_shadows(volume, centre(i,j,k), light, steps,
+ * strand_alpha, origin, size, thickness) (approximate_deep_shadows.glsl:24-36; call site volume.frag:72-78 with
+ * steps = raycast_steps = 1024 (interface.hh:101-105), thickness = 11.0) evaluated at every voxel centre: the
+ * visibility of the light from that voxel through the density volume.
+ *
+ * Arithmetic contract (fp32, every operation rounded separately, GLSL text order):
+ *   voxel_size = size / (W,H,D);  p = origin + ((float)i + 0.5f) * voxel_size        (the voxel centre, world space)
+ *   step_size = 1.0f / steps;  for (t = 0.0f; t < 1.0f; t += step_size)               (t accumulated in fp32)
+ *     point = p * (1.0f - t) + light * t                                               (GLSL mix)
+ *     u = (point - origin) / size                                                      (sample_volume.glsl:8)
+ *     LINEAR / CLAMP_TO_BORDER fetch at unnormalised coordinate c = u * res - 0.5f per axis:
+ *       i0 = floor(c), f = c - i0, texels i0 and i0 + 1 with weights (1.0f - f) and f, nested x, y, z as above
+ *     strands += sample * thickness
+ *   result = powf(1.0f - strand_alpha, strands)
+ * t_table (n_t entries) is the accumulated t sequence; the caller passes the same table to the GPU. */
+static float trilinear_at(const vol_t* v, float cx, float cy, float cz) {
+    const float fx0 = floorf(cx), fy0 = floorf(cy), fz0 = floorf(cz);
+    /* outside [-1, res) on any axis every tap is border: 0 (also keeps the int conversions in range) */
+    if (!(fx0 >= -1.0f && fx0 < (float)v->W && fy0 >= -1.0f && fy0 < (float)v->H && fz0 >= -1.0f && fz0 < (float)v->D)) return 0.0f;
+    const int x0 = (int)fx0, y0 = (int)fy0, z0 = (int)fz0;
+    const float fx = cx - fx0, fy = cy - fy0, fz = cz - fz0;
+    const float wx0 = 1.0f - fx, wy0 = 1.0f - fy, wz0 = 1.0f - fz;
+    float zz[2];
+    for (int c = 0; c < 2; ++c) {
+        float yy[2];
+        for (int b = 0; b < 2; ++b) {
+            const float t0 = tau(v, x0, y0 + b, z0 + c), t1 = tau(v, x0 + 1, y0 + b, z0 + c);
+            yy[b] = t0 * wx0 + t1 * fx;
+        }
+        zz[c] = yy[0] * wy0 + yy[1] * fy;
+    }
+    return zz[0] * wz0 + zz[1] * fz;
+}
+
+uint32_t oracle_adsm_t_table(float steps, float* table, uint32_t cap) {
+    const float step_size = 1.0f / steps;
+    uint32_t n = 0;
+    for (float t = 0.0f; t < 1.0f; t += step_size) {
+        if (n < cap && table) table[n] = t;
+        ++n;
+        if (n > (1u << 20)) break;                   /* steps so large that t stops advancing: not a usable setting */
+    }
+    return n;
+}
+
+void oracle_prefilter_adsm(const uint8_t* dens, uint32_t W, uint32_t H, uint32_t D,
+                           const float origin[3], const float size[3], const float light[3],
+                           float steps, float strand_alpha, float thickness, float* out) {
+    const vol_t v = {dens, (int)W, (int)H, (int)D};
+    const float res[3] = {(float)W, (float)H, (float)D};
+    float vs[3];
+    for (int c = 0; c < 3; ++c) vs[c] = size[c] / res[c];
+    const float step_size = 1.0f / steps;
+    const float base = 1.0f - strand_alpha;
+    for (int k = 0; k < v.D; ++k)
+        for (int j = 0; j < v.H; ++j)
+            for (int i = 0; i < v.W; ++i) {
+                const float p[3] = {origin[0] + ((float)i + 0.5f) * vs[0], origin[1] + ((float)j + 0.5f) * vs[1],
+                                    origin[2] + ((float)k + 0.5f) * vs[2]};
+                float strands = 0.0f;
+                for (float t = 0.0f; t < 1.0f; t += step_size) {
+                    float c[3];
+                    for (int a = 0; a < 3; ++a) {
+                        const float point = p[a] * (1.0f - t) + light[a] * t;
+                        const float u = (point - origin[a]) / size[a];
+                        c[a] = u * res[a] - 0.5f;
+                    }
+                    strands += trilinear_at(&v, c[0], c[1], c[2]) * thickness;
+                }
+                out[(size_t)i + (size_t)j * W + (size_t)k * W * H] = powf(base, strands);
+            }
+}

@@ -114,3 +114,55 @@ def test_prefilter_full_size_device_path(vox, port):
     # a voxel whose whole footprint is empty is exactly 1
     occ = torch.nn.functional.max_pool3d((dens.reshape(1, 1, D, H, W) > 0).float(), 7, 1, 3).reshape(-1) > 0
     assert torch.all(ao[~occ] == 1.0)
+
+
+# ---- volumetric ADSM transmittance volume (approximate_deep_shadows.glsl:24-36 at every voxel centre) ----------------
+@pytest.mark.parametrize("res", [(32, 32, 32), (48, 20, 12), (7, 5, 3), (4, 4, 4)])
+@pytest.mark.parametrize("light", [(30.0, 80.0, 20.0), (-15.0, 3.0, 2.0), (2.0, 2.5, 1.0), (1e4, -2e4, 5e3)])
+def test_adsm_against_oracle(vox, port, res, light):
+    """Light far outside, close by, INSIDE the volume, and very far: the march is clipped differently each time."""
+    W, H, D = res
+    rng = np.random.default_rng(W * 7 + H)
+    origin, size = np.array([-1.0, 0.5, -2.0], np.float32), np.array([6.0, 5.0, 4.0], np.float32)
+    for d in (_noise(rng, W * H * D, 0.1), _noise(rng, W * H * D, 0.6) // 8):
+        want = port.prefilter_adsm(d, W, H, D, origin, size, light)
+        got = vox.adsm(d, W, H, D, origin, size, light)
+        _close(got, want, f"adsm {res} light={light}")
+
+
+@pytest.mark.parametrize("steps,alpha,thickness", [(1024.0, 0.3, 11.0), (100.0, 0.3, 11.0), (333.0, 0.05, 2.0), (64.0, 0.9, 0.5), (1.0, 0.3, 11.0)])
+def test_adsm_parameters(vox, port, steps, alpha, thickness):
+    """steps = 100 takes 101 samples (the fp32 accumulation of t in the shader's loop): the t table reproduces it."""
+    W, H, D = 24, 16, 20
+    rng = np.random.default_rng(int(steps))
+    d = _noise(rng, W * H * D, 0.2) // 4
+    origin, size, light = [0.0, 0.0, 0.0], [3.0, 2.0, 2.5], [4.0, 9.0, -3.0]
+    want = port.prefilter_adsm(d, W, H, D, origin, size, light, steps=steps, strand_alpha=alpha, thickness=thickness)
+    got = vox.adsm(d, W, H, D, origin, size, light, steps=steps, strand_alpha=alpha, thickness=thickness)
+    _close(got, want, f"adsm steps={steps}")
+
+
+def test_adsm_of_a_voxelised_style_and_properties(vox, port):
+    """On real (synthetic-hair) densities: parity, an empty volume is fully lit, and more hair never lets more light through."""
+    W = H = D = 40
+    v, n, s = synth.shape("ponytail", seed=5, seg_len=1.0, scale=0.03)
+    lo, hi = port.generate_bounding_box(v)
+    size = (hi - lo).astype(np.float32)
+    d = vox.voxelize_segments(v, None, lo, size, W, H, D, segs_per_strand=s)
+    light = (lo + size * np.array([0.5, 3.0, 0.5], np.float32))
+    got = vox.adsm(d, W, H, D, lo, size, light)
+    _close(got, port.prefilter_adsm(d, W, H, D, lo, size, light), "adsm hair")
+    assert np.all(vox.adsm(np.zeros_like(d), W, H, D, lo, size, light) == 1.0)
+    denser = vox.adsm(np.minimum(d.astype(np.int32) * 2, 255).astype(np.uint8), W, H, D, lo, size, light)
+    assert np.all(denser <= got)
+
+
+def test_adsm_device_resident_matches_host_api(vox):
+    import torch
+    W, H, D = 32, 16, 8
+    rng = np.random.default_rng(9)
+    d = _noise(rng, W * H * D, 0.3)
+    host = vox.adsm(d, W, H, D, [0, 0, 0], [4, 2, 1], [5, 6, 7])
+    dev = vox.adsm_dev(torch.from_numpy(d).cuda(), W, H, D, [0, 0, 0], [4, 2, 1], [5, 6, 7])
+    torch.cuda.synchronize()
+    assert np.array_equal(dev.cpu().numpy(), host)

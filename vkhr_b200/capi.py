@@ -76,6 +76,11 @@ class PrefilterParams(C.Structure):
 PREFILTER_GENERIC = 1 << 0
 
 
+class AdsmParams(C.Structure):
+    """``vkhr_b200_adsm_params``."""
+    _fields_ = [("light", C.c_float * 3), ("steps", C.c_float), ("strand_alpha", C.c_float), ("thickness", C.c_float)]
+
+
 class VkhrB200Error(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"vkhr_b200 error {code}: {message}")
@@ -131,6 +136,8 @@ _PROTOTYPES = {
     "vkhr_b200_prefilter_defaults": (None, [C.POINTER(PrefilterParams)]),
     "vkhr_b200_prefilter_dev": (_int, [c_ctx, _P, _u32, _u32, _u32, C.POINTER(PrefilterParams), _P, _P, _P, _P]),
     "vkhr_b200_prefilter": (_int, [c_ctx, _P, _u32, _u32, _u32, C.POINTER(PrefilterParams), _P, _P, _P]),
+    "vkhr_b200_adsm_dev": (_int, [c_ctx, _P, _u32, _u32, _u32, _vec3, _vec3, C.POINTER(AdsmParams), _P, _P]),
+    "vkhr_b200_adsm": (_int, [c_ctx, _P, _u32, _u32, _u32, _vec3, _vec3, C.POINTER(AdsmParams), _P]),
     "vkhr_b200_malloc": (_int, [c_ctx, _sz, C.POINTER(_P)]),
     "vkhr_b200_free": (_int, [c_ctx, _P]),
     "vkhr_b200_memset": (_int, [c_ctx, _P, _int, _sz, _P]),

@@ -35,6 +35,7 @@ struct InstanceDev {
     uint32_t        kind;           // WalkKind
     uint32_t        vps_magic;      // floor(2^32 / (segs_per_strand + 1)) + 1   (strand-end test without a division)
     uint32_t        pad;
+    unsigned long long* stats;      // PACKED8 red mode: [0] = samples added by the walk, [1] = byte sum of the volume
 };
 
 // A batch travels to the kernels as a __grid_constant__ parameter: every per-instance constant is then
@@ -43,21 +44,38 @@ struct InstanceDev {
 constexpr uint32_t kMaxBatch = 64;
 struct Batch {
     uint32_t n;
-    uint32_t pad[3];
+    uint32_t pad;
+    uint32_t* ticket;               // pipelined walk: CTA start-order counter (global memory, zeroed by the prologue)
     InstanceDev inst[kMaxBatch];
 };
+// Per-instance statistics block of the PACKED8 red mode (InstanceDev::stats), 32 bytes:
+//   [0] samples added by the walk   [1] byte sum of the finished volume
+//   [2] low word: CTAs that have finished clearing their slice of this volume (pipelined walk)
+constexpr uint32_t kStatsWords64 = 4;
 static_assert(sizeof(Batch) <= 16 * 1024, "kernel parameter space");
 
 // ---------------------------------------------------------------------------
 // Sinks: what one sample does to the grid.
 // ---------------------------------------------------------------------------
 
+// Global-space atomics spelled out: after a pointer has been pinned into registers (asm volatile) the compiler
+// no longer knows its address space and would emit the slower generic ATOM.
+__device__ __forceinline__ void red_add_u32(uint32_t* p, uint32_t v) {
+    asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t atom_add_u32(uint32_t* p, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+
 // COUNT32: plain u32 hit counter, clamped later.  `red.global.add.u32` (no return).
 struct SinkCount32 {
     uint32_t* counts;
     template <int SLOT = 0>
-    __device__ __forceinline__ void put(uint32_t idx) { atomicAdd(counts + idx, 1u); }
+    __device__ __forceinline__ void put(uint32_t idx) { red_add_u32(counts + idx, 1u); }
     __device__ __forceinline__ void finish() {}
+    __device__ __forceinline__ void words_pin() { asm volatile("" : "+l"(counts)); }
 };
 
 // PACKED8: the u8 output grid itself is the counter; four voxels share one
@@ -93,10 +111,35 @@ struct SinkPacked8 {
     template <int SLOT>
     __device__ __forceinline__ void put(uint32_t idx) {
         check<SLOT>();
-        pend_old[SLOT] = atomicAdd(words + (idx >> 2), 1u << ((idx & 3u) * 8u));
+        pend_old[SLOT] = atom_add_u32(words + (idx >> 2), 1u << ((idx & 3u) * 8u));
         pend_idx[SLOT] = idx;
     }
     __device__ __forceinline__ void finish() { check<0>(); check<1>(); check<2>(); check<3>(); }
+    __device__ __forceinline__ void words_pin() { asm volatile("" : "+l"(words)); }
+};
+
+// PACKED8, fire-and-forget: `red.global.add.u32` of 1 << (8 * byte) with no return value -- one L1TEX
+// wavefront per sample instead of ~1.6 for the returning `atom` (ncu: l1tex__data_pipe_lsu_wavefronts), no
+// scoreboard wait, no pending-result registers.  A byte that receives more than 255 hits carries into its
+// neighbour, and nobody sees it happen; instead every lane counts the samples it adds, the warp adds its total
+// to stats[0], and k_finish_packed compares it with the byte sum of the finished volume: a carry out of a
+// byte lowers the byte sum by 255 (or 256 out of the word's top byte) and nothing ever raises it, so
+//     byte sum == samples  <=>  no byte ever carried  <=>  every voxel holds its exact count (<= 255).
+// A mismatch (never for hair at a useful resolution) re-voxelises that instance with u32 counters.
+struct SinkPacked8Red {
+    uint32_t* words;
+    unsigned long long* stats;
+    uint32_t n = 0;
+    template <int SLOT = 0>
+    __device__ __forceinline__ void put(uint32_t idx) {
+        red_add_u32(words + (idx >> 2), 1u << ((idx & 3u) * 8u));       // RED.E.ADD: no return value
+        ++n;
+    }
+    __device__ __forceinline__ void finish() {                         // all 32 lanes together
+        const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, n);
+        if ((threadIdx.x & 31u) == 0u && total) atomicAdd(stats, (unsigned long long)total);
+    }
+    __device__ __forceinline__ void words_pin() { asm volatile("" : "+l"(words)); }
 };
 
 // Recount pass of PACKED8: only samples landing in flagged words are counted,
@@ -117,6 +160,29 @@ template <> struct SinkOf<0> { using type = SinkCount32;
     __device__ static type make(const InstanceDev& I) { return SinkCount32{I.counts}; } };
 template <> struct SinkOf<1> { using type = SinkPacked8;
     __device__ static type make(const InstanceDev& I) { SinkPacked8 k; k.words = reinterpret_cast<uint32_t*>(I.densities); k.ovf_bitmap = I.ovf_bitmap; k.ovf_flag = I.ovf_flag; return k; } };
+
+// Measurement-only sinks (VKHR_B200_WALK=null|sector|line|lines8): same instruction stream, different L1TEX wavefront counts.
+template <int KIND> struct SinkProbe {
+    uint32_t* words; unsigned long long* stats; uint32_t n = 0;
+    template <int SLOT = 0>
+    __device__ __forceinline__ void put(uint32_t idx) {
+        const uint32_t inc = 1u << ((idx & 3u) * 8u);
+        if (KIND == 0) n ^= idx + inc;                                                   // no memory operation at all
+        else if (KIND == 1) red_add_u32(words + (idx & 7u), inc);                        // all lanes in ONE 32-byte sector
+        else if (KIND == 2) red_add_u32(words + (idx & 7u) + 8u * (threadIdx.x & 3u), inc);        // one 128-byte line, 4 sectors
+        else red_add_u32(words + (idx & 7u) + 8u * (threadIdx.x & 3u) + 32u * ((idx >> 3) & 0xFFFFu) , inc);   // lanes spread over lines, 4-lane groups keep distinct sectors
+        if (KIND != 0) ++n;
+    }
+    __device__ __forceinline__ void finish() { if (n == 0xDEADBEEFu) *stats = n; }
+    __device__ __forceinline__ void words_pin() { asm volatile("" : "+l"(words)); }
+};
+template <> struct SinkOf<10> { using type = SinkProbe<0>; __device__ static type make(const InstanceDev& I) { type k; k.words = reinterpret_cast<uint32_t*>(I.densities); k.stats = I.stats; return k; } };
+template <> struct SinkOf<11> { using type = SinkProbe<1>; __device__ static type make(const InstanceDev& I) { type k; k.words = reinterpret_cast<uint32_t*>(I.densities); k.stats = I.stats; return k; } };
+template <> struct SinkOf<12> { using type = SinkProbe<2>; __device__ static type make(const InstanceDev& I) { type k; k.words = reinterpret_cast<uint32_t*>(I.densities); k.stats = I.stats; return k; } };
+template <> struct SinkOf<13> { using type = SinkProbe<3>; __device__ static type make(const InstanceDev& I) { type k; k.words = reinterpret_cast<uint32_t*>(I.densities); k.stats = I.stats; return k; } };
+
+template <> struct SinkOf<2> { using type = SinkPacked8Red;
+    __device__ static type make(const InstanceDev& I) { SinkPacked8Red k; k.words = reinterpret_cast<uint32_t*>(I.densities); k.stats = I.stats; return k; } };
 
 // ---------------------------------------------------------------------------
 // Walk kernel for uniform strands (no index buffer): the hot kernel.
@@ -173,7 +239,7 @@ __device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %
 
 template <int MODE, int EXACT>
 __global__ void __launch_bounds__(kWalkThreads, VKHR_WALK_MIN_CTAS)
-k_walk_uniform(const __grid_constant__ Batch B, uint32_t first) {
+k_walk_uniform_v5(const __grid_constant__ Batch B, uint32_t first) {
     __shared__ __align__(128) float s_stage[kWarpsPerBlock][kStageFloats];
     const unsigned long long t_start = g_cta_trace ? globaltimer_ns() : 0ull;
     __shared__ __align__(8) unsigned long long s_bar[kWarpsPerBlock];
@@ -259,6 +325,186 @@ k_walk_uniform(const __grid_constant__ Batch B, uint32_t first) {
             g_cta_trace[4ull * slot + 3] = ((unsigned long long)(first + blockIdx.y) << 32) | blockIdx.x;
         }
     }
+}
+
+template <class T> __device__ __forceinline__ T* pin(T* p) { asm volatile("" : "+l"(p)); return p; }
+
+// The walk of CTA `bx` of instance I (uniform strands); shared by k_walk_uniform and k_walk_pipeline.
+template <int MODE, int EXACT>
+__device__ __forceinline__ void walk_uniform_cta(const InstanceDev& I, uint32_t bx, uint32_t inst_id,
+                                                 float (*s_stage)[kStageFloats], unsigned long long* s_bar) {
+    const unsigned long long t_start = g_cta_trace ? globaltimer_ns() : 0ull;
+    if (bx >= I.n_tiles || I.kind != WK_UNIFORM) return;          // n_tiles counts CTAs
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const GridParams g = pin(I.grid);                              // registers, not indexed constant loads
+    const uint32_t n_vertices = pin(I.n_vertices);
+    const uint32_t n_floats = 3u * n_vertices;
+    const uint32_t n_warp_tiles = (n_vertices + kTileStride - 1u) / kTileStride;
+    const float* __restrict__ verts = I.vertices;
+    float* stage = s_stage[warp];
+    auto sink = SinkOf<MODE>::make(I);
+    sink.words_pin();
+
+    const uint32_t range = bx * kWarpsPerBlock + warp;     // this warp's range of kTilesPerWarp tiles
+    const uint32_t tile0 = range * kTilesPerWarp;
+    const uint32_t n_tiles = min(kTilesPerWarp, n_warp_tiles - min(tile0, n_warp_tiles));
+    if (n_tiles == 0) return;                                      // whole warps only
+
+    // ---- stage the warp's vertex range (8 tiles + one tip vertex, 3 KB) into shared memory -----------------
+    // 16-byte aligned vertex buffers: ONE bulk copy issued by lane 0, completion on the warp's own mbarrier.
+    // Anything else (a 4-byte aligned view, the last bytes of the buffer): coalesced 32-bit loads.
+    {
+        const uint32_t start = kRangeFloats * range;                // first float of the range
+        const uint32_t need = min(kNeedFloats, n_floats - start);   // floats this warp reads from `stage`
+        uint32_t bulk = 0;                                          // floats that arrive by bulk copy
+        if ((reinterpret_cast<uintptr_t>(verts) & 15u) == 0u)
+            bulk = min(kBulkBytes, ((n_floats - start) * 4u) & ~15u) / 4u;
+        const uint32_t bar = smem_u32(&s_bar[warp]);
+        if (bulk) {
+            if (lane == 0) mbar_init(bar, 1);
+            __syncwarp();
+            if (lane == 0) bulk_load(smem_u32(stage), verts + start, bulk * 4u, bar);
+        }
+        for (uint32_t j = bulk + lane; j < need; j += 32u) stage[j] = __ldg(verts + start + j);
+        // floats past the end of the vertex buffer (last warp of an instance only) are never walked, but their
+        // lanes take part in the warp's range vote: give them a harmless value instead of stale shared memory
+        for (uint32_t j = need + lane; j < kNeedFloats; j += 32u) stage[j] = g.ox;
+        if (bulk) mbar_wait(bar, 0);
+        __syncwarp();
+    }
+
+    // ---- loop-carried lane state, all in registers ---------------------------------------------------------
+    // lane_off: this lane's vertex of tile 0 in `stage` (tile k is 93 floats further).
+    // x: global vertex index of this lane's vertex; r = x mod (segs + 1), advanced by 31 mod (segs + 1) per tile
+    // (one multiply-high division per warp instead of one per tile).
+    uint32_t lane_off = pin(3u * lane);                            // float offset into `stage` (kept an offset: shared address space)
+    const uint32_t vps = pin(I.segs_per_strand + 1u);
+    uint32_t x = kTileStride * tile0 + lane;
+    uint32_t r, r_step;
+    {
+        const uint32_t magic = I.vps_magic;                        // floor(2^32 / vps) + 1: quotient exact or one too large
+        r = x - __umulhi(x, magic) * vps;
+        if ((int32_t)r < 0) r += vps;
+        r_step = kTileStride - __umulhi(kTileStride, magic) * vps;
+        if ((int32_t)r_step < 0) r_step += vps;
+        r = pin(r); r_step = pin(r_step);
+    }
+
+    // ---- software-pipelined tile loop ------------------------------------------------------------------
+    // Shared-memory loads and shuffles share the SM's memory-instruction queue with the reds; behind a burst
+    // of reds each round trip takes as long as the queue is deep.  So nothing in a tile's walk waits for a
+    // round trip issued in the same iteration: the raw floats of tile k+2 and the transformed + shuffled end
+    // points of tile k+1 are requested BEFORE tile k is walked.
+    float r0, r1, r2, px, py, pz, tx, ty, tz;
+    r0 = stage[lane_off]; r1 = stage[lane_off + 1u]; r2 = stage[lane_off + 2u];
+    to_voxel_space_warp(g, r0, r1, r2, px, py, pz);
+    tx = __shfl_down_sync(kFullWarp, px, 1);
+    ty = __shfl_down_sync(kFullWarp, py, 1);
+    tz = __shfl_down_sync(kFullWarp, pz, 1);
+    lane_off += 3u * kTileStride;
+    if (n_tiles > 1u) { r0 = stage[lane_off]; r1 = stage[lane_off + 1u]; r2 = stage[lane_off + 2u]; }
+    for (uint32_t k = n_tiles; k > 0u; --k) {
+        float npx = 0.f, npy = 0.f, npz = 0.f, ntx = 0.f, nty = 0.f, ntz = 0.f;
+        if (k > 1u) {                                              // warp-uniform
+            to_voxel_space_warp(g, r0, r1, r2, npx, npy, npz);
+            ntx = __shfl_down_sync(kFullWarp, npx, 1);
+            nty = __shfl_down_sync(kFullWarp, npy, 1);
+            ntz = __shfl_down_sync(kFullWarp, npz, 1);
+            lane_off += 3u * kTileStride;
+            if (k > 2u) { r0 = stage[lane_off]; r1 = stage[lane_off + 1u]; r2 = stage[lane_off + 2u]; }
+        }
+        // vertex x starts a segment unless it is the last of its strand
+        const bool active = lane < kTileStride && x + 1u < n_vertices && r != vps - 1u;
+        walk_voxel_space_warp<EXACT, false>(g, active, px, py, pz, tx, ty, tz, sink);
+        px = npx; py = npy; pz = npz; tx = ntx; ty = nty; tz = ntz;
+        x += kTileStride;
+        r += r_step;
+        if (r >= vps) r -= vps;
+    }
+    sink.finish();
+    if (g_cta_trace && threadIdx.x == 0) {                         // warp 0's own duration (no CTA barrier here)
+        const unsigned int slot = atomicAdd(&g_cta_trace_count, 1u);
+        if (slot < (1u << 20)) {
+            g_cta_trace[4ull * slot + 0] = smid();
+            g_cta_trace[4ull * slot + 1] = t_start;
+            g_cta_trace[4ull * slot + 2] = globaltimer_ns();
+            g_cta_trace[4ull * slot + 3] = ((unsigned long long)inst_id << 32) | bx;
+        }
+    }
+}
+
+template <int MODE, int EXACT>
+__global__ void __launch_bounds__(kWalkThreads, VKHR_WALK_MIN_CTAS)
+k_walk_uniform(const __grid_constant__ Batch B, uint32_t first) {
+    __shared__ __align__(128) float s_stage[kWarpsPerBlock][kStageFloats];
+    __shared__ __align__(8) unsigned long long s_bar[kWarpsPerBlock];
+    walk_uniform_cta<MODE, EXACT>(B.inst[first + blockIdx.y], blockIdx.x, first + blockIdx.y, s_stage, s_bar);
+}
+
+// ---------------------------------------------------------------------------
+// Pipelined crowd walk (PACKED8 red mode): clear and walk in ONE launch, so that every volume is walked
+// while its freshly written zeros are still in L2.
+//
+// Measured on B200 (profiles/r02_*): fire-and-forget reds run at the L1TEX wavefront rate as long as their
+// target sectors are L2-resident (the walk of 64 instances into ONE shared volume takes 1.1 ms), but a red
+// that misses L2 holds its slot for a DRAM fill, and the same walk into 64 volumes that a separate clear
+// pass has long since pushed out to HBM takes 2.2 ms.  So the clear of instance i+1 is done by the CTAs of
+// instance i, immediately before they walk: its 16 MiB of dirty zeros stay in L2 for the few tens of
+// microseconds until instance i+1's own CTAs arrive.  HBM then sees every vertex once (read) and every texel
+// once (the final write-back) -- the algorithmic traffic, with no clear pass and no read fills.
+//
+// Ordering without a grid barrier: CTAs draw a ticket when they START (not from blockIdx, whose dispatch order
+// is not promised); ticket / gridDim.x is the instance, ticket % gridDim.x the CTA within it.  A CTA of
+// instance i waits until all gridDim.x CTAs of instance i-1 have cleared their slice of volume i -- they hold
+// lower tickets, so they have all started and do their clearing first: the wait cannot deadlock and is short.
+// Volume `first` is cleared by k_pipeline_prologue.
+// ---------------------------------------------------------------------------
+template <int EXACT>
+__global__ void __launch_bounds__(kWalkThreads, VKHR_WALK_MIN_CTAS)
+k_walk_pipeline(const __grid_constant__ Batch B, uint32_t first, uint32_t count) {
+    __shared__ __align__(128) float s_stage[kWarpsPerBlock][kStageFloats];
+    __shared__ __align__(8) unsigned long long s_bar[kWarpsPerBlock];
+    __shared__ uint32_t s_ticket;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(B.ticket, 1u);
+    __syncthreads();
+    const uint32_t ticket = s_ticket;
+    const uint32_t y = ticket / gridDim.x, bx = ticket - y * gridDim.x;
+    const InstanceDev& I = B.inst[first + y];
+    if (y + 1u < count) {                                          // clear slice bx of the NEXT instance's volume
+        const InstanceDev& N = B.inst[first + y + 1u];
+        uint4* d = reinterpret_cast<uint4*>(N.densities);
+        const uint32_t n16 = N.grid.n_voxels >> 4;
+        const uint32_t per = (n16 + gridDim.x - 1u) / gridDim.x;
+        const uint32_t lo = min(n16, bx * per), hi = min(n16, lo + per);
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        for (uint32_t i = lo + threadIdx.x; i < hi; i += kWalkThreads) d[i] = z;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(reinterpret_cast<uint32_t*>(N.stats + 2), 1u);
+    }
+    if (y > 0u) {                                                  // my own volume must be completely cleared
+        if (threadIdx.x == 0) {
+            const volatile uint32_t* done = reinterpret_cast<const volatile uint32_t*>(I.stats + 2);
+            uint32_t spin = 0;
+            while (*done < gridDim.x) { __nanosleep(64); if (++spin > (1u << 26)) __trap(); }
+            __threadfence();
+        }
+        __syncthreads();
+    }
+    walk_uniform_cta<2, EXACT>(I, bx, first + y, s_stage, s_bar);
+}
+
+// Prologue of the pipelined walk: zero the first volume, every instance's statistics block and the ticket.
+__global__ void __launch_bounds__(256) k_pipeline_prologue(const __grid_constant__ Batch B, uint32_t first, uint32_t count) {
+    const InstanceDev& I = B.inst[first];
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    uint4* d = reinterpret_cast<uint4*>(I.densities);
+    const uint32_t n16 = I.grid.n_voxels >> 4;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t i = t; i < n16; i += stride) d[i] = z;
+    if (t < count * kStatsWords64) B.inst[first + t / kStatsWords64].stats[t % kStatsWords64] = 0ull;
+    if (t == 0) *B.ticket = 0u;
 }
 
 // ---------------------------------------------------------------------------
@@ -451,9 +697,39 @@ __global__ void __launch_bounds__(256) k_clear_packed_batch(const __grid_constan
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     for (uint32_t i = t; i < n16; i += stride) d[i] = z;
-    const uint32_t n_bm = (I.grid.n_voxels / 4 + 31) / 32;          // bitmap words
-    for (uint32_t i = t; i < n_bm; i += stride) I.ovf_bitmap[i] = 0u;
-    if (t == 0) *I.ovf_flag = 0u;
+    if (I.ovf_bitmap) {                                             // atom mode only
+        const uint32_t n_bm = (I.grid.n_voxels / 4 + 31) / 32;      // bitmap words
+        for (uint32_t i = t; i < n_bm; i += stride) I.ovf_bitmap[i] = 0u;
+        if (t == 0) *I.ovf_flag = 0u;
+    }
+    if (I.stats && t == 0) { I.stats[0] = 0ull; I.stats[1] = 0ull; I.stats[2] = 0ull; I.stats[3] = 0ull; }
+}
+
+// PACKED8 red mode: byte sum of every instance's finished volume -> stats[1] (compared with stats[0], the number of
+// samples the walk added, by k_finish_packed).  blockIdx.y + first = instance; four 16-byte loads in flight per thread.
+__device__ __forceinline__ uint32_t bytesum16(uint4 a, uint32_t acc) {
+    acc = __dp4a(a.x, 0x01010101u, acc); acc = __dp4a(a.y, 0x01010101u, acc);
+    acc = __dp4a(a.z, 0x01010101u, acc); return __dp4a(a.w, 0x01010101u, acc);
+}
+__global__ void __launch_bounds__(256) k_verify_packed_batch(const __grid_constant__ Batch B, uint32_t first) {
+    const InstanceDev& I = B.inst[first + blockIdx.y];
+    const uint4* d = reinterpret_cast<const uint4*>(I.densities);
+    const uint32_t n16 = I.grid.n_voxels >> 4;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t acc = 0;
+    for (; i + 3u * stride < n16; i += 4u * stride) {
+        const uint4 a = __ldcs(d + i), b = __ldcs(d + i + stride), c = __ldcs(d + i + 2u * stride), e = __ldcs(d + i + 3u * stride);
+        acc = bytesum16(a, acc); acc = bytesum16(b, acc); acc = bytesum16(c, acc); acc = bytesum16(e, acc);
+    }
+    for (; i < n16; i += stride) acc = bytesum16(__ldcs(d + i), acc);
+    __shared__ uint32_t s_acc;
+    if (threadIdx.x == 0) s_acc = 0;
+    __syncthreads();
+    acc = __reduce_add_sync(0xFFFFFFFFu, acc);
+    if ((threadIdx.x & 31u) == 0u && acc) atomicAdd(&s_acc, acc);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_acc) atomicAdd(I.stats + 1, (unsigned long long)s_acc);
 }
 
 // densities = min(counts, 255)  (hair_style.cc:322: `if (d != 255) d += 1`),

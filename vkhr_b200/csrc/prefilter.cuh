@@ -291,4 +291,110 @@ k_prefilter_tiled(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Volumetric ADSM transmittance volume: volume_approximated_deep_shadows (share/shaders/self-shadowing/
+// approximate_deep_shadows.glsl:24-36, call site volumes/volume.frag:72-78) evaluated at every voxel centre --
+// the visibility of the light from that voxel through the strand density volume.  One thread per voxel marches
+// the shader's own sample sequence t = 0, step, 2 step, ... (t accumulated in fp32: the table is that sequence)
+// from the centre to the light; every fp32 operation is a separately rounded intrinsic in the order of the GLSL
+// text (the arithmetic contract is written out in prefilter_oracle.c of the test infrastructure), so the strand
+// sum is bit-identical and only the final powf may differ in the last place.
+// Samples whose footprint lies outside the grid fetch the border colour (0) and add +0.0f, which leaves the sum
+// unchanged: the march is clipped to the parameter range in which the ray can touch [-1, res) (plus a margin of
+// two steps for the rounding of the clip itself), and every sample inside that range is still bounds-checked.
+// ---------------------------------------------------------------------------------------------------------
+struct AdsmArgs {
+    const uint8_t* dens;
+    int W, H, D;
+    float ox, oy, oz, sx, sy, sz, lx, ly, lz;
+    float vsx, vsy, vsz;                 // size / resolution
+    const float* t_table;                // the accumulated t sequence (t < 1)
+    uint32_t n_t;
+    float step_size, thickness, base;    // 1 / steps, thickness, 1 - strand_alpha
+    float* out;
+};
+
+constexpr int kAdsmThreads = 256;
+
+__global__ void __launch_bounds__(kAdsmThreads)
+k_adsm(const __grid_constant__ AdsmArgs A) {
+    __shared__ float s_tau[256];                                     // R8_UNORM decode: (float)v / 255.0f
+    for (int v = threadIdx.x; v < 256; v += blockDim.x) s_tau[v] = __fdiv_rn((float)v, 255.0f);
+    __syncthreads();
+    const uint64_t n = (uint64_t)A.W * A.H * A.D;
+    const uint64_t lin = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lin >= n) return;
+    const int i = (int)(lin % (uint64_t)A.W), j = (int)((lin / (uint64_t)A.W) % (uint64_t)A.H), k = (int)(lin / ((uint64_t)A.W * A.H));
+    const float resx = (float)A.W, resy = (float)A.H, resz = (float)A.D;
+    const float px = __fadd_rn(A.ox, __fmul_rn(__fadd_rn((float)i, 0.5f), A.vsx));
+    const float py = __fadd_rn(A.oy, __fmul_rn(__fadd_rn((float)j, 0.5f), A.vsy));
+    const float pz = __fadd_rn(A.oz, __fmul_rn(__fadd_rn((float)k, 0.5f), A.vsz));
+
+    // ---- clip: parameter range in which the texel coordinate can lie in [-1, res) on every axis ----------------
+    float t_lo = 0.0f, t_hi = 1.0f;
+    {
+        const float c0[3] = {(float)i, (float)j, (float)k};
+        const float cl[3] = {(A.lx - A.ox) / A.sx * resx - 0.5f, (A.ly - A.oy) / A.sy * resy - 0.5f, (A.lz - A.oz) / A.sz * resz - 0.5f};
+        const float hi[3] = {resx, resy, resz};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float d = cl[a] - c0[a];
+            if (fabsf(d) > 1e-20f) {
+                const float ta = (-1.0f - c0[a]) / d, tb = (hi[a] - c0[a]) / d;
+                t_lo = fmaxf(t_lo, fminf(ta, tb));
+                t_hi = fminf(t_hi, fmaxf(ta, tb));
+            }                                                        // d == 0: the centre itself is inside on this axis
+        }
+    }
+    const float margin = 2.0f * A.step_size + 1e-5f;
+    t_lo -= margin; t_hi += margin;
+    // first k with t_k >= t_lo, first k with t_k > t_hi (the table is increasing)
+    uint32_t k_lo = 0, k_hi = A.n_t;
+    {
+        uint32_t lo = 0, hi = A.n_t;
+        while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (__ldg(A.t_table + m) < t_lo) lo = m + 1; else hi = m; }
+        k_lo = lo;
+        hi = A.n_t;
+        while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (__ldg(A.t_table + m) <= t_hi) lo = m + 1; else hi = m; }
+        k_hi = lo;
+    }
+
+    const size_t sy = (size_t)A.W, sz = (size_t)A.W * A.H;
+    float strands = 0.0f;
+    for (uint32_t q = k_lo; q < k_hi; ++q) {
+        const float t = __ldg(A.t_table + q);
+        const float omt = __fsub_rn(1.0f, t);
+        // point = mix(p, light, t); u = (point - origin) / size; c = u * res - 0.5
+        const float cx = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(__fadd_rn(__fmul_rn(px, omt), __fmul_rn(A.lx, t)), A.ox), A.sx), resx), 0.5f);
+        const float cy = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(__fadd_rn(__fmul_rn(py, omt), __fmul_rn(A.ly, t)), A.oy), A.sy), resy), 0.5f);
+        const float cz = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(__fadd_rn(__fmul_rn(pz, omt), __fmul_rn(A.lz, t)), A.oz), A.sz), resz), 0.5f);
+        const float fx0 = floorf(cx), fy0 = floorf(cy), fz0 = floorf(cz);
+        if (!(fx0 >= -1.0f && fx0 < resx && fy0 >= -1.0f && fy0 < resy && fz0 >= -1.0f && fz0 < resz)) continue;   // all border: +0
+        const int x0 = (int)fx0, y0 = (int)fy0, z0 = (int)fz0;
+        const float fx = __fsub_rn(cx, fx0), fy = __fsub_rn(cy, fy0), fz = __fsub_rn(cz, fz0);
+        const float wx0 = __fsub_rn(1.0f, fx), wy0 = __fsub_rn(1.0f, fy), wz0 = __fsub_rn(1.0f, fz);
+        const bool xin0 = x0 >= 0, xin1 = x0 + 1 < A.W;
+        float zz[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            float yy[2];
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const int y = y0 + b, z = z0 + c;
+                float t0 = 0.0f, t1 = 0.0f;
+                if (y >= 0 && y < A.H && z >= 0 && z < A.D) {
+                    const uint8_t* row = A.dens + (size_t)y * sy + (size_t)z * sz;
+                    if (xin0) t0 = s_tau[__ldg(row + x0)];
+                    if (xin1) t1 = s_tau[__ldg(row + x0 + 1)];
+                }
+                yy[b] = __fadd_rn(__fmul_rn(t0, wx0), __fmul_rn(t1, fx));
+            }
+            zz[c] = __fadd_rn(__fmul_rn(yy[0], wy0), __fmul_rn(yy[1], fy));
+        }
+        const float s = __fadd_rn(__fmul_rn(zz[0], wz0), __fmul_rn(zz[1], fz));
+        strands = __fadd_rn(strands, __fmul_rn(s, A.thickness));
+    }
+    A.out[lin] = powf(A.base, strands);
+}
+
 }  // namespace vkhr_b200

@@ -99,6 +99,65 @@ k_repair_packed(const __grid_constant__ Batch B, uint32_t* __restrict__ scratch)
 }
 
 // ---------------------------------------------------------------------------
+// PACKED8 red mode: the rare recount, one persistent cooperative kernel.  Instances whose byte sum (stats[1],
+// k_verify_packed_batch) differs from the number of samples the walk added (stats[0]) had a byte carry, i.e. a
+// voxel with more than 255 hits: they are re-voxelised with u32 counters on the shared scratch grid and
+// rewritten as min(count, 255)  (hair_style.cc:322: `if (d != 255) d += 1`).  With no mismatch (hair at any
+// useful resolution) every CTA returns after comparing n pairs of counters.
+// ---------------------------------------------------------------------------
+template <bool VERTICES>
+__global__ void __launch_bounds__(kWalkThreads)
+k_finish_packed(const __grid_constant__ Batch B, uint32_t* __restrict__ scratch) {
+    const uint32_t n_inst = B.n;
+    const InstanceDev* inst = B.inst;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nthreads = gridDim.x * blockDim.x;
+    // common case first: every byte sum (k_verify_packed_batch) equals its sample count -> out
+    int any = 0;
+    for (uint32_t k = threadIdx.x; k < n_inst; k += blockDim.x) any |= (__ldcg(inst[k].stats) != __ldcg(inst[k].stats + 1));
+    if (!__syncthreads_or(any)) return;                        // same answer in every CTA
+    cg::grid_group grid = cg::this_grid();
+    for (uint32_t k = 0; k < n_inst; ++k) {
+        const InstanceDev& I = inst[k];
+        if (__ldcg(I.stats) == __ldcg(I.stats + 1)) continue;      // uniform across the grid: the common case
+        const GridParams g = I.grid;
+        const uint32_t n16 = g.n_voxels >> 4;
+        uint4* counts4 = reinterpret_cast<uint4*>(scratch);
+        for (uint32_t i = tid; i < 4u * n16; i += nthreads) counts4[i] = make_uint4(0, 0, 0, 0);
+        grid.sync();
+        SinkCount32 sink{scratch};
+        if (VERTICES) {
+            for (uint32_t i = tid; i < I.n_vertices; i += nthreads) {
+                const float* v = I.vertices + 3ull * i;
+                uint32_t idx;
+                if (voxel_index(g, to_voxel_space(__ldg(v), g.ox, g.vsx, g.rvx), to_voxel_space(__ldg(v + 1), g.oy, g.vsy, g.rvy),
+                                to_voxel_space(__ldg(v + 2), g.oz, g.vsz, g.rvz), idx))
+                    sink.put<0>(idx);
+            }
+        } else if (I.indices) {
+            for (uint64_t s = tid; s < I.n_segments; s += nthreads) {
+                const uint2 pr = __ldg(reinterpret_cast<const uint2*>(I.indices) + s);
+                const float* a = I.vertices + 3ull * pr.x;
+                const float* b = I.vertices + 3ull * pr.y;
+                walk_segment(g, __ldg(a), __ldg(a + 1), __ldg(a + 2), __ldg(b), __ldg(b + 1), __ldg(b + 2), sink);
+            }
+        } else {
+            const uint32_t vps = I.segs_per_strand + 1u;
+            for (uint32_t v = tid; v + 1u < I.n_vertices; v += nthreads) {
+                if (v % vps == vps - 1u) continue;             // last vertex of a strand starts no segment
+                const float* a = I.vertices + 3ull * v;
+                walk_segment(g, __ldg(a), __ldg(a + 1), __ldg(a + 2), __ldg(a + 3), __ldg(a + 4), __ldg(a + 5), sink);
+            }
+        }
+        grid.sync();
+        uint4* out4 = reinterpret_cast<uint4*>(I.densities);
+        for (uint32_t i = tid; i < n16; i += nthreads)
+            out4[i] = make_uint4(clamp4(counts4[4 * i]), clamp4(counts4[4 * i + 1]), clamp4(counts4[4 * i + 2]), clamp4(counts4[4 * i + 3]));
+        grid.sync();                                           // scratch is reused by the next such instance
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Context
 // ---------------------------------------------------------------------------
 struct DevBuf {
@@ -125,6 +184,15 @@ struct vkhr_b200_ctx {
     Slot slots[kSlots];
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     int repair_blocks[2] = {0, 0};
+    int finish_blocks[2] = {0, 0};
+    bool no_int_index = false;    // A/B only
+    bool no_pipeline = false;     // A/B only
+    uint32_t alias_volumes = 0;   // A/B only: every instance writes into one of the first N volumes (L2-warm probe; wrong results)
+    uint32_t chunk_override = 0;  // A/B only: instances per clear/walk/finish group
+    int walk_variant = 1;         // PACKED8 walk: 1 = atom + overflow bitmap (default), 2 = red + byte-sum verification, 5 = round-1 v5 kernel (A/B only)
+    DevBuf adsm_table;            // the ADSM march's accumulated t sequence for `adsm_steps`
+    float adsm_steps = 0.0f;
+    uint32_t adsm_n = 0;
     uint32_t pf_smem_opted = 0;   // dynamic shared memory the tiled prefilter kernel has been opted into
     Batch batch;          // host copy of the kernel-parameter batch being launched
     // optional per-phase device timing (vkhr_b200_profile_*): CUDA events recorded on the
@@ -238,6 +306,16 @@ int make_grid(vkhr_b200_ctx* ctx, const float origin[3], const float size[3],
     auto recip = [](float vs) { return (vs >= 9.094947e-13f && vs <= 1.0995116e12f) ? 1.0f / vs : 0.0f; };
     g.rvx = recip(g.vsx); g.rvy = recip(g.vsy); g.rvz = recip(g.vsz);
     g.fast_div = (g.rvx != 0.0f && g.rvy != 0.0f && g.rvz != 0.0f) ? 1u : 0u;
+    // Small grids (<= 2^24 voxels): the fp32 index expression is exact for bounded positions, so the hot kernel
+    // may compute it in int32 (walk.cuh, sample_index<2>).  The bound keeps |y*W| < 2^22, |z*W*H| < 2^30 and
+    // leaves room for the rounding drift of the accumulated `root += dir`.
+    g.small_grid = (n <= (1ull << 24) && !g.index_exact) ? 1u : 0u;
+    g.pos_limit = 3.0e38f;
+    if (g.small_grid) {
+        const unsigned long long m = std::max(std::max(W, H), D);
+        const unsigned long long lim = std::min<unsigned long long>(8192ull, std::min((1ull << 21) / m, (1ull << 29) / ((unsigned long long)W * H)));
+        if (lim >= 8) g.pos_limit = (float)lim; else g.small_grid = 0u;
+    }
     return VKHR_B200_OK;
 }
 
@@ -292,7 +370,7 @@ BatchPlan fill_batch(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool verti
         I.n_vertices = jobs[k].n_vertices;
         I.segs_per_strand = jobs[k].segs;
         I.grid = jobs[k].grid;
-        I.densities = jobs[k].d_dens;
+        I.densities = (ctx->alias_volumes && n > 1) ? jobs[k % ctx->alias_volumes].d_dens : jobs[k].d_dens;   // A/B only
         I.kind = kind;
         if (kind == WK_UNIFORM) {
             // warp-tiles of kTileStride vertices, kTilesPerWarp per warp, kWarpsPerBlock warps per CTA
@@ -318,8 +396,23 @@ int launch_walk(vkhr_b200_ctx* ctx, const BatchPlan& plan, bool exact, uint32_t 
     (void)plan;
     if (tiles[WK_UNIFORM]) {
         const dim3 grid(tiles[WK_UNIFORM], count);
-        if (exact) k_walk_uniform<MODE, 1><<<grid, kWalkThreads, 0, s>>>(B, first);
-        else       k_walk_uniform<MODE, 0><<<grid, kWalkThreads, 0, s>>>(B, first);
+        bool small = !exact;                                   // int32 index: every instance on a small grid
+        for (uint32_t k = first; k < first + count; ++k) small = small && B.inst[k].grid.small_grid;
+        if (MODE == 1 && ctx->walk_variant == 5) {             // round-1 kernel, kept for A/B measurements
+            if (exact) k_walk_uniform_v5<1, 1><<<grid, kWalkThreads, 0, s>>>(B, first);
+            else       k_walk_uniform_v5<1, 0><<<grid, kWalkThreads, 0, s>>>(B, first);
+        }
+        else if (MODE == 2 && ctx->walk_variant >= 10) {       // measurement-only sinks (results are NOT a voxelisation)
+            switch (ctx->walk_variant) {
+                case 10: k_walk_uniform<10, 2><<<grid, kWalkThreads, 0, s>>>(B, first); break;
+                case 11: k_walk_uniform<11, 2><<<grid, kWalkThreads, 0, s>>>(B, first); break;
+                case 12: k_walk_uniform<12, 2><<<grid, kWalkThreads, 0, s>>>(B, first); break;
+                default: k_walk_uniform<13, 2><<<grid, kWalkThreads, 0, s>>>(B, first); break;
+            }
+        }
+        else if (exact) k_walk_uniform<MODE, 1><<<grid, kWalkThreads, 0, s>>>(B, first);
+        else if (small && !ctx->no_int_index) k_walk_uniform<MODE, 2><<<grid, kWalkThreads, 0, s>>>(B, first);
+        else            k_walk_uniform<MODE, 0><<<grid, kWalkThreads, 0, s>>>(B, first);
         ctx->launches++;
     }
     if (tiles[WK_INDEXED]) {
@@ -353,6 +446,21 @@ int launch_repair(vkhr_b200_ctx* ctx, uint32_t* scratch, cudaStream_t s) {
     return VKHR_B200_OK;
 }
 
+template <bool VERTICES>
+int launch_finish(vkhr_b200_ctx* ctx, uint32_t* scratch, cudaStream_t s) {
+    int& blocks = ctx->finish_blocks[VERTICES ? 1 : 0];
+    if (blocks == 0) {
+        int per_sm = 0;
+        CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_finish_packed<VERTICES>, kWalkThreads, 0));
+        if (per_sm < 1) return fail(ctx, VKHR_B200_ERR_CUDA, "finish kernel does not fit on an SM");
+        blocks = per_sm * ctx->sm_count;
+    }
+    void* args[] = {(void*)&ctx->batch, (void*)&scratch};
+    CU_CHECK(ctx, cudaLaunchCooperativeKernel((void*)k_finish_packed<VERTICES>, dim3(blocks), dim3(kWalkThreads), args, 0, s));
+    ctx->launches++;
+    return VKHR_B200_OK;
+}
+
 // The voxelisation of `n` instances at one resolution into their u8 grids, kMaxBatch at a time.
 int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_mode, uint32_t flags, cudaStream_t s) {
     if (n == 0) return VKHR_B200_OK;
@@ -365,9 +473,11 @@ int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_
         return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "PACKED8 needs W*H*D % 16 == 0 and 16-byte aligned densities");
 
     if (packed) {
-        // scratch: per-instance overflow bitmap + flag, one shared u32 recount grid
-        const size_t bm_words = ((nv / 4 + 31) / 32 + 3) & ~size_t(3);
-        const uint32_t chunk = std::min<uint32_t>(n, kMaxBatch);
+        // scratch: per instance 16 bytes of stats (red mode) or an overflow bitmap + flag (atom mode), and one
+        // shared u32 recount grid
+        const bool red = ctx->walk_variant == 2 || ctx->walk_variant >= 10;
+        const size_t bm_words = red ? 4 : (((nv / 4 + 31) / 32 + 3) & ~size_t(3));   // red: 32 bytes of stats per instance
+        const uint32_t chunk = std::min<uint32_t>(n, std::min<uint32_t>(kMaxBatch, ctx->chunk_override ? ctx->chunk_override : kMaxBatch));
         RET_IF(reserve(ctx, ctx->bitmap, (size_t)chunk * (bm_words + 4) * 4));
         RET_IF(reserve(ctx, ctx->counts, nv * 4));
         ctx->counts_clean_bytes = 0;                   // the recount may leave entries behind
@@ -376,24 +486,54 @@ int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_
             const uint32_t m = std::min(chunk, n - first);
             const BatchPlan plan = fill_batch(ctx, jobs + first, m, vertices_mode);
             for (uint32_t k = 0; k < m; ++k) {
-                ctx->batch.inst[k].ovf_flag = base + (size_t)k * (bm_words + 4);
-                ctx->batch.inst[k].ovf_bitmap = base + (size_t)k * (bm_words + 4) + 4;
+                uint32_t* blk = base + (size_t)k * (bm_words + 4);          // 16-byte aligned
+                ctx->batch.inst[k].stats = red ? reinterpret_cast<unsigned long long*>(blk) : nullptr;
+                ctx->batch.inst[k].ovf_flag = red ? nullptr : blk;
+                ctx->batch.inst[k].ovf_bitmap = red ? nullptr : blk + 4;
                 ctx->batch.inst[k].counts = static_cast<uint32_t*>(ctx->counts.p);
             }
             const unsigned gx = stride_blocks(ctx, nv / 16, 256, m >= 8 ? 2 : 8);
-            {
-                PhaseMark mk(ctx, s, PH_CLEAR);
-                k_clear_packed_batch<<<dim3(gx, m), 256, 0, s>>>(ctx->batch, 0u);
-                ctx->launches++;
-            }
-            if (plan.max_tiles[0] + plan.max_tiles[1] + plan.max_tiles[2]) {
+            // pipelined crowd walk (kernels.cuh, k_walk_pipeline): uniform strands, red mode, more than one instance
+            const bool pipeline = red && ctx->walk_variant == 2 && !ctx->no_pipeline && m > 1 && plan.max_tiles[WK_UNIFORM] &&
+                                  !plan.max_tiles[WK_INDEXED] && !plan.max_tiles[WK_SPLAT];
+            ctx->batch.ticket = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->small.p) + 128);
+            if (pipeline) {
+                bool small = !exact;
+                for (uint32_t k = 0; k < m; ++k) small = small && ctx->batch.inst[k].grid.small_grid;
+                {
+                    PhaseMark mk(ctx, s, PH_CLEAR);
+                    k_pipeline_prologue<<<stride_blocks(ctx, nv / 16, 256, 8), 256, 0, s>>>(ctx->batch, 0u, m);
+                    ctx->launches++;
+                }
                 {
                     PhaseMark mk(ctx, s, PH_WALK);
-                    RET_IF(launch_walk<1>(ctx, plan, exact, 0, m, s));
+                    const dim3 grid(plan.max_tiles[WK_UNIFORM], m);
+                    if (exact)      k_walk_pipeline<1><<<grid, kWalkThreads, 0, s>>>(ctx->batch, 0u, m);
+                    else if (small) k_walk_pipeline<2><<<grid, kWalkThreads, 0, s>>>(ctx->batch, 0u, m);
+                    else            k_walk_pipeline<0><<<grid, kWalkThreads, 0, s>>>(ctx->batch, 0u, m);
+                    ctx->launches++;
                 }
+            } else {
+                {
+                    PhaseMark mk(ctx, s, PH_CLEAR);
+                    k_clear_packed_batch<<<dim3(gx, m), 256, 0, s>>>(ctx->batch, 0u);
+                    ctx->launches++;
+                }
+                if (plan.max_tiles[0] + plan.max_tiles[1] + plan.max_tiles[2]) {
+                    PhaseMark mk(ctx, s, PH_WALK);
+                    if (red) RET_IF(launch_walk<2>(ctx, plan, exact, 0, m, s));
+                    else     RET_IF(launch_walk<1>(ctx, plan, exact, 0, m, s));
+                }
+            }
+            if (plan.max_tiles[0] + plan.max_tiles[1] + plan.max_tiles[2]) {
                 PhaseMark mk(ctx, s, PH_FINISH);
-                if (vertices_mode) RET_IF(launch_repair<true>(ctx, static_cast<uint32_t*>(ctx->counts.p), s));
-                else               RET_IF(launch_repair<false>(ctx, static_cast<uint32_t*>(ctx->counts.p), s));
+                uint32_t* scratch = static_cast<uint32_t*>(ctx->counts.p);
+                if (red) {
+                    k_verify_packed_batch<<<dim3(gx, m), 256, 0, s>>>(ctx->batch, 0u);
+                    ctx->launches++;
+                    if (vertices_mode) RET_IF(launch_finish<true>(ctx, scratch, s)); else RET_IF(launch_finish<false>(ctx, scratch, s));
+                }
+                else { if (vertices_mode) RET_IF(launch_repair<true>(ctx, scratch, s)); else RET_IF(launch_repair<false>(ctx, scratch, s)); }
             }
             CU_CHECK(ctx, cudaGetLastError());
         }
@@ -546,6 +686,20 @@ int vkhr_b200_create(int device, vkhr_b200_ctx** out) {
         delete ctx;
         return VKHR_B200_ERR_OUT_OF_MEMORY;
     }
+    // measurement switches (A/B runs of tools/*.sh); the default is the shipped configuration
+    if (const char* v = std::getenv("VKHR_B200_WALK")) {
+        if (!std::strcmp(v, "atom")) ctx->walk_variant = 1;
+        else if (!std::strcmp(v, "v5")) ctx->walk_variant = 5;
+        else if (!std::strcmp(v, "red")) ctx->walk_variant = 2;
+        else if (!std::strcmp(v, "null")) ctx->walk_variant = 10;
+        else if (!std::strcmp(v, "sector")) ctx->walk_variant = 11;
+        else if (!std::strcmp(v, "line")) ctx->walk_variant = 12;
+        else if (!std::strcmp(v, "lines8")) ctx->walk_variant = 13;
+    }
+    if (const char* v = std::getenv("VKHR_B200_NO_PIPELINE")) ctx->no_pipeline = (v[0] == '1');
+    if (const char* v = std::getenv("VKHR_B200_ALIAS")) ctx->alias_volumes = (uint32_t)std::atoi(v);
+    if (const char* v = std::getenv("VKHR_B200_CHUNK")) ctx->chunk_override = (uint32_t)std::atoi(v);
+    if (const char* v = std::getenv("VKHR_B200_NO_INT_INDEX")) ctx->no_int_index = (v[0] == '1');
     *out = ctx;
     return VKHR_B200_OK;
 }
@@ -554,7 +708,7 @@ void vkhr_b200_destroy(vkhr_b200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->counts, &ctx->bitmap, &ctx->small, &ctx->tacc, &ctx->st_vertices,
+    DevBuf* bufs[] = {&ctx->counts, &ctx->bitmap, &ctx->small, &ctx->tacc, &ctx->adsm_table, &ctx->st_vertices,
                       &ctx->st_indices, &ctx->st_tangents, &ctx->st_dens, &ctx->st_tang_out};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (auto& sl : ctx->slots) {
@@ -1093,6 +1247,62 @@ int vkhr_b200_prefilter(vkhr_b200_ctx* ctx, const uint8_t* densities, uint32_t W
     RET_IF(vkhr_b200_prefilter_dev(ctx, static_cast<const uint8_t*>(ctx->st_dens.p), W, H, D, params, d_out[0], d_out[1], d_out[2], ctx->stream));
     for (int k = 0; k < 3; ++k)
         if (outs[k]) CU_CHECK(ctx, cudaMemcpyAsync(outs[k], d_out[k], n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return VKHR_B200_OK;
+}
+
+// ---- volumetric ADSM transmittance volume (approximate_deep_shadows.glsl:24-36 at every voxel centre) ----
+int vkhr_b200_adsm_dev(vkhr_b200_ctx* ctx, const uint8_t* d_densities, uint32_t W, uint32_t H, uint32_t D,
+                       const float origin[3], const float size[3], const vkhr_b200_adsm_params* P, float* d_out, void* stream) {
+    RET_IF(bind(ctx));
+    if (!d_densities || !d_out || !origin || !size || !P) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null argument");
+    const unsigned long long n = (unsigned long long)W * H * D;
+    if (n == 0) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "zero resolution");
+    if (W > 32768 || H > 32768 || D > 32768 || n >= (1ull << 40)) return fail(ctx, VKHR_B200_ERR_UNSUPPORTED, "resolution too large");
+    for (int c = 0; c < 3; ++c)
+        if (!std::isfinite(origin[c]) || !std::isfinite(size[c]) || !(size[c] > 0.0f) || !std::isfinite(P->light[c]))
+            return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "AABB and light must be finite, size > 0");
+    if (!(P->steps >= 1.0f) || !(P->steps <= 65536.0f)) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "steps must be in [1, 65536]");
+    cudaStream_t s = pick(ctx, stream);
+    // the shader's t sequence: for (t = 0; t < 1; t += 1 / steps), accumulated in fp32
+    if (ctx->adsm_steps != P->steps) {
+        std::vector<float> table;
+        const float step_size = 1.0f / P->steps;
+        for (float t = 0.0f; t < 1.0f; t += step_size) { table.push_back(t); if (table.size() > (1u << 20)) break; }
+        RET_IF(reserve(ctx, ctx->adsm_table, table.size() * 4));
+        CU_CHECK(ctx, cudaMemcpyAsync(ctx->adsm_table.p, table.data(), table.size() * 4, cudaMemcpyHostToDevice, s));
+        CU_CHECK(ctx, cudaStreamSynchronize(s));               // `table` dies at the end of this scope
+        ctx->adsm_steps = P->steps;
+        ctx->adsm_n = (uint32_t)table.size();
+    }
+    AdsmArgs A;
+    A.dens = d_densities; A.W = (int)W; A.H = (int)H; A.D = (int)D;
+    A.ox = origin[0]; A.oy = origin[1]; A.oz = origin[2];
+    A.sx = size[0]; A.sy = size[1]; A.sz = size[2];
+    A.lx = P->light[0]; A.ly = P->light[1]; A.lz = P->light[2];
+    A.vsx = size[0] / (float)W; A.vsy = size[1] / (float)H; A.vsz = size[2] / (float)D;
+    A.t_table = static_cast<const float*>(ctx->adsm_table.p);
+    A.n_t = ctx->adsm_n;
+    A.step_size = 1.0f / P->steps; A.thickness = P->thickness; A.base = 1.0f - P->strand_alpha;
+    A.out = d_out;
+    PhaseMark mk(ctx, s, PH_PREFILTER);
+    k_adsm<<<(unsigned)((n + kAdsmThreads - 1) / kAdsmThreads), kAdsmThreads, 0, s>>>(A);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return VKHR_B200_OK;
+}
+
+int vkhr_b200_adsm(vkhr_b200_ctx* ctx, const uint8_t* densities, uint32_t W, uint32_t H, uint32_t D,
+                   const float origin[3], const float size[3], const vkhr_b200_adsm_params* P, float* out) {
+    RET_IF(bind(ctx));
+    if (!densities || !out) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null argument");
+    const size_t n = (size_t)W * H * D;
+    if (n == 0) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "zero resolution");
+    RET_IF(stage_in(ctx, ctx->st_dens, densities, n));
+    RET_IF(reserve(ctx, ctx->st_tang_out, n * 4));
+    RET_IF(vkhr_b200_adsm_dev(ctx, static_cast<const uint8_t*>(ctx->st_dens.p), W, H, D, origin, size, P,
+                              static_cast<float*>(ctx->st_tang_out.p), ctx->stream));
+    CU_CHECK(ctx, cudaMemcpyAsync(out, ctx->st_tang_out.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     return VKHR_B200_OK;
 }

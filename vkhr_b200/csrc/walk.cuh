@@ -27,6 +27,8 @@ struct GridParams {
     uint32_t index_exact;      // VKHR_B200_INDEX_EXACT
     float rvx, rvy, rvz;       // RN(1 / voxel_size), or 0 when the fast exact division must not be used
     uint32_t fast_div;         // all three reciprocals are usable (warp-cooperative fast path)
+    float pos_limit;           // fast walk only while |x|+|y|+|z| of every end point (voxel space) stays below this
+    uint32_t small_grid;       // W*H*D <= 2^24: the fp32 index expression is exact, so an int32 index equals it
 };
 
 // Correctly rounded a / d for d > 0, given y = RN(1/d) (0 = not available).
@@ -68,7 +70,7 @@ __device__ __forceinline__ bool voxel_index(const GridParams& g, float px, float
     float vx = glm_min(floorf(px), g.rx1);
     float vy = glm_min(floorf(py), g.ry1);
     float vz = glm_min(floorf(pz), g.rz1);
-    if (EXACT == 0 || (EXACT < 0 && !g.index_exact)) {
+    if (EXACT == 0 || EXACT == 2 || (EXACT < 0 && !g.index_exact)) {
         // voxel.x + voxel.y*width + voxel.z*width*height, all in fp32 (hair_style.cc:276,:321)
         float a = __fmul_rn(vy, g.Wf);
         float b = __fmul_rn(vz, g.Wf);
@@ -122,7 +124,7 @@ __device__ __forceinline__ void walk_voxel_space(const GridParams& g,
             const float vz = fminf(floorf(rz), g.rz1);
             uint32_t idx;
             bool ok;
-            if (EXACT == 0 || (EXACT < 0 && !g.index_exact)) {
+            if (EXACT == 0 || EXACT == 2 || (EXACT < 0 && !g.index_exact)) {
                 const float f = __fadd_rn(__fadd_rn(vx, __fmul_rn(vy, g.Wf)), __fmul_rn(__fmul_rn(vz, g.Wf), g.Hf));
                 idx = __float2uint_rz(f);                                 // negative -> 0, checked through f
                 ok = (f >= 0.0f) && (f < 4294967296.0f) && idx < g.n_voxels;
@@ -193,11 +195,13 @@ __device__ __forceinline__ GridParams pin(const GridParams& c) {
     g.vsx = pin(c.vsx); g.vsy = pin(c.vsy); g.vsz = pin(c.vsz);
     g.rx1 = pin(c.rx1); g.ry1 = pin(c.ry1); g.rz1 = pin(c.rz1);
     g.Wf = pin(c.Wf); g.Hf = pin(c.Hf);
-    g.W = c.W; g.H = c.H; g.D = c.D;                       // exact-index mode only
+    g.W = pin(c.W); g.H = pin(c.H); g.D = pin(c.D);        // integer index modes only (dead otherwise)
     g.n_voxels = pin(c.n_voxels);
     g.index_exact = c.index_exact;
     g.rvx = pin(c.rvx); g.rvy = pin(c.rvy); g.rvz = pin(c.rvz);
     g.fast_div = pin(c.fast_div);
+    g.pos_limit = pin(c.pos_limit);
+    g.small_grid = c.small_grid;
     return g;
 }
 
@@ -235,6 +239,16 @@ __device__ __forceinline__ void to_voxel_space_warp(const GridParams& g, float w
 // One sample of the walk for finite positions: voxel, fp32 (or exact) linear index, range test.
 template <int EXACT>
 __device__ __forceinline__ bool sample_index(const GridParams& g, float rx, float ry, float rz, uint32_t& idx) {
+    if (EXACT == 2) {
+        // Small grids (W*H*D <= 2^24) with bounded positions (|p| < pos_limit, voted by the caller): every
+        // term of the fp32 expression is an exactly representable integer, so the int32 expression is the
+        // same number; a negative index (the fp32 path's f < 0) wraps above n_voxels and is dropped.
+        const int ix = min(__float2int_rd(rx), (int)g.W - 1);
+        const int iy = min(__float2int_rd(ry), (int)g.H - 1);
+        const int iz = min(__float2int_rd(rz), (int)g.D - 1);
+        idx = (uint32_t)((iz * (int)g.H + iy) * (int)g.W + ix);
+        return idx < g.n_voxels;
+    }
     const float vx = fminf(floorf(rx), g.rx1);
     const float vy = fminf(floorf(ry), g.ry1);
     const float vz = fminf(floorf(rz), g.rz1);
@@ -253,7 +267,7 @@ __device__ __forceinline__ bool sample_index(const GridParams& g, float rx, floa
 
 // The sampled walk of one segment per lane, end points in voxel space (hair_style.cc:315-328).
 // `active` = this lane has a segment.
-template <int EXACT, class Sink>
+template <int EXACT, bool CHECK_TIP = true, class Sink>
 __device__ __forceinline__ void walk_voxel_space_warp(const GridParams& g, bool active,
                                                       float rx, float ry, float rz,
                                                       float tx, float ty, float tz, Sink& sink) {
@@ -262,8 +276,12 @@ __device__ __forceinline__ void walk_voxel_space_warp(const GridParams& g, bool 
     const bool go = active && (steps > 0.0f) && (steps < 16777216.0f);        // 0 / NaN: no samples; >= 2^24: never ends
     // fast when the root is finite (then every later position is finite too: |root| + 2^24 |dir|, so
     // glm::min == fminf) and the three divisions by `steps` are inside the FMA division's range
-    const bool fast = !go || ((steps >= 9.094947e-13f) && div_fast_ok(dx) && div_fast_ok(dy) && div_fast_ok(dz) &&
-                              (__fadd_rn(__fadd_rn(fabsf(rx), fabsf(ry)), fabsf(rz)) < 3.0e38f));
+    // (EXACT == 2 needs the bound on EVERY end point the warp holds, idle lanes included: lane t's tip is lane
+    // t+1's root in the uniform kernel; CHECK_TIP adds the tip for kernels whose tips are not another lane's root)
+    bool bounded = __fadd_rn(__fadd_rn(fabsf(rx), fabsf(ry)), fabsf(rz)) < g.pos_limit;
+    if (CHECK_TIP && EXACT == 2) bounded = bounded && (__fadd_rn(__fadd_rn(fabsf(tx), fabsf(ty)), fabsf(tz)) < g.pos_limit);
+    const bool fast = (EXACT == 2 || go ? bounded : true) &&
+                      (!go || ((steps >= 9.094947e-13f) && div_fast_ok(dx) && div_fast_ok(dy) && div_fast_ok(dz)));
     if (__all_sync(kFullWarp, fast)) {
         if (go) {
             const float y = __frcp_rn(steps);                                 // RN(1/steps)

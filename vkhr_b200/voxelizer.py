@@ -196,6 +196,25 @@ class Voxelizer:
                                                     _p(out.get("ao")), _p(out.get("opacity")), _p(out.get("gauss"))))
         return out
 
+    @staticmethod
+    def adsm_params(light, steps=1024.0, strand_alpha=0.3, thickness=11.0) -> "capi.AdsmParams":
+        """``vkhr_b200_adsm_params``: lights[0].origin + raycast_steps / hair_alpha / thickness (volume.frag:72-78)."""
+        p = capi.AdsmParams()
+        p.light = (C.c_float * 3)(*[float(x) for x in light])
+        p.steps, p.strand_alpha, p.thickness = float(steps), float(strand_alpha), float(thickness)
+        return p
+
+    def adsm(self, densities, W, H, D, aabb_origin, aabb_size, light, **params) -> np.ndarray:
+        """Volumetric ADSM transmittance volume (``volume_approximated_deep_shadows`` at every voxel centre), host arrays."""
+        d = _np(densities, np.uint8).reshape(-1)
+        if d.size != W * H * D:
+            raise ValueError("densities does not match W*H*D")
+        out = np.empty(d.size, dtype=np.float32)
+        p = self.adsm_params(light, **params)
+        capi.check(self._h, lib.vkhr_b200_adsm(self._h, _p(d), int(W), int(H), int(D), capi.vec3(aabb_origin), capi.vec3(aabb_size),
+                                               C.byref(p), _p(out)))
+        return out
+
     def generate_bounding_box(self, vertices) -> tuple[np.ndarray, np.ndarray]:
         """``HairStyle::generate_bounding_box`` (reference hair_style.cc:215-234): (min, max) folded from (0,0,0)."""
         v = _np(vertices, np.float32).reshape(-1, 3)
@@ -362,6 +381,21 @@ class Voxelizer:
         ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())   # noqa: E731
         capi.check(self._h, lib.vkhr_b200_prefilter_dev(self._h, C.c_void_p(densities.data_ptr()), int(W), int(H), int(D),
                                                         C.byref(p), ptr(ao), ptr(opacity), ptr(gauss), self._torch_stream(stream)))
+
+    def adsm_dev(self, densities, W, H, D, aabb_origin, aabb_size, light, out=None, stream=None, **params):
+        """Device-resident ADSM transmittance volume: ``out`` is a cuda float32 tensor of W*H*D (allocated if None)."""
+        import torch
+        self._check_dev(densities, torch.uint8, "densities")
+        if densities.numel() != int(W) * int(H) * int(D):
+            raise ValueError("densities does not match W*H*D")
+        if out is None:
+            out = torch.empty(densities.numel(), dtype=torch.float32, device=densities.device)
+        self._check_dev(out, torch.float32, "out")
+        p = self.adsm_params(light, **params)
+        capi.check(self._h, lib.vkhr_b200_adsm_dev(self._h, C.c_void_p(densities.data_ptr()), int(W), int(H), int(D),
+                                                   capi.vec3(aabb_origin), capi.vec3(aabb_size), C.byref(p),
+                                                   C.c_void_p(out.data_ptr()), self._torch_stream(stream)))
+        return out
 
     def generate_bounding_box_dev(self, vertices, out=None, stream=None):
         import torch
