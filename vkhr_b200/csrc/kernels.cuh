@@ -453,58 +453,79 @@ k_walk_uniform(const __grid_constant__ Batch B, uint32_t first) {
 // microseconds until instance i+1's own CTAs arrive.  HBM then sees every vertex once (read) and every texel
 // once (the final write-back) -- the algorithmic traffic, with no clear pass and no read fills.
 //
-// Ordering without a grid barrier: CTAs draw a ticket when they START (not from blockIdx, whose dispatch order
-// is not promised); ticket / gridDim.x is the instance, ticket % gridDim.x the CTA within it.  A CTA of
-// instance i waits until all gridDim.x CTAs of instance i-1 have cleared their slice of volume i -- they hold
-// lower tickets, so they have all started and do their clearing first: the wait cannot deadlock and is short.
-// Volume `first` is cleared by k_pipeline_prologue.
+// Ordering without a grid barrier and without assuming a dispatch order: the clear of a volume is a list of
+// gridDim.x slices handed out by an atomic ticket (stats[2], low word) and counted off when done (high word).
+// Every CTA of instance i takes ONE slice of volume i + kClearAhead before it walks; a CTA that finds its own
+// volume not completely cleared yet does not just wait -- it takes slices itself until none are left, then
+// waits only for slices that running CTAs are still writing.  Nobody ever waits for a CTA that has not started.
+// The first kClearAhead volumes are cleared by k_pipeline_prologue.
 // ---------------------------------------------------------------------------
+constexpr uint32_t kClearAhead = 2;      // volumes i+1 and i+2 are zero in L2 while i is walked
+
+// Clear slice `s` of N's volume and count it off.  All threads of the CTA.
+__device__ __forceinline__ void pipeline_clear_slice(const InstanceDev& N, uint32_t s, uint32_t n_slices) {
+    uint4* d = reinterpret_cast<uint4*>(N.densities);
+    const uint32_t n16 = N.grid.n_voxels >> 4;
+    const uint32_t per = (n16 + n_slices - 1u) / n_slices;
+    const uint32_t lo = min(n16, s * per), hi = min(n16, lo + per);
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += kWalkThreads) d[i] = z;
+    __syncthreads();                                               // the CTA's stores happen-before thread 0's release
+    if (threadIdx.x == 0)
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(reinterpret_cast<uint32_t*>(N.stats + 2) + 1), "r"(1u) : "memory");
+}
+
 template <int EXACT>
 __global__ void __launch_bounds__(kWalkThreads, VKHR_WALK_MIN_CTAS)
 k_walk_pipeline(const __grid_constant__ Batch B, uint32_t first, uint32_t count) {
     __shared__ __align__(128) float s_stage[kWarpsPerBlock][kStageFloats];
     __shared__ __align__(8) unsigned long long s_bar[kWarpsPerBlock];
-    __shared__ uint32_t s_ticket;
-    if (threadIdx.x == 0) s_ticket = atomicAdd(B.ticket, 1u);
-    __syncthreads();
-    const uint32_t ticket = s_ticket;
-    const uint32_t y = ticket / gridDim.x, bx = ticket - y * gridDim.x;
+    __shared__ uint32_t s_slice;
+    const uint32_t y = blockIdx.y, n_slices = gridDim.x;
+    if (y + kClearAhead < count) {                                 // one slice of the volume kClearAhead instances on
+        const InstanceDev& N = B.inst[first + y + kClearAhead];
+        if (threadIdx.x == 0) s_slice = atomicAdd(reinterpret_cast<uint32_t*>(N.stats + 2), 1u);
+        __syncthreads();
+        const uint32_t s = s_slice;
+        if (s < n_slices) pipeline_clear_slice(N, s, n_slices);    // (uniform across the CTA)
+    }
     const InstanceDev& I = B.inst[first + y];
-    if (y + 1u < count) {                                          // clear slice bx of the NEXT instance's volume
-        const InstanceDev& N = B.inst[first + y + 1u];
-        uint4* d = reinterpret_cast<uint4*>(N.densities);
-        const uint32_t n16 = N.grid.n_voxels >> 4;
-        const uint32_t per = (n16 + gridDim.x - 1u) / gridDim.x;
-        const uint32_t lo = min(n16, bx * per), hi = min(n16, lo + per);
-        const uint4 z = make_uint4(0, 0, 0, 0);
-        for (uint32_t i = lo + threadIdx.x; i < hi; i += kWalkThreads) d[i] = z;
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) atomicAdd(reinterpret_cast<uint32_t*>(N.stats + 2), 1u);
-    }
-    if (y > 0u) {                                                  // my own volume must be completely cleared
-        if (threadIdx.x == 0) {
-            const volatile uint32_t* done = reinterpret_cast<const volatile uint32_t*>(I.stats + 2);
-            uint32_t spin = 0;
-            while (*done < gridDim.x) { __nanosleep(64); if (++spin > (1u << 26)) __trap(); }
-            __threadfence();
+    if (y >= kClearAhead) {                                        // my own volume must be completely cleared
+        uint32_t* ctr = reinterpret_cast<uint32_t*>(I.stats + 2);
+        for (uint32_t spin = 0;; ++spin) {
+            __syncthreads();                                       // s_slice is reused
+            if (threadIdx.x == 0) {
+                uint32_t done;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(done) : "l"(ctr + 1) : "memory");
+                uint32_t s = 0xFFFFFFFFu;                          // done
+                if (done < n_slices) {
+                    s = atomicAdd(ctr, 1u);                        // help: take a slice nobody has started
+                    if (s >= n_slices) { s = 0xFFFFFFFEu; __nanosleep(64); }   // all taken, some still being written
+                }
+                s_slice = s;
+            }
+            __syncthreads();
+            const uint32_t s = s_slice;
+            if (s == 0xFFFFFFFFu) break;
+            if (s < n_slices) pipeline_clear_slice(I, s, n_slices);
+            if (spin > (1u << 24)) __trap();                       // a lost signal must fail, not hang the device
         }
-        __syncthreads();
     }
-    walk_uniform_cta<2, EXACT>(I, bx, first + y, s_stage, s_bar);
+    walk_uniform_cta<2, EXACT>(I, blockIdx.x, first + y, s_stage, s_bar);
 }
 
-// Prologue of the pipelined walk: zero the first volume, every instance's statistics block and the ticket.
+// Prologue of the pipelined walk: zero the first kClearAhead volumes, every instance's statistics block and the ticket.
 __global__ void __launch_bounds__(256) k_pipeline_prologue(const __grid_constant__ Batch B, uint32_t first, uint32_t count) {
-    const InstanceDev& I = B.inst[first];
     const uint4 z = make_uint4(0, 0, 0, 0);
-    uint4* d = reinterpret_cast<uint4*>(I.densities);
-    const uint32_t n16 = I.grid.n_voxels >> 4;
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    for (uint32_t i = t; i < n16; i += stride) d[i] = z;
+    for (uint32_t k = 0; k < min(count, kClearAhead); ++k) {
+        const InstanceDev& I = B.inst[first + k];
+        uint4* d = reinterpret_cast<uint4*>(I.densities);
+        const uint32_t n16 = I.grid.n_voxels >> 4;
+        for (uint32_t i = t; i < n16; i += stride) d[i] = z;
+    }
     if (t < count * kStatsWords64) B.inst[first + t / kStatsWords64].stats[t % kStatsWords64] = 0ull;
-    if (t == 0) *B.ticket = 0u;
 }
 
 // ---------------------------------------------------------------------------
