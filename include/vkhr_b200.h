@@ -273,6 +273,20 @@ VKHR_B200_API int vkhr_b200_prefilter(
     const vkhr_b200_prefilter_params* params,
     float* ao_out, float* opacity_out, float* gauss_out);
 
+/* ---- .hair bytes -> volume -------------------------------------------------- *
+ * The load-time path of the reference in one call: HairStyle::load (hair_style.cc:24-47;
+ * 128-byte header + raw arrays, hair_style.hh:147-174), what SceneGraph::add_style adds
+ * when the file lacks it (scene_graph.cc:235-242: generate_indices from segments[] or
+ * default_segment_count, generate_bounding_box; the strand shuffle does not change
+ * densities), then voxelize_segments(W, H, D) over get_bounding_box()
+ * (rasterizer/hair_style.cc:65-66,75).  The arrays are used in place from the file image:
+ * vertices (and indices / tangents when present) are uploaded as they lie, indices of
+ * strands with different lengths are generated on the device.  aabb_out (optional) receives
+ * origin[3], size[3] -- the caller's volume_bounds.  tangents_out may be NULL. */
+VKHR_B200_API int vkhr_b200_voxelize_hair(
+    vkhr_b200_ctx* ctx, const void* hair_bytes, size_t n_bytes, uint32_t W, uint32_t H, uint32_t D,
+    uint32_t flags, uint8_t* densities_out, int8_t* tangents_out, float aabb_out[6]);
+
 /* ---- volumetric ADSM transmittance volume ---------------------------------- *
  * volume_approximated_deep_shadows(density, centre, light, steps, strand_alpha,
  * origin, size, thickness) of share/shaders/self-shadowing/approximate_deep_shadows.glsl:24-36

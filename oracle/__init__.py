@@ -267,6 +267,11 @@ class RefHairStyle:
         self._lib.vkhr_ref_get_aabb(self._h, out)
         return np.array(out, dtype=np.float32)
 
+    def prepare(self):
+        """SceneGraph::add_style's generate_* calls for the fields the file lacked (no shuffle)."""
+        self._lib.vkhr_ref_prepare(self._h)
+        return self
+
     def save(self, path):
         if self._lib.vkhr_ref_save(self._h, path.encode()) != 0:
             raise IOError(path)
@@ -298,6 +303,8 @@ class _Ref:
         L.vkhr_ref_index_count.restype = C.c_uint64
         L.vkhr_ref_voxelize.restype = C.c_double
         L.vkhr_ref_voxelize.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, _u8p, _i8p]
+        L.vkhr_ref_prepare.argtypes = [C.c_void_p]
+        L.vkhr_ref_prepare.restype = None
         for name in ("vkhr_ref_destroy", "vkhr_ref_vertex_count", "vkhr_ref_strand_count", "vkhr_ref_segment_count",
                      "vkhr_ref_index_count", "vkhr_ref_default_segment_count", "vkhr_ref_has_bounding_box"):
             getattr(L, name).argtypes = [C.c_void_p]

@@ -53,6 +53,15 @@ void* vkhr_ref_load(const char* path) {
     return hs;
 }
 
+// What SceneGraph::add_style does to a freshly loaded style (src/vkhr/scene_graph.cc:235-242), minus the
+// random shuffle: generate whatever the file did not carry.
+void vkhr_ref_prepare(void* h) {
+    auto* hs = static_cast<vkhr::HairStyle*>(h);
+    if (!hs->has_tangents()) hs->generate_tangents();
+    if (!hs->has_indices()) hs->generate_indices();
+    if (!hs->has_bounding_box()) hs->generate_bounding_box();
+}
+
 // Build a HairStyle the way SceneGraph::add_style prepares one
 // (src/vkhr/scene_graph.cc:222-245), minus the random shuffle: tangents,
 // indices, and (when aabb_min == NULL) the generated bounding box.

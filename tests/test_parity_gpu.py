@@ -461,3 +461,67 @@ def test_cpp_dropin_against_linked_reference():
     assert r.returncode == 0, r.stdout + r.stderr
     assert "drop-in test ok" in r.stdout
     assert r.stdout.count("bit-exact") == 5 and "MISMATCH" not in r.stdout
+
+
+# ---- .hair file image -> volume (HairStyle::load + SceneGraph::add_style + voxelize_segments) -----------------------
+def _hair_file(tmp_path, name, strands, segs, *, segments=None, indices=False, tangents=False, bbox=False, seed=4):
+    from vkhr_b200.hair_style import HairStyle
+    hs = HairStyle()
+    if segments is None:
+        hs.vertices = synth.strands(strands, segs, seed=seed)
+        hs.set_strand_count(strands)
+        hs.set_default_segment_count(segs)
+    else:
+        hs.vertices = np.concatenate([synth.strands(1, int(c), seed=seed + k) for k, c in enumerate(segments)])
+        hs.segments = np.asarray(segments, dtype=np.uint16)
+    if indices:
+        hs.generate_indices()
+    if tangents:
+        hs.generate_tangents()
+    if bbox:
+        lo, hi = synth.host_bounding_box(hs.vertices)
+        hs.set_bounding_box(lo - 0.25, hi + 0.5)               # NOT the generated box: the header's must be used
+    p = str(tmp_path / name)
+    assert hs.save(p)
+    return p
+
+
+@pytest.mark.parametrize("case", ["uniform", "uniform+bbox", "uniform+indices+tangents+bbox", "segments", "segments+bbox",
+                                  "segments-equal", "segments+indices"])
+@pytest.mark.parametrize("res", [(32, 32, 32), (40, 24, 16)])
+def test_voxelize_hair_file_matches_the_reference_loader(vox, ref, tmp_path, case, res):
+    """The reference loads the same file, generates what add_style would generate, and voxelises: same bytes."""
+    W, H, D = res
+    rng = np.random.default_rng(len(case))
+    kw = {"indices": "indices" in case, "tangents": "tangents" in case, "bbox": "bbox" in case}
+    if case.startswith("segments-equal"):
+        p = _hair_file(tmp_path, "s.hair", 0, 0, segments=[5] * 37, **kw)
+    elif case.startswith("segments"):
+        p = _hair_file(tmp_path, "s.hair", 0, 0, segments=rng.integers(1, 9, 61), **kw)      # odd strand count: vertices at offset % 4 == 2
+    else:
+        p = _hair_file(tmp_path, "u.hair", 53, 7, **kw)
+    r = ref.load(p).prepare()
+    want, want_t, _ = r.voxelize("segments", W, H, D, want_tangents=True)
+    blob = open(p, "rb").read()
+    got, got_t, origin, size = vox.voxelize_hair(blob, W, H, D, want_tangents=True)
+    assert np.array_equal(got, want), f"{case}: densities differ from the reference's"
+    box = r.aabb
+    assert np.array_equal(origin, box[0:3]) and np.array_equal(size, box[4:7])
+    unsat = (want > 0) & (want < 255)                           # tangents: +-1 LSB where the reference's own sum is order-stable
+    assert np.abs(got_t.astype(np.int16) - want_t.astype(np.int16))[unsat].max(initial=0) <= 1
+    assert want.sum() > 0
+
+
+def test_voxelize_hair_file_rejects_bad_images(vox, tmp_path):
+    from vkhr_b200.capi import VkhrB200Error
+    p = _hair_file(tmp_path, "ok.hair", 9, 3)
+    blob = open(p, "rb").read()
+    for bad in (b"", blob[:100], b"NOPE" + blob[4:], blob[:-8]):
+        with pytest.raises(VkhrB200Error):
+            vox.voxelize_hair(bad, 8, 8, 8)
+    # a header whose counts do not add up
+    import struct
+    broken = bytearray(blob)
+    struct.pack_into("<I", broken, 16, 4)                       # default_segment_count 3 -> 4
+    with pytest.raises(VkhrB200Error):
+        vox.voxelize_hair(bytes(broken), 8, 8, 8)

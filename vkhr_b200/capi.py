@@ -136,6 +136,7 @@ _PROTOTYPES = {
     "vkhr_b200_prefilter_defaults": (None, [C.POINTER(PrefilterParams)]),
     "vkhr_b200_prefilter_dev": (_int, [c_ctx, _P, _u32, _u32, _u32, C.POINTER(PrefilterParams), _P, _P, _P, _P]),
     "vkhr_b200_prefilter": (_int, [c_ctx, _P, _u32, _u32, _u32, C.POINTER(PrefilterParams), _P, _P, _P]),
+    "vkhr_b200_voxelize_hair": (_int, [c_ctx, _P, _sz, _u32, _u32, _u32, _u32, _P, _P, C.c_float * 6]),
     "vkhr_b200_adsm_dev": (_int, [c_ctx, _P, _u32, _u32, _u32, _vec3, _vec3, C.POINTER(AdsmParams), _P, _P]),
     "vkhr_b200_adsm": (_int, [c_ctx, _P, _u32, _u32, _u32, _vec3, _vec3, C.POINTER(AdsmParams), _P]),
     "vkhr_b200_malloc": (_int, [c_ctx, _sz, C.POINTER(_P)]),

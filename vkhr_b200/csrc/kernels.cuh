@@ -35,7 +35,6 @@ struct InstanceDev {
     uint32_t        kind;           // WalkKind
     uint32_t        vps_magic;      // floor(2^32 / (segs_per_strand + 1)) + 1   (strand-end test without a division)
     uint32_t        pad;
-    unsigned long long* stats;      // PACKED8 red mode: [0] = samples added by the walk, [1] = byte sum of the volume
 };
 
 // A batch travels to the kernels as a __grid_constant__ parameter: every per-instance constant is then
@@ -44,14 +43,9 @@ struct InstanceDev {
 constexpr uint32_t kMaxBatch = 64;
 struct Batch {
     uint32_t n;
-    uint32_t pad;
-    uint32_t* ticket;               // pipelined walk: CTA start-order counter (global memory, zeroed by the prologue)
+    uint32_t pad[3];
     InstanceDev inst[kMaxBatch];
 };
-// Per-instance statistics block of the PACKED8 red mode (InstanceDev::stats), 32 bytes:
-//   [0] samples added by the walk   [1] byte sum of the finished volume
-//   [2] low word: CTAs that have finished clearing their slice of this volume (pipelined walk)
-constexpr uint32_t kStatsWords64 = 4;
 static_assert(sizeof(Batch) <= 16 * 1024, "kernel parameter space");
 
 // ---------------------------------------------------------------------------
@@ -118,30 +112,6 @@ struct SinkPacked8 {
     __device__ __forceinline__ void words_pin() { asm volatile("" : "+l"(words)); }
 };
 
-// PACKED8, fire-and-forget: `red.global.add.u32` of 1 << (8 * byte) with no return value -- one L1TEX
-// wavefront per sample instead of ~1.6 for the returning `atom` (ncu: l1tex__data_pipe_lsu_wavefronts), no
-// scoreboard wait, no pending-result registers.  A byte that receives more than 255 hits carries into its
-// neighbour, and nobody sees it happen; instead every lane counts the samples it adds, the warp adds its total
-// to stats[0], and k_finish_packed compares it with the byte sum of the finished volume: a carry out of a
-// byte lowers the byte sum by 255 (or 256 out of the word's top byte) and nothing ever raises it, so
-//     byte sum == samples  <=>  no byte ever carried  <=>  every voxel holds its exact count (<= 255).
-// A mismatch (never for hair at a useful resolution) re-voxelises that instance with u32 counters.
-struct SinkPacked8Red {
-    uint32_t* words;
-    unsigned long long* stats;
-    uint32_t n = 0;
-    template <int SLOT = 0>
-    __device__ __forceinline__ void put(uint32_t idx) {
-        red_add_u32(words + (idx >> 2), 1u << ((idx & 3u) * 8u));       // RED.E.ADD: no return value
-        ++n;
-    }
-    __device__ __forceinline__ void finish() {                         // all 32 lanes together
-        const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, n);
-        if ((threadIdx.x & 31u) == 0u && total) atomicAdd(stats, (unsigned long long)total);
-    }
-    __device__ __forceinline__ void words_pin() { asm volatile("" : "+l"(words)); }
-};
-
 // Recount pass of PACKED8: only samples landing in flagged words are counted,
 // into the u32 scratch grid.
 struct SinkRecount {
@@ -160,29 +130,6 @@ template <> struct SinkOf<0> { using type = SinkCount32;
     __device__ static type make(const InstanceDev& I) { return SinkCount32{I.counts}; } };
 template <> struct SinkOf<1> { using type = SinkPacked8;
     __device__ static type make(const InstanceDev& I) { SinkPacked8 k; k.words = reinterpret_cast<uint32_t*>(I.densities); k.ovf_bitmap = I.ovf_bitmap; k.ovf_flag = I.ovf_flag; return k; } };
-
-// Measurement-only sinks (VKHR_B200_WALK=null|sector|line|lines8): same instruction stream, different L1TEX wavefront counts.
-template <int KIND> struct SinkProbe {
-    uint32_t* words; unsigned long long* stats; uint32_t n = 0;
-    template <int SLOT = 0>
-    __device__ __forceinline__ void put(uint32_t idx) {
-        const uint32_t inc = 1u << ((idx & 3u) * 8u);
-        if (KIND == 0) n ^= idx + inc;                                                   // no memory operation at all
-        else if (KIND == 1) red_add_u32(words + (idx & 7u), inc);                        // all lanes in ONE 32-byte sector
-        else if (KIND == 2) red_add_u32(words + (idx & 7u) + 8u * (threadIdx.x & 3u), inc);        // one 128-byte line, 4 sectors
-        else red_add_u32(words + (idx & 7u) + 8u * (threadIdx.x & 3u) + 32u * ((idx >> 3) & 0xFFFFu) , inc);   // lanes spread over lines, 4-lane groups keep distinct sectors
-        if (KIND != 0) ++n;
-    }
-    __device__ __forceinline__ void finish() { if (n == 0xDEADBEEFu) *stats = n; }
-    __device__ __forceinline__ void words_pin() { asm volatile("" : "+l"(words)); }
-};
-template <> struct SinkOf<10> { using type = SinkProbe<0>; __device__ static type make(const InstanceDev& I) { type k; k.words = reinterpret_cast<uint32_t*>(I.densities); k.stats = I.stats; return k; } };
-template <> struct SinkOf<11> { using type = SinkProbe<1>; __device__ static type make(const InstanceDev& I) { type k; k.words = reinterpret_cast<uint32_t*>(I.densities); k.stats = I.stats; return k; } };
-template <> struct SinkOf<12> { using type = SinkProbe<2>; __device__ static type make(const InstanceDev& I) { type k; k.words = reinterpret_cast<uint32_t*>(I.densities); k.stats = I.stats; return k; } };
-template <> struct SinkOf<13> { using type = SinkProbe<3>; __device__ static type make(const InstanceDev& I) { type k; k.words = reinterpret_cast<uint32_t*>(I.densities); k.stats = I.stats; return k; } };
-
-template <> struct SinkOf<2> { using type = SinkPacked8Red;
-    __device__ static type make(const InstanceDev& I) { SinkPacked8Red k; k.words = reinterpret_cast<uint32_t*>(I.densities); k.stats = I.stats; return k; } };
 
 // ---------------------------------------------------------------------------
 // Walk kernel for uniform strands (no index buffer): the hot kernel.
@@ -237,99 +184,9 @@ __device__ unsigned int g_cta_trace_count = 0;
 __device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
 
-template <int MODE, int EXACT>
-__global__ void __launch_bounds__(kWalkThreads, VKHR_WALK_MIN_CTAS)
-k_walk_uniform_v5(const __grid_constant__ Batch B, uint32_t first) {
-    __shared__ __align__(128) float s_stage[kWarpsPerBlock][kStageFloats];
-    const unsigned long long t_start = g_cta_trace ? globaltimer_ns() : 0ull;
-    __shared__ __align__(8) unsigned long long s_bar[kWarpsPerBlock];
-    const InstanceDev& I = B.inst[first + blockIdx.y];
-    if (blockIdx.x >= I.n_tiles || I.kind != WK_UNIFORM) return;   // n_tiles counts CTAs
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const GridParams g = pin(I.grid);                              // registers, not indexed constant loads
-    const uint32_t n_vertices = pin(I.n_vertices);
-    const uint32_t n_floats = 3u * n_vertices;
-    const uint32_t n_warp_tiles = (n_vertices + kTileStride - 1u) / kTileStride;
-    const uint32_t vps = pin(I.segs_per_strand + 1u);
-    const uint32_t vps_magic = pin(I.vps_magic);
-    const float* __restrict__ verts = I.vertices;
-    float* stage = s_stage[warp];
-    auto sink = SinkOf<MODE>::make(I);
-
-    const uint32_t range = blockIdx.x * kWarpsPerBlock + warp;     // this warp's range of kTilesPerWarp tiles
-    const uint32_t tile0 = range * kTilesPerWarp;
-    const uint32_t n_tiles = min(kTilesPerWarp, n_warp_tiles - min(tile0, n_warp_tiles));
-    if (n_tiles == 0) return;                                      // whole warps only
-
-    // ---- stage the warp's vertex range (8 tiles + one tip vertex, 3 KB) into shared memory -----------------
-    // 16-byte aligned vertex buffers: ONE bulk copy issued by lane 0, completion on the warp's own mbarrier.
-    // Anything else (a 4-byte aligned view, the last bytes of the buffer): coalesced 32-bit loads.
-    {
-        const uint32_t start = kRangeFloats * range;                // first float of the range
-        const uint32_t need = min(kNeedFloats, n_floats - start);   // floats this warp reads from `stage`
-        uint32_t bulk = 0;                                          // floats that arrive by bulk copy
-        if ((reinterpret_cast<uintptr_t>(verts) & 15u) == 0u)
-            bulk = min(kBulkBytes, ((n_floats - start) * 4u) & ~15u) / 4u;
-        const uint32_t bar = smem_u32(&s_bar[warp]);
-        if (bulk) {
-            if (lane == 0) mbar_init(bar, 1);
-            __syncwarp();
-            if (lane == 0) bulk_load(smem_u32(stage), verts + start, bulk * 4u, bar);
-        }
-        for (uint32_t j = bulk + lane; j < need; j += 32u) stage[j] = __ldg(verts + start + j);
-        if (bulk) mbar_wait(bar, 0);
-        __syncwarp();
-    }
-
-    // ---- software-pipelined tile loop ------------------------------------------------------------------
-    // Shared-memory loads and shuffles share the SM's memory-instruction queue with the reds; behind a burst
-    // of reds each round trip takes as long as the queue is deep.  So nothing in a tile's walk waits for a
-    // round trip issued in the same iteration: the raw floats of tile k+2 and the transformed + shuffled end
-    // points of tile k+1 are requested BEFORE tile k is walked.
-    auto load_raw = [&](uint32_t k, float& a, float& b, float& c) {
-        const float* r = stage + 3u * kTileStride * k + 3u * lane;
-        a = r[0]; b = r[1]; c = r[2];
-    };
-    float r0, r1, r2, px, py, pz, tx, ty, tz;
-    load_raw(0, r0, r1, r2);
-    to_voxel_space_warp(g, r0, r1, r2, px, py, pz);
-    tx = __shfl_down_sync(kFullWarp, px, 1);
-    ty = __shfl_down_sync(kFullWarp, py, 1);
-    tz = __shfl_down_sync(kFullWarp, pz, 1);
-    if (n_tiles > 1u) load_raw(1, r0, r1, r2);
-    for (uint32_t k = 0; k < n_tiles; ++k) {
-        float npx = 0.f, npy = 0.f, npz = 0.f, ntx = 0.f, nty = 0.f, ntz = 0.f;
-        if (k + 1u < n_tiles) {                                    // warp-uniform
-            to_voxel_space_warp(g, r0, r1, r2, npx, npy, npz);
-            ntx = __shfl_down_sync(kFullWarp, npx, 1);
-            nty = __shfl_down_sync(kFullWarp, npy, 1);
-            ntz = __shfl_down_sync(kFullWarp, npz, 1);
-            if (k + 2u < n_tiles) load_raw(k + 2u, r0, r1, r2);
-        }
-        // vertex x starts a segment unless it is the last of its strand: x mod vps by multiply-high
-        // (the quotient estimate is exact or one too large)
-        const uint32_t x = kTileStride * (tile0 + k) + lane;
-        uint32_t r = x - __umulhi(x, vps_magic) * vps;
-        if ((int32_t)r < 0) r += vps;
-        const bool active = lane < kTileStride && x + 1u < n_vertices && r != vps - 1u;
-        walk_voxel_space_warp<EXACT>(g, active, px, py, pz, tx, ty, tz, sink);
-        px = npx; py = npy; pz = npz; tx = ntx; ty = nty; tz = ntz;
-    }
-    sink.finish();
-    if (g_cta_trace && threadIdx.x == 0) {                         // warp 0's own duration (no CTA barrier here)
-        const unsigned int slot = atomicAdd(&g_cta_trace_count, 1u);
-        if (slot < (1u << 20)) {
-            g_cta_trace[4ull * slot + 0] = smid();
-            g_cta_trace[4ull * slot + 1] = t_start;
-            g_cta_trace[4ull * slot + 2] = globaltimer_ns();
-            g_cta_trace[4ull * slot + 3] = ((unsigned long long)(first + blockIdx.y) << 32) | blockIdx.x;
-        }
-    }
-}
-
 template <class T> __device__ __forceinline__ T* pin(T* p) { asm volatile("" : "+l"(p)); return p; }
 
-// The walk of CTA `bx` of instance I (uniform strands); shared by k_walk_uniform and k_walk_pipeline.
+// The walk of CTA `bx` of instance I (uniform strands).
 template <int MODE, int EXACT>
 __device__ __forceinline__ void walk_uniform_cta(const InstanceDev& I, uint32_t bx, uint32_t inst_id,
                                                  float (*s_stage)[kStageFloats], unsigned long long* s_bar) {
@@ -439,93 +296,6 @@ k_walk_uniform(const __grid_constant__ Batch B, uint32_t first) {
     __shared__ __align__(128) float s_stage[kWarpsPerBlock][kStageFloats];
     __shared__ __align__(8) unsigned long long s_bar[kWarpsPerBlock];
     walk_uniform_cta<MODE, EXACT>(B.inst[first + blockIdx.y], blockIdx.x, first + blockIdx.y, s_stage, s_bar);
-}
-
-// ---------------------------------------------------------------------------
-// Pipelined crowd walk (PACKED8 red mode): clear and walk in ONE launch, so that every volume is walked
-// while its freshly written zeros are still in L2.
-//
-// Measured on B200 (profiles/r02_*): fire-and-forget reds run at the L1TEX wavefront rate as long as their
-// target sectors are L2-resident (the walk of 64 instances into ONE shared volume takes 1.1 ms), but a red
-// that misses L2 holds its slot for a DRAM fill, and the same walk into 64 volumes that a separate clear
-// pass has long since pushed out to HBM takes 2.2 ms.  So the clear of instance i+1 is done by the CTAs of
-// instance i, immediately before they walk: its 16 MiB of dirty zeros stay in L2 for the few tens of
-// microseconds until instance i+1's own CTAs arrive.  HBM then sees every vertex once (read) and every texel
-// once (the final write-back) -- the algorithmic traffic, with no clear pass and no read fills.
-//
-// Ordering without a grid barrier and without assuming a dispatch order: the clear of a volume is a list of
-// gridDim.x slices handed out by an atomic ticket (stats[2], low word) and counted off when done (high word).
-// Every CTA of instance i takes ONE slice of volume i + kClearAhead before it walks; a CTA that finds its own
-// volume not completely cleared yet does not just wait -- it takes slices itself until none are left, then
-// waits only for slices that running CTAs are still writing.  Nobody ever waits for a CTA that has not started.
-// The first kClearAhead volumes are cleared by k_pipeline_prologue.
-// ---------------------------------------------------------------------------
-constexpr uint32_t kClearAhead = 2;      // volumes i+1 and i+2 are zero in L2 while i is walked
-
-// Clear slice `s` of N's volume and count it off.  All threads of the CTA.
-__device__ __forceinline__ void pipeline_clear_slice(const InstanceDev& N, uint32_t s, uint32_t n_slices) {
-    uint4* d = reinterpret_cast<uint4*>(N.densities);
-    const uint32_t n16 = N.grid.n_voxels >> 4;
-    const uint32_t per = (n16 + n_slices - 1u) / n_slices;
-    const uint32_t lo = min(n16, s * per), hi = min(n16, lo + per);
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    for (uint32_t i = lo + threadIdx.x; i < hi; i += kWalkThreads) d[i] = z;
-    __syncthreads();                                               // the CTA's stores happen-before thread 0's release
-    if (threadIdx.x == 0)
-        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(reinterpret_cast<uint32_t*>(N.stats + 2) + 1), "r"(1u) : "memory");
-}
-
-template <int EXACT>
-__global__ void __launch_bounds__(kWalkThreads, VKHR_WALK_MIN_CTAS)
-k_walk_pipeline(const __grid_constant__ Batch B, uint32_t first, uint32_t count) {
-    __shared__ __align__(128) float s_stage[kWarpsPerBlock][kStageFloats];
-    __shared__ __align__(8) unsigned long long s_bar[kWarpsPerBlock];
-    __shared__ uint32_t s_slice;
-    const uint32_t y = blockIdx.y, n_slices = gridDim.x;
-    if (y + kClearAhead < count) {                                 // one slice of the volume kClearAhead instances on
-        const InstanceDev& N = B.inst[first + y + kClearAhead];
-        if (threadIdx.x == 0) s_slice = atomicAdd(reinterpret_cast<uint32_t*>(N.stats + 2), 1u);
-        __syncthreads();
-        const uint32_t s = s_slice;
-        if (s < n_slices) pipeline_clear_slice(N, s, n_slices);    // (uniform across the CTA)
-    }
-    const InstanceDev& I = B.inst[first + y];
-    if (y >= kClearAhead) {                                        // my own volume must be completely cleared
-        uint32_t* ctr = reinterpret_cast<uint32_t*>(I.stats + 2);
-        for (uint32_t spin = 0;; ++spin) {
-            __syncthreads();                                       // s_slice is reused
-            if (threadIdx.x == 0) {
-                uint32_t done;
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(done) : "l"(ctr + 1) : "memory");
-                uint32_t s = 0xFFFFFFFFu;                          // done
-                if (done < n_slices) {
-                    s = atomicAdd(ctr, 1u);                        // help: take a slice nobody has started
-                    if (s >= n_slices) { s = 0xFFFFFFFEu; __nanosleep(64); }   // all taken, some still being written
-                }
-                s_slice = s;
-            }
-            __syncthreads();
-            const uint32_t s = s_slice;
-            if (s == 0xFFFFFFFFu) break;
-            if (s < n_slices) pipeline_clear_slice(I, s, n_slices);
-            if (spin > (1u << 24)) __trap();                       // a lost signal must fail, not hang the device
-        }
-    }
-    walk_uniform_cta<2, EXACT>(I, blockIdx.x, first + y, s_stage, s_bar);
-}
-
-// Prologue of the pipelined walk: zero the first kClearAhead volumes, every instance's statistics block and the ticket.
-__global__ void __launch_bounds__(256) k_pipeline_prologue(const __grid_constant__ Batch B, uint32_t first, uint32_t count) {
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    for (uint32_t k = 0; k < min(count, kClearAhead); ++k) {
-        const InstanceDev& I = B.inst[first + k];
-        uint4* d = reinterpret_cast<uint4*>(I.densities);
-        const uint32_t n16 = I.grid.n_voxels >> 4;
-        for (uint32_t i = t; i < n16; i += stride) d[i] = z;
-    }
-    if (t < count * kStatsWords64) B.inst[first + t / kStatsWords64].stats[t % kStatsWords64] = 0ull;
 }
 
 // ---------------------------------------------------------------------------
@@ -718,39 +488,9 @@ __global__ void __launch_bounds__(256) k_clear_packed_batch(const __grid_constan
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     for (uint32_t i = t; i < n16; i += stride) d[i] = z;
-    if (I.ovf_bitmap) {                                             // atom mode only
-        const uint32_t n_bm = (I.grid.n_voxels / 4 + 31) / 32;      // bitmap words
-        for (uint32_t i = t; i < n_bm; i += stride) I.ovf_bitmap[i] = 0u;
-        if (t == 0) *I.ovf_flag = 0u;
-    }
-    if (I.stats && t == 0) { I.stats[0] = 0ull; I.stats[1] = 0ull; I.stats[2] = 0ull; I.stats[3] = 0ull; }
-}
-
-// PACKED8 red mode: byte sum of every instance's finished volume -> stats[1] (compared with stats[0], the number of
-// samples the walk added, by k_finish_packed).  blockIdx.y + first = instance; four 16-byte loads in flight per thread.
-__device__ __forceinline__ uint32_t bytesum16(uint4 a, uint32_t acc) {
-    acc = __dp4a(a.x, 0x01010101u, acc); acc = __dp4a(a.y, 0x01010101u, acc);
-    acc = __dp4a(a.z, 0x01010101u, acc); return __dp4a(a.w, 0x01010101u, acc);
-}
-__global__ void __launch_bounds__(256) k_verify_packed_batch(const __grid_constant__ Batch B, uint32_t first) {
-    const InstanceDev& I = B.inst[first + blockIdx.y];
-    const uint4* d = reinterpret_cast<const uint4*>(I.densities);
-    const uint32_t n16 = I.grid.n_voxels >> 4;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t acc = 0;
-    for (; i + 3u * stride < n16; i += 4u * stride) {
-        const uint4 a = __ldcs(d + i), b = __ldcs(d + i + stride), c = __ldcs(d + i + 2u * stride), e = __ldcs(d + i + 3u * stride);
-        acc = bytesum16(a, acc); acc = bytesum16(b, acc); acc = bytesum16(c, acc); acc = bytesum16(e, acc);
-    }
-    for (; i < n16; i += stride) acc = bytesum16(__ldcs(d + i), acc);
-    __shared__ uint32_t s_acc;
-    if (threadIdx.x == 0) s_acc = 0;
-    __syncthreads();
-    acc = __reduce_add_sync(0xFFFFFFFFu, acc);
-    if ((threadIdx.x & 31u) == 0u && acc) atomicAdd(&s_acc, acc);
-    __syncthreads();
-    if (threadIdx.x == 0 && s_acc) atomicAdd(I.stats + 1, (unsigned long long)s_acc);
+    const uint32_t n_bm = (I.grid.n_voxels / 4 + 31) / 32;          // bitmap words
+    for (uint32_t i = t; i < n_bm; i += stride) I.ovf_bitmap[i] = 0u;
+    if (t == 0) *I.ovf_flag = 0u;
 }
 
 // densities = min(counts, 255)  (hair_style.cc:322: `if (d != 255) d += 1`),
@@ -882,6 +622,20 @@ k_downsample(const uint8_t* __restrict__ in, uint32_t W, uint32_t H, uint32_t w,
             }
         out[o] = (uint8_t)(filter == 0 ? mx : filter == 1 ? s / 8 : filter == 2 ? s : mn);
     }
+}
+
+// ---------------------------------------------------------------------------
+// HairStyle::generate_indices (hair_style.cc:196-213) for strands of different lengths: segment j of the style
+// belongs to the strand s with seg_prefix[s] <= j < seg_prefix[s+1] and joins vertices (j + s, j + s + 1) --
+// every earlier strand contributes one vertex that starts no segment.  One thread per segment.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_generate_indices(const uint32_t* __restrict__ seg_prefix, uint32_t n_strands, uint32_t n_segments, uint2* __restrict__ pairs) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_segments) return;
+    uint32_t lo = 0, hi = n_strands;                        // last s with seg_prefix[s] <= j
+    while (hi - lo > 1u) { const uint32_t m = (lo + hi) >> 1; if (__ldg(seg_prefix + m) <= j) lo = m; else hi = m; }
+    pairs[j] = make_uint2(j + lo, j + lo + 1u);
 }
 
 // ---------------------------------------------------------------------------

@@ -222,11 +222,45 @@ k_prefilter_tiled(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         if (tid == 0 && tile + gridDim.x < n_tiles) issue(tile + gridDim.x, buf ^ 1u);   // prefetch the next tile
         pf_mbar_wait(bar0 + 8u * buf, (it >> 1) & 1u);
         const unsigned char* stage = pf_smem + buf * P.stage_bytes;
+        int x0, y0, z0;
+        tile_origin(tile, x0, y0, z0);
+
+        // ---- empty space: a staged box (tile + halo) without a single hair writes the constants of empty space ----
+        // (most tiles of a hair volume at 512^3 and above; the barrier below also orders every thread's last read of
+        // this stage buffer before thread 0 re-arms it at the top of the next iteration)
+        {
+            int nz = 0;
+            const uint4* s16 = reinterpret_cast<const uint4*>(stage);
+            for (int c = tid; c < (int)(box_bytes / 16u); c += kPfThreads) {
+                const uint4 q = s16[c];
+                nz |= (int)((q.x | q.y | q.z | q.w) != 0u);
+            }
+            if (!__syncthreads_or(nz)) {
+                float* outs[3] = {A.ao, A.opacity, A.gauss};
+                const float vals[3] = {ao_empty, A.opacity ? oplut[0] : 0.0f, 0.0f};
+#pragma unroll
+                for (int o = 0; o < 3; ++o) {
+                    float* out = outs[o];
+                    if (!out) continue;
+                    const bool vec = (reinterpret_cast<uintptr_t>(out) & 15u) == 0u;
+                    const float4 v4 = make_float4(vals[o], vals[o], vals[o], vals[o]);
+                    for (int q = tid; q < (kPfTX / 4) * kPfTY * kPfTZ; q += kPfThreads) {
+                        const int X = x0 + 4 * (q % (kPfTX / 4)), Y = y0 + (q / (kPfTX / 4)) % kPfTY, Z = z0 + q / ((kPfTX / 4) * kPfTY);
+                        if (Y >= A.H || Z >= A.D || X >= A.W) continue;
+                        float* dst = out + ((size_t)X + (size_t)Y * A.W + (size_t)Z * A.W * A.H);
+                        if (vec && X + 3 < A.W) __stcs(reinterpret_cast<float4*>(dst), v4);
+                        else for (int e = 0; e < 4 && X + e < A.W; ++e) __stcs(dst + e, vals[o]);
+                    }
+                }
+                continue;
+            }
+        }
 
         // ---- u8 rows -> float rows (+ which rows hold anything) --------------------------------------------
         int mine = 0;
         constexpr int kParts = kPfBX / 16;
-        for (int c = tid; c < kParts * BY * BZ; c += kPfThreads) {
+        const bool need_ftile = A.ao != nullptr || A.gauss != nullptr;           // opacity reads the staged bytes directly
+        for (int c = tid; need_ftile && c < kParts * BY * BZ; c += kPfThreads) {
             const int row = c / kParts, part = c - kParts * row;
             const int f0 = part * 16 - (kPfLead - h);                        // float-tile x of this chunk's first byte
             if (f0 + 16 <= 0 || f0 >= FX) continue;                          // chunk entirely outside the used span
@@ -247,8 +281,6 @@ k_prefilter_tiled(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         const int tile_any = __syncthreads_or(mine);
 
         // ---- one output row (32 voxels along x) per warp-iteration ---------------------------------------------
-        int x0, y0, z0;
-        tile_origin(tile, x0, y0, z0);
         for (int rr = warp; rr < kPfTY * kPfTZ; rr += kPfThreads / 32) {
             const int jy = rr % kPfTY, kz = rr / kPfTY;
             const int X = x0 + lane, Y = y0 + jy, Z = z0 + kz;
@@ -308,6 +340,8 @@ struct AdsmArgs {
     int W, H, D;
     float ox, oy, oz, sx, sy, sz, lx, ly, lz;
     float vsx, vsy, vsz;                 // size / resolution
+    const uint32_t* occ;                 // coarse occupancy bits (k_adsm_occupancy), or nullptr
+    int occ_nx32, occ_ny, occ_nz;        // words per row, rows, slices
     const float* t_table;                // the accumulated t sequence (t < 1)
     uint32_t n_t;
     float step_size, thickness, base;    // 1 / steps, thickness, 1 - strand_alpha
@@ -315,6 +349,26 @@ struct AdsmArgs {
 };
 
 constexpr int kAdsmThreads = 256;
+
+// Coarse occupancy for empty-space skipping.  A LINEAR sample whose lower texel is (x0, y0, z0), x0 in [-1, W-1],
+// reads texels x0 and x0 + 1 per axis; cell c = (x0 + 1) >> 2 therefore covers texels [4c - 1, 4c + 3].  Bit
+// (cx, cy, cz) is set when any texel of that 5 x 5 x 5 block is non-zero: a clear bit proves the sample is exactly
+// 0.0f (all eight texels zero), and adding +0.0f leaves the strand sum unchanged, so skipping it is exact.
+__global__ void __launch_bounds__(256)
+k_adsm_occupancy(const uint8_t* __restrict__ dens, int W, int H, int D, int nx32, int ny, int nz, uint32_t* __restrict__ occ) {
+    const uint64_t n = (uint64_t)nx32 * 32u * ny * nz;
+    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (uint64_t)gridDim.x * blockDim.x) {
+        const int cx = (int)(c % (uint64_t)(nx32 * 32)), cy = (int)((c / (uint64_t)(nx32 * 32)) % (uint64_t)ny), cz = (int)(c / ((uint64_t)nx32 * 32u * ny));
+        uint32_t any = 0;
+        for (int z = max(4 * cz - 1, 0); z <= min(4 * cz + 3, D - 1); ++z)
+            for (int y = max(4 * cy - 1, 0); y <= min(4 * cy + 3, H - 1); ++y) {
+                const uint8_t* row = dens + (size_t)y * W + (size_t)z * W * H;
+                for (int x = max(4 * cx - 1, 0); x <= min(4 * cx + 3, W - 1); ++x) any |= __ldg(row + x);
+            }
+        const uint32_t bits = __ballot_sync(0xFFFFFFFFu, any != 0u);      // 32 consecutive cx = one word (n is a multiple of 32)
+        if ((threadIdx.x & 31) == 0) occ[c >> 5] = bits;
+    }
+}
 
 __global__ void __launch_bounds__(kAdsmThreads)
 k_adsm(const __grid_constant__ AdsmArgs A) {
@@ -371,6 +425,10 @@ k_adsm(const __grid_constant__ AdsmArgs A) {
         const float fx0 = floorf(cx), fy0 = floorf(cy), fz0 = floorf(cz);
         if (!(fx0 >= -1.0f && fx0 < resx && fy0 >= -1.0f && fy0 < resy && fz0 >= -1.0f && fz0 < resz)) continue;   // all border: +0
         const int x0 = (int)fx0, y0 = (int)fy0, z0 = (int)fz0;
+        if (A.occ) {                                                 // empty neighbourhood: the sample is exactly +0
+            const int ccx = (x0 + 1) >> 2, ccy = (y0 + 1) >> 2, ccz = (z0 + 1) >> 2;
+            if (!((__ldg(A.occ + ((size_t)ccz * A.occ_ny + ccy) * A.occ_nx32 + (ccx >> 5)) >> (ccx & 31)) & 1u)) continue;
+        }
         const float fx = __fsub_rn(cx, fx0), fy = __fsub_rn(cy, fy0), fz = __fsub_rn(cz, fz0);
         const float wx0 = __fsub_rn(1.0f, fx), wy0 = __fsub_rn(1.0f, fy), wz0 = __fsub_rn(1.0f, fz);
         const bool xin0 = x0 >= 0, xin1 = x0 + 1 < A.W;

@@ -99,65 +99,6 @@ k_repair_packed(const __grid_constant__ Batch B, uint32_t* __restrict__ scratch)
 }
 
 // ---------------------------------------------------------------------------
-// PACKED8 red mode: the rare recount, one persistent cooperative kernel.  Instances whose byte sum (stats[1],
-// k_verify_packed_batch) differs from the number of samples the walk added (stats[0]) had a byte carry, i.e. a
-// voxel with more than 255 hits: they are re-voxelised with u32 counters on the shared scratch grid and
-// rewritten as min(count, 255)  (hair_style.cc:322: `if (d != 255) d += 1`).  With no mismatch (hair at any
-// useful resolution) every CTA returns after comparing n pairs of counters.
-// ---------------------------------------------------------------------------
-template <bool VERTICES>
-__global__ void __launch_bounds__(kWalkThreads)
-k_finish_packed(const __grid_constant__ Batch B, uint32_t* __restrict__ scratch) {
-    const uint32_t n_inst = B.n;
-    const InstanceDev* inst = B.inst;
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t nthreads = gridDim.x * blockDim.x;
-    // common case first: every byte sum (k_verify_packed_batch) equals its sample count -> out
-    int any = 0;
-    for (uint32_t k = threadIdx.x; k < n_inst; k += blockDim.x) any |= (__ldcg(inst[k].stats) != __ldcg(inst[k].stats + 1));
-    if (!__syncthreads_or(any)) return;                        // same answer in every CTA
-    cg::grid_group grid = cg::this_grid();
-    for (uint32_t k = 0; k < n_inst; ++k) {
-        const InstanceDev& I = inst[k];
-        if (__ldcg(I.stats) == __ldcg(I.stats + 1)) continue;      // uniform across the grid: the common case
-        const GridParams g = I.grid;
-        const uint32_t n16 = g.n_voxels >> 4;
-        uint4* counts4 = reinterpret_cast<uint4*>(scratch);
-        for (uint32_t i = tid; i < 4u * n16; i += nthreads) counts4[i] = make_uint4(0, 0, 0, 0);
-        grid.sync();
-        SinkCount32 sink{scratch};
-        if (VERTICES) {
-            for (uint32_t i = tid; i < I.n_vertices; i += nthreads) {
-                const float* v = I.vertices + 3ull * i;
-                uint32_t idx;
-                if (voxel_index(g, to_voxel_space(__ldg(v), g.ox, g.vsx, g.rvx), to_voxel_space(__ldg(v + 1), g.oy, g.vsy, g.rvy),
-                                to_voxel_space(__ldg(v + 2), g.oz, g.vsz, g.rvz), idx))
-                    sink.put<0>(idx);
-            }
-        } else if (I.indices) {
-            for (uint64_t s = tid; s < I.n_segments; s += nthreads) {
-                const uint2 pr = __ldg(reinterpret_cast<const uint2*>(I.indices) + s);
-                const float* a = I.vertices + 3ull * pr.x;
-                const float* b = I.vertices + 3ull * pr.y;
-                walk_segment(g, __ldg(a), __ldg(a + 1), __ldg(a + 2), __ldg(b), __ldg(b + 1), __ldg(b + 2), sink);
-            }
-        } else {
-            const uint32_t vps = I.segs_per_strand + 1u;
-            for (uint32_t v = tid; v + 1u < I.n_vertices; v += nthreads) {
-                if (v % vps == vps - 1u) continue;             // last vertex of a strand starts no segment
-                const float* a = I.vertices + 3ull * v;
-                walk_segment(g, __ldg(a), __ldg(a + 1), __ldg(a + 2), __ldg(a + 3), __ldg(a + 4), __ldg(a + 5), sink);
-            }
-        }
-        grid.sync();
-        uint4* out4 = reinterpret_cast<uint4*>(I.densities);
-        for (uint32_t i = tid; i < n16; i += nthreads)
-            out4[i] = make_uint4(clamp4(counts4[4 * i]), clamp4(counts4[4 * i + 1]), clamp4(counts4[4 * i + 2]), clamp4(counts4[4 * i + 3]));
-        grid.sync();                                           // scratch is reused by the next such instance
-    }
-}
-
-// ---------------------------------------------------------------------------
 // Context
 // ---------------------------------------------------------------------------
 struct DevBuf {
@@ -184,12 +125,7 @@ struct vkhr_b200_ctx {
     Slot slots[kSlots];
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     int repair_blocks[2] = {0, 0};
-    int finish_blocks[2] = {0, 0};
-    bool no_int_index = false;    // A/B only
-    bool no_pipeline = false;     // A/B only
-    uint32_t alias_volumes = 0;   // A/B only: every instance writes into one of the first N volumes (L2-warm probe; wrong results)
-    uint32_t chunk_override = 0;  // A/B only: instances per clear/walk/finish group
-    int walk_variant = 1;         // PACKED8 walk: 1 = atom + overflow bitmap (default), 2 = red + byte-sum verification, 5 = round-1 v5 kernel (A/B only)
+    DevBuf adsm_occ;              // ADSM coarse occupancy bits
     DevBuf adsm_table;            // the ADSM march's accumulated t sequence for `adsm_steps`
     float adsm_steps = 0.0f;
     uint32_t adsm_n = 0;
@@ -370,7 +306,7 @@ BatchPlan fill_batch(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool verti
         I.n_vertices = jobs[k].n_vertices;
         I.segs_per_strand = jobs[k].segs;
         I.grid = jobs[k].grid;
-        I.densities = (ctx->alias_volumes && n > 1) ? jobs[k % ctx->alias_volumes].d_dens : jobs[k].d_dens;   // A/B only
+        I.densities = jobs[k].d_dens;
         I.kind = kind;
         if (kind == WK_UNIFORM) {
             // warp-tiles of kTileStride vertices, kTilesPerWarp per warp, kWarpsPerBlock warps per CTA
@@ -398,20 +334,8 @@ int launch_walk(vkhr_b200_ctx* ctx, const BatchPlan& plan, bool exact, uint32_t 
         const dim3 grid(tiles[WK_UNIFORM], count);
         bool small = !exact;                                   // int32 index: every instance on a small grid
         for (uint32_t k = first; k < first + count; ++k) small = small && B.inst[k].grid.small_grid;
-        if (MODE == 1 && ctx->walk_variant == 5) {             // round-1 kernel, kept for A/B measurements
-            if (exact) k_walk_uniform_v5<1, 1><<<grid, kWalkThreads, 0, s>>>(B, first);
-            else       k_walk_uniform_v5<1, 0><<<grid, kWalkThreads, 0, s>>>(B, first);
-        }
-        else if (MODE == 2 && ctx->walk_variant >= 10) {       // measurement-only sinks (results are NOT a voxelisation)
-            switch (ctx->walk_variant) {
-                case 10: k_walk_uniform<10, 2><<<grid, kWalkThreads, 0, s>>>(B, first); break;
-                case 11: k_walk_uniform<11, 2><<<grid, kWalkThreads, 0, s>>>(B, first); break;
-                case 12: k_walk_uniform<12, 2><<<grid, kWalkThreads, 0, s>>>(B, first); break;
-                default: k_walk_uniform<13, 2><<<grid, kWalkThreads, 0, s>>>(B, first); break;
-            }
-        }
-        else if (exact) k_walk_uniform<MODE, 1><<<grid, kWalkThreads, 0, s>>>(B, first);
-        else if (small && !ctx->no_int_index) k_walk_uniform<MODE, 2><<<grid, kWalkThreads, 0, s>>>(B, first);
+        if (exact)      k_walk_uniform<MODE, 1><<<grid, kWalkThreads, 0, s>>>(B, first);
+        else if (small) k_walk_uniform<MODE, 2><<<grid, kWalkThreads, 0, s>>>(B, first);
         else            k_walk_uniform<MODE, 0><<<grid, kWalkThreads, 0, s>>>(B, first);
         ctx->launches++;
     }
@@ -446,21 +370,6 @@ int launch_repair(vkhr_b200_ctx* ctx, uint32_t* scratch, cudaStream_t s) {
     return VKHR_B200_OK;
 }
 
-template <bool VERTICES>
-int launch_finish(vkhr_b200_ctx* ctx, uint32_t* scratch, cudaStream_t s) {
-    int& blocks = ctx->finish_blocks[VERTICES ? 1 : 0];
-    if (blocks == 0) {
-        int per_sm = 0;
-        CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_finish_packed<VERTICES>, kWalkThreads, 0));
-        if (per_sm < 1) return fail(ctx, VKHR_B200_ERR_CUDA, "finish kernel does not fit on an SM");
-        blocks = per_sm * ctx->sm_count;
-    }
-    void* args[] = {(void*)&ctx->batch, (void*)&scratch};
-    CU_CHECK(ctx, cudaLaunchCooperativeKernel((void*)k_finish_packed<VERTICES>, dim3(blocks), dim3(kWalkThreads), args, 0, s));
-    ctx->launches++;
-    return VKHR_B200_OK;
-}
-
 // The voxelisation of `n` instances at one resolution into their u8 grids, kMaxBatch at a time.
 int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_mode, uint32_t flags, cudaStream_t s) {
     if (n == 0) return VKHR_B200_OK;
@@ -473,11 +382,9 @@ int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_
         return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "PACKED8 needs W*H*D % 16 == 0 and 16-byte aligned densities");
 
     if (packed) {
-        // scratch: per instance 16 bytes of stats (red mode) or an overflow bitmap + flag (atom mode), and one
-        // shared u32 recount grid
-        const bool red = ctx->walk_variant == 2 || ctx->walk_variant >= 10;
-        const size_t bm_words = red ? 4 : (((nv / 4 + 31) / 32 + 3) & ~size_t(3));   // red: 32 bytes of stats per instance
-        const uint32_t chunk = std::min<uint32_t>(n, std::min<uint32_t>(kMaxBatch, ctx->chunk_override ? ctx->chunk_override : kMaxBatch));
+        // scratch: per-instance overflow bitmap + flag, one shared u32 recount grid
+        const size_t bm_words = ((nv / 4 + 31) / 32 + 3) & ~size_t(3);
+        const uint32_t chunk = std::min<uint32_t>(n, kMaxBatch);
         RET_IF(reserve(ctx, ctx->bitmap, (size_t)chunk * (bm_words + 4) * 4));
         RET_IF(reserve(ctx, ctx->counts, nv * 4));
         ctx->counts_clean_bytes = 0;                   // the recount may leave entries behind
@@ -486,54 +393,24 @@ int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_
             const uint32_t m = std::min(chunk, n - first);
             const BatchPlan plan = fill_batch(ctx, jobs + first, m, vertices_mode);
             for (uint32_t k = 0; k < m; ++k) {
-                uint32_t* blk = base + (size_t)k * (bm_words + 4);          // 16-byte aligned
-                ctx->batch.inst[k].stats = red ? reinterpret_cast<unsigned long long*>(blk) : nullptr;
-                ctx->batch.inst[k].ovf_flag = red ? nullptr : blk;
-                ctx->batch.inst[k].ovf_bitmap = red ? nullptr : blk + 4;
+                ctx->batch.inst[k].ovf_flag = base + (size_t)k * (bm_words + 4);
+                ctx->batch.inst[k].ovf_bitmap = base + (size_t)k * (bm_words + 4) + 4;
                 ctx->batch.inst[k].counts = static_cast<uint32_t*>(ctx->counts.p);
             }
             const unsigned gx = stride_blocks(ctx, nv / 16, 256, m >= 8 ? 2 : 8);
-            // pipelined crowd walk (kernels.cuh, k_walk_pipeline): uniform strands, red mode, more than one instance
-            const bool pipeline = red && ctx->walk_variant == 2 && !ctx->no_pipeline && m > 1 && plan.max_tiles[WK_UNIFORM] &&
-                                  !plan.max_tiles[WK_INDEXED] && !plan.max_tiles[WK_SPLAT];
-            ctx->batch.ticket = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->small.p) + 128);
-            if (pipeline) {
-                bool small = !exact;
-                for (uint32_t k = 0; k < m; ++k) small = small && ctx->batch.inst[k].grid.small_grid;
-                {
-                    PhaseMark mk(ctx, s, PH_CLEAR);
-                    k_pipeline_prologue<<<stride_blocks(ctx, nv / 16, 256, 8), 256, 0, s>>>(ctx->batch, 0u, m);
-                    ctx->launches++;
-                }
-                {
-                    PhaseMark mk(ctx, s, PH_WALK);
-                    const dim3 grid(plan.max_tiles[WK_UNIFORM], m);
-                    if (exact)      k_walk_pipeline<1><<<grid, kWalkThreads, 0, s>>>(ctx->batch, 0u, m);
-                    else if (small) k_walk_pipeline<2><<<grid, kWalkThreads, 0, s>>>(ctx->batch, 0u, m);
-                    else            k_walk_pipeline<0><<<grid, kWalkThreads, 0, s>>>(ctx->batch, 0u, m);
-                    ctx->launches++;
-                }
-            } else {
-                {
-                    PhaseMark mk(ctx, s, PH_CLEAR);
-                    k_clear_packed_batch<<<dim3(gx, m), 256, 0, s>>>(ctx->batch, 0u);
-                    ctx->launches++;
-                }
-                if (plan.max_tiles[0] + plan.max_tiles[1] + plan.max_tiles[2]) {
-                    PhaseMark mk(ctx, s, PH_WALK);
-                    if (red) RET_IF(launch_walk<2>(ctx, plan, exact, 0, m, s));
-                    else     RET_IF(launch_walk<1>(ctx, plan, exact, 0, m, s));
-                }
+            {
+                PhaseMark mk(ctx, s, PH_CLEAR);
+                k_clear_packed_batch<<<dim3(gx, m), 256, 0, s>>>(ctx->batch, 0u);
+                ctx->launches++;
             }
             if (plan.max_tiles[0] + plan.max_tiles[1] + plan.max_tiles[2]) {
-                PhaseMark mk(ctx, s, PH_FINISH);
-                uint32_t* scratch = static_cast<uint32_t*>(ctx->counts.p);
-                if (red) {
-                    k_verify_packed_batch<<<dim3(gx, m), 256, 0, s>>>(ctx->batch, 0u);
-                    ctx->launches++;
-                    if (vertices_mode) RET_IF(launch_finish<true>(ctx, scratch, s)); else RET_IF(launch_finish<false>(ctx, scratch, s));
+                {
+                    PhaseMark mk(ctx, s, PH_WALK);
+                    RET_IF(launch_walk<1>(ctx, plan, exact, 0, m, s));
                 }
-                else { if (vertices_mode) RET_IF(launch_repair<true>(ctx, scratch, s)); else RET_IF(launch_repair<false>(ctx, scratch, s)); }
+                PhaseMark mk(ctx, s, PH_FINISH);
+                if (vertices_mode) RET_IF(launch_repair<true>(ctx, static_cast<uint32_t*>(ctx->counts.p), s));
+                else               RET_IF(launch_repair<false>(ctx, static_cast<uint32_t*>(ctx->counts.p), s));
             }
             CU_CHECK(ctx, cudaGetLastError());
         }
@@ -686,20 +563,6 @@ int vkhr_b200_create(int device, vkhr_b200_ctx** out) {
         delete ctx;
         return VKHR_B200_ERR_OUT_OF_MEMORY;
     }
-    // measurement switches (A/B runs of tools/*.sh); the default is the shipped configuration
-    if (const char* v = std::getenv("VKHR_B200_WALK")) {
-        if (!std::strcmp(v, "atom")) ctx->walk_variant = 1;
-        else if (!std::strcmp(v, "v5")) ctx->walk_variant = 5;
-        else if (!std::strcmp(v, "red")) ctx->walk_variant = 2;
-        else if (!std::strcmp(v, "null")) ctx->walk_variant = 10;
-        else if (!std::strcmp(v, "sector")) ctx->walk_variant = 11;
-        else if (!std::strcmp(v, "line")) ctx->walk_variant = 12;
-        else if (!std::strcmp(v, "lines8")) ctx->walk_variant = 13;
-    }
-    if (const char* v = std::getenv("VKHR_B200_NO_PIPELINE")) ctx->no_pipeline = (v[0] == '1');
-    if (const char* v = std::getenv("VKHR_B200_ALIAS")) ctx->alias_volumes = (uint32_t)std::atoi(v);
-    if (const char* v = std::getenv("VKHR_B200_CHUNK")) ctx->chunk_override = (uint32_t)std::atoi(v);
-    if (const char* v = std::getenv("VKHR_B200_NO_INT_INDEX")) ctx->no_int_index = (v[0] == '1');
     *out = ctx;
     return VKHR_B200_OK;
 }
@@ -708,7 +571,7 @@ void vkhr_b200_destroy(vkhr_b200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->counts, &ctx->bitmap, &ctx->small, &ctx->tacc, &ctx->adsm_table, &ctx->st_vertices,
+    DevBuf* bufs[] = {&ctx->counts, &ctx->bitmap, &ctx->small, &ctx->tacc, &ctx->adsm_table, &ctx->adsm_occ, &ctx->st_vertices,
                       &ctx->st_indices, &ctx->st_tangents, &ctx->st_dens, &ctx->st_tang_out};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (auto& sl : ctx->slots) {
@@ -1251,6 +1114,110 @@ int vkhr_b200_prefilter(vkhr_b200_ctx* ctx, const uint8_t* densities, uint32_t W
     return VKHR_B200_OK;
 }
 
+// ---- .hair bytes -> volume (HairStyle::load + SceneGraph::add_style + voxelize_segments) -------------------
+// File layout: SURVEY Appendix C / include/vkhr/scene_graph/hair_style.hh:147-174, src/.../hair_style.cc:24-47.
+int vkhr_b200_voxelize_hair(vkhr_b200_ctx* ctx, const void* hair_bytes, size_t n_bytes, uint32_t W, uint32_t H, uint32_t D,
+                            uint32_t flags, uint8_t* densities_out, int8_t* tangents_out, float aabb_out[6]) {
+    RET_IF(bind(ctx));
+    if (!hair_bytes || !densities_out) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null file bytes or densities");
+    const unsigned char* f = static_cast<const unsigned char*>(hair_bytes);
+    if (n_bytes < 128 || std::memcmp(f, "HAIR", 4) != 0) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "not a .hair file (signature)");
+    uint32_t strands, nverts, bits, dsegs;
+    float bbox[6];
+    std::memcpy(&strands, f + 4, 4); std::memcpy(&nverts, f + 8, 4); std::memcpy(&bits, f + 12, 4); std::memcpy(&dsegs, f + 16, 4);
+    std::memcpy(bbox, f + 104, 24);                            // bounding_box_min[3], bounding_box_max[3]
+    if (!(bits & 2u) || nverts == 0) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, ".hair file without vertices");
+    // array offsets, in file order: segments, vertices, thickness, transparency, color, tangents, indices
+    size_t off = 128, o_seg = 0, o_vert = 0, o_tan = 0, o_idx = 0;
+    if (bits & 1u) { o_seg = off; off += (size_t)strands * 2; }
+    o_vert = off; off += (size_t)nverts * 12;
+    if (bits & 4u) off += (size_t)nverts * 4;
+    if (bits & 8u) off += (size_t)nverts * 4;
+    if (bits & 16u) off += (size_t)nverts * 12;
+    if (bits & 32u) { o_tan = off; off += (size_t)nverts * 12; }
+    if (strands > nverts) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, ".hair header: more strands than vertices");
+    const uint64_t n_file_indices = 2ull * (nverts - strands);  // read_indices sizes the array from get_segment_count()
+    if (bits & 64u) { o_idx = off; off += (size_t)n_file_indices * 4; }
+    if (off > n_bytes) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, ".hair file is shorter than its header says");
+
+    cudaStream_t s = ctx->stream;
+    RET_IF(stage_in(ctx, ctx->st_vertices, f + o_vert, (size_t)nverts * 12));
+    const float* d_vertices = static_cast<const float*>(ctx->st_vertices.p);
+    // bounding box: the header's (get_bounding_box, hair_style.cc:236-255), else generate_bounding_box (:215-234)
+    if (!(bits & 128u)) {
+        float* d_box = reinterpret_cast<float*>(static_cast<char*>(ctx->small.p) + 64);
+        RET_IF(vkhr_b200_generate_bounding_box_dev(ctx, d_vertices, nverts, d_box, s));
+        CU_CHECK(ctx, cudaMemcpyAsync(bbox, d_box, 24, cudaMemcpyDeviceToHost, s));
+        CU_CHECK(ctx, cudaStreamSynchronize(s));
+    }
+    const float origin[3] = {bbox[0], bbox[1], bbox[2]};
+    const float size[3] = {bbox[3] - bbox[0], bbox[4] - bbox[1], bbox[5] - bbox[2]};
+    if (aabb_out) { std::memcpy(aabb_out, origin, 12); std::memcpy(aabb_out + 3, size, 12); }
+    // indices: the file's, else generate_indices (hair_style.cc:196-213) from segments[] or default_segment_count
+    const uint32_t* d_indices = nullptr;
+    uint64_t n_indices = 0;
+    uint32_t segs = 0;
+    if (bits & 64u) {
+        RET_IF(stage_in(ctx, ctx->st_indices, f + o_idx, (size_t)n_file_indices * 4));
+        d_indices = static_cast<const uint32_t*>(ctx->st_indices.p);
+        n_indices = n_file_indices;
+    } else if (bits & 1u) {
+        std::vector<uint32_t> prefix((size_t)strands + 1);
+        uint64_t total = 0;
+        bool uniform = strands > 0;
+        uint16_t first_len = 0;
+        if (strands) std::memcpy(&first_len, f + o_seg, 2);
+        for (uint32_t k = 0; k < strands; ++k) {
+            uint16_t len;
+            std::memcpy(&len, f + o_seg + (size_t)k * 2, 2);
+            prefix[k] = (uint32_t)total;
+            total += len;
+            uniform = uniform && len == first_len;
+        }
+        prefix[strands] = (uint32_t)total;
+        if (total + strands != nverts) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, ".hair segments[] do not add up to the vertex count");
+        if (uniform && first_len > 0) segs = first_len;           // equal strands: no index buffer needed
+        else if (total > 0) {
+            RET_IF(reserve(ctx, ctx->st_tangents, prefix.size() * 4));         // (free at this point; tangents are staged later)
+            CU_CHECK(ctx, cudaMemcpyAsync(ctx->st_tangents.p, prefix.data(), prefix.size() * 4, cudaMemcpyHostToDevice, s));
+            RET_IF(reserve(ctx, ctx->st_indices, (size_t)total * 8));
+            k_generate_indices<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(static_cast<const uint32_t*>(ctx->st_tangents.p), strands,
+                                                                                (uint32_t)total, static_cast<uint2*>(ctx->st_indices.p));
+            ctx->launches++;
+            CU_CHECK(ctx, cudaGetLastError());
+            CU_CHECK(ctx, cudaStreamSynchronize(s));                            // `prefix` dies here; st_tangents is reused below
+            d_indices = static_cast<const uint32_t*>(ctx->st_indices.p);
+            n_indices = 2 * total;
+        }
+    } else {
+        if (dsegs == 0 || nverts % (dsegs + 1) != 0 || nverts / (dsegs + 1) != strands)
+            return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, ".hair header: strand_count * (default_segment_count + 1) != vertex_count");
+        segs = dsegs;
+    }
+    GridParams g;
+    RET_IF(make_grid(ctx, origin, size, W, H, D, flags, g));
+    const size_t nv = g.n_voxels;
+    RET_IF(reserve(ctx, ctx->st_dens, nv));
+    if (tangents_out) RET_IF(reserve(ctx, ctx->st_tang_out, nv * 4));
+    if (!d_indices && segs == 0) {                                              // no segments at all: empty volume
+        CU_CHECK(ctx, cudaMemsetAsync(ctx->st_dens.p, 0, nv, s));
+        if (tangents_out) CU_CHECK(ctx, cudaMemsetAsync(ctx->st_tang_out.p, 0, nv * 4, s));
+    } else {
+        const float* d_tangents = nullptr;                                      // the file's tangents, else derived on the fly
+        if (tangents_out && (bits & 32u)) {
+            RET_IF(stage_in(ctx, ctx->st_tangents, f + o_tan, (size_t)nverts * 12));
+            d_tangents = static_cast<const float*>(ctx->st_tangents.p);
+        }
+        RET_IF(vkhr_b200_voxelize_segments_dev(ctx, d_vertices, nverts, d_indices, n_indices, segs, d_tangents, origin, size, W, H, D, flags,
+                                               static_cast<uint8_t*>(ctx->st_dens.p),
+                                               tangents_out ? static_cast<int8_t*>(ctx->st_tang_out.p) : nullptr, s));
+    }
+    CU_CHECK(ctx, cudaMemcpyAsync(densities_out, ctx->st_dens.p, nv, cudaMemcpyDeviceToHost, s));
+    if (tangents_out) CU_CHECK(ctx, cudaMemcpyAsync(tangents_out, ctx->st_tang_out.p, nv * 4, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(ctx, cudaStreamSynchronize(s));
+    return VKHR_B200_OK;
+}
+
 // ---- volumetric ADSM transmittance volume (approximate_deep_shadows.glsl:24-36 at every voxel centre) ----
 int vkhr_b200_adsm_dev(vkhr_b200_ctx* ctx, const uint8_t* d_densities, uint32_t W, uint32_t H, uint32_t D,
                        const float origin[3], const float size[3], const vkhr_b200_adsm_params* P, float* d_out, void* stream) {
@@ -1286,6 +1253,14 @@ int vkhr_b200_adsm_dev(vkhr_b200_ctx* ctx, const uint8_t* d_densities, uint32_t 
     A.step_size = 1.0f / P->steps; A.thickness = P->thickness; A.base = 1.0f - P->strand_alpha;
     A.out = d_out;
     PhaseMark mk(ctx, s, PH_PREFILTER);
+    // coarse occupancy bits for empty-space skipping (cells of 4 texels; x0 + 1 ranges over [0, W])
+    A.occ_nx32 = (int)((W / 4 + 1 + 31) / 32); A.occ_ny = (int)(H / 4 + 1); A.occ_nz = (int)(D / 4 + 1);
+    const size_t occ_words = (size_t)A.occ_nx32 * A.occ_ny * A.occ_nz;
+    RET_IF(reserve(ctx, ctx->adsm_occ, occ_words * 4));
+    A.occ = static_cast<const uint32_t*>(ctx->adsm_occ.p);
+    k_adsm_occupancy<<<stride_blocks(ctx, occ_words * 32, 256, 16), 256, 0, s>>>(d_densities, (int)W, (int)H, (int)D, A.occ_nx32, A.occ_ny, A.occ_nz,
+                                                                                 static_cast<uint32_t*>(ctx->adsm_occ.p));
+    ctx->launches++;
     k_adsm<<<(unsigned)((n + kAdsmThreads - 1) / kAdsmThreads), kAdsmThreads, 0, s>>>(A);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());

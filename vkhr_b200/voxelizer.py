@@ -196,6 +196,18 @@ class Voxelizer:
                                                     _p(out.get("ao")), _p(out.get("opacity")), _p(out.get("gauss"))))
         return out
 
+    def voxelize_hair(self, hair_bytes, W, H, D, flags: int = 0, want_tangents: bool = False):
+        """``.hair`` file image -> (densities, tangents | None, aabb_origin, aabb_size): HairStyle::load +
+        SceneGraph::add_style's missing-field generation + voxelize_segments over get_bounding_box()."""
+        buf = np.frombuffer(bytes(hair_bytes), dtype=np.uint8)
+        dens = np.empty(int(W) * int(H) * int(D), dtype=np.uint8)
+        tang = np.empty((dens.size, 4), dtype=np.int8) if want_tangents else None
+        box = (C.c_float * 6)()
+        capi.check(self._h, lib.vkhr_b200_voxelize_hair(self._h, _p(buf), buf.size, int(W), int(H), int(D), int(flags),
+                                                        _p(dens), _p(tang), box))
+        b = np.array(box, dtype=np.float32)
+        return dens, tang, b[:3].copy(), b[3:].copy()
+
     @staticmethod
     def adsm_params(light, steps=1024.0, strand_alpha=0.3, thickness=11.0) -> "capi.AdsmParams":
         """``vkhr_b200_adsm_params``: lights[0].origin + raycast_steps / hair_alpha / thickness (volume.frag:72-78)."""
