@@ -14,6 +14,7 @@
 #include <cstdint>
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include "walk.cuh"      // div_exact: the correctly rounded quotient without the division instruction sequence
 
 namespace vkhr_b200 {
 
@@ -340,6 +341,7 @@ struct AdsmArgs {
     int W, H, D;
     float ox, oy, oz, sx, sy, sz, lx, ly, lz;
     float vsx, vsy, vsz;                 // size / resolution
+    float rsx, rsy, rsz;                 // RN(1 / size) for div_exact, or 0 (plain IEEE division)
     const uint32_t* occ;                 // coarse occupancy bits (k_adsm_occupancy), or nullptr
     int occ_nx32, occ_ny, occ_nz;        // words per row, rows, slices
     const float* t_table;                // the accumulated t sequence (t < 1)
@@ -419,9 +421,9 @@ k_adsm(const __grid_constant__ AdsmArgs A) {
         const float t = __ldg(A.t_table + q);
         const float omt = __fsub_rn(1.0f, t);
         // point = mix(p, light, t); u = (point - origin) / size; c = u * res - 0.5
-        const float cx = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(__fadd_rn(__fmul_rn(px, omt), __fmul_rn(A.lx, t)), A.ox), A.sx), resx), 0.5f);
-        const float cy = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(__fadd_rn(__fmul_rn(py, omt), __fmul_rn(A.ly, t)), A.oy), A.sy), resy), 0.5f);
-        const float cz = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(__fadd_rn(__fmul_rn(pz, omt), __fmul_rn(A.lz, t)), A.oz), A.sz), resz), 0.5f);
+        const float cx = __fsub_rn(__fmul_rn(div_exact(__fsub_rn(__fadd_rn(__fmul_rn(px, omt), __fmul_rn(A.lx, t)), A.ox), A.sx, A.rsx), resx), 0.5f);
+        const float cy = __fsub_rn(__fmul_rn(div_exact(__fsub_rn(__fadd_rn(__fmul_rn(py, omt), __fmul_rn(A.ly, t)), A.oy), A.sy, A.rsy), resy), 0.5f);
+        const float cz = __fsub_rn(__fmul_rn(div_exact(__fsub_rn(__fadd_rn(__fmul_rn(pz, omt), __fmul_rn(A.lz, t)), A.oz), A.sz, A.rsz), resz), 0.5f);
         const float fx0 = floorf(cx), fy0 = floorf(cy), fz0 = floorf(cz);
         if (!(fx0 >= -1.0f && fx0 < resx && fy0 >= -1.0f && fy0 < resy && fz0 >= -1.0f && fz0 < resz)) continue;   // all border: +0
         const int x0 = (int)fx0, y0 = (int)fy0, z0 = (int)fz0;
@@ -431,23 +433,38 @@ k_adsm(const __grid_constant__ AdsmArgs A) {
         }
         const float fx = __fsub_rn(cx, fx0), fy = __fsub_rn(cy, fy0), fz = __fsub_rn(cz, fz0);
         const float wx0 = __fsub_rn(1.0f, fx), wy0 = __fsub_rn(1.0f, fy), wz0 = __fsub_rn(1.0f, fz);
-        const bool xin0 = x0 >= 0, xin1 = x0 + 1 < A.W;
         float zz[2];
+        if (x0 >= 0 && x0 + 1 < A.W && y0 >= 0 && y0 + 1 < A.H && z0 >= 0 && z0 + 1 < A.D) {
+            // interior footprint (almost every sample): eight loads off one base pointer, no per-texel bounds tests
+            const uint8_t* p = A.dens + ((size_t)z0 * sz + (size_t)y0 * sy + (size_t)x0);
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            float yy[2];
+            for (int c = 0; c < 2; ++c) {
+                float yy[2];
 #pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                const int y = y0 + b, z = z0 + c;
-                float t0 = 0.0f, t1 = 0.0f;
-                if (y >= 0 && y < A.H && z >= 0 && z < A.D) {
-                    const uint8_t* row = A.dens + (size_t)y * sy + (size_t)z * sz;
-                    if (xin0) t0 = s_tau[__ldg(row + x0)];
-                    if (xin1) t1 = s_tau[__ldg(row + x0 + 1)];
+                for (int b = 0; b < 2; ++b) {
+                    const uint8_t* row = p + (size_t)c * sz + (size_t)b * sy;
+                    yy[b] = __fadd_rn(__fmul_rn(s_tau[__ldg(row)], wx0), __fmul_rn(s_tau[__ldg(row + 1)], fx));
                 }
-                yy[b] = __fadd_rn(__fmul_rn(t0, wx0), __fmul_rn(t1, fx));
+                zz[c] = __fadd_rn(__fmul_rn(yy[0], wy0), __fmul_rn(yy[1], fy));
             }
-            zz[c] = __fadd_rn(__fmul_rn(yy[0], wy0), __fmul_rn(yy[1], fy));
+        } else {
+            const bool xin0 = x0 >= 0, xin1 = x0 + 1 < A.W;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                float yy[2];
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const int y = y0 + b, z = z0 + c;
+                    float t0 = 0.0f, t1 = 0.0f;
+                    if (y >= 0 && y < A.H && z >= 0 && z < A.D) {
+                        const uint8_t* row = A.dens + (size_t)y * sy + (size_t)z * sz;
+                        if (xin0) t0 = s_tau[__ldg(row + x0)];
+                        if (xin1) t1 = s_tau[__ldg(row + x0 + 1)];
+                    }
+                    yy[b] = __fadd_rn(__fmul_rn(t0, wx0), __fmul_rn(t1, fx));
+                }
+                zz[c] = __fadd_rn(__fmul_rn(yy[0], wy0), __fmul_rn(yy[1], fy));
+            }
         }
         const float s = __fadd_rn(__fmul_rn(zz[0], wz0), __fmul_rn(zz[1], fz));
         strands = __fadd_rn(strands, __fmul_rn(s, A.thickness));

@@ -1248,6 +1248,10 @@ int vkhr_b200_adsm_dev(vkhr_b200_ctx* ctx, const uint8_t* d_densities, uint32_t 
     A.sx = size[0]; A.sy = size[1]; A.sz = size[2];
     A.lx = P->light[0]; A.ly = P->light[1]; A.lz = P->light[2];
     A.vsx = size[0] / (float)W; A.vsy = size[1] / (float)H; A.vsz = size[2] / (float)D;
+    {   // RN(1 / size) when the FMA division of walk.cuh applies (size in [2^-40, 2^40]), else 0 = IEEE division
+        auto recip = [](float v) { return (v >= 9.094947e-13f && v <= 1.0995116e12f) ? 1.0f / v : 0.0f; };
+        A.rsx = recip(size[0]); A.rsy = recip(size[1]); A.rsz = recip(size[2]);
+    }
     A.t_table = static_cast<const float*>(ctx->adsm_table.p);
     A.n_t = ctx->adsm_n;
     A.step_size = 1.0f / P->steps; A.thickness = P->thickness; A.base = 1.0f - P->strand_alpha;
