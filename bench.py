@@ -37,6 +37,11 @@ if ROOT not in sys.path:
 import numpy as np
 
 METRIC = "strand segments voxelised per second"
+
+
+def _emit(line: str):          # replaced in main() by a writer that keeps library chatter off stdout
+    print(line, flush=True)
+
 UNIT = "M seg/s"
 
 
@@ -229,7 +234,7 @@ def run_reference(args, rank: int):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
 
 
 # --------------------------------------------------------------------------------------
@@ -241,6 +246,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "single process: unbound"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -349,7 +355,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         e2e = {"value": n_seg * I * world * ke / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": I * V * 12,
                "d2h_bytes_per_step": I * nvox, "steps": ke, "ms_per_step": dt / ke * 1e3,
                "api": "vkhr_b200_voxelize_segments_batch (host pointers, pinned; H2D / kernels / D2H of consecutive "
-                      "instances pipelined on three streams)"}
+                      "instances pipelined on three streams)", "host_affinity": numa}
         # the frame that came back over PCIe must equal the device-resident one
         frame()
         torch.cuda.synchronize()
@@ -423,9 +429,27 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "other_configs": others,
         }
-        print(json.dumps(line), flush=True)
+        _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bind_to_gpu_numa_node(index: int) -> str:
+    """Pin this process (and therefore its first-touch pinned host buffers) to the CPUs next to GPU `index`."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus near gpu {index}"
+    except Exception as e:  # noqa: BLE001
+        return f"unbound ({str(e)[:60]})"
+    return "unbound"
 
 
 def main():
@@ -442,6 +466,18 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29531"), __file__] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
+    # Libraries (NCCL prints its version banner) may write to stdout; the contract is ONE JSON line there.  Everything
+    # but the final line goes to stderr: fd 1 is pointed at fd 2 until the result is printed.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: str):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
+    globals()["_emit"] = emit
     run_ours(args, rank, local_rank, world)
 
 
