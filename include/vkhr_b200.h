@@ -215,6 +215,22 @@ VKHR_B200_API int vkhr_b200_count_vertices_dev(
     uint32_t W, uint32_t H, uint32_t D, uint32_t flags,
     uint32_t* d_counts_inout, void* stream);
 
+/* Multi-GPU combine on saturated u8 partials (each a complete voxelisation of one strand shard):
+ * out[i] = min(sum over the n_slabs consecutive arrays of slab_bytes bytes, 255).  Exact, because
+ * min(sum_r min(c_r, 255), 255) == min(sum_r c_r, 255) (hair_style.cc:322-325 only saturates). */
+VKHR_B200_API int vkhr_b200_saturating_sum_u8_dev(
+    vkhr_b200_ctx* ctx, const uint8_t* d_slabs, uint32_t n_slabs, uint64_t slab_bytes,
+    uint8_t* d_out, void* stream);
+
+/* The same combine fused with its exchange, over NVLink peer memory: d_partials[r] / d_outs[r] are rank r's
+ * partial and output volumes as mapped into THIS process (symmetric memory / cudaIpc / cuMem peer mappings, up to 16).
+ * The calling rank sums bytes [slab_offset, slab_offset + slab_bytes) of every partial with saturation and stores the
+ * result into that range of every output: reduce-scatter + clamp + all-gather in one kernel.  The caller orders it
+ * between two barriers of the group (all partials written before; all outputs written after). */
+VKHR_B200_API int vkhr_b200_combine_peer_u8_dev(
+    vkhr_b200_ctx* ctx, const void* const* d_partials, void* const* d_outs, uint32_t n_peers,
+    uint64_t slab_offset_bytes, uint64_t slab_bytes, void* stream);
+
 /* densities = min(counts, 255), optionally followed by normalize (flags). */
 VKHR_B200_API int vkhr_b200_clamp_counts_dev(
     vkhr_b200_ctx* ctx, const uint32_t* d_counts, uint64_t n_voxels, uint32_t flags,

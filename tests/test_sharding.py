@@ -59,13 +59,24 @@ def _worker(rank, world, port_no, res, results):
         def clamp_fn(counts, out, flags=0):
             out.copy_(torch.clamp(counts, max=255).to(torch.uint8))
 
-        sv = sharding.ShardedVoxelizer(None, None, count_fn=count_fn, clamp_fn=clamp_fn)
+        def partial_fn(mode, vertices, indices, segs, origin, size, W, H, D, out, flags):
+            vv = vertices.numpy().reshape(-1, 3)
+            if mode == "segments":
+                d = P.voxelize_segments(vv, P.generate_indices(vv.shape[0] // (segs + 1), segs), origin, size, W, H, D)
+            else:
+                d = P.voxelize_vertices(vv, origin, size, W, H, D)
+            out.copy_(torch.from_numpy(d))
+
+        def satsum_fn(slabs, out):
+            out.copy_(torch.clamp(slabs.to(torch.int32).sum(dim=0), max=255).to(torch.uint8))
+
+        sv = sharding.ShardedVoxelizer(None, None, count_fn=count_fn, clamp_fn=clamp_fn, partial_fn=partial_fn, satsum_fn=satsum_fn)
         lo_l, hi_l = P.generate_bounding_box(mine)
         lo, hi = sv.global_bounding_box(lo_l, hi_l)
         size = (hi - lo).astype(np.float32)
         t = torch.from_numpy(mine.reshape(-1))
         got = {}
-        for schedule in ("allreduce", "rs_ag"):
+        for schedule in ("allreduce", "rs_ag", "u8"):
             got["seg_" + schedule] = sv.voxelize_segments(t, None, s, lo, size, W, H, D, schedule=schedule).numpy().copy()
             got["ver_" + schedule] = sv.voxelize_vertices(t, lo, size, W, H, D, schedule=schedule).numpy().copy()
         results[rank] = (lo, hi, got, count)
@@ -92,6 +103,6 @@ def test_two_rank_gloo_equals_single_process(res):
     for r in range(world):
         rlo, rhi, got, _ = results[r]
         assert np.array_equal(rlo, lo) and np.array_equal(rhi, hi)
-        for schedule in ("allreduce", "rs_ag"):
+        for schedule in ("allreduce", "rs_ag", "u8"):
             assert np.array_equal(got["seg_" + schedule], want_seg), (r, schedule)
             assert np.array_equal(got["ver_" + schedule], want_ver), (r, schedule)

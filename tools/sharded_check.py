@@ -3,7 +3,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29544 \
         tools/sharded_check.py [--strands 1000000] [--segs 32] [--res 512] [--reps 10]
 Every rank voxelises its contiguous strand range into a partial u32 grid; the grids are combined with an NCCL
-integer collective (both schedules of vkhr_b200/sharding.py).  Rank 0 also voxelises the WHOLE set alone and the
+integer collective (all three schedules of vkhr_b200/sharding.py).  Rank 0 also voxelises the WHOLE set alone and the
 volumes must be byte-identical.  Prints one JSON object on rank 0.
 """
 import argparse
@@ -50,14 +50,14 @@ def main():
     res = {"world": world, "strands": n, "segments": n * s, "resolution": W}
     out = torch.empty(sharding.padded_voxels(W ** 3, world), dtype=torch.uint8, device=dev)
     vols = {}
-    for schedule in ("allreduce", "rs_ag"):
+    for schedule in ("allreduce", "rs_ag", "u8") + (("p2p",) if os.environ.get("VKHR_B200_P2P", "1") != "0" else ()):
         for _ in range(2):
-            sv.voxelize_segments(mine_t, None, s, lo, size, W, W, W, out=out, schedule=schedule)
+            sv.voxelize_segments(mine_t, None, s, lo, size, W, W, W, out=None if schedule == "p2p" else out, schedule=schedule)
         dist.barrier(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.reps):
-            vol = sv.voxelize_segments(mine_t, None, s, lo, size, W, W, W, out=out, schedule=schedule)
+            vol = sv.voxelize_segments(mine_t, None, s, lo, size, W, W, W, out=None if schedule == "p2p" else out, schedule=schedule)
         e1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1) / args.reps], device=dev)

@@ -522,6 +522,53 @@ k_clamp_counts(uint32_t* __restrict__ counts, uint64_t n, uint8_t* __restrict__ 
     }
 }
 
+// Multi-GPU combine on saturated u8 partials: out[i] = min(sum_r slab_r[i], 255).  Every partial is already
+// min(count_r, 255), and min(sum_r min(c_r, 255), 255) == min(sum_r c_r, 255), so the byte-wise saturating add
+// (`__vaddus4`, four voxels per instruction) is exact -- and the partials are 4x smaller than u32 counts on the wire.
+// slabs: n_slabs consecutive arrays of slab_bytes (a multiple of 16) each.
+__global__ void __launch_bounds__(256)
+k_saturating_sum_u8(const uint4* __restrict__ slabs, uint32_t n_slabs, uint64_t slab16, uint4* __restrict__ out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < slab16; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 acc = __ldcs(slabs + i);
+        for (uint32_t r = 1; r < n_slabs; ++r) {
+            const uint4 v = __ldcs(slabs + (uint64_t)r * slab16 + i);
+            acc.x = __vaddus4(acc.x, v.x); acc.y = __vaddus4(acc.y, v.y); acc.z = __vaddus4(acc.z, v.z); acc.w = __vaddus4(acc.w, v.w);
+        }
+        out[i] = acc;
+    }
+}
+
+// The same combine as ONE kernel over NVLink peer memory: every GPU owns a slab of the volume, reads that slab of
+// every peer's saturated u8 partial straight out of the peer's HBM (P2P loads), adds with saturation, and stores
+// the finished slab into every peer's output volume (P2P stores) -- reduce-scatter, clamp and all-gather without
+// an intermediate buffer or a second pass.  The caller brackets it with two device-side barriers of the
+// symmetric-memory group (partials complete before, outputs complete after).
+constexpr uint32_t kMaxPeers = 16;
+struct PeerPtrs {
+    const uint4* part[kMaxPeers];
+    uint4* out[kMaxPeers];
+    uint32_t n;
+};
+__global__ void __launch_bounds__(256)
+k_combine_peer_u8(const __grid_constant__ PeerPtrs P, uint64_t off16, uint64_t slab16) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < slab16; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 v[kMaxPeers];
+#pragma unroll
+        for (uint32_t r = 0; r < kMaxPeers; ++r)                 // all loads first: one NVLink round trip, not n
+            if (r < P.n) v[r] = __ldcg(P.part[r] + off16 + i);
+        uint4 acc = v[0];
+#pragma unroll
+        for (uint32_t r = 1; r < kMaxPeers; ++r)
+            if (r < P.n) {
+                acc.x = __vaddus4(acc.x, v[r].x); acc.y = __vaddus4(acc.y, v[r].y);
+                acc.z = __vaddus4(acc.z, v[r].z); acc.w = __vaddus4(acc.w, v[r].w);
+            }
+#pragma unroll
+        for (uint32_t r = 0; r < kMaxPeers; ++r)
+            if (r < P.n) __stcg(P.out[r] + off16 + i, acc);
+    }
+}
+
 // Same for an output grid that is not 16-byte aligned (a view into a caller's buffer): one voxel per thread.
 template <bool ZERO>
 __global__ void __launch_bounds__(256)

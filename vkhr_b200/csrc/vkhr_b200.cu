@@ -741,6 +741,43 @@ int vkhr_b200_clamp_counts_dev(vkhr_b200_ctx* ctx, const uint32_t* d_counts, uin
     return VKHR_B200_OK;
 }
 
+int vkhr_b200_saturating_sum_u8_dev(vkhr_b200_ctx* ctx, const uint8_t* d_slabs, uint32_t n_slabs, uint64_t slab_bytes,
+                                    uint8_t* d_out, void* stream) {
+    RET_IF(bind(ctx));
+    if (!d_slabs || !d_out || n_slabs == 0) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null pointer or no slabs");
+    if ((slab_bytes & 15u) || (reinterpret_cast<uintptr_t>(d_slabs) & 15u) || (reinterpret_cast<uintptr_t>(d_out) & 15u))
+        return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "slabs and output must be 16-byte aligned, slab_bytes a multiple of 16");
+    if (slab_bytes == 0) return VKHR_B200_OK;
+    cudaStream_t s = pick(ctx, stream);
+    k_saturating_sum_u8<<<stride_blocks(ctx, slab_bytes / 16, 256, 8), 256, 0, s>>>(
+        reinterpret_cast<const uint4*>(d_slabs), n_slabs, slab_bytes / 16, reinterpret_cast<uint4*>(d_out));
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return VKHR_B200_OK;
+}
+
+int vkhr_b200_combine_peer_u8_dev(vkhr_b200_ctx* ctx, const void* const* d_partials, void* const* d_outs, uint32_t n_peers,
+                                  uint64_t slab_offset_bytes, uint64_t slab_bytes, void* stream) {
+    RET_IF(bind(ctx));
+    if (!d_partials || !d_outs || n_peers == 0 || n_peers > kMaxPeers)
+        return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "peer pointer arrays: 1.." + std::to_string(kMaxPeers) + " peers");
+    if ((slab_offset_bytes & 15u) || (slab_bytes & 15u)) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "slab offset and size must be multiples of 16");
+    PeerPtrs P{};
+    P.n = n_peers;
+    for (uint32_t r = 0; r < n_peers; ++r) {
+        if (!d_partials[r] || !d_outs[r] || (reinterpret_cast<uintptr_t>(d_partials[r]) & 15u) || (reinterpret_cast<uintptr_t>(d_outs[r]) & 15u))
+            return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "peer buffers must be non-null and 16-byte aligned");
+        P.part[r] = static_cast<const uint4*>(d_partials[r]);
+        P.out[r] = static_cast<uint4*>(d_outs[r]);
+    }
+    if (slab_bytes == 0) return VKHR_B200_OK;
+    cudaStream_t s = pick(ctx, stream);
+    k_combine_peer_u8<<<stride_blocks(ctx, slab_bytes / 16, 256, 8), 256, 0, s>>>(P, slab_offset_bytes / 16, slab_bytes / 16);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return VKHR_B200_OK;
+}
+
 // ---- Volume operations ---------------------------------------------------------
 int vkhr_b200_normalize_dev(vkhr_b200_ctx* ctx, uint8_t* d_densities, uint64_t n_voxels, void* stream) {
     RET_IF(bind(ctx));

@@ -6,11 +6,19 @@ partials are summed with ONE integer collective over NVLink and clamped:
 result for every partition because the reference's counter only saturates
 (``if (d != 255) d += 1``, hair_style.cc:277-280, :322-325).
 
-Two exchange schedules:
+Three exchange schedules:
 
 * ``"allreduce"``  -- ``all_reduce(u32 grid, SUM)`` then a local clamp: 2(n-1)/n * 4 N^3 bytes per GPU.
 * ``"rs_ag"``      -- ``reduce_scatter(u32)`` -> the owner clamps its slab -> ``all_gather(u8)``:
   (n-1)/n * (4 + 1) N^3 bytes per GPU, 37.5 % less NVLink traffic, and the clamp touches 1/n of the grid.
+* ``"u8"``         -- every rank voxelises its shard straight into a SATURATED u8 partial (the single-GPU PACKED8
+  path, no u32 grid at all); ``all_to_all(u8 slabs)`` -> the owner adds its n partial slabs with a byte-wise
+  saturating add -> ``all_gather(u8)``: 2 (n-1)/n * N^3 bytes per GPU, 4x less than the all-reduce.  Exact because
+  ``min(sum_r min(c_r, 255), 255) == min(sum_r c_r, 255)``.
+* ``"p2p"``        -- the same arithmetic as ``"u8"`` with the exchange fused into ONE kernel over NVLink peer memory
+  (``vkhr_b200_combine_peer_u8_dev``): partial and output volumes live in torch symmetric memory, every GPU reads its
+  slab of all partials straight from the peers' HBM and stores the finished slab into all outputs; two device-side
+  barriers of the symmetric-memory group bracket the kernel.  CUDA + NVLink only (no gloo form).
 
 torch.distributed is the plumbing (NCCL on the GPUs; gloo in the CPU tests of this module's host
 logic).  Counting and clamping run in libvkhr_b200.so; ``count_fn`` / ``clamp_fn`` exist so that the
@@ -53,7 +61,8 @@ class ShardedVoxelizer:
     """voxelize_segments / voxelize_vertices over the ranks of a torch.distributed group."""
 
     def __init__(self, voxelizer=None, group=None, count_fn: Optional[Callable] = None,
-                 clamp_fn: Optional[Callable] = None):
+                 clamp_fn: Optional[Callable] = None, partial_fn: Optional[Callable] = None,
+                 satsum_fn: Optional[Callable] = None):
         import torch.distributed as dist
         self.dist = dist
         self.vox = voxelizer
@@ -62,6 +71,8 @@ class ShardedVoxelizer:
         self.rank = dist.get_rank(group)
         self._count = count_fn or self._count_cuda
         self._clamp = clamp_fn or self._clamp_cuda
+        self._partial = partial_fn or self._partial_cuda
+        self._satsum = satsum_fn or self._satsum_cuda
         self._counts = None
 
     # ---- the CUDA path (the only one the package uses) -------------------------------------------
@@ -76,6 +87,31 @@ class ShardedVoxelizer:
 
     def _clamp_cuda(self, counts, out, flags=0):
         self.vox.clamp_counts_dev(counts, flags=flags, out=out)
+
+    def _partial_cuda(self, mode, vertices, indices, segs, origin, size, W, H, D, out, flags):
+        """This shard's saturated u8 volume (the ordinary single-GPU voxelisation of the shard)."""
+        if self.vox is None:
+            raise RuntimeError("ShardedVoxelizer needs a Voxelizer: there is no CPU fallback")
+        if mode == "segments":
+            self.vox.voxelize_segments_dev(vertices, indices, origin, size, W, H, D, segs_per_strand=segs, flags=flags, out=out)
+        else:
+            self.vox.voxelize_vertices_dev(vertices, origin, size, W, H, D, flags=flags, out=out)
+
+    def _satsum_cuda(self, slabs, out):
+        self.vox.saturating_sum_u8_dev(slabs, out=out)
+
+    def _exchange_slabs(self, partial, slab):
+        """recv[r] = rank r's partial of MY slab.  NCCL: one all_to_all; gloo (CPU tests) has none: all_gather + slice."""
+        import torch
+        recv = torch.empty_like(partial)
+        if self.dist.get_backend(self.group) == "nccl":
+            self.dist.all_to_all_single(recv, partial, group=self.group)
+        else:
+            every = [torch.empty_like(partial) for _ in range(self.world)]
+            self.dist.all_gather(every, partial, group=self.group)
+            for r in range(self.world):
+                recv[r * slab:(r + 1) * slab] = every[r][self.rank * slab:(self.rank + 1) * slab]
+        return recv.view(self.world, slab)
 
     # ---- AABB: every rank must voxelise into the same box ------------------------------------------
     def global_bounding_box(self, local_min, local_max):
@@ -101,11 +137,36 @@ class ShardedVoxelizer:
         """All ranks call this with THEIR shard (torch tensors on the collective's device); every rank returns the
         complete W*H*D uint8 volume.  ``mode``: "segments" | "vertices"."""
         import torch
-        if schedule not in ("allreduce", "rs_ag"):
-            raise ValueError("schedule must be 'allreduce' or 'rs_ag'")
+        if schedule not in ("allreduce", "rs_ag", "u8", "p2p"):
+            raise ValueError("schedule must be 'allreduce', 'rs_ag', 'u8' or 'p2p'")
         nv = W * H * D
         nvp = padded_voxels(nv, self.world)
         dev = vertices.device
+        if schedule == "p2p" and self.world > 1:
+            return self._voxelize_p2p(mode, vertices, indices, segs_per_strand, aabb_origin, aabb_size, W, H, D, flags, out)
+        if schedule == "u8" and self.world > 1:
+            if out is None:
+                out = torch.empty(nvp, dtype=torch.uint8, device=dev)
+            elif out.numel() < nvp:
+                raise ValueError(f"out must hold the padded grid ({nvp} bytes)")
+            if getattr(self, "_partial_u8", None) is None or self._partial_u8.numel() != nvp or self._partial_u8.device != dev:
+                self._partial_u8 = torch.zeros(nvp, dtype=torch.uint8, device=dev)      # the pad stays zero
+            partial = self._partial_u8
+            if vertices.numel():
+                self._partial(mode, vertices, indices, segs_per_strand, aabb_origin, aabb_size, W, H, D, partial[:nv], flags & 1)
+            else:
+                partial.zero_()
+            slab = nvp // self.world
+            slabs = self._exchange_slabs(partial, slab)
+            mine_u8 = torch.empty(slab, dtype=torch.uint8, device=dev)
+            self._satsum(slabs, mine_u8)
+            self.dist.all_gather_into_tensor(out[:nvp], mine_u8, group=self.group)
+            vol = out[:nv]
+            if flags & 2:
+                if self.vox is None:
+                    raise RuntimeError("NORMALIZE needs the CUDA library")
+                self.vox.normalize_dev(vol)
+            return vol
         if self._counts is None or self._counts.numel() != nvp or self._counts.device != dev:
             self._counts = torch.zeros(nvp, dtype=torch.int32, device=dev)
         else:
@@ -135,6 +196,46 @@ class ShardedVoxelizer:
             if self.vox is None:
                 raise RuntimeError("NORMALIZE needs the CUDA library")
             self.vox.normalize_dev(vol)
+        return vol
+
+    def _symmetric(self, nvp, dev):
+        """(partial, out, handles) in symmetric memory for a padded grid of nvp bytes; allocated and exchanged once."""
+        import torch
+        import torch.distributed._symmetric_memory as symm_mem
+        cached = getattr(self, "_symm", None)
+        if cached is None or cached[0] != nvp:
+            group = self.group if self.group is not None else self.dist.group.WORLD
+            partial = symm_mem.empty(nvp, dtype=torch.uint8, device=dev)
+            outbuf = symm_mem.empty(nvp, dtype=torch.uint8, device=dev)
+            hp = symm_mem.rendezvous(partial, group)
+            ho = symm_mem.rendezvous(outbuf, group)
+            partial.zero_()
+            self._symm = cached = (nvp, partial, outbuf, hp, ho)
+        return cached[1:]
+
+    def _voxelize_p2p(self, mode, vertices, indices, segs, origin, size, W, H, D, flags, out):
+        import torch
+        if self.vox is None:
+            raise RuntimeError("the p2p schedule needs the CUDA library and NVLink peer access")
+        nv = W * H * D
+        nvp = padded_voxels(nv, self.world)
+        partial, outbuf, hp, ho = self._symmetric(nvp, vertices.device)
+        if vertices.numel():
+            self._partial(mode, vertices, indices, segs, origin, size, W, H, D, partial[:nv], flags & 1)
+        else:
+            partial.zero_()
+        slab = nvp // self.world
+        hp.barrier(channel=0)                              # every partial is complete and visible to its peers
+        self.vox.combine_peer_u8_dev(hp.buffer_ptrs, ho.buffer_ptrs, self.rank * slab, slab)
+        ho.barrier(channel=0)                              # every slab has been stored into this rank's output
+        vol = outbuf[:nv]
+        if flags & 2:
+            self.vox.normalize_dev(vol)
+        if out is not None:
+            if out.numel() < nv:
+                raise ValueError("out is too small")
+            out[:nv].copy_(vol)
+            vol = out[:nv]
         return vol
 
     def voxelize_segments(self, vertices, indices, segs_per_strand, aabb_origin, aabb_size, W, H, D, **kw):

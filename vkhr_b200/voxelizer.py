@@ -362,6 +362,31 @@ class Voxelizer:
         capi.check(self._h, rc)
         return out
 
+    def saturating_sum_u8_dev(self, slabs, out=None, stream=None):
+        """out[i] = min(sum_r slabs[r, i], 255): the combine of saturated u8 partial volumes (multi-GPU)."""
+        import torch
+        self._check_dev(slabs, torch.uint8, "slabs")
+        if slabs.dim() != 2:
+            raise ValueError("slabs must be (n_slabs, slab_bytes)")
+        if out is None:
+            out = torch.empty(slabs.shape[1], dtype=torch.uint8, device=slabs.device)
+        self._check_dev(out, torch.uint8, "out")
+        capi.check(self._h, lib.vkhr_b200_saturating_sum_u8_dev(self._h, C.c_void_p(slabs.data_ptr()), int(slabs.shape[0]),
+                                                                int(slabs.shape[1]), C.c_void_p(out.data_ptr()),
+                                                                self._torch_stream(stream)))
+        return out
+
+    def combine_peer_u8_dev(self, partial_ptrs, out_ptrs, slab_offset: int, slab_bytes: int, stream=None):
+        """Fused peer-memory combine: ``partial_ptrs`` / ``out_ptrs`` are the device addresses of every rank's partial /
+        output volume as mapped in this process (e.g. ``_SymmetricMemory.buffer_ptrs``)."""
+        n = len(partial_ptrs)
+        if n != len(out_ptrs):
+            raise ValueError("one output pointer per partial pointer")
+        pa = (C.c_void_p * n)(*[int(p) for p in partial_ptrs])
+        oa = (C.c_void_p * n)(*[int(p) for p in out_ptrs])
+        capi.check(self._h, lib.vkhr_b200_combine_peer_u8_dev(self._h, pa, oa, n, int(slab_offset), int(slab_bytes),
+                                                              self._torch_stream(stream)))
+
     def normalize_dev(self, densities, stream=None):
         import torch
         self._check_dev(densities, torch.uint8, "densities")
