@@ -525,3 +525,40 @@ def test_voxelize_hair_file_rejects_bad_images(vox, tmp_path):
     struct.pack_into("<I", broken, 16, 4)                       # default_segment_count 3 -> 4
     with pytest.raises(VkhrB200Error):
         vox.voxelize_hair(bytes(broken), 8, 8, 8)
+
+
+# ---- multi-GPU combine on one device: k "fake ranks"  ----------------------------------------------------
+@pytest.mark.parametrize("k", [2, 4, 8])
+@pytest.mark.parametrize("res", [(64, 64, 64), (12, 8, 8)])
+def test_fake_rank_u8_combine_equals_single_voxelisation(vox, port, k, res):
+    """Strand shards voxelised into saturated u8 partials, combined by (a) the saturating-sum kernel over stacked slabs and
+    (b) the fused peer-memory kernel (every fake rank sums its slab of all partials and stores it into all outputs):
+    byte-identical to one voxelisation of the whole set -- also on a coarse grid where voxels pass 255."""
+    import torch
+    from vkhr_b200 import sharding
+    W, H, D = res
+    v, n, s = synth.shape("ponytail", seed=21, seg_len=1.0, scale=0.04)
+    lo, hi = port.generate_bounding_box(v)
+    size = (hi - lo).astype(np.float32)
+    want = port.voxelize_segments(v, port.generate_indices(n, s), lo, size, W, H, D)
+    if res == (12, 8, 8):
+        assert want.max() == 255
+    nv = W * H * D
+    nvp = sharding.padded_voxels(nv, k)
+    partials = torch.zeros((k, nvp), dtype=torch.uint8, device="cuda")
+    for r in range(k):
+        mine = np.ascontiguousarray(sharding.shard_vertices(v, n, s, k, r))
+        if mine.size:
+            vox.voxelize_segments_dev(torch.from_numpy(mine.reshape(-1)).cuda(), None, lo, size, W, H, D, segs_per_strand=s,
+                                      out=partials[r, :nv])
+    got = vox.saturating_sum_u8_dev(partials)
+    torch.cuda.synchronize()
+    assert np.array_equal(got[:nv].cpu().numpy(), want)
+    outs = torch.full((k, nvp), 7, dtype=torch.uint8, device="cuda")
+    slab = nvp // k
+    pp, op = [partials[r].data_ptr() for r in range(k)], [outs[r].data_ptr() for r in range(k)]
+    for r in range(k):
+        vox.combine_peer_u8_dev(pp, op, r * slab, slab)
+    torch.cuda.synchronize()
+    for r in range(k):
+        assert np.array_equal(outs[r, :nv].cpu().numpy(), want), f"fake rank {r}"
