@@ -250,3 +250,24 @@ def test_prefilter_gauss_and_opacity_oracle(port):
         assert np.allclose(got, acc / tot, rtol=2e-5, atol=1e-7)
     op = port.prefilter_opacity(d, 0.3, 11.0)
     assert np.allclose(op, (1 - 0.3) ** (d / 255.0 * 11.0), rtol=2e-6)
+
+
+# ---- the ADSM restatement (oracle/prefilter_oracle.c): hand-checkable cases -------------------------------------------
+def test_adsm_oracle_known_answers(port):
+    """One texel of density 255 (tau = 1), light straight above at ten voxel sizes: the march samples tau * (1 - 10 t) while
+    10 t < 1, i.e. for t_k = k / 1024, k = 0..102, so strands = thickness * (103 - 10 * (102 * 103 / 2) / 1024)."""
+    d = np.array([255], dtype=np.uint8)
+    got = port.prefilter_adsm(d, 1, 1, 1, [0, 0, 0], [1, 1, 1], [0.5, 0.5, 10.5], steps=1024.0, strand_alpha=0.3, thickness=0.1)
+    strands = 0.1 * (103 - 10 * (102 * 103 / 2) / 1024)
+    assert abs(float(got[0]) - 0.7 ** strands) <= 1e-4 * 0.7 ** strands
+    # an empty volume lets everything through; the t sequence is the shader's fp32 accumulation (100 steps -> 101 samples)
+    assert np.all(port.prefilter_adsm(np.zeros(27, np.uint8), 3, 3, 3, [0, 0, 0], [1, 1, 1], [5, 5, 5]) == 1.0)
+    t = port.adsm_t_table(100.0)
+    assert len(t) == 101 and t[0] == 0.0 and np.all(np.diff(t) > 0) and t[-1] < 1.0
+    assert len(port.adsm_t_table(1024.0)) == 1024 and port.adsm_t_table(1024.0)[3] == np.float32(3 / 1024)
+    # more hair between a voxel and the light never brightens it
+    rng = np.random.default_rng(1)
+    dens = (rng.random(6 * 5 * 4) < 0.3) * rng.integers(1, 100, 6 * 5 * 4)
+    a = port.prefilter_adsm(dens.astype(np.uint8), 6, 5, 4, [0, 0, 0], [3, 2.5, 2], [1, 9, 1])
+    b = port.prefilter_adsm((dens * 2).astype(np.uint8), 6, 5, 4, [0, 0, 0], [3, 2.5, 2], [1, 9, 1])
+    assert np.all(b <= a) and a.min() >= 0 and a.max() <= 1.0 and (a < 1.0).any()
