@@ -231,6 +231,16 @@ VKHR_B200_API int vkhr_b200_combine_peer_u8_dev(
     vkhr_b200_ctx* ctx, const void* const* d_partials, void* const* d_outs, uint32_t n_peers,
     uint64_t slab_offset_bytes, uint64_t slab_bytes, void* stream);
 
+/* Sparse form of the fused combine: vkhr_b200_chunk_bitmap_dev writes one bit per 16-byte chunk of a volume (set =
+ * the chunk holds a non-zero byte; n_bytes a multiple of 512); the combine reads the peers' bitmaps, fetches a chunk
+ * only from the peers that have something in it and stores only non-zero results.  Every rank must have zeroed its
+ * OUTPUT before the first barrier.  Slab offset and size: multiples of 512 bytes. */
+VKHR_B200_API int vkhr_b200_chunk_bitmap_dev(
+    vkhr_b200_ctx* ctx, const uint8_t* d_volume, uint64_t n_bytes, uint32_t* d_bitmap_out, void* stream);
+VKHR_B200_API int vkhr_b200_combine_peer_u8_sparse_dev(
+    vkhr_b200_ctx* ctx, const void* const* d_partials, const void* const* d_bitmaps, void* const* d_outs,
+    uint32_t n_peers, uint64_t slab_offset_bytes, uint64_t slab_bytes, void* stream);
+
 /* densities = min(counts, 255), optionally followed by normalize (flags). */
 VKHR_B200_API int vkhr_b200_clamp_counts_dev(
     vkhr_b200_ctx* ctx, const uint32_t* d_counts, uint64_t n_voxels, uint32_t flags,

@@ -544,7 +544,7 @@ def test_fake_rank_u8_combine_equals_single_voxelisation(vox, port, k, res):
     if res == (12, 8, 8):
         assert want.max() == 255
     nv = W * H * D
-    nvp = sharding.padded_voxels(nv, k)
+    nvp = (nv + 512 * k - 1) // (512 * k) * (512 * k)              # whole bitmap words per slab (the p2p schedule's padding)
     partials = torch.zeros((k, nvp), dtype=torch.uint8, device="cuda")
     for r in range(k):
         mine = np.ascontiguousarray(sharding.shard_vertices(v, n, s, k, r))
@@ -562,3 +562,17 @@ def test_fake_rank_u8_combine_equals_single_voxelisation(vox, port, k, res):
     torch.cuda.synchronize()
     for r in range(k):
         assert np.array_equal(outs[r, :nv].cpu().numpy(), want), f"fake rank {r}"
+    # sparse form: chunk bitmaps, zeroed outputs, only non-zero chunks move
+    bitmaps = torch.empty((k, nvp // 512), dtype=torch.int32, device="cuda")
+    for r in range(k):
+        vox.chunk_bitmap_dev(partials[r], bitmaps[r])
+    chunks = partials.view(k, -1, 16).ne(0).any(dim=2)                                   # [k, n_chunks]
+    bits = (bitmaps.view(k, -1, 1) >> torch.arange(32, device="cuda", dtype=torch.int32)) & 1
+    assert torch.equal(bits.view(k, -1).bool(), chunks), "chunk bitmap"
+    outs.zero_()
+    bp = [bitmaps[r].data_ptr() for r in range(k)]
+    for r in range(k):
+        vox.combine_peer_u8_sparse_dev(pp, bp, op, r * slab, slab)
+    torch.cuda.synchronize()
+    for r in range(k):
+        assert np.array_equal(outs[r, :nv].cpu().numpy(), want), f"fake rank {r} (sparse)"

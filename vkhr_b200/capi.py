@@ -127,6 +127,8 @@ _PROTOTYPES = {
     "vkhr_b200_count_vertices_dev": (_int, [c_ctx, _P, _u32, _vec3, _vec3, _u32, _u32, _u32, _u32, _P, _P]),
     "vkhr_b200_saturating_sum_u8_dev": (_int, [c_ctx, _P, _u32, _u64, _P, _P]),
     "vkhr_b200_combine_peer_u8_dev": (_int, [c_ctx, _P, _P, _u32, _u64, _u64, _P]),
+    "vkhr_b200_chunk_bitmap_dev": (_int, [c_ctx, _P, _u64, _P, _P]),
+    "vkhr_b200_combine_peer_u8_sparse_dev": (_int, [c_ctx, _P, _P, _P, _u32, _u64, _u64, _P]),
     "vkhr_b200_clamp_counts_dev": (_int, [c_ctx, _P, _u64, _u32, _P, _P]),
     "vkhr_b200_normalize_dev": (_int, [c_ctx, _P, _u64, _P]),
     "vkhr_b200_normalize": (_int, [c_ctx, _P, _u64]),

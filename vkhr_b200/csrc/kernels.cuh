@@ -569,6 +569,49 @@ k_combine_peer_u8(const __grid_constant__ PeerPtrs P, uint64_t off16, uint64_t s
     }
 }
 
+// Sparse form of the fused combine.  A hair volume is mostly zeros and a strand shard's partial even more so: each
+// rank publishes one bit per 16-byte chunk of its partial (k_chunk_bitmap), the owner of a slab reads the peers'
+// bitmap words (one broadcast load per warp and peer), fetches a chunk only from the peers that have something in it,
+// and stores only non-zero results -- the outputs are zeroed by their owners before the first barrier.  NVLink then
+// carries the hair, not the empty space.
+__global__ void __launch_bounds__(256)
+k_chunk_bitmap(const uint4* __restrict__ vol, uint64_t n16, uint32_t* __restrict__ bitmap) {
+    // n16 is a multiple of 32 (the grid is padded to 16 * 32 * world bytes): whole warps, one word per warp-iteration
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldcs(vol + i);
+        const uint32_t bits = __ballot_sync(0xFFFFFFFFu, (v.x | v.y | v.z | v.w) != 0u);
+        if ((threadIdx.x & 31u) == 0u) bitmap[i >> 5] = bits;
+    }
+}
+struct PeerPtrsSparse {
+    const uint4* part[kMaxPeers];
+    const uint32_t* bits[kMaxPeers];
+    uint4* out[kMaxPeers];
+    uint32_t n;
+};
+__global__ void __launch_bounds__(256)
+k_combine_peer_u8_sparse(const __grid_constant__ PeerPtrsSparse P, uint64_t off16, uint64_t slab16) {
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < slab16; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t c = off16 + i;                            // chunk index in the whole grid; c >> 5 is warp-uniform
+        uint32_t have = 0;                                       // peers with a non-zero chunk here
+#pragma unroll
+        for (uint32_t r = 0; r < kMaxPeers; ++r)
+            if (r < P.n) have |= ((__ldcg(P.bits[r] + (c >> 5)) >> lane) & 1u) << r;
+        if (!have) continue;
+        uint4 acc = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (uint32_t r = 0; r < kMaxPeers; ++r)
+            if (r < P.n && ((have >> r) & 1u)) {
+                const uint4 v = __ldcg(P.part[r] + c);
+                acc.x = __vaddus4(acc.x, v.x); acc.y = __vaddus4(acc.y, v.y); acc.z = __vaddus4(acc.z, v.z); acc.w = __vaddus4(acc.w, v.w);
+            }
+#pragma unroll
+        for (uint32_t r = 0; r < kMaxPeers; ++r)
+            if (r < P.n) __stcg(P.out[r] + c, acc);
+    }
+}
+
 // Same for an output grid that is not 16-byte aligned (a view into a caller's buffer): one voxel per thread.
 template <bool ZERO>
 __global__ void __launch_bounds__(256)

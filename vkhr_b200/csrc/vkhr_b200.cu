@@ -778,6 +778,45 @@ int vkhr_b200_combine_peer_u8_dev(vkhr_b200_ctx* ctx, const void* const* d_parti
     return VKHR_B200_OK;
 }
 
+int vkhr_b200_chunk_bitmap_dev(vkhr_b200_ctx* ctx, const uint8_t* d_volume, uint64_t n_bytes, uint32_t* d_bitmap, void* stream) {
+    RET_IF(bind(ctx));
+    if (!d_volume || !d_bitmap) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null pointer");
+    if ((n_bytes & 511u) || (reinterpret_cast<uintptr_t>(d_volume) & 15u))
+        return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "volume must be 16-byte aligned and a multiple of 512 bytes (32 chunks per bitmap word)");
+    if (n_bytes == 0) return VKHR_B200_OK;
+    cudaStream_t s = pick(ctx, stream);
+    k_chunk_bitmap<<<stride_blocks(ctx, n_bytes / 16, 256, 8), 256, 0, s>>>(reinterpret_cast<const uint4*>(d_volume), n_bytes / 16, d_bitmap);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return VKHR_B200_OK;
+}
+
+int vkhr_b200_combine_peer_u8_sparse_dev(vkhr_b200_ctx* ctx, const void* const* d_partials, const void* const* d_bitmaps,
+                                         void* const* d_outs, uint32_t n_peers, uint64_t slab_offset_bytes, uint64_t slab_bytes,
+                                         void* stream) {
+    RET_IF(bind(ctx));
+    if (!d_partials || !d_bitmaps || !d_outs || n_peers == 0 || n_peers > kMaxPeers)
+        return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "peer pointer arrays: 1.." + std::to_string(kMaxPeers) + " peers");
+    if ((slab_offset_bytes & 511u) || (slab_bytes & 511u))
+        return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "slab offset and size must be multiples of 512 (whole bitmap words)");
+    PeerPtrsSparse P{};
+    P.n = n_peers;
+    for (uint32_t r = 0; r < n_peers; ++r) {
+        if (!d_partials[r] || !d_bitmaps[r] || !d_outs[r] || (reinterpret_cast<uintptr_t>(d_partials[r]) & 15u) ||
+            (reinterpret_cast<uintptr_t>(d_outs[r]) & 15u) || (reinterpret_cast<uintptr_t>(d_bitmaps[r]) & 3u))
+            return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "peer buffers must be non-null and aligned");
+        P.part[r] = static_cast<const uint4*>(d_partials[r]);
+        P.bits[r] = static_cast<const uint32_t*>(d_bitmaps[r]);
+        P.out[r] = static_cast<uint4*>(d_outs[r]);
+    }
+    if (slab_bytes == 0) return VKHR_B200_OK;
+    cudaStream_t s = pick(ctx, stream);
+    k_combine_peer_u8_sparse<<<stride_blocks(ctx, slab_bytes / 16, 256, 8), 256, 0, s>>>(P, slab_offset_bytes / 16, slab_bytes / 16);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return VKHR_B200_OK;
+}
+
 // ---- Volume operations ---------------------------------------------------------
 int vkhr_b200_normalize_dev(vkhr_b200_ctx* ctx, uint8_t* d_densities, uint64_t n_voxels, void* stream) {
     RET_IF(bind(ctx));

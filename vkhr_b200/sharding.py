@@ -18,7 +18,9 @@ Three exchange schedules:
 * ``"p2p"``        -- the same arithmetic as ``"u8"`` with the exchange fused into ONE kernel over NVLink peer memory
   (``vkhr_b200_combine_peer_u8_dev``): partial and output volumes live in torch symmetric memory, every GPU reads its
   slab of all partials straight from the peers' HBM and stores the finished slab into all outputs; two device-side
-  barriers of the symmetric-memory group bracket the kernel.  CUDA + NVLink only (no gloo form).
+  barriers of the symmetric-memory group bracket the kernel.  The exchange is sparse: one bit per 16-byte chunk of each
+  partial tells the owner which peers to read, and only non-zero results are stored (outputs zeroed beforehand), so
+  NVLink carries the hair and not the empty space.  CUDA + NVLink only (no gloo form).
 
 torch.distributed is the plumbing (NCCL on the GPUs; gloo in the CPU tests of this module's host
 logic).  Counting and clamping run in libvkhr_b200.so; ``count_fn`` / ``clamp_fn`` exist so that the
@@ -199,18 +201,19 @@ class ShardedVoxelizer:
         return vol
 
     def _symmetric(self, nvp, dev):
-        """(partial, out, handles) in symmetric memory for a padded grid of nvp bytes; allocated and exchanged once."""
+        """(partial, bitmap, out, partial handle, bitmap handle, out handle) in symmetric memory for a padded grid of nvp
+        bytes; allocated and exchanged once per grid size."""
         import torch
         import torch.distributed._symmetric_memory as symm_mem
         cached = getattr(self, "_symm", None)
         if cached is None or cached[0] != nvp:
             group = self.group if self.group is not None else self.dist.group.WORLD
             partial = symm_mem.empty(nvp, dtype=torch.uint8, device=dev)
+            bitmap = symm_mem.empty(nvp // 512, dtype=torch.int32, device=dev)
             outbuf = symm_mem.empty(nvp, dtype=torch.uint8, device=dev)
-            hp = symm_mem.rendezvous(partial, group)
-            ho = symm_mem.rendezvous(outbuf, group)
+            hp, hb, ho = (symm_mem.rendezvous(t, group) for t in (partial, bitmap, outbuf))
             partial.zero_()
-            self._symm = cached = (nvp, partial, outbuf, hp, ho)
+            self._symm = cached = (nvp, partial, bitmap, outbuf, hp, hb, ho)
         return cached[1:]
 
     def _voxelize_p2p(self, mode, vertices, indices, segs, origin, size, W, H, D, flags, out):
@@ -218,15 +221,18 @@ class ShardedVoxelizer:
         if self.vox is None:
             raise RuntimeError("the p2p schedule needs the CUDA library and NVLink peer access")
         nv = W * H * D
-        nvp = padded_voxels(nv, self.world)
-        partial, outbuf, hp, ho = self._symmetric(nvp, vertices.device)
+        q = 512 * self.world                               # whole bitmap words (32 chunks of 16 bytes) per slab
+        nvp = (nv + q - 1) // q * q
+        partial, bitmap, outbuf, hp, hb, ho = self._symmetric(nvp, vertices.device)
         if vertices.numel():
             self._partial(mode, vertices, indices, segs, origin, size, W, H, D, partial[:nv], flags & 1)
         else:
             partial.zero_()
+        self.vox.chunk_bitmap_dev(partial, bitmap)         # which 16-byte chunks of my partial hold anything
+        outbuf.zero_()                                     # peers only send non-zero results
         slab = nvp // self.world
-        hp.barrier(channel=0)                              # every partial is complete and visible to its peers
-        self.vox.combine_peer_u8_dev(hp.buffer_ptrs, ho.buffer_ptrs, self.rank * slab, slab)
+        hp.barrier(channel=0)                              # partials, bitmaps and zeroed outputs are complete and visible
+        self.vox.combine_peer_u8_sparse_dev(hp.buffer_ptrs, hb.buffer_ptrs, ho.buffer_ptrs, self.rank * slab, slab)
         ho.barrier(channel=0)                              # every slab has been stored into this rank's output
         vol = outbuf[:nv]
         if flags & 2:

@@ -387,6 +387,27 @@ class Voxelizer:
         capi.check(self._h, lib.vkhr_b200_combine_peer_u8_dev(self._h, pa, oa, n, int(slab_offset), int(slab_bytes),
                                                               self._torch_stream(stream)))
 
+    def chunk_bitmap_dev(self, volume, bitmap, stream=None):
+        """One bit per 16-byte chunk of ``volume`` (cuda uint8, a multiple of 512 bytes) into ``bitmap`` (cuda int32)."""
+        import torch
+        self._check_dev(volume, torch.uint8, "volume")
+        self._check_dev(bitmap, torch.int32, "bitmap")
+        if bitmap.numel() * 512 < volume.numel():
+            raise ValueError("bitmap too small")
+        capi.check(self._h, lib.vkhr_b200_chunk_bitmap_dev(self._h, C.c_void_p(volume.data_ptr()), volume.numel(),
+                                                           C.c_void_p(bitmap.data_ptr()), self._torch_stream(stream)))
+
+    def combine_peer_u8_sparse_dev(self, partial_ptrs, bitmap_ptrs, out_ptrs, slab_offset: int, slab_bytes: int, stream=None):
+        """Sparse fused peer-memory combine (outputs zeroed beforehand; see include/vkhr_b200.h)."""
+        n = len(partial_ptrs)
+        if n != len(out_ptrs) or n != len(bitmap_ptrs):
+            raise ValueError("one bitmap and one output pointer per partial pointer")
+        pa = (C.c_void_p * n)(*[int(p) for p in partial_ptrs])
+        ba = (C.c_void_p * n)(*[int(p) for p in bitmap_ptrs])
+        oa = (C.c_void_p * n)(*[int(p) for p in out_ptrs])
+        capi.check(self._h, lib.vkhr_b200_combine_peer_u8_sparse_dev(self._h, pa, ba, oa, n, int(slab_offset), int(slab_bytes),
+                                                                     self._torch_stream(stream)))
+
     def normalize_dev(self, densities, stream=None):
         import torch
         self._check_dev(densities, torch.uint8, "densities")
