@@ -145,3 +145,26 @@ def test_synth_shapes():
     w = synth.sway(v, n, s, t=3.0)
     assert np.array_equal(w.reshape(n, s + 1, 3)[:, 0], v.reshape(n, s + 1, 3)[:, 0])   # roots stay
     assert not np.array_equal(w, v)
+
+
+def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
+    """`bench.py --impl reference` needs no GPU: rank 0 prints ONE JSON line (metric, unit, cpu_baseline, e2e with zero
+    copy bytes), every other rank prints nothing and exits 0."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--res", "64"], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "M seg/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    env["RANK"] = "1"
+    other = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                           capture_output=True, text=True, env=env, timeout=600)
+    assert other.returncode == 0 and other.stdout.strip() == ""
