@@ -287,7 +287,10 @@ typedef struct vkhr_b200_prefilter_params {
     float gauss_width;     /* kernel_width of filter_volume, odd, 1..9 (3) */
     uint32_t flags;        /* VKHR_B200_PREFILTER_* */
 } vkhr_b200_prefilter_params;
-enum { VKHR_B200_PREFILTER_GENERIC = 1u << 0 };   /* force the untiled kernel (testing) */
+enum {
+    VKHR_B200_PREFILTER_GENERIC = 1u << 0,   /* force the untiled kernel (testing) */
+    VKHR_B200_PREFILTER_ROWWISE = 1u << 1    /* tiled kernel: one AO evaluation per voxel instead of the register-tiled z column (testing, A/B timing) */
+};
 
 VKHR_B200_API void vkhr_b200_prefilter_defaults(vkhr_b200_prefilter_params* params);
 VKHR_B200_API int vkhr_b200_prefilter_dev(

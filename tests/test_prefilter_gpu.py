@@ -45,6 +45,27 @@ def test_ao_against_oracle(vox, port, res, radius):
         assert np.array_equal(gen, got), "tiled and generic kernels must agree bit for bit"
 
 
+@pytest.mark.parametrize("res", [(64, 32, 16), (48, 40, 24), (32, 24, 11)])
+@pytest.mark.parametrize("radius", [0.0, 0.5, 1.0, 1.3, 2.0, 2.5, 3.0, 3.75, 4.0, 4.5, 6.0])
+@pytest.mark.parametrize("gauss_width", [None, 9.0])
+def test_ao_column_form_equals_row_wise_and_generic(vox, port, res, radius, gauss_width):
+    """The register-tiled z-column AO (one instantiation per tap-offset pair up to radius 4) against the row-wise tiled
+    kernel and the generic kernel, bit for bit -- also when a wider Gaussian sets the tile's halo (9^3: halo 4)."""
+    W, H, D = res
+    rng = np.random.default_rng(W * 17 + int(radius * 100))
+    for d in (_noise(rng, W * H * D, 0.02), _noise(rng, W * H * D, 0.5), _hair(vox, port, W, H, D)):
+        kw = dict(ao=True, ao_radius=radius)
+        if gauss_width:
+            kw.update(gauss=True, gauss_width=gauss_width, opacity=True)
+        col = vox.prefilter(d, W, H, D, **kw)
+        row = vox.prefilter(d, W, H, D, flags=capi.PREFILTER_ROWWISE, **kw)
+        gen = vox.prefilter(d, W, H, D, flags=capi.PREFILTER_GENERIC, **kw)
+        for k in col:
+            assert np.array_equal(col[k], row[k]), f"{k}: column vs row-wise, r={radius}"
+            assert np.array_equal(col[k], gen[k]), f"{k}: column vs generic, r={radius}"
+    _close(col["ao"], port.prefilter_ao(d, W, H, D, radius=radius), f"ao r={radius}")
+
+
 @pytest.mark.parametrize("radius,exponent,ao_max", [(5.75, 10.0, 0.16), (7.25, 3.0, 0.4), (8.0, 32.0, 0.05), (8.5, 1.0, 0.2), (12.0, 10.0, 0.16)])
 def test_ao_large_radii_and_ui_ranges(vox, port, radius, exponent, ao_max):
     """The UI ranges (interface.cc:291-293): radius 0..8, exponent 0..32, clamp 0..0.4; halo > 8 takes the generic kernel."""

@@ -13,7 +13,7 @@ size = (hi - lo).astype(np.float32)
 vt = torch.from_numpy(v).cuda().reshape(-1)
 d = vox.voxelize_segments_dev(vt, None, lo, size, W, W, W, segs_per_strand=s)
 out = [torch.empty(W ** 3, dtype=torch.float32, device="cuda") for _ in range(3)]
-res = {"W": W, "nonzero_fraction": float((d != 0).float().mean().item())}
+res = {"W": W, "lib": os.path.basename(os.environ.get("VKHR_B200_LIB", "libvkhr_b200.so")), "nonzero_fraction": float((d != 0).float().mean().item())}
 
 
 def timed(name, fn, reps=5, alg_bytes=None):
@@ -35,11 +35,13 @@ def timed(name, fn, reps=5, alg_bytes=None):
 
 n3 = W ** 3
 timed("ao", lambda: vox.prefilter_dev(d, W, W, W, ao=out[0]), alg_bytes=5 * n3)
+from vkhr_b200 import capi
+timed("ao_rowwise", lambda: vox.prefilter_dev(d, W, W, W, ao=out[0], flags=capi.PREFILTER_ROWWISE), alg_bytes=5 * n3)
 timed("opacity", lambda: vox.prefilter_dev(d, W, W, W, opacity=out[1]), alg_bytes=5 * n3)
 timed("gauss3", lambda: vox.prefilter_dev(d, W, W, W, gauss=out[2]), alg_bytes=5 * n3)
 timed("ao+opacity", lambda: vox.prefilter_dev(d, W, W, W, ao=out[0], opacity=out[1]), alg_bytes=9 * n3)
 timed("ao+opacity+gauss3", lambda: vox.prefilter_dev(d, W, W, W, ao=out[0], opacity=out[1], gauss=out[2]), alg_bytes=13 * n3)
-if W <= 512:
+if W <= 512 and not os.environ.get("PF_NO_ADSM"):
     light = lo + size * np.array([0.5, 3.0, 0.5], np.float32)
     timed("adsm_1024steps", lambda: vox.adsm_dev(d, W, W, W, lo, size, light, out=out[0]), reps=2, alg_bytes=5 * n3)
 print(json.dumps(res))

@@ -74,6 +74,7 @@ class PrefilterParams(C.Structure):
 
 
 PREFILTER_GENERIC = 1 << 0
+PREFILTER_ROWWISE = 1 << 1
 
 
 class AdsmParams(C.Structure):

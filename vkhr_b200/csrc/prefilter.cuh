@@ -18,7 +18,13 @@
 
 namespace vkhr_b200 {
 
-constexpr int kPfTX = 32, kPfTY = 8, kPfTZ = 8;      // output voxels per tile
+#ifndef VKHR_B200_PF_TZ
+#define VKHR_B200_PF_TZ 8
+#endif
+#ifndef VKHR_B200_PF_MIN_CTAS
+#define VKHR_B200_PF_MIN_CTAS 1
+#endif
+constexpr int kPfTX = 32, kPfTY = 8, kPfTZ = VKHR_B200_PF_TZ;      // output voxels per tile
 // The staged box starts kPfLead texels left of the tile: the innermost TMA coordinate must be a multiple of 16 BYTES
 // (measured: tools/tma_probe.cu -- x = -16, 16, 48 load, x = -3, 4, 29 raise "illegal instruction"), so the halo
 // cannot start at x0 - halo; the box is [x0 - 16, x0 + 48) and the kernel uses [x0 - halo, x0 + 32 + halo) of it.
@@ -83,6 +89,76 @@ __device__ __forceinline__ float lao_at(const PrefilterArgs& A, Fetch&& fetch) {
                 density = __fadd_rn(density, (A.ao_max < s) ? A.ao_max : s);
             }
     return powf(__fsub_rn(1.0f, __fdiv_rn(density, 8.0f)), A.ao_exponent);    // pow(kernel_size = 2, 3) = 8
+}
+
+// The same sum for a COLUMN of kPfTZ voxels along z (one thread: fixed x, y): the x- and y-lerps of plane z' are
+// shared by the four outputs z = z' - o (o = the four z offsets), so they are computed once per plane instead of once
+// per output -- 8 x-lerps + 4 y-lerps per plane, 8 z-lerps per output; per voxel 28 instead of 64 texel loads and 29
+// instead of 56 lerps at kPfTZ = 8, radius 2.5.  Every lerp is the operation sequence of lao_at, and an output adds its
+// eight clamped z-lerps in lao_at's (sz, sy, sx) order, so the result is bit-identical to lao_at.  The tap offsets
+// are template parameters (NO0, NO0 + 1 below, PO0, PO0 + 1 above the voxel): the loop over planes unrolls fully and
+// the window of live planes (PO0 - NO0 + 2 planes x 4 floats) stays in registers.
+// A plane whose four tap rows hold no hair contributes exact zeros (+0 * w + +0 * w, w >= 0) and is not read; an
+// output whose four planes are all such planes is the empty-space constant.
+template <int NO0, int PO0, class Emit>
+__device__ __forceinline__ void lao_column(const PrefilterArgs& A, const float* __restrict__ column, const uint32_t* __restrict__ flagcol,
+                                           int plane_floats, int row_floats, int BY, bool tile_any, float ao_empty, int n_out, Emit&& emit) {
+    // column  = texel (lane, jy, kz = 0) of the float tile; flagcol = row flag of (jy, kz = 0)
+    constexpr int SPAN = PO0 - NO0 + 1;                  // planes between the first and the last tap plane of an output
+    constexpr int NQ = kPfTZ + SPAN;                     // planes q = 0 .. NQ-1 sit at z offset q + NO0 from output 0
+    const int oy[4] = {NO0, NO0 + 1, PO0, PO0 + 1};
+    const AxisTaps ax[2] = {A.neg, A.pos};
+    float yl[NQ][4];                                     // [q][2 * sx + sy]
+    bool live[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        uint32_t any = 0u;
+        if (tile_any) {
+#pragma unroll
+            for (int yr = 0; yr < 4; ++yr) any |= flagcol[(q + NO0) * BY + oy[yr]];
+        }
+        live[q] = any != 0u;
+        if (any) {
+            const float* pl = column + (q + NO0) * plane_floats;
+            float xl[2][4];
+#pragma unroll
+            for (int yr = 0; yr < 4; ++yr) {
+                const float* row = pl + oy[yr] * row_floats;
+                xl[0][yr] = __fadd_rn(__fmul_rn(row[NO0], ax[0].w0), __fmul_rn(row[NO0 + 1], ax[0].w1));
+                xl[1][yr] = __fadd_rn(__fmul_rn(row[PO0], ax[1].w0), __fmul_rn(row[PO0 + 1], ax[1].w1));
+            }
+#pragma unroll
+            for (int sx = 0; sx < 2; ++sx)
+#pragma unroll
+                for (int sy = 0; sy < 2; ++sy)
+                    yl[q][2 * sx + sy] = __fadd_rn(__fmul_rn(xl[sx][2 * sy], ax[sy].w0), __fmul_rn(xl[sx][2 * sy + 1], ax[sy].w1));
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) yl[q][c] = 0.0f;
+        }
+        if (q >= SPAN) {                                 // output kz = q - SPAN has its last plane
+            const int kz = q - SPAN;
+            if (kz < n_out) {                            // warp-uniform
+                float r = ao_empty;
+                if (live[kz] || live[kz + 1] || live[kz + SPAN - 1] || live[kz + SPAN]) {
+                    float density = 0.0f;
+#pragma unroll
+                    for (int sz = 0; sz < 2; ++sz) {
+                        const int qa = kz + (sz ? SPAN - 1 : 0);
+#pragma unroll
+                        for (int sy = 0; sy < 2; ++sy)
+#pragma unroll
+                            for (int sx = 0; sx < 2; ++sx) {
+                                const float s = __fadd_rn(__fmul_rn(yl[qa][2 * sx + sy], ax[sz].w0), __fmul_rn(yl[qa + 1][2 * sx + sy], ax[sz].w1));
+                                density = __fadd_rn(density, (A.ao_max < s) ? A.ao_max : s);
+                            }
+                    }
+                    r = powf(__fsub_rn(1.0f, __fdiv_rn(density, 8.0f)), A.ao_exponent);
+                }
+                emit(kz, r);
+            }
+        }
+    }
 }
 
 // Gaussian weight of tap (x,y,z) (sample_volume.glsl:26-27, precedence quirk kept).
@@ -171,7 +247,15 @@ __host__ __device__ inline PfSmemPlan pf_plan(int halo, int g_range) {
     return p;
 }
 
-__global__ void __launch_bounds__(kPfThreads)
+// NO0 / PO0: the AO tap offsets as compile-time constants (lao_column: one warp per y row, the tile's kPfTZ outputs of a
+// lane as one register-tiled column), or kPfRowWise: offsets read from A, one lao_at per voxel (any radius, and the
+// launches that do not ask for AO).
+constexpr int kPfRowWise = 99;
+constexpr int kPfVariantCount = 10;                  // row-wise + 9 column instantiations (the host's dispatch table)
+static_assert(kPfThreads / 32 == kPfTY, "one warp per y row of the tile");
+
+template <int NO0, int PO0>
+__global__ void __launch_bounds__(kPfThreads, VKHR_B200_PF_MIN_CTAS)
 k_prefilter_tiled(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ PrefilterArgs A) {
     extern __shared__ __align__(128) unsigned char pf_smem[];
     const int h = A.halo, BY = kPfTY + 2 * h, BZ = kPfTZ + 2 * h, FX = kPfTX + 2 * h;
@@ -213,7 +297,7 @@ k_prefilter_tiled(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     }
     for (int r = tid; r < BY * BZ; r += kPfThreads) rowflag[r] = 0u;
     // constants of empty space
-    const float ao_empty = powf(__fsub_rn(1.0f, __fdiv_rn(0.0f, 8.0f)), A.ao_exponent);
+    const float ao_empty = lao_at(A, [](int, int, int) -> float { return 0.0f; });
     __syncthreads();
     if (blockIdx.x < n_tiles && tid == 0) issue(blockIdx.x, 0);
 
@@ -281,6 +365,19 @@ k_prefilter_tiled(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         }
         const int tile_any = __syncthreads_or(mine);
 
+        // ---- AO, column form: warp = y row jy, lane = x, the kPfTZ outputs along z from one pass over the planes ----
+        if constexpr (NO0 != kPfRowWise) {
+            const int X = x0 + lane, Y = y0 + warp;
+            if (A.ao && Y < A.H) {                                            // warp-uniform
+                const size_t zs = (size_t)A.W * A.H;
+                float* out = A.ao + ((size_t)X + (size_t)Y * A.W + (size_t)z0 * zs);
+                const bool inside = X < A.W;
+                lao_column<NO0, PO0>(A, ftile + (h * BY + (warp + h)) * FX + (lane + h), rowflag + h * BY + (warp + h),
+                                     BY * FX, FX, BY, tile_any != 0, ao_empty, min(kPfTZ, A.D - z0),
+                                     [&](int kz, float r) { if (inside) __stcs(out + (size_t)kz * zs, r); });
+            }
+        }
+
         // ---- one output row (32 voxels along x) per warp-iteration ---------------------------------------------
         for (int rr = warp; rr < kPfTY * kPfTZ; rr += kPfThreads / 32) {
             const int jy = rr % kPfTY, kz = rr / kPfTY;
@@ -291,7 +388,7 @@ k_prefilter_tiled(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             const float* centre = ftile + ((kz + h) * BY + (jy + h)) * FX + (lane + h);
             auto fetch = [&](int ox, int oy, int oz) -> float { return centre[(oz * BY + oy) * FX + ox]; };
             auto flag = [&](int oy, int oz) -> uint32_t { return rowflag[(kz + h + oz) * BY + (jy + h + oy)]; };
-            if (A.ao) {
+            if (NO0 == kPfRowWise && A.ao) {
                 float r = ao_empty;
                 uint32_t any = 0u;
                 if (tile_any) {

@@ -129,7 +129,7 @@ struct vkhr_b200_ctx {
     DevBuf adsm_table;            // the ADSM march's accumulated t sequence for `adsm_steps`
     float adsm_steps = 0.0f;
     uint32_t adsm_n = 0;
-    uint32_t pf_smem_opted = 0;   // dynamic shared memory the tiled prefilter kernel has been opted into
+    uint32_t pf_smem_opted[kPfVariantCount] = {};   // dynamic shared memory each tiled prefilter instantiation has been opted into
     Batch batch;          // host copy of the kernel-parameter batch being launched
     // optional per-phase device timing (vkhr_b200_profile_*): CUDA events recorded on the
     // launching stream around each phase of run_voxelize
@@ -1075,6 +1075,20 @@ AxisTaps axis_taps(float r, bool positive) {
     return a;
 }
 
+// instantiations of the tiled kernel: [0] row-wise (offsets at run time), then the column form for the tap offsets
+// (neg.o0, pos.o0) of a non-integer radius with floor f: (-f-1, f), and of an integer radius r: (-r, r), up to radius 4
+// (the default is 2.5; wider windows need more than 200 registers per thread and stay row-wise)
+typedef void (*PfKernel)(const CUtensorMap, const PrefilterArgs);
+struct PfVariant { int no0, po0; PfKernel kernel; };
+#define PF_COL(n, p) {n, p, k_prefilter_tiled<n, p>}
+const PfVariant kPfVariantTable[] = {
+    {kPfRowWise, kPfRowWise, k_prefilter_tiled<kPfRowWise, kPfRowWise>},
+    PF_COL(0, 0), PF_COL(-1, 0), PF_COL(-1, 1), PF_COL(-2, 1), PF_COL(-2, 2), PF_COL(-3, 2), PF_COL(-3, 3), PF_COL(-4, 3), PF_COL(-4, 4),
+};
+#undef PF_COL
+constexpr int kPfVariants = (int)(sizeof(kPfVariantTable) / sizeof(kPfVariantTable[0]));
+static_assert(kPfVariants == kPfVariantCount, "the context keeps one shared-memory opt-in per instantiation");
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1153,16 +1167,24 @@ int vkhr_b200_prefilter_dev(vkhr_b200_ctx* ctx, const uint8_t* d_densities, uint
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(ctx, VKHR_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)cr));
     const PfSmemPlan plan = pf_plan(halo, A.g_range);
-    if (plan.total > ctx->pf_smem_opted) {
-        CU_CHECK(ctx, cudaFuncSetAttribute(k_prefilter_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total));
-        ctx->pf_smem_opted = plan.total;
+    // AO with tap offsets the column kernel is instantiated for (every radius of the UI range 0..8 whose halo fits a
+    // tile) takes that instantiation; everything else the row-wise one
+    int variant = 0;
+    if (d_ao && !(P.flags & VKHR_B200_PREFILTER_ROWWISE))
+        for (int v = 1; v < kPfVariants; ++v)
+            if (kPfVariantTable[v].no0 == A.neg.o0 && kPfVariantTable[v].po0 == A.pos.o0 && A.neg.o1 == A.neg.o0 + 1 && A.pos.o1 == A.pos.o0 + 1)
+                variant = v;
+    const PfKernel kernel = kPfVariantTable[variant].kernel;
+    if (plan.total > ctx->pf_smem_opted[variant]) {
+        CU_CHECK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total));
+        ctx->pf_smem_opted[variant] = plan.total;
     }
     int per_sm = 0;
-    CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_prefilter_tiled, kPfThreads, plan.total));
+    CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPfThreads, plan.total));
     if (per_sm < 1) return fail(ctx, VKHR_B200_ERR_CUDA, "prefilter kernel does not fit on an SM");
     const uint64_t n_tiles = (uint64_t)A.tiles_x * A.tiles_y * A.tiles_z;
     const unsigned blocks = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)per_sm * ctx->sm_count);
-    k_prefilter_tiled<<<blocks, kPfThreads, plan.total, s>>>(tmap, A);
+    kernel<<<blocks, kPfThreads, plan.total, s>>>(tmap, A);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     return VKHR_B200_OK;
