@@ -168,3 +168,21 @@ def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
     other = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                            capture_output=True, text=True, env=env, timeout=600)
     assert other.returncode == 0 and other.stdout.strip() == ""
+
+
+def test_ao_column_form_equals_per_voxel_form_in_host_emulation(tmp_path):
+    """lao_column (register-tiled z column) against lao_at (one evaluation per voxel), both taken verbatim from
+    prefilter.cuh and compiled for the host: every output bit-identical, for every tap-offset pair the kernel is
+    instantiated for (tests/host_emulation/lao_column_check.cc).  The GPU test of the same name checks the kernels."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "vkhr_b200", "csrc", "prefilter.cuh")).read()
+    body = text[text.index("constexpr int kPfTX"):text.index("// Gaussian weight of tap")]
+    assert "lao_column" in body and "lao_at" in body
+    extract = tmp_path / "lao_extract.inc"
+    extract.write_text(body.replace("__device__ __forceinline__", "static inline"))
+    exe = tmp_path / "lao_column_check"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", f'-DLAO_EXTRACT="{extract}"',
+                           "-o", str(exe), os.path.join(root, "tests", "host_emulation", "lao_column_check.cc")])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "TOTAL bad=0" in out.stdout, out.stdout[-2000:]
+    assert "nontrivial=0\n" not in out.stdout.split("fill=0.00")[0], "the dense cases must exercise non-empty outputs"

@@ -18,13 +18,10 @@
 
 namespace vkhr_b200 {
 
-#ifndef VKHR_B200_PF_TZ
-#define VKHR_B200_PF_TZ 8
-#endif
-#ifndef VKHR_B200_PF_MIN_CTAS
-#define VKHR_B200_PF_MIN_CTAS 1
-#endif
-constexpr int kPfTX = 32, kPfTY = 8, kPfTZ = VKHR_B200_PF_TZ;      // output voxels per tile
+constexpr int kPfTX = 32, kPfTY = 8;                 // output voxels per tile along x, y
+// ... and along z: 8, or 16 where two CTAs of the deeper tile still fit an SM (the column form of AO shares its x/y
+// lerps along z, and the halo planes are a smaller share of a deeper tile: 22/16 instead of 14/8 at radius 2.5)
+constexpr int kPfTZ = 8, kPfTZDeep = 16;
 // The staged box starts kPfLead texels left of the tile: the innermost TMA coordinate must be a multiple of 16 BYTES
 // (measured: tools/tma_probe.cu -- x = -16, 16, 48 load, x = -3, 4, 29 raise "illegal instruction"), so the halo
 // cannot start at x0 - halo; the box is [x0 - 16, x0 + 48) and the kernel uses [x0 - halo, x0 + 32 + halo) of it.
@@ -91,21 +88,21 @@ __device__ __forceinline__ float lao_at(const PrefilterArgs& A, Fetch&& fetch) {
     return powf(__fsub_rn(1.0f, __fdiv_rn(density, 8.0f)), A.ao_exponent);    // pow(kernel_size = 2, 3) = 8
 }
 
-// The same sum for a COLUMN of kPfTZ voxels along z (one thread: fixed x, y): the x- and y-lerps of plane z' are
+// The same sum for a COLUMN of TZ voxels along z (one thread: fixed x, y): the x- and y-lerps of plane z' are
 // shared by the four outputs z = z' - o (o = the four z offsets), so they are computed once per plane instead of once
 // per output -- 8 x-lerps + 4 y-lerps per plane, 8 z-lerps per output; per voxel 28 instead of 64 texel loads and 29
-// instead of 56 lerps at kPfTZ = 8, radius 2.5.  Every lerp is the operation sequence of lao_at, and an output adds its
+// instead of 56 lerps at TZ = 8, radius 2.5.  Every lerp is the operation sequence of lao_at, and an output adds its
 // eight clamped z-lerps in lao_at's (sz, sy, sx) order, so the result is bit-identical to lao_at.  The tap offsets
 // are template parameters (NO0, NO0 + 1 below, PO0, PO0 + 1 above the voxel): the loop over planes unrolls fully and
 // the window of live planes (PO0 - NO0 + 2 planes x 4 floats) stays in registers.
 // A plane whose four tap rows hold no hair contributes exact zeros (+0 * w + +0 * w, w >= 0) and is not read; an
 // output whose four planes are all such planes is the empty-space constant.
-template <int NO0, int PO0, class Emit>
+template <int NO0, int PO0, int TZ, class Emit>
 __device__ __forceinline__ void lao_column(const PrefilterArgs& A, const float* __restrict__ column, const uint32_t* __restrict__ flagcol,
                                            int plane_floats, int row_floats, int BY, bool tile_any, float ao_empty, int n_out, Emit&& emit) {
     // column  = texel (lane, jy, kz = 0) of the float tile; flagcol = row flag of (jy, kz = 0)
     constexpr int SPAN = PO0 - NO0 + 1;                  // planes between the first and the last tap plane of an output
-    constexpr int NQ = kPfTZ + SPAN;                     // planes q = 0 .. NQ-1 sit at z offset q + NO0 from output 0
+    constexpr int NQ = TZ + SPAN;                        // planes q = 0 .. NQ-1 sit at z offset q + NO0 from output 0
     const int oy[4] = {NO0, NO0 + 1, PO0, PO0 + 1};
     const AxisTaps ax[2] = {A.neg, A.pos};
     float yl[NQ][4];                                     // [q][2 * sx + sy]
@@ -231,9 +228,9 @@ __device__ __forceinline__ void pf_mbar_wait(uint32_t bar, uint32_t parity) {
 struct PfSmemPlan {
     uint32_t stage_bytes, stage1, ftile, flags, lut, oplut, gw, bars, total;
 };
-__host__ __device__ inline PfSmemPlan pf_plan(int halo, int g_range) {
+__host__ __device__ inline PfSmemPlan pf_plan(int halo, int g_range, int tz) {
     PfSmemPlan p;
-    const uint32_t BY = kPfTY + 2 * halo, BZ = kPfTZ + 2 * halo, FX = kPfTX + 2 * halo;
+    const uint32_t BY = kPfTY + 2 * halo, BZ = tz + 2 * halo, FX = kPfTX + 2 * halo;
     p.stage_bytes = (kPfBX * BY * BZ + 127u) & ~127u;
     p.stage1 = p.stage_bytes;
     p.ftile = 2 * p.stage_bytes;
@@ -247,19 +244,19 @@ __host__ __device__ inline PfSmemPlan pf_plan(int halo, int g_range) {
     return p;
 }
 
-// NO0 / PO0: the AO tap offsets as compile-time constants (lao_column: one warp per y row, the tile's kPfTZ outputs of a
+// NO0 / PO0: the AO tap offsets as compile-time constants (lao_column: one warp per y row, the tile's TZ outputs of a
 // lane as one register-tiled column), or kPfRowWise: offsets read from A, one lao_at per voxel (any radius, and the
 // launches that do not ask for AO).
 constexpr int kPfRowWise = 99;
-constexpr int kPfVariantCount = 10;                  // row-wise + 9 column instantiations (the host's dispatch table)
+constexpr int kPfVariantCount = 19;                  // row-wise + 9 column instantiations x 2 tile depths (the host's dispatch table)
 static_assert(kPfThreads / 32 == kPfTY, "one warp per y row of the tile");
 
-template <int NO0, int PO0>
-__global__ void __launch_bounds__(kPfThreads, VKHR_B200_PF_MIN_CTAS)
+template <int NO0, int PO0, int TZ>
+__global__ void __launch_bounds__(kPfThreads, TZ == kPfTZ ? 3 : 2)        // measured: 2.09 ms (one CTA of 166 registers) -> 1.41 ms at 512^3
 k_prefilter_tiled(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ PrefilterArgs A) {
     extern __shared__ __align__(128) unsigned char pf_smem[];
-    const int h = A.halo, BY = kPfTY + 2 * h, BZ = kPfTZ + 2 * h, FX = kPfTX + 2 * h;
-    const PfSmemPlan P = pf_plan(h, A.g_range);
+    const int h = A.halo, BY = kPfTY + 2 * h, BZ = TZ + 2 * h, FX = kPfTX + 2 * h;
+    const PfSmemPlan P = pf_plan(h, A.g_range, TZ);
     float* ftile = reinterpret_cast<float*>(pf_smem + P.ftile);
     uint32_t* rowflag = reinterpret_cast<uint32_t*>(pf_smem + P.flags);
     float* lut = reinterpret_cast<float*>(pf_smem + P.lut);
@@ -273,7 +270,7 @@ k_prefilter_tiled(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     auto tile_origin = [&](uint32_t t, int& x0, int& y0, int& z0) {
         x0 = (int)(t % A.tiles_x) * kPfTX;
         y0 = (int)((t / A.tiles_x) % A.tiles_y) * kPfTY;
-        z0 = (int)(t / (A.tiles_x * A.tiles_y)) * kPfTZ;
+        z0 = (int)(t / (A.tiles_x * A.tiles_y)) * TZ;
     };
     auto issue = [&](uint32_t t, uint32_t buf) {
         int x0, y0, z0;
@@ -329,7 +326,7 @@ k_prefilter_tiled(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                     if (!out) continue;
                     const bool vec = (reinterpret_cast<uintptr_t>(out) & 15u) == 0u;
                     const float4 v4 = make_float4(vals[o], vals[o], vals[o], vals[o]);
-                    for (int q = tid; q < (kPfTX / 4) * kPfTY * kPfTZ; q += kPfThreads) {
+                    for (int q = tid; q < (kPfTX / 4) * kPfTY * TZ; q += kPfThreads) {
                         const int X = x0 + 4 * (q % (kPfTX / 4)), Y = y0 + (q / (kPfTX / 4)) % kPfTY, Z = z0 + q / ((kPfTX / 4) * kPfTY);
                         if (Y >= A.H || Z >= A.D || X >= A.W) continue;
                         float* dst = out + ((size_t)X + (size_t)Y * A.W + (size_t)Z * A.W * A.H);
@@ -365,21 +362,22 @@ k_prefilter_tiled(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         }
         const int tile_any = __syncthreads_or(mine);
 
-        // ---- AO, column form: warp = y row jy, lane = x, the kPfTZ outputs along z from one pass over the planes ----
+        // ---- AO, column form: warp = y row jy, lane = x, the TZ outputs along z from one pass over the planes ----
         if constexpr (NO0 != kPfRowWise) {
             const int X = x0 + lane, Y = y0 + warp;
             if (A.ao && Y < A.H) {                                            // warp-uniform
                 const size_t zs = (size_t)A.W * A.H;
                 float* out = A.ao + ((size_t)X + (size_t)Y * A.W + (size_t)z0 * zs);
                 const bool inside = X < A.W;
-                lao_column<NO0, PO0>(A, ftile + (h * BY + (warp + h)) * FX + (lane + h), rowflag + h * BY + (warp + h),
-                                     BY * FX, FX, BY, tile_any != 0, ao_empty, min(kPfTZ, A.D - z0),
+                lao_column<NO0, PO0, TZ>(A, ftile + (h * BY + (warp + h)) * FX + (lane + h), rowflag + h * BY + (warp + h),
+                                     BY * FX, FX, BY, tile_any != 0, ao_empty, min(TZ, A.D - z0),
                                      [&](int kz, float r) { if (inside) __stcs(out + (size_t)kz * zs, r); });
             }
         }
 
         // ---- one output row (32 voxels along x) per warp-iteration ---------------------------------------------
-        for (int rr = warp; rr < kPfTY * kPfTZ; rr += kPfThreads / 32) {
+        const bool row_work = A.opacity != nullptr || A.gauss != nullptr || (NO0 == kPfRowWise && A.ao != nullptr);
+        for (int rr = warp; row_work && rr < kPfTY * TZ; rr += kPfThreads / 32) {
             const int jy = rr % kPfTY, kz = rr / kPfTY;
             const int X = x0 + lane, Y = y0 + jy, Z = z0 + kz;
             if (Y >= A.H || Z >= A.D) continue;                               // warp-uniform

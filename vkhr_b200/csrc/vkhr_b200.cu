@@ -109,6 +109,7 @@ struct DevBuf {
 struct vkhr_b200_ctx {
     int device = 0;
     int sm_count = 0;
+    size_t smem_per_sm = 0;       // shared memory of one SM (bytes): how many CTAs of the tiled prefilter fit
     cudaStream_t stream = nullptr;
     std::string err;
     uint64_t launches = 0;
@@ -552,6 +553,7 @@ int vkhr_b200_create(int device, vkhr_b200_ctx** out) {
     vkhr_b200_ctx* ctx = new vkhr_b200_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_per_sm = prop.sharedMemPerMultiprocessor;
     if (cudaSetDevice(device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx;
@@ -1075,14 +1077,15 @@ AxisTaps axis_taps(float r, bool positive) {
     return a;
 }
 
-// instantiations of the tiled kernel: [0] row-wise (offsets at run time), then the column form for the tap offsets
+// instantiations of the tiled kernel: [0] row-wise (tap offsets at run time), then the column form for the tap offsets
 // (neg.o0, pos.o0) of a non-integer radius with floor f: (-f-1, f), and of an integer radius r: (-r, r), up to radius 4
-// (the default is 2.5; wider windows need more than 200 registers per thread and stay row-wise)
+// (the default is 2.5; wider windows need more than 200 registers per thread and stay row-wise), each with tiles 8 and
+// 16 voxels deep
 typedef void (*PfKernel)(const CUtensorMap, const PrefilterArgs);
-struct PfVariant { int no0, po0; PfKernel kernel; };
-#define PF_COL(n, p) {n, p, k_prefilter_tiled<n, p>}
+struct PfVariant { int no0, po0, tz; PfKernel kernel; };
+#define PF_COL(n, p) {n, p, kPfTZ, k_prefilter_tiled<n, p, kPfTZ>}, {n, p, kPfTZDeep, k_prefilter_tiled<n, p, kPfTZDeep>}
 const PfVariant kPfVariantTable[] = {
-    {kPfRowWise, kPfRowWise, k_prefilter_tiled<kPfRowWise, kPfRowWise>},
+    {kPfRowWise, kPfRowWise, kPfTZ, k_prefilter_tiled<kPfRowWise, kPfRowWise, kPfTZ>},
     PF_COL(0, 0), PF_COL(-1, 0), PF_COL(-1, 1), PF_COL(-2, 1), PF_COL(-2, 2), PF_COL(-3, 2), PF_COL(-3, 3), PF_COL(-4, 3), PF_COL(-4, 4),
 };
 #undef PF_COL
@@ -1143,7 +1146,7 @@ int vkhr_b200_prefilter_dev(vkhr_b200_ctx* ctx, const uint8_t* d_densities, uint
         halo = std::max(halo, A.g_range);
     }
     A.halo = halo;
-    A.tiles_x = (W + kPfTX - 1) / kPfTX; A.tiles_y = (H + kPfTY - 1) / kPfTY; A.tiles_z = (D + kPfTZ - 1) / kPfTZ;
+    A.tiles_x = (W + kPfTX - 1) / kPfTX; A.tiles_y = (H + kPfTY - 1) / kPfTY;
     cudaStream_t s = pick(ctx, stream);
     PhaseMark mk(ctx, s, PH_PREFILTER);
     const bool tiled = !(P.flags & VKHR_B200_PREFILTER_GENERIC) && halo <= kPfMaxHalo && (W % 16u) == 0 &&
@@ -1157,24 +1160,28 @@ int vkhr_b200_prefilter_dev(vkhr_b200_ctx* ctx, const uint8_t* d_densities, uint
     }
     EncodeTiledFn encode = encode_tiled_fn();
     if (!encode) return fail(ctx, VKHR_B200_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    // AO with tap offsets the column kernel is instantiated for (every radius up to 4 voxels) takes that instantiation --
+    // with the deep tile when two CTAs of it fit an SM -- everything else the row-wise one
+    int variant = 0;
+    if (d_ao && !(P.flags & VKHR_B200_PREFILTER_ROWWISE) && A.neg.o1 == A.neg.o0 + 1 && A.pos.o1 == A.pos.o0 + 1) {
+        const bool deep = 2u * (pf_plan(halo, A.g_range, kPfTZDeep).total + 1024u) <= (uint32_t)ctx->smem_per_sm && D > (uint32_t)kPfTZ;
+        for (int v = 1; v < kPfVariants; ++v)
+            if (kPfVariantTable[v].no0 == A.neg.o0 && kPfVariantTable[v].po0 == A.pos.o0 && kPfVariantTable[v].tz == (deep ? kPfTZDeep : kPfTZ))
+                variant = v;
+    }
+    const PfKernel kernel = kPfVariantTable[variant].kernel;
+    const int tz = kPfVariantTable[variant].tz;
+    A.tiles_z = (D + tz - 1) / tz;
     CUtensorMap tmap;
     const cuuint64_t gdim[3] = {W, H, D};
     const cuuint64_t gstride[2] = {(cuuint64_t)W, (cuuint64_t)W * H};                 // bytes, dims 1 and 2
-    const cuuint32_t box[3] = {(cuuint32_t)kPfBX, (cuuint32_t)(kPfTY + 2 * halo), (cuuint32_t)(kPfTZ + 2 * halo)};
+    const cuuint32_t box[3] = {(cuuint32_t)kPfBX, (cuuint32_t)(kPfTY + 2 * halo), (cuuint32_t)(tz + 2 * halo)};
     const cuuint32_t estride[3] = {1, 1, 1};
     const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(d_densities), gdim, gstride, box, estride,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(ctx, VKHR_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)cr));
-    const PfSmemPlan plan = pf_plan(halo, A.g_range);
-    // AO with tap offsets the column kernel is instantiated for (every radius of the UI range 0..8 whose halo fits a
-    // tile) takes that instantiation; everything else the row-wise one
-    int variant = 0;
-    if (d_ao && !(P.flags & VKHR_B200_PREFILTER_ROWWISE))
-        for (int v = 1; v < kPfVariants; ++v)
-            if (kPfVariantTable[v].no0 == A.neg.o0 && kPfVariantTable[v].po0 == A.pos.o0 && A.neg.o1 == A.neg.o0 + 1 && A.pos.o1 == A.pos.o0 + 1)
-                variant = v;
-    const PfKernel kernel = kPfVariantTable[variant].kernel;
+    const PfSmemPlan plan = pf_plan(halo, A.g_range, tz);
     if (plan.total > ctx->pf_smem_opted[variant]) {
         CU_CHECK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total));
         ctx->pf_smem_opted[variant] = plan.total;
