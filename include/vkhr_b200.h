@@ -69,12 +69,17 @@ enum {
     /* Apply Volume::normalize() (hair_style.cc:344-357) to the densities, as
      * the only caller does (rasterizer/hair_style.cc:77). */
     VKHR_B200_NORMALIZE = 1u << 1,
-    /* Kernel strategy override (default: chosen from the grid size).
+    /* Kernel strategy override (default: BRICK8 where it can run, else PACKED8, else COUNT32).
      * COUNT32: u32 hit counts in context scratch, then clamp to u8.
      * PACKED8: saturating counts kept directly in the u8 output grid
      *          (byte-packed 32-bit atomics, exact overflow repair). */
     VKHR_B200_STRATEGY_COUNT32 = 1u << 8,
-    VKHR_B200_STRATEGY_PACKED8 = 1u << 9
+    VKHR_B200_STRATEGY_PACKED8 = 1u << 9,
+    /* BRICK8: PACKED8 counted in a context-owned scratch volume stored as 4x4x2-voxel bricks (one
+     *          32-byte sector each, so neighbouring samples of a strand share atomic request packets),
+     *          then copied out to the x-fastest output layout.  Uniform strands on grids of at most
+     *          2^24 voxels with W % 4 == H % 4 == D % 2 == 0; anything else falls back to PACKED8. */
+    VKHR_B200_STRATEGY_BRICK8 = 1u << 10
 };
 
 /* 2x2x2 reduction functors for vkhr_b200_downsample (Volume::downsample takes
@@ -93,6 +98,9 @@ VKHR_B200_API void* vkhr_b200_stream(vkhr_b200_ctx* ctx);
 VKHR_B200_API int vkhr_b200_synchronize(vkhr_b200_ctx* ctx);
 /* Number of kernels this context has launched so far. */
 VKHR_B200_API uint64_t vkhr_b200_launch_count(const vkhr_b200_ctx* ctx);
+/* Strategy the last voxelisation of this context ran with: VKHR_B200_STRATEGY_COUNT32 / _PACKED8 / _BRICK8
+ * (0 before the first call).  Introspection for tests and benchmarks; no reference counterpart. */
+VKHR_B200_API uint32_t vkhr_b200_last_strategy(const vkhr_b200_ctx* ctx);
 
 /* Per-phase device timing.  While enabled, every voxelize call records CUDA
  * events on its launching stream around its phases; profile_read waits for

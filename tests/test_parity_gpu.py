@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 import vkhr_b200
 from vkhr_b200 import HairStyle, capi, synth
 
-STRATEGIES = [0, capi.STRATEGY_COUNT32, capi.STRATEGY_PACKED8]
+STRATEGIES = [0, capi.STRATEGY_COUNT32, capi.STRATEGY_PACKED8, capi.STRATEGY_BRICK8]   # BRICK8 falls back to PACKED8 where it cannot run
 
 
 def _fnv(port, a):
@@ -240,7 +240,7 @@ def test_device_api_batch_and_shards(vox, port):
         insts.append({"vertices": torch.from_numpy(v).to(dev).reshape(-1), "segs_per_strand": s,
                       "aabb_origin": lo, "aabb_size": size,
                       "out": torch.full((W * H * D,), 9, dtype=torch.uint8, device=dev)})
-    for strat in (0, capi.STRATEGY_COUNT32):
+    for strat in (0, capi.STRATEGY_COUNT32, capi.STRATEGY_BRICK8):
         for ins in insts:
             ins["out"].fill_(9)
         vox.voxelize_segments_batch_dev(insts, W, H, D, flags=strat)
@@ -576,3 +576,94 @@ def test_fake_rank_u8_combine_equals_single_voxelisation(vox, port, k, res):
     torch.cuda.synchronize()
     for r in range(k):
         assert np.array_equal(outs[r, :nv].cpu().numpy(), want), f"fake rank {r} (sparse)"
+
+
+# ---- BRICK8: the brick-ordered scratch volume + copy-out ------------------------------------------------------------
+
+def test_brick8_runs_where_it_can_and_falls_back_elsewhere(vox, port):
+    v, n, s = synth.shape("ponytail", seed=31, seg_len=0.8, scale=0.02)
+    lo, hi = port.generate_bounding_box(v)
+    size = (hi - lo).astype(np.float32)
+    idx = port.generate_indices(n, s)
+    B = capi.STRATEGY_BRICK8
+    cases = [((64, 64, 64), True, B), ((64, 32, 16), True, B), ((4, 4, 2), True, B), ((128, 8, 6), True, B), ((36, 20, 8), True, B),
+             ((64, 64, 64), False, capi.STRATEGY_PACKED8),          # explicit index pairs
+             ((30, 20, 9), True, capi.STRATEGY_COUNT32),            # W % 4 != 0 and W*H*D % 16 != 0
+             ((30, 20, 10), True, capi.STRATEGY_PACKED8),           # W % 4 != 0
+             ((32, 32, 15), True, capi.STRATEGY_PACKED8)]           # D odd
+    for flag in (B, 0):                                             # BRICK8 is also what the default picks where it can run
+        for (W, H, D), uniform, expect in cases:
+            want = port.voxelize_segments(v, idx, lo, size, W, H, D)
+            got = vox.voxelize_segments(v, None if uniform else idx, lo, size, W, H, D, segs_per_strand=s if uniform else 0, flags=flag)
+            assert vox.last_strategy == expect, ((W, H, D), uniform, vox.last_strategy)
+            assert np.array_equal(got, want), ((W, H, D), uniform)
+    got = vox.voxelize_segments(v, None, lo, size, 64, 64, 64, segs_per_strand=s, flags=B | capi.INDEX_EXACT)
+    assert vox.last_strategy == capi.STRATEGY_PACKED8                                   # exact-index mode keeps the linear layout
+    assert np.array_equal(got, port.voxelize_segments(v, idx, lo, size, 64, 64, 64, flags=capi.INDEX_EXACT))
+
+
+@pytest.mark.parametrize("res", [(8, 8, 4), (16, 8, 2), (4, 4, 2), (12, 12, 6)])
+def test_brick8_saturation_is_repaired_exactly(vox, port, res):
+    """More than 255 hits per voxel: the byte carries inside the brick word, the word is flagged at its LINEAR
+    position and recounted after the copy-out."""
+    W, H, D = res
+    v, n, s = synth.shape("ponytail", seed=5, seg_len=1.0, scale=0.03)
+    lo, hi = port.generate_bounding_box(v)
+    size = (hi - lo).astype(np.float32)
+    want = port.voxelize_segments(v, port.generate_indices(n, s), lo, size, W, H, D)
+    assert (want == 255).sum() > 0
+    for _ in range(2):                                              # the second call sees the scratch the first one left
+        got = vox.voxelize_segments(v, None, lo, size, W, H, D, segs_per_strand=s, flags=capi.STRATEGY_BRICK8)
+        assert vox.last_strategy == capi.STRATEGY_BRICK8
+        assert np.array_equal(got, want)
+        assert np.array_equal(vox.voxelize_segments(v, None, lo, size, W, H, D, segs_per_strand=s, flags=capi.STRATEGY_BRICK8 | capi.NORMALIZE),
+                              port.normalize(want))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_brick8_strands_leaving_the_box_and_scratch_reuse(vox, port, seed):
+    """A bounding box smaller than the hair (negative and beyond-the-grid coordinates: the reference's fp32 index
+    still lands some of those samples in the grid), then a different style and resolution on the same context:
+    the scratch must come back all zero every time."""
+    rng = np.random.default_rng(4000 + seed)
+    for trial in range(3):
+        n, s = int(rng.integers(50, 2500)), int(rng.integers(1, 24))
+        v = synth.strands(n, s, seed=int(rng.integers(1, 2**31)), seg_len=float(rng.uniform(0.2, 6.0)),
+                          curl=float(rng.uniform(0.1, 2.0)), gravity=float(rng.uniform(0, 0.6)))
+        W, H, D = int(rng.choice([4, 8, 16, 36, 64, 128])), int(rng.choice([4, 8, 20, 64, 100])), int(rng.choice([2, 4, 6, 32, 64]))
+        lo, hi = v.min(axis=0), v.max(axis=0)
+        shrink = np.float32(rng.uniform(0.0, 0.35))
+        lo2 = (lo + shrink * (hi - lo)).astype(np.float32)
+        size = ((hi - lo) * np.float32(1.0 - 1.7 * shrink)).astype(np.float32)
+        want = port.voxelize_segments(v, port.generate_indices(n, s), lo2, size, W, H, D)
+        got = vox.voxelize_segments(v, None, lo2, size, W, H, D, segs_per_strand=s, flags=capi.STRATEGY_BRICK8)
+        assert vox.last_strategy == capi.STRATEGY_BRICK8
+        assert np.array_equal(got, want), (seed, trial, (W, H, D))
+
+
+def test_brick8_crowd_at_256_equals_packed8(vox, port):
+    """The bench configuration in small: ponytail-shaped instances at 256^3 through the batch entry point, every
+    output byte written (pre-filled with 9), identical to PACKED8; instance 0 against the oracle."""
+    import torch
+    dev = torch.device("cuda", 0)
+    W = H = D = 256
+    insts = []
+    for k in range(3):
+        v, n, s = synth.shape("ponytail", seed=900 + k, seg_len=0.5, scale=0.25 if k else 1.0)
+        lo, hi = synth.host_bounding_box(v)
+        insts.append({"vertices": torch.from_numpy(v).to(dev).reshape(-1), "segs_per_strand": s, "aabb_origin": lo,
+                      "aabb_size": (hi - lo).astype(np.float32), "out": torch.full((W * H * D,), 9, dtype=torch.uint8, device=dev),
+                      "host": (v, n, s, lo, hi)})
+    outs = {}
+    for strat in (capi.STRATEGY_PACKED8, capi.STRATEGY_BRICK8, capi.STRATEGY_BRICK8):
+        for ins in insts:
+            ins["out"].fill_(9)
+        vox.voxelize_segments_batch_dev([{k: x for k, x in ins.items() if k != "host"} for ins in insts], W, H, D, flags=strat)
+        torch.cuda.synchronize()
+        assert vox.last_strategy == strat
+        outs[strat] = [ins["out"].clone() for ins in insts]
+    for a, b in zip(outs[capi.STRATEGY_PACKED8], outs[capi.STRATEGY_BRICK8]):
+        assert torch.equal(a, b)
+    v, n, s, lo, hi = insts[1]["host"]
+    want = port.voxelize_segments(v, port.generate_indices(n, s), lo, (hi - lo).astype(np.float32), W, H, D)
+    assert np.array_equal(outs[capi.STRATEGY_BRICK8][1].cpu().numpy(), want)

@@ -28,6 +28,7 @@ INDEX_EXACT = 1 << 0
 NORMALIZE = 1 << 1
 STRATEGY_COUNT32 = 1 << 8
 STRATEGY_PACKED8 = 1 << 9
+STRATEGY_BRICK8 = 1 << 10
 
 DOWNSAMPLE_MAX, DOWNSAMPLE_MEAN, DOWNSAMPLE_SUM, DOWNSAMPLE_MIN = 0, 1, 2, 3
 
@@ -112,6 +113,7 @@ _PROTOTYPES = {
     "vkhr_b200_stream": (_P, [c_ctx]),
     "vkhr_b200_synchronize": (_int, [c_ctx]),
     "vkhr_b200_launch_count": (_u64, [c_ctx]),
+    "vkhr_b200_last_strategy": (C.c_uint32, [c_ctx]),
     "vkhr_b200_profile_enable": (_int, [c_ctx, _int]),
     "vkhr_b200_profile_read": (_int, [c_ctx, C.c_double * 4, C.c_uint32 * 4]),
     "vkhr_b200_selftest_division": (_int, [c_ctx, C.c_float, _u64, _u64, C.POINTER(_u64)]),

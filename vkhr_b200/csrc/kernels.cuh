@@ -31,6 +31,7 @@ struct InstanceDev {
     uint32_t*       counts;         // W*H*D u32 (COUNT32 / recount scratch) or nullptr
     uint32_t*       ovf_bitmap;     // PACKED8: 1 bit per 32-bit word of `densities`
     uint32_t*       ovf_flag;       // PACKED8: != 0 when any word overflowed
+    uint8_t*        brick;          // BRICK8: W*H*D u8 scratch in brick order (zero between calls), or nullptr
     uint32_t        n_tiles;        // CTAs this instance needs in its walk kernel
     uint32_t        kind;           // WalkKind
     uint32_t        vps_magic;      // floor(2^32 / (segs_per_strand + 1)) + 1   (strand-end test without a division)
@@ -112,6 +113,44 @@ struct SinkPacked8 {
     __device__ __forceinline__ void words_pin() { asm volatile("" : "+l"(words)); }
 };
 
+// BRICK8: the same counter words, stored brick by brick in a scratch volume (brick_word in walk.cuh).  The pending
+// ring keeps the LINEAR index: its low two bits name the byte in either layout, and an overflow is flagged at the
+// linear word, where k_repair_packed rewrites it after the copy-out (k_untile_batch).
+// (Moving the two rare paths -- overflow flag, linear-index samples -- into __noinline__ functions was measured: the
+// call ABI costs spills in the tile loop and the walk went from 1.21 to 1.82 ms; they stay inline.)
+struct SinkPacked8Brick {
+    static constexpr int kDepth = 4;
+    uint32_t* words;                // the brick-ordered scratch
+    uint32_t* ovf_bitmap;
+    uint32_t* ovf_flag;
+    uint32_t wh;                    // (W / 4) | (H / 4) << 16: only the literal (slow) path needs the resolution
+    uint32_t pend_old[kDepth] = {0, 0, 0, 0};
+    uint32_t pend_idx[kDepth] = {0, 0, 0, 0};
+    template <int SLOT>
+    __device__ __forceinline__ void check() {
+        if (__byte_perm(pend_old[SLOT], 0u, 0x4440u | (pend_idx[SLOT] & 3u)) == 0xFFu) {
+            const uint32_t w = pend_idx[SLOT] >> 2;
+            atomicOr(ovf_bitmap + (w >> 5), 1u << (w & 31u));
+            *ovf_flag = 1u;
+        }
+    }
+    template <int SLOT>
+    __device__ __forceinline__ void put_brick(uint32_t lin, uint32_t bword) {
+        check<SLOT>();
+        pend_old[SLOT] = atom_add_u32(words + bword, 1u << ((lin & 3u) * 8u));
+        pend_idx[SLOT] = lin;
+    }
+    template <int SLOT>
+    __device__ __forceinline__ void put(uint32_t lin) {            // literal path: voxel from the linear index
+        const uint32_t W = (wh & 0xFFFFu) << 2, H = (wh >> 16) << 2;
+        const uint32_t x = lin % W, t = lin / W, y = t % H, z = t / H;
+        const uint32_t brick = ((z >> 1) * (H >> 2) + (y >> 2)) * (W >> 2) + (x >> 2);
+        put_brick<SLOT>(lin, (brick << 3) | ((z & 1u) << 2) | (y & 3u));
+    }
+    __device__ __forceinline__ void finish() { check<0>(); check<1>(); check<2>(); check<3>(); }
+    __device__ __forceinline__ void words_pin() { asm volatile("" : "+l"(words)); }
+};
+
 // Recount pass of PACKED8: only samples landing in flagged words are counted,
 // into the u32 scratch grid.
 struct SinkRecount {
@@ -131,6 +170,11 @@ template <> struct SinkOf<0> { using type = SinkCount32;
 template <> struct SinkOf<1> { using type = SinkPacked8;
     __device__ static type make(const InstanceDev& I) { SinkPacked8 k; k.words = reinterpret_cast<uint32_t*>(I.densities); k.ovf_bitmap = I.ovf_bitmap; k.ovf_flag = I.ovf_flag; return k; } };
 
+template <> struct SinkOf<3> { using type = SinkPacked8Brick;
+    __device__ static type make(const InstanceDev& I) {
+        SinkPacked8Brick k; k.words = reinterpret_cast<uint32_t*>(I.brick); k.ovf_bitmap = I.ovf_bitmap; k.ovf_flag = I.ovf_flag;
+        k.wh = (I.grid.W >> 2) | ((I.grid.H >> 2) << 16); return k; } };
+
 // ---------------------------------------------------------------------------
 // Walk kernel for uniform strands (no index buffer): the hot kernel.
 //
@@ -145,7 +189,7 @@ template <> struct SinkOf<1> { using type = SinkPacked8;
 // read from HBM once (1/31 twice); per-instance constants come from the constant
 // bank (the batch is a __grid_constant__ parameter); the L1TEX path carries only
 // the vertex stream and the reds.  blockIdx.y + first = instance.
-// MODE 0 = COUNT32, 1 = PACKED8.
+// MODE 0 = COUNT32, 1 = PACKED8, 3 = BRICK8 (with EXACT = 3).
 // ---------------------------------------------------------------------------
 constexpr uint32_t kTilesPerWarp = 8;
 constexpr uint32_t kWarpsPerBlock = kWalkThreads / 32;
@@ -480,17 +524,42 @@ __global__ void __launch_bounds__(256) k_zero16(uint4* __restrict__ p, uint64_t 
 
 // PACKED8 clear for a batch: densities, overflow bitmap and flag of every instance.
 // blockIdx.y + first = instance.  n_voxels % 16 == 0 is guaranteed by the host (else COUNT32).
-__global__ void __launch_bounds__(256) k_clear_packed_batch(const __grid_constant__ Batch B, uint32_t first) {
+// volumes == 0 (BRICK8): bitmaps and flags only -- the copy-out writes every byte of the densities.
+__global__ void __launch_bounds__(256) k_clear_packed_batch(const __grid_constant__ Batch B, uint32_t first, uint32_t volumes) {
     const InstanceDev& I = B.inst[first + blockIdx.y];
     const uint4 z = make_uint4(0, 0, 0, 0);
     uint4* d = reinterpret_cast<uint4*>(I.densities);
-    const uint32_t n16 = I.grid.n_voxels >> 4;
+    const uint32_t n16 = volumes ? I.grid.n_voxels >> 4 : 0u;
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     for (uint32_t i = t; i < n16; i += stride) d[i] = z;
     const uint32_t n_bm = (I.grid.n_voxels / 4 + 31) / 32;          // bitmap words
     for (uint32_t i = t; i < n_bm; i += stride) I.ovf_bitmap[i] = 0u;
     if (t == 0) *I.ovf_flag = 0u;
+}
+
+// BRICK8 copy-out: brick-ordered scratch -> the x-fastest output volume (Volume::densities, hair_style.hh:89-101),
+// one brick (two 16-byte loads) per thread; the 32 bricks of a warp are consecutive in x, so each of its eight
+// 4-byte stores covers 128 contiguous bytes of one output row.  A brick that held anything is zeroed behind the
+// read, which restores the scratch's all-zero state for the next call without a clear pass.
+__global__ void __launch_bounds__(256) k_untile_batch(const __grid_constant__ Batch B, uint32_t first) {
+    const InstanceDev& I = B.inst[first + blockIdx.y];
+    const uint32_t wrow = I.grid.W >> 2, byn = I.grid.H >> 2;             // words (= bricks) per row, brick rows per slab
+    const uint32_t wslab = wrow * I.grid.H;
+    const uint32_t n_bricks = wrow * byn * (I.grid.D >> 1);
+    uint4* __restrict__ src = reinterpret_cast<uint4*>(I.brick);
+    uint32_t* __restrict__ dst = reinterpret_cast<uint32_t*>(I.densities);
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < n_bricks; b += stride) {
+        const uint4 q0 = __ldcs(src + 2u * b), q1 = __ldcs(src + 2u * b + 1u);   // z even, z odd: rows y & 3 = 0..3
+        const uint32_t bx = b % wrow, t = b / wrow, by = t % byn, bz = t / byn;
+        uint32_t* o = dst + (size_t)(2u * bz) * wslab + (size_t)(4u * by) * wrow + bx;
+        __stcs(o, q0.x); __stcs(o + wrow, q0.y); __stcs(o + 2u * wrow, q0.z); __stcs(o + 3u * wrow, q0.w);
+        o += wslab;
+        __stcs(o, q1.x); __stcs(o + wrow, q1.y); __stcs(o + 2u * wrow, q1.z); __stcs(o + 3u * wrow, q1.w);
+        if ((q0.x | q0.y | q0.z | q0.w | q1.x | q1.y | q1.z | q1.w) != 0u) { src[2u * b] = z; src[2u * b + 1u] = z; }
+    }
 }
 
 // densities = min(counts, 255)  (hair_style.cc:322: `if (d != 255) d += 1`),

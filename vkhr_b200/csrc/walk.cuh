@@ -265,7 +265,16 @@ __device__ __forceinline__ bool sample_index(const GridParams& g, float rx, floa
     }
 }
 
+// Brick layout of the BRICK8 scratch volume: a brick is 4 x 4 x 2 voxels (x, y, z) = eight 32-bit words = one 32-byte
+// sector; word ((z & 1) << 2) | (y & 3) of the brick holds the four voxels x & ~3 .. x | 3 of that row -- the same
+// four voxels, in the same byte order, as word idx >> 2 of the x-fastest volume (W % 4 == 0).
+__device__ __forceinline__ uint32_t brick_word(const GridParams& g, int ix, int iy, int iz) {
+    const uint32_t brick = ((uint32_t)(iz >> 1) * (g.H >> 2) + (uint32_t)(iy >> 2)) * (g.W >> 2) + (uint32_t)(ix >> 2);
+    return (brick << 3) | ((uint32_t)(iz & 1) << 2) | (uint32_t)(iy & 3);
+}
+
 // The sampled walk of one segment per lane, end points in voxel space (hair_style.cc:315-328).
+// EXACT == 3: the int32 index of EXACT == 2 for a sink that counts in the brick layout (put_brick).
 // `active` = this lane has a segment.
 template <int EXACT, bool CHECK_TIP = true, class Sink>
 __device__ __forceinline__ void walk_voxel_space_warp(const GridParams& g, bool active,
@@ -279,8 +288,8 @@ __device__ __forceinline__ void walk_voxel_space_warp(const GridParams& g, bool 
     // (EXACT == 2 needs the bound on EVERY end point the warp holds, idle lanes included: lane t's tip is lane
     // t+1's root in the uniform kernel; CHECK_TIP adds the tip for kernels whose tips are not another lane's root)
     bool bounded = __fadd_rn(__fadd_rn(fabsf(rx), fabsf(ry)), fabsf(rz)) < g.pos_limit;
-    if (CHECK_TIP && EXACT == 2) bounded = bounded && (__fadd_rn(__fadd_rn(fabsf(tx), fabsf(ty)), fabsf(tz)) < g.pos_limit);
-    const bool fast = (EXACT == 2 || go ? bounded : true) &&
+    if (CHECK_TIP && EXACT >= 2) bounded = bounded && (__fadd_rn(__fadd_rn(fabsf(tx), fabsf(ty)), fabsf(tz)) < g.pos_limit);
+    const bool fast = (EXACT >= 2 || go ? bounded : true) &&
                       (!go || ((steps >= 9.094947e-13f) && div_fast_ok(dx) && div_fast_ok(dy) && div_fast_ok(dz)));
     if (__all_sync(kFullWarp, fast)) {
         if (go) {
@@ -290,8 +299,19 @@ __device__ __forceinline__ void walk_voxel_space_warp(const GridParams& g, bool 
             dz = div_fast(dz, steps, y);
             // while (steps-- > 0.0f); unrolled by four so that a sink may keep one pending result per position
             auto sample = [&](auto slot) {
-                uint32_t idx;
-                if (sample_index<EXACT>(g, rx, ry, rz, idx)) sink.template put<decltype(slot)::value>(idx);
+                if constexpr (EXACT == 3) {
+                    const int ix = min(__float2int_rd(rx), (int)g.W - 1);
+                    const int iy = min(__float2int_rd(ry), (int)g.H - 1);
+                    const int iz = min(__float2int_rd(rz), (int)g.D - 1);
+                    const uint32_t lin = (uint32_t)((iz * (int)g.H + iy) * (int)g.W + ix);   // the reference's index, as EXACT == 2
+                    if (lin < g.n_voxels) {
+                        if ((ix | iy | iz) >= 0) sink.template put_brick<decltype(slot)::value>(lin, brick_word(g, ix, iy, iz));
+                        else sink.template put<decltype(slot)::value>(lin);   // a negative coordinate that still indexes a voxel
+                    }
+                } else {
+                    uint32_t idx;
+                    if (sample_index<EXACT>(g, rx, ry, rz, idx)) sink.template put<decltype(slot)::value>(idx);
+                }
                 rx = __fadd_rn(rx, dx);
                 ry = __fadd_rn(ry, dy);
                 rz = __fadd_rn(rz, dz);
@@ -306,7 +326,7 @@ __device__ __forceinline__ void walk_voxel_space_warp(const GridParams& g, bool 
             }
         }
     } else if (go) {
-        walk_voxel_space<EXACT>(g, rx, ry, rz, tx, ty, tz, sink);             // the literal code, any input
+        walk_voxel_space<(EXACT == 3 ? 2 : EXACT)>(g, rx, ry, rz, tx, ty, tz, sink);   // the literal code, any input
     }
 }
 

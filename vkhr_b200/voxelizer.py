@@ -60,6 +60,11 @@ class Voxelizer:
         return int(lib.vkhr_b200_launch_count(self._h))
 
     @property
+    def last_strategy(self) -> int:
+        """Strategy flag (capi.STRATEGY_*) the last voxelisation ran with."""
+        return int(lib.vkhr_b200_last_strategy(self._h))
+
+    @property
     def stream(self) -> int:
         return int(lib.vkhr_b200_stream(self._h) or 0)
 
