@@ -317,15 +317,21 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     vox.profile_enable(False)
     ms_instr = p0.elapsed_time(p1)
     walk_ms = prof["walk"]["ms"] / max(prof["walk"]["spans"], 1)             # per launch
+    if vox.last_strategy == capi.STRATEGY_BRICK8:
+        # the volume exists only after the copy-out: the pair (walk, copy-out) is what the algorithmic bytes are held against
+        walk_ms = (prof["walk"]["ms"] + prof["finish"]["ms"]) / args.steps      # one walk + one copy-out (+ the repair's look at the flags) per step
     alg_bytes = I * (12 * V + nvox)                                          # 12*V + W*H*D per instance
     peak, peak_src = hbm_peak()
     achieved = alg_bytes / (walk_ms * 1e-3) / 1e9 if walk_ms > 0 else 0.0
     phases_ms = {k: prof[k]["ms"] / args.steps for k in prof}
     step_ms = ms / args.steps
+    strat = {capi.STRATEGY_COUNT32: (0, "count32", "u32 counts"), capi.STRATEGY_PACKED8: (1, "packed8", "packed u8 atomics in the output volume"),
+             capi.STRATEGY_BRICK8: (3, "brick8", "packed u8 atomics in the brick-ordered scratch volume, + k_untile_batch, the copy-out: kernel_ms is the pair")
+             }.get(vox.last_strategy, (1, "packed8", "packed u8 atomics"))
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": ncu_traffic(f"k_walk_uniform<{0 if args.strategy == 'count32' else 1}>@{I}x{W}^3"),
-        "kernel": "k_walk_uniform (strand walk + packed u8 atomics)", "kernel_ms_per_launch": walk_ms,
+        "traffic": ncu_traffic(f"k_walk_uniform<{strat[0]}>@{I}x{W}^3"),
+        "kernel": f"k_walk_uniform<{strat[0]}> (strand walk, {strat[2]})", "strategy": strat[1], "kernel_ms_per_launch": walk_ms,
         "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
         "phase_ms_per_step": phases_ms, "kernel_share_of_step": (phases_ms["walk"] / (ms_instr / args.steps)) if ms_instr else None,
         "whole_path_frac": (alg_bytes / (step_ms * 1e-3) / 1e9) / peak,
@@ -410,8 +416,12 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         if sigma:
             # secondary bound: one 32-byte atomic request packet per sample; the measured ceiling of
             # packed atomics with one lane per sector on this part is 220 G/s (profiles/r01_microbench.json)
+            # per SECTOR-request, whatever the number of lanes in it; BRICK8 puts 1 / 0.6 samples into one (ncu, profiles/traffic.json)
+            sps = ncu_traffic(f"atom_sectors_per_sample<{strat[0]}>@{I}x{W}^3") or 1.0
+            g_sectors = sigma * n_seg * I * sps / (walk_ms * 1e-3) / 1e9
             roofline["atomic"] = {"samples_per_launch": sigma * n_seg * I, "achieved_Gsamples_s": sigma * n_seg * I / (walk_ms * 1e-3) / 1e9,
-                                  "peak_Gsamples_s": 220.0, "frac": sigma * n_seg * I / (walk_ms * 1e-3) / 1e9 / 220.0,
+                                  "request_sectors_per_sample": sps, "achieved_Gsectors_s": g_sectors,
+                                  "peak_Gsectors_s": 220.0, "frac": g_sectors / 220.0,
                                   "peak_source": "tools/microbench.cu on this pool (profiles/r01_microbench.json)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

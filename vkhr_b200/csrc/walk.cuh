@@ -304,10 +304,8 @@ __device__ __forceinline__ void walk_voxel_space_warp(const GridParams& g, bool 
                     const int iy = min(__float2int_rd(ry), (int)g.H - 1);
                     const int iz = min(__float2int_rd(rz), (int)g.D - 1);
                     const uint32_t lin = (uint32_t)((iz * (int)g.H + iy) * (int)g.W + ix);   // the reference's index, as EXACT == 2
-                    if (lin < g.n_voxels) {
-                        if ((ix | iy | iz) >= 0) sink.template put_brick<decltype(slot)::value>(lin, brick_word(g, ix, iy, iz));
-                        else sink.template put<decltype(slot)::value>(lin);   // a negative coordinate that still indexes a voxel
-                    }
+                    if ((ix | iy | iz) >= 0) sink.template put_brick<decltype(slot)::value>(lin, brick_word(g, ix, iy, iz));   // inside the grid
+                    else if (lin < g.n_voxels) sink.template put<decltype(slot)::value>(lin);   // a negative coordinate that still indexes a voxel
                 } else {
                     uint32_t idx;
                     if (sample_index<EXACT>(g, rx, ry, rz, idx)) sink.template put<decltype(slot)::value>(idx);
