@@ -20,7 +20,12 @@ if os.path.exists(rep):
     wr = float(row["dram__bytes_write.sum"]) * scale[units["dram__bytes_write.sum"]]
     tpath = os.path.join(P, "traffic.json")
     t = json.load(open(tpath)) if os.path.exists(tpath) else {}
-    t["k_walk_uniform<1>@64x256^3"] = int(rd + wr)
-    t["_source"] = f"ncu --set full, one launch of the 64-instance walk ({tag}): dram__bytes_read.sum {rd / 1e9:.3f} GB + dram__bytes_write.sum {wr / 1e9:.3f} GB"
+    mode = 3 if "<(int)3" in row.get("Kernel Name", "") else 1              # BRICK8 or PACKED8 walk
+    t[f"k_walk_uniform<{mode}>@64x256^3"] = int(rd + wr)
+    t["_source" if mode == 1 else "_source_brick8"] = (f"ncu --set full, one launch of the 64-instance walk ({tag}): dram__bytes_read.sum "
+                                                        f"{rd / 1e9:.3f} GB + dram__bytes_write.sum {wr / 1e9:.3f} GB")
+    sectors = row.get("lts__t_sectors_srcunit_tex_op_atom.sum")
+    if mode == 3 and sectors:
+        t["atom_sectors_per_sample<3>@64x256^3"] = round(float(sectors) / 209630528.0, 4)     # samples of the bench frame (bench.py prints them)
     json.dump(t, open(tpath, "w"), indent=1)
     print("traffic", rd, wr)

@@ -13,3 +13,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 12 -c 1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_walk_uniform -s 3 -c 1 -o gpurun_out/prof_walk64 -f \
     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-others > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out | head -40
+timeout 600 ncu --set full --clock-control none -k regex:k_untile_batch -s 3 -c 1 -o gpurun_out/prof_untile64 -f \
+    python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-others > gpurun_out/ncu_untile.log 2>&1
