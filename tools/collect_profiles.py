@@ -20,7 +20,8 @@ if os.path.exists(rep):
     wr = float(row["dram__bytes_write.sum"]) * scale[units["dram__bytes_write.sum"]]
     tpath = os.path.join(P, "traffic.json")
     t = json.load(open(tpath)) if os.path.exists(tpath) else {}
-    mode = 3 if "<(int)3" in row.get("Kernel Name", "") else 1              # BRICK8 or PACKED8 walk
+    import re
+    mode = 3 if re.search(r"k_walk_uniform<\(?(int)?\)?\s*3", row.get("Kernel Name", "")) else 1     # BRICK8 or PACKED8 walk
     t[f"k_walk_uniform<{mode}>@64x256^3"] = int(rd + wr)
     t["_source" if mode == 1 else "_source_brick8"] = (f"ncu --set full, one launch of the 64-instance walk ({tag}): dram__bytes_read.sum "
                                                         f"{rd / 1e9:.3f} GB + dram__bytes_write.sum {wr / 1e9:.3f} GB")
