@@ -143,11 +143,11 @@ def make_instance(seed: int, seg_len: float):
     return v, n, s, lo, (hi - lo).astype(np.float32)
 
 
-def other_configs(vox, dev, args):
+def other_configs(vox, dev, args, flags=0):
     """Short device-resident timings (CUDA events, 20 reps after 3 warm-ups) of the other BASELINE.json configs that
     fit one GPU; inputs are rotated over 8 copies (> L2) for the small sets.  Parity for these lives in tests/."""
     import torch
-    from vkhr_b200 import synth
+    from vkhr_b200 import capi, synth
     out = {}
     cases = [("configs[0] ponytail 256^3, one instance", "ponytail", 0.5, 256, 8),
              ("configs[1] Yuksel-straight-shaped 50,000 x 65 at 512^3", "straight", 0.5, 512, 2),
@@ -166,7 +166,7 @@ def other_configs(vox, dev, args):
             pf = [torch.empty(W ** 3, dtype=torch.float32, device=dev) for _ in range(2)] if prefilter else None
 
             def once(r):
-                vox.voxelize_segments_dev(vt[r % copies], None, lo, size, W, W, W, segs_per_strand=s, out=o[r % copies])
+                vox.voxelize_segments_dev(vt[r % copies], None, lo, size, W, W, W, segs_per_strand=s, out=o[r % copies], flags=flags)
                 if prefilter:
                     vox.prefilter_dev(o[r % copies], W, W, W, ao=pf[0], opacity=pf[1])
             for r in range(3):
@@ -180,7 +180,8 @@ def other_configs(vox, dev, args):
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / reps
             alg = 12 * v.shape[0] + W ** 3 + (W ** 3 * (1 + 4 * 2) if prefilter else 0)      # prefilter N^3 (1 + 4k)
-            out[name] = {"segments": n * s, "ms": ms, "value": n * s / ms / 1e3, "unit": UNIT,
+            sname = {capi.STRATEGY_COUNT32: "count32", capi.STRATEGY_PACKED8: "packed8", capi.STRATEGY_BRICK8: "brick8"}.get(vox.last_strategy)
+            out[name] = {"segments": n * s, "ms": ms, "value": n * s / ms / 1e3, "unit": UNIT, "strategy": sname,
                          "hbm_frac_whole_path": alg / (ms * 1e-3) / 1e9 / hbm_peak()[0]}
             del vt, o, pf
             torch.cuda.empty_cache()
@@ -404,7 +405,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
     others = None
     if rank == 0 and world == 1 and not args.no_others:
-        others = other_configs(vox, dev, args)
+        others = other_configs(vox, dev, args, flags)
     if rank == 0:
         sigma = None
         try:

@@ -641,6 +641,40 @@ def test_brick8_strands_leaving_the_box_and_scratch_reuse(vox, port, seed):
         assert np.array_equal(got, want), (seed, trial, (W, H, D))
 
 
+@pytest.mark.parametrize("res,expect", [((512, 256, 256), capi.STRATEGY_BRICK8), ((1024, 128, 256), capi.STRATEGY_BRICK8),
+                                        ((256, 512, 130), capi.STRATEGY_BRICK8), ((300, 300, 200), capi.STRATEGY_PACKED8)])
+def test_brick8_above_2pow24_voxels_keeps_the_fp32_index_rounding(vox, port, res, expect):
+    """Grids above 2^24 voxels: the reference's fp32 index rounds (hair_style.cc:321), and the ROUNDED index names the
+    voxel.  With W and H powers of two the brick is taken from the bit fields of that index; other sizes stay PACKED8.
+    A box smaller than the hair adds negative / clamped coordinates."""
+    W, H, D = res
+    v, n, s = synth.shape("ponytail", seed=41, seg_len=2.5, scale=0.03)
+    lo, hi = port.generate_bounding_box(v)
+    idx = port.generate_indices(n, s)
+    for shrink in (0.0, 0.2):
+        lo2 = (lo + np.float32(shrink) * (hi - lo)).astype(np.float32)
+        size = ((hi - lo) * np.float32(1.0 - 1.6 * shrink)).astype(np.float32)
+        want = port.voxelize_segments(v, idx, lo2, size, W, H, D)
+        got = vox.voxelize_segments(v, None, lo2, size, W, H, D, segs_per_strand=s, flags=capi.STRATEGY_BRICK8)
+        assert vox.last_strategy == expect
+        assert np.array_equal(got, want), (res, shrink)
+        # the rounding is real at these sizes: the exact-index volume differs
+        if shrink == 0.0 and expect == capi.STRATEGY_BRICK8:
+            assert not np.array_equal(want, port.voxelize_segments(v, idx, lo2, size, W, H, D, flags=capi.INDEX_EXACT))
+
+
+def test_brick8_default_follows_the_segment_density(vox, port):
+    """The default takes BRICK8 only when the copy-out pays: about one segment per 100 voxels or more."""
+    v, n, s = synth.shape("ponytail", seed=43, seg_len=1.0, scale=0.01)            # 1363 strands x 12 segments
+    lo, hi = port.generate_bounding_box(v)
+    size = (hi - lo).astype(np.float32)
+    for res, expect in [((64, 64, 64), capi.STRATEGY_BRICK8), ((128, 128, 128), capi.STRATEGY_PACKED8)]:
+        W, H, D = res
+        got = vox.voxelize_segments(v, None, lo, size, W, H, D, segs_per_strand=s)
+        assert vox.last_strategy == expect, res
+        assert np.array_equal(got, port.voxelize_segments(v, port.generate_indices(n, s), lo, size, W, H, D))
+
+
 def test_brick8_crowd_at_256_equals_packed8(vox, port):
     """The bench configuration in small: ponytail-shaped instances at 256^3 through the batch entry point, every
     output byte written (pre-filled with 9), identical to PACKED8; instance 0 against the oracle."""

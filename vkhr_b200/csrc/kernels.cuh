@@ -118,12 +118,15 @@ struct SinkPacked8 {
 // linear word, where k_repair_packed rewrites it after the copy-out (k_untile_batch).
 // (Moving the two rare paths -- overflow flag, linear-index samples -- into __noinline__ functions was measured: the
 // call ABI costs spills in the tile loop and the walk went from 1.21 to 1.82 ms; they stay inline.)
+// POW2: W and H are powers of two and `wh` holds their logarithms -- a linear index is decomposed by bit fields, which
+// is also how the fast path of large grids finds its brick (walk.cuh, EXACT == 4).
+template <bool POW2>
 struct SinkPacked8Brick {
     static constexpr int kDepth = 4;
     uint32_t* words;                // the brick-ordered scratch
     uint32_t* ovf_bitmap;
     uint32_t* ovf_flag;
-    uint32_t wh;                    // (W / 4) | (H / 4) << 16: only the literal (slow) path needs the resolution
+    uint32_t wh;                    // (W / 4) | (H / 4) << 16 (only the literal path needs it); POW2: log2 W | log2 H << 8
     uint32_t pend_old[kDepth] = {0, 0, 0, 0};
     uint32_t pend_idx[kDepth] = {0, 0, 0, 0};
     template <int SLOT>
@@ -141,7 +144,10 @@ struct SinkPacked8Brick {
         pend_idx[SLOT] = lin;
     }
     template <int SLOT>
+    __device__ __forceinline__ void put_linear(uint32_t lin) { put_brick<SLOT>(lin, brick_word_pow2(lin, wh & 0xFFu, wh >> 8)); }
+    template <int SLOT>
     __device__ __forceinline__ void put(uint32_t lin) {            // literal path: voxel from the linear index
+        if (POW2) { put_linear<SLOT>(lin); return; }
         const uint32_t W = (wh & 0xFFFFu) << 2, H = (wh >> 16) << 2;
         const uint32_t x = lin % W, t = lin / W, y = t % H, z = t / H;
         const uint32_t brick = ((z >> 1) * (H >> 2) + (y >> 2)) * (W >> 2) + (x >> 2);
@@ -170,10 +176,14 @@ template <> struct SinkOf<0> { using type = SinkCount32;
 template <> struct SinkOf<1> { using type = SinkPacked8;
     __device__ static type make(const InstanceDev& I) { SinkPacked8 k; k.words = reinterpret_cast<uint32_t*>(I.densities); k.ovf_bitmap = I.ovf_bitmap; k.ovf_flag = I.ovf_flag; return k; } };
 
-template <> struct SinkOf<3> { using type = SinkPacked8Brick;
+template <> struct SinkOf<3> { using type = SinkPacked8Brick<false>;
     __device__ static type make(const InstanceDev& I) {
-        SinkPacked8Brick k; k.words = reinterpret_cast<uint32_t*>(I.brick); k.ovf_bitmap = I.ovf_bitmap; k.ovf_flag = I.ovf_flag;
+        type k; k.words = reinterpret_cast<uint32_t*>(I.brick); k.ovf_bitmap = I.ovf_bitmap; k.ovf_flag = I.ovf_flag;
         k.wh = (I.grid.W >> 2) | ((I.grid.H >> 2) << 16); return k; } };
+template <> struct SinkOf<4> { using type = SinkPacked8Brick<true>;
+    __device__ static type make(const InstanceDev& I) {
+        type k; k.words = reinterpret_cast<uint32_t*>(I.brick); k.ovf_bitmap = I.ovf_bitmap; k.ovf_flag = I.ovf_flag;
+        k.wh = (31u - (uint32_t)__clz((int)I.grid.W)) | ((31u - (uint32_t)__clz((int)I.grid.H)) << 8); return k; } };
 
 // ---------------------------------------------------------------------------
 // Walk kernel for uniform strands (no index buffer): the hot kernel.
@@ -189,7 +199,7 @@ template <> struct SinkOf<3> { using type = SinkPacked8Brick;
 // read from HBM once (1/31 twice); per-instance constants come from the constant
 // bank (the batch is a __grid_constant__ parameter); the L1TEX path carries only
 // the vertex stream and the reds.  blockIdx.y + first = instance.
-// MODE 0 = COUNT32, 1 = PACKED8, 3 = BRICK8 (with EXACT = 3).
+// MODE 0 = COUNT32, 1 = PACKED8, 3 = BRICK8 on small grids (EXACT = 3), 4 = BRICK8 on power-of-two grids of any size (EXACT = 4).
 // ---------------------------------------------------------------------------
 constexpr uint32_t kTilesPerWarp = 8;
 constexpr uint32_t kWarpsPerBlock = kWalkThreads / 32;

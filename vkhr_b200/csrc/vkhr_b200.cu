@@ -338,9 +338,10 @@ int launch_walk(vkhr_b200_ctx* ctx, const BatchPlan& plan, bool exact, uint32_t 
         const dim3 grid(tiles[WK_UNIFORM], count);
         bool small = !exact;                                   // int32 index: every instance on a small grid
         for (uint32_t k = first; k < first + count; ++k) small = small && B.inst[k].grid.small_grid;
-        if constexpr (MODE == 3) {                             // BRICK8: the host has checked small && !exact
-            if (exact || !small) return fail(ctx, VKHR_B200_ERR_UNSUPPORTED, "BRICK8 needs the int32 index path");
-            k_walk_uniform<3, 3><<<grid, kWalkThreads, 0, s>>>(B, first);
+        if constexpr (MODE == 3) {                             // BRICK8: the host has checked !exact and the grid
+            if (exact) return fail(ctx, VKHR_B200_ERR_UNSUPPORTED, "BRICK8 does not run in exact-index mode");
+            if (small) k_walk_uniform<3, 3><<<grid, kWalkThreads, 0, s>>>(B, first);
+            else       k_walk_uniform<4, 4><<<grid, kWalkThreads, 0, s>>>(B, first);   // W, H powers of two: fp32 index, bit-field bricks
         } else {
             if (exact)      k_walk_uniform<MODE, 1><<<grid, kWalkThreads, 0, s>>>(B, first);
             else if (small) k_walk_uniform<MODE, 2><<<grid, kWalkThreads, 0, s>>>(B, first);
@@ -399,11 +400,18 @@ int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_
     // BRICK8: uniform strands, the int32 index path, whole bricks; otherwise plain PACKED8
     // (the default where it can run: 1.63 ms against 1.97 ms for the 64-instance crowd frame at 256^3 on B200)
     bool brick = packed && !(flags & VKHR_B200_STRATEGY_PACKED8) && !vertices_mode && !exact;
+    uint64_t total_segments = 0;
     for (uint32_t k = 0; brick && k < n; ++k) {
         const GridParams& g = jobs[k].grid;
-        brick = jobs[k].d_indices == nullptr && g.small_grid && g.W % 4u == 0 && g.H % 4u == 0 && g.D % 2u == 0 &&
+        const bool pow2 = (g.W & (g.W - 1u)) == 0 && (g.H & (g.H - 1u)) == 0;
+        brick = jobs[k].d_indices == nullptr && (g.small_grid || pow2) && g.W % 4u == 0 && g.H % 4u == 0 && g.D % 2u == 0 &&
                 g.W / 4u < 65536u && g.H / 4u < 65536u;
+        total_segments += jobs[k].n_segments;
     }
+    // the copy-out moves 2-3 bytes per voxel: it pays once there is about one segment per 100 voxels (measured on B200:
+    // 0.1 segments per voxel, the crowd at 256^3: 1.97 -> 1.63 ms; 0.24, 32 M segments at 512^3: 0.87 -> 0.67 ms;
+    // 0.024, 3.25 M at 512^3: 0.151 -> 0.129 ms; 0.0015, 1.6 M at 1024^3: 0.52 -> 0.59 ms, the clear pass is cheaper)
+    if (brick && !(flags & VKHR_B200_STRATEGY_BRICK8) && total_segments * 100ull < (uint64_t)n * nv) brick = false;
 
     ctx->last_strategy = brick ? VKHR_B200_STRATEGY_BRICK8 : packed ? VKHR_B200_STRATEGY_PACKED8 : VKHR_B200_STRATEGY_COUNT32;
     if (packed) {

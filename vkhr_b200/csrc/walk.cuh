@@ -273,8 +273,18 @@ __device__ __forceinline__ uint32_t brick_word(const GridParams& g, int ix, int 
     return (brick << 3) | ((uint32_t)(iz & 1) << 2) | (uint32_t)(iy & 3);
 }
 
+// The brick word of a LINEAR index when W and H are powers of two (lw = log2 W, lh = log2 H): bit fields only.
+__device__ __forceinline__ uint32_t brick_word_pow2(uint32_t lin, uint32_t lw, uint32_t lh) {
+    const uint32_t x = lin & ((1u << lw) - 1u), y = (lin >> lw) & ((1u << lh) - 1u), z = lin >> (lw + lh);
+    const uint32_t brick = ((((z >> 1) << (lh - 2u)) | (y >> 2)) << (lw - 2u)) | (x >> 2);
+    return (brick << 3) | ((z & 1u) << 2) | (y & 3u);
+}
+
 // The sampled walk of one segment per lane, end points in voxel space (hair_style.cc:315-328).
 // EXACT == 3: the int32 index of EXACT == 2 for a sink that counts in the brick layout (put_brick).
+// EXACT == 4: the reference's fp32 index (it rounds above 2^24 voxels, hair_style.cc:321) for such a sink on a grid
+//             whose W and H are powers of two: the ROUNDED index is what names the voxel, so the brick word is taken
+//             from its bit fields (sink.put_linear).
 // `active` = this lane has a segment.
 template <int EXACT, bool CHECK_TIP = true, class Sink>
 __device__ __forceinline__ void walk_voxel_space_warp(const GridParams& g, bool active,
@@ -306,6 +316,9 @@ __device__ __forceinline__ void walk_voxel_space_warp(const GridParams& g, bool 
                     const uint32_t lin = (uint32_t)((iz * (int)g.H + iy) * (int)g.W + ix);   // the reference's index, as EXACT == 2
                     if ((ix | iy | iz) >= 0) sink.template put_brick<decltype(slot)::value>(lin, brick_word(g, ix, iy, iz));   // inside the grid
                     else if (lin < g.n_voxels) sink.template put<decltype(slot)::value>(lin);   // a negative coordinate that still indexes a voxel
+                } else if constexpr (EXACT == 4) {
+                    uint32_t idx;
+                    if (sample_index<0>(g, rx, ry, rz, idx)) sink.template put_linear<decltype(slot)::value>(idx);
                 } else {
                     uint32_t idx;
                     if (sample_index<EXACT>(g, rx, ry, rz, idx)) sink.template put<decltype(slot)::value>(idx);
@@ -324,7 +337,7 @@ __device__ __forceinline__ void walk_voxel_space_warp(const GridParams& g, bool 
             }
         }
     } else if (go) {
-        walk_voxel_space<(EXACT == 3 ? 2 : EXACT)>(g, rx, ry, rz, tx, ty, tz, sink);   // the literal code, any input
+        walk_voxel_space<(EXACT == 3 ? 2 : EXACT == 4 ? 0 : EXACT)>(g, rx, ry, rz, tx, ty, tz, sink);   // the literal code, any input
     }
 }
 
