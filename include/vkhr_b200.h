@@ -77,7 +77,7 @@ enum {
     VKHR_B200_STRATEGY_PACKED8 = 1u << 9,
     /* BRICK8: PACKED8 counted in a context-owned scratch volume stored as 4x4x2-voxel bricks (one
      *          32-byte sector each, so neighbouring samples of a strand share atomic request packets),
-     *          then copied out to the x-fastest output layout.  Uniform strands, W % 4 == H % 4 == D % 2 == 0,
+     *          then copied out to the x-fastest output layout.  Segments only, W % 4 == H % 4 == D % 2 == 0,
      *          and either at most 2^24 voxels or W and H powers of two (above 2^24 voxels the reference's fp32
      *          index rounds, and the brick is taken from the bit fields of the rounded index); anything else
      *          falls back to PACKED8.  The default picks it from about one segment per 100 voxels upwards. */

@@ -587,7 +587,7 @@ def test_brick8_runs_where_it_can_and_falls_back_elsewhere(vox, port):
     idx = port.generate_indices(n, s)
     B = capi.STRATEGY_BRICK8
     cases = [((64, 64, 64), True, B), ((64, 32, 16), True, B), ((4, 4, 2), True, B), ((128, 8, 6), True, B), ((36, 20, 8), True, B),
-             ((64, 64, 64), False, capi.STRATEGY_PACKED8),          # explicit index pairs
+             ((64, 64, 64), False, B), ((36, 20, 8), False, B),      # explicit index pairs (k_walk_indexed)
              ((30, 20, 9), True, capi.STRATEGY_COUNT32),            # W % 4 != 0 and W*H*D % 16 != 0
              ((30, 20, 10), True, capi.STRATEGY_PACKED8),           # W % 4 != 0
              ((32, 32, 15), True, capi.STRATEGY_PACKED8)]           # D odd
@@ -658,6 +658,9 @@ def test_brick8_above_2pow24_voxels_keeps_the_fp32_index_rounding(vox, port, res
         got = vox.voxelize_segments(v, None, lo2, size, W, H, D, segs_per_strand=s, flags=capi.STRATEGY_BRICK8)
         assert vox.last_strategy == expect
         assert np.array_equal(got, want), (res, shrink)
+        got = vox.voxelize_segments(v, idx, lo2, size, W, H, D, flags=capi.STRATEGY_BRICK8)      # index pairs: k_walk_indexed
+        assert vox.last_strategy == expect
+        assert np.array_equal(got, want), (res, shrink, "indexed")
         # the rounding is real at these sizes: the exact-index volume differs
         if shrink == 0.0 and expect == capi.STRATEGY_BRICK8:
             assert not np.array_equal(want, port.voxelize_segments(v, idx, lo2, size, W, H, D, flags=capi.INDEX_EXACT))

@@ -350,7 +350,15 @@ int launch_walk(vkhr_b200_ctx* ctx, const BatchPlan& plan, bool exact, uint32_t 
         ctx->launches++;
     }
     if constexpr (MODE == 3) {
-        if (tiles[WK_INDEXED] || tiles[WK_SPLAT]) return fail(ctx, VKHR_B200_ERR_UNSUPPORTED, "BRICK8 walks uniform strands only");
+        if (tiles[WK_SPLAT]) return fail(ctx, VKHR_B200_ERR_UNSUPPORTED, "BRICK8 walks segments only");
+        if (tiles[WK_INDEXED]) {                               // explicit index pairs: the reference's own call (generate_indices)
+            const dim3 grid(tiles[WK_INDEXED], count);
+            bool small = true;
+            for (uint32_t k = first; k < first + count; ++k) small = small && B.inst[k].grid.small_grid;
+            if (small) k_walk_indexed<3, 3><<<grid, kWalkThreads, 0, s>>>(B, first);
+            else       k_walk_indexed<4, 4><<<grid, kWalkThreads, 0, s>>>(B, first);
+            ctx->launches++;
+        }
         CU_CHECK(ctx, cudaGetLastError());
         return VKHR_B200_OK;
     } else {
@@ -397,14 +405,14 @@ int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_
     if ((flags & VKHR_B200_STRATEGY_PACKED8) && !packed)
         return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "PACKED8 needs W*H*D % 16 == 0 and 16-byte aligned densities");
 
-    // BRICK8: uniform strands, the int32 index path, whole bricks; otherwise plain PACKED8
+    // BRICK8: segments (uniform strands or index pairs), whole bricks, a small or power-of-two grid; otherwise plain PACKED8
     // (the default where it can run: 1.63 ms against 1.97 ms for the 64-instance crowd frame at 256^3 on B200)
     bool brick = packed && !(flags & VKHR_B200_STRATEGY_PACKED8) && !vertices_mode && !exact;
     uint64_t total_segments = 0;
     for (uint32_t k = 0; brick && k < n; ++k) {
         const GridParams& g = jobs[k].grid;
         const bool pow2 = (g.W & (g.W - 1u)) == 0 && (g.H & (g.H - 1u)) == 0;
-        brick = jobs[k].d_indices == nullptr && (g.small_grid || pow2) && g.W % 4u == 0 && g.H % 4u == 0 && g.D % 2u == 0 &&
+        brick = (g.small_grid || pow2) && g.W % 4u == 0 && g.H % 4u == 0 && g.D % 2u == 0 &&
                 g.W / 4u < 65536u && g.H / 4u < 65536u;
         total_segments += jobs[k].n_segments;
     }
