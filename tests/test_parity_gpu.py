@@ -678,6 +678,32 @@ def test_brick8_default_follows_the_segment_density(vox, port):
         assert np.array_equal(got, port.voxelize_segments(v, port.generate_indices(n, s), lo, size, W, H, D))
 
 
+def test_brick8_batch_with_one_saturating_instance(vox, port):
+    """BRICK8 decides per instance whether any byte carried (samples added == byte sum of the volume): in a batch only
+    the instance that saturates is recounted, the others keep their copied-out volumes; a second run on the same
+    context sees clean statistics and a clean scratch."""
+    import torch
+    dev = torch.device("cuda", 0)
+    W, H, D = 16, 8, 4
+    insts, wants = [], []
+    for k, scale in enumerate((0.0005, 0.03, 0.001)):                     # sparse, dense (saturates), sparse
+        v, n, s = synth.shape("ponytail", seed=60 + k, seg_len=1.0, scale=scale)
+        lo, hi = port.generate_bounding_box(v)
+        size = (hi - lo).astype(np.float32)
+        wants.append(port.voxelize_segments(v, port.generate_indices(n, s), lo, size, W, H, D))
+        insts.append({"vertices": torch.from_numpy(v).to(dev).reshape(-1), "segs_per_strand": s, "aabb_origin": lo,
+                      "aabb_size": size, "out": torch.full((W * H * D,), 7, dtype=torch.uint8, device=dev)})
+    assert (wants[1] == 255).sum() > 0 and (wants[0] == 255).sum() == 0 and (wants[2] == 255).sum() == 0
+    for _ in range(2):
+        for ins in insts:
+            ins["out"].fill_(7)
+        vox.voxelize_segments_batch_dev(insts, W, H, D, flags=capi.STRATEGY_BRICK8)
+        torch.cuda.synchronize()
+        assert vox.last_strategy == capi.STRATEGY_BRICK8
+        for k, (ins, want) in enumerate(zip(insts, wants)):
+            assert np.array_equal(ins["out"].cpu().numpy(), want), k
+
+
 def test_brick8_crowd_at_256_equals_packed8(vox, port):
     """The bench configuration in small: ponytail-shaped instances at 256^3 through the batch entry point, every
     output byte written (pre-filled with 9), identical to PACKED8; instance 0 against the oracle."""

@@ -32,6 +32,8 @@ struct InstanceDev {
     uint32_t*       ovf_bitmap;     // PACKED8: 1 bit per 32-bit word of `densities`
     uint32_t*       ovf_flag;       // PACKED8: != 0 when any word overflowed
     uint8_t*        brick;          // BRICK8: W*H*D u8 scratch in brick order (zero between calls), or nullptr
+    unsigned long long* stats;      // BRICK8: kStatSlots partial counts of the samples the walk added, then kStatSlots
+                                    // partial byte sums of the copy-out (k_brick_verdict compares the totals); or nullptr
     uint32_t        n_tiles;        // CTAs this instance needs in its walk kernel
     uint32_t        kind;           // WalkKind
     uint32_t        vps_magic;      // floor(2^32 / (segs_per_strand + 1)) + 1   (strand-end test without a division)
@@ -42,6 +44,9 @@ struct InstanceDev {
 // read through the constant cache, not through L1TEX (which the atomics need), and no table upload
 // precedes the launch.  blockIdx.y + first selects the instance.
 constexpr uint32_t kMaxBatch = 64;
+// BRICK8 statistics are spread over slots: thousands of warps adding to ONE address serialise at L2 (measured: the
+// crowd walk went from 0.97 to 1.37 ms with a single counter per instance).
+constexpr uint32_t kStatSlots = 256;
 struct Batch {
     uint32_t n;
     uint32_t pad[3];
@@ -113,35 +118,28 @@ struct SinkPacked8 {
     __device__ __forceinline__ void words_pin() { asm volatile("" : "+l"(words)); }
 };
 
-// BRICK8: the same counter words, stored brick by brick in a scratch volume (brick_word in walk.cuh).  The pending
-// ring keeps the LINEAR index: its low two bits name the byte in either layout, and an overflow is flagged at the
-// linear word, where k_repair_packed rewrites it after the copy-out (k_untile_batch).
-// (Moving the two rare paths -- overflow flag, linear-index samples -- into __noinline__ functions was measured: the
-// call ABI costs spills in the tile loop and the walk went from 1.21 to 1.82 ms; they stay inline.)
+// BRICK8: the same counter words, stored brick by brick in a scratch volume (brick_word in walk.cuh), and added
+// with a fire-and-forget `red` -- no returned word, no pending ring, no wait for a round trip.  Whether a byte ever
+// carried is decided once per instance instead: the walk counts the samples it added, the copy-out (k_untile_batch)
+// sums the bytes it reads (slotted partial sums in `stats`).  Every add raises the byte sum by exactly 1 unless it carries
+// out of its byte, and then by less (-254 into the next byte, -255 out of the word), so the two numbers are equal if
+// and only if no voxel received more than 255 hits -- in which case the bytes ARE the counts.  Otherwise
+// k_brick_verdict flags the instance and k_repair_packed recounts it in u32 and rewrites its whole volume.
+// In the x-fastest layout the same `red` was slower than the returning `atom` (a `red` that misses L2
+// stalls its slice); in the brick layout it is faster: 1.19 -> 0.97 ms for the crowd walk.
+// (Moving rare paths into __noinline__ functions was measured too: the call ABI costs spills in the tile loop.)
 // POW2: W and H are powers of two and `wh` holds their logarithms -- a linear index is decomposed by bit fields, which
 // is also how the fast path of large grids finds its brick (walk.cuh, EXACT == 4).
 template <bool POW2>
 struct SinkPacked8Brick {
-    static constexpr int kDepth = 4;
     uint32_t* words;                // the brick-ordered scratch
-    uint32_t* ovf_bitmap;
-    uint32_t* ovf_flag;
+    unsigned long long* stats;
     uint32_t wh;                    // (W / 4) | (H / 4) << 16 (only the literal path needs it); POW2: log2 W | log2 H << 8
-    uint32_t pend_old[kDepth] = {0, 0, 0, 0};
-    uint32_t pend_idx[kDepth] = {0, 0, 0, 0};
-    template <int SLOT>
-    __device__ __forceinline__ void check() {
-        if (__byte_perm(pend_old[SLOT], 0u, 0x4440u | (pend_idx[SLOT] & 3u)) == 0xFFu) {
-            const uint32_t w = pend_idx[SLOT] >> 2;
-            atomicOr(ovf_bitmap + (w >> 5), 1u << (w & 31u));
-            *ovf_flag = 1u;
-        }
-    }
+    uint32_t added = 0;             // samples this lane added
     template <int SLOT>
     __device__ __forceinline__ void put_brick(uint32_t lin, uint32_t bword) {
-        check<SLOT>();
-        pend_old[SLOT] = atom_add_u32(words + bword, 1u << ((lin & 3u) * 8u));
-        pend_idx[SLOT] = lin;
+        red_add_u32(words + bword, 1u << ((lin & 3u) * 8u));
+        ++added;
     }
     template <int SLOT>
     __device__ __forceinline__ void put_linear(uint32_t lin) { put_brick<SLOT>(lin, brick_word_pow2(lin, wh & 0xFFu, wh >> 8)); }
@@ -153,19 +151,24 @@ struct SinkPacked8Brick {
         const uint32_t brick = ((z >> 1) * (H >> 2) + (y >> 2)) * (W >> 2) + (x >> 2);
         put_brick<SLOT>(lin, (brick << 3) | ((z & 1u) << 2) | (y & 3u));
     }
-    __device__ __forceinline__ void finish() { check<0>(); check<1>(); check<2>(); check<3>(); }
+    // all 32 lanes of the warp call finish() together (the kernels return early only as whole warps)
+    __device__ __forceinline__ void finish() {
+        const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, added);
+        if ((threadIdx.x & 31u) == 0u && total)
+            atomicAdd(stats + ((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (kStatSlots - 1u)), (unsigned long long)total);
+    }
     __device__ __forceinline__ void words_pin() { asm volatile("" : "+l"(words)); }
 };
 
 // Recount pass of PACKED8: only samples landing in flagged words are counted,
 // into the u32 scratch grid.
 struct SinkRecount {
-    const uint32_t* ovf_bitmap;
+    const uint32_t* ovf_bitmap;     // nullptr: every word is recounted (BRICK8: the byte sum did not match)
     uint32_t* counts;
     template <int SLOT = 0>
     __device__ __forceinline__ void put(uint32_t idx) {
         const uint32_t w = idx >> 2;
-        if ((__ldg(ovf_bitmap + (w >> 5)) >> (w & 31u)) & 1u) atomicAdd(counts + idx, 1u);
+        if (!ovf_bitmap || ((__ldg(ovf_bitmap + (w >> 5)) >> (w & 31u)) & 1u)) atomicAdd(counts + idx, 1u);
     }
     __device__ __forceinline__ void finish() {}
 };
@@ -178,11 +181,11 @@ template <> struct SinkOf<1> { using type = SinkPacked8;
 
 template <> struct SinkOf<3> { using type = SinkPacked8Brick<false>;
     __device__ static type make(const InstanceDev& I) {
-        type k; k.words = reinterpret_cast<uint32_t*>(I.brick); k.ovf_bitmap = I.ovf_bitmap; k.ovf_flag = I.ovf_flag;
+        type k; k.words = reinterpret_cast<uint32_t*>(I.brick); k.stats = I.stats;
         k.wh = (I.grid.W >> 2) | ((I.grid.H >> 2) << 16); return k; } };
 template <> struct SinkOf<4> { using type = SinkPacked8Brick<true>;
     __device__ static type make(const InstanceDev& I) {
-        type k; k.words = reinterpret_cast<uint32_t*>(I.brick); k.ovf_bitmap = I.ovf_bitmap; k.ovf_flag = I.ovf_flag;
+        type k; k.words = reinterpret_cast<uint32_t*>(I.brick); k.stats = I.stats;
         k.wh = (31u - (uint32_t)__clz((int)I.grid.W)) | ((31u - (uint32_t)__clz((int)I.grid.H)) << 8); return k; } };
 
 // ---------------------------------------------------------------------------
@@ -534,24 +537,28 @@ __global__ void __launch_bounds__(256) k_zero16(uint4* __restrict__ p, uint64_t 
 
 // PACKED8 clear for a batch: densities, overflow bitmap and flag of every instance.
 // blockIdx.y + first = instance.  n_voxels % 16 == 0 is guaranteed by the host (else COUNT32).
-// volumes == 0 (BRICK8): bitmaps and flags only -- the copy-out writes every byte of the densities.
+// volumes == 0 (BRICK8): flag and statistics only -- the copy-out writes every byte of the densities, and the walk
+// does not use the bitmap.
 __global__ void __launch_bounds__(256) k_clear_packed_batch(const __grid_constant__ Batch B, uint32_t first, uint32_t volumes) {
     const InstanceDev& I = B.inst[first + blockIdx.y];
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    uint4* d = reinterpret_cast<uint4*>(I.densities);
-    const uint32_t n16 = volumes ? I.grid.n_voxels >> 4 : 0u;
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) *I.ovf_flag = 0u;
+    if (I.stats) for (uint32_t i = t; i < 2u * kStatSlots; i += stride) I.stats[i] = 0ull;
+    if (!volumes) return;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    uint4* d = reinterpret_cast<uint4*>(I.densities);
+    const uint32_t n16 = I.grid.n_voxels >> 4;
     for (uint32_t i = t; i < n16; i += stride) d[i] = z;
     const uint32_t n_bm = (I.grid.n_voxels / 4 + 31) / 32;          // bitmap words
     for (uint32_t i = t; i < n_bm; i += stride) I.ovf_bitmap[i] = 0u;
-    if (t == 0) *I.ovf_flag = 0u;
 }
 
 // BRICK8 copy-out: brick-ordered scratch -> the x-fastest output volume (Volume::densities, hair_style.hh:89-101),
 // one brick (two 16-byte loads) per thread; the 32 bricks of a warp are consecutive in x, so each of its eight
 // 4-byte stores covers 128 contiguous bytes of one output row.  A brick that held anything is zeroed behind the
-// read, which restores the scratch's all-zero state for the next call without a clear pass.
+// read, which restores the scratch's all-zero state for the next call without a clear pass.  It also sums the bytes
+// it reads (slotted partial sums): equal to the number of samples the walk added iff no byte carried (SinkPacked8Brick).
 __global__ void __launch_bounds__(256) k_untile_batch(const __grid_constant__ Batch B, uint32_t first) {
     const InstanceDev& I = B.inst[first + blockIdx.y];
     const uint32_t wrow = I.grid.W >> 2, byn = I.grid.H >> 2;             // words (= bricks) per row, brick rows per slab
@@ -561,14 +568,37 @@ __global__ void __launch_bounds__(256) k_untile_batch(const __grid_constant__ Ba
     uint32_t* __restrict__ dst = reinterpret_cast<uint32_t*>(I.densities);
     const uint4 z = make_uint4(0, 0, 0, 0);
     const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t bytes = 0;                                                   // < 2^32: at most 8160 per brick, n_bricks / threads bricks
     for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < n_bricks; b += stride) {
         const uint4 q0 = __ldcs(src + 2u * b), q1 = __ldcs(src + 2u * b + 1u);   // z even, z odd: rows y & 3 = 0..3
+        bytes += __vsadu4(q0.x, 0u) + __vsadu4(q0.y, 0u) + __vsadu4(q0.z, 0u) + __vsadu4(q0.w, 0u) +
+                 __vsadu4(q1.x, 0u) + __vsadu4(q1.y, 0u) + __vsadu4(q1.z, 0u) + __vsadu4(q1.w, 0u);
         const uint32_t bx = b % wrow, t = b / wrow, by = t % byn, bz = t / byn;
         uint32_t* o = dst + (size_t)(2u * bz) * wslab + (size_t)(4u * by) * wrow + bx;
         __stcs(o, q0.x); __stcs(o + wrow, q0.y); __stcs(o + 2u * wrow, q0.z); __stcs(o + 3u * wrow, q0.w);
         o += wslab;
         __stcs(o, q1.x); __stcs(o + wrow, q1.y); __stcs(o + 2u * wrow, q1.z); __stcs(o + 3u * wrow, q1.w);
         if ((q0.x | q0.y | q0.z | q0.w | q1.x | q1.y | q1.z | q1.w) != 0u) { src[2u * b] = z; src[2u * b + 1u] = z; }
+    }
+    // the byte sum of the instance (the loop's trip count differs by at most one between lanes: no lane has left)
+    const unsigned long long lo = __reduce_add_sync(0xFFFFFFFFu, bytes & 0xFFFFu), hi = __reduce_add_sync(0xFFFFFFFFu, bytes >> 16);
+    if ((threadIdx.x & 31u) == 0u && (lo | hi))
+        atomicAdd(I.stats + kStatSlots + ((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (kStatSlots - 1u)), lo + (hi << 16));
+}
+
+// BRICK8 verdict, one CTA of kStatSlots threads per instance: samples added != byte sum of the volume means some byte
+// carried; the instance is flagged (2 = recount every word) for k_repair_packed.
+__global__ void __launch_bounds__(kStatSlots) k_brick_verdict(const __grid_constant__ Batch B, uint32_t first) {
+    const InstanceDev& I = B.inst[first + blockIdx.x];
+    __shared__ unsigned long long s_sum[2][kStatSlots / 32];
+    unsigned long long a = I.stats[threadIdx.x], b = I.stats[kStatSlots + threadIdx.x];
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(0xFFFFFFFFu, a, o); b += __shfl_down_sync(0xFFFFFFFFu, b, o); }
+    if ((threadIdx.x & 31u) == 0u) { s_sum[0][threadIdx.x >> 5] = a; s_sum[1][threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a = 0; b = 0;
+        for (uint32_t w = 0; w < kStatSlots / 32; ++w) { a += s_sum[0][w]; b += s_sum[1][w]; }
+        if (a != b) *I.ovf_flag = 2u;
     }
 }
 

@@ -38,6 +38,8 @@ k_repair_packed(const __grid_constant__ Batch B, uint32_t* __restrict__ scratch)
     // common case first: no instance overflowed -> one parallel look at the flags and out
     const uint32_t n_inst = B.n;
     const InstanceDev* inst = B.inst;
+    // (BRICK8 has no per-word flags: k_brick_verdict sets the flag to 2 when the byte sum of the volume differs from
+    // the number of samples added, and then every word is recounted)
     int any = 0;
     for (uint32_t k = threadIdx.x; k < n_inst; k += blockDim.x) any |= (*inst[k].ovf_flag != 0u);
     if (!__syncthreads_or(any)) return;                        // same answer in every CTA
@@ -46,14 +48,16 @@ k_repair_packed(const __grid_constant__ Batch B, uint32_t* __restrict__ scratch)
     const uint32_t nthreads = gridDim.x * blockDim.x;
     for (uint32_t k = 0; k < n_inst; ++k) {
         const InstanceDev& I = inst[k];
-        if (*I.ovf_flag == 0u) continue;                       // uniform across the grid
+        const uint32_t flag = *I.ovf_flag;                     // nothing below writes it: uniform across the grid
+        if (flag == 0u) continue;
+        const bool all = flag == 2u;
         const GridParams g = I.grid;
         const uint32_t n_words = g.n_voxels >> 2;
         const uint32_t n_bm = (n_words + 31) / 32;
         uint32_t* words = reinterpret_cast<uint32_t*>(I.densities);
         uint4* counts4 = reinterpret_cast<uint4*>(scratch);
         for (uint32_t b = tid; b < n_bm; b += nthreads) {
-            uint32_t m = I.ovf_bitmap[b];
+            uint32_t m = all ? 0xFFFFFFFFu : I.ovf_bitmap[b];
             while (m) {
                 const uint32_t w = b * 32 + (__ffs(m) - 1);
                 m &= m - 1;
@@ -61,7 +65,7 @@ k_repair_packed(const __grid_constant__ Batch B, uint32_t* __restrict__ scratch)
             }
         }
         grid.sync();
-        SinkRecount sink{I.ovf_bitmap, scratch};
+        SinkRecount sink{all ? nullptr : I.ovf_bitmap, scratch};
         if (VERTICES) {
             for (uint32_t i = tid; i < I.n_vertices; i += nthreads) {
                 const float* v = I.vertices + 3ull * i;
@@ -87,7 +91,7 @@ k_repair_packed(const __grid_constant__ Batch B, uint32_t* __restrict__ scratch)
         }
         grid.sync();
         for (uint32_t b = tid; b < n_bm; b += nthreads) {
-            uint32_t m = I.ovf_bitmap[b];
+            uint32_t m = all ? 0xFFFFFFFFu : I.ovf_bitmap[b];
             while (m) {
                 const uint32_t w = b * 32 + (__ffs(m) - 1);
                 m &= m - 1;
@@ -338,30 +342,11 @@ int launch_walk(vkhr_b200_ctx* ctx, const BatchPlan& plan, bool exact, uint32_t 
         const dim3 grid(tiles[WK_UNIFORM], count);
         bool small = !exact;                                   // int32 index: every instance on a small grid
         for (uint32_t k = first; k < first + count; ++k) small = small && B.inst[k].grid.small_grid;
-        if constexpr (MODE == 3) {                             // BRICK8: the host has checked !exact and the grid
-            if (exact) return fail(ctx, VKHR_B200_ERR_UNSUPPORTED, "BRICK8 does not run in exact-index mode");
-            if (small) k_walk_uniform<3, 3><<<grid, kWalkThreads, 0, s>>>(B, first);
-            else       k_walk_uniform<4, 4><<<grid, kWalkThreads, 0, s>>>(B, first);   // W, H powers of two: fp32 index, bit-field bricks
-        } else {
-            if (exact)      k_walk_uniform<MODE, 1><<<grid, kWalkThreads, 0, s>>>(B, first);
-            else if (small) k_walk_uniform<MODE, 2><<<grid, kWalkThreads, 0, s>>>(B, first);
-            else            k_walk_uniform<MODE, 0><<<grid, kWalkThreads, 0, s>>>(B, first);
-        }
+        if (exact)      k_walk_uniform<MODE, 1><<<grid, kWalkThreads, 0, s>>>(B, first);
+        else if (small) k_walk_uniform<MODE, 2><<<grid, kWalkThreads, 0, s>>>(B, first);
+        else            k_walk_uniform<MODE, 0><<<grid, kWalkThreads, 0, s>>>(B, first);
         ctx->launches++;
     }
-    if constexpr (MODE == 3) {
-        if (tiles[WK_SPLAT]) return fail(ctx, VKHR_B200_ERR_UNSUPPORTED, "BRICK8 walks segments only");
-        if (tiles[WK_INDEXED]) {                               // explicit index pairs: the reference's own call (generate_indices)
-            const dim3 grid(tiles[WK_INDEXED], count);
-            bool small = true;
-            for (uint32_t k = first; k < first + count; ++k) small = small && B.inst[k].grid.small_grid;
-            if (small) k_walk_indexed<3, 3><<<grid, kWalkThreads, 0, s>>>(B, first);
-            else       k_walk_indexed<4, 4><<<grid, kWalkThreads, 0, s>>>(B, first);
-            ctx->launches++;
-        }
-        CU_CHECK(ctx, cudaGetLastError());
-        return VKHR_B200_OK;
-    } else {
     if (tiles[WK_INDEXED]) {
         const dim3 grid(tiles[WK_INDEXED], count);
         if (exact) k_walk_indexed<MODE, 1><<<grid, kWalkThreads, 0, s>>>(B, first);
@@ -376,7 +361,34 @@ int launch_walk(vkhr_b200_ctx* ctx, const BatchPlan& plan, bool exact, uint32_t 
     }
     CU_CHECK(ctx, cudaGetLastError());
     return VKHR_B200_OK;
+}
+
+// The BRICK8 walk of instances [first, first + count): segments only (uniform strands and / or index pairs), never in
+// exact-index mode; small grids take the int32 index (<3, 3>), larger ones -- W, H powers of two, checked by the
+// caller -- the reference's rounded fp32 index decomposed by bit fields (<4, 4>).
+int launch_walk_brick(vkhr_b200_ctx* ctx, uint32_t first, uint32_t count, cudaStream_t s) {
+    const Batch& B = ctx->batch;
+    uint32_t tiles[3] = {0, 0, 0};
+    bool small = true;
+    for (uint32_t k = first; k < first + count; ++k) {
+        tiles[B.inst[k].kind] = std::max(tiles[B.inst[k].kind], B.inst[k].n_tiles);
+        small = small && B.inst[k].grid.small_grid;
     }
+    if (tiles[WK_SPLAT]) return fail(ctx, VKHR_B200_ERR_UNSUPPORTED, "BRICK8 walks segments only");
+    if (tiles[WK_UNIFORM]) {
+        const dim3 grid(tiles[WK_UNIFORM], count);
+        if (small) k_walk_uniform<3, 3><<<grid, kWalkThreads, 0, s>>>(B, first);
+        else       k_walk_uniform<4, 4><<<grid, kWalkThreads, 0, s>>>(B, first);
+        ctx->launches++;
+    }
+    if (tiles[WK_INDEXED]) {                                   // explicit index pairs: what the reference's own caller passes
+        const dim3 grid(tiles[WK_INDEXED], count);
+        if (small) k_walk_indexed<3, 3><<<grid, kWalkThreads, 0, s>>>(B, first);
+        else       k_walk_indexed<4, 4><<<grid, kWalkThreads, 0, s>>>(B, first);
+        ctx->launches++;
+    }
+    CU_CHECK(ctx, cudaGetLastError());
+    return VKHR_B200_OK;
 }
 
 template <bool VERTICES>
@@ -424,7 +436,9 @@ int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_
     ctx->last_strategy = brick ? VKHR_B200_STRATEGY_BRICK8 : packed ? VKHR_B200_STRATEGY_PACKED8 : VKHR_B200_STRATEGY_COUNT32;
     if (packed) {
         // scratch: per-instance overflow bitmap + flag, one shared u32 recount grid
+        // per instance: a header (flag at word [0], the 2 x kStatSlots u64 statistics of BRICK8 from word [4]) + the bitmap
         const size_t bm_words = ((nv / 4 + 31) / 32 + 3) & ~size_t(3);
+        constexpr size_t kHdr = 4 + 4 * (size_t)kStatSlots;
         const uint32_t chunk = std::min<uint32_t>(n, kMaxBatch);
         if (brick) {
             const size_t need = (size_t)chunk * nv;
@@ -436,7 +450,7 @@ int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_
             }
             ctx->brick_clean_bytes = 0;                                    // until the copy-out of every chunk has been queued
         }
-        RET_IF(reserve(ctx, ctx->bitmap, (size_t)chunk * (bm_words + 4) * 4));
+        RET_IF(reserve(ctx, ctx->bitmap, (size_t)chunk * (bm_words + kHdr) * 4));
         RET_IF(reserve(ctx, ctx->counts, nv * 4));
         ctx->counts_clean_bytes = 0;                   // the recount may leave entries behind
         uint32_t* base = static_cast<uint32_t*>(ctx->bitmap.p);
@@ -444,13 +458,14 @@ int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_
             const uint32_t m = std::min(chunk, n - first);
             const BatchPlan plan = fill_batch(ctx, jobs + first, m, vertices_mode);
             for (uint32_t k = 0; k < m; ++k) {
-                ctx->batch.inst[k].ovf_flag = base + (size_t)k * (bm_words + 4);
-                ctx->batch.inst[k].ovf_bitmap = base + (size_t)k * (bm_words + 4) + 4;
+                ctx->batch.inst[k].ovf_flag = base + (size_t)k * (bm_words + kHdr);
+                ctx->batch.inst[k].ovf_bitmap = base + (size_t)k * (bm_words + kHdr) + kHdr;
+                ctx->batch.inst[k].stats = brick ? reinterpret_cast<unsigned long long*>(base + (size_t)k * (bm_words + kHdr) + 4) : nullptr;
                 ctx->batch.inst[k].counts = static_cast<uint32_t*>(ctx->counts.p);
             }
             for (uint32_t k = 0; brick && k < m; ++k)
                 ctx->batch.inst[k].brick = static_cast<uint8_t*>(ctx->brick.p) + (size_t)k * nv;
-            const unsigned gx = brick ? stride_blocks(ctx, bm_words / 4 + 1, 256, 1) : stride_blocks(ctx, nv / 16, 256, m >= 8 ? 2 : 8);
+            const unsigned gx = brick ? 1u : stride_blocks(ctx, nv / 16, 256, m >= 8 ? 2 : 8);
             {
                 PhaseMark mk(ctx, s, PH_CLEAR);
                 k_clear_packed_batch<<<dim3(gx, m), 256, 0, s>>>(ctx->batch, 0u, brick ? 0u : 1u);
@@ -460,11 +475,12 @@ int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_
             if (brick) {
                 if (any_work) {
                     PhaseMark mk(ctx, s, PH_WALK);
-                    RET_IF(launch_walk<3>(ctx, plan, exact, 0, m, s));
+                    RET_IF(launch_walk_brick(ctx, 0, m, s));
                 }
                 PhaseMark mk(ctx, s, PH_FINISH);                           // the copy-out also writes the zeros of an empty volume
                 k_untile_batch<<<dim3(stride_blocks(ctx, nv / 32, 256, m >= 8 ? 2 : 8), m), 256, 0, s>>>(ctx->batch, 0u);
-                ctx->launches++;
+                k_brick_verdict<<<m, kStatSlots, 0, s>>>(ctx->batch, 0u);
+                ctx->launches += 2;
             }
             if (any_work) {
                 if (!brick) {
