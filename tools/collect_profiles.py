@@ -25,8 +25,8 @@ if os.path.exists(rep):
     t[f"k_walk_uniform<{mode}>@64x256^3"] = int(rd + wr)
     t["_source" if mode == 1 else "_source_brick8"] = (f"ncu --set full, one launch of the 64-instance walk ({tag}): dram__bytes_read.sum "
                                                         f"{rd / 1e9:.3f} GB + dram__bytes_write.sum {wr / 1e9:.3f} GB")
-    sectors = row.get("lts__t_sectors_srcunit_tex_op_atom.sum")
+    sectors = float(row.get("lts__t_sectors_srcunit_tex_op_atom.sum") or 0) + float(row.get("lts__t_sectors_srcunit_tex_op_red.sum") or 0)
     if mode == 3 and sectors:
-        t["atom_sectors_per_sample<3>@64x256^3"] = round(float(sectors) / 209630528.0, 4)     # samples of the bench frame (bench.py prints them)
+        t["atom_sectors_per_sample<3>@64x256^3"] = round(sectors / 209630528.0, 4)            # samples of the bench frame (bench.py prints them)
     json.dump(t, open(tpath, "w"), indent=1)
     print("traffic", rd, wr)
