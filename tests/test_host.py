@@ -186,3 +186,48 @@ def test_ao_column_form_equals_per_voxel_form_in_host_emulation(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and "TOTAL bad=0" in out.stdout, out.stdout[-2000:]
     assert "nontrivial=0\n" not in out.stdout.split("fill=0.00")[0], "the dense cases must exercise non-empty outputs"
+
+
+def test_brick8_layout_is_a_permutation_of_the_volume_words():
+    """The BRICK8 scratch layout restated in numpy (walk.cuh brick_word / brick_word_pow2, kernels.cuh k_untile_batch):
+    every 32-bit word of the x-fastest volume has exactly one brick word, the copy-out's (brick, word) -> linear word
+    mapping is its inverse, and the bit-field form used above 2^24 voxels equals the general form on power-of-two grids."""
+    for W, H, D in [(4, 4, 2), (8, 4, 2), (36, 20, 8), (64, 32, 16), (128, 8, 6), (256, 256, 4)]:
+        z, y, x = np.meshgrid(np.arange(D), np.arange(H), np.arange(W), indexing="ij")
+        x, y, z = x.ravel(), y.ravel(), z.ravel()
+        lin = (z * H + y) * W + x
+        brick = ((z >> 1) * (H >> 2) + (y >> 2)) * (W >> 2) + (x >> 2)
+        bword = (brick << 3) | ((z & 1) << 2) | (y & 3)
+        bbyte = (bword << 2) | (x & 3)                                   # byte address in the scratch volume
+        assert np.array_equal(np.sort(bbyte), np.arange(W * H * D)), (W, H, D)
+        assert np.array_equal(bbyte & 3, lin & 3)                        # the same byte of the word in both layouts
+        # the copy-out: brick b, word w of the brick -> linear word
+        wrow, byn = W >> 2, H >> 2
+        b, w = bword >> 3, bword & 7
+        bx, t = b % wrow, b // wrow
+        by, bz = t % byn, t // byn
+        lin_word = (2 * bz + (w >> 2)) * (wrow * H) + (4 * by + (w & 3)) * wrow + bx
+        assert np.array_equal(lin_word, lin >> 2), (W, H, D)
+        if W & (W - 1) == 0 and H & (H - 1) == 0:
+            lw, lh = W.bit_length() - 1, H.bit_length() - 1
+            x2, y2, z2 = lin & (W - 1), (lin >> lw) & (H - 1), lin >> (lw + lh)
+            b2 = ((((z2 >> 1) << (lh - 2)) | (y2 >> 2)) << (lw - 2)) | (x2 >> 2)
+            assert np.array_equal((b2 << 3) | ((z2 & 1) << 2) | (y2 & 3), bword), (W, H, D)
+
+
+def test_byte_sum_equals_sample_count_iff_no_byte_carried():
+    """The overflow test of the BRICK8 walk: packed-u8 adds of 1 << 8*byte into 32-bit words; the byte sum of the
+    volume equals the number of adds exactly when no voxel received more than 255 of them."""
+    rng = np.random.default_rng(7)
+    for trial in range(200):
+        n_words = int(rng.integers(1, 6))
+        hot = rng.random() < 0.5                                          # half of the trials push some voxel past 255
+        n_adds = int(rng.integers(200, 1500)) if hot else int(rng.integers(0, 200))
+        vox = rng.integers(0, 4 * n_words, n_adds) if not hot else np.where(rng.random(n_adds) < 0.7, rng.integers(0, 4 * n_words), rng.integers(0, 4 * n_words, n_adds))
+        words = np.zeros(n_words, dtype=np.uint64)
+        for v in vox:
+            words[v >> 2] = (words[v >> 2] + (np.uint64(1) << np.uint64(8 * (v & 3)))) & np.uint64(0xFFFFFFFF)
+        byte_sum = int(sum(int((w >> np.uint64(8 * b)) & np.uint64(0xFF)) for w in words for b in range(4)))
+        counts = np.bincount(vox, minlength=4 * n_words)
+        assert (byte_sum == n_adds) == bool((counts <= 255).all()), (trial, byte_sum, n_adds, counts.max())
+        assert byte_sum <= n_adds
