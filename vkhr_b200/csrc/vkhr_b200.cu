@@ -439,16 +439,29 @@ int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_
         // per instance: a header (flag at word [0], the 2 x kStatSlots u64 statistics of BRICK8 from word [4]) + the bitmap
         const size_t bm_words = ((nv / 4 + 31) / 32 + 3) & ~size_t(3);
         constexpr size_t kHdr = 4 + 4 * (size_t)kStatSlots;
-        const uint32_t chunk = std::min<uint32_t>(n, kMaxBatch);
+        uint32_t chunk = std::min<uint32_t>(n, kMaxBatch);
         if (brick) {
-            const size_t need = (size_t)chunk * nv;
+            // one scratch volume per instance of a chunk, within a 4 GiB budget (64 instances at 256^3 take 1 GiB; a
+            // 1024^3 volume is 1 GiB by itself); if even that cannot be allocated the default falls back to counting in
+            // the output volumes (PACKED8)
+            const size_t budget = size_t(4) << 30;
+            const uint32_t bchunk = (uint32_t)std::min<size_t>(chunk, std::max<size_t>(1, budget / nv));
+            const size_t need = (size_t)bchunk * nv;
             if (need > ctx->brick.cap) ctx->brick_clean_bytes = 0;         // reserve() reallocates: contents undefined
-            RET_IF(reserve(ctx, ctx->brick, need));
-            if (ctx->brick_clean_bytes < need) {
-                PhaseMark mk(ctx, s, PH_CLEAR);
-                CU_CHECK(ctx, cudaMemsetAsync(ctx->brick.p, 0, need, s));
+            const int rc = reserve(ctx, ctx->brick, need);
+            if (rc != VKHR_B200_OK) {
+                if (flags & VKHR_B200_STRATEGY_BRICK8) return rc;
+                brick = false;
+                ctx->brick_clean_bytes = 0;
+                ctx->last_strategy = VKHR_B200_STRATEGY_PACKED8;
+            } else {
+                chunk = bchunk;
+                if (ctx->brick_clean_bytes < need) {
+                    PhaseMark mk(ctx, s, PH_CLEAR);
+                    CU_CHECK(ctx, cudaMemsetAsync(ctx->brick.p, 0, need, s));
+                }
+                ctx->brick_clean_bytes = 0;                                // until the copy-out of every chunk has been queued
             }
-            ctx->brick_clean_bytes = 0;                                    // until the copy-out of every chunk has been queued
         }
         RET_IF(reserve(ctx, ctx->bitmap, (size_t)chunk * (bm_words + kHdr) * 4));
         RET_IF(reserve(ctx, ctx->counts, nv * 4));
