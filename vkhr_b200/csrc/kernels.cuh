@@ -88,10 +88,11 @@ struct SinkCount32 {
 // results in registers, slot chosen at compile time by the unrolled walk), so
 // up to kDepth atomics of a thread are in flight and their round trips overlap
 // the arithmetic of the following samples.
-// (A fire-and-forget `red` with a byte-sum verification pass was measured as
-// well -- DESIGN.md "what was tried": the walk is no faster, because the cost
-// of a sample is its 32-byte request packet to L2 either way, and the extra
-// pass over the grid is not free.)
+// (A fire-and-forget `red` with a byte-sum verification pass was measured in
+// this x-fastest layout as well -- DESIGN.md 6.4: the walk is no faster, because
+// the cost of a sample is its 32-byte request packet to L2 either way, and the
+// extra pass over the grid is not free.  In the brick layout it is, and BRICK8
+// below works that way.)
 struct SinkPacked8 {
     static constexpr int kDepth = 4;
     uint32_t* words;
