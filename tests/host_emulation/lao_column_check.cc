@@ -4,7 +4,8 @@
 // constants and the Gaussian weight function), turns `__device__ __forceinline__` into `static inline`, writes it to
 // LAO_EXTRACT and compiles this file with g++ -ffp-contract=off.  The rounding intrinsics become plain fp32
 // operations, so the check is about the INDEXING of the register-tiled column form: for random float tiles and row
-// flags, every output of lao_column must be bit-identical to lao_at at the same voxel, for every instantiated tap
+// flags, every output of lao_column (and of lao_column_rolled, its period-unrolled form) must be bit-identical to
+// lao_at at the same voxel, for every instantiated tap
 // offset pair, tile halo and number of valid outputs.
 #include <algorithm>
 #include <cmath>
@@ -59,8 +60,13 @@ static int run1(float radius, int h, double fill, int n_out) {
         for (int lane = 0; lane < 32; ++lane) {
             float got[TZ];
             for (int k = 0; k < TZ; ++k) got[k] = -777.0f;
+            float rolled[TZ];
+            for (int k = 0; k < TZ; ++k) rolled[k] = -777.0f;
             lao_column<NO0, PO0, TZ>(A, ftile.data() + (h * BY + (jy + h)) * FX + (lane + h), flag.data() + h * BY + (jy + h), BY * FX, FX, BY,
                                  tile_any, ao_empty, n_out, [&](int kz, float r) { got[kz] = r; });
+            lao_column_rolled<NO0, PO0, TZ>(A, ftile.data() + (h * BY + (jy + h)) * FX + (lane + h), flag.data() + h * BY + (jy + h), BY * FX, FX, BY,
+                                        tile_any, ao_empty, n_out, [&](int kz, float r) { rolled[kz] = r; });
+            if (std::memcmp(got, rolled, sizeof got)) { if (bad < 5) std::printf("r=%g jy=%d lane=%d: rolled form differs\n", radius, jy, lane); ++bad; }
             for (int kz = 0; kz < TZ; ++kz) {
                 const float* centre = ftile.data() + ((kz + h) * BY + (jy + h)) * FX + (lane + h);
                 const float want = lao_at(A, [&](int ox, int oy, int oz) -> float { return centre[(oz * BY + oy) * FX + ox]; });

@@ -177,7 +177,7 @@ def test_ao_column_form_equals_per_voxel_form_in_host_emulation(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     text = open(os.path.join(root, "vkhr_b200", "csrc", "prefilter.cuh")).read()
     body = text[text.index("constexpr int kPfTX"):text.index("// Gaussian weight of tap")]
-    assert "lao_column" in body and "lao_at" in body
+    assert "lao_column" in body and "lao_column_rolled" in body and "lao_at" in body
     extract = tmp_path / "lao_extract.inc"
     extract.write_text(body.replace("__device__ __forceinline__", "static inline"))
     exe = tmp_path / "lao_column_check"

@@ -158,6 +158,83 @@ __device__ __forceinline__ void lao_column(const PrefilterArgs& A, const float* 
     }
 }
 
+// lao_column with the plane loop unrolled by the PERIOD of the register window (SPAN + 1 planes) instead of fully:
+// plane q lives in slot q mod (SPAN + 1), so inside one period every slot index is a compile-time constant and the code
+// is (SPAN + 1) / (TZ + SPAN) of the fully unrolled form (a third at radius 2.5, TZ = 16) -- the fully unrolled kernel
+// spends its third largest stall waiting for instructions.  Same operations in the same order:
+// bit-identical (tests/host_emulation).  An A/B build option (VKHR_B200_PF_ROLLED), not yet timed on the GPU.
+template <int NO0, int PO0, int TZ, class Emit>
+__device__ __forceinline__ void lao_column_rolled(const PrefilterArgs& A, const float* __restrict__ column, const uint32_t* __restrict__ flagcol,
+                                                  int plane_floats, int row_floats, int BY, bool tile_any, float ao_empty, int n_out, Emit&& emit) {
+    constexpr int SPAN = PO0 - NO0 + 1;
+    constexpr int P = SPAN + 1;                          // window period
+    constexpr int NQ = TZ + SPAN;
+    const int oy[4] = {NO0, NO0 + 1, PO0, PO0 + 1};
+    const AxisTaps ax[2] = {A.neg, A.pos};
+    float yl[P][4];                                      // [q mod P][2 * sx + sy]
+    bool live[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        live[j] = false;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) yl[j][c] = 0.0f;
+    }
+#pragma unroll 1
+    for (int q0 = 0; q0 < NQ; q0 += P) {
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            const int q = q0 + j;                        // q mod P == j: q0 is a multiple of P
+            if (q >= NQ) break;                          // warp-uniform
+            uint32_t any = 0u;
+            if (tile_any) {
+#pragma unroll
+                for (int yr = 0; yr < 4; ++yr) any |= flagcol[(q + NO0) * BY + oy[yr]];
+            }
+            live[j] = any != 0u;
+            if (any) {
+                const float* pl = column + (q + NO0) * plane_floats;
+                float xl[2][4];
+#pragma unroll
+                for (int yr = 0; yr < 4; ++yr) {
+                    const float* row = pl + oy[yr] * row_floats;
+                    xl[0][yr] = __fadd_rn(__fmul_rn(row[NO0], ax[0].w0), __fmul_rn(row[NO0 + 1], ax[0].w1));
+                    xl[1][yr] = __fadd_rn(__fmul_rn(row[PO0], ax[1].w0), __fmul_rn(row[PO0 + 1], ax[1].w1));
+                }
+#pragma unroll
+                for (int sx = 0; sx < 2; ++sx)
+#pragma unroll
+                    for (int sy = 0; sy < 2; ++sy)
+                        yl[j][2 * sx + sy] = __fadd_rn(__fmul_rn(xl[sx][2 * sy], ax[sy].w0), __fmul_rn(xl[sx][2 * sy + 1], ax[sy].w1));
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) yl[j][c] = 0.0f;
+            }
+            const int kz = q - SPAN;                     // the output whose last plane this is
+            if (kz >= 0 && kz < n_out) {                 // warp-uniform
+                // its planes kz, kz + 1, kz + SPAN - 1, kz + SPAN sit in slots j + 1, j + 2, j - 1, j (mod P)
+                const int s0 = (j + 1) % P, s1 = (j + 2) % P, s2 = (j + P - 1) % P, s3 = j;
+                float r = ao_empty;
+                if (live[s0] || live[s1] || live[s2] || live[s3]) {
+                    float density = 0.0f;
+#pragma unroll
+                    for (int sz = 0; sz < 2; ++sz) {
+                        const int qa = sz ? s2 : s0, qb = sz ? s3 : s1;
+#pragma unroll
+                        for (int sy = 0; sy < 2; ++sy)
+#pragma unroll
+                            for (int sx = 0; sx < 2; ++sx) {
+                                const float s = __fadd_rn(__fmul_rn(yl[qa][2 * sx + sy], ax[sz].w0), __fmul_rn(yl[qb][2 * sx + sy], ax[sz].w1));
+                                density = __fadd_rn(density, (A.ao_max < s) ? A.ao_max : s);
+                            }
+                    }
+                    r = powf(__fsub_rn(1.0f, __fdiv_rn(density, 8.0f)), A.ao_exponent);
+                }
+                emit(kz, r);
+            }
+        }
+    }
+}
+
 // Gaussian weight of tap (x,y,z) (sample_volume.glsl:26-27, precedence quirk kept).
 __device__ __forceinline__ float gauss_weight(float x, float y, float z, float sigma2) {
     const float e = __fmul_rn(__fdiv_rn(__fmul_rn(-1.0f, __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z))), 2.0f), sigma2);
@@ -396,7 +473,12 @@ k_prefilter_tiled(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                 const size_t zs = (size_t)A.W * A.H;
                 float* out = A.ao + ((size_t)X + (size_t)Y * A.W + (size_t)z0 * zs);
                 const bool inside = X < A.W;
-                lao_column<NO0, PO0, TZ>(A, ftile + (h * BY + (warp + h)) * FX + (lane + hx), rowflag + h * BY + (warp + h),
+#ifdef VKHR_B200_PF_ROLLED
+                lao_column_rolled<NO0, PO0, TZ>(
+#else
+                lao_column<NO0, PO0, TZ>(
+#endif
+                                     A, ftile + (h * BY + (warp + h)) * FX + (lane + hx), rowflag + h * BY + (warp + h),
                                      BY * FX, FX, BY, tile_any != 0, ao_empty, min(TZ, A.D - z0),
                                      [&](int kz, float r) { if (inside) __stcs(out + (size_t)kz * zs, r); });
             }
