@@ -137,7 +137,7 @@ def ncu_traffic(kernel_key: str):
 
 
 def make_instance(seed: int, seg_len: float):
-    from vkhr_b200 import synth
+    from harness import synth
     v, n, s = synth.shape("ponytail", seed=seed, seg_len=seg_len)
     lo, hi = synth.host_bounding_box(v)
     return v, n, s, lo, (hi - lo).astype(np.float32)
@@ -147,7 +147,8 @@ def other_configs(vox, dev, args, flags=0):
     """Short device-resident timings (CUDA events, 20 reps after 3 warm-ups) of the other BASELINE.json configs that
     fit one GPU; inputs are rotated over 8 copies (> L2) for the small sets.  Parity for these lives in tests/."""
     import torch
-    from vkhr_b200 import capi, synth
+    from vkhr_b200 import capi
+    from harness import synth
     out = {}
     cases = [("configs[0] ponytail 256^3, one instance", "ponytail", 0.5, 256, 8),
              ("configs[1] Yuksel-straight-shaped 50,000 x 65 at 512^3", "straight", 0.5, 512, 2),

@@ -1,4 +1,5 @@
-// synth.cc -- host-side synthetic strand generator (harness input, not part of parity).
+// synth.cc -- host-side synthetic strand generator (HARNESS input: tests, bench.py, golden generation;
+// never linked into the product library, not part of parity).
 //
 // The reference's assets (share/styles/*.hair) are Git-LFS pointers in the
 // checkout, so every workload is generated: seeded random-walk
@@ -8,8 +9,6 @@
 // RNG: the xorshift64 recurrence the reference uses for its strand shuffle
 // (src/vkhr/scene_graph/hair_style.cc:679-685), one stream per strand seeded
 // seed ^ 0x9E3779B97F4A7C15 * (strand + 1); u = (x >> 11) * 2^-53.
-#include "../../include/vkhr_b200.h"
-
 #include <cmath>
 #include <cstdint>
 
@@ -32,10 +31,10 @@ extern "C" {
 //   step k    p += seg_len * normalize(dir + curl * (u3 - 0.5) + gravity * (0,-1,0) + gather * toward_axis)
 // `gather` pulls strands toward the vertical line through the root box centre
 // (a ponytail-like band); 0 disables it.
-int vkhr_b200_synth_strands(uint32_t n_strands, uint32_t segs_per_strand, uint64_t seed,
+int vkhr_harness_synth_strands(uint32_t n_strands, uint32_t segs_per_strand, uint64_t seed,
                             const float root_min[3], const float root_max[3],
                             float seg_len, float curl, float gravity, float gather, float* xyz_out) {
-    if (!xyz_out || !root_min || !root_max || segs_per_strand == 0) return VKHR_B200_ERR_INVALID_ARGUMENT;
+    if (!xyz_out || !root_min || !root_max || segs_per_strand == 0) return -1;
     const double cx = 0.5 * (double(root_min[0]) + root_max[0]);
     const double cz = 0.5 * (double(root_min[2]) + root_max[2]);
     const size_t vps = size_t(segs_per_strand) + 1;
@@ -63,14 +62,14 @@ int vkhr_b200_synth_strands(uint32_t n_strands, uint32_t segs_per_strand, uint64
             }
         }
     }
-    return VKHR_B200_OK;
+    return 0;
 }
 
 // Per-frame sway of config 5: vertex k of a strand moves by
 // amplitude * (k/S)^2 * (sin(omega*t + phi_s), 0, cos(omega*t + phi_s)), phi_s from the strand id.
-int vkhr_b200_synth_sway(const float* xyz_in, uint32_t n_strands, uint32_t segs_per_strand,
+int vkhr_harness_synth_sway(const float* xyz_in, uint32_t n_strands, uint32_t segs_per_strand,
                          float t, float amplitude, float omega, float* xyz_out) {
-    if (!xyz_in || !xyz_out || segs_per_strand == 0) return VKHR_B200_ERR_INVALID_ARGUMENT;
+    if (!xyz_in || !xyz_out || segs_per_strand == 0) return -1;
     const size_t vps = size_t(segs_per_strand) + 1;
 #pragma omp parallel for schedule(static)
     for (long long s = 0; s < (long long)n_strands; ++s) {
@@ -84,7 +83,7 @@ int vkhr_b200_synth_sway(const float* xyz_in, uint32_t n_strands, uint32_t segs_
             xyz_out[i + 2] = float(double(xyz_in[i + 2]) + double(amplitude) * w * w * cz);
         }
     }
-    return VKHR_B200_OK;
+    return 0;
 }
 
 }  // extern "C"

@@ -28,7 +28,12 @@
  * Host-pointer entry points are synchronous.  `_dev` entry points take device
  * pointers, enqueue on the given cudaStream_t (NULL = the context's own stream;
  * pass cudaStreamLegacy, (void*)1, for the legacy default stream) and return
- * without synchronising.
+ * without synchronising.  All per-call scratch (counters, flags, staging) is
+ * owned by the context and shared between calls: when a call arrives on a
+ * different stream than the previous one, the library orders it behind the
+ * previous call with an event (record on the old stream, wait on the new), so
+ * switching streams is safe; two calls may still not be ISSUED concurrently
+ * from two host threads on one context.
  *
  * Errors: every call returns 0 or a negative vkhr_b200_status; nothing throws.
  * There is no CPU fallback: without a usable sm_100 device vkhr_b200_create fails.
@@ -113,18 +118,6 @@ VKHR_B200_API uint32_t vkhr_b200_last_strategy(const vkhr_b200_ctx* ctx);
 VKHR_B200_API int vkhr_b200_profile_enable(vkhr_b200_ctx* ctx, int enable);
 VKHR_B200_API int vkhr_b200_profile_read(vkhr_b200_ctx* ctx, double ms_out[4], uint32_t spans_out[4]);
 VKHR_B200_API int vkhr_b200_profile_read_ex(vkhr_b200_ctx* ctx, double* ms_out, uint32_t* spans_out, uint32_t n_phases);
-
-/* Self test of the kernels' fast exact division (walk.cuh div_exact): compares it
- * bit for bit with the IEEE division instruction sequence on n_trials
- * pseudo-random numerators for one divisor; *mismatches must come back 0. */
-VKHR_B200_API int vkhr_b200_selftest_division(vkhr_b200_ctx* ctx, float divisor, uint64_t n_trials,
-                                              uint64_t seed, uint64_t* mismatches);
-
-/* Measurement only: while enabled, every CTA of the uniform walk kernel records
- * {SM id, start ns, end ns, (instance << 32) | block} (4 x u64 per record).
- * enable = 1 arms the trace; enable = 0 disarms it and copies up to max_records out. */
-VKHR_B200_API int vkhr_b200_debug_trace(vkhr_b200_ctx* ctx, int enable, unsigned long long* host_out,
-                                        uint32_t max_records, uint32_t* n_records);
 
 /* ---- host-pointer API: replaces HairStyle::voxelize_segments ----------
  * (hair_style.hh:104, hair_style.cc:296-342).
@@ -355,16 +348,6 @@ VKHR_B200_API int vkhr_b200_free(vkhr_b200_ctx* ctx, void* d_ptr);
 VKHR_B200_API int vkhr_b200_memset(vkhr_b200_ctx* ctx, void* d_ptr, int value, size_t bytes, void* stream);
 VKHR_B200_API int vkhr_b200_upload(vkhr_b200_ctx* ctx, void* d_dst, const void* src, size_t bytes, void* stream);
 VKHR_B200_API int vkhr_b200_download(vkhr_b200_ctx* ctx, void* dst, const void* d_src, size_t bytes, void* stream);
-
-/* ---- harness helpers (host side; inputs only, not part of parity) ------- *
- * The reference's .hair assets are Git-LFS pointers in the checkout, so the
- * named workloads are generated: seeded random-walk strands of the named
- * shape (xorshift64 of hair_style.cc:679-685, one stream per strand). */
-VKHR_B200_API int vkhr_b200_synth_strands(uint32_t n_strands, uint32_t segs_per_strand, uint64_t seed,
-    const float root_min[3], const float root_max[3], float seg_len, float curl, float gravity, float gather,
-    float* xyz_out);
-VKHR_B200_API int vkhr_b200_synth_sway(const float* xyz_in, uint32_t n_strands, uint32_t segs_per_strand,
-    float t, float amplitude, float omega, float* xyz_out);
 
 #ifdef __cplusplus
 }

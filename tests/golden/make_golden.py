@@ -26,7 +26,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "..", ".."))
 
 import oracle  # noqa: E402
-from vkhr_b200 import synth  # noqa: E402  (host-side generator only)
+from harness import synth# noqa: E402  (host-side generator only)
 
 KAT_VERTICES = [[0, 0, 0], [4, 4, 4], [0.5, 3.5, 0.5], [3, 3.5, 0.5], [4, 4, 4], [3, 4, 2.5], [1, 1, 1], [1, 1, 1]]
 

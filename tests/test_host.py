@@ -8,7 +8,8 @@ import numpy as np
 import pytest
 
 import vkhr_b200
-from vkhr_b200 import HairStyle, capi, synth
+from vkhr_b200 import HairStyle, capi
+from harness import synth
 
 
 def test_library_exports_every_declared_symbol():

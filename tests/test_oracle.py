@@ -6,7 +6,7 @@ import pytest
 
 from conftest import dense
 
-from vkhr_b200 import synth
+from harness import synth
 
 
 def _fnv(port, a):

@@ -9,7 +9,8 @@ from conftest import dense
 pytestmark = pytest.mark.gpu
 
 import vkhr_b200
-from vkhr_b200 import HairStyle, capi, synth
+from vkhr_b200 import HairStyle, capi
+from harness import synth
 
 STRATEGIES = [0, capi.STRATEGY_COUNT32, capi.STRATEGY_PACKED8, capi.STRATEGY_BRICK8]   # BRICK8 falls back to PACKED8 where it cannot run
 
@@ -25,9 +26,11 @@ def test_native_library_is_loaded():
     assert "sm_100a" in vkhr_b200.Voxelizer.version()
 
 
-def test_fast_division_is_exact(vox):
+def test_fast_division_is_exact():
     """The kernels replace `a / d` by an FMA sequence with a precomputed reciprocal (walk.cuh div_exact);
-    it must equal the IEEE division bit for bit, including operands on both sides of its range guard."""
+    it must equal the IEEE division bit for bit, including operands on both sides of its range guard.
+    (The self-test kernels live in the harness library, which includes the product's walk.cuh.)"""
+    from harness import selftest
     rng = np.random.default_rng(3)
     divisors = [1.0, 0.21861044, 0.39062497, 1.9999999, 1.0000001, 3.0, 0.1, 7.0, 1.5, 0.75, 255.0, 1e-3, 1e4,
                 float(np.float32(100.0) / np.float32(256.0)), float(np.float32(56.558083) / np.float32(256.0))]
@@ -36,9 +39,17 @@ def test_fast_division_is_exact(vox):
     divisors += [1e-13, 1e13]            # outside the fast range: must still be exact (plain division)
     total = 0
     for i, d in enumerate(divisors):
-        assert vox.selftest_division(d, n_trials=1 << 26, seed=1000 + i) == 0, d
+        assert selftest.division(d, n_trials=1 << 26, seed=1000 + i) == 0, d
         total += 1 << 26
     assert total > 2_000_000_000
+
+
+def test_walk_reciprocal_is_correctly_rounded_for_every_step_count():
+    """`direction /= steps` (hair_style.cc:317): the walk's reciprocal (walk.cuh rcp_steps: MUFU.RCP + one Newton step,
+    no range test) equals __frcp_rn, and the FMA division built on it equals the IEEE division, for EVERY float
+    steps in [2^-40, 2^24] -- the whole interval the fast path admits (about 5.4e8 divisors, 3 numerators each)."""
+    from harness import selftest
+    assert selftest.rcp(9.094947e-13, 16777216.0) == 0
 
 
 def test_unaligned_and_offset_device_buffers(vox, port):

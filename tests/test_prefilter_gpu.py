@@ -6,7 +6,8 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-from vkhr_b200 import capi, synth
+from vkhr_b200 import capi
+from harness import synth
 
 REL_TOL = 1e-6
 

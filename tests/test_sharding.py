@@ -9,7 +9,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from vkhr_b200 import sharding, synth
+from vkhr_b200 import sharding
+from harness import synth
 
 
 def test_strand_range_partitions_every_strand_once():

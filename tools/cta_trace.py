@@ -3,7 +3,8 @@ import ctypes as C, json, os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np, torch
 import vkhr_b200
-from vkhr_b200 import capi, synth
+from vkhr_b200 import capi
+from harness import synth
 
 inst = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 dev = torch.device("cuda", 0)

@@ -3,7 +3,7 @@ import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import vkhr_b200
-from vkhr_b200 import synth
+from harness import synth
 
 vox = vkhr_b200.Voxelizer(0)
 res = {}

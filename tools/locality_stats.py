@@ -11,7 +11,7 @@ shared-memory brick histogram over strands binned by root could absorb.
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-from vkhr_b200 import synth
+from harness import synth
 
 W = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 v, n, s = synth.shape("ponytail", seed=0x5EED, seg_len=0.5)

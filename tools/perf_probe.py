@@ -15,7 +15,8 @@ import numpy as np
 import torch
 
 import vkhr_b200
-from vkhr_b200 import capi, synth
+from vkhr_b200 import capi
+from harness import synth
 
 
 def main():

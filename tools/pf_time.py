@@ -3,7 +3,7 @@ import json, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import vkhr_b200
-from vkhr_b200 import synth
+from harness import synth
 
 W = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 vox = vkhr_b200.Voxelizer(0)

@@ -18,7 +18,8 @@ import torch
 import torch.distributed as dist
 
 import vkhr_b200
-from vkhr_b200 import sharding, synth
+from vkhr_b200 import sharding
+from harness import synth
 
 
 def main():

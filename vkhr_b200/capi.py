@@ -13,7 +13,7 @@ import re
 
 from . import build as _build
 
-LIB_PATH = os.environ.get("VKHR_B200_LIB") or _build.LIB      # override: A/B builds of the same ABI (measurement)
+LIB_PATH = _build.LIB
 HEADER_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "include", "vkhr_b200.h")
 
 # status codes / flags (include/vkhr_b200.h)
@@ -116,8 +116,6 @@ _PROTOTYPES = {
     "vkhr_b200_last_strategy": (C.c_uint32, [c_ctx]),
     "vkhr_b200_profile_enable": (_int, [c_ctx, _int]),
     "vkhr_b200_profile_read": (_int, [c_ctx, C.c_double * 4, C.c_uint32 * 4]),
-    "vkhr_b200_selftest_division": (_int, [c_ctx, C.c_float, _u64, _u64, C.POINTER(_u64)]),
-    "vkhr_b200_debug_trace": (_int, [c_ctx, _int, _P, _u32, C.POINTER(_u32)]),
     "vkhr_b200_voxelize_segments": (_int, [c_ctx, _P, _u32, _P, _u64, _u32, _P, _vec3, _vec3, _u32, _u32, _u32, _u32, _P, _P]),
     "vkhr_b200_voxelize_vertices": (_int, [c_ctx, _P, _u32, _P, _vec3, _vec3, _u32, _u32, _u32, _u32, _P, _P]),
     "vkhr_b200_voxelize_segments_dev": (_int, [c_ctx, _P, _u32, _P, _u64, _u32, _P, _vec3, _vec3, _u32, _u32, _u32, _u32, _P, _P, _P]),
@@ -151,8 +149,6 @@ _PROTOTYPES = {
     "vkhr_b200_memset": (_int, [c_ctx, _P, _int, _sz, _P]),
     "vkhr_b200_upload": (_int, [c_ctx, _P, _P, _sz, _P]),
     "vkhr_b200_download": (_int, [c_ctx, _P, _P, _sz, _P]),
-    "vkhr_b200_synth_strands": (_int, [_u32, _u32, _u64, _vec3, _vec3, C.c_float, C.c_float, C.c_float, C.c_float, _P]),
-    "vkhr_b200_synth_sway": (_int, [_P, _u32, _u32, C.c_float, C.c_float, C.c_float, _P]),
 }
 
 for _name, (_res, _args) in _PROTOTYPES.items():

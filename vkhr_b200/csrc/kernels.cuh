@@ -136,11 +136,18 @@ struct SinkPacked8Brick {
     uint32_t* words;                // the brick-ordered scratch
     unsigned long long* stats;
     uint32_t wh;                    // (W / 4) | (H / 4) << 16 (only the literal path needs it); POW2: log2 W | log2 H << 8
+    uint32_t wb, hb;                // bricks per row (W / 4), brick rows per slab (H / 4): put_xyz
     uint32_t added = 0;             // samples this lane added
     template <int SLOT>
     __device__ __forceinline__ void put_brick(uint32_t lin, uint32_t bword) {
         red_add_u32(words + bword, 1u << ((lin & 3u) * 8u));
         ++added;
+    }
+    // a voxel inside the grid by its coordinates (the int32-index walk, EXACT == 3): two IMADs name the brick
+    template <int SLOT>
+    __device__ __forceinline__ void put_xyz(int ix, int iy, int iz) {
+        const uint32_t brick = ((uint32_t)(iz >> 1) * hb + (uint32_t)(iy >> 2)) * wb + (uint32_t)(ix >> 2);
+        put_brick<SLOT>((uint32_t)ix, brick * 8u + ((uint32_t)(iz & 1) * 4u + (uint32_t)(iy & 3)));
     }
     template <int SLOT>
     __device__ __forceinline__ void put_linear(uint32_t lin) { put_brick<SLOT>(lin, brick_word_pow2(lin, wh & 0xFFu, wh >> 8)); }
@@ -157,19 +164,21 @@ struct SinkPacked8Brick {
         const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, added);
         if ((threadIdx.x & 31u) == 0u && total)
             atomicAdd(stats + ((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (kStatSlots - 1u)), (unsigned long long)total);
+        added = 0;
     }
-    __device__ __forceinline__ void words_pin() { asm volatile("" : "+l"(words)); }
+    __device__ __forceinline__ void words_pin() { asm volatile("" : "+l"(words)); asm volatile("" : "+r"(wb)); asm volatile("" : "+r"(hb)); }
 };
 
-// Recount pass of PACKED8: only samples landing in flagged words are counted,
-// into the u32 scratch grid.
+// Recount pass of PACKED8 / BRICK8: only samples landing in flagged words of the voxel chunk [c0, c0 + span) are
+// counted, into the u32 chunk scratch (k_repair_packed).
 struct SinkRecount {
     const uint32_t* ovf_bitmap;     // nullptr: every word is recounted (BRICK8: the byte sum did not match)
-    uint32_t* counts;
+    uint32_t* counts;               // u32 per voxel of the chunk
+    uint32_t c0, span;
     template <int SLOT = 0>
     __device__ __forceinline__ void put(uint32_t idx) {
-        const uint32_t w = idx >> 2;
-        if (!ovf_bitmap || ((__ldg(ovf_bitmap + (w >> 5)) >> (w & 31u)) & 1u)) atomicAdd(counts + idx, 1u);
+        const uint32_t rel = idx - c0, w = idx >> 2;
+        if (rel < span && (!ovf_bitmap || ((__ldg(ovf_bitmap + (w >> 5)) >> (w & 31u)) & 1u))) atomicAdd(counts + rel, 1u);
     }
     __device__ __forceinline__ void finish() {}
 };
@@ -183,11 +192,11 @@ template <> struct SinkOf<1> { using type = SinkPacked8;
 template <> struct SinkOf<3> { using type = SinkPacked8Brick<false>;
     __device__ static type make(const InstanceDev& I) {
         type k; k.words = reinterpret_cast<uint32_t*>(I.brick); k.stats = I.stats;
-        k.wh = (I.grid.W >> 2) | ((I.grid.H >> 2) << 16); return k; } };
+        k.wh = (I.grid.W >> 2) | ((I.grid.H >> 2) << 16); k.wb = I.grid.W >> 2; k.hb = I.grid.H >> 2; return k; } };
 template <> struct SinkOf<4> { using type = SinkPacked8Brick<true>;
     __device__ static type make(const InstanceDev& I) {
         type k; k.words = reinterpret_cast<uint32_t*>(I.brick); k.stats = I.stats;
-        k.wh = (31u - (uint32_t)__clz((int)I.grid.W)) | ((31u - (uint32_t)__clz((int)I.grid.H)) << 8); return k; } };
+        k.wh = (31u - (uint32_t)__clz((int)I.grid.W)) | ((31u - (uint32_t)__clz((int)I.grid.H)) << 8); k.wb = I.grid.W >> 2; k.hb = I.grid.H >> 2; return k; } };
 
 // ---------------------------------------------------------------------------
 // Walk kernel for uniform strands (no index buffer): the hot kernel.
@@ -227,6 +236,11 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     for (uint32_t spin = 0; !done; ++spin) {
@@ -236,19 +250,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
-// Measurement only: when non-null, every CTA of k_walk_uniform records {smid, start ns, end ns, instance}.
-__device__ unsigned long long* g_cta_trace = nullptr;
-__device__ unsigned int g_cta_trace_count = 0;
-__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-__device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
-
 template <class T> __device__ __forceinline__ T* pin(T* p) { asm volatile("" : "+l"(p)); return p; }
 
 // The walk of CTA `bx` of instance I (uniform strands).
 template <int MODE, int EXACT>
 __device__ __forceinline__ void walk_uniform_cta(const InstanceDev& I, uint32_t bx, uint32_t inst_id,
                                                  float (*s_stage)[kStageFloats], unsigned long long* s_bar) {
-    const unsigned long long t_start = g_cta_trace ? globaltimer_ns() : 0ull;
     if (bx >= I.n_tiles || I.kind != WK_UNIFORM) return;          // n_tiles counts CTAs
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const GridParams g = pin(I.grid);                              // registers, not indexed constant loads
@@ -289,10 +296,12 @@ __device__ __forceinline__ void walk_uniform_cta(const InstanceDev& I, uint32_t 
     }
 
     // ---- loop-carried lane state, all in registers ---------------------------------------------------------
-    // lane_off: this lane's vertex of tile 0 in `stage` (tile k is 93 floats further).
+    // saddr: shared-memory address of this lane's vertex of the tile being fetched (a tile is 93 floats further);
+    // kept as a pinned 32-bit shared address -- left to itself the compiler rebuilds it from %tid and the CTA's
+    // shared window (two S2R, a LEA, two IMADs) for every tile.
     // x: global vertex index of this lane's vertex; r = x mod (segs + 1), advanced by 31 mod (segs + 1) per tile
     // (one multiply-high division per warp instead of one per tile).
-    uint32_t lane_off = pin(3u * lane);                            // float offset into `stage` (kept an offset: shared address space)
+    uint32_t saddr = pin(smem_u32(stage) + 12u * lane);
     const uint32_t vps = pin(I.segs_per_strand + 1u);
     uint32_t x = kTileStride * tile0 + lane;
     uint32_t r, r_step;
@@ -304,48 +313,48 @@ __device__ __forceinline__ void walk_uniform_cta(const InstanceDev& I, uint32_t 
         if ((int32_t)r_step < 0) r_step += vps;
         r = pin(r); r_step = pin(r_step);
     }
+    const bool seg_lane = pin((uint32_t)(lane < kTileStride)) != 0u;   // lane 31 only supplies the tip of lane 30
 
     // ---- software-pipelined tile loop ------------------------------------------------------------------
     // Shared-memory loads and shuffles share the SM's memory-instruction queue with the reds; behind a burst
     // of reds each round trip takes as long as the queue is deep.  So nothing in a tile's walk waits for a
     // round trip issued in the same iteration: the raw floats of tile k+2 and the transformed + shuffled end
-    // points of tile k+1 are requested BEFORE tile k is walked.
-    float r0, r1, r2, px, py, pz, tx, ty, tz;
-    r0 = stage[lane_off]; r1 = stage[lane_off + 1u]; r2 = stage[lane_off + 2u];
-    to_voxel_space_warp(g, r0, r1, r2, px, py, pz);
-    tx = __shfl_down_sync(kFullWarp, px, 1);
-    ty = __shfl_down_sync(kFullWarp, py, 1);
-    tz = __shfl_down_sync(kFullWarp, pz, 1);
-    lane_off += 3u * kTileStride;
-    if (n_tiles > 1u) { r0 = stage[lane_off]; r1 = stage[lane_off + 1u]; r2 = stage[lane_off + 2u]; }
-    for (uint32_t k = n_tiles; k > 0u; --k) {
-        float npx = 0.f, npy = 0.f, npz = 0.f, ntx = 0.f, nty = 0.f, ntz = 0.f;
+    // points of tile k+1 are requested BEFORE tile k is walked.  The loop body is written out twice with the two
+    // end-point sets swapping roles, so no register moves carry one iteration's "next" into the other's "current".
+    struct Ends { float px, py, pz, tx, ty, tz; };
+    float r0, r1, r2;
+    auto fetch = [&]() { r0 = lds_f32(saddr); r1 = lds_f32(saddr + 4u); r2 = lds_f32(saddr + 8u); saddr += 12u * kTileStride; };
+    auto transform = [&](Ends& e) {
+        to_voxel_space_warp(g, r0, r1, r2, e.px, e.py, e.pz);
+        e.tx = __shfl_down_sync(kFullWarp, e.px, 1);
+        e.ty = __shfl_down_sync(kFullWarp, e.py, 1);
+        e.tz = __shfl_down_sync(kFullWarp, e.pz, 1);
+    };
+    // one tile: k tiles are left including this one; `cur` holds its end points, `nxt` receives the next tile's
+    auto tile = [&](const Ends& cur, Ends& nxt, uint32_t k) {
         if (k > 1u) {                                              // warp-uniform
-            to_voxel_space_warp(g, r0, r1, r2, npx, npy, npz);
-            ntx = __shfl_down_sync(kFullWarp, npx, 1);
-            nty = __shfl_down_sync(kFullWarp, npy, 1);
-            ntz = __shfl_down_sync(kFullWarp, npz, 1);
-            lane_off += 3u * kTileStride;
-            if (k > 2u) { r0 = stage[lane_off]; r1 = stage[lane_off + 1u]; r2 = stage[lane_off + 2u]; }
+            transform(nxt);
+            if (k > 2u) fetch();
         }
         // vertex x starts a segment unless it is the last of its strand
-        const bool active = lane < kTileStride && x + 1u < n_vertices && r != vps - 1u;
-        walk_voxel_space_warp<EXACT, false>(g, active, px, py, pz, tx, ty, tz, sink);
-        px = npx; py = npy; pz = npz; tx = ntx; ty = nty; tz = ntz;
+        const bool active = seg_lane && x + 1u < n_vertices && r != vps - 1u;
+        walk_voxel_space_warp<EXACT, false>(g, active, cur.px, cur.py, cur.pz, cur.tx, cur.ty, cur.tz, sink);
         x += kTileStride;
         r += r_step;
         if (r >= vps) r -= vps;
+    };
+    Ends ea, eb;
+    eb.px = eb.py = eb.pz = eb.tx = eb.ty = eb.tz = 0.0f;
+    fetch();
+    transform(ea);
+    if (n_tiles > 1u) fetch();
+    for (uint32_t k = n_tiles;;) {
+        tile(ea, eb, k);
+        if (--k == 0u) break;
+        tile(eb, ea, k);
+        if (--k == 0u) break;
     }
     sink.finish();
-    if (g_cta_trace && threadIdx.x == 0) {                         // warp 0's own duration (no CTA barrier here)
-        const unsigned int slot = atomicAdd(&g_cta_trace_count, 1u);
-        if (slot < (1u << 20)) {
-            g_cta_trace[4ull * slot + 0] = smid();
-            g_cta_trace[4ull * slot + 1] = t_start;
-            g_cta_trace[4ull * slot + 2] = globaltimer_ns();
-            g_cta_trace[4ull * slot + 3] = ((unsigned long long)inst_id << 32) | bx;
-        }
-    }
 }
 
 template <int MODE, int EXACT>
@@ -371,10 +380,12 @@ k_walk_indexed(const __grid_constant__ Batch B, uint32_t first) {
     float ax = 0.f, ay = 0.f, az = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
     if (active) {
         const uint2 pr = __ldg(reinterpret_cast<const uint2*>(I.indices) + s);
-        const float* a = I.vertices + 3ull * pr.x;
-        const float* b = I.vertices + 3ull * pr.y;
-        ax = __ldg(a); ay = __ldg(a + 1); az = __ldg(a + 2);
-        bx = __ldg(b); by = __ldg(b + 1); bz = __ldg(b + 2);
+        if (pr.x < I.n_vertices && pr.y < I.n_vertices) {          // an index past the vertex array (a corrupt file) is dropped, not read
+            const float* a = I.vertices + 3ull * pr.x;
+            const float* b = I.vertices + 3ull * pr.y;
+            ax = __ldg(a); ay = __ldg(a + 1); az = __ldg(a + 2);
+            bx = __ldg(b); by = __ldg(b + 1); bz = __ldg(b + 2);
+        }
     }
     auto sink = SinkOf<MODE>::make(I);
     float px, py, pz, tx, ty, tz;
@@ -504,24 +515,6 @@ k_finish_tangent(unsigned long long* __restrict__ acc, uint64_t n_voxels, uint8_
         dens[i] = (uint8_t)min(count, 255u);
         if (tang) tang[i] = t;
     }
-}
-
-// Bitwise comparison of div_exact against the IEEE division on pseudo-random
-// operands (self test of the fast exact division; see walk.cuh).
-__global__ void __launch_bounds__(256)
-k_selftest_division(float d, float y, uint64_t seed, uint32_t per_thread, unsigned long long* mismatches) {
-    uint64_t x = seed ^ (0x9E3779B97F4A7C15ull * ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 1));
-    uint32_t bad = 0;
-    for (uint32_t i = 0; i < per_thread; ++i) {
-        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
-        // random sign and mantissa, exponent spread over [2^-70, 2^70] (both sides of the guard)
-        const uint32_t e = 127u - 70u + (uint32_t)((x >> 40) % 141u);
-        const float a = __uint_as_float(((uint32_t)x & 0x807FFFFFu) | (e << 23));
-        const float q = div_exact(a, d, y);
-        const float want = __fdiv_rn(a, d);
-        bad += (__float_as_uint(q) != __float_as_uint(want));
-    }
-    if (bad) atomicAdd(mismatches, (unsigned long long)bad);
 }
 
 // ---------------------------------------------------------------------------
@@ -871,9 +864,14 @@ k_aabb_reduce(const float* __restrict__ xyz, uint32_t n_vertices, uint32_t* __re
         for (int r = 0; r < 3; ++r) {
             const uint64_t i = base + r * 256 + threadIdx.x;
             if (i < n) {
-                const uint32_t k = f2key(xyz[i]);
-                lo[r] = min(lo[r], k);
-                hi[r] = max(hi[r], k);
+                // the reference folds with `(b < a) ? b : a` / `(a < b) ? b : a` from +0.0f (hair_style.cc:215-234): a -0.0f
+                // never replaces +0.0f and a NaN never replaces anything.  `f + 0.0f` turns -0.0f into +0.0f.
+                const float f = __fadd_rn(xyz[i], 0.0f);
+                if (f == f) {
+                    const uint32_t k = f2key(f);
+                    lo[r] = min(lo[r], k);
+                    hi[r] = max(hi[r], k);
+                }
             }
         }
     }

@@ -283,6 +283,7 @@ __device__ __forceinline__ float opacity_of(const PrefilterArgs& A, uint32_t d) 
     return powf(A.one_minus_alpha, __fmul_rn(__fdiv_rn((float)d, 255.0f), A.thickness));
 }
 
+#ifndef VKHR_PF_TILED_ONLY      // the non-template kernels live in ONE translation unit (vkhr_b200.cu)
 // ---- generic kernel: any grid size / alignment / radius; one thread per voxel, texels straight from global ----
 __global__ void __launch_bounds__(256)
 k_prefilter_generic(const __grid_constant__ PrefilterArgs A) {
@@ -307,6 +308,8 @@ k_prefilter_generic(const __grid_constant__ PrefilterArgs A) {
         if (A.gauss) A.gauss[v] = gauss_at(A, s_gw, g_total, fetch);
     }
 }
+
+#endif  // VKHR_PF_TILED_ONLY
 
 // ---- tiled kernel: persistent CTAs, 3-D TMA box loads (zero fill outside the grid = the black border) ----------
 __device__ __forceinline__ uint32_t pf_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -352,6 +355,10 @@ __host__ __device__ inline PfSmemPlan pf_plan(int halo, int g_range, int tz) {
 // lane as one register-tiled column), or kPfRowWise: offsets read from A, one lao_at per voxel (any radius, and the
 // launches that do not ask for AO).
 constexpr int kPfRowWise = 99;
+// One instantiation of the tiled kernel, as the host's dispatch table sees it.  The instantiations are spread over
+// translation units (prefilter_variants.cu, one tap-offset pair each) and collected through pf_variants_<g>().
+typedef void (*PfKernel)(const CUtensorMap, const PrefilterArgs);
+struct PfVariant { int no0, po0, tz; PfKernel kernel; };
 constexpr int kPfVariantCount = 19;                  // row-wise + 9 column instantiations x 2 tile depths (the host's dispatch table)
 static_assert(kPfThreads / 32 == kPfTY, "one warp per y row of the tile");
 static_assert(kPfThreads % (kPfBX / 4) == 0 && kPfLead % 4 == 0, "a thread converts the same word of every staged row it visits");
@@ -530,6 +537,7 @@ k_prefilter_tiled(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     }
 }
 
+#ifndef VKHR_PF_TILED_ONLY
 // ---------------------------------------------------------------------------------------------------------
 // Volumetric ADSM transmittance volume: volume_approximated_deep_shadows (share/shaders/self-shadowing/
 // approximate_deep_shadows.glsl:24-36, call site volumes/volume.frag:72-78) evaluated at every voxel centre --
@@ -677,5 +685,7 @@ k_adsm(const __grid_constant__ AdsmArgs A) {
     }
     A.out[lin] = powf(A.base, strands);
 }
+
+#endif  // VKHR_PF_TILED_ONLY
 
 }  // namespace vkhr_b200

@@ -24,21 +24,27 @@ namespace cg = cooperative_groups;
 using namespace vkhr_b200;
 
 // ---------------------------------------------------------------------------
-// PACKED8 repair: one persistent cooperative kernel.  Instances whose overflow
+// PACKED8 / BRICK8 repair: one persistent cooperative kernel.  Instances whose overflow
 // flag is set (some voxel received more than 255 hits) are handled one after
-// the other on a single shared u32 scratch grid:
+// the other on a single shared u32 scratch of kRepairChunk voxels (64 MiB; a
+// whole 256^3 volume, 1/8 of a 512^3, 1/64 of a 1024^3 one -- the scratch used
+// to be a full W*H*D u32 grid, 4 GiB at 1024^3, reserved eagerly for a pass that
+// almost never runs).  Per chunk of the volume:
 //   zero the scratch entries of flagged words -> grid barrier ->
-//   re-walk the instance, counting only samples that land in flagged words ->
-//   grid barrier -> rewrite the flagged words as min(count, 255).
+//   re-walk the instance, counting only samples that land in flagged words of the chunk ->
+//   grid barrier -> rewrite those words as min(count, 255).
+// Chunks without a flagged word are skipped (one extra barrier to agree on that).
 // With no flag set (the common case) every CTA returns after reading n flags.
 // ---------------------------------------------------------------------------
+constexpr uint32_t kRepairChunk = 1u << 24;                    // voxels; a multiple of 128 (whole bitmap words)
+
 template <bool VERTICES>
 __global__ void __launch_bounds__(kWalkThreads)
 k_repair_packed(const __grid_constant__ Batch B, uint32_t* __restrict__ scratch) {
     // common case first: no instance overflowed -> one parallel look at the flags and out
     const uint32_t n_inst = B.n;
     const InstanceDev* inst = B.inst;
-    // (BRICK8 has no per-word flags: k_brick_verdict sets the flag to 2 when the byte sum of the volume differs from
+    // (BRICK8 has no per-word flags: the verdict sets the flag to 2 when the byte sum of the volume differs from
     // the number of samples added, and then every word is recounted)
     int any = 0;
     for (uint32_t k = threadIdx.x; k < n_inst; k += blockDim.x) any |= (*inst[k].ovf_flag != 0u);
@@ -52,53 +58,66 @@ k_repair_packed(const __grid_constant__ Batch B, uint32_t* __restrict__ scratch)
         if (flag == 0u) continue;
         const bool all = flag == 2u;
         const GridParams g = I.grid;
-        const uint32_t n_words = g.n_voxels >> 2;
-        const uint32_t n_bm = (n_words + 31) / 32;
         uint32_t* words = reinterpret_cast<uint32_t*>(I.densities);
         uint4* counts4 = reinterpret_cast<uint4*>(scratch);
-        for (uint32_t b = tid; b < n_bm; b += nthreads) {
-            uint32_t m = all ? 0xFFFFFFFFu : I.ovf_bitmap[b];
-            while (m) {
-                const uint32_t w = b * 32 + (__ffs(m) - 1);
-                m &= m - 1;
-                if (w < n_words) counts4[w] = make_uint4(0, 0, 0, 0);
+        volatile uint32_t* chunk_any = I.ovf_flag + 1;         // header word [1]: does this chunk hold a flagged word?
+        for (uint32_t c0 = 0; c0 < g.n_voxels; c0 += kRepairChunk) {
+            const uint32_t span = min(kRepairChunk, g.n_voxels - c0);          // voxels of this chunk
+            const uint32_t w0 = c0 >> 2, n_words = span >> 2;                  // its 32-bit words (n_voxels % 16 == 0)
+            const uint32_t b0 = w0 >> 5, n_bm = (n_words + 31u) >> 5;          // its bitmap words
+            if (!all) {
+                if (tid == 0) *chunk_any = 0u;
+                grid.sync();
             }
+            bool mine = false;
+            for (uint32_t b = tid; b < n_bm; b += nthreads) {
+                uint32_t m = all ? 0xFFFFFFFFu : I.ovf_bitmap[b0 + b];
+                mine = mine || m != 0u;
+                while (m) {
+                    const uint32_t w = b * 32 + (__ffs(m) - 1);
+                    m &= m - 1;
+                    if (w < n_words) counts4[w] = make_uint4(0, 0, 0, 0);
+                }
+            }
+            if (!all && mine) *chunk_any = 1u;
+            grid.sync();
+            if (!all && *chunk_any == 0u) continue;            // uniform: written before the barrier, not after
+            SinkRecount sink{all ? nullptr : I.ovf_bitmap, scratch, c0, span};
+            if (VERTICES) {
+                for (uint32_t i = tid; i < I.n_vertices; i += nthreads) {
+                    const float* v = I.vertices + 3ull * i;
+                    uint32_t idx;
+                    if (voxel_index(g, to_voxel_space(__ldg(v), g.ox, g.vsx, g.rvx), to_voxel_space(__ldg(v + 1), g.oy, g.vsy, g.rvy),
+                                    to_voxel_space(__ldg(v + 2), g.oz, g.vsz, g.rvz), idx))
+                        sink.put<0>(idx);
+                }
+            } else if (I.indices) {
+                for (uint64_t s = tid; s < I.n_segments; s += nthreads) {
+                    const uint2 pr = __ldg(reinterpret_cast<const uint2*>(I.indices) + s);
+                    if (pr.x >= I.n_vertices || pr.y >= I.n_vertices) continue;      // as the walk: dropped, not read
+                    const float* a = I.vertices + 3ull * pr.x;
+                    const float* b = I.vertices + 3ull * pr.y;
+                    walk_segment(g, __ldg(a), __ldg(a + 1), __ldg(a + 2), __ldg(b), __ldg(b + 1), __ldg(b + 2), sink);
+                }
+            } else {
+                const uint32_t vps = I.segs_per_strand + 1u;
+                for (uint32_t v = tid; v + 1u < I.n_vertices; v += nthreads) {
+                    if (v % vps == vps - 1u) continue;             // last vertex of a strand starts no segment
+                    const float* a = I.vertices + 3ull * v;
+                    walk_segment(g, __ldg(a), __ldg(a + 1), __ldg(a + 2), __ldg(a + 3), __ldg(a + 4), __ldg(a + 5), sink);
+                }
+            }
+            grid.sync();
+            for (uint32_t b = tid; b < n_bm; b += nthreads) {
+                uint32_t m = all ? 0xFFFFFFFFu : I.ovf_bitmap[b0 + b];
+                while (m) {
+                    const uint32_t w = b * 32 + (__ffs(m) - 1);
+                    m &= m - 1;
+                    if (w < n_words) words[w0 + w] = clamp4(counts4[w]);
+                }
+            }
+            grid.sync();                                           // scratch is reused by the next chunk / flagged instance
         }
-        grid.sync();
-        SinkRecount sink{all ? nullptr : I.ovf_bitmap, scratch};
-        if (VERTICES) {
-            for (uint32_t i = tid; i < I.n_vertices; i += nthreads) {
-                const float* v = I.vertices + 3ull * i;
-                uint32_t idx;
-                if (voxel_index(g, to_voxel_space(__ldg(v), g.ox, g.vsx, g.rvx), to_voxel_space(__ldg(v + 1), g.oy, g.vsy, g.rvy),
-                                to_voxel_space(__ldg(v + 2), g.oz, g.vsz, g.rvz), idx))
-                    sink.put<0>(idx);
-            }
-        } else if (I.indices) {
-            for (uint64_t s = tid; s < I.n_segments; s += nthreads) {
-                const uint2 pr = __ldg(reinterpret_cast<const uint2*>(I.indices) + s);
-                const float* a = I.vertices + 3ull * pr.x;
-                const float* b = I.vertices + 3ull * pr.y;
-                walk_segment(g, __ldg(a), __ldg(a + 1), __ldg(a + 2), __ldg(b), __ldg(b + 1), __ldg(b + 2), sink);
-            }
-        } else {
-            const uint32_t vps = I.segs_per_strand + 1u;
-            for (uint32_t v = tid; v + 1u < I.n_vertices; v += nthreads) {
-                if (v % vps == vps - 1u) continue;             // last vertex of a strand starts no segment
-                const float* a = I.vertices + 3ull * v;
-                walk_segment(g, __ldg(a), __ldg(a + 1), __ldg(a + 2), __ldg(a + 3), __ldg(a + 4), __ldg(a + 5), sink);
-            }
-        }
-        grid.sync();
-        for (uint32_t b = tid; b < n_bm; b += nthreads) {
-            uint32_t m = all ? 0xFFFFFFFFu : I.ovf_bitmap[b];
-            while (m) {
-                const uint32_t w = b * 32 + (__ffs(m) - 1);
-                m &= m - 1;
-                if (w < n_words) words[w] = clamp4(counts4[w]);
-            }
-        }
-        grid.sync();                                           // scratch is reused by the next flagged instance
     }
 }
 
@@ -115,6 +134,11 @@ struct vkhr_b200_ctx {
     int sm_count = 0;
     size_t smem_per_sm = 0;       // shared memory of one SM (bytes): how many CTAs of the tiled prefilter fit
     cudaStream_t stream = nullptr;
+    // every entry point shares the context's scratch: a call on another stream than the previous call's is ordered
+    // behind it (pick())
+    cudaStream_t last_stream = nullptr;
+    bool last_stream_valid = false;
+    cudaEvent_t order_event = nullptr;
     std::string err;
     uint64_t launches = 0;
     DevBuf counts;        // u32 scratch grid(s)
@@ -199,8 +223,19 @@ int reserve(vkhr_b200_ctx* ctx, DevBuf& b, size_t bytes) {
     return VKHR_B200_OK;
 }
 
+// The stream of this call.  The context's scratch (counters, flags, staging, the "known zero" invariants) is shared
+// between calls, so a call that arrives on a different stream than the previous one waits for it: an event recorded on
+// the old stream, awaited on the new one.  (A stream the caller has destroyed meanwhile has no pending work: the failing
+// record is ignored.)
 inline cudaStream_t pick(vkhr_b200_ctx* ctx, void* stream) {
-    return stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    if (ctx->last_stream_valid && s != ctx->last_stream && ctx->order_event) {
+        if (cudaEventRecord(ctx->order_event, ctx->last_stream) == cudaSuccess) cudaStreamWaitEvent(s, ctx->order_event, 0);
+        else (void)cudaGetLastError();
+    }
+    ctx->last_stream = s;
+    ctx->last_stream_valid = true;
+    return s;
 }
 
 cudaEvent_t take_event(vkhr_b200_ctx* ctx) {
@@ -266,6 +301,8 @@ int make_grid(vkhr_b200_ctx* ctx, const float origin[3], const float size[3],
 // Number of segments described by (indices, n_indices) or by uniform strands.
 int segment_count(vkhr_b200_ctx* ctx, const uint32_t* d_indices, uint64_t n_indices, uint32_t n_vertices,
                   uint32_t segs, uint64_t& n_segments) {
+    if (n_vertices > 0xFFFFFFFFu / 3u - 1024u)                   // the kernels address floats with 32-bit offsets
+        return fail(ctx, VKHR_B200_ERR_UNSUPPORTED, "more than 2^32 / 3 vertices");
     if (d_indices) {
         if (reinterpret_cast<uintptr_t>(d_indices) & 7u)
             return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "indices must be 8-byte aligned");
@@ -464,7 +501,7 @@ int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_
             }
         }
         RET_IF(reserve(ctx, ctx->bitmap, (size_t)chunk * (bm_words + kHdr) * 4));
-        RET_IF(reserve(ctx, ctx->counts, nv * 4));
+        RET_IF(reserve(ctx, ctx->counts, std::min<uint64_t>(nv, kRepairChunk) * 4));   // the repair's chunk scratch, not a whole u32 grid
         ctx->counts_clean_bytes = 0;                   // the recount may leave entries behind
         uint32_t* base = static_cast<uint32_t*>(ctx->bitmap.p);
         for (uint32_t first = 0; first < n; first += chunk) {
@@ -651,6 +688,7 @@ int vkhr_b200_create(int device, vkhr_b200_ctx** out) {
         delete ctx;
         return fail(nullptr, VKHR_B200_ERR_CUDA, "cannot create a stream on the device");
     }
+    if (cudaEventCreateWithFlags(&ctx->order_event, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); ctx->order_event = nullptr; }
     if (reserve(ctx, ctx->small, 256) != VKHR_B200_OK) {
         g_create_error = ctx->err;
         cudaStreamDestroy(ctx->stream);
@@ -665,7 +703,7 @@ void vkhr_b200_destroy(vkhr_b200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->counts, &ctx->bitmap, &ctx->small, &ctx->tacc, &ctx->adsm_table, &ctx->adsm_occ, &ctx->st_vertices,
+    DevBuf* bufs[] = {&ctx->counts, &ctx->bitmap, &ctx->brick, &ctx->small, &ctx->tacc, &ctx->adsm_table, &ctx->adsm_occ, &ctx->st_vertices,
                       &ctx->st_indices, &ctx->st_tangents, &ctx->st_dens, &ctx->st_tang_out};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (auto& sl : ctx->slots) {
@@ -674,6 +712,7 @@ void vkhr_b200_destroy(vkhr_b200_ctx* ctx) {
         cudaEvent_t ev[] = {sl.uploaded, sl.computed, sl.downloaded};
         for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e);
     }
+    if (ctx->order_event) cudaEventDestroy(ctx->order_event);
     if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -721,24 +760,6 @@ int vkhr_b200_profile_read_ex(vkhr_b200_ctx* ctx, double* ms_out, uint32_t* span
 
 int vkhr_b200_profile_read(vkhr_b200_ctx* ctx, double ms_out[4], uint32_t spans_out[4]) {
     return vkhr_b200_profile_read_ex(ctx, ms_out, spans_out, 4);
-}
-
-int vkhr_b200_selftest_division(vkhr_b200_ctx* ctx, float divisor, uint64_t n_trials, uint64_t seed, uint64_t* mismatches) {
-    RET_IF(bind(ctx));
-    if (!mismatches || !(divisor > 0.0f) || !std::isfinite(divisor))
-        return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "divisor must be finite and > 0");
-    unsigned long long* d_bad = reinterpret_cast<unsigned long long*>(static_cast<uint32_t*>(ctx->small.p) + 32);
-    CU_CHECK(ctx, cudaMemsetAsync(d_bad, 0, 8, ctx->stream));
-    const float y = (divisor >= 9.094947e-13f && divisor <= 1.0995116e12f) ? 1.0f / divisor : 0.0f;
-    const unsigned blocks = ctx->sm_count * 16, threads = 256;
-    const uint64_t per = (n_trials + (uint64_t)blocks * threads - 1) / ((uint64_t)blocks * threads);
-    k_selftest_division<<<blocks, threads, 0, ctx->stream>>>(divisor, y, seed, (uint32_t)per, d_bad);
-    ctx->launches++;
-    unsigned long long bad = 0;
-    CU_CHECK(ctx, cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    *mismatches = bad;
-    return VKHR_B200_OK;
 }
 
 // ---- device-pointer API -----------------------------------------------------
@@ -970,6 +991,7 @@ int vkhr_b200_voxelize_segments(vkhr_b200_ctx* ctx, const float* vertices, uint3
                                 uint32_t W, uint32_t H, uint32_t D, uint32_t flags,
                                 uint8_t* densities_out, int8_t* tangents_out) {
     RET_IF(bind(ctx));
+    (void)pick(ctx, nullptr);                                   // the context's own stream, ordered behind the previous call
     if (!densities_out || (n_vertices && !vertices)) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null vertices or densities");
     GridParams g;
     RET_IF(make_grid(ctx, aabb_origin, aabb_size, W, H, D, flags, g));
@@ -1003,6 +1025,7 @@ int vkhr_b200_voxelize_vertices(vkhr_b200_ctx* ctx, const float* vertices, uint3
                                 uint32_t W, uint32_t H, uint32_t D, uint32_t flags,
                                 uint8_t* densities_out, int8_t* tangents_out) {
     RET_IF(bind(ctx));
+    (void)pick(ctx, nullptr);                                   // the context's own stream, ordered behind the previous call
     if (!densities_out || (n_vertices && !vertices)) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null vertices or densities");
     if (tangents_out && !tangents_in)
         return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "voxelize_vertices needs tangents_in to produce tangents_out");
@@ -1031,6 +1054,7 @@ int vkhr_b200_voxelize_vertices(vkhr_b200_ctx* ctx, const float* vertices, uint3
 
 int vkhr_b200_normalize(vkhr_b200_ctx* ctx, uint8_t* densities, uint64_t n_voxels) {
     RET_IF(bind(ctx));
+    (void)pick(ctx, nullptr);                                   // the context's own stream, ordered behind the previous call
     if (!densities) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null densities");
     if (n_voxels == 0) return VKHR_B200_OK;
     RET_IF(stage_in(ctx, ctx->st_dens, densities, n_voxels));
@@ -1043,6 +1067,7 @@ int vkhr_b200_normalize(vkhr_b200_ctx* ctx, uint8_t* densities, uint64_t n_voxel
 int vkhr_b200_downsample(vkhr_b200_ctx* ctx, const uint8_t* densities, uint32_t W, uint32_t H, uint32_t D,
                          int filter, uint8_t* out) {
     RET_IF(bind(ctx));
+    (void)pick(ctx, nullptr);                                   // the context's own stream, ordered behind the previous call
     if (!densities || !out) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null pointer");
     const size_t n_in = (size_t)W * H * D, n_out = (size_t)(W / 2) * (H / 2) * (D / 2);
     if (n_out == 0) return VKHR_B200_OK;
@@ -1057,6 +1082,7 @@ int vkhr_b200_downsample(vkhr_b200_ctx* ctx, const uint8_t* densities, uint32_t 
 
 int vkhr_b200_generate_bounding_box(vkhr_b200_ctx* ctx, const float* vertices, uint32_t n_vertices, float aabb_out[6]) {
     RET_IF(bind(ctx));
+    (void)pick(ctx, nullptr);                                   // the context's own stream, ordered behind the previous call
     if (!aabb_out || (n_vertices && !vertices)) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null pointer");
     RET_IF(stage_in(ctx, ctx->st_vertices, vertices, (size_t)n_vertices * 12));
     float* d_out = reinterpret_cast<float*>(static_cast<uint32_t*>(ctx->small.p) + 16);
@@ -1070,6 +1096,7 @@ int vkhr_b200_generate_bounding_box(vkhr_b200_ctx* ctx, const float* vertices, u
 int vkhr_b200_voxelize_segments_batch(vkhr_b200_ctx* ctx, const vkhr_b200_host_instance* instances, uint32_t n,
                                       uint32_t W, uint32_t H, uint32_t D, uint32_t flags) {
     RET_IF(bind(ctx));
+    (void)pick(ctx, nullptr);                                   // the context's own stream, ordered behind the previous call
     if (n == 0) return VKHR_B200_OK;
     if (!instances) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null instance array");
     // validate everything and size the slots before anything is enqueued
@@ -1173,17 +1200,26 @@ AxisTaps axis_taps(float r, bool positive) {
 // instantiations of the tiled kernel: [0] row-wise (tap offsets at run time), then the column form for the tap offsets
 // (neg.o0, pos.o0) of a non-integer radius with floor f: (-f-1, f), and of an integer radius r: (-r, r), up to radius 4
 // (the default is 2.5; wider windows need more than 200 registers per thread and stay row-wise), each with tiles 8 and
-// 16 voxels deep
-typedef void (*PfKernel)(const CUtensorMap, const PrefilterArgs);
-struct PfVariant { int no0, po0, tz; PfKernel kernel; };
-#define PF_COL(n, p) {n, p, kPfTZ, k_prefilter_tiled<n, p, kPfTZ>}, {n, p, kPfTZDeep, k_prefilter_tiled<n, p, kPfTZDeep>}
-const PfVariant kPfVariantTable[] = {
-    {kPfRowWise, kPfRowWise, kPfTZ, k_prefilter_tiled<kPfRowWise, kPfRowWise, kPfTZ>},
-    PF_COL(0, 0), PF_COL(-1, 0), PF_COL(-1, 1), PF_COL(-2, 1), PF_COL(-2, 2), PF_COL(-3, 2), PF_COL(-3, 3), PF_COL(-4, 3), PF_COL(-4, 4),
+// 16 voxels deep.  They are compiled in prefilter_variants.cu, one tap-offset pair per object file.
+}  // namespace
+extern "C++" {                                       // (this part of the file sits inside the extern "C" block of the ABI)
+namespace vkhr_b200 {
+int pf_variants_0(PfVariant*); int pf_variants_1(PfVariant*); int pf_variants_2(PfVariant*);
+int pf_variants_3(PfVariant*); int pf_variants_4(PfVariant*); int pf_variants_5(PfVariant*);
+int pf_variants_6(PfVariant*); int pf_variants_7(PfVariant*); int pf_variants_8(PfVariant*);
+}
+}  // extern "C++"
+namespace {
+struct PfTable {
+    PfVariant v[kPfVariantCount];
+    int n = 0;
+    PfTable() {
+        int (*groups[])(PfVariant*) = {pf_variants_0, pf_variants_1, pf_variants_2, pf_variants_3, pf_variants_4,
+                                       pf_variants_5, pf_variants_6, pf_variants_7, pf_variants_8};
+        for (auto g : groups) n += g(v + n);                 // 3 + 8 x 2 = kPfVariantCount entries, [0] = row-wise
+    }
 };
-#undef PF_COL
-constexpr int kPfVariants = (int)(sizeof(kPfVariantTable) / sizeof(kPfVariantTable[0]));
-static_assert(kPfVariants == kPfVariantCount, "the context keeps one shared-memory opt-in per instantiation");
+const PfTable& pf_table() { static const PfTable t; return t; }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1258,12 +1294,12 @@ int vkhr_b200_prefilter_dev(vkhr_b200_ctx* ctx, const uint8_t* d_densities, uint
     int variant = 0;
     if (d_ao && !(P.flags & VKHR_B200_PREFILTER_ROWWISE) && A.neg.o1 == A.neg.o0 + 1 && A.pos.o1 == A.pos.o0 + 1) {
         const bool deep = 2u * (pf_plan(halo, A.g_range, kPfTZDeep).total + 1024u) <= (uint32_t)ctx->smem_per_sm && D > (uint32_t)kPfTZ;
-        for (int v = 1; v < kPfVariants; ++v)
-            if (kPfVariantTable[v].no0 == A.neg.o0 && kPfVariantTable[v].po0 == A.pos.o0 && kPfVariantTable[v].tz == (deep ? kPfTZDeep : kPfTZ))
+        for (int v = 1; v < pf_table().n; ++v)
+            if (pf_table().v[v].no0 == A.neg.o0 && pf_table().v[v].po0 == A.pos.o0 && pf_table().v[v].tz == (deep ? kPfTZDeep : kPfTZ))
                 variant = v;
     }
-    const PfKernel kernel = kPfVariantTable[variant].kernel;
-    const int tz = kPfVariantTable[variant].tz;
+    const PfKernel kernel = pf_table().v[variant].kernel;
+    const int tz = pf_table().v[variant].tz;
     A.tiles_z = (D + tz - 1) / tz;
     CUtensorMap tmap;
     const cuuint64_t gdim[3] = {W, H, D};
@@ -1293,6 +1329,7 @@ int vkhr_b200_prefilter_dev(vkhr_b200_ctx* ctx, const uint8_t* d_densities, uint
 int vkhr_b200_prefilter(vkhr_b200_ctx* ctx, const uint8_t* densities, uint32_t W, uint32_t H, uint32_t D,
                         const vkhr_b200_prefilter_params* params, float* ao_out, float* opacity_out, float* gauss_out) {
     RET_IF(bind(ctx));
+    (void)pick(ctx, nullptr);                                   // the context's own stream, ordered behind the previous call
     if (!densities) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null densities");
     const size_t n = (size_t)W * H * D;
     if (n == 0) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "zero resolution");
@@ -1317,6 +1354,7 @@ int vkhr_b200_prefilter(vkhr_b200_ctx* ctx, const uint8_t* densities, uint32_t W
 int vkhr_b200_voxelize_hair(vkhr_b200_ctx* ctx, const void* hair_bytes, size_t n_bytes, uint32_t W, uint32_t H, uint32_t D,
                             uint32_t flags, uint8_t* densities_out, int8_t* tangents_out, float aabb_out[6]) {
     RET_IF(bind(ctx));
+    (void)pick(ctx, nullptr);                                   // the context's own stream, ordered behind the previous call
     if (!hair_bytes || !densities_out) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null file bytes or densities");
     const unsigned char* f = static_cast<const unsigned char*>(hair_bytes);
     if (n_bytes < 128 || std::memcmp(f, "HAIR", 4) != 0) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "not a .hair file (signature)");
@@ -1472,6 +1510,7 @@ int vkhr_b200_adsm_dev(vkhr_b200_ctx* ctx, const uint8_t* d_densities, uint32_t 
 int vkhr_b200_adsm(vkhr_b200_ctx* ctx, const uint8_t* densities, uint32_t W, uint32_t H, uint32_t D,
                    const float origin[3], const float size[3], const vkhr_b200_adsm_params* P, float* out) {
     RET_IF(bind(ctx));
+    (void)pick(ctx, nullptr);                                   // the context's own stream, ordered behind the previous call
     if (!densities || !out) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null argument");
     const size_t n = (size_t)W * H * D;
     if (n == 0) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "zero resolution");
@@ -1481,30 +1520,6 @@ int vkhr_b200_adsm(vkhr_b200_ctx* ctx, const uint8_t* densities, uint32_t W, uin
                               static_cast<float*>(ctx->st_tang_out.p), ctx->stream));
     CU_CHECK(ctx, cudaMemcpyAsync(out, ctx->st_tang_out.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    return VKHR_B200_OK;
-}
-
-// ---- measurement only: per-CTA trace of the walk kernel ------------------------------
-int vkhr_b200_debug_trace(vkhr_b200_ctx* ctx, int enable, unsigned long long* host_out, uint32_t max_records, uint32_t* n_records) {
-    RET_IF(bind(ctx));
-    static unsigned long long* d_buf = nullptr;
-    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    CU_CHECK(ctx, cudaDeviceSynchronize());
-    if (enable) {
-        if (!d_buf) CU_CHECK(ctx, cudaMalloc(&d_buf, (size_t)(1u << 20) * 32));
-        unsigned int zero = 0;
-        CU_CHECK(ctx, cudaMemcpyToSymbol(g_cta_trace_count, &zero, 4));
-        CU_CHECK(ctx, cudaMemcpyToSymbol(g_cta_trace, &d_buf, 8));
-        return VKHR_B200_OK;
-    }
-    unsigned long long* null = nullptr;
-    unsigned int n = 0;
-    CU_CHECK(ctx, cudaMemcpyToSymbol(g_cta_trace, &null, 8));
-    CU_CHECK(ctx, cudaMemcpyFromSymbol(&n, g_cta_trace_count, 4));
-    if (n > max_records) n = max_records;
-    if (n > (1u << 20)) n = 1u << 20;
-    if (host_out && n && d_buf) CU_CHECK(ctx, cudaMemcpy(host_out, d_buf, (size_t)n * 32, cudaMemcpyDeviceToHost));
-    if (n_records) *n_records = n;
     return VKHR_B200_OK;
 }
 

@@ -211,6 +211,22 @@ __device__ __forceinline__ bool div_fast_ok(float a) {
     const float aa = fabsf(a);
     return (aa <= 1.1529215e18f) && (aa >= 8.6736174e-19f || aa == 0.0f);
 }
+// The same test for three numerators at once, in nine instructions instead of twenty-odd:
+//   lower bound  w = 2 * bits - 1 drops the sign and sends +-0 to 0xFFFFFFFF, so min(w) >= 2 * bits(2^-60) - 1 says
+//                "every numerator is zero or at least 2^-60" (NaN and infinities pass this half);
+//   upper bound  max(|a|) <= 2^60 with the single-instruction maximum, which ignores a NaN operand -- a NaN
+//                numerator therefore takes the FMA sequence, which returns NaN like the division does, and every NaN
+//                is dropped alike by the walk (its range vote fails on a NaN position; the index test on a NaN index).
+__device__ __forceinline__ bool div_fast_ok3(float a, float b, float c) {
+    const uint32_t wa = 2u * __float_as_uint(a) - 1u, wb = 2u * __float_as_uint(b) - 1u, wc = 2u * __float_as_uint(c) - 1u;
+    const float hi = fmaxf(fmaxf(fabsf(a), fabsf(b)), fabsf(c));
+    return min(min(wa, wb), wc) >= 2u * 0x21800000u - 1u && hi <= 1.1529215e18f;
+}
+// The lower half alone, for numerators whose magnitude is already known to be below 2^60.
+__device__ __forceinline__ bool div_fast_ok3_lower(float a, float b, float c) {
+    const uint32_t wa = 2u * __float_as_uint(a) - 1u, wb = 2u * __float_as_uint(b) - 1u, wc = 2u * __float_as_uint(c) - 1u;
+    return min(min(wa, wb), wc) >= 2u * 0x21800000u - 1u;
+}
 // The Markstein sequence of div_exact without its guard.
 __device__ __forceinline__ float div_fast(float a, float d, float y) {
     const float q0 = __fmul_rn(a, y);
@@ -219,13 +235,21 @@ __device__ __forceinline__ float div_fast(float a, float d, float y) {
     const float r1 = __fmaf_rn(-q1, d, a);
     return __fmaf_rn(r1, y, q1);
 }
+// RN(1 / s) for a normal s well inside the exponent range (the walk calls it for steps in [2^-40, 2^24)): the
+// hardware approximation and one Newton step -- the in-range path of __frcp_rn without its range test and branch.
+// harness/selftest.cu compares it with __frcp_rn for EVERY float of that interval.
+__device__ __forceinline__ float rcp_steps(float s) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s));
+    const float e = __fmaf_rn(s, r, -1.0f);
+    return __fmaf_rn(r, -e, r);
+}
 
 // (v - origin) / voxel_size for one vertex per lane (hair_style.cc:274, :312-313).
 __device__ __forceinline__ void to_voxel_space_warp(const GridParams& g, float wx, float wy, float wz,
                                                     float& px, float& py, float& pz) {
     const float ax = __fsub_rn(wx, g.ox), ay = __fsub_rn(wy, g.oy), az = __fsub_rn(wz, g.oz);
-    const bool ok = div_fast_ok(ax) && div_fast_ok(ay) && div_fast_ok(az);
-    if (g.fast_div && __all_sync(kFullWarp, ok)) {
+    if (g.fast_div && __all_sync(kFullWarp, div_fast_ok3(ax, ay, az))) {
         px = div_fast(ax, g.vsx, g.rvx);
         py = div_fast(ay, g.vsy, g.rvy);
         pz = div_fast(az, g.vsz, g.rvz);
@@ -296,14 +320,15 @@ __device__ __forceinline__ void walk_voxel_space_warp(const GridParams& g, bool 
     // fast when the root is finite (then every later position is finite too: |root| + 2^24 |dir|, so
     // glm::min == fminf) and the three divisions by `steps` are inside the FMA division's range
     // (EXACT == 2 needs the bound on EVERY end point the warp holds, idle lanes included: lane t's tip is lane
-    // t+1's root in the uniform kernel; CHECK_TIP adds the tip for kernels whose tips are not another lane's root)
+    // t+1's root in the uniform kernel; CHECK_TIP adds the tip for kernels whose tips are not another lane's root).
+    // |direction| <= steps < 2^24, so only the lower bound of the numerators is left to test.
     bool bounded = __fadd_rn(__fadd_rn(fabsf(rx), fabsf(ry)), fabsf(rz)) < g.pos_limit;
     if (CHECK_TIP && EXACT >= 2) bounded = bounded && (__fadd_rn(__fadd_rn(fabsf(tx), fabsf(ty)), fabsf(tz)) < g.pos_limit);
     const bool fast = (EXACT >= 2 || go ? bounded : true) &&
-                      (!go || ((steps >= 9.094947e-13f) && div_fast_ok(dx) && div_fast_ok(dy) && div_fast_ok(dz)));
+                      (!go || ((steps >= 9.094947e-13f) && div_fast_ok3_lower(dx, dy, dz)));
     if (__all_sync(kFullWarp, fast)) {
         if (go) {
-            const float y = __frcp_rn(steps);                                 // RN(1/steps)
+            const float y = rcp_steps(steps);                                 // RN(1/steps)
             dx = div_fast(dx, steps, y);
             dy = div_fast(dy, steps, y);
             dz = div_fast(dz, steps, y);
@@ -313,9 +338,11 @@ __device__ __forceinline__ void walk_voxel_space_warp(const GridParams& g, bool 
                     const int ix = min(__float2int_rd(rx), (int)g.W - 1);
                     const int iy = min(__float2int_rd(ry), (int)g.H - 1);
                     const int iz = min(__float2int_rd(rz), (int)g.D - 1);
-                    const uint32_t lin = (uint32_t)((iz * (int)g.H + iy) * (int)g.W + ix);   // the reference's index, as EXACT == 2
-                    if ((ix | iy | iz) >= 0) sink.template put_brick<decltype(slot)::value>(lin, brick_word(g, ix, iy, iz));   // inside the grid
-                    else if (lin < g.n_voxels) sink.template put<decltype(slot)::value>(lin);   // a negative coordinate that still indexes a voxel
+                    if ((ix | iy | iz) >= 0) sink.template put_xyz<decltype(slot)::value>(ix, iy, iz);   // inside the grid
+                    else {                                                   // a negative coordinate that still indexes a voxel
+                        const uint32_t lin = (uint32_t)((iz * (int)g.H + iy) * (int)g.W + ix);   // the reference's index, as EXACT == 2
+                        if (lin < g.n_voxels) sink.template put<decltype(slot)::value>(lin);
+                    }
                 } else if constexpr (EXACT == 4) {
                     uint32_t idx;
                     if (sample_index<0>(g, rx, ry, rz, idx)) sink.template put_linear<decltype(slot)::value>(idx);

@@ -78,12 +78,6 @@ class Voxelizer:
         names = ("clear", "walk", "finish", "normalize", "prefilter")
         return {k: {"ms": ms[i], "spans": int(n[i])} for i, k in enumerate(names)}
 
-    def selftest_division(self, divisor: float, n_trials: int = 1 << 26, seed: int = 1) -> int:
-        """Mismatches between the kernels' fast exact division and the IEEE division (must be 0)."""
-        bad = C.c_uint64(0)
-        capi.check(self._h, lib.vkhr_b200_selftest_division(self._h, float(divisor), int(n_trials), int(seed), C.byref(bad)))
-        return int(bad.value)
-
     def synchronize(self) -> None:
         capi.check(self._h, lib.vkhr_b200_synchronize(self._h))
 
