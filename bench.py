@@ -54,7 +54,8 @@ def parse_args():
     p.add_argument("--instances", type=int, default=64, help="crowd instances per GPU")
     p.add_argument("--res", type=int, default=256)
     p.add_argument("--seg-len", type=float, default=0.5, help="synthetic segment length (0.5: ~2 samples/segment at 256^3)")
-    p.add_argument("--strategy", default="auto", choices=["auto", "packed8", "count32", "brick8"])
+    p.add_argument("--strategy", default="auto", choices=["auto", "packed8", "count32", "brick8", "brick8-split"])
+    p.add_argument("--ring-mib", type=int, default=0, help="BRICK8 scratch ring of the frame kernel in MiB (0 = library default)")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-others", action="store_true", help="skip the short device-resident timings of the other BASELINE configs")
@@ -268,7 +269,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     W = args.res
     nvox = W * W * W
     I = args.instances
-    flags = {"auto": 0, "packed8": capi.STRATEGY_PACKED8, "count32": capi.STRATEGY_COUNT32, "brick8": capi.STRATEGY_BRICK8}[args.strategy]
+    flags = {"auto": 0, "packed8": capi.STRATEGY_PACKED8, "count32": capi.STRATEGY_COUNT32, "brick8": capi.STRATEGY_BRICK8,
+             "brick8-split": capi.STRATEGY_BRICK8 | capi.BRICK8_SPLIT}[args.strategy]
+    if args.ring_mib:
+        vox.set_scratch_ring_bytes(args.ring_mib << 20)
 
     # ---- inputs: I instances per rank, pinned on the host, resident on the device -------------
     v0, n_strands, segs, lo0, size0 = make_instance(0x5EED + rank * I, args.seg_len)

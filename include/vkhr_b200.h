@@ -86,7 +86,11 @@ enum {
      *          and either at most 2^24 voxels or W and H powers of two (above 2^24 voxels the reference's fp32
      *          index rounds, and the brick is taken from the bit fields of the rounded index); anything else
      *          falls back to PACKED8.  The default picks it from about one segment per 100 voxels upwards. */
-    VKHR_B200_STRATEGY_BRICK8 = 1u << 10
+    VKHR_B200_STRATEGY_BRICK8 = 1u << 10,
+    /* BRICK8 normally runs as ONE persistent launch per batch (walk and copy-out of consecutive instances side by side,
+     * through a ring of scratch volumes that stays in L2).  This flag runs it as the separate kernels of round 1 instead
+     * (clear, walk, copy-out, verdict): the cross-check of the frame kernel in the tests, and the A/B timing. */
+    VKHR_B200_BRICK8_SPLIT = 1u << 11
 };
 
 /* 2x2x2 reduction functors for vkhr_b200_downsample (Volume::downsample takes
@@ -108,6 +112,11 @@ VKHR_B200_API uint64_t vkhr_b200_launch_count(const vkhr_b200_ctx* ctx);
 /* Strategy the last voxelisation of this context ran with: VKHR_B200_STRATEGY_COUNT32 / _PACKED8 / _BRICK8
  * (0 before the first call).  Introspection for tests and benchmarks; no reference counterpart. */
 VKHR_B200_API uint32_t vkhr_b200_last_strategy(const vkhr_b200_ctx* ctx);
+
+/* Bytes of BRICK8 scratch the frame kernel keeps in flight: a ring of floor(bytes / (W*H*D)) volumes (at least one, at
+ * most eight), sized to stay resident in L2 beside the streams of strands and output volumes (default 48 MiB of the
+ * B200's 126 MB).  Tuning knob; results do not depend on it. */
+VKHR_B200_API int vkhr_b200_set_scratch_ring_bytes(vkhr_b200_ctx* ctx, size_t bytes);
 
 /* Per-phase device timing.  While enabled, every voxelize call records CUDA
  * events on its launching stream around its phases; profile_read waits for

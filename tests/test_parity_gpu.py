@@ -12,7 +12,8 @@ import vkhr_b200
 from vkhr_b200 import HairStyle, capi
 from harness import synth
 
-STRATEGIES = [0, capi.STRATEGY_COUNT32, capi.STRATEGY_PACKED8, capi.STRATEGY_BRICK8]   # BRICK8 falls back to PACKED8 where it cannot run
+# BRICK8 falls back to PACKED8 where it cannot run; BRICK8 | BRICK8_SPLIT = the separate kernels of round 1 instead of the frame kernel
+STRATEGIES = [0, capi.STRATEGY_COUNT32, capi.STRATEGY_PACKED8, capi.STRATEGY_BRICK8, capi.STRATEGY_BRICK8 | capi.BRICK8_SPLIT]
 
 
 def _fnv(port, a):
@@ -741,3 +742,73 @@ def test_brick8_crowd_at_256_equals_packed8(vox, port):
     v, n, s, lo, hi = insts[1]["host"]
     want = port.voxelize_segments(v, port.generate_indices(n, s), lo, (hi - lo).astype(np.float32), W, H, D)
     assert np.array_equal(outs[capi.STRATEGY_BRICK8][1].cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("ring_volumes", [1, 2, 3, 8])
+def test_frame_kernel_rings_mixed_batches_and_repeated_frames(port, ring_volumes):
+    """The frame kernel (one persistent launch: walk + copy-out through a ring of scratch volumes): batches larger than
+    the ring, a ring of ONE volume (copy-out directly behind its walk), uniform / indexed / empty / saturating instances in
+    one batch, and several frames in a row (the two control blocks alternate) -- always the oracle's volumes, and
+    always identical to the split form."""
+    import torch
+    dev = torch.device("cuda", 0)
+    W, H, D = 64, 32, 16
+    nv = W * H * D
+    rng = np.random.default_rng(77)
+    with vkhr_b200.Voxelizer(0) as vox:
+        vox.set_scratch_ring_bytes(ring_volumes * nv)
+        insts, wants = [], []
+        for k in range(7):
+            scale = (0.001, 0.02, 0.004, 0.0, 0.06, 0.002, 0.01)[k]
+            if scale == 0.0:                                              # an instance without segments: its volume must come back all zero
+                v, n, s = np.zeros((0, 3), np.float32), 0, 5
+                lo, size = np.zeros(3, np.float32), np.ones(3, np.float32)
+                want = np.zeros(nv, np.uint8)
+                idx = None
+            else:
+                v, n, s = synth.shape("ponytail", seed=300 + k, seg_len=float(rng.uniform(0.5, 2.0)), scale=scale)
+                lo, hi = port.generate_bounding_box(v)
+                size = (hi - lo).astype(np.float32)
+                idx = port.generate_indices(n, s)
+                want = port.voxelize_segments(v, idx, lo, size, W, H, D)
+            ins = {"vertices": torch.from_numpy(v).to(dev).reshape(-1) if v.size else torch.zeros(3, dtype=torch.float32, device=dev)[:0],
+                   "aabb_origin": lo, "aabb_size": size, "out": torch.full((nv,), 5, dtype=torch.uint8, device=dev)}
+            if k % 3 == 2 and idx is not None:                            # explicit index pairs (what the reference's caller passes)
+                ins["indices"] = torch.from_numpy(idx.astype(np.int32)).to(dev)
+            else:
+                ins["segs_per_strand"] = s
+            insts.append(ins)
+            wants.append(want)
+        assert any((w == 255).any() for w in wants), "one instance must saturate (verdict + repair path)"
+        for frame in range(3):
+            for flags in (capi.STRATEGY_BRICK8, capi.STRATEGY_BRICK8 | capi.BRICK8_SPLIT):
+                for ins in insts:
+                    ins["out"].fill_(5)
+                live = [i for i in insts if i["vertices"].numel()] if frame == 1 else insts    # frame 1: a different batch size
+                live_w = [w for i, w in zip(insts, wants) if i["vertices"].numel()] if frame == 1 else wants
+                vox.voxelize_segments_batch_dev(live, W, H, D, flags=flags)
+                torch.cuda.synchronize()
+                assert vox.last_strategy == capi.STRATEGY_BRICK8
+                for k, (ins, want) in enumerate(zip(live, live_w)):
+                    assert np.array_equal(ins["out"].cpu().numpy(), want), (frame, flags, k)
+
+
+def test_frame_kernel_is_one_launch_per_frame(vox, port):
+    """BRICK8 through the frame kernel: the frame kernel + the repair kernel's look at the flags; the split form: clear,
+    walk, copy-out, verdict, repair."""
+    import torch
+    dev = torch.device("cuda", 0)
+    v, n, s = synth.shape("ponytail", seed=9, seg_len=0.5, scale=0.05)
+    lo, hi = port.generate_bounding_box(v)
+    size = (hi - lo).astype(np.float32)
+    vt = torch.from_numpy(v).to(dev).reshape(-1)
+    out = torch.empty(64 ** 3, dtype=torch.uint8, device=dev)
+    vox.voxelize_segments_dev(vt, None, lo, size, 64, 64, 64, segs_per_strand=s, out=out, flags=capi.STRATEGY_BRICK8)   # warm-up: allocations, memsets
+    l0 = vox.launch_count
+    vox.voxelize_segments_dev(vt, None, lo, size, 64, 64, 64, segs_per_strand=s, out=out, flags=capi.STRATEGY_BRICK8)
+    assert vox.launch_count - l0 == 2
+    l0 = vox.launch_count
+    vox.voxelize_segments_dev(vt, None, lo, size, 64, 64, 64, segs_per_strand=s, out=out, flags=capi.STRATEGY_BRICK8 | capi.BRICK8_SPLIT)
+    assert vox.launch_count - l0 == 5
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), port.voxelize_segments(v, port.generate_indices(n, s), lo, size, 64, 64, 64))

@@ -7,12 +7,12 @@ CUDA behind the C ABI of ``include/vkhr_b200.h``.  Importing this package loads
 import fails -- there is no CPU fallback.
 """
 from . import capi                                   # noqa: F401  (loads the native library, or raises)
-from .capi import (DOWNSAMPLE_MAX, DOWNSAMPLE_MEAN, DOWNSAMPLE_MIN, DOWNSAMPLE_SUM, INDEX_EXACT, NORMALIZE,
+from .capi import (BRICK8_SPLIT, DOWNSAMPLE_MAX, DOWNSAMPLE_MEAN, DOWNSAMPLE_MIN, DOWNSAMPLE_SUM, INDEX_EXACT, NORMALIZE,
                    STRATEGY_BRICK8, STRATEGY_COUNT32, STRATEGY_PACKED8, VkhrB200Error)
 from .hair_style import AABB, HairStyle, Volume
 from .voxelizer import Voxelizer, default_voxelizer
 
 __all__ = ["AABB", "HairStyle", "Volume", "Voxelizer", "default_voxelizer", "VkhrB200Error",
-           "INDEX_EXACT", "NORMALIZE", "STRATEGY_BRICK8", "STRATEGY_COUNT32", "STRATEGY_PACKED8",
+           "INDEX_EXACT", "NORMALIZE", "BRICK8_SPLIT", "STRATEGY_BRICK8", "STRATEGY_COUNT32", "STRATEGY_PACKED8",
            "DOWNSAMPLE_MAX", "DOWNSAMPLE_MEAN", "DOWNSAMPLE_SUM", "DOWNSAMPLE_MIN"]
 __version__ = "0.1.0"

@@ -29,6 +29,7 @@ NORMALIZE = 1 << 1
 STRATEGY_COUNT32 = 1 << 8
 STRATEGY_PACKED8 = 1 << 9
 STRATEGY_BRICK8 = 1 << 10
+BRICK8_SPLIT = 1 << 11
 
 DOWNSAMPLE_MAX, DOWNSAMPLE_MEAN, DOWNSAMPLE_SUM, DOWNSAMPLE_MIN = 0, 1, 2, 3
 
@@ -114,6 +115,7 @@ _PROTOTYPES = {
     "vkhr_b200_synchronize": (_int, [c_ctx]),
     "vkhr_b200_launch_count": (_u64, [c_ctx]),
     "vkhr_b200_last_strategy": (C.c_uint32, [c_ctx]),
+    "vkhr_b200_set_scratch_ring_bytes": (_int, [c_ctx, _sz]),
     "vkhr_b200_profile_enable": (_int, [c_ctx, _int]),
     "vkhr_b200_profile_read": (_int, [c_ctx, C.c_double * 4, C.c_uint32 * 4]),
     "vkhr_b200_voxelize_segments": (_int, [c_ctx, _P, _u32, _P, _u64, _u32, _P, _vec3, _vec3, _u32, _u32, _u32, _u32, _P, _P]),

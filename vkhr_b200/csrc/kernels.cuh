@@ -252,20 +252,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 
 template <class T> __device__ __forceinline__ T* pin(T* p) { asm volatile("" : "+l"(p)); return p; }
 
-// The walk of CTA `bx` of instance I (uniform strands).
-template <int MODE, int EXACT>
-__device__ __forceinline__ void walk_uniform_cta(const InstanceDev& I, uint32_t bx, uint32_t inst_id,
-                                                 float (*s_stage)[kStageFloats], unsigned long long* s_bar) {
-    if (bx >= I.n_tiles || I.kind != WK_UNIFORM) return;          // n_tiles counts CTAs
+// The walk of one warp's range of CTA-item `bx` of instance I (uniform strands): 8 tiles of 31 segments.
+// `bar` / `parity`: the warp's own mbarrier (initialised once per kernel, count 1) and the phase the next bulk copy
+// completes; the sink is the caller's (it calls finish()).  All 32 lanes call this together.
+template <int EXACT, class Sink>
+__device__ __forceinline__ void walk_uniform_warp(const InstanceDev& I, uint32_t bx, float* stage, uint32_t bar, uint32_t& parity, Sink& sink) {
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const GridParams g = pin(I.grid);                              // registers, not indexed constant loads
     const uint32_t n_vertices = pin(I.n_vertices);
     const uint32_t n_floats = 3u * n_vertices;
     const uint32_t n_warp_tiles = (n_vertices + kTileStride - 1u) / kTileStride;
     const float* __restrict__ verts = I.vertices;
-    float* stage = s_stage[warp];
-    auto sink = SinkOf<MODE>::make(I);
-    sink.words_pin();
 
     const uint32_t range = bx * kWarpsPerBlock + warp;     // this warp's range of kTilesPerWarp tiles
     const uint32_t tile0 = range * kTilesPerWarp;
@@ -281,17 +278,16 @@ __device__ __forceinline__ void walk_uniform_cta(const InstanceDev& I, uint32_t 
         uint32_t bulk = 0;                                          // floats that arrive by bulk copy
         if ((reinterpret_cast<uintptr_t>(verts) & 15u) == 0u)
             bulk = min(kBulkBytes, ((n_floats - start) * 4u) & ~15u) / 4u;
-        const uint32_t bar = smem_u32(&s_bar[warp]);
-        if (bulk) {
-            if (lane == 0) mbar_init(bar, 1);
-            __syncwarp();
-            if (lane == 0) bulk_load(smem_u32(stage), verts + start, bulk * 4u, bar);
+        if (bulk && lane == 0) {
+            // (a persistent kernel reuses the slot: earlier generic-proxy accesses are ordered before the async-proxy write)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            bulk_load(smem_u32(stage), verts + start, bulk * 4u, bar);
         }
         for (uint32_t j = bulk + lane; j < need; j += 32u) stage[j] = __ldg(verts + start + j);
         // floats past the end of the vertex buffer (last warp of an instance only) are never walked, but their
         // lanes take part in the warp's range vote: give them a harmless value instead of stale shared memory
         for (uint32_t j = need + lane; j < kNeedFloats; j += 32u) stage[j] = g.ox;
-        if (bulk) mbar_wait(bar, 0);
+        if (bulk) { mbar_wait(bar, parity); parity ^= 1u; }
         __syncwarp();
     }
 
@@ -316,45 +312,30 @@ __device__ __forceinline__ void walk_uniform_cta(const InstanceDev& I, uint32_t 
     const bool seg_lane = pin((uint32_t)(lane < kTileStride)) != 0u;   // lane 31 only supplies the tip of lane 30
 
     // ---- software-pipelined tile loop ------------------------------------------------------------------
-    // Shared-memory loads and shuffles share the SM's memory-instruction queue with the reds; behind a burst
-    // of reds each round trip takes as long as the queue is deep.  So nothing in a tile's walk waits for a
-    // round trip issued in the same iteration: the raw floats of tile k+2 and the transformed + shuffled end
-    // points of tile k+1 are requested BEFORE tile k is walked.  The loop body is written out twice with the two
-    // end-point sets swapping roles, so no register moves carry one iteration's "next" into the other's "current".
-    struct Ends { float px, py, pz, tx, ty, tz; };
-    float r0, r1, r2;
+    // The raw floats of tile k+1 are requested before tile k is walked and transformed (three exact divisions, then
+    // the shuffle that hands lane t the vertex of lane t+1) right after it: the shared-memory round trip hides
+    // behind the walk, and only three registers of look-ahead stay live across it (keeping the transformed end
+    // points of the next tile live as well cost spills at 48 registers per thread).
+    float r0, r1, r2, px, py, pz, tx, ty, tz;
     auto fetch = [&]() { r0 = lds_f32(saddr); r1 = lds_f32(saddr + 4u); r2 = lds_f32(saddr + 8u); saddr += 12u * kTileStride; };
-    auto transform = [&](Ends& e) {
-        to_voxel_space_warp(g, r0, r1, r2, e.px, e.py, e.pz);
-        e.tx = __shfl_down_sync(kFullWarp, e.px, 1);
-        e.ty = __shfl_down_sync(kFullWarp, e.py, 1);
-        e.tz = __shfl_down_sync(kFullWarp, e.pz, 1);
+    auto transform = [&]() {
+        to_voxel_space_warp(g, r0, r1, r2, px, py, pz);
+        tx = __shfl_down_sync(kFullWarp, px, 1);
+        ty = __shfl_down_sync(kFullWarp, py, 1);
+        tz = __shfl_down_sync(kFullWarp, pz, 1);
     };
-    // one tile: k tiles are left including this one; `cur` holds its end points, `nxt` receives the next tile's
-    auto tile = [&](const Ends& cur, Ends& nxt, uint32_t k) {
-        if (k > 1u) {                                              // warp-uniform
-            transform(nxt);
-            if (k > 2u) fetch();
-        }
+    fetch();
+    transform();
+    for (uint32_t k = n_tiles; k > 0u; --k) {
+        if (k > 1u) fetch();                                       // warp-uniform
         // vertex x starts a segment unless it is the last of its strand
         const bool active = seg_lane && x + 1u < n_vertices && r != vps - 1u;
-        walk_voxel_space_warp<EXACT, false>(g, active, cur.px, cur.py, cur.pz, cur.tx, cur.ty, cur.tz, sink);
+        walk_voxel_space_warp<EXACT, false>(g, active, px, py, pz, tx, ty, tz, sink);
         x += kTileStride;
         r += r_step;
         if (r >= vps) r -= vps;
-    };
-    Ends ea, eb;
-    eb.px = eb.py = eb.pz = eb.tx = eb.ty = eb.tz = 0.0f;
-    fetch();
-    transform(ea);
-    if (n_tiles > 1u) fetch();
-    for (uint32_t k = n_tiles;;) {
-        tile(ea, eb, k);
-        if (--k == 0u) break;
-        tile(eb, ea, k);
-        if (--k == 0u) break;
+        if (k > 1u) transform();
     }
-    sink.finish();
 }
 
 template <int MODE, int EXACT>
@@ -362,19 +343,26 @@ __global__ void __launch_bounds__(kWalkThreads, VKHR_WALK_MIN_CTAS)
 k_walk_uniform(const __grid_constant__ Batch B, uint32_t first) {
     __shared__ __align__(128) float s_stage[kWarpsPerBlock][kStageFloats];
     __shared__ __align__(8) unsigned long long s_bar[kWarpsPerBlock];
-    walk_uniform_cta<MODE, EXACT>(B.inst[first + blockIdx.y], blockIdx.x, first + blockIdx.y, s_stage, s_bar);
+    const InstanceDev& I = B.inst[first + blockIdx.y];
+    if (blockIdx.x >= I.n_tiles || I.kind != WK_UNIFORM) return;          // n_tiles counts CTAs
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t bar = smem_u32(&s_bar[warp]);
+    if ((threadIdx.x & 31u) == 0u) mbar_init(bar, 1);
+    __syncwarp();
+    uint32_t parity = 0;
+    auto sink = SinkOf<MODE>::make(I);
+    sink.words_pin();
+    walk_uniform_warp<EXACT>(I, blockIdx.x, s_stage[warp], bar, parity, sink);
+    sink.finish();
 }
 
 // ---------------------------------------------------------------------------
 // Generic walk: explicit index buffer (arbitrary vertex pairs), one thread per
 // segment, gathered vertex loads.
 // ---------------------------------------------------------------------------
-template <int MODE, int EXACT>
-__global__ void __launch_bounds__(kWalkThreads)
-k_walk_indexed(const __grid_constant__ Batch B, uint32_t first) {
-    const InstanceDev& I = B.inst[first + blockIdx.y];
-    if (blockIdx.x >= I.n_tiles || I.kind != WK_INDEXED) return;
-    const uint64_t s = (uint64_t)blockIdx.x * kWalkThreads + threadIdx.x;
+// Segment `s` of an indexed instance for this lane (all 32 lanes call it together).
+template <int EXACT, class Sink>
+__device__ __forceinline__ void walk_indexed_lane(const InstanceDev& I, uint64_t s, Sink& sink) {
     const bool active = s < I.n_segments;
     const GridParams& g = I.grid;
     float ax = 0.f, ay = 0.f, az = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
@@ -387,12 +375,185 @@ k_walk_indexed(const __grid_constant__ Batch B, uint32_t first) {
             bx = __ldg(b); by = __ldg(b + 1); bz = __ldg(b + 2);
         }
     }
-    auto sink = SinkOf<MODE>::make(I);
     float px, py, pz, tx, ty, tz;
     to_voxel_space_warp(g, ax, ay, az, px, py, pz);
     to_voxel_space_warp(g, bx, by, bz, tx, ty, tz);
     walk_voxel_space_warp<EXACT>(g, active, px, py, pz, tx, ty, tz, sink);
+}
+
+template <int MODE, int EXACT>
+__global__ void __launch_bounds__(kWalkThreads)
+k_walk_indexed(const __grid_constant__ Batch B, uint32_t first) {
+    const InstanceDev& I = B.inst[first + blockIdx.y];
+    if (blockIdx.x >= I.n_tiles || I.kind != WK_INDEXED) return;
+    auto sink = SinkOf<MODE>::make(I);
+    walk_indexed_lane<EXACT>(I, (uint64_t)blockIdx.x * kWalkThreads + threadIdx.x, sink);
     sink.finish();
+}
+
+// ---------------------------------------------------------------------------
+// The frame kernel: BRICK8 walk AND copy-out of a whole batch in ONE persistent launch.
+//
+// Work items are drawn from a ticket counter in a fixed order: for instance p = 0, 1, ... the walk items of p (one
+// CTA-item = 8 warp-ranges of 8 tiles, as a CTA of k_walk_uniform; 2048 segments of an indexed instance), then the
+// copy-out items of instance p - delay (2048 bricks each).  Instance i counts in scratch slot i mod `ring` -- a ring of
+// a few volumes that stays resident in the 126 MB L2, so the walk's reds, the copy-out's reads and the zeros it writes
+// behind itself never travel to HBM; what does is the algorithmic traffic: the strands once, the output volumes once.
+// The copy-out of one instance runs beside the walk of the next on the same SMs: the walk is bound by its instructions
+// (84 % issue-active), the copy-out by memory, and together they fill both.
+//
+// Dependencies are counters in a small control block: a copy item of instance i waits until all walk items of i have
+// reported (walk_done[i]); a walk item of instance i waits until the copy-out of instance i - ring has released the slot
+// (copy_done).  An item only ever waits for items with SMALLER tickets, and a ticket is drawn by a CTA that is already
+// running, so the lowest unfinished ticket never waits: no deadlock, whatever the number of resident CTAs (no
+// cooperative launch needed).  delay < ring keeps that true for the slot reuse.  Waits spin with a bound and trap.
+// The verdict of the fire-and-forget `red` walk (samples added == byte sum, see SinkPacked8Brick) is taken by the CTA
+// that finishes an instance's last copy item.  The control block of the NEXT call is zeroed here (two blocks alternate),
+// so a frame is exactly one launch (+ the repair kernel's look at the flags).
+// ---------------------------------------------------------------------------
+constexpr uint32_t kFrameStatSlots = 32;
+constexpr uint32_t kFrameCopyBricks = 2048;                     // bricks per copy item: 8 per thread
+constexpr uint32_t kFrameIndexedSegs = 2048;                    // segments per walk item of an indexed instance
+struct FrameCtl {
+    uint32_t ticket;
+    uint32_t pad[31];
+    uint32_t walk_done[kMaxBatch];
+    uint32_t copy_done[kMaxBatch];
+    unsigned long long added[kMaxBatch][kFrameStatSlots];       // samples the walk added, slotted
+    unsigned long long bytes[kMaxBatch][kFrameStatSlots];       // byte sums the copy-out read, slotted
+};
+struct FramePlan {
+    uint32_t n;                                                 // instances of this launch
+    uint32_t ring, delay;                                       // scratch slots; copy-out of p - delay follows the walk of p
+    uint32_t total;                                             // items
+    uint32_t copy_items;                                        // per instance (one resolution per batch)
+    uint32_t n_bricks;
+    uint32_t phase_start[kMaxBatch + 2];                        // first ticket of phase p (n + delay phases)
+    uint8_t* ring_base;
+    unsigned long long slot_bytes;
+    FrameCtl* ctl;
+    FrameCtl* ctl_next;
+};
+
+// thread 0 waits until *p >= need (acquire), then the CTA meets at a barrier
+__device__ __forceinline__ void frame_wait_ge(const uint32_t* p, uint32_t need) {
+    if (threadIdx.x == 0) {
+        uint32_t v;
+        for (uint32_t spin = 0;; ++spin) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+            if (v >= need) break;
+            __nanosleep(100);
+            if (spin > (1u << 23)) __trap();                       // a lost dependency must fail, not hang the device
+        }
+    }
+    __syncthreads();
+}
+
+template <int MODE, int EXACT>
+__global__ void __launch_bounds__(kWalkThreads, VKHR_WALK_MIN_CTAS)
+k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
+    __shared__ __align__(128) float s_stage[kWarpsPerBlock][kStageFloats];
+    __shared__ __align__(8) unsigned long long s_bar[kWarpsPerBlock];
+    __shared__ uint32_t s_item[2][4];
+    __shared__ unsigned long long s_sum[kWarpsPerBlock];
+    __shared__ uint32_t s_last;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t bar = smem_u32(&s_bar[warp]);
+    if (lane == 0) mbar_init(bar, 1);
+    uint32_t parity = 0;
+    FrameCtl* const ctl = P.ctl;
+    if (blockIdx.x == gridDim.x - 1) {                             // the next call's control block (nobody uses it during this call)
+        uint4* z = reinterpret_cast<uint4*>(P.ctl_next);
+        for (uint32_t i = threadIdx.x; i < sizeof(FrameCtl) / 16u; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    // thread 0 draws a ticket and resolves it: s_item[slot] = {ticket, phase, item within the phase}
+    auto draw = [&](uint32_t slot) {
+        const uint32_t t = atomicAdd(&ctl->ticket, 1u);
+        uint32_t lo = 0, hi = P.n + P.delay;
+        if (t < P.total)
+            while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (P.phase_start[mid] <= t) lo = mid; else hi = mid; }
+        s_item[slot][0] = t; s_item[slot][1] = lo; s_item[slot][2] = t - P.phase_start[lo];
+    };
+    if (threadIdx.x == 0) draw(0);
+    __syncthreads();
+    for (uint32_t it = 0;; ++it) {
+        // (the broadcasts tell the compiler that the ticket -- and with it the instance and its constants -- is
+        // warp-uniform: they then live in uniform registers and the constant bank, as in k_walk_uniform where the
+        // instance comes from blockIdx)
+        const uint32_t t = __reduce_max_sync(kFullWarp, s_item[it & 1u][0]);      // REDUX writes a uniform register
+        if (t >= P.total) break;                                   // uniform
+        const uint32_t lo = __reduce_max_sync(kFullWarp, s_item[it & 1u][1]), local = __reduce_max_sync(kFullWarp, s_item[it & 1u][2]);
+        if (threadIdx.x == 0) draw((it + 1u) & 1u);                // the next item, drawn behind this one's work
+        const uint32_t wn = lo < P.n ? B.inst[lo].n_tiles : 0u;
+        if (local < wn) {
+            // ---- walk item `local` of instance lo -----------------------------------------------------------
+            const uint32_t i = lo;
+            const InstanceDev& I = B.inst[i];
+            if (i >= P.ring) frame_wait_ge(&ctl->copy_done[i - P.ring], P.copy_items);      // the slot's previous tenant has been copied out
+            auto sink = SinkOf<MODE>::make(I);
+            sink.words = reinterpret_cast<uint32_t*>(P.ring_base + (unsigned long long)(i % P.ring) * P.slot_bytes);
+            sink.words_pin();
+            if (I.kind == WK_UNIFORM) walk_uniform_warp<EXACT>(I, local, s_stage[warp], bar, parity, sink);
+            else
+                for (uint32_t j = 0; j < kFrameIndexedSegs / kWalkThreads; ++j)
+                    walk_indexed_lane<EXACT>(I, ((uint64_t)local * (kFrameIndexedSegs / kWalkThreads) + j) * kWalkThreads + threadIdx.x, sink);
+            const uint32_t added = __reduce_add_sync(kFullWarp, sink.added);
+            if (lane == 0) s_sum[warp] = added;
+            __threadfence();                                       // this thread's reds are performed before the item reports
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned long long sum = 0;
+                for (uint32_t w = 0; w < kWarpsPerBlock; ++w) sum += s_sum[w];
+                if (sum) atomicAdd(&ctl->added[i][t & (kFrameStatSlots - 1u)], sum);
+                __threadfence();
+                atomicAdd(&ctl->walk_done[i], 1u);
+            }
+        } else {
+            // ---- copy-out item of instance lo - delay: brick order -> the x-fastest output volume -------------
+            const uint32_t i = lo - P.delay, c = local - wn;
+            const InstanceDev& I = B.inst[i];
+            frame_wait_ge(&ctl->walk_done[i], I.n_tiles);
+            const uint32_t wrow = I.grid.W >> 2, byn = I.grid.H >> 2;             // words (= bricks) per row, brick rows per slab
+            const uint32_t wslab = wrow * I.grid.H;
+            uint4* __restrict__ src = reinterpret_cast<uint4*>(P.ring_base + (unsigned long long)(i % P.ring) * P.slot_bytes);
+            uint32_t* __restrict__ dst = reinterpret_cast<uint32_t*>(I.densities);
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            uint32_t bytes = 0;                                                   // at most 8 x 8160
+            const uint32_t b_end = min((c + 1u) * kFrameCopyBricks, P.n_bricks);
+            for (uint32_t b = c * kFrameCopyBricks + threadIdx.x; b < b_end; b += kWalkThreads) {
+                const uint4 q0 = __ldcg(src + 2u * b), q1 = __ldcg(src + 2u * b + 1u);   // L2 is where the reds landed; L1 may be stale
+                bytes += __vsadu4(q0.x, 0u) + __vsadu4(q0.y, 0u) + __vsadu4(q0.z, 0u) + __vsadu4(q0.w, 0u) +
+                         __vsadu4(q1.x, 0u) + __vsadu4(q1.y, 0u) + __vsadu4(q1.z, 0u) + __vsadu4(q1.w, 0u);
+                const uint32_t bx = b % wrow, tt = b / wrow, by = tt % byn, bz = tt / byn;
+                uint32_t* o = dst + (size_t)(2u * bz) * wslab + (size_t)(4u * by) * wrow + bx;
+                __stcs(o, q0.x); __stcs(o + wrow, q0.y); __stcs(o + 2u * wrow, q0.z); __stcs(o + 3u * wrow, q0.w);
+                o += wslab;
+                __stcs(o, q1.x); __stcs(o + wrow, q1.y); __stcs(o + 2u * wrow, q1.z); __stcs(o + 3u * wrow, q1.w);
+                if ((q0.x | q0.y | q0.z | q0.w | q1.x | q1.y | q1.z | q1.w) != 0u) { __stcg(src + 2u * b, z); __stcg(src + 2u * b + 1u, z); }
+            }
+            const uint32_t wsum = __reduce_add_sync(kFullWarp, bytes);
+            if (lane == 0) s_sum[warp] = wsum;
+            __threadfence();                                       // the zeros are in place before the slot is released
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned long long sum = 0;
+                for (uint32_t w = 0; w < kWarpsPerBlock; ++w) sum += s_sum[w];
+                if (sum) atomicAdd(&ctl->bytes[i][t & (kFrameStatSlots - 1u)], sum);
+                __threadfence();
+                s_last = (atomicAdd(&ctl->copy_done[i], 1u) == P.copy_items - 1u) ? 1u : 0u;
+            }
+            __syncthreads();
+            if (s_last && warp == 0) {
+                // the instance is complete: samples added != byte sum of the volume means some byte carried (more than
+                // 255 hits in a voxel) -> flag 2, k_repair_packed recounts the instance in u32
+                __threadfence();
+                unsigned long long a = *(volatile unsigned long long*)&ctl->added[i][lane], y = *(volatile unsigned long long*)&ctl->bytes[i][lane];
+                for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(kFullWarp, a, o); y += __shfl_down_sync(kFullWarp, y, o); }
+                if (lane == 0) *I.ovf_flag = (a != y) ? 2u : 0u;
+            }
+        }
+        __syncthreads();                                           // s_item / s_sum / s_last are reused by the next item
+    }
 }
 
 // Vertex splat (voxelize_vertices): one thread per vertex.

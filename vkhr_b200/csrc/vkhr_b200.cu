@@ -147,6 +147,10 @@ struct vkhr_b200_ctx {
     uint32_t last_strategy = 0;   // VKHR_B200_STRATEGY_* of the last run_voxelize
     DevBuf brick;         // BRICK8 scratch volumes (brick order); all zero between calls up to brick_clean_bytes
     size_t brick_clean_bytes = 0;
+    DevBuf frame_ctl;     // two FrameCtl blocks of the frame kernel (they alternate; each call zeroes the next call's)
+    uint64_t frame_calls = 0;
+    int frame_blocks[2] = {0, 0};                 // resident CTAs of k_frame<3,3> / <4,4> (occupancy x SMs)
+    size_t ring_budget = size_t(48) << 20;        // bytes of BRICK8 scratch the frame kernel keeps in flight (L2-resident ring)
     DevBuf small;         // lohi[2] + aabb keys[6] + aabb floats[6]
     DevBuf tacc;          // tangent mode: 16-byte accumulator per voxel
     size_t tacc_clean_bytes = 0;     // leading bytes of `tacc` known to be zero
@@ -337,7 +341,7 @@ struct BatchPlan {
     uint32_t max_tiles[3] = {0, 0, 0};      // per WalkKind: grid.x of that kernel (0 = not needed)
 };
 
-BatchPlan fill_batch(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_mode) {
+BatchPlan fill_batch(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_mode, bool frame = false) {
     BatchPlan plan;
     Batch& B = ctx->batch;
     B.n = n;
@@ -360,7 +364,8 @@ BatchPlan fill_batch(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool verti
             I.n_tiles = (uint32_t)((warp_tiles + per_cta - 1) / per_cta);
         } else {
             const uint64_t items = (kind == WK_INDEXED) ? jobs[k].n_segments : jobs[k].n_vertices;
-            I.n_tiles = (uint32_t)((items + kWalkThreads - 1) / kWalkThreads);
+            const uint64_t per_item = frame ? kFrameIndexedSegs : kWalkThreads;     // the frame kernel's walk items are larger
+            I.n_tiles = (uint32_t)((items + per_item - 1) / per_item);
         }
         I.vps_magic = (uint32_t)((1ull << 32) / (uint64_t)(jobs[k].segs + 1u)) + 1u;
         plan.max_tiles[kind] = std::max(plan.max_tiles[kind], I.n_tiles);
@@ -443,6 +448,82 @@ int launch_repair(vkhr_b200_ctx* ctx, uint32_t* scratch, cudaStream_t s) {
     return VKHR_B200_OK;
 }
 
+// BRICK8 as ONE launch per batch: the frame kernel (kernels.cuh, k_frame) walks and copies out through a ring of
+// L2-resident scratch volumes; then the repair kernel looks at the verdict flags.  `small`: every grid <= 2^24 voxels.
+int run_frame(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool small, cudaStream_t s) {
+    const uint64_t nv = jobs[0].grid.n_voxels;
+    uint32_t ring = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(ctx->ring_budget / nv, 1), 8);
+    ring = std::min(ring, std::min(n, kMaxBatch));
+    const uint32_t delay = ring >= 2u ? 1u : 0u;                   // delay < ring: a walk never waits for a later ticket
+    const size_t need = (size_t)ring * nv;
+    if (need > ctx->brick.cap) ctx->brick_clean_bytes = 0;         // reserve() reallocates: contents undefined
+    RET_IF(reserve(ctx, ctx->brick, need));
+    if (ctx->brick_clean_bytes < need) {
+        PhaseMark mk(ctx, s, PH_CLEAR);
+        CU_CHECK(ctx, cudaMemsetAsync(ctx->brick.p, 0, need, s));
+    }
+    ctx->brick_clean_bytes = 0;                                    // until every launch below has been queued
+    if (!ctx->frame_ctl.p) {
+        RET_IF(reserve(ctx, ctx->frame_ctl, 2 * sizeof(FrameCtl)));
+        CU_CHECK(ctx, cudaMemsetAsync(ctx->frame_ctl.p, 0, 2 * sizeof(FrameCtl), s));
+        ctx->frame_calls = 0;
+    }
+    const size_t bm_words = 4;                                     // no per-word bitmap: the verdict flags whole instances
+    constexpr size_t kHdr = 4;
+    const uint32_t chunk = std::min<uint32_t>(n, kMaxBatch);
+    RET_IF(reserve(ctx, ctx->bitmap, (size_t)chunk * (bm_words + kHdr) * 4));
+    RET_IF(reserve(ctx, ctx->counts, std::min<uint64_t>(nv, kRepairChunk) * 4));   // the repair's chunk scratch
+    ctx->counts_clean_bytes = 0;
+    uint32_t* base = static_cast<uint32_t*>(ctx->bitmap.p);
+    int& blocks = ctx->frame_blocks[small ? 0 : 1];
+    if (blocks == 0) {
+        int per_sm = 0;
+        if (small) CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame<3, 3>, kWalkThreads, 0));
+        else       CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame<4, 4>, kWalkThreads, 0));
+        if (per_sm < 1) return fail(ctx, VKHR_B200_ERR_CUDA, "frame kernel does not fit on an SM");
+        blocks = per_sm * ctx->sm_count;
+    }
+    for (uint32_t first = 0; first < n; first += chunk) {
+        const uint32_t m = std::min(chunk, n - first);
+        fill_batch(ctx, jobs + first, m, false, true);
+        FramePlan P{};
+        P.n = m; P.ring = std::min(ring, m); P.delay = P.ring >= 2u ? delay : 0u;
+        P.n_bricks = (uint32_t)(nv / 32);
+        P.copy_items = (P.n_bricks + kFrameCopyBricks - 1) / kFrameCopyBricks;
+        uint32_t t = 0;
+        for (uint32_t p = 0; p < m + P.delay; ++p) {
+            P.phase_start[p] = t;
+            if (p < m) t += ctx->batch.inst[p].n_tiles;
+            if (p >= P.delay) t += P.copy_items;
+        }
+        P.phase_start[m + P.delay] = t;
+        P.total = t;
+        P.ring_base = static_cast<uint8_t*>(ctx->brick.p);
+        P.slot_bytes = nv;
+        FrameCtl* ctl = static_cast<FrameCtl*>(ctx->frame_ctl.p);
+        P.ctl = ctl + (ctx->frame_calls & 1u);
+        P.ctl_next = ctl + ((ctx->frame_calls + 1u) & 1u);
+        ctx->frame_calls++;
+        for (uint32_t k = 0; k < m; ++k) {
+            ctx->batch.inst[k].ovf_flag = base + (size_t)k * (bm_words + kHdr);
+            ctx->batch.inst[k].ovf_bitmap = base + (size_t)k * (bm_words + kHdr) + kHdr;
+            ctx->batch.inst[k].counts = static_cast<uint32_t*>(ctx->counts.p);
+        }
+        const unsigned grid = (unsigned)std::min<uint32_t>(P.total, (uint32_t)blocks);
+        {
+            PhaseMark mk(ctx, s, PH_WALK);
+            if (small) k_frame<3, 3><<<grid, kWalkThreads, 0, s>>>(ctx->batch, P);
+            else       k_frame<4, 4><<<grid, kWalkThreads, 0, s>>>(ctx->batch, P);
+            ctx->launches++;
+            CU_CHECK(ctx, cudaGetLastError());
+        }
+        PhaseMark mk(ctx, s, PH_FINISH);
+        RET_IF(launch_repair<false>(ctx, static_cast<uint32_t*>(ctx->counts.p), s));
+    }
+    ctx->brick_clean_bytes = need;                                 // every copy-out re-zeroed what its walk touched
+    return VKHR_B200_OK;
+}
+
 // The voxelisation of `n` instances at one resolution into their u8 grids, kMaxBatch at a time.
 int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_mode, uint32_t flags, cudaStream_t s) {
     if (n == 0) return VKHR_B200_OK;
@@ -471,6 +552,22 @@ int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_
     if (brick && !(flags & VKHR_B200_STRATEGY_BRICK8) && total_segments * 100ull < (uint64_t)n * nv) brick = false;
 
     ctx->last_strategy = brick ? VKHR_B200_STRATEGY_BRICK8 : packed ? VKHR_B200_STRATEGY_PACKED8 : VKHR_B200_STRATEGY_COUNT32;
+    if (brick && !(flags & VKHR_B200_BRICK8_SPLIT)) {
+        bool small = true;
+        for (uint32_t k = 0; k < n; ++k) small = small && jobs[k].grid.small_grid;
+        const int rc = run_frame(ctx, jobs, n, small, s);
+        if (rc == VKHR_B200_ERR_OUT_OF_MEMORY && !(flags & VKHR_B200_STRATEGY_BRICK8)) {
+            brick = false;                                             // no room for the scratch ring: count in the output volumes
+            ctx->last_strategy = VKHR_B200_STRATEGY_PACKED8;
+        } else {
+            RET_IF(rc);
+            if (flags & VKHR_B200_NORMALIZE) {
+                PhaseMark mk(ctx, s, PH_NORMALIZE);
+                for (uint32_t k = 0; k < n; ++k) RET_IF(vkhr_b200_normalize_dev(ctx, jobs[k].d_dens, nv, s));
+            }
+            return VKHR_B200_OK;
+        }
+    }
     if (packed) {
         // scratch: per-instance overflow bitmap + flag, one shared u32 recount grid
         // per instance: a header (flag at word [0], the 2 x kStatSlots u64 statistics of BRICK8 from word [4]) + the bitmap
@@ -703,7 +800,7 @@ void vkhr_b200_destroy(vkhr_b200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->counts, &ctx->bitmap, &ctx->brick, &ctx->small, &ctx->tacc, &ctx->adsm_table, &ctx->adsm_occ, &ctx->st_vertices,
+    DevBuf* bufs[] = {&ctx->counts, &ctx->bitmap, &ctx->brick, &ctx->frame_ctl, &ctx->small, &ctx->tacc, &ctx->adsm_table, &ctx->adsm_occ, &ctx->st_vertices,
                       &ctx->st_indices, &ctx->st_tangents, &ctx->st_dens, &ctx->st_tang_out};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (auto& sl : ctx->slots) {
@@ -735,6 +832,13 @@ int vkhr_b200_synchronize(vkhr_b200_ctx* ctx) {
 
 uint64_t vkhr_b200_launch_count(const vkhr_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 uint32_t vkhr_b200_last_strategy(const vkhr_b200_ctx* ctx) { return ctx ? ctx->last_strategy : 0u; }
+
+int vkhr_b200_set_scratch_ring_bytes(vkhr_b200_ctx* ctx, size_t bytes) {
+    RET_IF(bind(ctx));
+    if (bytes == 0) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "ring bytes must be > 0");
+    ctx->ring_budget = bytes;
+    return VKHR_B200_OK;
+}
 
 int vkhr_b200_profile_enable(vkhr_b200_ctx* ctx, int enable) {
     RET_IF(bind(ctx));

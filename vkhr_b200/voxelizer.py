@@ -68,6 +68,10 @@ class Voxelizer:
     def stream(self) -> int:
         return int(lib.vkhr_b200_stream(self._h) or 0)
 
+    def set_scratch_ring_bytes(self, n_bytes: int) -> None:
+        """BRICK8 scratch the frame kernel keeps in flight (an L2-resident ring of volumes); a tuning knob."""
+        capi.check(self._h, lib.vkhr_b200_set_scratch_ring_bytes(self._h, int(n_bytes)))
+
     def profile_enable(self, on: bool = True) -> None:
         capi.check(self._h, lib.vkhr_b200_profile_enable(self._h, int(bool(on))))
 
