@@ -4,22 +4,24 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (default): the multi-character crowd of BASELINE.json configs[3] -- per-frame
-re-voxelisation of ponytail-shaped instances (136,320 strands x 12 segments = 1,635,840 segments
-each, the shape of configs[0]) into one 256^3 u8 density volume per instance.  A "step" is one frame:
-every instance owned by the rank is voxelised once.  Instances are independent objects, so ranks shard
-them with NO data-path collective ("scaling": "weak": `--instances` per GPU, 64 by default, i.e. at
-N=1 exactly the 64-instance / ~104.7 M-segment crowd).  Inputs are synthetic (the reference's .hair
-assets are Git-LFS pointers) and 1.36 GB per rank, far larger than the 126 MB L2, so consecutive
-steps cannot be served from cache.
+Workload: the multi-character crowd of BASELINE.json configs[3] -- per-frame re-voxelisation of 64
+ponytail-shaped instances (136,320 strands x 12 segments = 1,635,840 segments each, the shape of
+configs[0]; ~104.7 M segments per frame) into one 256^3 u8 density volume per instance.  A "step" is one
+frame of the WHOLE crowd.  The 64 instances are independent objects, so N ranks shard them (64 / N each) with
+NO data-path collective, and the crowd stays the same at every N: "scaling": "strong" (this is the
+configuration north_star's 85 % efficiency target is quoted on).  Inputs are synthetic (the reference's
+.hair assets are Git-LFS pointers), 1.36 GB of strands + 1.07 GB of volumes per frame, larger than the L2.
 
-Output: ONE JSON line on rank 0 (see the keys at the bottom).  `value` is device-resident throughput
-(CUDA events, max over ranks); `e2e` goes through the host-pointer C-ABI call with pinned host buffers
-(H2D + kernels + D2H inside the timed region); `roofline` is the walk kernel's algorithmic bytes over
-its event-timed duration; `cpu_baseline` is the unmodified reference CPU voxeliser timed on this box.
+Output: ONE JSON line on rank 0.  `value` is device-resident throughput (CUDA events, max over ranks); `e2e`
+goes through the host-pointer C-ABI call with pinned host buffers (H2D + kernels + D2H inside the timed
+region); `roofline` holds the frame kernel's algorithmic bytes against its event-timed duration;
+`cpu_baseline` is the unmodified reference CPU voxeliser (whole call, all host cores) with its walk-only and
+one-thread figures beside it; `strand_sharded` is BASELINE configs[2] (1 M strands x 32 segments at 512^3)
+sharded by strand range over the N GPUs with an integer combine -- NCCL u32 all-reduce (north_star's form) and
+the fused peer-memory kernel -- each checked byte for byte against the one-GPU volume.
 
-`--impl reference` times the reference's own CPU implementation (oracle/_ref, the unmodified
-hair_style.cc; else the C port) on the same per-instance workload, one instance per step.
+`--impl reference` times the reference's own CPU implementation (oracle/_ref, the unmodified hair_style.cc; else
+the C port) on a bounded sample of the same workload: one instance of the crowd per step, all host cores.
 """
 from __future__ import annotations
 
@@ -34,15 +36,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-import numpy as np
-
 METRIC = "strand segments voxelised per second"
+UNIT = "M seg/s"
+CROWD = 64                     # instances of BASELINE configs[3]
 
 
 def _emit(line: str):          # replaced in main() by a writer that keeps library chatter off stdout
     print(line, flush=True)
-
-UNIT = "M seg/s"
 
 
 def parse_args():
@@ -51,7 +51,7 @@ def parse_args():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--instances", type=int, default=64, help="crowd instances per GPU")
+    p.add_argument("--instances", type=int, default=CROWD, help="crowd instances in total (sharded over the GPUs)")
     p.add_argument("--res", type=int, default=256)
     p.add_argument("--seg-len", type=float, default=0.5, help="synthetic segment length (0.5: ~2 samples/segment at 256^3)")
     p.add_argument("--strategy", default="auto", choices=["auto", "packed8", "count32", "brick8", "brick8-split"])
@@ -59,9 +59,22 @@ def parse_args():
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-others", action="store_true", help="skip the short device-resident timings of the other BASELINE configs")
+    p.add_argument("--no-sharded", action="store_true", help="skip the strand-sharded configs[2] block")
     p.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
-    p.add_argument("--cpu-seconds", type=float, default=12.0)
+    p.add_argument("--cpu-seconds", type=float, default=10.0)
     return p.parse_args()
+
+
+def workload_config(args) -> dict:
+    """The `config` both arms print (identical: the driver compares them)."""
+    W = args.res
+    n_seg = 136_320 * 12
+    return {
+        "workload": f"multi-character crowd (BASELINE configs[3]): {args.instances} ponytail-shaped instances "
+                    f"(136,320 strands x 12 segments = {n_seg} segments each, {args.instances * n_seg} segments per step), "
+                    f"each re-voxelised into its own {W}^3 u8 volume every step",
+        "instances": args.instances, "segments_per_instance": n_seg, "resolution": [W, W, W], "seg_len": args.seg_len,
+    }
 
 
 # --------------------------------------------------------------------------------------
@@ -137,33 +150,153 @@ def ncu_traffic(kernel_key: str):
         return None
 
 
-def make_instance(seed: int, seg_len: float):
+def make_instance(index: int, seg_len: float):
+    """Instance `index` of the crowd (the same strands whatever the number of ranks)."""
+    import numpy as np
     from harness import synth
-    v, n, s = synth.shape("ponytail", seed=seed, seg_len=seg_len)
+    v, n, s = synth.shape("ponytail", seed=0x5EED + index, seg_len=seg_len)
     lo, hi = synth.host_bounding_box(v)
     return v, n, s, lo, (hi - lo).astype(np.float32)
+
+
+def set_omp_threads(n: int):
+    """OpenMP threads of the reference's quantise loop: pinned explicitly, the same in both arms and at every N
+    (torchrun exports OMP_NUM_THREADS=1 to its workers, which used to make the N > 1 reference arm a different run)."""
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(n))
+    except Exception:  # noqa: BLE001
+        pass
+
+
+def cpu_reference_figures(args, v0, n_strands, segs, lo, size, budget_s: float, check_against=None) -> dict:
+    """The reference's CPU voxeliser on this box: the whole call with all cores (the stock behaviour), the same with one
+    OpenMP thread (its quantise loop gets FASTER: SURVEY F12), and the walk alone (C port, density only, one core)."""
+    import numpy as np
+    import oracle
+    W = args.res
+    n_seg = n_strands * segs
+    cores = os.cpu_count() or 1
+    out = {"unit": UNIT, "cores": cores}
+    P = oracle.port()
+    idx = P.generate_indices(n_strands, segs)
+
+    def timed(fn, seconds, min_runs=2):
+        times = []
+        t_end = time.perf_counter() + seconds
+        while time.perf_counter() < t_end or len(times) < min_runs:
+            t0 = time.perf_counter()
+            r = fn()
+            times.append(time.perf_counter() - t0)
+        return sorted(times)[len(times) // 2], len(times), r
+
+    if oracle.ref_available():
+        hs = oracle.ref().create(v0, n_strands, segs)
+        set_omp_threads(cores)
+        med, runs, (d_ref, _, _) = timed(lambda: hs.voxelize("segments", W, W, W), budget_s * 0.5)
+        out.update({"value": n_seg / med / 1e6, "kind": "reference",
+                    "sample": f"instance 0 of the crowd ({n_seg} segments, {W}^3), unmodified reference HairStyle::voxelize_segments "
+                              f"whole call (serial walk + tangent volume + OpenMP quantise on {cores} threads), median of {runs} runs"})
+        set_omp_threads(1)
+        med1, runs1, _ = timed(lambda: hs.voxelize("segments", W, W, W), budget_s * 0.25)
+        out["whole_call_one_omp_thread"] = {"value": n_seg / med1 / 1e6, "unit": UNIT, "runs": runs1}
+        set_omp_threads(cores)
+        if check_against is not None:
+            assert np.array_equal(check_against(), d_ref), "GPU volume differs from the reference's"
+            out["sample"] += "; bit-exact vs GPU: yes"
+    medw, runsw, d_port = timed(lambda: P.voxelize_segments(v0, idx, lo, size, W, W, W), budget_s * 0.25)
+    out["walk_only"] = {"value": n_seg / medw / 1e6, "unit": UNIT, "cores": 1, "kind": "port", "runs": runsw,
+                        "sample": "density-only C restatement of hair_style.cc:296-329 (no tangent volume, no quantise pass)"}
+    if "value" not in out:
+        out.update({"value": out["walk_only"]["value"], "kind": "port", "cores": 1, "sample": out["walk_only"]["sample"]})
+        if check_against is not None:
+            assert np.array_equal(check_against(), d_port), "GPU volume differs from the port's"
+    return out
+
+
+# --------------------------------------------------------------------------------------
+def run_reference(args, rank: int):
+    """The reference's own CPU voxeliser on this box's host cores: one instance of the crowd per step."""
+    if rank != 0:
+        return
+    import oracle
+    v, n, s, lo, size = make_instance(0, args.seg_len)
+    W = args.res
+    cores = os.cpu_count() or 1
+    set_omp_threads(cores)
+    if oracle.ref_available():
+        kind = "reference"
+        hs = oracle.ref().create(v, n, s)          # generate_bounding_box: the same AABB as make_instance
+
+        def step():
+            hs.voxelize("segments", W, W, W)
+        threads = cores
+        sample = (f"unmodified reference HairStyle::voxelize_segments({W}^3) whole call (serial walk + tangent volume + OpenMP "
+                  f"quantise, OMP_NUM_THREADS pinned to {cores}), 1 instance of the crowd ({n * s} segments) per step")
+    else:
+        kind = "port"
+        P = oracle.port()
+        idx = P.generate_indices(n, s)
+
+        def step():
+            P.voxelize_segments(v, idx, lo, size, W, W, W)
+        threads = 1
+        sample = f"C port, density-only walk, 1 instance of the crowd ({n * s} segments) per step"
+    for _ in range(min(args.warmup, 2)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = n * s * args.steps / dt / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 walk -> u8 counts",
+        "data": "synthetic", "config": workload_config(args),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    _emit(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------
+def timed_local(fn, reps):
+    import torch
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        r = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, r
 
 
 def other_configs(vox, dev, args, flags=0):
     """Short device-resident timings (CUDA events, 20 reps after 3 warm-ups) of the other BASELINE.json configs that
     fit one GPU; inputs are rotated over 8 copies (> L2) for the small sets.  Parity for these lives in tests/."""
+    import numpy as np
     import torch
     from vkhr_b200 import capi
     from harness import synth
     out = {}
-    cases = [("configs[0] ponytail 256^3, one instance", "ponytail", 0.5, 256, 8),
-             ("configs[1] Yuksel-straight-shaped 50,000 x 65 at 512^3", "straight", 0.5, 512, 2),
-             ("configs[2] 1M strands x 32 segments at 512^3 (one GPU)", "big", 0.5, 512, 1),
-             ("configs[4] animated ponytail frame at 1024^3 (voxelise only)", "ponytail", 0.5, 1024, 1),
-             ("configs[4] animated ponytail frame at 1024^3 (voxelise + AO/opacity prefilter)", "ponytail", 0.5, 1024, 1)]
-    for name, shape, seg_len, W, copies in cases:
+    cases = [("configs[0] ponytail 256^3, one instance", "ponytail", 256, 8, False),
+             ("configs[1] Yuksel-straight-shaped 50,000 x 65 at 512^3", "straight", 512, 2, False),
+             ("configs[1] Yuksel-curly-shaped 50,000 x 65 at 512^3", "curly", 512, 2, False),
+             ("configs[4] animated ponytail frame at 1024^3 (voxelise only)", "ponytail", 1024, 1, False),
+             ("configs[4] animated ponytail frame at 1024^3 (voxelise + AO/opacity prefilter)", "ponytail", 1024, 1, True)]
+    for name, shape, W, copies, prefilter in cases:
         try:
-            v, n, s = synth.shape(shape, seed=0x5EED, seg_len=seg_len)
+            v, n, s = synth.shape(shape, seed=0x5EED, seg_len=0.5)
             lo, hi = synth.host_bounding_box(v)
             size = (hi - lo).astype(np.float32)
             vt = [torch.from_numpy(v).to(dev).reshape(-1).clone() for _ in range(copies)]
             o = [torch.empty(W ** 3, dtype=torch.uint8, device=dev) for _ in range(copies)]
-            prefilter = "prefilter" in name
             reps = 5 if prefilter else 20
             pf = [torch.empty(W ** 3, dtype=torch.float32, device=dev) for _ in range(2)] if prefilter else None
 
@@ -192,56 +325,92 @@ def other_configs(vox, dev, args, flags=0):
     return out
 
 
-# --------------------------------------------------------------------------------------
-def run_reference(args, rank: int):
-    """The reference's own CPU voxeliser on this box's host cores: one ponytail instance per step."""
-    if rank != 0:
-        return
-    import oracle
-    v, n, s, lo, size = make_instance(0x5EED, args.seg_len)
-    W = args.res
-    cores = os.cpu_count() or 1
-    if oracle.ref_available():
-        kind = "reference"
-        hs = oracle.ref().create(v, n, s)          # generate_bounding_box: the same AABB as make_instance
+def strand_sharded(vox, dev, rank: int, world: int, reps: int = 10) -> dict:
+    """BASELINE configs[2]: 1 M strands x 32 segments (32 M segments) at 512^3, strands sharded by contiguous range over
+    the ranks, partial volumes combined with ONE integer exchange.  Every schedule is asserted byte-identical to the
+    volume rank 0 computes alone from the whole set."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from vkhr_b200 import sharding
+    from harness import synth
+    W = 512
+    n, s = synth.shape_counts("big")
+    first, count = sharding.strand_range(n, world, rank)
+    mine, _, _ = synth.shape("big", seed=0x5EED, seg_len=0.5, first_strand=first, n_strands=count)
+    mine_t = torch.from_numpy(mine).to(dev).reshape(-1)
+    res = {"workload": f"BASELINE configs[2]: {n} strands x {s} segments = {n * s} segments at {W}^3, contiguous strand ranges "
+                       f"over {world} GPU(s), one shared AABB, integer combine",
+           "segments": n * s, "resolution": [W, W, W], "world": world}
 
-        def step():
-            hs.voxelize("segments", W, W, W)
-        threads = int(os.environ.get("OMP_NUM_THREADS", cores))
-        sample = (f"unmodified reference HairStyle::voxelize_segments({W}^3) whole call (serial walk + OpenMP tangent "
-                  f"quantise), 1 ponytail instance ({n * s} segments) per step")
-    else:
-        kind = "port"
-        P = oracle.port()
-        idx = P.generate_indices(n, s)
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, r
 
-        def step():
-            P.voxelize_segments(v, idx, lo, size, W, W, W)
-        threads = 1
-        sample = f"C port, density-only walk, 1 ponytail instance ({n * s} segments) per step"
-    for _ in range(min(args.warmup, 2)):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = time.perf_counter() - t0
-    val = n * s * args.steps / dt / 1e6
-    line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 walk -> u8 counts",
-        "data": "synthetic",
-        "config": {"workload": f"crowd of ponytail-shaped instances (136,320 strands x 12 segments) at {W}^3; "
-                               "one instance per step on the host CPU", "resolution": [W, W, W], "seg_len": args.seg_len},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    _emit(json.dumps(line))
+    if world == 1:
+        lo, hi = vox.generate_bounding_box_dev(mine_t).cpu().numpy().reshape(2, 3)
+        size = (hi - lo).astype(np.float32)
+        ms, _ = timed(lambda: vox.voxelize_segments_dev(mine_t, None, lo, size, W, W, W, segs_per_strand=s))
+        res["one_gpu"] = {"ms": ms, "value": n * s / ms / 1e3, "unit": UNIT}
+        return res
+    sv = sharding.ShardedVoxelizer(vox)
+    bb = vox.generate_bounding_box_dev(mine_t).cpu().numpy()
+    lo, hi = sv.global_bounding_box(bb[:3], bb[3:])
+    size = (hi - lo).astype(np.float32)
+    nv = W ** 3
+    out = torch.empty(sharding.padded_voxels(nv, world), dtype=torch.uint8, device=dev)
+    vols = {}
+    nvlink = {"allreduce": 2 * (world - 1) / world * 4 * nv, "p2p": 2 * (world - 1) / world * nv}
+    for schedule in ("allreduce", "p2p"):
+        try:
+            ms, vol = timed(lambda: sv.voxelize_segments(mine_t, None, s, lo, size, W, W, W,
+                                                         out=None if schedule == "p2p" else out, schedule=schedule))
+            res[schedule] = {"ms": ms, "value": n * s / ms / 1e3, "unit": UNIT,
+                             "nvlink_bytes_per_gpu" + ("_upper_bound_sparse_exchange" if schedule == "p2p" else ""): int(nvlink[schedule])}
+            vols[schedule] = vol[:nv].clone()
+        except Exception as e:  # noqa: BLE001
+            res[schedule] = {"error": str(e)[:300]}
+    # the one-GPU volume of the whole set (rank 0 alone; the others wait), and the comparison
+    ok = True
+    if rank == 0:
+        full, _, _ = synth.shape("big", seed=0x5EED, seg_len=0.5)
+        full_t = torch.from_numpy(full).to(dev).reshape(-1)
+        flo, fhi = vox.generate_bounding_box_dev(full_t).cpu().numpy().reshape(2, 3)
+        res["aabb_equals_whole_set"] = bool(np.array_equal(flo, lo) and np.array_equal(fhi, hi))
+        ms1, ref = timed_local(lambda: vox.voxelize_segments_dev(full_t, None, lo, size, W, W, W, segs_per_strand=s), reps)
+        res["one_gpu"] = {"ms": ms1, "value": n * s / ms1 / 1e3, "unit": UNIT}
+        for name, v in vols.items():
+            same = bool(torch.equal(v, ref))
+            res[name]["byte_identical_to_one_gpu"] = same
+            res[name]["speedup_vs_one_gpu"] = ms1 / res[name]["ms"]
+            ok = ok and same
+        del full_t, ref
+    dist.barrier()
+    torch.cuda.synchronize()
+    assert ok, f"a sharded volume differs from the one-GPU volume: {res}"
+    del out, vols
+    torch.cuda.empty_cache()
+    return res
 
 
 # --------------------------------------------------------------------------------------
 def run_ours(args, rank: int, local_rank: int, world: int):
+    import numpy as np
     import torch
     import torch.distributed as dist
     import vkhr_b200
@@ -268,21 +437,23 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     vox = vkhr_b200.Voxelizer(local_rank)
     W = args.res
     nvox = W * W * W
-    I = args.instances
+    total = args.instances
+    mine = list(range(rank, total, world))                  # this rank's instances of the crowd
+    I = len(mine)
     flags = {"auto": 0, "packed8": capi.STRATEGY_PACKED8, "count32": capi.STRATEGY_COUNT32, "brick8": capi.STRATEGY_BRICK8,
              "brick8-split": capi.STRATEGY_BRICK8 | capi.BRICK8_SPLIT}[args.strategy]
     if args.ring_mib:
         vox.set_scratch_ring_bytes(args.ring_mib << 20)
 
-    # ---- inputs: I instances per rank, pinned on the host, resident on the device -------------
-    v0, n_strands, segs, lo0, size0 = make_instance(0x5EED + rank * I, args.seg_len)
+    # ---- inputs: this rank's instances, pinned on the host, resident on the device -------------
+    v0, n_strands, segs, lo0, size0 = make_instance(mine[0], args.seg_len)
     V = v0.shape[0]
     n_seg = n_strands * segs
     host_v = torch.empty((I, V * 3), dtype=torch.float32).pin_memory()
     host_out = torch.empty((I, nvox), dtype=torch.uint8).pin_memory()
     aabbs = []
-    for k in range(I):
-        v, _, _, lo, size = (v0, n_strands, segs, lo0, size0) if k == 0 else make_instance(0x5EED + rank * I + k, args.seg_len)
+    for k, g in enumerate(mine):
+        v, _, _, lo, size = (v0, n_strands, segs, lo0, size0) if k == 0 else make_instance(g, args.seg_len)
         host_v[k].numpy()[:] = v.reshape(-1)
         aabbs.append((lo, size))
     dev_v = host_v.to(dev)
@@ -308,39 +479,41 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     barrier()
     launches = vox.launch_count - l0
     ms = max_over_ranks(e0.elapsed_time(e1))
-    value = n_seg * I * world * args.steps / (ms * 1e-3) / 1e6
+    step_ms = ms / args.steps
+    value = n_seg * total * args.steps / (ms * 1e-3) / 1e6
 
-    # ---- the same K steps with per-phase CUDA events (for the roofline of the walk kernel) -----
+    # ---- the same K steps with per-phase CUDA events on the launching stream (roofline of the dominant kernel) -----
     vox.profile_enable(True)
     vox.profile_read()
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record()
     for _ in range(args.steps):
         frame()
-    p1.record()
     torch.cuda.synchronize()
     prof = vox.profile_read()
     vox.profile_enable(False)
-    ms_instr = p0.elapsed_time(p1)
-    walk_ms = prof["walk"]["ms"] / max(prof["walk"]["spans"], 1)             # per launch
-    if vox.last_strategy == capi.STRATEGY_BRICK8:
-        # the volume exists only after the copy-out: the pair (walk, copy-out) is what the algorithmic bytes are held against
-        walk_ms = (prof["walk"]["ms"] + prof["finish"]["ms"]) / args.steps      # one walk + one copy-out (+ the repair's look at the flags) per step
+    phases_ms = {k: prof[k]["ms"] / args.steps for k in prof}
+    brick = vox.last_strategy == capi.STRATEGY_BRICK8
+    fused = brick and not (flags & capi.BRICK8_SPLIT)
+    if fused:
+        kernel, kernel_key = "k_frame<3,3> (BRICK8 strand walk + copy-out of the rank's instances, one persistent launch)", f"k_frame@{I}x{W}^3"
+        kernel_ms = phases_ms["walk"]
+    elif brick:
+        kernel, kernel_key = ("k_walk_uniform<3,3> + k_untile_batch (BRICK8 as separate kernels; kernel_ms and traffic are the pair's)",
+                              f"k_walk_uniform<3>+k_untile_batch@{I}x{W}^3")
+        kernel_ms = phases_ms["walk"] + phases_ms["finish"]
+    else:
+        kernel, kernel_key = "k_walk_uniform (strand walk)", f"k_walk_uniform<1>@{I}x{W}^3"
+        kernel_ms = phases_ms["walk"]
     alg_bytes = I * (12 * V + nvox)                                          # 12*V + W*H*D per instance
     peak, peak_src = hbm_peak()
-    achieved = alg_bytes / (walk_ms * 1e-3) / 1e9 if walk_ms > 0 else 0.0
-    phases_ms = {k: prof[k]["ms"] / args.steps for k in prof}
-    step_ms = ms / args.steps
-    strat = {capi.STRATEGY_COUNT32: (0, "count32", "u32 counts"), capi.STRATEGY_PACKED8: (1, "packed8", "packed u8 atomics in the output volume"),
-             capi.STRATEGY_BRICK8: (3, "brick8", "packed u8 atomics in the brick-ordered scratch volume, + k_untile_batch, the copy-out: kernel_ms is the pair")
-             }.get(vox.last_strategy, (1, "packed8", "packed u8 atomics"))
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+    sname = {capi.STRATEGY_COUNT32: "count32", capi.STRATEGY_PACKED8: "packed8", capi.STRATEGY_BRICK8: "brick8"}.get(vox.last_strategy)
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": ncu_traffic(f"k_walk_uniform<{strat[0]}>@{I}x{W}^3"),
-        "kernel": f"k_walk_uniform<{strat[0]}> (strand walk, {strat[2]})", "strategy": strat[1], "kernel_ms_per_launch": walk_ms,
-        "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-        "phase_ms_per_step": phases_ms, "kernel_share_of_step": (phases_ms["walk"] / (ms_instr / args.steps)) if ms_instr else None,
+        "traffic": ncu_traffic(kernel_key), "kernel": kernel, "strategy": sname + ("" if fused or not brick else "-split"),
+        "kernel_ms_per_launch": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+        "phase_ms_per_step": phases_ms, "kernel_share_of_step": kernel_ms / sum(phases_ms.values()) if sum(phases_ms.values()) else None,
         "whole_path_frac": (alg_bytes / (step_ms * 1e-3) / 1e9) / peak,
+        "note": "per-rank figures of rank 0 (its instances of the crowd); event-timed on the launching stream in a separate pass of K steps",
     }
 
     # ---- end to end through the host-pointer C ABI (pinned host buffers) ------------------------
@@ -352,7 +525,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                                        "aabb_size": aabbs[k][1], "out": ho[k]} for k in range(I)])
 
         def frame_e2e():
-            # one call for the crowd: upload of instance k+1, kernels of k and download of k-1 overlap
+            # one call for the rank's instances: upload of instance k+1, kernels of k and download of k-1 overlap
             vox.voxelize_segments_batch(hbatch, W, W, W, flags=flags)
 
         ke = args.e2e_steps or min(args.steps, 5)
@@ -364,50 +537,36 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0)
         barrier()
-        e2e = {"value": n_seg * I * world * ke / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": I * V * 12,
-               "d2h_bytes_per_step": I * nvox, "steps": ke, "ms_per_step": dt / ke * 1e3,
+        e2e = {"value": n_seg * total * ke / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": total * V * 12,
+               "d2h_bytes_per_step": total * nvox, "steps": ke, "ms_per_step": dt / ke * 1e3,
                "api": "vkhr_b200_voxelize_segments_batch (host pointers, pinned; H2D / kernels / D2H of consecutive "
-                      "instances pipelined on three streams)", "host_affinity": numa}
+                      "instances pipelined on three streams), one call per rank per step", "host_affinity": numa}
         # the frame that came back over PCIe must equal the device-resident one
         frame()
         torch.cuda.synchronize()
-        for k in (0, I // 2, I - 1):
+        for k in sorted({0, I // 2, I - 1}):
             assert torch.equal(host_out[k], dev_out[k].cpu()), "e2e result differs from the device-resident result"
     clocks = sampler.stop()
 
     # ---- the reference CPU voxeliser on this box's host cores (rank 0, N == 1 only) --------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        import oracle
-        cores = os.cpu_count() or 1
-        if oracle.ref_available():
-            hs = oracle.ref().create(v0, n_strands, segs)
-            times = []
-            t_end = time.perf_counter() + args.cpu_seconds
-            while time.perf_counter() < t_end or len(times) < 2:
-                t0 = time.perf_counter()
-                d_ref, _, _ = hs.voxelize("segments", W, W, W)
-                times.append(time.perf_counter() - t0)
+        def gpu_volume():
             frame()
             torch.cuda.synchronize()
-            assert np.array_equal(dev_out[0].cpu().numpy(), d_ref), "GPU volume differs from the reference's"
-            med = sorted(times)[len(times) // 2]
-            cpu = {"value": n_seg / med / 1e6, "unit": UNIT, "cores": int(os.environ.get("OMP_NUM_THREADS", cores)),
-                   "kind": "reference",
-                   "sample": f"instance 0 of the crowd ({n_seg} segments, {W}^3), unmodified reference "
-                             f"HairStyle::voxelize_segments whole call, median of {len(times)} runs; bit-exact vs GPU: yes"}
-        else:
-            P = oracle.port()
-            idx = P.generate_indices(n_strands, segs)
-            t0 = time.perf_counter()
-            reps = 0
-            while time.perf_counter() - t0 < args.cpu_seconds:
-                d_ref = P.voxelize_segments(v0, idx, aabbs[0][0], aabbs[0][1], W, W, W)
-                reps += 1
-            dt = time.perf_counter() - t0
-            cpu = {"value": n_seg * reps / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
-                   "sample": f"instance 0 of the crowd ({n_seg} segments, {W}^3), C port density-only walk, {reps} runs"}
+            return dev_out[0].cpu().numpy()
+        cpu = cpu_reference_figures(args, v0, n_strands, segs, aabbs[0][0], aabbs[0][1], args.cpu_seconds, check_against=gpu_volume)
 
+    sharded = None
+    if not args.no_sharded:
+        del batch, dev_out, dev_v
+        torch.cuda.empty_cache()
+        try:
+            sharded = strand_sharded(vox, dev, rank, world)
+        except AssertionError:
+            raise
+        except Exception as e:  # noqa: BLE001
+            sharded = {"error": str(e)[:300]}
     others = None
     if rank == 0 and world == 1 and not args.no_others:
         others = other_configs(vox, dev, args, flags)
@@ -419,34 +578,32 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             sigma = oracle.port().count_samples(v0, idx0, aabbs[0][0], aabbs[0][1], W, W, W) / n_seg
         except Exception:  # noqa: BLE001
             pass
-        if sigma:
-            # secondary bound: one 32-byte atomic request packet per sample; the measured ceiling of
-            # packed atomics with one lane per sector on this part is 220 G/s (profiles/r01_microbench.json)
-            # per SECTOR-request, whatever the number of lanes in it; BRICK8 puts 1 / 0.6 samples into one (ncu, profiles/traffic.json)
-            sps = ncu_traffic(f"atom_sectors_per_sample<{strat[0]}>@{I}x{W}^3") or 1.0
-            g_sectors = sigma * n_seg * I * sps / (walk_ms * 1e-3) / 1e9
-            roofline["atomic"] = {"samples_per_launch": sigma * n_seg * I, "achieved_Gsamples_s": sigma * n_seg * I / (walk_ms * 1e-3) / 1e9,
+        if sigma and brick:
+            # secondary bound: the SM -> L2 request path carries one 32-byte packet per distinct sector of a
+            # `red` warp instruction, 220 G packets/s on this part (profiles/r01_microbench.json); the brick layout puts
+            # 1 / 0.61 samples into one packet (ncu, profiles/traffic.json)
+            sps = ncu_traffic(f"red_sectors_per_sample@{W}^3") or 0.61
+            g_sectors = sigma * n_seg * I * sps / (kernel_ms * 1e-3) / 1e9
+            roofline["atomic"] = {"samples_per_launch": sigma * n_seg * I, "achieved_Gsamples_s": sigma * n_seg * I / (kernel_ms * 1e-3) / 1e9,
                                   "request_sectors_per_sample": sps, "achieved_Gsectors_s": g_sectors,
                                   "peak_Gsectors_s": 220.0, "frac": g_sectors / 220.0,
                                   "peak_source": "tools/microbench.cu on this pool (profiles/r01_microbench.json)"}
+        cfg = workload_config(args)
+        cfg.update({"instances_per_gpu": I, "sharding": "by instance (rank r takes instances r, r + N, ...), no collective",
+                    "samples_per_segment": sigma, "strategy": args.strategy,
+                    "cache": f"inputs {I * V * 12 / 1e6:.0f} MB + outputs {I * nvox / 1e6:.0f} MB per rank per step"
+                             + (", larger than the 126 MB L2; no flush needed" if I * (V * 12 + nvox) > 200e6 else
+                                ": not far above the 126 MB L2 -- part of a rank's input may be served from L2 between steps")})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 walk -> u8 counts", "data": "synthetic",
-            "config": {
-                "workload": f"multi-character crowd (BASELINE configs[3]): {I} ponytail-shaped instances per GPU "
-                            f"(136,320 strands x 12 segments = {n_seg} segments each, {I * n_seg} segments per GPU per "
-                            f"step), each re-voxelised into its own {W}^3 u8 volume; instances sharded across GPUs, "
-                            "no collective",
-                "instances_per_gpu": I, "segments_per_instance": n_seg, "resolution": [W, W, W],
-                "seg_len": args.seg_len, "samples_per_segment": sigma, "strategy": args.strategy,
-                "cache": f"inputs {I * V * 12 / 1e6:.0f} MB + outputs {I * nvox / 1e6:.0f} MB per rank per step, larger than the 126 MB L2; no flush needed",
-            },
+            "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32 walk -> u8 counts", "data": "synthetic", "config": cfg,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "other_configs": others,
+            "strand_sharded": sharded, "other_configs": others,
         }
         _emit(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -473,7 +630,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.instances % max(world, 1):
+        sys.exit(f"--instances {args.instances} is not a multiple of the {world} ranks")
     if args.impl == "reference":
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)       # before libgomp initialises (torchrun exports 1)
         run_reference(args, rank)
         return
     if world == 1 and args.gpus > 1:
@@ -482,6 +642,8 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29531"), __file__] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
+    # the host-side generator is OpenMP: give each rank its share of the cores (torchrun exports OMP_NUM_THREADS=1)
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(world, 1)))
     # Libraries (NCCL prints its version banner) may write to stdout; the contract is ONE JSON line there.  Everything
     # but the final line goes to stderr: fd 1 is pointed at fd 2 until the result is printed.
     sys.stdout.flush()

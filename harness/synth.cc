@@ -31,16 +31,17 @@ extern "C" {
 //   step k    p += seg_len * normalize(dir + curl * (u3 - 0.5) + gravity * (0,-1,0) + gather * toward_axis)
 // `gather` pulls strands toward the vertical line through the root box centre
 // (a ponytail-like band); 0 disables it.
+// `first_strand`: strand ids first_strand .. first_strand + n_strands - 1 of the set (a rank generates only its shard).
 int vkhr_harness_synth_strands(uint32_t n_strands, uint32_t segs_per_strand, uint64_t seed,
                             const float root_min[3], const float root_max[3],
-                            float seg_len, float curl, float gravity, float gather, float* xyz_out) {
+                            float seg_len, float curl, float gravity, float gather, uint64_t first_strand, float* xyz_out) {
     if (!xyz_out || !root_min || !root_max || segs_per_strand == 0) return -1;
     const double cx = 0.5 * (double(root_min[0]) + root_max[0]);
     const double cz = 0.5 * (double(root_min[2]) + root_max[2]);
     const size_t vps = size_t(segs_per_strand) + 1;
 #pragma omp parallel for schedule(static)
     for (long long s = 0; s < (long long)n_strands; ++s) {
-        Rng rng(seed ^ (0x9E3779B97F4A7C15ull * (uint64_t(s) + 1)));
+        Rng rng(seed ^ (0x9E3779B97F4A7C15ull * (uint64_t(s) + first_strand + 1)));
         for (int w = 0; w < 4; ++w) rng.next();       // decorrelate neighbouring seeds
         double p[3], d[3];
         for (int c = 0; c < 3; ++c)

@@ -45,9 +45,57 @@ def stats(d):
             "saturated": int(np.count_nonzero(d == 255)), "max": int(d.max())}
 
 
+SWAY_FRAMES = (0, 59, 119)          # config 5: first, middle and last frame of the 120-frame sequence
+
+
+def at_size(R):
+    """BASELINE.json configs 1, 2, 4 at their FULL sizes (fingerprints only; run with --sizes, merged into golden.json):
+    Yuksel-shaped straight / curly 50,000 x 65 at 512^3, 1 M strands x 32 at 512^3, and swayed ponytail frames in the
+    union AABB of the 120-frame sequence at 1024^3 (the reference needs ~18 GB and ~2 minutes per frame there)."""
+    fp = {}
+
+    def one(name, vb, nb, sb, res, extra, aabb=None):
+        h = R.create(vb, nb, sb) if aabb is None else R.create(vb, nb, sb, aabb_min=aabb[0], aabb_max=aabb[1])
+        d, _, sec = h.voxelize("segments", *res)
+        e = dict(extra)
+        e.update({"strands": nb, "segments_per_strand": sb, "resolution": list(res), "input_fnv": fnv(vb),
+                  "aabb": [float(x) for x in h.aabb], "segments": stats(d)})
+        e["segments"]["reference_seconds"] = round(sec, 3)
+        e["normalize_segments"] = stats(R.normalize(d))
+        fp[name] = e
+        print(name, json.dumps(e)[:400], flush=True)
+        h.close()
+
+    for name, shape in (("straight_512_full", "straight"), ("curly_512_full", "curly"), ("big_512_full", "big")):
+        vb, nb, sb = synth.shape(shape, seed=0x5EED, seg_len=0.5)
+        one(name, vb, nb, sb, (512, 512, 512), {"shape": shape, "seed": 0x5EED, "seg_len": 0.5, "scale": 1.0})
+    v0, n0, s0 = synth.shape("ponytail", seed=0x5EED, seg_len=0.5)
+    lo, hi = synth.sway_union_bounding_box(v0, n0, s0, range(120))
+    for t in SWAY_FRAMES:
+        vt = synth.sway(v0, n0, s0, float(t))
+        one(f"ponytail_sway_t{t}_1024", vt, n0, s0, (1024, 1024, 1024),
+            {"shape": "ponytail", "seed": 0x5EED, "seg_len": 0.5, "scale": 1.0, "sway_t": t,
+             "union_aabb_min": [float(x) for x in lo], "union_aabb_max": [float(x) for x in hi]}, aabb=(lo, hi))
+    return fp
+
+
 def main():
     R = oracle.ref()
+    if "--sizes" in sys.argv:
+        path = os.path.join(HERE, "golden.json")
+        with open(path) as f:
+            out_json = json.load(f)
+        out_json["fingerprints_at_size"] = at_size(R)
+        with open(path, "w") as f:
+            json.dump(out_json, f, indent=1, sort_keys=True)
+        print("merged fingerprints_at_size into", path)
+        return
     out_json = {}
+    try:                                    # keep the at-size fingerprints of an earlier --sizes run
+        with open(os.path.join(HERE, "golden.json")) as f:
+            out_json["fingerprints_at_size"] = json.load(f)["fingerprints_at_size"]
+    except Exception:  # noqa: BLE001
+        pass
 
     # ---- 1. Appendix B known answers -------------------------------------------------
     v = np.array(KAT_VERTICES, dtype=np.float32)

@@ -165,6 +165,14 @@ def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["impl"] == "reference" and d["unit"] == "M seg/s" and d["higher_is_better"] is True and d["value"] > 0
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    # the reference arm must not map the product library: it imports oracle/ and harness/ only
+    probe = subprocess.run([sys.executable, "-c",
+                            "import sys, os; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0', '--res', '32'];"
+                            "sys.path.insert(0, %r); import runpy; runpy.run_path(os.path.join(%r, 'bench.py'), run_name='__main__');"
+                            "m = open('/proc/self/maps').read(); assert 'libvkhr_b200' not in m, 'product library mapped'; "
+                            "assert 'vkhr_b200' not in sys.modules" % (root, root)],
+                           capture_output=True, text=True, env=env, timeout=600)
+    assert probe.returncode == 0, probe.stderr[-600:]
     env["RANK"] = "1"
     other = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                            capture_output=True, text=True, env=env, timeout=600)

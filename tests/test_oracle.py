@@ -271,3 +271,35 @@ def test_adsm_oracle_known_answers(port):
     a = port.prefilter_adsm(dens.astype(np.uint8), 6, 5, 4, [0, 0, 0], [3, 2.5, 2], [1, 9, 1])
     b = port.prefilter_adsm((dens * 2).astype(np.uint8), 6, 5, 4, [0, 0, 0], [3, 2.5, 2], [1, 9, 1])
     assert np.all(b <= a) and a.min() >= 0 and a.max() <= 1.0 and (a < 1.0).any()
+
+
+AT_SIZE = ["straight_512_full", "curly_512_full", "big_512_full", "ponytail_sway_t0_1024", "ponytail_sway_t59_1024", "ponytail_sway_t119_1024"]
+
+
+def at_size_input(e):
+    """The strands of a `fingerprints_at_size` entry (tests/golden/make_golden.py --sizes)."""
+    v, n, s = synth.shape(e["shape"], seed=e["seed"], seg_len=e["seg_len"], scale=e["scale"])
+    if "sway_t" in e:
+        v = synth.sway(v, n, s, float(e["sway_t"]))
+    return v, n, s
+
+
+@pytest.mark.parametrize("name", AT_SIZE)
+def test_port_at_the_baseline_sizes(port, golden, name):
+    """BASELINE.json configs 1 (straight AND curly, 50,000 x 65 at 512^3), 2 (1 M x 32 at 512^3) and 4 (swayed ponytail
+    frames in the union AABB of the sequence at 1024^3): the C restatement against fingerprints of the UNMODIFIED
+    reference at those sizes -- the fp32 index rounds in groups of up to 8 (512^3) and 64 (1024^3) voxels there
+    (hair_style.cc:321)."""
+    e = golden["fingerprints_at_size"][name]
+    v, n, s = at_size_input(e)
+    assert _fnv(port, v) == e["input_fnv"], "synthetic generator output changed: regenerate tests/golden (--sizes)"
+    W, H, D = e["resolution"]
+    bb = np.array(e["aabb"], dtype=np.float32)
+    if "sway_t" in e:
+        lo, hi = np.array(e["union_aabb_min"], np.float32), np.array(e["union_aabb_max"], np.float32)
+        assert np.array_equal(bb[:3], lo) and np.array_equal(bb[4:7], hi - lo)
+    d = port.voxelize_segments(v, port.generate_indices(n, s), bb[:3], bb[4:7], W, H, D)
+    st = e["segments"]
+    assert (_fnv(port, d), int(d.astype(np.int64).sum()), int(np.count_nonzero(d)), int((d == 255).sum())) == \
+           (st["fnv"], st["sum"], st["nonzero"], st["saturated"])
+    assert _fnv(port, port.normalize(d)) == e["normalize_segments"]["fnv"]

@@ -766,7 +766,13 @@ def test_frame_kernel_rings_mixed_batches_and_repeated_frames(port, ring_volumes
                 want = np.zeros(nv, np.uint8)
                 idx = None
             else:
-                v, n, s = synth.shape("ponytail", seed=300 + k, seg_len=float(rng.uniform(0.5, 2.0)), scale=scale)
+                if k == 4:                                                # a clump: thousands of hits in a few voxels (verdict + repair)
+                    n, s = 3000, 12
+                    v = synth.strands(n, s, seed=304, root_min=(1.0, 1.0, 1.0), root_max=(3.0, 3.0, 3.0), seg_len=0.4)
+                    v = np.concatenate([v, synth.strands(50, s, seed=305, seg_len=1.5)])      # + a few strands that span the box
+                    n += 50
+                else:
+                    v, n, s = synth.shape("ponytail", seed=300 + k, seg_len=float(rng.uniform(0.5, 2.0)), scale=scale)
                 lo, hi = port.generate_bounding_box(v)
                 size = (hi - lo).astype(np.float32)
                 idx = port.generate_indices(n, s)
@@ -812,3 +818,71 @@ def test_frame_kernel_is_one_launch_per_frame(vox, port):
     assert vox.launch_count - l0 == 5
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy(), port.voxelize_segments(v, port.generate_indices(n, s), lo, size, 64, 64, 64))
+
+
+# ---- BASELINE.json configs at their FULL sizes ---------------------------------------------------------------------
+from test_oracle import AT_SIZE, at_size_input  # noqa: E402
+
+
+@pytest.mark.parametrize("name", AT_SIZE)
+def test_baseline_configs_at_full_size(vox, port, golden, name):
+    """configs[1] straight AND curly 50,000 x 65 at 512^3, configs[2] 1 M x 32 at 512^3, configs[4] swayed ponytail
+    frames t = 0, 59, 119 in the union AABB of the 120-frame sequence at 1024^3: the default strategy and every forced
+    one against fingerprints of the UNMODIFIED reference at that size (bit-exact; the fp32 index of hair_style.cc:321
+    rounds in groups of up to 8 voxels at 512^3 and 64 at 1024^3)."""
+    import torch
+    dev = torch.device("cuda", 0)
+    e = golden["fingerprints_at_size"][name]
+    v, n, s = at_size_input(e)
+    assert _fnv(port, v) == e["input_fnv"], "synthetic generator output changed: regenerate tests/golden (--sizes)"
+    W, H, D = e["resolution"]
+    bb = np.array(e["aabb"], dtype=np.float32)
+    st = e["segments"]
+    vt = torch.from_numpy(v).to(dev).reshape(-1)
+    out = torch.empty(W * H * D, dtype=torch.uint8, device=dev)
+    seen = set()
+    for strat in STRATEGIES:
+        out.fill_(3)
+        vox.voxelize_segments_dev(vt, None, bb[:3], bb[4:7], W, H, D, segs_per_strand=s, flags=strat, out=out)
+        seen.add(vox.last_strategy)
+        d = out.cpu().numpy()
+        assert (_fnv(port, d), int(d.astype(np.int64).sum()), int(np.count_nonzero(d)), int((d == 255).sum())) == \
+               (st["fnv"], st["sum"], st["nonzero"], st["saturated"]), (name, strat)
+    assert seen == {capi.STRATEGY_COUNT32, capi.STRATEGY_PACKED8, capi.STRATEGY_BRICK8}
+    assert _fnv(port, vox.normalize_dev(out).cpu().numpy()) == e["normalize_segments"]["fnv"]
+    # explicit index pairs (the reference's own caller passes them) through the default strategy
+    if W == 512 and n <= 100_000:
+        it = torch.from_numpy(port.generate_indices(n, s).astype(np.int32)).to(dev)
+        d = vox.voxelize_segments_dev(vt, it, bb[:3], bb[4:7], W, H, D, out=out).cpu().numpy()
+        assert _fnv(port, d) == st["fnv"]
+    del out, vt
+    torch.cuda.empty_cache()
+
+
+def test_sway_sequence_union_bounding_box(vox, golden):
+    """configs[4]: the fixed AABB of the animated sequence is the union of the per-frame generate_bounding_box results
+    (the reference keeps the load-time AABB for every frame, rasterizer/hair_style.cc:66); all 120 frames on the GPU."""
+    import torch
+    dev = torch.device("cuda", 0)
+    e = golden["fingerprints_at_size"]["ponytail_sway_t0_1024"]
+    v0, n, s = synth.shape(e["shape"], seed=e["seed"], seg_len=e["seg_len"], scale=e["scale"])
+    lo = hi = None
+    box = torch.empty(6, dtype=torch.float32, device=dev)
+    for t in range(120):
+        vt = torch.from_numpy(synth.sway(v0, n, s, float(t))).to(dev).reshape(-1)
+        b = vox.generate_bounding_box_dev(vt, out=box).cpu().numpy()
+        lo = b[:3].copy() if lo is None else np.minimum(lo, b[:3])
+        hi = b[3:].copy() if hi is None else np.maximum(hi, b[3:])
+    assert np.array_equal(lo, np.array(e["union_aabb_min"], np.float32))
+    assert np.array_equal(hi, np.array(e["union_aabb_max"], np.float32))
+
+
+def test_bounding_box_signed_zero_and_nan(vox, port):
+    """generate_bounding_box folds with `(b < a) ? b : a` from +0.0f (hair_style.cc:215-234): a -0.0f coordinate never
+    replaces +0.0f, and a NaN never replaces anything."""
+    v = np.array([[-0.0, 1.0, 2.0], [3.0, -0.0, -0.0], [np.nan, 0.5, np.nan], [1.0, 2.0, -0.0]], dtype=np.float32)
+    lo, hi = vox.generate_bounding_box(v)
+    plo, phi = port.generate_bounding_box(v)
+    assert lo.tobytes() == plo.tobytes() and hi.tobytes() == phi.tobytes()
+    assert not np.signbit(lo).any() and not np.signbit(hi).any()
+    assert lo.tolist() == [0.0, 0.0, 0.0] and hi.tolist() == [3.0, 2.0, 2.0]

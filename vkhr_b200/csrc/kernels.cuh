@@ -995,8 +995,17 @@ k_generate_indices(const uint32_t* __restrict__ seg_prefix, uint32_t n_strands, 
 // ---------------------------------------------------------------------------
 // HairStyle::generate_bounding_box (hair_style.cc:215-234): min/max folded
 // from (0,0,0).  Floats are mapped to order-preserving u32 keys so the fold is
-// an integer atomicMin/Max; out[0..2] = min keys, out[3..5] = max keys,
+// an integer atomicMin/Max; keys[0..2] = min keys, keys[3..5] = max keys,
 // initialised to key(0.0f) by k_aabb_init and decoded by k_aabb_decode.
+//
+// Signed zeros.  The reference folds with glm::min(position, min) = (min < position) ? min : position and
+// glm::max(position, max) = (position < max) ? max : position: on a TIE the new position wins, and -0.0f ties with
+// +0.0f.  So when the minimum (or maximum) of an axis is zero, its SIGN is that of the last zero-valued coordinate in
+// vertex order (+ when no coordinate is zero: the initial value).  keys[6..8] track that coordinate per axis:
+// ((vertex + 1) << 1 | sign bit), folded with atomicMax.  Densities never see the difference ((v - -0.0f) == (v - 0.0f)
+// up to the sign of a zero, which floor / the index sum discard), but the AABB the caller gets back is byte-identical.
+// NaN coordinates: the reference's fold is order-dependent garbage there (a NaN replaces the running value, the next
+// vertex replaces the NaN); defined here as ignored.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t f2key(float f) {
     uint32_t u = __float_as_uint(f);
@@ -1007,28 +1016,29 @@ __device__ __forceinline__ float key2f(uint32_t k) {
 }
 __global__ void k_aabb_init(uint32_t* keys) {
     if (threadIdx.x < 6) keys[threadIdx.x] = f2key(0.0f);
+    else if (threadIdx.x < 9) keys[threadIdx.x] = 0u;
 }
 __global__ void __launch_bounds__(256)
 k_aabb_reduce(const float* __restrict__ xyz, uint32_t n_vertices, uint32_t* __restrict__ keys) {
     // A block-iteration covers 768 consecutive floats (a multiple of 3), so the
     // float at base + 256*r + t is component (t + r) % 3: each thread keeps three
     // running (min,max) pairs, one per r, with fully coalesced loads.
-    __shared__ uint32_t s_keys[6];
+    __shared__ uint32_t s_keys[9];
     const uint32_t z = f2key(0.0f);
     if (threadIdx.x < 6) s_keys[threadIdx.x] = z;
+    else if (threadIdx.x < 9) s_keys[threadIdx.x] = 0u;
     __syncthreads();
     const uint64_t n = 3ull * n_vertices;
-    uint32_t lo[3] = {z, z, z}, hi[3] = {z, z, z};
+    uint32_t lo[3] = {z, z, z}, hi[3] = {z, z, z}, zero[3] = {0u, 0u, 0u};
     const uint64_t stride = (uint64_t)gridDim.x * 768ull;
     for (uint64_t base = (uint64_t)blockIdx.x * 768ull; base < n; base += stride) {
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             const uint64_t i = base + r * 256 + threadIdx.x;
             if (i < n) {
-                // the reference folds with `(b < a) ? b : a` / `(a < b) ? b : a` from +0.0f (hair_style.cc:215-234): a -0.0f
-                // never replaces +0.0f and a NaN never replaces anything.  `f + 0.0f` turns -0.0f into +0.0f.
-                const float f = __fadd_rn(xyz[i], 0.0f);
-                if (f == f) {
+                const float f = xyz[i];
+                if (f == 0.0f) zero[r] = max(zero[r], (((uint32_t)(i / 3ull) + 1u) << 1) | (__float_as_uint(f) >> 31));
+                else if (f == f) {
                     const uint32_t k = f2key(f);
                     lo[r] = min(lo[r], k);
                     hi[r] = max(hi[r], k);
@@ -1041,13 +1051,18 @@ k_aabb_reduce(const float* __restrict__ xyz, uint32_t n_vertices, uint32_t* __re
         const int comp = (threadIdx.x + r) % 3;
         if (lo[r] != z) atomicMin(&s_keys[comp], lo[r]);
         if (hi[r] != z) atomicMax(&s_keys[3 + comp], hi[r]);
+        if (zero[r]) atomicMax(&s_keys[6 + comp], zero[r]);
     }
     __syncthreads();
     if (threadIdx.x < 3) atomicMin(keys + threadIdx.x, s_keys[threadIdx.x]);
-    else if (threadIdx.x < 6) atomicMax(keys + threadIdx.x, s_keys[threadIdx.x]);
+    else if (threadIdx.x < 9) atomicMax(keys + threadIdx.x, s_keys[threadIdx.x]);
 }
 __global__ void k_aabb_decode(const uint32_t* keys, float* out6) {
-    if (threadIdx.x < 6) out6[threadIdx.x] = key2f(keys[threadIdx.x]);
+    if (threadIdx.x < 6) {
+        float f = key2f(keys[threadIdx.x]);
+        if (f == 0.0f) f = (keys[6 + threadIdx.x % 3] & 1u) ? -0.0f : 0.0f;    // the last zero coordinate of the axis decides the sign
+        out6[threadIdx.x] = f;
+    }
 }
 
 }  // namespace vkhr_b200

@@ -1075,7 +1075,7 @@ int vkhr_b200_generate_bounding_box_dev(vkhr_b200_ctx* ctx, const float* d_verti
     RET_IF(bind(ctx));
     if (!d_aabb_out || (n_vertices && !d_vertices)) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null pointer");
     cudaStream_t s = pick(ctx, stream);
-    uint32_t* keys = static_cast<uint32_t*>(ctx->small.p) + 8;
+    uint32_t* keys = static_cast<uint32_t*>(ctx->small.p) + 32;          // 9 words: min keys, max keys, last-zero trackers
     k_aabb_init<<<1, 32, 0, s>>>(keys);
     ctx->launches++;
     if (n_vertices) {
