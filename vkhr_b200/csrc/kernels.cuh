@@ -252,88 +252,121 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 
 template <class T> __device__ __forceinline__ T* pin(T* p) { asm volatile("" : "+l"(p)); return p; }
 
-// The walk of one warp's range of CTA-item `bx` of instance I (uniform strands): 8 tiles of 31 segments.
-// `bar` / `parity`: the warp's own mbarrier (initialised once per kernel, count 1) and the phase the next bulk copy
-// completes; the sink is the caller's (it calls finish()).  All 32 lanes call this together.
-template <int EXACT, class Sink>
-__device__ __forceinline__ void walk_uniform_warp(const InstanceDev& I, uint32_t bx, float* stage, uint32_t bar, uint32_t& parity, Sink& sink) {
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const GridParams g = pin(I.grid);                              // registers, not indexed constant loads
-    const uint32_t n_vertices = pin(I.n_vertices);
-    const uint32_t n_floats = 3u * n_vertices;
-    const uint32_t n_warp_tiles = (n_vertices + kTileStride - 1u) / kTileStride;
+// A warp's range of an instance with uniform strands: 8 tiles of 31 segments (2976 bytes of vertices + one tip vertex).
+// Two steps, so that a persistent kernel can request the NEXT range's vertices before it walks the current one.
+//
+// stage_range: start moving the range's vertices into `stage`.  16-byte aligned vertex buffers: ONE bulk copy issued
+// by lane 0, completion on the mbarrier `bar`; anything else (a 4-byte aligned view, the last bytes of the buffer):
+// coalesced 32-bit loads.  Returns whether a bulk copy is in flight (the walk then waits for `bar`).
+__device__ __forceinline__ bool stage_range(const InstanceDev& I, uint32_t range, float* stage, uint32_t bar) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n_floats = 3u * I.n_vertices;
     const float* __restrict__ verts = I.vertices;
+    const uint32_t start = kRangeFloats * range;                // first float of the range
+    if (start >= n_floats) return false;
+    const uint32_t need = min(kNeedFloats, n_floats - start);   // floats this warp reads from `stage`
+    uint32_t bulk = 0;                                          // floats that arrive by bulk copy
+    if ((reinterpret_cast<uintptr_t>(verts) & 15u) == 0u)
+        bulk = min(kBulkBytes, ((n_floats - start) * 4u) & ~15u) / 4u;
+    if (bulk && lane == 0) {
+        // (a persistent kernel reuses the slot: earlier generic-proxy accesses are ordered before the async-proxy write)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        bulk_load(smem_u32(stage), verts + start, bulk * 4u, bar);
+    }
+    for (uint32_t j = bulk + lane; j < need; j += 32u) stage[j] = __ldg(verts + start + j);
+    // floats past the end of the vertex buffer (last warp of an instance only) are never walked, but their
+    // lanes take part in the warp's votes: give them a harmless value instead of stale shared memory
+    for (uint32_t j = need + lane; j < kNeedFloats; j += 32u) stage[j] = I.grid.ox;
+    return bulk != 0u;
+}
 
-    const uint32_t range = bx * kWarpsPerBlock + warp;     // this warp's range of kTilesPerWarp tiles
+// walk_range: the walk of a staged range.  `parity`: the phase of `bar` the bulk copy completes (flipped here); the
+// sink is the caller's (it calls finish()).  All 32 lanes call this together.
+template <int EXACT, class Sink>
+__device__ __forceinline__ void walk_range(const InstanceDev& I, uint32_t range, float* stage, uint32_t bar, bool bulk, uint32_t& parity, Sink& sink) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const GridParams g = pin(I.grid);                              // registers, not indexed constant loads
+    const uint32_t n_vertices = I.n_vertices;
+    const uint32_t n_warp_tiles = (n_vertices + kTileStride - 1u) / kTileStride;
     const uint32_t tile0 = range * kTilesPerWarp;
     const uint32_t n_tiles = min(kTilesPerWarp, n_warp_tiles - min(tile0, n_warp_tiles));
+    if (bulk) { mbar_wait(bar, parity); parity ^= 1u; }
+    __syncwarp();
     if (n_tiles == 0) return;                                      // whole warps only
 
-    // ---- stage the warp's vertex range (8 tiles + one tip vertex, 3 KB) into shared memory -----------------
-    // 16-byte aligned vertex buffers: ONE bulk copy issued by lane 0, completion on the warp's own mbarrier.
-    // Anything else (a 4-byte aligned view, the last bytes of the buffer): coalesced 32-bit loads.
+    // ---- which of this lane's (up to) 8 vertices start a segment: bit j = tile j ---------------------------------
+    // vertex x starts a segment unless it is the last of its strand (x mod (segs + 1): one multiply-high division per
+    // range, then += 31 mod (segs + 1) per tile) or of the instance; lane 31 only supplies the tip of lane 30
+    uint32_t starts = 0;
     {
-        const uint32_t start = kRangeFloats * range;                // first float of the range
-        const uint32_t need = min(kNeedFloats, n_floats - start);   // floats this warp reads from `stage`
-        uint32_t bulk = 0;                                          // floats that arrive by bulk copy
-        if ((reinterpret_cast<uintptr_t>(verts) & 15u) == 0u)
-            bulk = min(kBulkBytes, ((n_floats - start) * 4u) & ~15u) / 4u;
-        if (bulk && lane == 0) {
-            // (a persistent kernel reuses the slot: earlier generic-proxy accesses are ordered before the async-proxy write)
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            bulk_load(smem_u32(stage), verts + start, bulk * 4u, bar);
-        }
-        for (uint32_t j = bulk + lane; j < need; j += 32u) stage[j] = __ldg(verts + start + j);
-        // floats past the end of the vertex buffer (last warp of an instance only) are never walked, but their
-        // lanes take part in the warp's range vote: give them a harmless value instead of stale shared memory
-        for (uint32_t j = need + lane; j < kNeedFloats; j += 32u) stage[j] = g.ox;
-        if (bulk) { mbar_wait(bar, parity); parity ^= 1u; }
-        __syncwarp();
-    }
-
-    // ---- loop-carried lane state, all in registers ---------------------------------------------------------
-    // saddr: shared-memory address of this lane's vertex of the tile being fetched (a tile is 93 floats further);
-    // kept as a pinned 32-bit shared address -- left to itself the compiler rebuilds it from %tid and the CTA's
-    // shared window (two S2R, a LEA, two IMADs) for every tile.
-    // x: global vertex index of this lane's vertex; r = x mod (segs + 1), advanced by 31 mod (segs + 1) per tile
-    // (one multiply-high division per warp instead of one per tile).
-    uint32_t saddr = pin(smem_u32(stage) + 12u * lane);
-    const uint32_t vps = pin(I.segs_per_strand + 1u);
-    uint32_t x = kTileStride * tile0 + lane;
-    uint32_t r, r_step;
-    {
-        const uint32_t magic = I.vps_magic;                        // floor(2^32 / vps) + 1: quotient exact or one too large
-        r = x - __umulhi(x, magic) * vps;
+        const uint32_t vps = I.segs_per_strand + 1u, magic = I.vps_magic;   // floor(2^32 / vps) + 1: quotient exact or one too large
+        uint32_t x = kTileStride * tile0 + lane;
+        uint32_t r = x - __umulhi(x, magic) * vps, r_step = kTileStride - __umulhi(kTileStride, magic) * vps;
         if ((int32_t)r < 0) r += vps;
-        r_step = kTileStride - __umulhi(kTileStride, magic) * vps;
         if ((int32_t)r_step < 0) r_step += vps;
-        r = pin(r); r_step = pin(r_step);
+#pragma unroll
+        for (uint32_t j = 0; j < kTilesPerWarp; ++j) {
+            starts |= (uint32_t)(x + 1u < n_vertices && r != vps - 1u) << j;
+            x += kTileStride;
+            r += r_step;
+            if (r >= vps) r -= vps;
+        }
+        if (lane >= kTileStride) starts = 0u;
+        starts = pin(starts);
     }
-    const bool seg_lane = pin((uint32_t)(lane < kTileStride)) != 0u;   // lane 31 only supplies the tip of lane 30
 
     // ---- software-pipelined tile loop ------------------------------------------------------------------
-    // The raw floats of tile k+1 are requested before tile k is walked and transformed (three exact divisions, then
-    // the shuffle that hands lane t the vertex of lane t+1) right after it: the shared-memory round trip hides
-    // behind the walk, and only three registers of look-ahead stay live across it (keeping the transformed end
-    // points of the next tile live as well cost spills at 48 registers per thread).
+    // saddr: shared-memory address of this lane's vertex of the tile being fetched (a tile is 93 floats further), kept
+    // as a pinned 32-bit shared address (left to itself the compiler rebuilds it from %tid for every tile).  The raw
+    // floats of tile k+1 are requested before tile k is walked and transformed right after it: the shared-memory
+    // round trip hides behind the walk, and only three registers of look-ahead stay live across it.
+    uint32_t saddr = pin(smem_u32(stage) + 12u * lane);
     float r0, r1, r2, px, py, pz, tx, ty, tz;
     auto fetch = [&]() { r0 = lds_f32(saddr); r1 = lds_f32(saddr + 4u); r2 = lds_f32(saddr + 8u); saddr += 12u * kTileStride; };
-    auto transform = [&]() {
-        to_voxel_space_warp(g, r0, r1, r2, px, py, pz);
+    auto shuffle_tips = [&]() {                                    // lane t's tip is lane t + 1's vertex
         tx = __shfl_down_sync(kFullWarp, px, 1);
         ty = __shfl_down_sync(kFullWarp, py, 1);
         tz = __shfl_down_sync(kFullWarp, pz, 1);
+    };
+    constexpr bool kInterior = EXACT == 3;                          // the unguarded interior walk exists for the int32-index brick sink
+    const bool fast_div = kInterior && g.fast_div != 0u;            // (uniform) the FMA division applies to this instance's voxel sizes
+    auto transform = [&]() {
+        if (fast_div) {
+            // unguarded: validated by vertex_is_interior on the RESULT (walk.cuh); a tile that fails the vote is redone below
+            px = div_fast(__fsub_rn(r0, g.ox), g.vsx, g.rvx);
+            py = div_fast(__fsub_rn(r1, g.oy), g.vsy, g.rvy);
+            pz = div_fast(__fsub_rn(r2, g.oz), g.vsz, g.rvz);
+        } else {
+            to_voxel_space_warp(g, r0, r1, r2, px, py, pz);
+        }
+        shuffle_tips();
     };
     fetch();
     transform();
     for (uint32_t k = n_tiles; k > 0u; --k) {
         if (k > 1u) fetch();                                       // warp-uniform
-        // vertex x starts a segment unless it is the last of its strand
-        const bool active = seg_lane && x + 1u < n_vertices && r != vps - 1u;
-        walk_voxel_space_warp<EXACT, false>(g, active, px, py, pz, tx, ty, tz, sink);
-        x += kTileStride;
-        r += r_step;
-        if (r >= vps) r -= vps;
+        const bool active = (starts & 1u) != 0u;
+        starts >>= 1;
+        bool walked = false;
+        if constexpr (kInterior) if (fast_div) {
+            const float dx = __fsub_rn(tx, px), dy = __fsub_rn(ty, py), dz = __fsub_rn(tz, pz);
+            const float steps = fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz));   // no NaN here when the vote passes
+            const bool ok = vertex_is_interior(g, px, py, pz) && (!active || steps < 2048.0f);
+            if (__all_sync(kFullWarp, ok)) {
+                if (active && steps > 0.0f) walk_interior_lane(px, py, pz, dx, dy, dz, steps, sink);
+                walked = true;
+            }
+        }
+        if (!walked) {
+            if (fast_div) {
+                // a vertex on or outside the faces of the box, a NaN, a very long segment: the guarded code, from the
+                // tile's raw floats (still in the stage: 93 floats per tile)
+                const uint32_t a = smem_u32(stage) + 12u * lane + 12u * kTileStride * (n_tiles - k);
+                to_voxel_space_warp(g, lds_f32(a), lds_f32(a + 4u), lds_f32(a + 8u), px, py, pz);
+                shuffle_tips();
+            }
+            walk_voxel_space_warp<EXACT, false>(g, active, px, py, pz, tx, ty, tz, sink);
+        }
         if (k > 1u) transform();
     }
 }
@@ -352,7 +385,9 @@ k_walk_uniform(const __grid_constant__ Batch B, uint32_t first) {
     uint32_t parity = 0;
     auto sink = SinkOf<MODE>::make(I);
     sink.words_pin();
-    walk_uniform_warp<EXACT>(I, blockIdx.x, s_stage[warp], bar, parity, sink);
+    const uint32_t range = blockIdx.x * kWarpsPerBlock + warp;     // this warp's range of kTilesPerWarp tiles
+    const bool bulk = stage_range(I, range, s_stage[warp], bar);
+    walk_range<EXACT>(I, range, s_stage[warp], bar, bulk, parity, sink);
     sink.finish();
 }
 
@@ -392,28 +427,36 @@ k_walk_indexed(const __grid_constant__ Batch B, uint32_t first) {
 }
 
 // ---------------------------------------------------------------------------
-// The frame kernel: BRICK8 walk AND copy-out of a whole batch in ONE persistent launch.
+// The frame kernel: BRICK8 walk AND copy-out of a whole batch in ONE persistent launch of autonomous warps.
 //
-// Work items are drawn from a ticket counter in a fixed order: for instance p = 0, 1, ... the walk items of p (one
-// CTA-item = 8 warp-ranges of 8 tiles, as a CTA of k_walk_uniform; 2048 segments of an indexed instance), then the
-// copy-out items of instance p - delay (2048 bricks each).  Instance i counts in scratch slot i mod `ring` -- a ring of
-// a few volumes that stays resident in the 126 MB L2, so the walk's reds, the copy-out's reads and the zeros it writes
-// behind itself never travel to HBM; what does is the algorithmic traffic: the strands once, the output volumes once.
-// The copy-out of one instance runs beside the walk of the next on the same SMs: the walk is bound by its instructions
-// (84 % issue-active), the copy-out by memory, and together they fill both.
+// Every warp draws work items from a ticket counter, in a fixed order: for instance p = 0, 1, ... the walk items of p
+// (one item = one warp-range: 8 tiles of 31 segments of a uniform instance, 256 segments of an indexed one), then the
+// copy-out items of instance p - delay (256 bricks each).  Instance i counts in scratch slot i mod `ring` -- a ring of a
+// few volumes that stays resident in the 126 MB L2, so the walk's reds, the copy-out's reads and the zeros it writes
+// behind itself do not travel to HBM; what does is the algorithmic traffic: the strands once, the output volumes once.
+// The copy-out of one instance runs beside the walk of the next on the same SMs: the walk is bound by its instructions,
+// the copy-out by memory, and together they fill both.
+//
+// There is no CTA barrier after the prologue: a warp is never held up by the slowest warp of its CTA (a first version
+// with CTA-wide items spent a quarter of its warp-time at barriers, profiles/r02_b_frame64_cta_items_ncu_summary.txt).
+// A warp works one item ahead: while it walks a range, the bulk copy of its NEXT range's vertices is already in flight
+// into its second stage buffer, and the ticket after that has been drawn.
 //
 // Dependencies are counters in a small control block: a copy item of instance i waits until all walk items of i have
 // reported (walk_done[i]); a walk item of instance i waits until the copy-out of instance i - ring has released the slot
-// (copy_done).  An item only ever waits for items with SMALLER tickets, and a ticket is drawn by a CTA that is already
-// running, so the lowest unfinished ticket never waits: no deadlock, whatever the number of resident CTAs (no
-// cooperative launch needed).  delay < ring keeps that true for the slot reuse.  Waits spin with a bound and trap.
-// The verdict of the fire-and-forget `red` walk (samples added == byte sum, see SinkPacked8Brick) is taken by the CTA
-// that finishes an instance's last copy item.  The control block of the NEXT call is zeroed here (two blocks alternate),
-// so a frame is exactly one launch (+ the repair kernel's look at the flags).
+// (copy_done).  An item only ever waits for items with SMALLER tickets, and a ticket is drawn by a warp that is already
+// running and works its tickets in order, so the lowest unfinished ticket never waits: no deadlock, whatever the number
+// of resident CTAs (no cooperative launch needed).  delay < ring keeps that true for the slot reuse.  Waits spin with a
+// bound and trap.  The verdict of the fire-and-forget `red` walk (samples added == byte sum, see SinkPacked8Brick) is
+// taken by the warp that finishes an instance's last copy item.  The control block of the NEXT call is zeroed here (two
+// blocks alternate), so a frame is exactly one launch (+ the repair kernel's look at the flags).
 // ---------------------------------------------------------------------------
 constexpr uint32_t kFrameStatSlots = 32;
-constexpr uint32_t kFrameCopyBricks = 2048;                     // bricks per copy item: 8 per thread
-constexpr uint32_t kFrameIndexedSegs = 2048;                    // segments per walk item of an indexed instance
+constexpr uint32_t kFrameCopyBricks = 256;                      // bricks per copy item: 8 per lane
+constexpr uint32_t kFrameIndexedSegs = 256;                     // segments per walk item of an indexed instance: 8 per lane
+#ifndef VKHR_FRAME_MIN_CTAS
+#define VKHR_FRAME_MIN_CTAS 4
+#endif
 struct FrameCtl {
     uint32_t ticket;
     uint32_t pad[31];
@@ -434,83 +477,103 @@ struct FramePlan {
     FrameCtl* ctl;
     FrameCtl* ctl_next;
 };
+struct FrameWarpSmem {                                          // one per warp
+    float stage[2][kStageFloats];
+    unsigned long long bar[2];
+};
 
-// thread 0 waits until *p >= need (acquire), then the CTA meets at a barrier
+// lane 0 waits until *p >= need (acquire), then the warp reconverges
 __device__ __forceinline__ void frame_wait_ge(const uint32_t* p, uint32_t need) {
-    if (threadIdx.x == 0) {
+    if ((threadIdx.x & 31u) == 0u) {
         uint32_t v;
         for (uint32_t spin = 0;; ++spin) {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
             if (v >= need) break;
-            __nanosleep(100);
+            __nanosleep(200);
             if (spin > (1u << 23)) __trap();                       // a lost dependency must fail, not hang the device
         }
     }
-    __syncthreads();
+    __syncwarp();
 }
 
 template <int MODE, int EXACT>
-__global__ void __launch_bounds__(kWalkThreads, VKHR_WALK_MIN_CTAS)
+__global__ void __launch_bounds__(kWalkThreads, VKHR_FRAME_MIN_CTAS)
 k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
-    __shared__ __align__(128) float s_stage[kWarpsPerBlock][kStageFloats];
-    __shared__ __align__(8) unsigned long long s_bar[kWarpsPerBlock];
-    __shared__ uint32_t s_item[2][4];
-    __shared__ unsigned long long s_sum[kWarpsPerBlock];
-    __shared__ uint32_t s_last;
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t bar = smem_u32(&s_bar[warp]);
-    if (lane == 0) mbar_init(bar, 1);
-    uint32_t parity = 0;
+    extern __shared__ __align__(128) unsigned char s_frame_raw[];
+    FrameWarpSmem& S = reinterpret_cast<FrameWarpSmem*>(s_frame_raw)[threadIdx.x >> 5];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t bar0 = smem_u32(&S.bar[0]), bar1 = smem_u32(&S.bar[1]);
+    if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar1, 1); }
     FrameCtl* const ctl = P.ctl;
     if (blockIdx.x == gridDim.x - 1) {                             // the next call's control block (nobody uses it during this call)
         uint4* z = reinterpret_cast<uint4*>(P.ctl_next);
         for (uint32_t i = threadIdx.x; i < sizeof(FrameCtl) / 16u; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
     }
-    // thread 0 draws a ticket and resolves it: s_item[slot] = {ticket, phase, item within the phase}
-    auto draw = [&](uint32_t slot) {
-        const uint32_t t = atomicAdd(&ctl->ticket, 1u);
-        uint32_t lo = 0, hi = P.n + P.delay;
-        if (t < P.total)
-            while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (P.phase_start[mid] <= t) lo = mid; else hi = mid; }
-        s_item[slot][0] = t; s_item[slot][1] = lo; s_item[slot][2] = t - P.phase_start[lo];
+    __syncwarp();
+    uint32_t parity0 = 0, parity1 = 0;
+
+    // an item: its phase (= instance for a walk item) and its index within the phase, resolved from the ticket by lane 0
+    // and broadcast with REDUX -- the result lives in a uniform register, so the instance's constants come straight from
+    // the constant bank as in k_walk_uniform, where the instance is blockIdx.y
+    auto draw = [&]() -> uint32_t {                                // returns the ticket on every lane
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(&ctl->ticket, 1u);
+        return __reduce_max_sync(kFullWarp, t);
     };
-    if (threadIdx.x == 0) draw(0);
-    __syncthreads();
-    for (uint32_t it = 0;; ++it) {
-        // (the broadcasts tell the compiler that the ticket -- and with it the instance and its constants -- is
-        // warp-uniform: they then live in uniform registers and the constant bank, as in k_walk_uniform where the
-        // instance comes from blockIdx)
-        const uint32_t t = __reduce_max_sync(kFullWarp, s_item[it & 1u][0]);      // REDUX writes a uniform register
-        if (t >= P.total) break;                                   // uniform
-        const uint32_t lo = __reduce_max_sync(kFullWarp, s_item[it & 1u][1]), local = __reduce_max_sync(kFullWarp, s_item[it & 1u][2]);
-        if (threadIdx.x == 0) draw((it + 1u) & 1u);                // the next item, drawn behind this one's work
-        const uint32_t wn = lo < P.n ? B.inst[lo].n_tiles : 0u;
-        if (local < wn) {
-            // ---- walk item `local` of instance lo -----------------------------------------------------------
-            const uint32_t i = lo;
+    auto resolve = [&](uint32_t t, uint32_t& phase, uint32_t& local) {
+        uint32_t lo = 0;
+        if (lane == 0) {
+            uint32_t hi = P.n + P.delay;
+            while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (P.phase_start[mid] <= t) lo = mid; else hi = mid; }
+        }
+        phase = __reduce_max_sync(kFullWarp, lo);
+        local = t - P.phase_start[phase];
+    };
+    // is (phase, local) a walk item of a uniform instance?  (then its vertices can be requested ahead of time)
+    auto walk_items = [&](uint32_t phase) -> uint32_t { return phase < P.n ? B.inst[phase].n_tiles : 0u; };
+
+    uint32_t t_cur = draw(), t_nxt = draw();
+    uint32_t ph_cur = 0, lc_cur = 0, ph_nxt = 0, lc_nxt = 0;
+    bool bulk_cur = false, bulk_nxt = false;
+    uint32_t buf = 0;                                              // stage buffer of the current item
+    if (t_cur < P.total) {
+        resolve(t_cur, ph_cur, lc_cur);
+        if (lc_cur < walk_items(ph_cur) && B.inst[ph_cur].kind == WK_UNIFORM) bulk_cur = stage_range(B.inst[ph_cur], lc_cur, S.stage[0], bar0);
+    }
+    while (t_cur < P.total) {
+        // ---- one item ahead: resolve the next ticket, request its vertices into the other buffer, draw the ticket after it
+        if (t_nxt < P.total) {
+            resolve(t_nxt, ph_nxt, lc_nxt);
+            bulk_nxt = false;
+            if (lc_nxt < walk_items(ph_nxt) && B.inst[ph_nxt].kind == WK_UNIFORM)
+                bulk_nxt = stage_range(B.inst[ph_nxt], lc_nxt, S.stage[buf ^ 1u], buf ? bar0 : bar1);
+        }
+        const uint32_t t_after = draw();
+
+        const uint32_t wn = walk_items(ph_cur);
+        if (lc_cur < wn) {
+            // ---- walk item lc_cur of instance ph_cur -------------------------------------------------------------
+            const uint32_t i = ph_cur;
             const InstanceDev& I = B.inst[i];
             if (i >= P.ring) frame_wait_ge(&ctl->copy_done[i - P.ring], P.copy_items);      // the slot's previous tenant has been copied out
             auto sink = SinkOf<MODE>::make(I);
             sink.words = reinterpret_cast<uint32_t*>(P.ring_base + (unsigned long long)(i % P.ring) * P.slot_bytes);
             sink.words_pin();
-            if (I.kind == WK_UNIFORM) walk_uniform_warp<EXACT>(I, local, s_stage[warp], bar, parity, sink);
-            else
-                for (uint32_t j = 0; j < kFrameIndexedSegs / kWalkThreads; ++j)
-                    walk_indexed_lane<EXACT>(I, ((uint64_t)local * (kFrameIndexedSegs / kWalkThreads) + j) * kWalkThreads + threadIdx.x, sink);
-            const uint32_t added = __reduce_add_sync(kFullWarp, sink.added);
-            if (lane == 0) s_sum[warp] = added;
-            __threadfence();                                       // this thread's reds are performed before the item reports
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                unsigned long long sum = 0;
-                for (uint32_t w = 0; w < kWarpsPerBlock; ++w) sum += s_sum[w];
-                if (sum) atomicAdd(&ctl->added[i][t & (kFrameStatSlots - 1u)], sum);
-                __threadfence();
-                atomicAdd(&ctl->walk_done[i], 1u);
+            if (I.kind == WK_UNIFORM) {
+                if (buf) walk_range<EXACT>(I, lc_cur, S.stage[1], bar1, bulk_cur, parity1, sink);
+                else     walk_range<EXACT>(I, lc_cur, S.stage[0], bar0, bulk_cur, parity0, sink);
+            } else {
+                for (uint32_t j = 0; j < kFrameIndexedSegs / 32u; ++j)
+                    walk_indexed_lane<EXACT>(I, ((uint64_t)lc_cur * (kFrameIndexedSegs / 32u) + j) * 32u + lane, sink);
             }
+            const uint32_t added = __reduce_add_sync(kFullWarp, sink.added);
+            if (lane == 0 && added) atomicAdd(&ctl->added[i][t_cur & (kFrameStatSlots - 1u)], (unsigned long long)added);
+            __threadfence();                                       // every lane's reds (and the count) are performed before the item reports
+            __syncwarp();
+            if (lane == 0) atomicAdd(&ctl->walk_done[i], 1u);
         } else {
-            // ---- copy-out item of instance lo - delay: brick order -> the x-fastest output volume -------------
-            const uint32_t i = lo - P.delay, c = local - wn;
+            // ---- copy-out item of instance ph_cur - delay: brick order -> the x-fastest output volume ------------
+            const uint32_t i = ph_cur - P.delay, c = lc_cur - wn;
             const InstanceDev& I = B.inst[i];
             frame_wait_ge(&ctl->walk_done[i], I.n_tiles);
             const uint32_t wrow = I.grid.W >> 2, byn = I.grid.H >> 2;             // words (= bricks) per row, brick rows per slab
@@ -520,7 +583,8 @@ k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
             const uint4 z = make_uint4(0, 0, 0, 0);
             uint32_t bytes = 0;                                                   // at most 8 x 8160
             const uint32_t b_end = min((c + 1u) * kFrameCopyBricks, P.n_bricks);
-            for (uint32_t b = c * kFrameCopyBricks + threadIdx.x; b < b_end; b += kWalkThreads) {
+#pragma unroll 2
+            for (uint32_t b = c * kFrameCopyBricks + lane; b < b_end; b += 32u) {
                 const uint4 q0 = __ldcg(src + 2u * b), q1 = __ldcg(src + 2u * b + 1u);   // L2 is where the reds landed; L1 may be stale
                 bytes += __vsadu4(q0.x, 0u) + __vsadu4(q0.y, 0u) + __vsadu4(q0.z, 0u) + __vsadu4(q0.w, 0u) +
                          __vsadu4(q1.x, 0u) + __vsadu4(q1.y, 0u) + __vsadu4(q1.z, 0u) + __vsadu4(q1.w, 0u);
@@ -532,18 +596,12 @@ k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
                 if ((q0.x | q0.y | q0.z | q0.w | q1.x | q1.y | q1.z | q1.w) != 0u) { __stcg(src + 2u * b, z); __stcg(src + 2u * b + 1u, z); }
             }
             const uint32_t wsum = __reduce_add_sync(kFullWarp, bytes);
-            if (lane == 0) s_sum[warp] = wsum;
+            if (lane == 0 && wsum) atomicAdd(&ctl->bytes[i][t_cur & (kFrameStatSlots - 1u)], (unsigned long long)wsum);
             __threadfence();                                       // the zeros are in place before the slot is released
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                unsigned long long sum = 0;
-                for (uint32_t w = 0; w < kWarpsPerBlock; ++w) sum += s_sum[w];
-                if (sum) atomicAdd(&ctl->bytes[i][t & (kFrameStatSlots - 1u)], sum);
-                __threadfence();
-                s_last = (atomicAdd(&ctl->copy_done[i], 1u) == P.copy_items - 1u) ? 1u : 0u;
-            }
-            __syncthreads();
-            if (s_last && warp == 0) {
+            __syncwarp();
+            uint32_t last = 0;
+            if (lane == 0) last = (atomicAdd(&ctl->copy_done[i], 1u) == P.copy_items - 1u) ? 1u : 0u;
+            if (__reduce_max_sync(kFullWarp, last)) {
                 // the instance is complete: samples added != byte sum of the volume means some byte carried (more than
                 // 255 hits in a voxel) -> flag 2, k_repair_packed recounts the instance in u32
                 __threadfence();
@@ -552,7 +610,9 @@ k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
                 if (lane == 0) *I.ovf_flag = (a != y) ? 2u : 0u;
             }
         }
-        __syncthreads();                                           // s_item / s_sum / s_last are reused by the next item
+        t_cur = t_nxt; ph_cur = ph_nxt; lc_cur = lc_nxt; bulk_cur = bulk_nxt;
+        t_nxt = t_after;
+        buf ^= 1u;
     }
 }
 

@@ -361,7 +361,8 @@ BatchPlan fill_batch(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool verti
             // warp-tiles of kTileStride vertices, kTilesPerWarp per warp, kWarpsPerBlock warps per CTA
             const uint64_t warp_tiles = ((uint64_t)jobs[k].n_vertices + kTileStride - 1) / kTileStride;
             const uint64_t per_cta = (uint64_t)kWarpsPerBlock * kTilesPerWarp;
-            I.n_tiles = (uint32_t)((warp_tiles + per_cta - 1) / per_cta);
+            I.n_tiles = frame ? (uint32_t)((warp_tiles + kTilesPerWarp - 1) / kTilesPerWarp)      // the frame kernel's items are warp-ranges
+                              : (uint32_t)((warp_tiles + per_cta - 1) / per_cta);
         } else {
             const uint64_t items = (kind == WK_INDEXED) ? jobs[k].n_segments : jobs[k].n_vertices;
             const uint64_t per_item = frame ? kFrameIndexedSegs : kWalkThreads;     // the frame kernel's walk items are larger
@@ -475,11 +476,17 @@ int run_frame(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool small, cudaS
     RET_IF(reserve(ctx, ctx->counts, std::min<uint64_t>(nv, kRepairChunk) * 4));   // the repair's chunk scratch
     ctx->counts_clean_bytes = 0;
     uint32_t* base = static_cast<uint32_t*>(ctx->bitmap.p);
+    constexpr size_t kFrameSmem = kWarpsPerBlock * sizeof(FrameWarpSmem);
     int& blocks = ctx->frame_blocks[small ? 0 : 1];
     if (blocks == 0) {
         int per_sm = 0;
-        if (small) CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame<3, 3>, kWalkThreads, 0));
-        else       CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame<4, 4>, kWalkThreads, 0));
+        if (small) {
+            CU_CHECK(ctx, cudaFuncSetAttribute(k_frame<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFrameSmem));
+            CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame<3, 3>, kWalkThreads, kFrameSmem));
+        } else {
+            CU_CHECK(ctx, cudaFuncSetAttribute(k_frame<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFrameSmem));
+            CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame<4, 4>, kWalkThreads, kFrameSmem));
+        }
         if (per_sm < 1) return fail(ctx, VKHR_B200_ERR_CUDA, "frame kernel does not fit on an SM");
         blocks = per_sm * ctx->sm_count;
     }
@@ -509,11 +516,11 @@ int run_frame(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool small, cudaS
             ctx->batch.inst[k].ovf_bitmap = base + (size_t)k * (bm_words + kHdr) + kHdr;
             ctx->batch.inst[k].counts = static_cast<uint32_t*>(ctx->counts.p);
         }
-        const unsigned grid = (unsigned)std::min<uint32_t>(P.total, (uint32_t)blocks);
+        const unsigned grid = (unsigned)std::min<uint32_t>((P.total + kWarpsPerBlock - 1) / kWarpsPerBlock, (uint32_t)blocks);
         {
             PhaseMark mk(ctx, s, PH_WALK);
-            if (small) k_frame<3, 3><<<grid, kWalkThreads, 0, s>>>(ctx->batch, P);
-            else       k_frame<4, 4><<<grid, kWalkThreads, 0, s>>>(ctx->batch, P);
+            if (small) k_frame<3, 3><<<grid, kWalkThreads, kFrameSmem, s>>>(ctx->batch, P);
+            else       k_frame<4, 4><<<grid, kWalkThreads, kFrameSmem, s>>>(ctx->batch, P);
             ctx->launches++;
             CU_CHECK(ctx, cudaGetLastError());
         }
@@ -904,7 +911,7 @@ int vkhr_b200_voxelize_segments_batch_dev(vkhr_b200_ctx* ctx, const vkhr_b200_in
     std::vector<Job> jobs(n);
     for (uint32_t k = 0; k < n; ++k) {
         const vkhr_b200_instance& in = instances[k];
-        if (!in.d_vertices || !in.d_densities_out)
+        if ((!in.d_vertices && in.n_vertices) || !in.d_densities_out)      // (an instance without vertices gets an empty volume)
             return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "instance " + std::to_string(k) + ": null vertices or densities");
         Job& j = jobs[k];
         RET_IF(make_grid(ctx, in.aabb_origin, in.aabb_size, W, H, D, flags, j.grid));

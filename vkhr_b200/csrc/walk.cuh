@@ -368,6 +368,40 @@ __device__ __forceinline__ void walk_voxel_space_warp(const GridParams& g, bool 
     }
 }
 
+// ---------------------------------------------------------------------------
+// The interior walk (small grids, EXACT == 3 sinks): a tile whose 32 vertices ALL lie in [1, res - 1] on every axis.
+//
+// Then, for a segment of fewer than 2048 steps between two such vertices,
+//   * every sample lies in [0, res): the exact point root + k * dir is between the end points, and the accumulated
+//     `root += dir` is at most k half-ulps of a position below 8192 away from it (k * 2^-11 < 1), so neither the
+//     reference's upper clamp min(floor(p), res - 1) nor a negative coordinate can occur -- the loop needs no clamp and
+//     no sign test, and every sample is inside the grid (put_xyz);
+//   * the FMA division needs no range test: the numerators of (v - origin) / voxel_size were validated by the result
+//     (a numerator outside [2^-60, 2^60] gives a quotient above 2^20 or below 2^-20, which is not in [1, res - 1];
+//     NaN fails the comparison), and `direction / steps` divides differences of floats that are at least 1 by their
+//     largest magnitude: a component is zero or at least 2^-23, and so is `steps`.
+// The caller votes on the condition (vertex_is_interior on every lane's own vertex, idle lanes included, and
+// steps < 2048 on every lane with a segment) and runs the guarded walk_voxel_space_warp when it fails.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool vertex_is_interior(const GridParams& g, float px, float py, float pz) {
+    return fminf(fminf(px, py), pz) >= 1.0f && px <= g.rx1 && py <= g.ry1 && pz <= g.rz1;
+}
+template <class Sink>
+__device__ __forceinline__ void walk_interior_lane(float rx, float ry, float rz, float dx, float dy, float dz, float steps, Sink& sink) {
+    const float y = rcp_steps(steps);                                         // RN(1/steps)
+    dx = div_fast(dx, steps, y);
+    dy = div_fast(dy, steps, y);
+    dz = div_fast(dz, steps, y);
+    for (;;) {                                                                // while (steps-- > 0.0f)
+        sink.template put_xyz<0>(__float2int_rd(rx), __float2int_rd(ry), __float2int_rd(rz));
+        steps = __fsub_rn(steps, 1.0f);
+        if (!(steps > 0.0f)) break;
+        rx = __fadd_rn(rx, dx);
+        ry = __fadd_rn(ry, dy);
+        rz = __fadd_rn(rz, dz);
+    }
+}
+
 // Vertex pair of segment `s`.  indices == nullptr => uniform strands of
 // `segs` segments: the pairs HairStyle::generate_indices (hair_style.cc:196-213)
 // would emit, without reading an index buffer.
