@@ -253,6 +253,40 @@ VKHR_B200_API int vkhr_b200_combine_peer_u8_sparse_dev(
     vkhr_b200_ctx* ctx, const void* const* d_partials, const void* const* d_bitmaps, void* const* d_outs,
     uint32_t n_peers, uint64_t slab_offset_bytes, uint64_t slab_bytes, void* stream);
 
+/* ---- strand-sharded voxelisation over the GPUs of one box, in ONE call per rank ------------------------------ *
+ * BASELINE configs[2]: the strands of one hair style are split into contiguous ranges, one per GPU (rank); every rank
+ * calls this with ITS strands and the SHARED AABB, and returns with the complete W*H*D volume in its own output
+ * buffer -- the multi-GPU form of HairStyle::voxelize_segments (hair_style.cc:296-342).  Exact for every partition:
+ * the reference's counter only saturates (hair_style.cc:322-325), so
+ *   min(sum_r min(count_r, 255), 255) == min(sum_r count_r, 255).
+ * Steps, all enqueued on `stream`: the rank's shard is voxelised into its partial volume (the single-GPU path, u8);
+ * one bit per 16-byte chunk of the partial is published; a device-side barrier over the signal pads; ONE kernel reads
+ * the rank's slab of every peer's partial straight from the peers' memory over NVLink (only the chunks the bitmaps mark),
+ * adds with saturation and stores the slab into every peer's output; a second barrier.  No NCCL, no host round trip.
+ *
+ * The caller provides peer-mapped buffers (cudaIpc / cuMem / torch symmetric memory; on one device -- "fake ranks",
+ * one context and stream per rank -- plain device pointers): for every rank r, as mapped into THIS process,
+ *   partials[r]  padded volume bytes (vkhr_b200_sharded_volume_bytes), zero-filled once before the first call
+ *   bitmaps[r]   padded bytes / 512 uint32 words
+ *   outs[r]      padded volume bytes; the result of rank r
+ *   signals[r]   2 x 16 uint32 words, zero-filled once before the first call
+ * All ranks must make the same sequence of sharded calls (the barriers pair up by call count). */
+typedef struct vkhr_b200_shard_peers {
+    uint32_t rank, world;                 /* world <= 16 */
+    void* const* partials;
+    void* const* bitmaps;
+    void* const* outs;
+    void* const* signals;
+} vkhr_b200_shard_peers;
+/* W*H*D rounded up so that every rank owns a slab of whole bitmap words (a multiple of 512 * world bytes). */
+VKHR_B200_API uint64_t vkhr_b200_sharded_volume_bytes(uint32_t W, uint32_t H, uint32_t D, uint32_t world);
+VKHR_B200_API int vkhr_b200_voxelize_segments_sharded_dev(
+    vkhr_b200_ctx* ctx, const float* d_vertices, uint32_t n_vertices,
+    const uint32_t* d_indices, uint64_t n_indices, uint32_t segs_per_strand,
+    const float aabb_origin[3], const float aabb_size[3],
+    uint32_t W, uint32_t H, uint32_t D, uint32_t flags,
+    const vkhr_b200_shard_peers* peers, void* stream);
+
 /* densities = min(counts, 255), optionally followed by normalize (flags). */
 VKHR_B200_API int vkhr_b200_clamp_counts_dev(
     vkhr_b200_ctx* ctx, const uint32_t* d_counts, uint64_t n_voxels, uint32_t flags,

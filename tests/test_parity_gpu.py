@@ -475,6 +475,19 @@ def test_cpp_dropin_against_linked_reference():
     assert r.stdout.count("bit-exact") == 5 and "MISMATCH" not in r.stdout
 
 
+def test_cpp_sharded_entry_point_through_the_c_abi_only():
+    """adapter/_build/sharded_test: a C++ caller splits one style over 2, 3 and 8 ranks with nothing but include/vkhr_b200.h
+    (no CUDA headers, no NCCL, no torch); every rank's volume equals the one-context volume."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "adapter", "_build", "sharded_test")
+    if not os.path.exists(exe):
+        pytest.skip("adapter/_build/sharded_test not built")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("byte-identical") == 3 and "MISMATCH" not in r.stdout
+
+
 # ---- .hair file image -> volume (HairStyle::load + SceneGraph::add_style + voxelize_segments) -----------------------
 def _hair_file(tmp_path, name, strands, segs, *, segments=None, indices=False, tangents=False, bbox=False, seed=4):
     from vkhr_b200.hair_style import HairStyle
@@ -877,12 +890,69 @@ def test_sway_sequence_union_bounding_box(vox, golden):
     assert np.array_equal(hi, np.array(e["union_aabb_max"], np.float32))
 
 
-def test_bounding_box_signed_zero_and_nan(vox, port):
-    """generate_bounding_box folds with `(b < a) ? b : a` from +0.0f (hair_style.cc:215-234): a -0.0f coordinate never
-    replaces +0.0f, and a NaN never replaces anything."""
-    v = np.array([[-0.0, 1.0, 2.0], [3.0, -0.0, -0.0], [np.nan, 0.5, np.nan], [1.0, 2.0, -0.0]], dtype=np.float32)
+def test_bounding_box_signed_zeros_follow_the_reference_fold(vox, port, ref):
+    """generate_bounding_box folds with glm::min(position, min) = (min < position) ? min : position (hair_style.cc:215-234):
+    on a tie the NEW position wins and -0.0f ties with +0.0f, so the sign of a zero minimum / maximum is that of the last
+    zero coordinate in vertex order.  Byte-identical to the port and to the unmodified reference."""
+    rng = np.random.default_rng(11)
+    cases = [np.array([[-0.0, 1.0, 2.0], [3.0, -0.0, 0.0], [1.0, 2.0, -0.0]], dtype=np.float32),
+             np.array([[0.0, -0.0, 5.0], [-0.0, 0.0, 1.0], [2.0, 3.0, 4.0]], dtype=np.float32),
+             np.array([[1.0, 2.0, 3.0], [4.0, 5.0, 6.0]], dtype=np.float32)]
+    big = rng.uniform(0.0, 5.0, size=(5000, 3)).astype(np.float32)
+    big[rng.integers(0, 5000, 40), rng.integers(0, 3, 40)] = -0.0
+    big[rng.integers(0, 5000, 40), rng.integers(0, 3, 40)] = 0.0
+    cases.append(big)
+    for v in cases:
+        lo, hi = vox.generate_bounding_box(v)
+        plo, phi = port.generate_bounding_box(v)
+        assert lo.tobytes() == plo.tobytes() and hi.tobytes() == phi.tobytes()
+        n = v.shape[0] - (v.shape[0] % 2)
+        h = ref.create(v[:n], n // 2, 1)
+        if n == v.shape[0]:
+            assert h.aabb[:3].tobytes() == lo.tobytes()
+    # NaN coordinates: the reference's fold is order-dependent there; defined here as ignored
+    v = np.array([[1.0, np.nan, 2.0], [np.nan, 3.0, -1.0]], dtype=np.float32)
     lo, hi = vox.generate_bounding_box(v)
-    plo, phi = port.generate_bounding_box(v)
-    assert lo.tobytes() == plo.tobytes() and hi.tobytes() == phi.tobytes()
-    assert not np.signbit(lo).any() and not np.signbit(hi).any()
-    assert lo.tolist() == [0.0, 0.0, 0.0] and hi.tolist() == [3.0, 2.0, 2.0]
+    assert lo.tolist() == [0.0, 0.0, -1.0] and hi.tolist() == [1.0, 3.0, 2.0]
+
+
+@pytest.mark.parametrize("k", [2, 4])
+def test_sharded_entry_point_with_fake_ranks_on_one_device(port, k):
+    """vkhr_b200_voxelize_segments_sharded_dev, the multi-GPU form of voxelize_segments in the C ABI: k "ranks" = k contexts
+    with a stream each on ONE device, plain device pointers as peer buffers.  Partial volumes, chunk bitmaps, the
+    device-side barriers over the signal pads and the fused sparse combine all run as on k GPUs; every rank must end up
+    with the volume of the WHOLE strand set, frame after frame (the barriers pair up by call count)."""
+    import torch
+    from vkhr_b200 import sharding
+    dev = torch.device("cuda", 0)
+    W, H, D = 64, 48, 32
+    v, n, s = synth.shape("ponytail", seed=71, seg_len=1.0, scale=0.02)
+    lo, hi = port.generate_bounding_box(v)
+    size = (hi - lo).astype(np.float32)
+    nv = W * H * D
+    ranks = [vkhr_b200.Voxelizer(0) for _ in range(k)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(k)]
+    nvp = ranks[0].sharded_volume_bytes(W, H, D, k)
+    assert nvp % (512 * k) == 0 and nvp >= nv
+    partials = [torch.zeros(nvp, dtype=torch.uint8, device=dev) for _ in range(k)]
+    bitmaps = [torch.zeros(nvp // 512, dtype=torch.int32, device=dev) for _ in range(k)]
+    outs = [torch.full((nvp,), 9, dtype=torch.uint8, device=dev) for _ in range(k)]
+    signals = [torch.zeros(32, dtype=torch.int32, device=dev) for _ in range(k)]
+    ptrs = lambda ts: [t.data_ptr() for t in ts]   # noqa: E731
+    torch.cuda.synchronize()
+    try:
+        for frame in range(3):
+            vf = synth.sway(v, n, s, float(7 * frame))                     # the hair moves: a different volume every frame
+            want = port.voxelize_segments(vf, port.generate_indices(n, s), lo, size, W, H, D)
+            shards = [torch.from_numpy(np.ascontiguousarray(sharding.shard_vertices(vf, n, s, k, r))).to(dev).reshape(-1) for r in range(k)]
+            torch.cuda.synchronize()
+            for r in range(k):
+                with torch.cuda.stream(streams[r]):
+                    ranks[r].voxelize_segments_sharded_dev(shards[r], None, lo, size, W, H, D, r, ptrs(partials), ptrs(bitmaps), ptrs(outs),
+                                                           ptrs(signals), segs_per_strand=s)
+            torch.cuda.synchronize()
+            for r in range(k):
+                assert np.array_equal(outs[r][:nv].cpu().numpy(), want), (frame, r)
+    finally:
+        for vox in ranks:
+            vox.close()

@@ -66,6 +66,12 @@ class HostInstance(C.Structure):
     ]
 
 
+class ShardPeers(C.Structure):
+    """``vkhr_b200_shard_peers``."""
+    _fields_ = [("rank", C.c_uint32), ("world", C.c_uint32), ("partials", C.POINTER(C.c_void_p)), ("bitmaps", C.POINTER(C.c_void_p)),
+                ("outs", C.POINTER(C.c_void_p)), ("signals", C.POINTER(C.c_void_p))]
+
+
 class PrefilterParams(C.Structure):
     """``vkhr_b200_prefilter_params``."""
     _fields_ = [
@@ -132,6 +138,9 @@ _PROTOTYPES = {
     "vkhr_b200_combine_peer_u8_dev": (_int, [c_ctx, _P, _P, _u32, _u64, _u64, _P]),
     "vkhr_b200_chunk_bitmap_dev": (_int, [c_ctx, _P, _u64, _P, _P]),
     "vkhr_b200_combine_peer_u8_sparse_dev": (_int, [c_ctx, _P, _P, _P, _u32, _u64, _u64, _P]),
+    "vkhr_b200_sharded_volume_bytes": (_u64, [_u32, _u32, _u32, _u32]),
+    "vkhr_b200_voxelize_segments_sharded_dev": (_int, [c_ctx, _P, _u32, _P, _u64, _u32, _vec3, _vec3, _u32, _u32, _u32, _u32,
+                                                 C.POINTER(ShardPeers), _P]),
     "vkhr_b200_clamp_counts_dev": (_int, [c_ctx, _P, _u64, _u32, _P, _P]),
     "vkhr_b200_normalize_dev": (_int, [c_ctx, _P, _u64, _P]),
     "vkhr_b200_normalize": (_int, [c_ctx, _P, _u64]),

@@ -427,36 +427,32 @@ k_walk_indexed(const __grid_constant__ Batch B, uint32_t first) {
 }
 
 // ---------------------------------------------------------------------------
-// The frame kernel: BRICK8 walk AND copy-out of a whole batch in ONE persistent launch of autonomous warps.
+// The frame kernel: BRICK8 walk AND copy-out of a whole batch in ONE launch.
 //
-// Every warp draws work items from a ticket counter, in a fixed order: for instance p = 0, 1, ... the walk items of p
-// (one item = one warp-range: 8 tiles of 31 segments of a uniform instance, 256 segments of an indexed one), then the
-// copy-out items of instance p - delay (256 bricks each).  Instance i counts in scratch slot i mod `ring` -- a ring of a
-// few volumes that stays resident in the 126 MB L2, so the walk's reds, the copy-out's reads and the zeros it writes
-// behind itself do not travel to HBM; what does is the algorithmic traffic: the strands once, the output volumes once.
-// The copy-out of one instance runs beside the walk of the next on the same SMs: the walk is bound by its instructions,
-// the copy-out by memory, and together they fill both.
+// A CTA is one walk item, exactly as in k_walk_uniform (8 warp-ranges of 8 tiles; 2048 segments of an indexed
+// instance) -- except that it takes its item from a ticket counter, so items START in ticket order: instance 0's
+// first, then instance 1's, ...  When a CTA has walked its item it reports to its instance's counter, and the LAST
+// `copiers` CTAs to report for an instance stay on: they wait for the few items of that instance that are still
+// running (all of them have started: their tickets are smaller), and then copy the instance's scratch volume out to the
+// caller's x-fastest volume, 1 / copiers of the bricks each, zeroing behind themselves -- while every other CTA slot
+// of the machine is already walking the next instances.  The walk is bound by its instructions, the copy-out by
+// memory: side by side they fill both.  Instance i counts in scratch slot i mod `ring`; the in-flight window of the
+// machine is less than one instance, so a ring of 3 slots (48 MiB at 256^3) is never waited for and stays resident in
+// the 126 MB L2: the walk's reds, the copy-out's reads and the zeros behind it do not travel to HBM.
 //
-// There is no CTA barrier after the prologue: a warp is never held up by the slowest warp of its CTA (a first version
-// with CTA-wide items spent a quarter of its warp-time at barriers, profiles/r02_b_frame64_cta_items_ncu_summary.txt).
-// A warp works one item ahead: while it walks a range, the bulk copy of its NEXT range's vertices is already in flight
-// into its second stage buffer, and the ticket after that has been drawn.
-//
-// Dependencies are counters in a small control block: a copy item of instance i waits until all walk items of i have
-// reported (walk_done[i]); a walk item of instance i waits until the copy-out of instance i - ring has released the slot
-// (copy_done).  An item only ever waits for items with SMALLER tickets, and a ticket is drawn by a warp that is already
-// running and works its tickets in order, so the lowest unfinished ticket never waits: no deadlock, whatever the number
-// of resident CTAs (no cooperative launch needed).  delay < ring keeps that true for the slot reuse.  Waits spin with a
+// Waiting: a copier waits for walk items with smaller tickets (running CTAs); a walk CTA of instance i waits for the
+// copiers of instance i - ring, which are running CTAs waiting for running CTAs.  Nothing waits for a ticket that has
+// not been drawn, so there is no deadlock whatever the order in which the hardware starts CTAs.  Waits spin with a
 // bound and trap.  The verdict of the fire-and-forget `red` walk (samples added == byte sum, see SinkPacked8Brick) is
-// taken by the warp that finishes an instance's last copy item.  The control block of the NEXT call is zeroed here (two
-// blocks alternate), so a frame is exactly one launch (+ the repair kernel's look at the flags).
+// taken by an instance's last copier.  The control block of the NEXT call is zeroed here (two blocks alternate), so a
+// frame is one launch (+ the repair kernel's look at the flags).
+// (Two persistent forms were built and measured first -- CTA-wide and warp-wide items drawn from one ordered queue with
+// the copy-out as queue items: 1.27 ms and 2.1 ms per crowd frame against 1.19 ms for separate kernels; they spent their
+// time at CTA barriers, in fences and spinning on dependencies whose tickets sat in other warps' look-ahead,
+// profiles/r02_b_*, r02_d_*.)
 // ---------------------------------------------------------------------------
 constexpr uint32_t kFrameStatSlots = 32;
-constexpr uint32_t kFrameCopyBricks = 256;                      // bricks per copy item: 8 per lane
-constexpr uint32_t kFrameIndexedSegs = 256;                     // segments per walk item of an indexed instance: 8 per lane
-#ifndef VKHR_FRAME_MIN_CTAS
-#define VKHR_FRAME_MIN_CTAS 4
-#endif
+constexpr uint32_t kFrameIndexedSegs = 2048;                    // segments per walk item of an indexed instance
 struct FrameCtl {
     uint32_t ticket;
     uint32_t pad[31];
@@ -467,152 +463,139 @@ struct FrameCtl {
 };
 struct FramePlan {
     uint32_t n;                                                 // instances of this launch
-    uint32_t ring, delay;                                       // scratch slots; copy-out of p - delay follows the walk of p
-    uint32_t total;                                             // items
-    uint32_t copy_items;                                        // per instance (one resolution per batch)
+    uint32_t ring;                                              // scratch slots
+    uint32_t copiers;                                           // CTAs that copy an instance out (the last ones to finish its walk)
+    uint32_t total;                                             // items = CTAs
     uint32_t n_bricks;
-    uint32_t phase_start[kMaxBatch + 2];                        // first ticket of phase p (n + delay phases)
+    uint32_t item_start[kMaxBatch + 1];                         // first ticket of instance p (instances without segments get ONE item: their copy-out)
     uint8_t* ring_base;
     unsigned long long slot_bytes;
     FrameCtl* ctl;
     FrameCtl* ctl_next;
 };
-struct FrameWarpSmem {                                          // one per warp
-    float stage[2][kStageFloats];
-    unsigned long long bar[2];
-};
 
-// lane 0 waits until *p >= need (acquire), then the warp reconverges
+// thread 0 waits until *p >= need (acquire), then the CTA meets at a barrier
 __device__ __forceinline__ void frame_wait_ge(const uint32_t* p, uint32_t need) {
-    if ((threadIdx.x & 31u) == 0u) {
+    if (threadIdx.x == 0) {
         uint32_t v;
         for (uint32_t spin = 0;; ++spin) {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
             if (v >= need) break;
-            __nanosleep(200);
+            __nanosleep(100);
             if (spin > (1u << 23)) __trap();                       // a lost dependency must fail, not hang the device
         }
     }
-    __syncwarp();
+    __syncthreads();
 }
 
 template <int MODE, int EXACT>
-__global__ void __launch_bounds__(kWalkThreads, VKHR_FRAME_MIN_CTAS)
+__global__ void __launch_bounds__(kWalkThreads, VKHR_WALK_MIN_CTAS)
 k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
-    extern __shared__ __align__(128) unsigned char s_frame_raw[];
-    FrameWarpSmem& S = reinterpret_cast<FrameWarpSmem*>(s_frame_raw)[threadIdx.x >> 5];
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t bar0 = smem_u32(&S.bar[0]), bar1 = smem_u32(&S.bar[1]);
-    if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar1, 1); }
+    __shared__ __align__(128) float s_stage[kWarpsPerBlock][kStageFloats];
+    __shared__ __align__(8) unsigned long long s_bar[kWarpsPerBlock];
+    __shared__ uint32_t s_item[2];
+    __shared__ unsigned long long s_sum[kWarpsPerBlock];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t bar = smem_u32(&s_bar[warp]);
+    if (lane == 0) mbar_init(bar, 1);
     FrameCtl* const ctl = P.ctl;
-    if (blockIdx.x == gridDim.x - 1) {                             // the next call's control block (nobody uses it during this call)
+    if (threadIdx.x == 0) {
+        // items start in ticket order, whatever order the hardware starts CTAs in
+        const uint32_t t = atomicAdd(&ctl->ticket, 1u);
+        uint32_t lo = 0, hi = P.n;
+        while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (P.item_start[mid] <= t) lo = mid; else hi = mid; }
+        s_item[0] = lo; s_item[1] = t - P.item_start[lo];
+    }
+    __syncthreads();
+    // (REDUX writes a uniform register: the instance's constants then come from the constant bank, as in k_walk_uniform
+    // where the instance is blockIdx.y)
+    const uint32_t i = __reduce_max_sync(kFullWarp, s_item[0]), local = __reduce_max_sync(kFullWarp, s_item[1]);
+    if (i == 0 && local == 0) {                                    // the next call's control block (nobody uses it during this call)
         uint4* z = reinterpret_cast<uint4*>(P.ctl_next);
-        for (uint32_t i = threadIdx.x; i < sizeof(FrameCtl) / 16u; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+        for (uint32_t k = threadIdx.x; k < sizeof(FrameCtl) / 16u; k += blockDim.x) z[k] = make_uint4(0, 0, 0, 0);
     }
-    __syncwarp();
-    uint32_t parity0 = 0, parity1 = 0;
+    const InstanceDev& I = B.inst[i];
+    const uint32_t items = max(I.n_tiles, 1u);                     // CTAs of this instance
+    uint8_t* const slot = P.ring_base + (unsigned long long)(i % P.ring) * P.slot_bytes;
+    if (i >= P.ring) frame_wait_ge(&ctl->copy_done[i - P.ring], min(max(B.inst[i - P.ring].n_tiles, 1u), P.copiers));   // the slot's previous tenant is out
 
-    // an item: its phase (= instance for a walk item) and its index within the phase, resolved from the ticket by lane 0
-    // and broadcast with REDUX -- the result lives in a uniform register, so the instance's constants come straight from
-    // the constant bank as in k_walk_uniform, where the instance is blockIdx.y
-    auto draw = [&]() -> uint32_t {                                // returns the ticket on every lane
-        uint32_t t = 0;
-        if (lane == 0) t = atomicAdd(&ctl->ticket, 1u);
-        return __reduce_max_sync(kFullWarp, t);
-    };
-    auto resolve = [&](uint32_t t, uint32_t& phase, uint32_t& local) {
-        uint32_t lo = 0;
-        if (lane == 0) {
-            uint32_t hi = P.n + P.delay;
-            while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (P.phase_start[mid] <= t) lo = mid; else hi = mid; }
-        }
-        phase = __reduce_max_sync(kFullWarp, lo);
-        local = t - P.phase_start[phase];
-    };
-    // is (phase, local) a walk item of a uniform instance?  (then its vertices can be requested ahead of time)
-    auto walk_items = [&](uint32_t phase) -> uint32_t { return phase < P.n ? B.inst[phase].n_tiles : 0u; };
-
-    uint32_t t_cur = draw(), t_nxt = draw();
-    uint32_t ph_cur = 0, lc_cur = 0, ph_nxt = 0, lc_nxt = 0;
-    bool bulk_cur = false, bulk_nxt = false;
-    uint32_t buf = 0;                                              // stage buffer of the current item
-    if (t_cur < P.total) {
-        resolve(t_cur, ph_cur, lc_cur);
-        if (lc_cur < walk_items(ph_cur) && B.inst[ph_cur].kind == WK_UNIFORM) bulk_cur = stage_range(B.inst[ph_cur], lc_cur, S.stage[0], bar0);
-    }
-    while (t_cur < P.total) {
-        // ---- one item ahead: resolve the next ticket, request its vertices into the other buffer, draw the ticket after it
-        if (t_nxt < P.total) {
-            resolve(t_nxt, ph_nxt, lc_nxt);
-            bulk_nxt = false;
-            if (lc_nxt < walk_items(ph_nxt) && B.inst[ph_nxt].kind == WK_UNIFORM)
-                bulk_nxt = stage_range(B.inst[ph_nxt], lc_nxt, S.stage[buf ^ 1u], buf ? bar0 : bar1);
-        }
-        const uint32_t t_after = draw();
-
-        const uint32_t wn = walk_items(ph_cur);
-        if (lc_cur < wn) {
-            // ---- walk item lc_cur of instance ph_cur -------------------------------------------------------------
-            const uint32_t i = ph_cur;
-            const InstanceDev& I = B.inst[i];
-            if (i >= P.ring) frame_wait_ge(&ctl->copy_done[i - P.ring], P.copy_items);      // the slot's previous tenant has been copied out
-            auto sink = SinkOf<MODE>::make(I);
-            sink.words = reinterpret_cast<uint32_t*>(P.ring_base + (unsigned long long)(i % P.ring) * P.slot_bytes);
-            sink.words_pin();
+    // ---- the walk item ---------------------------------------------------------------------------------------
+    {
+        auto sink = SinkOf<MODE>::make(I);
+        sink.words = reinterpret_cast<uint32_t*>(slot);
+        sink.words_pin();
+        if (local < I.n_tiles) {
             if (I.kind == WK_UNIFORM) {
-                if (buf) walk_range<EXACT>(I, lc_cur, S.stage[1], bar1, bulk_cur, parity1, sink);
-                else     walk_range<EXACT>(I, lc_cur, S.stage[0], bar0, bulk_cur, parity0, sink);
+                uint32_t parity = 0;
+                const uint32_t range = local * kWarpsPerBlock + warp;
+                const bool bulk = stage_range(I, range, s_stage[warp], bar);
+                walk_range<EXACT>(I, range, s_stage[warp], bar, bulk, parity, sink);
             } else {
-                for (uint32_t j = 0; j < kFrameIndexedSegs / 32u; ++j)
-                    walk_indexed_lane<EXACT>(I, ((uint64_t)lc_cur * (kFrameIndexedSegs / 32u) + j) * 32u + lane, sink);
-            }
-            const uint32_t added = __reduce_add_sync(kFullWarp, sink.added);
-            if (lane == 0 && added) atomicAdd(&ctl->added[i][t_cur & (kFrameStatSlots - 1u)], (unsigned long long)added);
-            __threadfence();                                       // every lane's reds (and the count) are performed before the item reports
-            __syncwarp();
-            if (lane == 0) atomicAdd(&ctl->walk_done[i], 1u);
-        } else {
-            // ---- copy-out item of instance ph_cur - delay: brick order -> the x-fastest output volume ------------
-            const uint32_t i = ph_cur - P.delay, c = lc_cur - wn;
-            const InstanceDev& I = B.inst[i];
-            frame_wait_ge(&ctl->walk_done[i], I.n_tiles);
-            const uint32_t wrow = I.grid.W >> 2, byn = I.grid.H >> 2;             // words (= bricks) per row, brick rows per slab
-            const uint32_t wslab = wrow * I.grid.H;
-            uint4* __restrict__ src = reinterpret_cast<uint4*>(P.ring_base + (unsigned long long)(i % P.ring) * P.slot_bytes);
-            uint32_t* __restrict__ dst = reinterpret_cast<uint32_t*>(I.densities);
-            const uint4 z = make_uint4(0, 0, 0, 0);
-            uint32_t bytes = 0;                                                   // at most 8 x 8160
-            const uint32_t b_end = min((c + 1u) * kFrameCopyBricks, P.n_bricks);
-#pragma unroll 2
-            for (uint32_t b = c * kFrameCopyBricks + lane; b < b_end; b += 32u) {
-                const uint4 q0 = __ldcg(src + 2u * b), q1 = __ldcg(src + 2u * b + 1u);   // L2 is where the reds landed; L1 may be stale
-                bytes += __vsadu4(q0.x, 0u) + __vsadu4(q0.y, 0u) + __vsadu4(q0.z, 0u) + __vsadu4(q0.w, 0u) +
-                         __vsadu4(q1.x, 0u) + __vsadu4(q1.y, 0u) + __vsadu4(q1.z, 0u) + __vsadu4(q1.w, 0u);
-                const uint32_t bx = b % wrow, tt = b / wrow, by = tt % byn, bz = tt / byn;
-                uint32_t* o = dst + (size_t)(2u * bz) * wslab + (size_t)(4u * by) * wrow + bx;
-                __stcs(o, q0.x); __stcs(o + wrow, q0.y); __stcs(o + 2u * wrow, q0.z); __stcs(o + 3u * wrow, q0.w);
-                o += wslab;
-                __stcs(o, q1.x); __stcs(o + wrow, q1.y); __stcs(o + 2u * wrow, q1.z); __stcs(o + 3u * wrow, q1.w);
-                if ((q0.x | q0.y | q0.z | q0.w | q1.x | q1.y | q1.z | q1.w) != 0u) { __stcg(src + 2u * b, z); __stcg(src + 2u * b + 1u, z); }
-            }
-            const uint32_t wsum = __reduce_add_sync(kFullWarp, bytes);
-            if (lane == 0 && wsum) atomicAdd(&ctl->bytes[i][t_cur & (kFrameStatSlots - 1u)], (unsigned long long)wsum);
-            __threadfence();                                       // the zeros are in place before the slot is released
-            __syncwarp();
-            uint32_t last = 0;
-            if (lane == 0) last = (atomicAdd(&ctl->copy_done[i], 1u) == P.copy_items - 1u) ? 1u : 0u;
-            if (__reduce_max_sync(kFullWarp, last)) {
-                // the instance is complete: samples added != byte sum of the volume means some byte carried (more than
-                // 255 hits in a voxel) -> flag 2, k_repair_packed recounts the instance in u32
-                __threadfence();
-                unsigned long long a = *(volatile unsigned long long*)&ctl->added[i][lane], y = *(volatile unsigned long long*)&ctl->bytes[i][lane];
-                for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(kFullWarp, a, o); y += __shfl_down_sync(kFullWarp, y, o); }
-                if (lane == 0) *I.ovf_flag = (a != y) ? 2u : 0u;
+                for (uint32_t j = 0; j < kFrameIndexedSegs / kWalkThreads; ++j)
+                    walk_indexed_lane<EXACT>(I, ((uint64_t)local * (kFrameIndexedSegs / kWalkThreads) + j) * kWalkThreads + threadIdx.x, sink);
             }
         }
-        t_cur = t_nxt; ph_cur = ph_nxt; lc_cur = lc_nxt; bulk_cur = bulk_nxt;
-        t_nxt = t_after;
-        buf ^= 1u;
+        const uint32_t added = __reduce_add_sync(kFullWarp, sink.added);
+        if (lane == 0) s_sum[warp] = added;
+    }
+    __threadfence();                                               // this thread's reds are performed before the item reports
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long sum = 0;
+        for (uint32_t w = 0; w < kWarpsPerBlock; ++w) sum += s_sum[w];
+        if (sum) atomicAdd(&ctl->added[i][blockIdx.x & (kFrameStatSlots - 1u)], sum);
+        __threadfence();
+        s_item[0] = atomicAdd(&ctl->walk_done[i], 1u);             // how many items of the instance had reported before this one
+    }
+    __syncthreads();
+    const uint32_t order = __reduce_max_sync(kFullWarp, s_item[0]);
+    const uint32_t copiers = min(items, P.copiers);
+    if (order + copiers < items) return;                           // not among the last `copiers` to finish: done
+
+    // ---- copier `c` of the instance: brick order -> the x-fastest output volume, zeroing behind itself --------
+    const uint32_t c = order - (items - copiers);
+    frame_wait_ge(&ctl->walk_done[i], items);                      // the few items still running (all have started)
+    {
+        const uint32_t wrow = I.grid.W >> 2, byn = I.grid.H >> 2;  // words (= bricks) per row, brick rows per slab
+        const uint32_t wslab = wrow * I.grid.H;
+        uint4* __restrict__ src = reinterpret_cast<uint4*>(slot);
+        uint32_t* __restrict__ dst = reinterpret_cast<uint32_t*>(I.densities);
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        uint32_t bytes = 0;                                        // < 2^32: at most 8160 per brick, n_bricks / (copiers * 256) bricks per thread
+        const uint32_t per = (P.n_bricks + copiers - 1u) / copiers;
+        const uint32_t b_end = min((c + 1u) * per, P.n_bricks);
+#pragma unroll 4
+        for (uint32_t b = c * per + threadIdx.x; b < b_end; b += kWalkThreads) {
+            const uint4 q0 = __ldcg(src + 2u * b), q1 = __ldcg(src + 2u * b + 1u);   // L2 is where the reds landed; L1 may be stale
+            bytes += __vsadu4(q0.x, 0u) + __vsadu4(q0.y, 0u) + __vsadu4(q0.z, 0u) + __vsadu4(q0.w, 0u) +
+                     __vsadu4(q1.x, 0u) + __vsadu4(q1.y, 0u) + __vsadu4(q1.z, 0u) + __vsadu4(q1.w, 0u);
+            const uint32_t bx = b % wrow, tt = b / wrow, by = tt % byn, bz = tt / byn;
+            uint32_t* o = dst + (size_t)(2u * bz) * wslab + (size_t)(4u * by) * wrow + bx;
+            __stcs(o, q0.x); __stcs(o + wrow, q0.y); __stcs(o + 2u * wrow, q0.z); __stcs(o + 3u * wrow, q0.w);
+            o += wslab;
+            __stcs(o, q1.x); __stcs(o + wrow, q1.y); __stcs(o + 2u * wrow, q1.z); __stcs(o + 3u * wrow, q1.w);
+            if ((q0.x | q0.y | q0.z | q0.w | q1.x | q1.y | q1.z | q1.w) != 0u) { __stcg(src + 2u * b, z); __stcg(src + 2u * b + 1u, z); }
+        }
+        const unsigned long long lo16 = __reduce_add_sync(kFullWarp, bytes & 0xFFFFu), hi16 = __reduce_add_sync(kFullWarp, bytes >> 16);
+        if (lane == 0) s_sum[warp] = lo16 + (hi16 << 16);
+    }
+    __threadfence();                                               // the zeros are in place before the slot is released
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long sum = 0;
+        for (uint32_t w = 0; w < kWarpsPerBlock; ++w) sum += s_sum[w];
+        if (sum) atomicAdd(&ctl->bytes[i][c & (kFrameStatSlots - 1u)], sum);
+        __threadfence();
+        s_item[1] = (atomicAdd(&ctl->copy_done[i], 1u) == copiers - 1u) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_item[1] && warp == 0) {
+        // the instance is complete: samples added != byte sum of the volume means some byte carried (more than 255 hits
+        // in a voxel) -> flag 2, k_repair_packed recounts the instance in u32
+        __threadfence();
+        unsigned long long a = *(volatile unsigned long long*)&ctl->added[i][lane], y = *(volatile unsigned long long*)&ctl->bytes[i][lane];
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(kFullWarp, a, o); y += __shfl_down_sync(kFullWarp, y, o); }
+        if (lane == 0) *I.ovf_flag = (a != y) ? 2u : 0u;
     }
 }
 
@@ -934,6 +917,35 @@ k_combine_peer_u8_sparse(const __grid_constant__ PeerPtrsSparse P, uint64_t off1
         for (uint32_t r = 0; r < kMaxPeers; ++r)
             if (r < P.n) __stcg(P.out[r] + c, acc);
     }
+}
+
+// Device-side barrier of the ranks of a strand-sharded voxelisation, over peer memory: every rank owns a signal pad
+// (kMaxPeers words per slot) mapped into all ranks; rank r stores the call's epoch into word [slot][r] of EVERY pad and
+// then waits until all words of its own pad have reached the epoch.  One CTA; the stream order of the launching rank puts
+// everything it wrote before the barrier (partial volume, chunk bitmap, zeroed output) ahead of the signal
+// (__threadfence_system), and the waiting rank's later kernels behind the acquire.  Epochs only grow: no reset, no ABA.
+struct PeerSignals {
+    uint32_t* pad[kMaxPeers];
+    uint32_t n, rank;
+};
+__global__ void __launch_bounds__(32)
+k_peer_barrier(const __grid_constant__ PeerSignals S, uint32_t slot, uint32_t epoch) {
+    const uint32_t r = threadIdx.x;
+    __threadfence_system();
+    if (r < S.n) {
+        uint32_t* remote = S.pad[r] + slot * kMaxPeers + S.rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+        const uint32_t* mine = S.pad[S.rank] + slot * kMaxPeers + r;
+        uint32_t v;
+        for (uint32_t spin = 0;; ++spin) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+            if ((int32_t)(v - epoch) >= 0) break;
+            __nanosleep(200);
+            if (spin > (1u << 24)) __trap();                       // a rank that never arrives must fail, not hang the device
+        }
+    }
+    __syncwarp();
+    __threadfence_system();
 }
 
 // Same for an output grid that is not 16-byte aligned (a view into a caller's buffer): one voxel per thread.

@@ -147,9 +147,9 @@ struct vkhr_b200_ctx {
     uint32_t last_strategy = 0;   // VKHR_B200_STRATEGY_* of the last run_voxelize
     DevBuf brick;         // BRICK8 scratch volumes (brick order); all zero between calls up to brick_clean_bytes
     size_t brick_clean_bytes = 0;
+    uint32_t shard_epoch = 0;     // barriers of the sharded entry point pair up by call count
     DevBuf frame_ctl;     // two FrameCtl blocks of the frame kernel (they alternate; each call zeroes the next call's)
     uint64_t frame_calls = 0;
-    int frame_blocks[2] = {0, 0};                 // resident CTAs of k_frame<3,3> / <4,4> (occupancy x SMs)
     size_t ring_budget = size_t(48) << 20;        // bytes of BRICK8 scratch the frame kernel keeps in flight (L2-resident ring)
     DevBuf small;         // lohi[2] + aabb keys[6] + aabb floats[6]
     DevBuf tacc;          // tangent mode: 16-byte accumulator per voxel
@@ -361,8 +361,7 @@ BatchPlan fill_batch(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool verti
             // warp-tiles of kTileStride vertices, kTilesPerWarp per warp, kWarpsPerBlock warps per CTA
             const uint64_t warp_tiles = ((uint64_t)jobs[k].n_vertices + kTileStride - 1) / kTileStride;
             const uint64_t per_cta = (uint64_t)kWarpsPerBlock * kTilesPerWarp;
-            I.n_tiles = frame ? (uint32_t)((warp_tiles + kTilesPerWarp - 1) / kTilesPerWarp)      // the frame kernel's items are warp-ranges
-                              : (uint32_t)((warp_tiles + per_cta - 1) / per_cta);
+            I.n_tiles = (uint32_t)((warp_tiles + per_cta - 1) / per_cta);
         } else {
             const uint64_t items = (kind == WK_INDEXED) ? jobs[k].n_segments : jobs[k].n_vertices;
             const uint64_t per_item = frame ? kFrameIndexedSegs : kWalkThreads;     // the frame kernel's walk items are larger
@@ -441,7 +440,10 @@ int launch_repair(vkhr_b200_ctx* ctx, uint32_t* scratch, cudaStream_t s) {
         int per_sm = 0;
         CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_repair_packed<VERTICES>, kWalkThreads, 0));
         if (per_sm < 1) return fail(ctx, VKHR_B200_ERR_CUDA, "repair kernel does not fit on an SM");
-        blocks = per_sm * ctx->sm_count;
+        // one CTA slot per SM is left free: a cooperative grid only starts when ALL its CTAs fit at once, and a small kernel
+        // of another stream that is waiting for this one's stream (the device-side barrier of a sharded call on the same
+        // device) must not be able to keep it out for ever
+        blocks = std::max(per_sm - 1, 1) * ctx->sm_count;
     }
     void* args[] = {(void*)&ctx->batch, (void*)&scratch};
     CU_CHECK(ctx, cudaLaunchCooperativeKernel((void*)k_repair_packed<VERTICES>, dim3(blocks), dim3(kWalkThreads), args, 0, s));
@@ -455,7 +457,6 @@ int run_frame(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool small, cudaS
     const uint64_t nv = jobs[0].grid.n_voxels;
     uint32_t ring = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(ctx->ring_budget / nv, 1), 8);
     ring = std::min(ring, std::min(n, kMaxBatch));
-    const uint32_t delay = ring >= 2u ? 1u : 0u;                   // delay < ring: a walk never waits for a later ticket
     const size_t need = (size_t)ring * nv;
     if (need > ctx->brick.cap) ctx->brick_clean_bytes = 0;         // reserve() reallocates: contents undefined
     RET_IF(reserve(ctx, ctx->brick, need));
@@ -476,34 +477,21 @@ int run_frame(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool small, cudaS
     RET_IF(reserve(ctx, ctx->counts, std::min<uint64_t>(nv, kRepairChunk) * 4));   // the repair's chunk scratch
     ctx->counts_clean_bytes = 0;
     uint32_t* base = static_cast<uint32_t*>(ctx->bitmap.p);
-    constexpr size_t kFrameSmem = kWarpsPerBlock * sizeof(FrameWarpSmem);
-    int& blocks = ctx->frame_blocks[small ? 0 : 1];
-    if (blocks == 0) {
-        int per_sm = 0;
-        if (small) {
-            CU_CHECK(ctx, cudaFuncSetAttribute(k_frame<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFrameSmem));
-            CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame<3, 3>, kWalkThreads, kFrameSmem));
-        } else {
-            CU_CHECK(ctx, cudaFuncSetAttribute(k_frame<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFrameSmem));
-            CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame<4, 4>, kWalkThreads, kFrameSmem));
-        }
-        if (per_sm < 1) return fail(ctx, VKHR_B200_ERR_CUDA, "frame kernel does not fit on an SM");
-        blocks = per_sm * ctx->sm_count;
-    }
     for (uint32_t first = 0; first < n; first += chunk) {
         const uint32_t m = std::min(chunk, n - first);
         fill_batch(ctx, jobs + first, m, false, true);
         FramePlan P{};
-        P.n = m; P.ring = std::min(ring, m); P.delay = P.ring >= 2u ? delay : 0u;
+        P.n = m; P.ring = std::min(ring, m);
+        // copiers: few while other instances keep the machine busy (they hold CTA slots while they wait and copy), many
+        // when the copy-out is the tail of the call
+        P.copiers = m >= 4 ? 64u : 256u;
         P.n_bricks = (uint32_t)(nv / 32);
-        P.copy_items = (P.n_bricks + kFrameCopyBricks - 1) / kFrameCopyBricks;
         uint32_t t = 0;
-        for (uint32_t p = 0; p < m + P.delay; ++p) {
-            P.phase_start[p] = t;
-            if (p < m) t += ctx->batch.inst[p].n_tiles;
-            if (p >= P.delay) t += P.copy_items;
+        for (uint32_t p = 0; p < m; ++p) {
+            P.item_start[p] = t;
+            t += std::max(ctx->batch.inst[p].n_tiles, 1u);         // an instance without segments still needs its (empty) volume written
         }
-        P.phase_start[m + P.delay] = t;
+        P.item_start[m] = t;
         P.total = t;
         P.ring_base = static_cast<uint8_t*>(ctx->brick.p);
         P.slot_bytes = nv;
@@ -516,11 +504,10 @@ int run_frame(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool small, cudaS
             ctx->batch.inst[k].ovf_bitmap = base + (size_t)k * (bm_words + kHdr) + kHdr;
             ctx->batch.inst[k].counts = static_cast<uint32_t*>(ctx->counts.p);
         }
-        const unsigned grid = (unsigned)std::min<uint32_t>((P.total + kWarpsPerBlock - 1) / kWarpsPerBlock, (uint32_t)blocks);
         {
             PhaseMark mk(ctx, s, PH_WALK);
-            if (small) k_frame<3, 3><<<grid, kWalkThreads, kFrameSmem, s>>>(ctx->batch, P);
-            else       k_frame<4, 4><<<grid, kWalkThreads, kFrameSmem, s>>>(ctx->batch, P);
+            if (small) k_frame<3, 3><<<P.total, kWalkThreads, 0, s>>>(ctx->batch, P);
+            else       k_frame<4, 4><<<P.total, kWalkThreads, 0, s>>>(ctx->batch, P);
             ctx->launches++;
             CU_CHECK(ctx, cudaGetLastError());
         }
@@ -1041,6 +1028,57 @@ int vkhr_b200_combine_peer_u8_sparse_dev(vkhr_b200_ctx* ctx, const void* const* 
     k_combine_peer_u8_sparse<<<stride_blocks(ctx, slab_bytes / 16, 256, 8), 256, 0, s>>>(P, slab_offset_bytes / 16, slab_bytes / 16);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
+    return VKHR_B200_OK;
+}
+
+uint64_t vkhr_b200_sharded_volume_bytes(uint32_t W, uint32_t H, uint32_t D, uint32_t world) {
+    const uint64_t nv = (uint64_t)W * H * D, q = 512ull * (world ? world : 1u);
+    return (nv + q - 1) / q * q;
+}
+
+int vkhr_b200_voxelize_segments_sharded_dev(vkhr_b200_ctx* ctx, const float* d_vertices, uint32_t n_vertices,
+                                            const uint32_t* d_indices, uint64_t n_indices, uint32_t segs_per_strand,
+                                            const float aabb_origin[3], const float aabb_size[3],
+                                            uint32_t W, uint32_t H, uint32_t D, uint32_t flags,
+                                            const vkhr_b200_shard_peers* peers, void* stream) {
+    RET_IF(bind(ctx));
+    if (!peers || !peers->partials || !peers->bitmaps || !peers->outs || !peers->signals)
+        return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "null peer description");
+    const uint32_t world = peers->world, rank = peers->rank;
+    if (world == 0 || world > kMaxPeers || rank >= world)
+        return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "1.." + std::to_string(kMaxPeers) + " ranks, rank < world");
+    for (uint32_t r = 0; r < world; ++r)
+        if (!peers->partials[r] || !peers->bitmaps[r] || !peers->outs[r] || !peers->signals[r] ||
+            (reinterpret_cast<uintptr_t>(peers->partials[r]) & 15u) || (reinterpret_cast<uintptr_t>(peers->outs[r]) & 15u) ||
+            (reinterpret_cast<uintptr_t>(peers->bitmaps[r]) & 3u) || (reinterpret_cast<uintptr_t>(peers->signals[r]) & 3u))
+            return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "peer buffers must be non-null and aligned (volumes 16 bytes, words 4)");
+    GridParams g;
+    RET_IF(make_grid(ctx, aabb_origin, aabb_size, W, H, D, flags, g));
+    const uint64_t nv = g.n_voxels, nvp = vkhr_b200_sharded_volume_bytes(W, H, D, world), slab = nvp / world;
+    cudaStream_t s = pick(ctx, stream);
+    uint8_t* partial = static_cast<uint8_t*>(peers->partials[rank]);
+    uint8_t* out = static_cast<uint8_t*>(peers->outs[rank]);
+    // 1. this rank's shard -> its saturated u8 partial (the ordinary single-GPU voxelisation; the pad stays zero)
+    const bool empty = n_vertices == 0 || (d_indices && n_indices < 2);
+    if (empty) CU_CHECK(ctx, cudaMemsetAsync(partial, 0, nv, s));
+    else RET_IF(vkhr_b200_voxelize_segments_dev(ctx, d_vertices, n_vertices, d_indices, n_indices, segs_per_strand, nullptr, aabb_origin,
+                                                aabb_size, W, H, D, flags & ~(uint32_t)VKHR_B200_NORMALIZE, partial, nullptr, s));
+    // 2. which 16-byte chunks of it hold anything; the output starts from zero (peers store only non-zero results)
+    RET_IF(vkhr_b200_chunk_bitmap_dev(ctx, partial, nvp, static_cast<uint32_t*>(peers->bitmaps[rank]), s));
+    CU_CHECK(ctx, cudaMemsetAsync(out, 0, nvp, s));
+    // 3. barrier, combine my slab from all partials into all outputs, barrier
+    PeerSignals S{};
+    S.n = world; S.rank = rank;
+    for (uint32_t r = 0; r < world; ++r) S.pad[r] = static_cast<uint32_t*>(peers->signals[r]);
+    const uint32_t epoch = ++ctx->shard_epoch;
+    k_peer_barrier<<<1, 32, 0, s>>>(S, 0u, epoch);
+    ctx->launches++;
+    RET_IF(vkhr_b200_combine_peer_u8_sparse_dev(ctx, reinterpret_cast<const void* const*>(peers->partials),
+                                                reinterpret_cast<const void* const*>(peers->bitmaps), peers->outs, world, (uint64_t)rank * slab, slab, s));
+    k_peer_barrier<<<1, 32, 0, s>>>(S, 1u, epoch);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    if (flags & VKHR_B200_NORMALIZE) RET_IF(vkhr_b200_normalize_dev(ctx, out, nv, s));
     return VKHR_B200_OK;
 }
 

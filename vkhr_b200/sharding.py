@@ -201,8 +201,8 @@ class ShardedVoxelizer:
         return vol
 
     def _symmetric(self, nvp, dev):
-        """(partial, bitmap, out, partial handle, bitmap handle, out handle) in symmetric memory for a padded grid of nvp
-        bytes; allocated and exchanged once per grid size."""
+        """(partial, bitmap, out, signals and their handles) in symmetric memory for a padded grid of nvp bytes; allocated
+        and exchanged once per grid size."""
         import torch
         import torch.distributed._symmetric_memory as symm_mem
         cached = getattr(self, "_symm", None)
@@ -211,32 +211,28 @@ class ShardedVoxelizer:
             partial = symm_mem.empty(nvp, dtype=torch.uint8, device=dev)
             bitmap = symm_mem.empty(nvp // 512, dtype=torch.int32, device=dev)
             outbuf = symm_mem.empty(nvp, dtype=torch.uint8, device=dev)
-            hp, hb, ho = (symm_mem.rendezvous(t, group) for t in (partial, bitmap, outbuf))
+            signals = symm_mem.empty(2 * 16, dtype=torch.int32, device=dev)
+            hp, hb, ho, hs = (symm_mem.rendezvous(t, group) for t in (partial, bitmap, outbuf, signals))
             partial.zero_()
-            self._symm = cached = (nvp, partial, bitmap, outbuf, hp, hb, ho)
+            signals.zero_()
+            torch.cuda.synchronize()
+            self.dist.barrier(group=self.group)                 # every rank's pads are zero before anyone signals
+            self._symm = cached = (nvp, partial, bitmap, outbuf, signals, hp, hb, ho, hs)
         return cached[1:]
 
     def _voxelize_p2p(self, mode, vertices, indices, segs, origin, size, W, H, D, flags, out):
-        import torch
+        """ONE C-ABI call per rank (vkhr_b200_voxelize_segments_sharded_dev): shard -> u8 partial, chunk bitmap, device-side
+        barrier over the signal pads, the fused sparse peer-memory combine, second barrier."""
         if self.vox is None:
             raise RuntimeError("the p2p schedule needs the CUDA library and NVLink peer access")
+        if mode != "segments":
+            raise ValueError("the p2p schedule voxelises segments")
         nv = W * H * D
-        q = 512 * self.world                               # whole bitmap words (32 chunks of 16 bytes) per slab
-        nvp = (nv + q - 1) // q * q
-        partial, bitmap, outbuf, hp, hb, ho = self._symmetric(nvp, vertices.device)
-        if vertices.numel():
-            self._partial(mode, vertices, indices, segs, origin, size, W, H, D, partial[:nv], flags & 1)
-        else:
-            partial.zero_()
-        self.vox.chunk_bitmap_dev(partial, bitmap)         # which 16-byte chunks of my partial hold anything
-        outbuf.zero_()                                     # peers only send non-zero results
-        slab = nvp // self.world
-        hp.barrier(channel=0)                              # partials, bitmaps and zeroed outputs are complete and visible
-        self.vox.combine_peer_u8_sparse_dev(hp.buffer_ptrs, hb.buffer_ptrs, ho.buffer_ptrs, self.rank * slab, slab)
-        ho.barrier(channel=0)                              # every slab has been stored into this rank's output
+        nvp = self.vox.sharded_volume_bytes(W, H, D, self.world)
+        partial, bitmap, outbuf, signals, hp, hb, ho, hs = self._symmetric(nvp, vertices.device)
+        self.vox.voxelize_segments_sharded_dev(vertices, indices, origin, size, W, H, D, self.rank, hp.buffer_ptrs, hb.buffer_ptrs,
+                                               ho.buffer_ptrs, hs.buffer_ptrs, segs_per_strand=segs, flags=flags & 3)
         vol = outbuf[:nv]
-        if flags & 2:
-            self.vox.normalize_dev(vol)
         if out is not None:
             if out.numel() < nv:
                 raise ValueError("out is too small")

@@ -411,6 +411,34 @@ class Voxelizer:
         capi.check(self._h, lib.vkhr_b200_combine_peer_u8_sparse_dev(self._h, pa, ba, oa, n, int(slab_offset), int(slab_bytes),
                                                                      self._torch_stream(stream)))
 
+    @staticmethod
+    def sharded_volume_bytes(W, H, D, world) -> int:
+        return int(lib.vkhr_b200_sharded_volume_bytes(int(W), int(H), int(D), int(world)))
+
+    def voxelize_segments_sharded_dev(self, vertices, indices, aabb_origin, aabb_size, W, H, D, rank, partial_ptrs, bitmap_ptrs,
+                                      out_ptrs, signal_ptrs, segs_per_strand: int = 0, flags: int = 0, stream=None) -> None:
+        """This rank's part of a strand-sharded ``voxelize_segments`` (``vkhr_b200_voxelize_segments_sharded_dev``):
+        ``*_ptrs`` are the device addresses of every rank's partial / bitmap / output / signal buffers as mapped into this
+        process.  On return (stream-ordered) the complete volume is in ``out_ptrs[rank]``."""
+        import torch
+        n_v = 0
+        vp = None
+        if vertices is not None and vertices.numel():
+            self._check_dev(vertices, torch.float32, "vertices")
+            n_v, vp = vertices.numel() // 3, C.c_void_p(vertices.data_ptr())
+        if indices is not None:
+            self._check_dev(indices, torch.int32, "indices")
+        world = len(partial_ptrs)
+        if not (world == len(bitmap_ptrs) == len(out_ptrs) == len(signal_ptrs)):
+            raise ValueError("one partial, bitmap, output and signal pointer per rank")
+        arr = lambda ptrs: (C.c_void_p * world)(*[int(p) for p in ptrs])   # noqa: E731
+        pa, ba, oa, sa = arr(partial_ptrs), arr(bitmap_ptrs), arr(out_ptrs), arr(signal_ptrs)
+        peers = capi.ShardPeers(int(rank), world, pa, ba, oa, sa)
+        capi.check(self._h, lib.vkhr_b200_voxelize_segments_sharded_dev(
+            self._h, vp, n_v, None if indices is None else C.c_void_p(indices.data_ptr()), 0 if indices is None else indices.numel(),
+            int(segs_per_strand), capi.vec3(aabb_origin), capi.vec3(aabb_size), int(W), int(H), int(D), int(flags),
+            C.byref(peers), self._torch_stream(stream)))
+
     def normalize_dev(self, densities, stream=None):
         import torch
         self._check_dev(densities, torch.uint8, "densities")
