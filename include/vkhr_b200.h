@@ -335,7 +335,8 @@ typedef struct vkhr_b200_prefilter_params {
 } vkhr_b200_prefilter_params;
 enum {
     VKHR_B200_PREFILTER_GENERIC = 1u << 0,   /* force the untiled kernel (testing) */
-    VKHR_B200_PREFILTER_ROWWISE = 1u << 1    /* tiled kernel: one AO evaluation per voxel instead of the register-tiled z column (testing, A/B timing) */
+    VKHR_B200_PREFILTER_ROWWISE = 1u << 1,   /* tiled kernel: one AO evaluation per voxel instead of the register-tiled z column (testing, A/B timing) */
+    VKHR_B200_PREFILTER_DENSE = 1u << 2      /* tiled kernel: load every tile, without the occupancy pre-pass that skips tiles of empty space (testing, A/B timing) */
 };
 
 VKHR_B200_API void vkhr_b200_prefilter_defaults(vkhr_b200_prefilter_params* params);

@@ -138,6 +138,31 @@ def test_prefilter_full_size_device_path(vox, port):
     assert torch.all(ao[~occ] == 1.0)
 
 
+@pytest.mark.parametrize("res", [(128, 64, 48), (64, 64, 64), (96, 40, 24)])
+def test_sparse_volumes_skip_empty_tiles_bit_identically(vox, res):
+    """The occupancy pre-pass of the tiled kernel (cells of 32 x 8 x 8 voxels -> one activity byte per tile): tiles whose box
+    holds no hair are never loaded and get the constants of empty space.  Mostly empty volumes with hair in a few places
+    (a corner, a face, one voxel, a thin sheet) must come out bit-identical to the dense form (every tile loaded) and to
+    the generic kernel, for AO, opacity and a Gaussian whose halo is wider than the AO's."""
+    W, H, D = res
+    rng = np.random.default_rng(W + 3 * H)
+    vols = []
+    d = np.zeros((D, H, W), np.uint8); d[0, 0, 0] = 200; d[D - 1, H - 1, W - 1] = 7; vols.append(d)
+    d = np.zeros((D, H, W), np.uint8); d[D // 2, H // 3, 5:W - 9] = rng.integers(1, 255, W - 14); vols.append(d)
+    d = np.zeros((D, H, W), np.uint8); d[7:9, :, 31:33] = 255; d[15:17, 8, :] = 3; vols.append(d)           # straddles cell / tile faces
+    d = np.zeros((D, H, W), np.uint8); vols.append(d)                                                        # nothing at all
+    d = (rng.random((D, H, W)) < 0.0005).astype(np.uint8) * 90; vols.append(d)
+    for k, d in enumerate(vols):
+        d = d.reshape(-1)
+        kw = dict(ao=True, opacity=True, gauss=True, gauss_width=9.0)
+        got = vox.prefilter(d, W, H, D, **kw)
+        dense = vox.prefilter(d, W, H, D, flags=capi.PREFILTER_DENSE, **kw)
+        gen = vox.prefilter(d, W, H, D, flags=capi.PREFILTER_GENERIC, **kw)
+        for name in ("ao", "opacity", "gauss"):
+            assert np.array_equal(got[name], dense[name]), (k, name, "sparse vs dense")
+            assert np.array_equal(got[name], gen[name]), (k, name, "tiled vs generic")
+
+
 # ---- volumetric ADSM transmittance volume (approximate_deep_shadows.glsl:24-36 at every voxel centre) ----------------
 @pytest.mark.parametrize("res", [(32, 32, 32), (48, 20, 12), (7, 5, 3), (4, 4, 4)])
 @pytest.mark.parametrize("light", [(30.0, 80.0, 20.0), (-15.0, 3.0, 2.0), (2.0, 2.5, 1.0), (1e4, -2e4, 5e3)])

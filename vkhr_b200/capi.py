@@ -83,6 +83,7 @@ class PrefilterParams(C.Structure):
 
 PREFILTER_GENERIC = 1 << 0
 PREFILTER_ROWWISE = 1 << 1
+PREFILTER_DENSE = 1 << 2
 
 
 class AdsmParams(C.Structure):

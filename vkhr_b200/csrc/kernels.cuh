@@ -453,6 +453,10 @@ k_walk_indexed(const __grid_constant__ Batch B, uint32_t first) {
 // ---------------------------------------------------------------------------
 constexpr uint32_t kFrameStatSlots = 32;
 constexpr uint32_t kFrameIndexedSegs = 2048;                    // segments per walk item of an indexed instance
+#ifndef VKHR_FRAME_RANGES
+#define VKHR_FRAME_RANGES 2
+#endif
+constexpr uint32_t kFrameRanges = VKHR_FRAME_RANGES;            // warp-ranges a warp walks per item: the item's fixed costs (ticket, report, fence) are paid once
 struct FrameCtl {
     uint32_t ticket;
     uint32_t pad[31];
@@ -527,9 +531,12 @@ k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
         if (local < I.n_tiles) {
             if (I.kind == WK_UNIFORM) {
                 uint32_t parity = 0;
-                const uint32_t range = local * kWarpsPerBlock + warp;
-                const bool bulk = stage_range(I, range, s_stage[warp], bar);
-                walk_range<EXACT>(I, range, s_stage[warp], bar, bulk, parity, sink);
+                for (uint32_t rr = 0; rr < kFrameRanges; ++rr) {
+                    const uint32_t range = (local * kFrameRanges + rr) * kWarpsPerBlock + warp;
+                    const bool bulk = stage_range(I, range, s_stage[warp], bar);
+                    walk_range<EXACT>(I, range, s_stage[warp], bar, bulk, parity, sink);
+                    __syncwarp();
+                }
             } else {
                 for (uint32_t j = 0; j < kFrameIndexedSegs / kWalkThreads; ++j)
                     walk_indexed_lane<EXACT>(I, ((uint64_t)local * (kFrameIndexedSegs / kWalkThreads) + j) * kWalkThreads + threadIdx.x, sink);
@@ -538,12 +545,13 @@ k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
         const uint32_t added = __reduce_add_sync(kFullWarp, sink.added);
         if (lane == 0) s_sum[warp] = added;
     }
-    __threadfence();                                               // this thread's reds are performed before the item reports
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned long long sum = 0;
         for (uint32_t w = 0; w < kWarpsPerBlock; ++w) sum += s_sum[w];
         if (sum) atomicAdd(&ctl->added[i][blockIdx.x & (kFrameStatSlots - 1u)], sum);
+        // release: the fence is cumulative over everything that happens-before it -- the reds of all threads of the CTA
+        // are ordered before it by the barrier -- so the observer that acquires the counter sees them
         __threadfence();
         s_item[0] = atomicAdd(&ctl->walk_done[i], 1u);             // how many items of the instance had reported before this one
     }

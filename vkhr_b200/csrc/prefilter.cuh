@@ -46,6 +46,7 @@ struct PrefilterArgs {
     int g_range;               // (kernel_width - 1) / 2
     float g_sigma2;
     uint32_t tiles_x, tiles_y, tiles_z;
+    const uint8_t* tile_active; // one byte per tile (k_pf_tile_active): 0 = the tile and its halo hold no hair -> constants, no load; or nullptr
 };
 
 // ---- the arithmetic, shared by the tiled and the generic kernel ---------------------------------------------
@@ -284,6 +285,47 @@ __device__ __forceinline__ float opacity_of(const PrefilterArgs& A, uint32_t d) 
 }
 
 #ifndef VKHR_PF_TILED_ONLY      // the non-template kernels live in ONE translation unit (vkhr_b200.cu)
+// ---- occupancy pre-pass of the tiled kernel ------------------------------------------------------------------
+// Cells of 32 x 8 x 8 voxels (a quarter or half of a tile): occ[cell] = 1 when any voxel of the cell is non-zero.  One
+// warp per cell, four 16-byte loads per lane (W % 16 == 0 on the tiled path).  Reads the volume once: N^3 bytes.
+constexpr int kPfCellX = 32, kPfCellY = 8, kPfCellZ = 8;
+__global__ void __launch_bounds__(256)
+k_pf_cell_occupancy(const uint8_t* __restrict__ dens, int W, int H, int D, int cx, int cy, int cz, uint8_t* __restrict__ occ) {
+    const uint32_t n_cells = (uint32_t)cx * cy * cz;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); cell < n_cells; cell += gridDim.x * (blockDim.x >> 5)) {
+        const int x0 = (int)(cell % cx) * kPfCellX, y0 = (int)((cell / cx) % cy) * kPfCellY, z0 = (int)(cell / ((uint32_t)cx * cy)) * kPfCellZ;
+        uint32_t any = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int chunk = (int)lane + 32 * k;                               // 128 chunks: 64 rows x 2 halves
+            const int X = x0 + 16 * (chunk & 1), Y = y0 + ((chunk >> 1) & 7), Z = z0 + (chunk >> 4);
+            if (X < W && Y < H && Z < D) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(dens + (size_t)X + (size_t)Y * W + (size_t)Z * W * H));
+                any |= q.x | q.y | q.z | q.w;
+            }
+        }
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, any != 0u);
+        if (lane == 0) occ[cell] = b ? 1 : 0;
+    }
+}
+// active[tile] = 1 when a cell overlapping the tile's box (tile + halo, halo <= 8) is occupied.  One thread per tile.
+__global__ void __launch_bounds__(256)
+k_pf_tile_active(const uint8_t* __restrict__ occ, int cx, int cy, int cz, uint32_t tiles_x, uint32_t tiles_y, uint32_t tiles_z, int tz,
+                 uint8_t* __restrict__ active) {
+    const uint32_t n = tiles_x * tiles_y * tiles_z;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int tx = (int)(t % tiles_x), ty = (int)((t / tiles_x) % tiles_y), tzi = (int)(t / (tiles_x * tiles_y));
+    // tiles are kPfTX x kPfTY x tz voxels = 1 x 1 x (tz / 8) cells
+    const int zc0 = tzi * (tz / kPfCellZ) - 1, zc1 = (tzi + 1) * (tz / kPfCellZ);
+    uint32_t any = 0;
+    for (int z = max(zc0, 0); z <= min(zc1, cz - 1); ++z)
+        for (int y = max(ty - 1, 0); y <= min(ty + 1, cy - 1); ++y)
+            for (int x = max(tx - 1, 0); x <= min(tx + 1, cx - 1); ++x) any |= occ[((size_t)z * cy + y) * cx + x];
+    active[t] = any ? 1 : 0;
+}
+
 // ---- generic kernel: any grid size / alignment / radius; one thread per voxel, texels straight from global ----
 __global__ void __launch_bounds__(256)
 k_prefilter_generic(const __grid_constant__ PrefilterArgs A) {
@@ -409,20 +451,52 @@ k_prefilter_tiled(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     const float ao_empty = lao_at(A, [](int, int, int) -> float { return 0.0f; });
     __syncthreads();
     const float g_total = A.gauss ? gauss_total(A, gw) : 1.0f;
-    if (blockIdx.x < n_tiles && tid == 0) issue(blockIdx.x, 0);
+    // Sparse volumes (a 1024^3 hair volume is 99.5 % empty): tiles whose box (tile + halo) lies in empty occupancy cells
+    // are never loaded -- they get the constants of empty space straight away (k_pf_cell_occupancy / k_pf_tile_active).
+    auto is_active = [&](uint32_t t) -> bool { return !A.tile_active || A.tile_active[t] != 0; };
+    // the constants of empty space for one tile
+    auto fill_empty = [&](int x0, int y0, int z0) {
+        float* outs[3] = {A.ao, A.opacity, A.gauss};
+        const float vals[3] = {ao_empty, A.opacity ? oplut[0] : 0.0f, 0.0f};
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+            float* out = outs[o];
+            if (!out) continue;
+            const bool vec = (reinterpret_cast<uintptr_t>(out) & 15u) == 0u;
+            const float4 v4 = make_float4(vals[o], vals[o], vals[o], vals[o]);
+            for (int q = tid; q < (kPfTX / 4) * kPfTY * TZ; q += kPfThreads) {
+                const int X = x0 + 4 * (q % (kPfTX / 4)), Y = y0 + (q / (kPfTX / 4)) % kPfTY, Z = z0 + q / ((kPfTX / 4) * kPfTY);
+                if (Y >= A.H || Z >= A.D || X >= A.W) continue;
+                float* dst = out + ((size_t)X + (size_t)Y * A.W + (size_t)Z * A.W * A.H);
+                if (vec && X + 3 < A.W) __stcs(reinterpret_cast<float4*>(dst), v4);
+                else for (int e = 0; e < 4 && X + e < A.W; ++e) __stcs(dst + e, vals[o]);
+            }
+        }
+    };
+    bool act_cur = blockIdx.x < n_tiles && is_active(blockIdx.x);
+    if (act_cur && tid == 0) issue(blockIdx.x, 0);
 
-    uint32_t it = 0;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const uint32_t buf = it & 1u;
-        if (tid == 0 && tile + gridDim.x < n_tiles) issue(tile + gridDim.x, buf ^ 1u);   // prefetch the next tile
-        pf_mbar_wait(bar0 + 8u * buf, (it >> 1) & 1u);
-        const unsigned char* stage = pf_smem + buf * P.stage_bytes;
+    uint32_t na = 0;                                       // loaded tiles consumed so far: the next one arrives in buffer na & 1
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const bool act = act_cur;
+        const bool act_nxt = tile + gridDim.x < n_tiles && is_active(tile + gridDim.x);
+        act_cur = act_nxt;
         int x0, y0, z0;
         tile_origin(tile, x0, y0, z0);
+        if (!act) {
+            // (buffer na & 1 was last read two loaded tiles ago, with CTA barriers since)
+            if (tid == 0 && act_nxt) issue(tile + gridDim.x, na & 1u);
+            fill_empty(x0, y0, z0);
+            continue;
+        }
+        const uint32_t buf = na & 1u;
+        if (tid == 0 && act_nxt) issue(tile + gridDim.x, buf ^ 1u);   // prefetch the next tile
+        pf_mbar_wait(bar0 + 8u * buf, (na >> 1) & 1u);
+        ++na;
+        const unsigned char* stage = pf_smem + buf * P.stage_bytes;
 
         // ---- empty space: a staged box (tile + halo) without a single hair writes the constants of empty space ----
-        // (most tiles of a hair volume at 512^3 and above; the barrier below also orders every thread's last read of
-        // this stage buffer before thread 0 re-arms it at the top of the next iteration)
+        // (the barrier below also orders every thread's last read of this stage buffer before thread 0 re-arms it)
         {
             int nz = 0;
             const uint4* s16 = reinterpret_cast<const uint4*>(stage);
@@ -431,22 +505,7 @@ k_prefilter_tiled(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                 nz |= (int)((q.x | q.y | q.z | q.w) != 0u);
             }
             if (!__syncthreads_or(nz)) {
-                float* outs[3] = {A.ao, A.opacity, A.gauss};
-                const float vals[3] = {ao_empty, A.opacity ? oplut[0] : 0.0f, 0.0f};
-#pragma unroll
-                for (int o = 0; o < 3; ++o) {
-                    float* out = outs[o];
-                    if (!out) continue;
-                    const bool vec = (reinterpret_cast<uintptr_t>(out) & 15u) == 0u;
-                    const float4 v4 = make_float4(vals[o], vals[o], vals[o], vals[o]);
-                    for (int q = tid; q < (kPfTX / 4) * kPfTY * TZ; q += kPfThreads) {
-                        const int X = x0 + 4 * (q % (kPfTX / 4)), Y = y0 + (q / (kPfTX / 4)) % kPfTY, Z = z0 + q / ((kPfTX / 4) * kPfTY);
-                        if (Y >= A.H || Z >= A.D || X >= A.W) continue;
-                        float* dst = out + ((size_t)X + (size_t)Y * A.W + (size_t)Z * A.W * A.H);
-                        if (vec && X + 3 < A.W) __stcs(reinterpret_cast<float4*>(dst), v4);
-                        else for (int e = 0; e < 4 && X + e < A.W; ++e) __stcs(dst + e, vals[o]);
-                    }
-                }
+                fill_empty(x0, y0, z0);
                 continue;
             }
         }

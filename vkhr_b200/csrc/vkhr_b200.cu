@@ -150,7 +150,7 @@ struct vkhr_b200_ctx {
     uint32_t shard_epoch = 0;     // barriers of the sharded entry point pair up by call count
     DevBuf frame_ctl;     // two FrameCtl blocks of the frame kernel (they alternate; each call zeroes the next call's)
     uint64_t frame_calls = 0;
-    size_t ring_budget = size_t(48) << 20;        // bytes of BRICK8 scratch the frame kernel keeps in flight (L2-resident ring)
+    size_t ring_budget = size_t(64) << 20;        // bytes of BRICK8 scratch the frame kernel keeps in flight (L2-resident ring)
     DevBuf small;         // lohi[2] + aabb keys[6] + aabb floats[6]
     DevBuf tacc;          // tangent mode: 16-byte accumulator per voxel
     size_t tacc_clean_bytes = 0;     // leading bytes of `tacc` known to be zero
@@ -161,6 +161,7 @@ struct vkhr_b200_ctx {
     Slot slots[kSlots];
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     int repair_blocks[2] = {0, 0};
+    DevBuf pf_occ;                // prefilter: occupancy cells + tile activity bytes
     DevBuf adsm_occ;              // ADSM coarse occupancy bits
     DevBuf adsm_table;            // the ADSM march's accumulated t sequence for `adsm_steps`
     float adsm_steps = 0.0f;
@@ -361,7 +362,8 @@ BatchPlan fill_batch(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool verti
             // warp-tiles of kTileStride vertices, kTilesPerWarp per warp, kWarpsPerBlock warps per CTA
             const uint64_t warp_tiles = ((uint64_t)jobs[k].n_vertices + kTileStride - 1) / kTileStride;
             const uint64_t per_cta = (uint64_t)kWarpsPerBlock * kTilesPerWarp;
-            I.n_tiles = (uint32_t)((warp_tiles + per_cta - 1) / per_cta);
+            const uint64_t per_item = frame ? per_cta * kFrameRanges : per_cta;            // the frame kernel's items hold several ranges per warp
+            I.n_tiles = (uint32_t)((warp_tiles + per_item - 1) / per_item);
         } else {
             const uint64_t items = (kind == WK_INDEXED) ? jobs[k].n_segments : jobs[k].n_vertices;
             const uint64_t per_item = frame ? kFrameIndexedSegs : kWalkThreads;     // the frame kernel's walk items are larger
@@ -794,7 +796,7 @@ void vkhr_b200_destroy(vkhr_b200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->counts, &ctx->bitmap, &ctx->brick, &ctx->frame_ctl, &ctx->small, &ctx->tacc, &ctx->adsm_table, &ctx->adsm_occ, &ctx->st_vertices,
+    DevBuf* bufs[] = {&ctx->counts, &ctx->bitmap, &ctx->brick, &ctx->frame_ctl, &ctx->small, &ctx->tacc, &ctx->adsm_table, &ctx->adsm_occ, &ctx->pf_occ, &ctx->st_vertices,
                       &ctx->st_indices, &ctx->st_tangents, &ctx->st_dens, &ctx->st_tang_out};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (auto& sl : ctx->slots) {
@@ -1468,6 +1470,18 @@ int vkhr_b200_prefilter_dev(vkhr_b200_ctx* ctx, const uint8_t* d_densities, uint
     CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPfThreads, plan.total));
     if (per_sm < 1) return fail(ctx, VKHR_B200_ERR_CUDA, "prefilter kernel does not fit on an SM");
     const uint64_t n_tiles = (uint64_t)A.tiles_x * A.tiles_y * A.tiles_z;
+    // occupancy pre-pass: which tiles (with their halo) hold any hair at all -- the others are never loaded
+    if (!(P.flags & VKHR_B200_PREFILTER_DENSE)) {
+        const int cx = (int)((W + kPfCellX - 1) / kPfCellX), cy = (int)((H + kPfCellY - 1) / kPfCellY), cz = (int)((D + kPfCellZ - 1) / kPfCellZ);
+        const size_t n_cells = (size_t)cx * cy * cz, occ_bytes = (n_cells + 255) & ~size_t(255);
+        RET_IF(reserve(ctx, ctx->pf_occ, occ_bytes + n_tiles));
+        uint8_t* occ = static_cast<uint8_t*>(ctx->pf_occ.p);
+        uint8_t* active = occ + occ_bytes;
+        k_pf_cell_occupancy<<<stride_blocks(ctx, n_cells, 8, 16), 256, 0, s>>>(d_densities, (int)W, (int)H, (int)D, cx, cy, cz, occ);
+        k_pf_tile_active<<<(unsigned)((n_tiles + 255) / 256), 256, 0, s>>>(occ, cx, cy, cz, A.tiles_x, A.tiles_y, A.tiles_z, tz, active);
+        ctx->launches += 2;
+        A.tile_active = active;
+    }
     const unsigned blocks = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)per_sm * ctx->sm_count);
     kernel<<<blocks, kPfThreads, plan.total, s>>>(tmap, A);
     ctx->launches++;
