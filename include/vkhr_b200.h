@@ -308,6 +308,10 @@ VKHR_B200_API int vkhr_b200_generate_bounding_box_dev(vkhr_b200_ctx* ctx, const 
 VKHR_B200_API int vkhr_b200_generate_bounding_box(vkhr_b200_ctx* ctx, const float* vertices,
     uint32_t n_vertices, float aabb_out[6]);
 
+/* Volume::save (hair_style.cc:359-369): the raw u8 densities, no header, to `path` (host memory in, host file out).
+ * Returns VKHR_B200_OK, or VKHR_B200_ERR_INVALID_ARGUMENT when the file cannot be written (the reference returns false). */
+VKHR_B200_API int vkhr_b200_volume_save(const char* path, const uint8_t* densities, uint64_t n_voxels);
+
 /* ---- density -> AO / opacity / Gaussian prefilter -------------------------- *
  * What the reference's fragment shaders derive from the density volume at every
  * shaded point, precomputed once per voxel centre into float32 W*H*D volumes

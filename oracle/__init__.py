@@ -327,6 +327,12 @@ class _Ref:
             raise RuntimeError("vkhr_ref_create failed")
         return RefHairStyle(self.lib, h)
 
+    def volume_save(self, densities, path) -> bool:
+        """``HairStyle::Volume::save`` of the unmodified reference (hair_style.cc:359-369)."""
+        d = np.ascontiguousarray(densities, dtype=np.uint8).reshape(-1)
+        self.lib.vkhr_ref_volume_save.argtypes = [_u8p, C.c_uint64, C.c_char_p]
+        return bool(self.lib.vkhr_ref_volume_save(_ptr(d, _u8p), C.c_uint64(d.size), path.encode()))
+
     def load(self, path):
         h = self.lib.vkhr_ref_load(path.encode())
         if not h:

@@ -161,6 +161,13 @@ double vkhr_ref_voxelize(void* h, int mode, uint64_t W, uint64_t H, uint64_t D,
     return t1 - t0;
 }
 
+// HairStyle::Volume::save (:359-369): raw dump of the densities.  Returns 1 on success like the reference's bool.
+int vkhr_ref_volume_save(const uint8_t* densities, uint64_t n, const char* path) {
+    vkhr::HairStyle::Volume v{};
+    v.densities.assign(densities, densities + n);
+    return v.save(path) ? 1 : 0;
+}
+
 void vkhr_ref_normalize(uint8_t* densities, uint64_t n) {
     vkhr::HairStyle::Volume v{};
     v.densities.assign(densities, densities + n);

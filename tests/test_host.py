@@ -240,3 +240,20 @@ def test_byte_sum_equals_sample_count_iff_no_byte_carried():
         counts = np.bincount(vox, minlength=4 * n_words)
         assert (byte_sum == n_adds) == bool((counts <= 255).all()), (trial, byte_sum, n_adds, counts.max())
         assert byte_sum <= n_adds
+
+
+def test_volume_save_writes_what_the_reference_writes(tmp_path, ref):
+    """Volume::save (hair_style.cc:359-369) through the C ABI and the Python mirror: the same bytes on disk as the
+    unmodified reference's Volume::save, and False (not an exception) for a path that cannot be written."""
+    from vkhr_b200.hair_style import AABB, Volume
+    rng = np.random.default_rng(2)
+    d = rng.integers(0, 256, 24 * 16 * 8, dtype=np.uint8)
+    ours, theirs = str(tmp_path / "ours.raw"), str(tmp_path / "ref.raw")
+    vol = Volume(resolution=np.array([24.0, 16.0, 8.0], np.float32), bounds=AABB(np.zeros(3, np.float32), 1.0, np.ones(3, np.float32), 1.0),
+                 densities=d)
+    assert vol.save(ours) is True
+    assert ref.volume_save(d, theirs) is True
+    assert open(ours, "rb").read() == open(theirs, "rb").read() == d.tobytes()
+    assert vol.save(str(tmp_path / "no_such_dir" / "x.raw")) is False
+    assert ref.volume_save(d, str(tmp_path / "no_such_dir" / "x.raw")) is False
+    assert capi.lib.vkhr_b200_volume_save(None, None, 0) == capi.ERR_INVALID_ARGUMENT

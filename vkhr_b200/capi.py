@@ -150,6 +150,7 @@ _PROTOTYPES = {
     "vkhr_b200_generate_bounding_box_dev": (_int, [c_ctx, _P, _u32, _P, _P]),
     "vkhr_b200_generate_bounding_box": (_int, [c_ctx, _P, _u32, C.c_float * 6]),
     "vkhr_b200_profile_read_ex": (_int, [c_ctx, C.POINTER(C.c_double), C.POINTER(C.c_uint32), _u32]),
+    "vkhr_b200_volume_save": (_int, [C.c_char_p, _P, _u64]),
     "vkhr_b200_prefilter_defaults": (None, [C.POINTER(PrefilterParams)]),
     "vkhr_b200_prefilter_dev": (_int, [c_ctx, _P, _u32, _u32, _u32, C.POINTER(PrefilterParams), _P, _P, _P, _P]),
     "vkhr_b200_prefilter": (_int, [c_ctx, _P, _u32, _u32, _u32, C.POINTER(PrefilterParams), _P, _P, _P]),

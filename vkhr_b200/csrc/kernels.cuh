@@ -427,60 +427,63 @@ k_walk_indexed(const __grid_constant__ Batch B, uint32_t first) {
 }
 
 // ---------------------------------------------------------------------------
-// The frame kernel: BRICK8 walk AND copy-out of a whole batch in ONE launch.
+// The frame kernel: BRICK8 walk AND copy-out of a whole batch in ONE launch, warp-autonomous (no CTA barrier).
 //
-// A CTA is one walk item, exactly as in k_walk_uniform (8 warp-ranges of 8 tiles; 2048 segments of an indexed
-// instance) -- except that it takes its item from a ticket counter, so items START in ticket order: instance 0's
-// first, then instance 1's, ...  When a CTA has walked its item it reports to its instance's counter, and the LAST
-// `copiers` CTAs to report for an instance stay on: they wait for the few items of that instance that are still
-// running (all of them have started: their tickets are smaller), and then copy the instance's scratch volume out to the
-// caller's x-fastest volume, 1 / copiers of the bricks each, zeroing behind themselves -- while every other CTA slot
-// of the machine is already walking the next instances.  The walk is bound by its instructions, the copy-out by
-// memory: side by side they fill both.  Instance i counts in scratch slot i mod `ring`; the in-flight window of the
-// machine is less than one instance, so a ring of 3 slots (48 MiB at 256^3) is never waited for and stays resident in
-// the 126 MB L2: the walk's reds, the copy-out's reads and the zeros behind it do not travel to HBM.
+// The grid is k_walk_uniform's: blockIdx.y = instance, blockIdx.x = walk item (8 warp-ranges of 8 tiles, kFrameRanges of
+// them in a row; 2048 segments of an indexed instance), so instances START in order.  Every warp walks its ranges,
+// adds its sample count to the instance's statistics, fences and reports to the instance's counter -- on its own; nothing
+// waits for the slowest warp of a CTA.  The warps of an instance's LAST `copiers` CTAs stay on: they wait until every
+// warp of the instance has reported (they were the last to start, so few are still running) and then copy the
+// instance's scratch volume out to the caller's x-fastest volume, an equal share of the bricks each, zeroing behind
+// themselves -- while every other CTA slot of the machine is already walking the next instances.  The walk is bound by
+// its instructions, the copy-out by memory: side by side they fill both.  Instance i counts in scratch slot i mod
+// `ring`; a ring of four slots (64 MiB at 256^3) covers the window of instances in flight and stays largely resident
+// in the 126 MB L2, so the walk's reds, the copy-out's reads and the zeros behind it mostly stay off HBM.
 //
-// Waiting: a copier waits for walk items with smaller tickets (running CTAs); a walk CTA of instance i waits for the
-// copiers of instance i - ring, which are running CTAs waiting for running CTAs.  Nothing waits for a ticket that has
-// not been drawn, so there is no deadlock whatever the order in which the hardware starts CTAs.  Waits spin with a
-// bound and trap.  The verdict of the fire-and-forget `red` walk (samples added == byte sum, see SinkPacked8Brick) is
-// taken by an instance's last copier.  The control block of the NEXT call is zeroed here (two blocks alternate), so a
-// frame is one launch (+ the repair kernel's look at the flags).
-// (Two persistent forms were built and measured first -- CTA-wide and warp-wide items drawn from one ordered queue with
-// the copy-out as queue items: 1.27 ms and 2.1 ms per crowd frame against 1.19 ms for separate kernels; they spent their
-// time at CTA barriers, in fences and spinning on dependencies whose tickets sat in other warps' look-ahead,
-// profiles/r02_b_*, r02_d_*.)
+// Waiting: a copier warp waits for warps of its own instance (CTAs with smaller or equal block indices); a walk warp
+// of instance i waits (behind its vertex copy, already in flight) for the copiers of instance i - ring (smaller block
+// indices).  CTAs are dispatched in increasing linear block index (the order every spin-on-the-previous-block scheme
+// relies on -- serial split-K semaphores, decoupled look-back with block-index tickets), so whatever is waited for is
+// resident and running.  Waits are bounded: a lost dependency traps instead of hanging the device.  The verdict of the
+// fire-and-forget `red` walk (samples added == byte sum, see SinkPacked8Brick) is taken by an instance's last copier warp.
+// The control block of the NEXT call is zeroed here (two blocks alternate), so a frame is one launch (+ the repair
+// kernel's look at the flags).
+//
+// Three other forms were built and measured first (crowd frame, ms; separate kernels: 1.19): persistent CTAs drawing
+// CTA-wide items from one ordered ticket queue with the copy-out as queue items 1.27; the same with autonomous warps and
+// one item of look-ahead 2.1 (the tickets parked in look-ahead were the dependencies other warps span on); ticketed
+// one-item CTAs whose last finishers copy out 1.14-1.5 (a fifth of all warp-time at the barrier behind the ticket).
+// profiles/r02_b_*, r02_d_*, r02_e_*, r02_f_*.
 // ---------------------------------------------------------------------------
 constexpr uint32_t kFrameStatSlots = 32;
 constexpr uint32_t kFrameIndexedSegs = 2048;                    // segments per walk item of an indexed instance
 #ifndef VKHR_FRAME_RANGES
 #define VKHR_FRAME_RANGES 2
 #endif
-constexpr uint32_t kFrameRanges = VKHR_FRAME_RANGES;            // warp-ranges a warp walks per item: the item's fixed costs (ticket, report, fence) are paid once
+#ifndef VKHR_FRAME_MIN_CTAS
+#define VKHR_FRAME_MIN_CTAS 4
+#endif
+constexpr uint32_t kFrameRanges = VKHR_FRAME_RANGES;            // warp-ranges a warp walks per item: the item's fixed costs (fence, report) are paid once
 struct FrameCtl {
-    uint32_t ticket;
-    uint32_t pad[31];
-    uint32_t walk_done[kMaxBatch];
-    uint32_t copy_done[kMaxBatch];
+    uint32_t walk_done[kMaxBatch];                              // warps of the instance that have reported
+    uint32_t copy_done[kMaxBatch];                              // copier warps of the instance that have finished
     unsigned long long added[kMaxBatch][kFrameStatSlots];       // samples the walk added, slotted
     unsigned long long bytes[kMaxBatch][kFrameStatSlots];       // byte sums the copy-out read, slotted
 };
 struct FramePlan {
-    uint32_t n;                                                 // instances of this launch
     uint32_t ring;                                              // scratch slots
-    uint32_t copiers;                                           // CTAs that copy an instance out (the last ones to finish its walk)
-    uint32_t total;                                             // items = CTAs
+    uint32_t copiers;                                           // CTAs of an instance whose warps copy it out (the last ones by block index)
     uint32_t n_bricks;
-    uint32_t item_start[kMaxBatch + 1];                         // first ticket of instance p (instances without segments get ONE item: their copy-out)
+    uint32_t pad;
     uint8_t* ring_base;
     unsigned long long slot_bytes;
     FrameCtl* ctl;
     FrameCtl* ctl_next;
 };
 
-// thread 0 waits until *p >= need (acquire), then the CTA meets at a barrier
+// lane 0 waits until *p >= need (acquire), then the warp reconverges
 __device__ __forceinline__ void frame_wait_ge(const uint32_t* p, uint32_t need) {
-    if (threadIdx.x == 0) {
+    if ((threadIdx.x & 31u) == 0u) {
         uint32_t v;
         for (uint32_t spin = 0;; ++spin) {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -489,91 +492,82 @@ __device__ __forceinline__ void frame_wait_ge(const uint32_t* p, uint32_t need) 
             if (spin > (1u << 23)) __trap();                       // a lost dependency must fail, not hang the device
         }
     }
-    __syncthreads();
+    __syncwarp();
 }
 
 template <int MODE, int EXACT>
-__global__ void __launch_bounds__(kWalkThreads, VKHR_WALK_MIN_CTAS)
+__global__ void __launch_bounds__(kWalkThreads, VKHR_FRAME_MIN_CTAS)
 k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
     __shared__ __align__(128) float s_stage[kWarpsPerBlock][kStageFloats];
     __shared__ __align__(8) unsigned long long s_bar[kWarpsPerBlock];
-    __shared__ uint32_t s_item[2];
-    __shared__ unsigned long long s_sum[kWarpsPerBlock];
+    const uint32_t i = blockIdx.y;
+    const InstanceDev& I = B.inst[i];
+    const uint32_t items = max(I.n_tiles, 1u);                     // CTAs of this instance (one for an instance without segments: its copy-out)
+    if (blockIdx.x >= items) return;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t bar = smem_u32(&s_bar[warp]);
     if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
     FrameCtl* const ctl = P.ctl;
-    if (threadIdx.x == 0) {
-        // items start in ticket order, whatever order the hardware starts CTAs in
-        const uint32_t t = atomicAdd(&ctl->ticket, 1u);
-        uint32_t lo = 0, hi = P.n;
-        while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (P.item_start[mid] <= t) lo = mid; else hi = mid; }
-        s_item[0] = lo; s_item[1] = t - P.item_start[lo];
-    }
-    __syncthreads();
-    // (REDUX writes a uniform register: the instance's constants then come from the constant bank, as in k_walk_uniform
-    // where the instance is blockIdx.y)
-    const uint32_t i = __reduce_max_sync(kFullWarp, s_item[0]), local = __reduce_max_sync(kFullWarp, s_item[1]);
-    if (i == 0 && local == 0) {                                    // the next call's control block (nobody uses it during this call)
+    if (i == 0 && blockIdx.x == 0) {                               // the next call's control block (nobody uses it during this call)
         uint4* z = reinterpret_cast<uint4*>(P.ctl_next);
         for (uint32_t k = threadIdx.x; k < sizeof(FrameCtl) / 16u; k += blockDim.x) z[k] = make_uint4(0, 0, 0, 0);
     }
-    const InstanceDev& I = B.inst[i];
-    const uint32_t items = max(I.n_tiles, 1u);                     // CTAs of this instance
     uint8_t* const slot = P.ring_base + (unsigned long long)(i % P.ring) * P.slot_bytes;
-    if (i >= P.ring) frame_wait_ge(&ctl->copy_done[i - P.ring], min(max(B.inst[i - P.ring].n_tiles, 1u), P.copiers));   // the slot's previous tenant is out
+    const uint32_t copiers = min(items, P.copiers);
 
-    // ---- the walk item ---------------------------------------------------------------------------------------
+    // ---- the walk ------------------------------------------------------------------------------------------------
     {
         auto sink = SinkOf<MODE>::make(I);
         sink.words = reinterpret_cast<uint32_t*>(slot);
         sink.words_pin();
-        if (local < I.n_tiles) {
+        uint32_t parity = 0;
+        bool waited = i < P.ring;                                  // the slot's previous tenant: instance i - ring
+        auto wait_for_slot = [&]() {
+            if (!waited) {
+                const uint32_t prev_items = max(B.inst[i - P.ring].n_tiles, 1u);
+                frame_wait_ge(&ctl->copy_done[i - P.ring], min(prev_items, P.copiers) * kWarpsPerBlock);
+                waited = true;
+            }
+        };
+        if (blockIdx.x < I.n_tiles) {
             if (I.kind == WK_UNIFORM) {
-                uint32_t parity = 0;
                 for (uint32_t rr = 0; rr < kFrameRanges; ++rr) {
-                    const uint32_t range = (local * kFrameRanges + rr) * kWarpsPerBlock + warp;
-                    const bool bulk = stage_range(I, range, s_stage[warp], bar);
+                    const uint32_t range = (blockIdx.x * kFrameRanges + rr) * kWarpsPerBlock + warp;
+                    const bool bulk = stage_range(I, range, s_stage[warp], bar);     // the vertices are on their way ...
+                    wait_for_slot();                                                 // ... while the slot is checked
                     walk_range<EXACT>(I, range, s_stage[warp], bar, bulk, parity, sink);
                     __syncwarp();
                 }
             } else {
+                wait_for_slot();
                 for (uint32_t j = 0; j < kFrameIndexedSegs / kWalkThreads; ++j)
-                    walk_indexed_lane<EXACT>(I, ((uint64_t)local * (kFrameIndexedSegs / kWalkThreads) + j) * kWalkThreads + threadIdx.x, sink);
+                    walk_indexed_lane<EXACT>(I, ((uint64_t)blockIdx.x * (kFrameIndexedSegs / kWalkThreads) + j) * kWalkThreads + threadIdx.x, sink);
             }
         }
+        wait_for_slot();                                           // (a copier of an empty item must not zero a slot that is still being copied out)
         const uint32_t added = __reduce_add_sync(kFullWarp, sink.added);
-        if (lane == 0) s_sum[warp] = added;
+        if (lane == 0 && added) atomicAdd(&ctl->added[i][(blockIdx.x * kWarpsPerBlock + warp) & (kFrameStatSlots - 1u)], (unsigned long long)added);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long sum = 0;
-        for (uint32_t w = 0; w < kWarpsPerBlock; ++w) sum += s_sum[w];
-        if (sum) atomicAdd(&ctl->added[i][blockIdx.x & (kFrameStatSlots - 1u)], sum);
-        // release: the fence is cumulative over everything that happens-before it -- the reds of all threads of the CTA
-        // are ordered before it by the barrier -- so the observer that acquires the counter sees them
-        __threadfence();
-        s_item[0] = atomicAdd(&ctl->walk_done[i], 1u);             // how many items of the instance had reported before this one
-    }
-    __syncthreads();
-    const uint32_t order = __reduce_max_sync(kFullWarp, s_item[0]);
-    const uint32_t copiers = min(items, P.copiers);
-    if (order + copiers < items) return;                           // not among the last `copiers` to finish: done
+    __threadfence();                                               // every lane's reds (and the count) are performed before the warp reports
+    __syncwarp();
+    if (lane == 0) atomicAdd(&ctl->walk_done[i], 1u);
+    if (blockIdx.x + copiers < items) return;                      // not one of the instance's last `copiers` CTAs: done
 
-    // ---- copier `c` of the instance: brick order -> the x-fastest output volume, zeroing behind itself --------
-    const uint32_t c = order - (items - copiers);
-    frame_wait_ge(&ctl->walk_done[i], items);                      // the few items still running (all have started)
+    // ---- copier warp c of the instance: brick order -> the x-fastest output volume, zeroing behind itself --------
+    const uint32_t c = (blockIdx.x - (items - copiers)) * kWarpsPerBlock + warp, n_c = copiers * kWarpsPerBlock;
+    frame_wait_ge(&ctl->walk_done[i], items * kWarpsPerBlock);     // the warps still walking (all have started)
+    uint32_t bytes = 0;                                            // < 2^32: at most 8160 per brick
     {
         const uint32_t wrow = I.grid.W >> 2, byn = I.grid.H >> 2;  // words (= bricks) per row, brick rows per slab
         const uint32_t wslab = wrow * I.grid.H;
         uint4* __restrict__ src = reinterpret_cast<uint4*>(slot);
         uint32_t* __restrict__ dst = reinterpret_cast<uint32_t*>(I.densities);
         const uint4 z = make_uint4(0, 0, 0, 0);
-        uint32_t bytes = 0;                                        // < 2^32: at most 8160 per brick, n_bricks / (copiers * 256) bricks per thread
-        const uint32_t per = (P.n_bricks + copiers - 1u) / copiers;
+        const uint32_t per = ((P.n_bricks + n_c - 1u) / n_c + 31u) & ~31u;       // whole warp-rows of 32 bricks
         const uint32_t b_end = min((c + 1u) * per, P.n_bricks);
 #pragma unroll 4
-        for (uint32_t b = c * per + threadIdx.x; b < b_end; b += kWalkThreads) {
+        for (uint32_t b = c * per + lane; b < b_end; b += 32u) {
             const uint4 q0 = __ldcg(src + 2u * b), q1 = __ldcg(src + 2u * b + 1u);   // L2 is where the reds landed; L1 may be stale
             bytes += __vsadu4(q0.x, 0u) + __vsadu4(q0.y, 0u) + __vsadu4(q0.z, 0u) + __vsadu4(q0.w, 0u) +
                      __vsadu4(q1.x, 0u) + __vsadu4(q1.y, 0u) + __vsadu4(q1.z, 0u) + __vsadu4(q1.w, 0u);
@@ -584,20 +578,15 @@ k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
             __stcs(o, q1.x); __stcs(o + wrow, q1.y); __stcs(o + 2u * wrow, q1.z); __stcs(o + 3u * wrow, q1.w);
             if ((q0.x | q0.y | q0.z | q0.w | q1.x | q1.y | q1.z | q1.w) != 0u) { __stcg(src + 2u * b, z); __stcg(src + 2u * b + 1u, z); }
         }
-        const unsigned long long lo16 = __reduce_add_sync(kFullWarp, bytes & 0xFFFFu), hi16 = __reduce_add_sync(kFullWarp, bytes >> 16);
-        if (lane == 0) s_sum[warp] = lo16 + (hi16 << 16);
     }
+    const unsigned long long wsum = (unsigned long long)__reduce_add_sync(kFullWarp, bytes & 0xFFFFu) +
+                                    ((unsigned long long)__reduce_add_sync(kFullWarp, bytes >> 16) << 16);
+    if (lane == 0 && wsum) atomicAdd(&ctl->bytes[i][c & (kFrameStatSlots - 1u)], wsum);
     __threadfence();                                               // the zeros are in place before the slot is released
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long sum = 0;
-        for (uint32_t w = 0; w < kWarpsPerBlock; ++w) sum += s_sum[w];
-        if (sum) atomicAdd(&ctl->bytes[i][c & (kFrameStatSlots - 1u)], sum);
-        __threadfence();
-        s_item[1] = (atomicAdd(&ctl->copy_done[i], 1u) == copiers - 1u) ? 1u : 0u;
-    }
-    __syncthreads();
-    if (s_item[1] && warp == 0) {
+    __syncwarp();
+    uint32_t last = 0;
+    if (lane == 0) last = (atomicAdd(&ctl->copy_done[i], 1u) == n_c - 1u) ? 1u : 0u;
+    if (__reduce_max_sync(kFullWarp, last)) {
         // the instance is complete: samples added != byte sum of the volume means some byte carried (more than 255 hits
         // in a voxel) -> flag 2, k_repair_packed recounts the instance in u32
         __threadfence();
@@ -644,8 +633,13 @@ k_splat_batch(const __grid_constant__ Batch B, uint32_t first) {
 // ---------------------------------------------------------------------------
 constexpr int kTangentScale = 8192;
 
+// Sparse form (bits != nullptr): accumulators exist only for the voxels the density pass found non-empty -- slot of
+// voxel idx = prefix[idx / 32] + popcount of the lower bits of bits[idx / 32] -- so the scratch is 16 bytes per NON-EMPTY
+// voxel (35 MB for a ponytail at 256^3, 83 MB at 1024^3) instead of 16 bytes per voxel (256 MiB / 16 GiB).
 struct SinkTangent {
     unsigned long long* acc;
+    const uint32_t* bits = nullptr;       // one bit per voxel: density != 0
+    const uint32_t* prefix = nullptr;     // non-empty voxels before each 32-voxel word
     unsigned long long w0 = 0, w1 = 0;
     __device__ __forceinline__ void set(float tx, float ty, float tz) {
         auto q = [](float t) { return max(-kTangentScale, min(kTangentScale, __float2int_rn(t * (float)kTangentScale))); };   // NaN -> 0
@@ -655,8 +649,14 @@ struct SinkTangent {
     }
     template <int SLOT = 0>
     __device__ __forceinline__ void put(uint32_t idx) {
-        atomicAdd(acc + 2ull * idx, w0);
-        atomicAdd(acc + 2ull * idx + 1ull, w1);
+        unsigned long long slot = idx;
+        if (bits) {
+            const uint32_t w = idx >> 5, b = __ldg(bits + w);
+            if (!((b >> (idx & 31u)) & 1u)) return;                 // (cannot happen: the density pass counted this very sample)
+            slot = __ldg(prefix + w) + __popc(b & ((1u << (idx & 31u)) - 1u));
+        }
+        atomicAdd(acc + 2ull * slot, w0);
+        atomicAdd(acc + 2ull * slot + 1ull, w1);
     }
     __device__ __forceinline__ void finish() {}
 };
@@ -674,16 +674,18 @@ __device__ __forceinline__ void glm_normalize(float& x, float& y, float& z) {
 template <int KIND, int EXACT>
 __global__ void __launch_bounds__(kWalkThreads)
 k_walk_tangent(const float* __restrict__ vertices, const uint32_t* __restrict__ indices, const float* __restrict__ tangents,
-               uint64_t n_items, uint32_t segs, const __grid_constant__ GridParams g, unsigned long long* __restrict__ acc) {
+               uint64_t n_items, uint32_t n_vertices, uint32_t segs, const __grid_constant__ GridParams g, unsigned long long* __restrict__ acc,
+               const uint32_t* __restrict__ bits, const uint32_t* __restrict__ prefix) {
     const uint64_t s = (uint64_t)blockIdx.x * kWalkThreads + threadIdx.x;
-    const bool active = s < n_items;
+    bool active = s < n_items;
     uint32_t i0 = 0, i1 = 0;
     if (active) {
         if (KIND == WK_SPLAT) i0 = i1 = (uint32_t)s;
         else segment_vertices(KIND == WK_INDEXED ? indices : nullptr, segs, s, i0, i1);
+        if (i0 >= n_vertices || i1 >= n_vertices) active = false;    // an index past the vertex array is dropped, not read
     }
     float ax = 0.f, ay = 0.f, az = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
-    SinkTangent sink{acc};
+    SinkTangent sink{acc, bits, prefix};
     if (active) {
         const float* a = vertices + 3ull * i0;
         ax = __ldg(a); ay = __ldg(a + 1); az = __ldg(a + 2);
@@ -726,6 +728,52 @@ k_finish_tangent(unsigned long long* __restrict__ acc, uint64_t n_voxels, uint8_
         }
         dens[i] = (uint8_t)min(count, 255u);
         if (tang) tang[i] = t;
+    }
+}
+
+__device__ __forceinline__ uint32_t tangent_of(ulonglong2 w) {
+    const uint32_t count = (uint32_t)w.x;
+    if (!count) return 0u;
+    const float fc = (float)count, inv = 1.0f / (float)kTangentScale;
+    const int sx = (int)(uint32_t)(w.x >> 32);
+    const int sy = (int)((uint32_t)w.y - (uint32_t)kTangentScale * count);
+    const int sz = (int)(uint32_t)(w.y >> 32);
+    auto q = [&](int sum) { return (uint32_t)(uint8_t)(int8_t)__float2int_rz(__fmul_rn(__fdiv_rn(__fmul_rn((float)sum, inv), fc), 127.0f)); };
+    return q(sx) | (q(sy) << 8) | (q(sz) << 16);
+}
+
+// Sparse tangent pass, step 1: one bit per voxel (density != 0) and the number of set bits per 32-voxel word (the
+// exclusive scan of the counts gives every word its first accumulator slot).  One thread per word: two 16-byte loads.
+__global__ void __launch_bounds__(256)
+k_tangent_bitmap(const uint8_t* __restrict__ dens, uint32_t n_words, uint32_t* __restrict__ bits, uint32_t* __restrict__ counts) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    const uint4* p = reinterpret_cast<const uint4*>(dens) + 2ull * w;
+    const uint4 a = __ldg(p), b = __ldg(p + 1);
+    const uint32_t q[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        // bit per non-zero byte: (x | x >> 4 ...) folded to the byte's lowest bit
+        uint32_t x = q[k];
+        x |= x >> 4; x |= x >> 2; x |= x >> 1; x &= 0x01010101u;
+        m |= ((x & 1u) | ((x >> 7) & 2u) | ((x >> 14) & 4u) | ((x >> 21) & 8u)) << (4 * k);
+    }
+    bits[w] = m;
+    counts[w] = (uint32_t)__popc(m);
+}
+// step 3: every voxel's int8 tangent from its accumulator (0 where the voxel is empty).
+__global__ void __launch_bounds__(256)
+k_finish_tangent_sparse(const unsigned long long* __restrict__ acc, const uint32_t* __restrict__ bits, const uint32_t* __restrict__ prefix,
+                        uint64_t n_voxels, uint32_t* __restrict__ tang) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_voxels; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t w = (uint32_t)(i >> 5), b = __ldg(bits + w), bit = (uint32_t)i & 31u;
+        uint32_t t = 0;
+        if ((b >> bit) & 1u) {
+            const unsigned long long slot = __ldg(prefix + w) + __popc(b & ((1u << bit) - 1u));
+            t = tangent_of(__ldg(reinterpret_cast<const ulonglong2*>(acc) + slot));
+        }
+        tang[i] = t;
     }
 }
 

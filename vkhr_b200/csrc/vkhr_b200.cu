@@ -12,6 +12,7 @@
 #include "prefilter.cuh"
 
 #include <cooperative_groups.h>
+#include <cub/device/device_scan.cuh>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -152,7 +153,8 @@ struct vkhr_b200_ctx {
     uint64_t frame_calls = 0;
     size_t ring_budget = size_t(64) << 20;        // bytes of BRICK8 scratch the frame kernel keeps in flight (L2-resident ring)
     DevBuf small;         // lohi[2] + aabb keys[6] + aabb floats[6]
-    DevBuf tacc;          // tangent mode: 16-byte accumulator per voxel
+    DevBuf tacc;          // tangent mode: 16-byte accumulator per (non-empty) voxel
+    DevBuf tmeta;         // sparse tangent mode: voxel bitmap, per-word counts and slots, scan scratch
     size_t tacc_clean_bytes = 0;     // leading bytes of `tacc` known to be zero
     DevBuf st_vertices, st_indices, st_tangents, st_dens, st_tang_out;   // host-API staging
     // pipelined host crowd API: a ring of staging slots and two copy streams (one per PCIe direction)
@@ -483,18 +485,13 @@ int run_frame(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool small, cudaS
         const uint32_t m = std::min(chunk, n - first);
         fill_batch(ctx, jobs + first, m, false, true);
         FramePlan P{};
-        P.n = m; P.ring = std::min(ring, m);
+        P.ring = std::min(ring, m);
         // copiers: few while other instances keep the machine busy (they hold CTA slots while they wait and copy), many
         // when the copy-out is the tail of the call
         P.copiers = m >= 4 ? 64u : 256u;
         P.n_bricks = (uint32_t)(nv / 32);
-        uint32_t t = 0;
-        for (uint32_t p = 0; p < m; ++p) {
-            P.item_start[p] = t;
-            t += std::max(ctx->batch.inst[p].n_tiles, 1u);         // an instance without segments still needs its (empty) volume written
-        }
-        P.item_start[m] = t;
-        P.total = t;
+        uint32_t max_items = 1;
+        for (uint32_t p = 0; p < m; ++p) max_items = std::max(max_items, ctx->batch.inst[p].n_tiles);
         P.ring_base = static_cast<uint8_t*>(ctx->brick.p);
         P.slot_bytes = nv;
         FrameCtl* ctl = static_cast<FrameCtl*>(ctx->frame_ctl.p);
@@ -508,8 +505,9 @@ int run_frame(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool small, cudaS
         }
         {
             PhaseMark mk(ctx, s, PH_WALK);
-            if (small) k_frame<3, 3><<<P.total, kWalkThreads, 0, s>>>(ctx->batch, P);
-            else       k_frame<4, 4><<<P.total, kWalkThreads, 0, s>>>(ctx->batch, P);
+            const dim3 grid(max_items, m);
+            if (small) k_frame<3, 3><<<grid, kWalkThreads, 0, s>>>(ctx->batch, P);
+            else       k_frame<4, 4><<<grid, kWalkThreads, 0, s>>>(ctx->batch, P);
             ctx->launches++;
             CU_CHECK(ctx, cudaGetLastError());
         }
@@ -689,8 +687,33 @@ int run_count(vkhr_b200_ctx* ctx, const Job& j, bool vertices_mode, uint32_t fla
     return launch_walk<0>(ctx, plan, (flags & VKHR_B200_INDEX_EXACT) != 0, 0, 1, s);
 }
 
-// Densities AND the tangent volume of one instance (Volume::tangents): counts and integer tangent sums in a
-// 16-byte-per-voxel accumulator, then one pass that writes both outputs and leaves the accumulator zeroed.
+// Launch k_walk_tangent for one job.
+int launch_walk_tangent(vkhr_b200_ctx* ctx, const Job& j, const float* d_tangents_in, bool vertices_mode, bool exact,
+                        unsigned long long* acc, const uint32_t* bits, const uint32_t* prefix, cudaStream_t s) {
+    const uint64_t items = vertices_mode ? j.n_vertices : j.n_segments;
+    if (!items) return VKHR_B200_OK;
+    const unsigned blocks = (unsigned)((items + kWalkThreads - 1) / kWalkThreads);
+#define VKHR_LAUNCH_TANGENT(KIND)                                                                                      \
+    do {                                                                                                               \
+        if (exact) k_walk_tangent<KIND, 1><<<blocks, kWalkThreads, 0, s>>>(j.d_vertices, j.d_indices, d_tangents_in, items, j.n_vertices, j.segs, j.grid, acc, bits, prefix); \
+        else       k_walk_tangent<KIND, 0><<<blocks, kWalkThreads, 0, s>>>(j.d_vertices, j.d_indices, d_tangents_in, items, j.n_vertices, j.segs, j.grid, acc, bits, prefix); \
+    } while (0)
+    if (vertices_mode) VKHR_LAUNCH_TANGENT(WK_SPLAT);
+    else if (j.d_indices) VKHR_LAUNCH_TANGENT(WK_INDEXED);
+    else VKHR_LAUNCH_TANGENT(WK_UNIFORM);
+#undef VKHR_LAUNCH_TANGENT
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return VKHR_B200_OK;
+}
+
+// Densities AND the tangent volume of one instance (Volume::tangents).
+// Segments on grids of whole 32-voxel words take the SPARSE form: the densities come from the ordinary (fast) density
+// path; then the tangents are summed only where a voxel is non-empty -- a bitmap of the density volume, an exclusive
+// scan of its per-word popcounts (cub::DeviceScan) and 16 bytes of accumulator per non-empty voxel, instead of 16
+// bytes per voxel (16 GiB at 1024^3).  One device->host read of the non-empty count sizes the accumulator (this is the
+// load-time path of the reference, rasterizer/hair_style.cc:75; the per-frame path does not ask for tangents).
+// Everything else (vertices mode, odd grid sizes) counts and sums in a dense 16-byte-per-voxel accumulator.
 int run_tangent(vkhr_b200_ctx* ctx, const Job& j, const float* d_tangents_in, bool vertices_mode, uint32_t flags,
                 int8_t* d_tangents_out, cudaStream_t s) {
     if (reinterpret_cast<uintptr_t>(d_tangents_out) & 3u)
@@ -698,39 +721,66 @@ int run_tangent(vkhr_b200_ctx* ctx, const Job& j, const float* d_tangents_in, bo
     if (vertices_mode && !d_tangents_in)
         return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "voxelize_vertices needs tangents_in to produce tangents_out");
     const uint64_t nv = j.grid.n_voxels;
-    const size_t need = (size_t)nv * 16;
-    if (need > ctx->tacc.cap) ctx->tacc_clean_bytes = 0;
-    RET_IF(reserve(ctx, ctx->tacc, need));
-    unsigned long long* acc = static_cast<unsigned long long*>(ctx->tacc.p);
-    if (ctx->tacc_clean_bytes < need) {
-        PhaseMark mk(ctx, s, PH_CLEAR);
-        CU_CHECK(ctx, cudaMemsetAsync(acc, 0, need, s));
-    }
-    ctx->tacc_clean_bytes = 0;
     const bool exact = (flags & VKHR_B200_INDEX_EXACT) != 0;
-    const uint64_t items = vertices_mode ? j.n_vertices : j.n_segments;
-    if (items) {
-        PhaseMark mk(ctx, s, PH_WALK);
-        const unsigned blocks = (unsigned)((items + kWalkThreads - 1) / kWalkThreads);
-#define VKHR_LAUNCH_TANGENT(KIND)                                                                                      \
-        do {                                                                                                           \
-            if (exact) k_walk_tangent<KIND, 1><<<blocks, kWalkThreads, 0, s>>>(j.d_vertices, j.d_indices, d_tangents_in, items, j.segs, j.grid, acc); \
-            else       k_walk_tangent<KIND, 0><<<blocks, kWalkThreads, 0, s>>>(j.d_vertices, j.d_indices, d_tangents_in, items, j.segs, j.grid, acc); \
-        } while (0)
-        if (vertices_mode) VKHR_LAUNCH_TANGENT(WK_SPLAT);
-        else if (j.d_indices) VKHR_LAUNCH_TANGENT(WK_INDEXED);
-        else VKHR_LAUNCH_TANGENT(WK_UNIFORM);
-#undef VKHR_LAUNCH_TANGENT
-        ctx->launches++;
-        CU_CHECK(ctx, cudaGetLastError());
-    }
-    {
+    const bool sparse = !vertices_mode && nv % 32u == 0 && (reinterpret_cast<uintptr_t>(j.d_dens) & 15u) == 0;
+    if (sparse) {
+        RET_IF(run_voxelize(ctx, &j, 1, false, flags & ~(uint32_t)VKHR_B200_NORMALIZE, s));
+        const uint32_t n_words = (uint32_t)(nv / 32);
+        size_t scan_bytes = 0;
+        CU_CHECK(ctx, cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n_words, s));
+        const size_t words_bytes = ((size_t)n_words * 4 + 255) & ~size_t(255);
+        RET_IF(reserve(ctx, ctx->tmeta, 3 * words_bytes + scan_bytes + 256));
+        uint32_t* bits = static_cast<uint32_t*>(ctx->tmeta.p);
+        uint32_t* counts = bits + words_bytes / 4;
+        uint32_t* prefix = counts + words_bytes / 4;
+        void* scan_tmp = prefix + words_bytes / 4;
+        uint32_t last[2] = {0, 0};
+        {
+            PhaseMark mk(ctx, s, PH_CLEAR);
+            k_tangent_bitmap<<<(n_words + 255) / 256, 256, 0, s>>>(j.d_dens, n_words, bits, counts);
+            ctx->launches++;
+            CU_CHECK(ctx, cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, counts, prefix, (int)n_words, s));
+            CU_CHECK(ctx, cudaMemcpyAsync(&last[0], prefix + n_words - 1, 4, cudaMemcpyDeviceToHost, s));
+            CU_CHECK(ctx, cudaMemcpyAsync(&last[1], counts + n_words - 1, 4, cudaMemcpyDeviceToHost, s));
+            CU_CHECK(ctx, cudaStreamSynchronize(s));
+        }
+        const size_t nnz = (size_t)last[0] + last[1];
+        const size_t need = std::max<size_t>(nnz, 1) * 16;
+        if (need > ctx->tacc.cap) ctx->tacc_clean_bytes = 0;
+        RET_IF(reserve(ctx, ctx->tacc, need));
+        unsigned long long* acc = static_cast<unsigned long long*>(ctx->tacc.p);
+        CU_CHECK(ctx, cudaMemsetAsync(acc, 0, need, s));
+        ctx->tacc_clean_bytes = 0;
+        {
+            PhaseMark mk(ctx, s, PH_WALK);
+            RET_IF(launch_walk_tangent(ctx, j, d_tangents_in, false, exact, acc, bits, prefix, s));
+        }
         PhaseMark mk(ctx, s, PH_FINISH);
-        k_finish_tangent<<<stride_blocks(ctx, nv, 256, 16), 256, 0, s>>>(acc, nv, j.d_dens, reinterpret_cast<uint32_t*>(d_tangents_out));
+        k_finish_tangent_sparse<<<stride_blocks(ctx, nv, 256, 16), 256, 0, s>>>(acc, bits, prefix, nv, reinterpret_cast<uint32_t*>(d_tangents_out));
         ctx->launches++;
         CU_CHECK(ctx, cudaGetLastError());
+    } else {
+        const size_t need = (size_t)nv * 16;
+        if (need > ctx->tacc.cap) ctx->tacc_clean_bytes = 0;
+        RET_IF(reserve(ctx, ctx->tacc, need));
+        unsigned long long* acc = static_cast<unsigned long long*>(ctx->tacc.p);
+        if (ctx->tacc_clean_bytes < need) {
+            PhaseMark mk(ctx, s, PH_CLEAR);
+            CU_CHECK(ctx, cudaMemsetAsync(acc, 0, need, s));
+        }
+        ctx->tacc_clean_bytes = 0;
+        {
+            PhaseMark mk(ctx, s, PH_WALK);
+            RET_IF(launch_walk_tangent(ctx, j, d_tangents_in, vertices_mode, exact, acc, nullptr, nullptr, s));
+        }
+        {
+            PhaseMark mk(ctx, s, PH_FINISH);
+            k_finish_tangent<<<stride_blocks(ctx, nv, 256, 16), 256, 0, s>>>(acc, nv, j.d_dens, reinterpret_cast<uint32_t*>(d_tangents_out));
+            ctx->launches++;
+            CU_CHECK(ctx, cudaGetLastError());
+        }
+        ctx->tacc_clean_bytes = need;                   // the finish pass zeroed every entry it found non-empty
     }
-    ctx->tacc_clean_bytes = need;                       // the finish pass zeroed every entry it found non-empty
     if (flags & VKHR_B200_NORMALIZE) {
         PhaseMark mk(ctx, s, PH_NORMALIZE);
         RET_IF(vkhr_b200_normalize_dev(ctx, j.d_dens, nv, s));
@@ -796,7 +846,7 @@ void vkhr_b200_destroy(vkhr_b200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->counts, &ctx->bitmap, &ctx->brick, &ctx->frame_ctl, &ctx->small, &ctx->tacc, &ctx->adsm_table, &ctx->adsm_occ, &ctx->pf_occ, &ctx->st_vertices,
+    DevBuf* bufs[] = {&ctx->counts, &ctx->bitmap, &ctx->brick, &ctx->frame_ctl, &ctx->small, &ctx->tacc, &ctx->tmeta, &ctx->adsm_table, &ctx->adsm_occ, &ctx->pf_occ, &ctx->st_vertices,
                       &ctx->st_indices, &ctx->st_tangents, &ctx->st_dens, &ctx->st_tang_out};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (auto& sl : ctx->slots) {
@@ -1241,6 +1291,14 @@ int vkhr_b200_generate_bounding_box(vkhr_b200_ctx* ctx, const float* vertices, u
     CU_CHECK(ctx, cudaMemcpyAsync(aabb_out, d_out, 24, cudaMemcpyDeviceToHost, ctx->stream));
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     return VKHR_B200_OK;
+}
+
+int vkhr_b200_volume_save(const char* path, const uint8_t* densities, uint64_t n_voxels) {
+    if (!path || (!densities && n_voxels)) return VKHR_B200_ERR_INVALID_ARGUMENT;
+    std::FILE* f = std::fopen(path, "wb");
+    if (!f) return VKHR_B200_ERR_INVALID_ARGUMENT;
+    const bool ok = n_voxels == 0 || std::fwrite(densities, 1, n_voxels, f) == n_voxels;
+    return (std::fclose(f) == 0 && ok) ? VKHR_B200_OK : VKHR_B200_ERR_INVALID_ARGUMENT;
 }
 
 // ---- host-pointer crowd API: upload / kernels / download of consecutive instances overlap ----------

@@ -57,12 +57,8 @@ class Volume:
 
     def save(self, path: str) -> bool:
         """``Volume::save`` (hair_style.cc:359-369): raw dump of the densities."""
-        try:
-            with open(path, "wb") as f:
-                f.write(np.ascontiguousarray(self.densities, dtype=np.uint8).tobytes())
-            return True
-        except OSError:
-            return False
+        d = np.ascontiguousarray(self.densities, dtype=np.uint8).reshape(-1)
+        return capi.lib.vkhr_b200_volume_save(str(path).encode(), d.ctypes.data, d.size) == capi.OK
 
     def downsample(self, filter: int = capi.DOWNSAMPLE_MAX) -> "Volume":
         """``Volume::downsample`` (hair_style.hh:228-257) with one of the built-in 2x2x2 functors."""
