@@ -153,6 +153,10 @@ class Voxelizer:
         if isinstance(batch, (list, tuple)) and batch and isinstance(batch[0], dict):
             batch = self.make_host_batch(batch)
         arr = batch[0] if isinstance(batch, tuple) else batch
+        if isinstance(batch, tuple):
+            for v, o, _ in batch[1]:
+                if o.size != int(W) * int(H) * int(D):
+                    raise ValueError(f"out holds {o.size} bytes, the call needs {int(W) * int(H) * int(D)}")
         capi.check(self._h, lib.vkhr_b200_voxelize_segments_batch(self._h, arr, len(arr), int(W), int(H), int(D), int(flags)))
 
     def host_register(self, array: np.ndarray) -> None:
@@ -254,6 +258,10 @@ class Voxelizer:
         if t.dtype != dtype or not t.is_contiguous():
             raise ValueError(f"{name} must be contiguous {dtype}")
 
+    def _check_size(self, t, n, name):
+        if t.numel() != int(n):
+            raise ValueError(f"{name} holds {t.numel()} elements, the call needs {int(n)}")
+
     def voxelize_segments_dev(self, vertices, indices, aabb_origin, aabb_size, W, H, D,
                               segs_per_strand: int = 0, flags: int = 0, out=None, stream=None):
         import torch
@@ -264,6 +272,7 @@ class Voxelizer:
         if out is None:
             out = torch.empty(n, dtype=torch.uint8, device=vertices.device)
         self._check_dev(out, torch.uint8, "out")
+        self._check_size(out, n, "out")
         rc = lib.vkhr_b200_voxelize_segments_dev(
             self._h, C.c_void_p(vertices.data_ptr()), vertices.numel() // 3,
             None if indices is None else C.c_void_p(indices.data_ptr()),
@@ -280,6 +289,7 @@ class Voxelizer:
         if out is None:
             out = torch.empty(n, dtype=torch.uint8, device=vertices.device)
         self._check_dev(out, torch.uint8, "out")
+        self._check_size(out, n, "out")
         rc = lib.vkhr_b200_voxelize_vertices_dev(
             self._h, C.c_void_p(vertices.data_ptr()), vertices.numel() // 3, None,
             capi.vec3(aabb_origin), capi.vec3(aabb_size), int(W), int(H), int(D), int(flags),
@@ -319,6 +329,9 @@ class Voxelizer:
         if isinstance(batch, (list, tuple)) and batch and isinstance(batch[0], dict):
             batch = self.make_batch(batch)
         arr = batch[0] if isinstance(batch, tuple) else batch
+        if isinstance(batch, tuple):
+            for v, o, _ in batch[1]:
+                self._check_size(o, int(W) * int(H) * int(D), "out")
         rc = lib.vkhr_b200_voxelize_segments_batch_dev(self._h, arr, len(arr), int(W), int(H), int(D),
                                                        int(flags), self._torch_stream(stream))
         capi.check(self._h, rc)
@@ -346,6 +359,7 @@ class Voxelizer:
         import torch
         self._check_dev(vertices, torch.float32, "vertices")
         self._check_dev(counts, torch.int32, "counts")
+        self._check_size(counts, int(W) * int(H) * int(D), "counts")
         rc = lib.vkhr_b200_count_vertices_dev(
             self._h, C.c_void_p(vertices.data_ptr()), vertices.numel() // 3,
             capi.vec3(aabb_origin), capi.vec3(aabb_size), int(W), int(H), int(D), int(flags),
@@ -360,6 +374,7 @@ class Voxelizer:
         if out is None:
             out = torch.empty(counts.numel(), dtype=torch.uint8, device=counts.device)
         self._check_dev(out, torch.uint8, "out")
+        self._check_size(out, counts.numel(), "out")
         rc = lib.vkhr_b200_clamp_counts_dev(self._h, C.c_void_p(counts.data_ptr()), counts.numel(), int(flags),
                                             C.c_void_p(out.data_ptr()), self._torch_stream(stream))
         capi.check(self._h, rc)
@@ -449,8 +464,11 @@ class Voxelizer:
     def downsample_dev(self, densities, W, H, D, filter: int = capi.DOWNSAMPLE_MAX, out=None, stream=None):
         import torch
         self._check_dev(densities, torch.uint8, "densities")
+        self._check_size(densities, int(W) * int(H) * int(D), "densities")
         if out is None:
             out = torch.empty((W // 2) * (H // 2) * (D // 2), dtype=torch.uint8, device=densities.device)
+        self._check_dev(out, torch.uint8, "out")
+        self._check_size(out, (W // 2) * (H // 2) * (D // 2), "out")
         capi.check(self._h, lib.vkhr_b200_downsample_dev(self._h, C.c_void_p(densities.data_ptr()), int(W), int(H), int(D),
                                                          int(filter), C.c_void_p(out.data_ptr()), self._torch_stream(stream)))
         return out
