@@ -49,7 +49,9 @@ int main() {
     CHECK(one, vkhr_b200_voxelize_segments(one, xyz.data(), strands * vps, nullptr, 0, segs, nullptr, lo, size, W, H, D, 0, want.data(), nullptr));
 
     int bad = 0;
-    for (uint32_t world : {2u, 3u, 8u}) {
+    // (more fake ranks than hardware work queues would put one rank's kernels behind another rank's waiting barrier kernel:
+    // CUDA_DEVICE_MAX_CONNECTIONS, 8 by default -- real ranks have a device each)
+    for (uint32_t world : {2u, 3u, 4u}) {
         const uint64_t nvp = vkhr_b200_sharded_volume_bytes(W, H, D, world);
         std::vector<vkhr_b200_ctx*> ctx(world, nullptr);
         std::vector<void*> partials(world), bitmaps(world), outs(world), signals(world), verts(world);

@@ -427,33 +427,33 @@ k_walk_indexed(const __grid_constant__ Batch B, uint32_t first) {
 }
 
 // ---------------------------------------------------------------------------
-// The frame kernel: BRICK8 walk AND copy-out of a whole batch in ONE launch, warp-autonomous (no CTA barrier).
+// The frame kernel: BRICK8 walk AND copy-out of a whole batch in ONE launch.
 //
 // The grid is k_walk_uniform's: blockIdx.y = instance, blockIdx.x = walk item (8 warp-ranges of 8 tiles, kFrameRanges of
-// them in a row; 2048 segments of an indexed instance), so instances START in order.  Every warp walks its ranges,
-// adds its sample count to the instance's statistics, fences and reports to the instance's counter -- on its own; nothing
-// waits for the slowest warp of a CTA.  The warps of an instance's LAST `copiers` CTAs stay on: they wait until every
-// warp of the instance has reported (they were the last to start, so few are still running) and then copy the
-// instance's scratch volume out to the caller's x-fastest volume, an equal share of the bricks each, zeroing behind
-// themselves -- while every other CTA slot of the machine is already walking the next instances.  The walk is bound by
+// them in a row; 2048 segments of an indexed instance), so instances START in order.  A CTA walks its item, adds its
+// sample count to the instance's statistics and reports to the instance's counter (one fence, by one thread, behind the
+// CTA's barrier).  An instance's LAST `copiers` CTAs stay on: they wait until every CTA of the instance has reported
+// (they were the last to start, so few are still running) and then copy the instance's scratch volume out to the
+// caller's x-fastest volume, an equal share of the bricks each, zeroing behind themselves -- while every other CTA slot
+// of the machine is already walking the next instances.  The walk is bound by
 // its instructions, the copy-out by memory: side by side they fill both.  Instance i counts in scratch slot i mod
 // `ring`; a ring of four slots (64 MiB at 256^3) covers the window of instances in flight and stays largely resident
 // in the 126 MB L2, so the walk's reds, the copy-out's reads and the zeros behind it mostly stay off HBM.
 //
-// Waiting: a copier warp waits for warps of its own instance (CTAs with smaller or equal block indices); a walk warp
-// of instance i waits (behind its vertex copy, already in flight) for the copiers of instance i - ring (smaller block
-// indices).  CTAs are dispatched in increasing linear block index (the order every spin-on-the-previous-block scheme
+// Waiting: a copier waits for CTAs of its own instance (smaller block indices); a walk CTA of instance i waits (with
+// its vertex copy already in flight) for the copiers of instance i - ring (smaller block indices).  CTAs are dispatched in increasing linear block index (the order every spin-on-the-previous-block scheme
 // relies on -- serial split-K semaphores, decoupled look-back with block-index tickets), so whatever is waited for is
 // resident and running.  Waits are bounded: a lost dependency traps instead of hanging the device.  The verdict of the
-// fire-and-forget `red` walk (samples added == byte sum, see SinkPacked8Brick) is taken by an instance's last copier warp.
+// fire-and-forget `red` walk (samples added == byte sum, see SinkPacked8Brick) is taken by an instance's last copier.
 // The control block of the NEXT call is zeroed here (two blocks alternate), so a frame is one launch (+ the repair
 // kernel's look at the flags).
 //
 // Three other forms were built and measured first (crowd frame, ms; separate kernels: 1.19): persistent CTAs drawing
 // CTA-wide items from one ordered ticket queue with the copy-out as queue items 1.27; the same with autonomous warps and
 // one item of look-ahead 2.1 (the tickets parked in look-ahead were the dependencies other warps span on); ticketed
-// one-item CTAs whose last finishers copy out 1.14-1.5 (a fifth of all warp-time at the barrier behind the ticket).
-// profiles/r02_b_*, r02_d_*, r02_e_*, r02_f_*.
+// one-item CTAs whose last finishers copy out 1.14-1.5 (a fifth of all warp-time at the barrier behind the ticket); this
+// grid with warp-wise reports and copiers 1.78 (a fence per warp: 15 % of all warp-time in the fence).
+// profiles/r02_b_*, r02_d_*, r02_e_*, r02_f_*, r02_g_*.
 // ---------------------------------------------------------------------------
 constexpr uint32_t kFrameStatSlots = 32;
 constexpr uint32_t kFrameIndexedSegs = 2048;                    // segments per walk item of an indexed instance
@@ -465,14 +465,14 @@ constexpr uint32_t kFrameIndexedSegs = 2048;                    // segments per 
 #endif
 constexpr uint32_t kFrameRanges = VKHR_FRAME_RANGES;            // warp-ranges a warp walks per item: the item's fixed costs (fence, report) are paid once
 struct FrameCtl {
-    uint32_t walk_done[kMaxBatch];                              // warps of the instance that have reported
-    uint32_t copy_done[kMaxBatch];                              // copier warps of the instance that have finished
+    uint32_t walk_done[kMaxBatch];                              // CTAs of the instance that have reported
+    uint32_t copy_done[kMaxBatch];                              // copiers of the instance that have finished
     unsigned long long added[kMaxBatch][kFrameStatSlots];       // samples the walk added, slotted
     unsigned long long bytes[kMaxBatch][kFrameStatSlots];       // byte sums the copy-out read, slotted
 };
 struct FramePlan {
     uint32_t ring;                                              // scratch slots
-    uint32_t copiers;                                           // CTAs of an instance whose warps copy it out (the last ones by block index)
+    uint32_t copiers;                                           // CTAs of an instance that copy it out (the last ones by block index)
     uint32_t n_bricks;
     uint32_t pad;
     uint8_t* ring_base;
@@ -481,9 +481,9 @@ struct FramePlan {
     FrameCtl* ctl_next;
 };
 
-// lane 0 waits until *p >= need (acquire), then the warp reconverges
+// thread 0 waits until *p >= need (acquire), then the CTA meets at a barrier
 __device__ __forceinline__ void frame_wait_ge(const uint32_t* p, uint32_t need) {
-    if ((threadIdx.x & 31u) == 0u) {
+    if (threadIdx.x == 0) {
         uint32_t v;
         for (uint32_t spin = 0;; ++spin) {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -492,7 +492,7 @@ __device__ __forceinline__ void frame_wait_ge(const uint32_t* p, uint32_t need) 
             if (spin > (1u << 23)) __trap();                       // a lost dependency must fail, not hang the device
         }
     }
-    __syncwarp();
+    __syncthreads();
 }
 
 template <int MODE, int EXACT>
@@ -500,6 +500,8 @@ __global__ void __launch_bounds__(kWalkThreads, VKHR_FRAME_MIN_CTAS)
 k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
     __shared__ __align__(128) float s_stage[kWarpsPerBlock][kStageFloats];
     __shared__ __align__(8) unsigned long long s_bar[kWarpsPerBlock];
+    __shared__ unsigned long long s_sum[kWarpsPerBlock];
+    __shared__ uint32_t s_last;
     const uint32_t i = blockIdx.y;
     const InstanceDev& I = B.inst[i];
     const uint32_t items = max(I.n_tiles, 1u);                     // CTAs of this instance (one for an instance without segments: its copy-out)
@@ -515,6 +517,7 @@ k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
     }
     uint8_t* const slot = P.ring_base + (unsigned long long)(i % P.ring) * P.slot_bytes;
     const uint32_t copiers = min(items, P.copiers);
+    const bool uniform_item = blockIdx.x < I.n_tiles && I.kind == WK_UNIFORM;
 
     // ---- the walk ------------------------------------------------------------------------------------------------
     {
@@ -522,52 +525,54 @@ k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
         sink.words = reinterpret_cast<uint32_t*>(slot);
         sink.words_pin();
         uint32_t parity = 0;
-        bool waited = i < P.ring;                                  // the slot's previous tenant: instance i - ring
-        auto wait_for_slot = [&]() {
-            if (!waited) {
-                const uint32_t prev_items = max(B.inst[i - P.ring].n_tiles, 1u);
-                frame_wait_ge(&ctl->copy_done[i - P.ring], min(prev_items, P.copiers) * kWarpsPerBlock);
-                waited = true;
-            }
-        };
-        if (blockIdx.x < I.n_tiles) {
-            if (I.kind == WK_UNIFORM) {
-                for (uint32_t rr = 0; rr < kFrameRanges; ++rr) {
-                    const uint32_t range = (blockIdx.x * kFrameRanges + rr) * kWarpsPerBlock + warp;
-                    const bool bulk = stage_range(I, range, s_stage[warp], bar);     // the vertices are on their way ...
-                    wait_for_slot();                                                 // ... while the slot is checked
-                    walk_range<EXACT>(I, range, s_stage[warp], bar, bulk, parity, sink);
-                    __syncwarp();
-                }
-            } else {
-                wait_for_slot();
-                for (uint32_t j = 0; j < kFrameIndexedSegs / kWalkThreads; ++j)
-                    walk_indexed_lane<EXACT>(I, ((uint64_t)blockIdx.x * (kFrameIndexedSegs / kWalkThreads) + j) * kWalkThreads + threadIdx.x, sink);
-            }
+        // the first range's vertices are on their way while the slot is checked
+        uint32_t range = blockIdx.x * kFrameRanges * kWarpsPerBlock + warp;
+        bool bulk = uniform_item && stage_range(I, range, s_stage[warp], bar);
+        if (i >= P.ring) {                                         // the slot's previous tenant, instance i - ring, has been copied out
+            const uint32_t prev_items = max(B.inst[i - P.ring].n_tiles, 1u);
+            frame_wait_ge(&ctl->copy_done[i - P.ring], min(prev_items, P.copiers));
         }
-        wait_for_slot();                                           // (a copier of an empty item must not zero a slot that is still being copied out)
+        if (uniform_item) {
+            for (uint32_t rr = 0;;) {
+                walk_range<EXACT>(I, range, s_stage[warp], bar, bulk, parity, sink);
+                if (++rr == kFrameRanges) break;
+                __syncwarp();
+                range += kWarpsPerBlock;
+                bulk = stage_range(I, range, s_stage[warp], bar);
+            }
+        } else if (blockIdx.x < I.n_tiles) {
+            for (uint32_t j = 0; j < kFrameIndexedSegs / kWalkThreads; ++j)
+                walk_indexed_lane<EXACT>(I, ((uint64_t)blockIdx.x * (kFrameIndexedSegs / kWalkThreads) + j) * kWalkThreads + threadIdx.x, sink);
+        }
         const uint32_t added = __reduce_add_sync(kFullWarp, sink.added);
-        if (lane == 0 && added) atomicAdd(&ctl->added[i][(blockIdx.x * kWarpsPerBlock + warp) & (kFrameStatSlots - 1u)], (unsigned long long)added);
+        if (lane == 0) s_sum[warp] = added;
     }
-    __threadfence();                                               // every lane's reds (and the count) are performed before the warp reports
-    __syncwarp();
-    if (lane == 0) atomicAdd(&ctl->walk_done[i], 1u);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long sum = 0;
+        for (uint32_t w = 0; w < kWarpsPerBlock; ++w) sum += s_sum[w];
+        if (sum) atomicAdd(&ctl->added[i][blockIdx.x & (kFrameStatSlots - 1u)], sum);
+        // release: the fence is cumulative over everything that happens-before it -- the reds of all threads of the CTA
+        // are ordered before it by the barrier -- so the observer that acquires the counter sees them
+        __threadfence();
+        atomicAdd(&ctl->walk_done[i], 1u);
+    }
     if (blockIdx.x + copiers < items) return;                      // not one of the instance's last `copiers` CTAs: done
 
-    // ---- copier warp c of the instance: brick order -> the x-fastest output volume, zeroing behind itself --------
-    const uint32_t c = (blockIdx.x - (items - copiers)) * kWarpsPerBlock + warp, n_c = copiers * kWarpsPerBlock;
-    frame_wait_ge(&ctl->walk_done[i], items * kWarpsPerBlock);     // the warps still walking (all have started)
-    uint32_t bytes = 0;                                            // < 2^32: at most 8160 per brick
+    // ---- copier CTA c of the instance: brick order -> the x-fastest output volume, zeroing behind itself ---------
+    const uint32_t c = blockIdx.x - (items - copiers);
+    frame_wait_ge(&ctl->walk_done[i], items);                      // the CTAs still walking (all have started)
     {
         const uint32_t wrow = I.grid.W >> 2, byn = I.grid.H >> 2;  // words (= bricks) per row, brick rows per slab
         const uint32_t wslab = wrow * I.grid.H;
         uint4* __restrict__ src = reinterpret_cast<uint4*>(slot);
         uint32_t* __restrict__ dst = reinterpret_cast<uint32_t*>(I.densities);
         const uint4 z = make_uint4(0, 0, 0, 0);
-        const uint32_t per = ((P.n_bricks + n_c - 1u) / n_c + 31u) & ~31u;       // whole warp-rows of 32 bricks
+        uint32_t bytes = 0;                                        // < 2^32: at most 8160 per brick
+        const uint32_t per = ((P.n_bricks + copiers - 1u) / copiers + 31u) & ~31u;     // whole warp-rows of 32 bricks
         const uint32_t b_end = min((c + 1u) * per, P.n_bricks);
 #pragma unroll 4
-        for (uint32_t b = c * per + lane; b < b_end; b += 32u) {
+        for (uint32_t b = c * per + threadIdx.x; b < b_end; b += kWalkThreads) {
             const uint4 q0 = __ldcg(src + 2u * b), q1 = __ldcg(src + 2u * b + 1u);   // L2 is where the reds landed; L1 may be stale
             bytes += __vsadu4(q0.x, 0u) + __vsadu4(q0.y, 0u) + __vsadu4(q0.z, 0u) + __vsadu4(q0.w, 0u) +
                      __vsadu4(q1.x, 0u) + __vsadu4(q1.y, 0u) + __vsadu4(q1.z, 0u) + __vsadu4(q1.w, 0u);
@@ -578,15 +583,20 @@ k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
             __stcs(o, q1.x); __stcs(o + wrow, q1.y); __stcs(o + 2u * wrow, q1.z); __stcs(o + 3u * wrow, q1.w);
             if ((q0.x | q0.y | q0.z | q0.w | q1.x | q1.y | q1.z | q1.w) != 0u) { __stcg(src + 2u * b, z); __stcg(src + 2u * b + 1u, z); }
         }
+        const unsigned long long wsum = (unsigned long long)__reduce_add_sync(kFullWarp, bytes & 0xFFFFu) +
+                                        ((unsigned long long)__reduce_add_sync(kFullWarp, bytes >> 16) << 16);
+        if (lane == 0) s_sum[warp] = wsum;
     }
-    const unsigned long long wsum = (unsigned long long)__reduce_add_sync(kFullWarp, bytes & 0xFFFFu) +
-                                    ((unsigned long long)__reduce_add_sync(kFullWarp, bytes >> 16) << 16);
-    if (lane == 0 && wsum) atomicAdd(&ctl->bytes[i][c & (kFrameStatSlots - 1u)], wsum);
-    __threadfence();                                               // the zeros are in place before the slot is released
-    __syncwarp();
-    uint32_t last = 0;
-    if (lane == 0) last = (atomicAdd(&ctl->copy_done[i], 1u) == n_c - 1u) ? 1u : 0u;
-    if (__reduce_max_sync(kFullWarp, last)) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long sum = 0;
+        for (uint32_t w = 0; w < kWarpsPerBlock; ++w) sum += s_sum[w];
+        if (sum) atomicAdd(&ctl->bytes[i][c & (kFrameStatSlots - 1u)], sum);
+        __threadfence();                                           // the zeros (of every thread: barrier above) are in place before the slot is released
+        s_last = (atomicAdd(&ctl->copy_done[i], 1u) == copiers - 1u) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last && warp == 0) {
         // the instance is complete: samples added != byte sum of the volume means some byte carried (more than 255 hits
         // in a voxel) -> flag 2, k_repair_packed recounts the instance in u32
         __threadfence();

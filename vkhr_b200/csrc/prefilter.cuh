@@ -46,6 +46,7 @@ struct PrefilterArgs {
     int g_range;               // (kernel_width - 1) / 2
     float g_sigma2;
     uint32_t tiles_x, tiles_y, tiles_z;
+    uint32_t* tile_counter;     // dynamic tile scheduling: CTAs draw tiles from this counter (zeroed by k_pf_tile_active); nullptr = static stride
     const uint8_t* tile_active; // one byte per tile (k_pf_tile_active): 0 = the tile and its halo hold no hair -> constants, no load; or nullptr
 };
 
@@ -312,9 +313,10 @@ k_pf_cell_occupancy(const uint8_t* __restrict__ dens, int W, int H, int D, int c
 // active[tile] = 1 when a cell overlapping the tile's box (tile + halo, halo <= 8) is occupied.  One thread per tile.
 __global__ void __launch_bounds__(256)
 k_pf_tile_active(const uint8_t* __restrict__ occ, int cx, int cy, int cz, uint32_t tiles_x, uint32_t tiles_y, uint32_t tiles_z, int tz,
-                 uint8_t* __restrict__ active) {
+                 uint8_t* __restrict__ active, uint32_t* __restrict__ counter) {
     const uint32_t n = tiles_x * tiles_y * tiles_z;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) *counter = 0u;                                     // the tiled kernel draws its tiles from here
     if (t >= n) return;
     const int tx = (int)(t % tiles_x), ty = (int)((t / tiles_x) % tiles_y), tzi = (int)(t / (tiles_x * tiles_y));
     // tiles are kPfTX x kPfTY x tz voxels = 1 x 1 x (tz / 8) cells
@@ -473,24 +475,40 @@ k_prefilter_tiled(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             }
         }
     };
-    bool act_cur = blockIdx.x < n_tiles && is_active(blockIdx.x);
-    if (act_cur && tid == 0) issue(blockIdx.x, 0);
+    // Tiles are drawn from a counter, two ahead (the tile being worked on, the one being loaded, the ticket in flight):
+    // loaded tiles cost an order of magnitude more than tiles of empty space and come in runs, so a fixed stride leaves
+    // some CTAs with all the work (half of the tiles of a 1024^3 hair volume are loaded).
+    __shared__ uint32_t s_next[2];
+    const bool dynamic = A.tile_counter != nullptr;
+    if (dynamic && tid == 0) { s_next[0] = atomicAdd(A.tile_counter, 1u); s_next[1] = atomicAdd(A.tile_counter, 1u); }
+    __syncthreads();
+    uint32_t tile = dynamic ? s_next[0] : blockIdx.x, nxt = dynamic ? s_next[1] : blockIdx.x + gridDim.x, it = 0;
+    auto advance = [&]() {
+        __syncthreads();                                   // thread 0's ticket of this iteration is in s_next[it & 1]
+        tile = nxt;
+        nxt = dynamic ? s_next[it & 1u] : nxt + gridDim.x;
+        ++it;
+    };
+    bool act_cur = tile < n_tiles && is_active(tile);
+    __syncthreads();                                       // (s_next[0] has been read by everyone before it is overwritten)
+    if (act_cur && tid == 0) issue(tile, 0);
 
     uint32_t na = 0;                                       // loaded tiles consumed so far: the next one arrives in buffer na & 1
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (; tile < n_tiles; advance()) {
+        if (dynamic && tid == 0) s_next[it & 1u] = atomicAdd(A.tile_counter, 1u);
         const bool act = act_cur;
-        const bool act_nxt = tile + gridDim.x < n_tiles && is_active(tile + gridDim.x);
+        const bool act_nxt = nxt < n_tiles && is_active(nxt);
         act_cur = act_nxt;
         int x0, y0, z0;
         tile_origin(tile, x0, y0, z0);
         if (!act) {
             // (buffer na & 1 was last read two loaded tiles ago, with CTA barriers since)
-            if (tid == 0 && act_nxt) issue(tile + gridDim.x, na & 1u);
+            if (tid == 0 && act_nxt) issue(nxt, na & 1u);
             fill_empty(x0, y0, z0);
             continue;
         }
         const uint32_t buf = na & 1u;
-        if (tid == 0 && act_nxt) issue(tile + gridDim.x, buf ^ 1u);   // prefetch the next tile
+        if (tid == 0 && act_nxt) issue(nxt, buf ^ 1u);   // prefetch the next tile
         pf_mbar_wait(bar0 + 8u * buf, (na >> 1) & 1u);
         ++na;
         const unsigned char* stage = pf_smem + buf * P.stage_bytes;

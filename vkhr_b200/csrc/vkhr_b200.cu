@@ -1532,13 +1532,16 @@ int vkhr_b200_prefilter_dev(vkhr_b200_ctx* ctx, const uint8_t* d_densities, uint
     if (!(P.flags & VKHR_B200_PREFILTER_DENSE)) {
         const int cx = (int)((W + kPfCellX - 1) / kPfCellX), cy = (int)((H + kPfCellY - 1) / kPfCellY), cz = (int)((D + kPfCellZ - 1) / kPfCellZ);
         const size_t n_cells = (size_t)cx * cy * cz, occ_bytes = (n_cells + 255) & ~size_t(255);
-        RET_IF(reserve(ctx, ctx->pf_occ, occ_bytes + n_tiles));
+        const size_t tiles_bytes = (n_tiles + 255) & ~size_t(255);
+        RET_IF(reserve(ctx, ctx->pf_occ, occ_bytes + tiles_bytes + 256));
         uint8_t* occ = static_cast<uint8_t*>(ctx->pf_occ.p);
         uint8_t* active = occ + occ_bytes;
+        uint32_t* counter = reinterpret_cast<uint32_t*>(active + tiles_bytes);
         k_pf_cell_occupancy<<<stride_blocks(ctx, n_cells, 8, 16), 256, 0, s>>>(d_densities, (int)W, (int)H, (int)D, cx, cy, cz, occ);
-        k_pf_tile_active<<<(unsigned)((n_tiles + 255) / 256), 256, 0, s>>>(occ, cx, cy, cz, A.tiles_x, A.tiles_y, A.tiles_z, tz, active);
+        k_pf_tile_active<<<(unsigned)((n_tiles + 255) / 256), 256, 0, s>>>(occ, cx, cy, cz, A.tiles_x, A.tiles_y, A.tiles_z, tz, active, counter);
         ctx->launches += 2;
         A.tile_active = active;
+        A.tile_counter = counter;
     }
     const unsigned blocks = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)per_sm * ctx->sm_count);
     kernel<<<blocks, kPfThreads, plan.total, s>>>(tmap, A);
