@@ -70,12 +70,14 @@ int main() {
             CHECK(ctx[r], vkhr_b200_upload(ctx[r], verts[r], xyz.data() + size_t(first[r]) * vps * 3, nverts * 12, nullptr));
             CHECK(ctx[r], vkhr_b200_synchronize(ctx[r]));
         }
+        std::printf("world %u: buffers ready\n", world); std::fflush(stdout);
         for (int frame = 0; frame < 2; ++frame) {
             for (uint32_t r = 0; r < world; ++r) {                    // asynchronous: every rank's chain is enqueued, then all are awaited
                 vkhr_b200_shard_peers peers{r, world, partials.data(), bitmaps.data(), outs.data(), signals.data()};
                 CHECK(ctx[r], vkhr_b200_voxelize_segments_sharded_dev(ctx[r], static_cast<const float*>(verts[r]), (first[r + 1] - first[r]) * vps,
                                                                      nullptr, 0, segs, lo, size, W, H, D, 0, &peers, nullptr));
             }
+            std::printf("world %u frame %d: enqueued\n", world, frame); std::fflush(stdout);
             for (uint32_t r = 0; r < world; ++r) {
                 CHECK(ctx[r], vkhr_b200_synchronize(ctx[r]));
                 std::vector<uint8_t> got(nv);
