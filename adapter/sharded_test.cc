@@ -68,6 +68,12 @@ int main() {
             const size_t nverts = size_t(first[r + 1] - first[r]) * vps;
             CHECK(ctx[r], vkhr_b200_malloc(ctx[r], nverts * 12 + 16, &verts[r]));
             CHECK(ctx[r], vkhr_b200_upload(ctx[r], verts[r], xyz.data() + size_t(first[r]) * vps * 3, nverts * 12, nullptr));
+            // ONE DEVICE ONLY: the first voxelisation of a context allocates its scratch, and a device memory allocation
+            // serialises the device's streams (CUDA's implicit synchronisation) -- inside the sharded call that would put
+            // rank r + 1's kernels behind rank r's waiting barrier kernel.  So every context allocates here, up front.
+            // (Ranks on different GPUs do not share a device and need none of this.)
+            CHECK(ctx[r], vkhr_b200_voxelize_segments_dev(ctx[r], static_cast<const float*>(verts[r]), (first[r + 1] - first[r]) * vps, nullptr, 0, segs,
+                                                          nullptr, lo, size, W, H, D, 0, static_cast<uint8_t*>(outs[r]), nullptr, nullptr));
             CHECK(ctx[r], vkhr_b200_synchronize(ctx[r]));
         }
         std::printf("world %u: buffers ready\n", world); std::fflush(stdout);

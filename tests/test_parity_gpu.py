@@ -939,6 +939,13 @@ def test_sharded_entry_point_with_fake_ranks_on_one_device(port, k):
     outs = [torch.full((nvp,), 9, dtype=torch.uint8, device=dev) for _ in range(k)]
     signals = [torch.zeros(32, dtype=torch.int32, device=dev) for _ in range(k)]
     ptrs = lambda ts: [t.data_ptr() for t in ts]   # noqa: E731
+    # ONE DEVICE ONLY: a context's first voxelisation allocates its scratch, and a device memory allocation serialises the
+    # device's streams (CUDA's implicit synchronisation) -- inside a sharded call that would put rank r + 1's kernels behind
+    # rank r's waiting barrier kernel.  So every context allocates up front (ranks on different GPUs need none of this).
+    warm = torch.from_numpy(v).to(dev).reshape(-1)
+    for r in range(k):
+        with torch.cuda.stream(streams[r]):
+            ranks[r].voxelize_segments_dev(warm, None, lo, size, W, H, D, segs_per_strand=s, out=outs[r][:nv])
     torch.cuda.synchronize()
     try:
         for frame in range(3):
