@@ -272,7 +272,8 @@ VKHR_B200_API int vkhr_b200_combine_peer_u8_sparse_dev(
  *   signals[r]   2 x 16 uint32 words, zero-filled once before the first call
  * All ranks must make the same sequence of sharded calls (the barriers pair up by call count).  Ranks that share ONE
  * device (tests) must have made a plain voxelisation at this resolution before: a context's first call allocates its
- * scratch, and a device memory allocation serialises the device's streams -- behind another rank's waiting barrier. */
+ * scratch, and a device memory allocation serialises the device's streams -- behind another rank's waiting barrier.
+ * (For the same reason vkhr_b200_create loads the library's kernels eagerly: CUDA's lazy loading can synchronise the context.) */
 typedef struct vkhr_b200_shard_peers {
     uint32_t rank, world;                 /* world <= 16 */
     void* const* partials;

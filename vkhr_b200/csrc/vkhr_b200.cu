@@ -546,7 +546,10 @@ int run_voxelize(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool vertices_
     if (brick && !(flags & VKHR_B200_STRATEGY_BRICK8) && total_segments * 100ull < (uint64_t)n * nv) brick = false;
 
     ctx->last_strategy = brick ? VKHR_B200_STRATEGY_BRICK8 : packed ? VKHR_B200_STRATEGY_PACKED8 : VKHR_B200_STRATEGY_COUNT32;
-    if (brick && !(flags & VKHR_B200_BRICK8_SPLIT)) {
+    // the frame kernel pays where at least two scratch volumes fit its L2-resident ring (256^3: 16 MiB of 64); one big
+    // volume (512^3 and up) is copied out faster by the whole machine at once -- the separate kernels (measured on B200:
+    // 3.25 M segments at 512^3 0.109 ms split, 0.141 ms frame; one ponytail at 256^3 0.042 ms split, 0.035 ms frame)
+    if (brick && !(flags & VKHR_B200_BRICK8_SPLIT) && 2 * nv <= ctx->ring_budget) {
         bool small = true;
         for (uint32_t k = 0; k < n; ++k) small = small && jobs[k].grid.small_grid;
         const int rc = run_frame(ctx, jobs, n, small, s);
@@ -837,6 +840,24 @@ int vkhr_b200_create(int device, vkhr_b200_ctx** out) {
         cudaStreamDestroy(ctx->stream);
         delete ctx;
         return VKHR_B200_ERR_OUT_OF_MEMORY;
+    }
+    // CUDA loads kernels lazily, at their first launch, and loading can synchronise the context -- behind a kernel of
+    // another rank that is WAITING for this rank (the device-side barrier of a sharded call on a shared device), that is a
+    // deadlock.  So the kernels a sharded call can launch are loaded here, while nothing is waiting for anything.
+    {
+        cudaFuncAttributes fa;
+        const void* eager[] = {(const void*)k_peer_barrier, (const void*)k_chunk_bitmap, (const void*)k_combine_peer_u8_sparse,
+                               (const void*)k_combine_peer_u8, (const void*)k_frame<3, 3>, (const void*)k_frame<4, 4>,
+                               (const void*)k_walk_uniform<3, 3>, (const void*)k_walk_uniform<4, 4>, (const void*)k_walk_indexed<3, 3>,
+                               (const void*)k_walk_indexed<4, 4>, (const void*)k_walk_uniform<1, 0>, (const void*)k_walk_uniform<1, 1>,
+                               (const void*)k_walk_uniform<1, 2>, (const void*)k_walk_indexed<1, 0>, (const void*)k_walk_indexed<1, 1>,
+                               (const void*)k_walk_uniform<0, 0>, (const void*)k_walk_uniform<0, 1>, (const void*)k_walk_uniform<0, 2>,
+                               (const void*)k_walk_indexed<0, 0>, (const void*)k_walk_indexed<0, 1>, (const void*)k_clamp_counts<true>,
+                               (const void*)k_clamp_counts_unaligned<true>, (const void*)k_untile_batch, (const void*)k_clear_packed_batch,
+                               (const void*)k_brick_verdict, (const void*)k_repair_packed<false>, (const void*)k_minmax_init,
+                               (const void*)k_minmax_u8, (const void*)k_normalize_apply};
+        for (const void* k : eager)
+            if (cudaFuncGetAttributes(&fa, k) != cudaSuccess) (void)cudaGetLastError();
     }
     *out = ctx;
     return VKHR_B200_OK;
