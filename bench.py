@@ -427,6 +427,19 @@ def strand_sharded(vox, dev, rank: int, world: int, reps: int = 10) -> dict:
             res[schedule] = {"ms": ms, "value": n * s / ms / 1e3, "unit": UNIT,
                              "nvlink_bytes_per_gpu" + ("_upper_bound_sparse_exchange" if schedule == "p2p" else ""): int(nvlink[schedule])}
             vols[schedule] = vol[:nv].clone()
+            if schedule == "p2p":
+                # where the time goes on this rank: the library's per-phase CUDA events (a separate pass)
+                vox.profile_enable(True)
+                vox.profile_read()
+                for _ in range(reps):
+                    sv.voxelize_segments(mine_t, None, s, lo, size, W, W, W, schedule="p2p")
+                torch.cuda.synchronize()
+                pr = vox.profile_read()
+                vox.profile_enable(False)
+                res[schedule]["phases_ms_rank0"] = {"shard_voxelisation": (pr["walk"]["ms"] + pr["finish"]["ms"]) / reps,
+                                                    "chunk_bitmap_and_output_clear": pr["clear"]["ms"] / reps,
+                                                    "first_barrier_(waiting_for_the_slowest_rank)": pr["normalize"]["ms"] / reps,
+                                                    "fused_combine_and_second_barrier": pr["prefilter"]["ms"] / reps}
         except Exception as e:  # noqa: BLE001
             res[schedule] = {"error": str(e)[:300]}
     # the one-GPU volume of the whole set (rank 0 alone; the others wait), and the comparison

@@ -220,7 +220,7 @@ constexpr uint32_t kTileStride = 31;          // segments (= new vertices) per w
 constexpr uint32_t kRangeFloats = 3u * kTileStride * kTilesPerWarp;   // 744 floats = 2976 bytes (a multiple of 16)
 constexpr uint32_t kNeedFloats = kRangeFloats + 3u;                   // + the tip vertex of the range's last segment
 constexpr uint32_t kBulkBytes = ((kNeedFloats * 4u + 15u) / 16u) * 16u;   // 3008: what one bulk copy moves
-constexpr uint32_t kStageFloats = 768u;       // shared-memory slot of one warp (>= kBulkBytes / 4, 24 x 32)
+constexpr uint32_t kStageFloats = 752u;       // shared-memory slot of one warp (= kBulkBytes / 4; two per warp must fit 48 KB of static shared memory)
 static_assert(kRangeFloats * 4u % 16u == 0 && kBulkBytes <= kStageFloats * 4u, "bulk copy geometry");
 
 // mbarrier + 1-D bulk copy (TMA unit, `cp.async.bulk`, SASS UBLKCP): global -> shared without passing
@@ -474,7 +474,7 @@ struct FramePlan {
     uint32_t ring;                                              // scratch slots
     uint32_t copiers;                                           // CTAs of an instance that copy it out (the last ones by block index)
     uint32_t n_bricks;
-    uint32_t pad;
+    uint32_t copiers_last;                                      // ... of the batch's LAST instance: nothing walks beside its copy-out, so more hands
     uint8_t* ring_base;
     unsigned long long slot_bytes;
     FrameCtl* ctl;
@@ -498,8 +498,9 @@ __device__ __forceinline__ void frame_wait_ge(const uint32_t* p, uint32_t need) 
 template <int MODE, int EXACT>
 __global__ void __launch_bounds__(kWalkThreads, VKHR_FRAME_MIN_CTAS)
 k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
-    __shared__ __align__(128) float s_stage[kWarpsPerBlock][kStageFloats];
-    __shared__ __align__(8) unsigned long long s_bar[kWarpsPerBlock];
+    // two stage buffers per warp: the vertices of a warp's next range are in flight while it walks the current one
+    __shared__ __align__(128) float s_stage[2][kWarpsPerBlock][kStageFloats];
+    __shared__ __align__(8) unsigned long long s_bar[2][kWarpsPerBlock];
     __shared__ unsigned long long s_sum[kWarpsPerBlock];
     __shared__ uint32_t s_last;
     const uint32_t i = blockIdx.y;
@@ -507,8 +508,8 @@ k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
     const uint32_t items = max(I.n_tiles, 1u);                     // CTAs of this instance (one for an instance without segments: its copy-out)
     if (blockIdx.x >= items) return;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t bar = smem_u32(&s_bar[warp]);
-    if (lane == 0) mbar_init(bar, 1);
+    const uint32_t bar[2] = {smem_u32(&s_bar[0][warp]), smem_u32(&s_bar[1][warp])};
+    if (lane == 0) { mbar_init(bar[0], 1); mbar_init(bar[1], 1); }
     __syncwarp();
     FrameCtl* const ctl = P.ctl;
     if (i == 0 && blockIdx.x == 0) {                               // the next call's control block (nobody uses it during this call)
@@ -516,7 +517,7 @@ k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
         for (uint32_t k = threadIdx.x; k < sizeof(FrameCtl) / 16u; k += blockDim.x) z[k] = make_uint4(0, 0, 0, 0);
     }
     uint8_t* const slot = P.ring_base + (unsigned long long)(i % P.ring) * P.slot_bytes;
-    const uint32_t copiers = min(items, P.copiers);
+    const uint32_t copiers = min(items, i + 1u == gridDim.y ? P.copiers_last : P.copiers);
     const bool uniform_item = blockIdx.x < I.n_tiles && I.kind == WK_UNIFORM;
 
     // ---- the walk ------------------------------------------------------------------------------------------------
@@ -524,21 +525,25 @@ k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
         auto sink = SinkOf<MODE>::make(I);
         sink.words = reinterpret_cast<uint32_t*>(slot);
         sink.words_pin();
-        uint32_t parity = 0;
+        uint32_t parity[2] = {0, 0};
         // the first range's vertices are on their way while the slot is checked
         uint32_t range = blockIdx.x * kFrameRanges * kWarpsPerBlock + warp;
-        bool bulk = uniform_item && stage_range(I, range, s_stage[warp], bar);
+        bool bulk = uniform_item && stage_range(I, range, s_stage[0][warp], bar[0]);
         if (i >= P.ring) {                                         // the slot's previous tenant, instance i - ring, has been copied out
             const uint32_t prev_items = max(B.inst[i - P.ring].n_tiles, 1u);
             frame_wait_ge(&ctl->copy_done[i - P.ring], min(prev_items, P.copiers));
         }
         if (uniform_item) {
-            for (uint32_t rr = 0;;) {
-                walk_range<EXACT>(I, range, s_stage[warp], bar, bulk, parity, sink);
-                if (++rr == kFrameRanges) break;
+#pragma unroll
+            for (uint32_t rr = 0; rr < kFrameRanges; ++rr) {
+                const uint32_t b = rr & 1u;
+                bool bulk_nxt = false;
+                if (rr + 1u < kFrameRanges)                        // (buffer b ^ 1 was last read two ranges ago, by this warp)
+                    bulk_nxt = stage_range(I, range + kWarpsPerBlock, s_stage[b ^ 1u][warp], bar[b ^ 1u]);
+                walk_range<EXACT>(I, range, s_stage[b][warp], bar[b], bulk, parity[b], sink);
                 __syncwarp();
                 range += kWarpsPerBlock;
-                bulk = stage_range(I, range, s_stage[warp], bar);
+                bulk = bulk_nxt;
             }
         } else if (blockIdx.x < I.n_tiles) {
             for (uint32_t j = 0; j < kFrameIndexedSegs / kWalkThreads; ++j)

@@ -487,8 +487,9 @@ int run_frame(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool small, cudaS
         FramePlan P{};
         P.ring = std::min(ring, m);
         // copiers: few while other instances keep the machine busy (they hold CTA slots while they wait and copy), many
-        // when the copy-out is the tail of the call
-        P.copiers = m >= 4 ? 64u : 256u;
+        // for the last instance, whose copy-out is the tail of the call
+        P.copiers = 64u;
+        P.copiers_last = 256u;
         P.n_bricks = (uint32_t)(nv / 32);
         uint32_t max_items = 1;
         for (uint32_t p = 0; p < m; ++p) max_items = std::max(max_items, ctx->batch.inst[p].n_tiles);
@@ -1137,19 +1138,28 @@ int vkhr_b200_voxelize_segments_sharded_dev(vkhr_b200_ctx* ctx, const float* d_v
     else RET_IF(vkhr_b200_voxelize_segments_dev(ctx, d_vertices, n_vertices, d_indices, n_indices, segs_per_strand, nullptr, aabb_origin,
                                                 aabb_size, W, H, D, flags & ~(uint32_t)VKHR_B200_NORMALIZE, partial, nullptr, s));
     // 2. which 16-byte chunks of it hold anything; the output starts from zero (peers store only non-zero results)
-    RET_IF(vkhr_b200_chunk_bitmap_dev(ctx, partial, nvp, static_cast<uint32_t*>(peers->bitmaps[rank]), s));
-    CU_CHECK(ctx, cudaMemsetAsync(out, 0, nvp, s));
+    {
+        PhaseMark mk(ctx, s, PH_CLEAR);
+        RET_IF(vkhr_b200_chunk_bitmap_dev(ctx, partial, nvp, static_cast<uint32_t*>(peers->bitmaps[rank]), s));
+        CU_CHECK(ctx, cudaMemsetAsync(out, 0, nvp, s));
+    }
     // 3. barrier, combine my slab from all partials into all outputs, barrier
     PeerSignals S{};
     S.n = world; S.rank = rank;
     for (uint32_t r = 0; r < world; ++r) S.pad[r] = static_cast<uint32_t*>(peers->signals[r]);
     const uint32_t epoch = ++ctx->shard_epoch;
-    k_peer_barrier<<<1, 32, 0, s>>>(S, 0u, epoch);
-    ctx->launches++;
-    RET_IF(vkhr_b200_combine_peer_u8_sparse_dev(ctx, reinterpret_cast<const void* const*>(peers->partials),
-                                                reinterpret_cast<const void* const*>(peers->bitmaps), peers->outs, world, (uint64_t)rank * slab, slab, s));
-    k_peer_barrier<<<1, 32, 0, s>>>(S, 1u, epoch);
-    ctx->launches++;
+    {
+        PhaseMark mk(ctx, s, PH_NORMALIZE);                        // (profile slot [3]: the first barrier = waiting for the slowest rank)
+        k_peer_barrier<<<1, 32, 0, s>>>(S, 0u, epoch);
+        ctx->launches++;
+    }
+    {
+        PhaseMark mk(ctx, s, PH_PREFILTER);                        // (profile slot [4]: the fused combine + the second barrier)
+        RET_IF(vkhr_b200_combine_peer_u8_sparse_dev(ctx, reinterpret_cast<const void* const*>(peers->partials),
+                                                    reinterpret_cast<const void* const*>(peers->bitmaps), peers->outs, world, (uint64_t)rank * slab, slab, s));
+        k_peer_barrier<<<1, 32, 0, s>>>(S, 1u, epoch);
+        ctx->launches++;
+    }
     CU_CHECK(ctx, cudaGetLastError());
     if (flags & VKHR_B200_NORMALIZE) RET_IF(vkhr_b200_normalize_dev(ctx, out, nv, s));
     return VKHR_B200_OK;
