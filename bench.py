@@ -409,7 +409,8 @@ def strand_sharded(vox, dev, rank: int, world: int, reps: int = 10) -> dict:
     if world == 1:
         lo, hi = vox.generate_bounding_box_dev(mine_t).cpu().numpy().reshape(2, 3)
         size = (hi - lo).astype(np.float32)
-        ms, _ = timed(lambda: vox.voxelize_segments_dev(mine_t, None, lo, size, W, W, W, segs_per_strand=s))
+        out1 = torch.empty(W ** 3, dtype=torch.uint8, device=dev)
+        ms, _ = timed(lambda: vox.voxelize_segments_dev(mine_t, None, lo, size, W, W, W, segs_per_strand=s, out=out1))
         res["one_gpu"] = {"ms": ms, "value": n * s / ms / 1e3, "unit": UNIT}
         return res
     sv = sharding.ShardedVoxelizer(vox)
@@ -449,7 +450,8 @@ def strand_sharded(vox, dev, rank: int, world: int, reps: int = 10) -> dict:
         full_t = torch.from_numpy(full).to(dev).reshape(-1)
         flo, fhi = vox.generate_bounding_box_dev(full_t).cpu().numpy().reshape(2, 3)
         res["aabb_equals_whole_set"] = bool(np.array_equal(flo, lo) and np.array_equal(fhi, hi))
-        ms1, ref = timed_local(lambda: vox.voxelize_segments_dev(full_t, None, lo, size, W, W, W, segs_per_strand=s), reps)
+        out1 = torch.empty(W ** 3, dtype=torch.uint8, device=dev)
+        ms1, ref = timed_local(lambda: vox.voxelize_segments_dev(full_t, None, lo, size, W, W, W, segs_per_strand=s, out=out1), reps)
         res["one_gpu"] = {"ms": ms1, "value": n * s / ms1 / 1e3, "unit": UNIT}
         for name, v in vols.items():
             same = bool(torch.equal(v, ref))

@@ -463,6 +463,10 @@ constexpr uint32_t kFrameIndexedSegs = 2048;                    // segments per 
 #ifndef VKHR_FRAME_MIN_CTAS
 #define VKHR_FRAME_MIN_CTAS 4
 #endif
+#ifndef VKHR_FRAME_STAGES
+#define VKHR_FRAME_STAGES 1
+#endif
+constexpr uint32_t kFrameStages = VKHR_FRAME_STAGES;            // vertex stage buffers per warp
 constexpr uint32_t kFrameRanges = VKHR_FRAME_RANGES;            // warp-ranges a warp walks per item: the item's fixed costs (fence, report) are paid once
 struct FrameCtl {
     uint32_t walk_done[kMaxBatch];                              // CTAs of the instance that have reported
@@ -498,9 +502,10 @@ __device__ __forceinline__ void frame_wait_ge(const uint32_t* p, uint32_t need) 
 template <int MODE, int EXACT>
 __global__ void __launch_bounds__(kWalkThreads, VKHR_FRAME_MIN_CTAS)
 k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
-    // two stage buffers per warp: the vertices of a warp's next range are in flight while it walks the current one
-    __shared__ __align__(128) float s_stage[2][kWarpsPerBlock][kStageFloats];
-    __shared__ __align__(8) unsigned long long s_bar[2][kWarpsPerBlock];
+    // kFrameStages = 2: the vertices of a warp's next range are in flight while it walks the current one (measured: no
+    // gain -- 1.12 ms against 1.08 ms per crowd frame with one buffer, which leaves twice the L1; profiles/r02_m_*)
+    __shared__ __align__(128) float s_stage[kFrameStages][kWarpsPerBlock][kStageFloats];
+    __shared__ __align__(8) unsigned long long s_bar[kFrameStages][kWarpsPerBlock];
     __shared__ unsigned long long s_sum[kWarpsPerBlock];
     __shared__ uint32_t s_last;
     const uint32_t i = blockIdx.y;
@@ -508,8 +513,8 @@ k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
     const uint32_t items = max(I.n_tiles, 1u);                     // CTAs of this instance (one for an instance without segments: its copy-out)
     if (blockIdx.x >= items) return;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t bar[2] = {smem_u32(&s_bar[0][warp]), smem_u32(&s_bar[1][warp])};
-    if (lane == 0) { mbar_init(bar[0], 1); mbar_init(bar[1], 1); }
+    const uint32_t bar[2] = {smem_u32(&s_bar[0][warp]), smem_u32(&s_bar[kFrameStages - 1u][warp])};
+    if (lane == 0) { mbar_init(bar[0], 1); if (kFrameStages > 1u) mbar_init(bar[1], 1); }
     __syncwarp();
     FrameCtl* const ctl = P.ctl;
     if (i == 0 && blockIdx.x == 0) {                               // the next call's control block (nobody uses it during this call)
@@ -536,13 +541,14 @@ k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
         if (uniform_item) {
 #pragma unroll
             for (uint32_t rr = 0; rr < kFrameRanges; ++rr) {
-                const uint32_t b = rr & 1u;
+                const uint32_t b = kFrameStages > 1u ? (rr & 1u) : 0u, nb = kFrameStages > 1u ? (b ^ 1u) : 0u;
                 bool bulk_nxt = false;
-                if (rr + 1u < kFrameRanges)                        // (buffer b ^ 1 was last read two ranges ago, by this warp)
-                    bulk_nxt = stage_range(I, range + kWarpsPerBlock, s_stage[b ^ 1u][warp], bar[b ^ 1u]);
+                if (kFrameStages > 1u && rr + 1u < kFrameRanges)   // (buffer nb was last read two ranges ago, by this warp)
+                    bulk_nxt = stage_range(I, range + kWarpsPerBlock, s_stage[nb][warp], bar[nb]);
                 walk_range<EXACT>(I, range, s_stage[b][warp], bar[b], bulk, parity[b], sink);
                 __syncwarp();
                 range += kWarpsPerBlock;
+                if (kFrameStages == 1u && rr + 1u < kFrameRanges) bulk_nxt = stage_range(I, range, s_stage[0][warp], bar[0]);
                 bulk = bulk_nxt;
             }
         } else if (blockIdx.x < I.n_tiles) {
