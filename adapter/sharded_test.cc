@@ -60,11 +60,11 @@ int main() {
         for (uint32_t r = 0; r < world; ++r) {
             CHECK(nullptr, vkhr_b200_create(0, &ctx[r]));
             CHECK(ctx[r], vkhr_b200_malloc(ctx[r], nvp, &partials[r]));
-            CHECK(ctx[r], vkhr_b200_malloc(ctx[r], 2 * (nvp / 512) * 4, &bitmaps[r]));
+            CHECK(ctx[r], vkhr_b200_malloc(ctx[r], nvp / 512 * 4, &bitmaps[r]));
             CHECK(ctx[r], vkhr_b200_malloc(ctx[r], nvp, &outs[r]));
-            CHECK(ctx[r], vkhr_b200_malloc(ctx[r], 4 * 16 * 4, &signals[r]));
+            CHECK(ctx[r], vkhr_b200_malloc(ctx[r], 2 * 16 * 4, &signals[r]));
             CHECK(ctx[r], vkhr_b200_memset(ctx[r], partials[r], 0, nvp, nullptr));
-            CHECK(ctx[r], vkhr_b200_memset(ctx[r], signals[r], 0, 4 * 16 * 4, nullptr));
+            CHECK(ctx[r], vkhr_b200_memset(ctx[r], signals[r], 0, 2 * 16 * 4, nullptr));
             const size_t nverts = size_t(first[r + 1] - first[r]) * vps;
             CHECK(ctx[r], vkhr_b200_malloc(ctx[r], nverts * 12 + 16, &verts[r]));
             CHECK(ctx[r], vkhr_b200_upload(ctx[r], verts[r], xyz.data() + size_t(first[r]) * vps * 3, nverts * 12, nullptr));

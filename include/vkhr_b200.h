@@ -260,19 +260,16 @@ VKHR_B200_API int vkhr_b200_combine_peer_u8_sparse_dev(
  * the reference's counter only saturates (hair_style.cc:322-325), so
  *   min(sum_r min(count_r, 255), 255) == min(sum_r count_r, 255).
  * Steps, all enqueued on `stream`: the rank's shard is voxelised into its partial volume (the single-GPU path, u8);
- * one bit per 16-byte chunk of the partial is published; a device-side barrier over the signal pads; one kernel loads
+ * one bit per 16-byte chunk of the partial is published; a device-side barrier over the signal pads; ONE kernel reads
  * the rank's slab of every peer's partial straight from the peers' memory over NVLink (only the chunks the bitmaps mark),
- * adds with saturation and stores the slab into the rank's own output, with a bitmap of the result; a second barrier;
- * one kernel pulls the other ranks' slabs, chunk by marked chunk, from their owners' outputs.  No NCCL, no host round
- * trip.  On return (stream-ordered) outs[rank] is complete; peers may still be READING it: do not overwrite or free an
- * output before every rank has synchronised (a further sharded call is fine: it waits for those reads itself).
+ * adds with saturation and stores the slab into every peer's output; a second barrier.  No NCCL, no host round trip.
  *
  * The caller provides peer-mapped buffers (cudaIpc / cuMem / torch symmetric memory; on one device -- "fake ranks",
  * one context and stream per rank -- plain device pointers): for every rank r, as mapped into THIS process,
  *   partials[r]  padded volume bytes (vkhr_b200_sharded_volume_bytes), zero-filled once before the first call
- *   bitmaps[r]   2 x padded bytes / 512 uint32 words (partial bitmap, result bitmap)
+ *   bitmaps[r]   padded bytes / 512 uint32 words
  *   outs[r]      padded volume bytes; the result of rank r
- *   signals[r]   4 x 16 uint32 words, zero-filled once before the first call
+ *   signals[r]   2 x 16 uint32 words, zero-filled once before the first call
  * All ranks must make the same sequence of sharded calls (the barriers pair up by call count).  Ranks that share ONE
  * device (tests) must have made a plain voxelisation at this resolution before: a context's first call allocates its
  * scratch, and a device memory allocation serialises the device's streams -- behind another rank's waiting barrier.

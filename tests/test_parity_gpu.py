@@ -935,9 +935,9 @@ def test_sharded_entry_point_with_fake_ranks_on_one_device(port, k):
     nvp = ranks[0].sharded_volume_bytes(W, H, D, k)
     assert nvp % (512 * k) == 0 and nvp >= nv
     partials = [torch.zeros(nvp, dtype=torch.uint8, device=dev) for _ in range(k)]
-    bitmaps = [torch.zeros(2 * (nvp // 512), dtype=torch.int32, device=dev) for _ in range(k)]
+    bitmaps = [torch.zeros(nvp // 512, dtype=torch.int32, device=dev) for _ in range(k)]
     outs = [torch.full((nvp,), 9, dtype=torch.uint8, device=dev) for _ in range(k)]
-    signals = [torch.zeros(64, dtype=torch.int32, device=dev) for _ in range(k)]
+    signals = [torch.zeros(32, dtype=torch.int32, device=dev) for _ in range(k)]
     ptrs = lambda ts: [t.data_ptr() for t in ts]   # noqa: E731
     # ONE DEVICE ONLY: a context's first voxelisation allocates its scratch, and a device memory allocation serialises the
     # device's streams (CUDA's implicit synchronisation) -- inside a sharded call that would put rank r + 1's kernels behind

@@ -996,76 +996,6 @@ k_combine_peer_u8_sparse(const __grid_constant__ PeerPtrsSparse P, uint64_t off1
     }
 }
 
-// The sharded call's exchange as PULLS (round 2; the push form above stores every non-zero 16-byte chunk into seven remote
-// outputs, and NVLink carries 16-byte writes at a fraction of its bandwidth: 0.29 ms for the combine at 8 GPUs and 512^3).
-//   A  k_combine_pull: the owner of a slab loads the marked chunks of every peer's partial (remote loads), adds with
-//      saturation, stores the slab into ITS OWN output only, and publishes one bit per chunk of the RESULT
-//      (warp ballot) -- reduce-scatter + clamp, local stores only;
-//   B  k_gather_pull: every rank then pulls the other ranks' finished slabs, chunk by marked chunk, from the owners'
-//      outputs into its own (pre-zeroed) output -- all-gather with 16-byte remote loads, four bitmap words per warp in
-//      flight.
-__global__ void __launch_bounds__(256)
-k_combine_pull(const __grid_constant__ PeerPtrsSparse P, uint32_t rank, uint64_t off16, uint64_t slab16, uint32_t* __restrict__ result_bits) {
-    const uint32_t lane = threadIdx.x & 31u;
-    // slab16 is a multiple of 32: whole warps, one result word per warp-iteration
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < slab16; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t c = off16 + i;
-        uint32_t have = 0;
-#pragma unroll
-        for (uint32_t r = 0; r < kMaxPeers; ++r)
-            if (r < P.n) have |= ((__ldcg(P.bits[r] + (c >> 5)) >> lane) & 1u) << r;
-        uint4 acc = make_uint4(0, 0, 0, 0);
-        if (have) {
-#pragma unroll
-            for (uint32_t r = 0; r < kMaxPeers; ++r)
-                if (r < P.n && ((have >> r) & 1u)) {
-                    const uint4 v = __ldcg(P.part[r] + c);
-                    acc.x = __vaddus4(acc.x, v.x); acc.y = __vaddus4(acc.y, v.y); acc.z = __vaddus4(acc.z, v.z); acc.w = __vaddus4(acc.w, v.w);
-                }
-            __stcg(P.out[rank] + c, acc);
-        }
-        const uint32_t bits = __ballot_sync(0xFFFFFFFFu, (acc.x | acc.y | acc.z | acc.w) != 0u);
-        if (lane == 0) result_bits[c >> 5] = bits;
-    }
-}
-struct PeerGather {
-    const uint4* out[kMaxPeers];          // every rank's output volume
-    const uint32_t* rbits[kMaxPeers];     // every rank's RESULT bitmap (valid in the rank's own slab)
-    uint32_t n, rank;
-};
-__global__ void __launch_bounds__(256)
-k_gather_pull(const __grid_constant__ PeerGather G, uint64_t slab16) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint64_t words_per_slab = slab16 >> 5;
-    const uint64_t n_words = words_per_slab * (G.n - 1u);         // bitmap words of the OTHER ranks' slabs
-    uint4* __restrict__ mine = const_cast<uint4*>(G.out[G.rank]);
-    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t w0 = warp0 * 4u; w0 < n_words; w0 += n_warps * 4u) {
-        uint32_t bits[4];
-        uint64_t chunk0[4];
-        uint32_t owner[4];
-#pragma unroll
-        for (uint32_t k = 0; k < 4u; ++k) {
-            bits[k] = 0u; chunk0[k] = 0; owner[k] = 0;
-            const uint64_t w = w0 + k;
-            if (w < n_words) {
-                uint32_t q = (uint32_t)(w / words_per_slab);          // the k-th other rank ...
-                if (q >= G.rank) ++q;                                  // ... skipping this one
-                const uint64_t gw = (uint64_t)q * words_per_slab + (w % words_per_slab);   // word of the whole volume
-                owner[k] = q; chunk0[k] = gw << 5;
-                bits[k] = __ldcg(G.rbits[q] + gw);
-            }
-        }
-        uint4 v[4];
-#pragma unroll
-        for (uint32_t k = 0; k < 4u; ++k)
-            if ((bits[k] >> lane) & 1u) v[k] = __ldcg(G.out[owner[k]] + chunk0[k] + lane);
-#pragma unroll
-        for (uint32_t k = 0; k < 4u; ++k)
-            if ((bits[k] >> lane) & 1u) __stcs(mine + chunk0[k] + lane, v[k]);
-    }
-}
-
 // Device-side barrier of the ranks of a strand-sharded voxelisation, over peer memory: every rank owns a signal pad
 // (kMaxPeers words per slot) mapped into all ranks; rank r stores the call's epoch into word [slot][r] of EVERY pad and
 // then waits until all words of its own pad have reached the epoch.  One CTA; the stream order of the launching rank puts

@@ -848,7 +848,7 @@ int vkhr_b200_create(int device, vkhr_b200_ctx** out) {
     {
         cudaFuncAttributes fa;
         const void* eager[] = {(const void*)k_peer_barrier, (const void*)k_chunk_bitmap, (const void*)k_combine_peer_u8_sparse,
-                               (const void*)k_combine_peer_u8, (const void*)k_combine_pull, (const void*)k_gather_pull, (const void*)k_frame<3, 3>, (const void*)k_frame<4, 4>,
+                               (const void*)k_combine_peer_u8, (const void*)k_frame<3, 3>, (const void*)k_frame<4, 4>,
                                (const void*)k_walk_uniform<3, 3>, (const void*)k_walk_uniform<4, 4>, (const void*)k_walk_indexed<3, 3>,
                                (const void*)k_walk_indexed<4, 4>, (const void*)k_walk_uniform<1, 0>, (const void*)k_walk_uniform<1, 1>,
                                (const void*)k_walk_uniform<1, 2>, (const void*)k_walk_indexed<1, 0>, (const void*)k_walk_indexed<1, 1>,
@@ -1137,45 +1137,28 @@ int vkhr_b200_voxelize_segments_sharded_dev(vkhr_b200_ctx* ctx, const float* d_v
     if (empty) CU_CHECK(ctx, cudaMemsetAsync(partial, 0, nv, s));
     else RET_IF(vkhr_b200_voxelize_segments_dev(ctx, d_vertices, n_vertices, d_indices, n_indices, segs_per_strand, nullptr, aabb_origin,
                                                 aabb_size, W, H, D, flags & ~(uint32_t)VKHR_B200_NORMALIZE, partial, nullptr, s));
+    // 2. which 16-byte chunks of it hold anything; the output starts from zero (peers store only non-zero results)
+    {
+        PhaseMark mk(ctx, s, PH_CLEAR);
+        RET_IF(vkhr_b200_chunk_bitmap_dev(ctx, partial, nvp, static_cast<uint32_t*>(peers->bitmaps[rank]), s));
+        CU_CHECK(ctx, cudaMemsetAsync(out, 0, nvp, s));
+    }
+    // 3. barrier, combine my slab from all partials into all outputs, barrier
     PeerSignals S{};
     S.n = world; S.rank = rank;
     for (uint32_t r = 0; r < world; ++r) S.pad[r] = static_cast<uint32_t*>(peers->signals[r]);
     const uint32_t epoch = ++ctx->shard_epoch;
-    const uint64_t bm_words = nvp / 512;                           // words of one bitmap
-    uint32_t* my_bits = static_cast<uint32_t*>(peers->bitmaps[rank]);
-    // 2. every rank has finished pulling the PREVIOUS call's result out of this rank's output (hidden behind step 1);
-    //    then: which 16-byte chunks of the partial hold anything, and the output starts from zero
-    {
-        PhaseMark mk(ctx, s, PH_CLEAR);
-        k_peer_barrier<<<1, 32, 0, s>>>(S, 2u, epoch);
-        RET_IF(vkhr_b200_chunk_bitmap_dev(ctx, partial, nvp, my_bits, s));
-        CU_CHECK(ctx, cudaMemsetAsync(out, 0, nvp, s));
-        ctx->launches++;
-    }
-    // 3. barrier; A: combine my slab from all partials into MY output (+ the result's chunk bitmap); barrier; B: pull the
-    //    other slabs from their owners
     {
         PhaseMark mk(ctx, s, PH_NORMALIZE);                        // (profile slot [3]: the first barrier = waiting for the slowest rank)
         k_peer_barrier<<<1, 32, 0, s>>>(S, 0u, epoch);
         ctx->launches++;
     }
     {
-        PhaseMark mk(ctx, s, PH_PREFILTER);                        // (profile slot [4]: combine, barrier, gather)
-        PeerPtrsSparse P{};
-        PeerGather G{};
-        P.n = G.n = world; G.rank = rank;
-        for (uint32_t r = 0; r < world; ++r) {
-            P.part[r] = static_cast<const uint4*>(peers->partials[r]);
-            P.bits[r] = static_cast<const uint32_t*>(peers->bitmaps[r]);
-            P.out[r] = static_cast<uint4*>(peers->outs[r]);
-            G.out[r] = static_cast<const uint4*>(peers->outs[r]);
-            G.rbits[r] = static_cast<const uint32_t*>(peers->bitmaps[r]) + bm_words;   // second half: the result bitmap
-        }
-        const uint64_t slab16 = slab / 16;
-        k_combine_pull<<<stride_blocks(ctx, slab16, 256, 8), 256, 0, s>>>(P, rank, (uint64_t)rank * slab16, slab16, my_bits + bm_words);
+        PhaseMark mk(ctx, s, PH_PREFILTER);                        // (profile slot [4]: the fused combine + the second barrier)
+        RET_IF(vkhr_b200_combine_peer_u8_sparse_dev(ctx, reinterpret_cast<const void* const*>(peers->partials),
+                                                    reinterpret_cast<const void* const*>(peers->bitmaps), peers->outs, world, (uint64_t)rank * slab, slab, s));
         k_peer_barrier<<<1, 32, 0, s>>>(S, 1u, epoch);
-        if (world > 1) k_gather_pull<<<stride_blocks(ctx, slab16 * (world - 1) / 4 + 1, 256, 8), 256, 0, s>>>(G, slab16);
-        ctx->launches += 3;
+        ctx->launches++;
     }
     CU_CHECK(ctx, cudaGetLastError());
     if (flags & VKHR_B200_NORMALIZE) RET_IF(vkhr_b200_normalize_dev(ctx, out, nv, s));

@@ -209,9 +209,9 @@ class ShardedVoxelizer:
         if cached is None or cached[0] != nvp:
             group = self.group if self.group is not None else self.dist.group.WORLD
             partial = symm_mem.empty(nvp, dtype=torch.uint8, device=dev)
-            bitmap = symm_mem.empty(2 * (nvp // 512), dtype=torch.int32, device=dev)     # partial bitmap + result bitmap
+            bitmap = symm_mem.empty(nvp // 512, dtype=torch.int32, device=dev)
             outbuf = symm_mem.empty(nvp, dtype=torch.uint8, device=dev)
-            signals = symm_mem.empty(4 * 16, dtype=torch.int32, device=dev)
+            signals = symm_mem.empty(2 * 16, dtype=torch.int32, device=dev)
             hp, hb, ho, hs = (symm_mem.rendezvous(t, group) for t in (partial, bitmap, outbuf, signals))
             partial.zero_()
             signals.zero_()
