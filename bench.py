@@ -286,6 +286,7 @@ def other_configs(vox, dev, args, flags=0):
     from harness import synth
     out = {}
     cases = [("configs[0] ponytail 256^3, one instance", "ponytail", 256, 8, False),
+             ("configs[0] ponytail 256^3, one instance, densities + tangent volume (the reference's default mode)", "ponytail", 256, 8, "tangents"),
              ("configs[1] Yuksel-straight-shaped 50,000 x 65 at 512^3", "straight", 512, 2, False),
              ("configs[1] Yuksel-curly-shaped 50,000 x 65 at 512^3", "curly", 512, 2, False),
              ("configs[4] animated ponytail frame at 1024^3 (voxelise only)", "ponytail", 1024, 1, False),
@@ -298,10 +299,14 @@ def other_configs(vox, dev, args, flags=0):
             vt = [torch.from_numpy(v).to(dev).reshape(-1).clone() for _ in range(copies)]
             o = [torch.empty(W ** 3, dtype=torch.uint8, device=dev) for _ in range(copies)]
             reps = 5 if prefilter else 20
+            tangents = prefilter == "tangents"
+            prefilter = prefilter is True
             pf = [torch.empty(W ** 3, dtype=torch.float32, device=dev) for _ in range(2)] if prefilter else None
+            to = [torch.empty(4 * W ** 3, dtype=torch.int8, device=dev) for _ in range(copies)] if tangents else None
 
             def once(r):
-                vox.voxelize_segments_dev(vt[r % copies], None, lo, size, W, W, W, segs_per_strand=s, out=o[r % copies], flags=flags)
+                vox.voxelize_segments_dev(vt[r % copies], None, lo, size, W, W, W, segs_per_strand=s, out=o[r % copies], flags=flags,
+                                          tangents_out=to[r % copies] if tangents else None)
                 if prefilter:
                     vox.prefilter_dev(o[r % copies], W, W, W, ao=pf[0], opacity=pf[1])
             for r in range(3):
@@ -314,11 +319,11 @@ def other_configs(vox, dev, args, flags=0):
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / reps
-            alg = 12 * v.shape[0] + W ** 3 + (W ** 3 * (1 + 4 * 2) if prefilter else 0)      # prefilter N^3 (1 + 4k)
+            alg = 12 * v.shape[0] + W ** 3 + (W ** 3 * (1 + 4 * 2) if prefilter else 0) + (4 * W ** 3 if tangents else 0)      # prefilter N^3 (1 + 4k)
             sname = {capi.STRATEGY_COUNT32: "count32", capi.STRATEGY_PACKED8: "packed8", capi.STRATEGY_BRICK8: "brick8"}.get(vox.last_strategy)
             out[name] = {"segments": n * s, "ms": ms, "value": n * s / ms / 1e3, "unit": UNIT, "strategy": sname,
                          "hbm_frac_whole_path": alg / (ms * 1e-3) / 1e9 / hbm_peak()[0]}
-            del vt, o, pf
+            del vt, o, pf, to
             torch.cuda.empty_cache()
         except Exception as e:  # noqa: BLE001
             out[name] = {"error": str(e)[:200]}

@@ -415,6 +415,13 @@ def test_tangent_volume_golden(vox, port, small_sets, res):
     d2, t2 = vox.voxelize_segments(v, None, bb[:3], bb[4:7], W, H, D, segs_per_strand=s, want_tangents=True)
     assert np.array_equal(d2, want_d)
     _assert_tangents_close(t2, want_t, want_d, f"uniform {tag}")
+    # device-resident call with a tangent output: the same bytes as the host-buffer call
+    import torch
+    dv = torch.from_numpy(v).cuda().reshape(-1)
+    dt = torch.empty(4 * W * H * D, dtype=torch.int8, device="cuda")
+    dd = vox.voxelize_segments_dev(dv, None, bb[:3], bb[4:7], W, H, D, segs_per_strand=s, tangents_out=dt)
+    torch.cuda.synchronize()
+    assert np.array_equal(dd.cpu().numpy(), d2) and np.array_equal(dt.cpu().numpy().reshape(-1, 4), t2.reshape(-1, 4))
     # order independence: reversing the strand order must not change a single byte
     order = np.arange(n)[::-1]
     vr = v.reshape(n, s + 1, 3)[order].reshape(-1, 3)

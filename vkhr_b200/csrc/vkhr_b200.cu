@@ -455,6 +455,9 @@ int launch_repair(vkhr_b200_ctx* ctx, uint32_t* scratch, cudaStream_t s) {
     return VKHR_B200_OK;
 }
 
+#ifndef VKHR_FRAME_COPIERS
+#define VKHR_FRAME_COPIERS 64u
+#endif
 // BRICK8 as ONE launch per batch: the frame kernel (kernels.cuh, k_frame) walks and copies out through a ring of
 // L2-resident scratch volumes; then the repair kernel looks at the verdict flags.  `small`: every grid <= 2^24 voxels.
 int run_frame(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool small, cudaStream_t s) {
@@ -488,7 +491,7 @@ int run_frame(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool small, cudaS
         P.ring = std::min(ring, m);
         // copiers: few while other instances keep the machine busy (they hold CTA slots while they wait and copy), many
         // for the last instance, whose copy-out is the tail of the call
-        P.copiers = 64u;
+        P.copiers = VKHR_FRAME_COPIERS;
         P.copiers_last = 256u;
         P.n_bricks = (uint32_t)(nv / 32);
         uint32_t max_items = 1;

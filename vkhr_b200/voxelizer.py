@@ -263,7 +263,9 @@ class Voxelizer:
             raise ValueError(f"{name} holds {t.numel()} elements, the call needs {int(n)}")
 
     def voxelize_segments_dev(self, vertices, indices, aabb_origin, aabb_size, W, H, D,
-                              segs_per_strand: int = 0, flags: int = 0, out=None, stream=None):
+                              segs_per_strand: int = 0, flags: int = 0, out=None, stream=None, tangents_out=None):
+        """Device-resident ``HairStyle::voxelize_segments``; ``tangents_out`` (int8, W*H*D*4) also asks for
+        ``Volume::tangents`` of normalize(tip - root) per segment (the reference's default mode, hair_style.cc:309-327)."""
         import torch
         self._check_dev(vertices, torch.float32, "vertices")
         if indices is not None:
@@ -273,12 +275,16 @@ class Voxelizer:
             out = torch.empty(n, dtype=torch.uint8, device=vertices.device)
         self._check_dev(out, torch.uint8, "out")
         self._check_size(out, n, "out")
+        if tangents_out is not None:
+            self._check_dev(tangents_out, torch.int8, "tangents_out")
+            self._check_size(tangents_out, 4 * n, "tangents_out")
         rc = lib.vkhr_b200_voxelize_segments_dev(
             self._h, C.c_void_p(vertices.data_ptr()), vertices.numel() // 3,
             None if indices is None else C.c_void_p(indices.data_ptr()),
             0 if indices is None else indices.numel(), int(segs_per_strand), None,
             capi.vec3(aabb_origin), capi.vec3(aabb_size), int(W), int(H), int(D), int(flags),
-            C.c_void_p(out.data_ptr()), None, self._torch_stream(stream))
+            C.c_void_p(out.data_ptr()), None if tangents_out is None else C.c_void_p(tangents_out.data_ptr()),
+            self._torch_stream(stream))
         capi.check(self._h, rc)
         return out
 
