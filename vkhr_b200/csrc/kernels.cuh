@@ -37,7 +37,7 @@ struct InstanceDev {
     uint32_t        n_tiles;        // CTAs this instance needs in its walk kernel
     uint32_t        kind;           // WalkKind
     uint32_t        vps_magic;      // floor(2^32 / (segs_per_strand + 1)) + 1   (strand-end test without a division)
-    uint32_t        pad;
+    uint32_t        tile_step;      // 31 mod (segs_per_strand + 1): how far the strand position moves from one warp-tile to the next
 };
 
 // A batch travels to the kernels as a __grid_constant__ parameter: every per-instance constant is then
@@ -269,6 +269,15 @@ __device__ __forceinline__ bool stage_range(const InstanceDev& I, uint32_t range
     const uint32_t n_floats = 3u * I.n_vertices;
     const float* __restrict__ verts = I.vertices;
     const uint32_t start = kRangeFloats * range;                // first float of the range
+    // the common case, decided by a handful of warp-uniform instructions: a whole range and its tip vertex inside a
+    // 16-byte aligned buffer -- one bulk copy of constant size, nothing to fill in by hand
+    if (start + kStageFloats <= n_floats && (reinterpret_cast<uintptr_t>(verts) & 15u) == 0u) {
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            bulk_load(smem_u32(stage), verts + start, kBulkBytes, bar);
+        }
+        return true;
+    }
     if (start >= n_floats) return false;
     const uint32_t need = min(kNeedFloats, n_floats - start);   // floats this warp reads from `stage`
     uint32_t bulk = 0;                                          // floats that arrive by bulk copy
@@ -289,9 +298,9 @@ __device__ __forceinline__ bool stage_range(const InstanceDev& I, uint32_t range
 // walk_range: the walk of a staged range.  `parity`: the phase of `bar` the bulk copy completes (flipped here); the
 // sink is the caller's (it calls finish()).  All 32 lanes call this together.
 template <int EXACT, class Sink>
-__device__ __forceinline__ void walk_range(const InstanceDev& I, uint32_t range, float* stage, uint32_t bar, bool bulk, uint32_t& parity, Sink& sink) {
+__device__ __forceinline__ void walk_range(const InstanceDev& I, const GridParams& g, uint32_t range, float* stage, uint32_t bar, bool bulk, uint32_t& parity, Sink& sink) {
+    // g: the caller's pin(I.grid) -- registers, not indexed constant loads, and loaded once per CTA, not once per range
     const uint32_t lane = threadIdx.x & 31u;
-    const GridParams g = pin(I.grid);                              // registers, not indexed constant loads
     const uint32_t n_vertices = I.n_vertices;
     const uint32_t n_warp_tiles = (n_vertices + kTileStride - 1u) / kTileStride;
     const uint32_t tile0 = range * kTilesPerWarp;
@@ -300,25 +309,23 @@ __device__ __forceinline__ void walk_range(const InstanceDev& I, uint32_t range,
     __syncwarp();
     if (n_tiles == 0) return;                                      // whole warps only
 
-    // ---- which of this lane's (up to) 8 vertices start a segment: bit j = tile j ---------------------------------
-    // vertex x starts a segment unless it is the last of its strand (x mod (segs + 1): one multiply-high division per
-    // range, then += 31 mod (segs + 1) per tile) or of the instance; lane 31 only supplies the tip of lane 30
-    uint32_t starts = 0;
+    // ---- which of this lane's vertices start a segment ---------------------------------------------------------
+    // vertex x starts a segment unless it is the last of its strand: r = x mod (segs + 1) (one multiply-high division
+    // per range, then += 31 mod (segs + 1) per tile) is segs.  Lane 31 only supplies the tip of lane 30: it is parked on
+    // r = segs.  No test against n_vertices: n_vertices is a multiple of segs + 1 (checked on the host), so the
+    // instance's last vertex ends a strand, and the lanes past it hold stage_range's filler -- one and the same point,
+    // segments of zero steps, which add nothing on either path of the walk.
+    // (sp1 = r + 1 in [1, vps] is what is kept, so that the test and the wrap need vps alone; vps and the step are pinned
+    // in registers: left to itself the compiler reloads them from the indexed constant bank for every tile)
+    const uint32_t vps = pin(I.segs_per_strand + 1u);
+    uint32_t sp1, r_step;
     {
-        const uint32_t vps = I.segs_per_strand + 1u, magic = I.vps_magic;   // floor(2^32 / vps) + 1: quotient exact or one too large
-        uint32_t x = kTileStride * tile0 + lane;
-        uint32_t r = x - __umulhi(x, magic) * vps, r_step = kTileStride - __umulhi(kTileStride, magic) * vps;
+        const uint32_t x = kTileStride * tile0 + lane;
+        uint32_t r = x - __umulhi(x, I.vps_magic) * vps;            // vps_magic = floor(2^32 / vps) + 1: quotient exact or one too large
         if ((int32_t)r < 0) r += vps;
-        if ((int32_t)r_step < 0) r_step += vps;
-#pragma unroll
-        for (uint32_t j = 0; j < kTilesPerWarp; ++j) {
-            starts |= (uint32_t)(x + 1u < n_vertices && r != vps - 1u) << j;
-            x += kTileStride;
-            r += r_step;
-            if (r >= vps) r -= vps;
-        }
-        if (lane >= kTileStride) starts = 0u;
-        starts = pin(starts);
+        const bool tip_only = lane >= kTileStride;
+        sp1 = tip_only ? vps : r + 1u;
+        r_step = pin(tip_only ? 0u : I.tile_step);                  // 31 mod (segs + 1), from the host
     }
 
     // ---- software-pipelined tile loop ------------------------------------------------------------------
@@ -351,8 +358,9 @@ __device__ __forceinline__ void walk_range(const InstanceDev& I, uint32_t range,
     transform();
     for (uint32_t k = n_tiles; k > 0u; --k) {
         if (k > 1u) fetch();                                       // warp-uniform
-        const bool active = (starts & 1u) != 0u;
-        starts >>= 1;
+        const bool active = sp1 != vps;
+        sp1 += r_step;
+        if (sp1 > vps) sp1 -= vps;
         bool walked = false;
         if constexpr (kInterior) if (fast_div) {
             const float dx = __fsub_rn(tx, px), dy = __fsub_rn(ty, py), dz = __fsub_rn(tz, pz);
@@ -373,6 +381,10 @@ __device__ __forceinline__ void walk_range(const InstanceDev& I, uint32_t range,
             }
             walk_voxel_space_warp<EXACT, false>(g, active, px, py, pz, tx, ty, tz, sink);
         }
+        // the lanes without a segment skipped the walk: meet them here.  (Left to itself the compiler reconverges
+        // behind the transform and runs its 19 instructions once for each half of the warp: 7 % of the frame kernel's
+        // instructions, ncu source page of round 2.)
+        __syncwarp();
         if (k > 1u) transform();
     }
 }
@@ -393,7 +405,8 @@ k_walk_uniform(const __grid_constant__ Batch B, uint32_t first) {
     sink.words_pin();
     const uint32_t range = blockIdx.x * kWarpsPerBlock + warp;     // this warp's range of kTilesPerWarp tiles
     const bool bulk = stage_range(I, range, s_stage[warp], bar);
-    walk_range<EXACT>(I, range, s_stage[warp], bar, bulk, parity, sink);
+    const GridParams g = pin(I.grid);
+    walk_range<EXACT>(I, g, range, s_stage[warp], bar, bulk, parity, sink);
     sink.finish();
 }
 
@@ -527,23 +540,20 @@ k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
         uint4* z = reinterpret_cast<uint4*>(P.ctl_next);
         for (uint32_t k = threadIdx.x; k < sizeof(FrameCtl) / 16u; k += blockDim.x) z[k] = make_uint4(0, 0, 0, 0);
     }
-    uint8_t* const slot = P.ring_base + (unsigned long long)(i % P.ring) * P.slot_bytes;
-    const uint32_t copiers = min(items, i + 1u == gridDim.y ? P.copiers_last : P.copiers);
+    const uint32_t n_inst = gridDim.y;
     const bool uniform_item = blockIdx.x < I.n_tiles && I.kind == WK_UNIFORM;
 
     // ---- the walk ------------------------------------------------------------------------------------------------
     {
         auto sink = SinkOf<MODE>::make(I);
-        sink.words = reinterpret_cast<uint32_t*>(slot);
         sink.words_pin();
+        const GridParams g = pin(I.grid);
         uint32_t parity[2] = {0, 0};
         // the first range's vertices are on their way while the slot is checked
         uint32_t range = blockIdx.x * kFrameRanges * kWarpsPerBlock + warp;
         bool bulk = uniform_item && stage_range(I, range, s_stage[0][warp], bar[0]);
-        if (i >= P.ring) {                                         // the slot's previous tenant, instance i - ring, has been copied out
-            const uint32_t prev_items = max(B.inst[i - P.ring].n_tiles, 1u);
-            frame_wait_ge(&ctl->copy_done[i - P.ring], min(prev_items, P.copiers));
-        }
+        if (i >= P.ring)                                           // the slot's previous tenant, instance i - ring, has been copied out
+            frame_wait_ge(&ctl->copy_done[i - P.ring], min(max(B.inst[i - P.ring + 1u].n_tiles, 1u), P.copiers));   // by CTAs of the instance behind it
         if (uniform_item) {
 #pragma unroll
             for (uint32_t rr = 0; rr < kFrameRanges; ++rr) {
@@ -551,7 +561,7 @@ k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
                 bool bulk_nxt = false;
                 if (kFrameStages > 1u && rr + 1u < kFrameRanges)   // (buffer nb was last read two ranges ago, by this warp)
                     bulk_nxt = stage_range(I, range + kWarpsPerBlock, s_stage[nb][warp], bar[nb]);
-                walk_range<EXACT>(I, range, s_stage[b][warp], bar[b], bulk, parity[b], sink);
+                walk_range<EXACT>(I, g, range, s_stage[b][warp], bar[b], bulk, parity[b], sink);
                 __syncwarp();
                 range += kWarpsPerBlock;
                 if (kFrameStages == 1u && rr + 1u < kFrameRanges) bulk_nxt = stage_range(I, range, s_stage[0][warp], bar[0]);
@@ -574,52 +584,88 @@ k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
         __threadfence();
         atomicAdd(&ctl->walk_done[i], 1u);
     }
-    if (blockIdx.x + copiers < items) return;                      // not one of the instance's last `copiers` CTAs: done
-
-    // ---- copier CTA c of the instance: brick order -> the x-fastest output volume, zeroing behind itself ---------
-    const uint32_t c = blockIdx.x - (items - copiers);
-    frame_wait_ge(&ctl->walk_done[i], items);                      // the CTAs still walking (all have started)
-    {
-        const uint32_t wrow = I.grid.W >> 2, byn = I.grid.H >> 2;  // words (= bricks) per row, brick rows per slab
-        const uint32_t wslab = wrow * I.grid.H;
-        uint4* __restrict__ src = reinterpret_cast<uint4*>(slot);
-        uint32_t* __restrict__ dst = reinterpret_cast<uint32_t*>(I.densities);
-        const uint4 z = make_uint4(0, 0, 0, 0);
-        uint32_t bytes = 0;                                        // < 2^32: at most 8160 per brick
-        const uint32_t per = ((P.n_bricks + copiers - 1u) / copiers + 31u) & ~31u;     // whole warp-rows of 32 bricks
-        const uint32_t b_end = min((c + 1u) * per, P.n_bricks);
-#pragma unroll 4
-        for (uint32_t b = c * per + threadIdx.x; b < b_end; b += kWalkThreads) {
-            const uint4 q0 = __ldcg(src + 2u * b), q1 = __ldcg(src + 2u * b + 1u);   // L2 is where the reds landed; L1 may be stale
-            bytes += __vsadu4(q0.x, 0u) + __vsadu4(q0.y, 0u) + __vsadu4(q0.z, 0u) + __vsadu4(q0.w, 0u) +
-                     __vsadu4(q1.x, 0u) + __vsadu4(q1.y, 0u) + __vsadu4(q1.z, 0u) + __vsadu4(q1.w, 0u);
-            const uint32_t bx = b % wrow, tt = b / wrow, by = tt % byn, bz = tt / byn;
-            uint32_t* o = dst + (size_t)(2u * bz) * wslab + (size_t)(4u * by) * wrow + bx;
-            __stcs(o, q0.x); __stcs(o + wrow, q0.y); __stcs(o + 2u * wrow, q0.z); __stcs(o + 3u * wrow, q0.w);
-            o += wslab;
-            __stcs(o, q1.x); __stcs(o + wrow, q1.y); __stcs(o + 2u * wrow, q1.z); __stcs(o + 3u * wrow, q1.w);
-            if ((q0.x | q0.y | q0.z | q0.w | q1.x | q1.y | q1.z | q1.w) != 0u) { __stcg(src + 2u * b, z); __stcg(src + 2u * b + 1u, z); }
+    // ---- the copy-out: brick order -> the x-fastest output volume, zeroing behind itself -------------------------
+    // Role 0: the last `copiers` CTAs of instance i copy out instance i - 1, an equal share of its bricks each.  Every
+    // CTA of instance i - 1 was dispatched before this one and has (almost always) reported by now: no CTA slot is
+    // held by a waiting copier, and the copy-out of an instance is spread over as many CTAs as the walk leaves time for.
+    // Role 1: nobody comes behind the batch's last instance -- its own last `copiers_last` CTAs wait for its walk and
+    // copy it out.
+#pragma unroll 1
+    for (uint32_t role = 0; role < 2u; ++role) {
+        if (role == 0u ? i == 0u : i + 1u != n_inst) continue;
+        const uint32_t t = role == 0u ? i - 1u : i;                // the instance copied out
+        const uint32_t copiers = min(items, role == 0u ? P.copiers : P.copiers_last);
+        if (blockIdx.x + copiers < items) continue;                // not one of instance i's last `copiers` CTAs
+        const uint32_t c = blockIdx.x - (items - copiers);
+        const InstanceDev& T = B.inst[t];
+        frame_wait_ge(&ctl->walk_done[t], max(T.n_tiles, 1u));     // every walk CTA of instance t has reported (acquire)
+        {
+            const uint32_t wrow = T.grid.W >> 2, byn = T.grid.H >> 2;  // words (= bricks) per row, brick rows per slab
+            const uint32_t wslab = wrow * T.grid.H;
+            // brick number -> (bx, by, bz) by multiply-high: m = floor((2^32 - 1) / d) + 1 gives the quotient or one more
+            // (then the remainder is negative); computed once per thread here -- in the loop the compiler re-derived both
+            // divisions, reciprocals included, for every brick (a quarter of the copy-out's instructions)
+            const uint32_t m_row = wrow > 1u ? 0xFFFFFFFFu / wrow + 1u : 0u;   // (a power of two: 2^32 / d itself, exact)
+            const uint32_t m_byn = byn > 1u ? 0xFFFFFFFFu / byn + 1u : 0u;
+            uint4* __restrict__ src = reinterpret_cast<uint4*>(T.brick);
+            uint32_t* __restrict__ dst = reinterpret_cast<uint32_t*>(T.densities);   // a volume of the frame kernel is at most 2^23 words
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            uint32_t bytes = 0;                                    // < 2^32: at most 8160 per brick
+            const uint32_t per = ((P.n_bricks + copiers - 1u) / copiers + 31u) & ~31u;     // whole warp-rows of 32 bricks
+            const uint32_t b_end = min((c + 1u) * per, P.n_bricks);
+            // Four bricks per thread and round: ALL eight 16-byte loads are issued before the first of them is used
+            // (as a plain unrolled loop each brick's loads stay behind the previous brick's stores to `src`).
+            constexpr uint32_t kInFlight = 4;
+            for (uint32_t b0 = c * per + threadIdx.x; b0 < b_end; b0 += kInFlight * kWalkThreads) {
+                uint4 q[kInFlight][2];
+#pragma unroll
+                for (uint32_t j = 0; j < kInFlight; ++j) {
+                    const uint32_t b = b0 + j * kWalkThreads;
+                    if (b < b_end) { q[j][0] = __ldcg(src + 2u * b); q[j][1] = __ldcg(src + 2u * b + 1u); }   // L2 is where the reds landed; L1 may be stale
+                    else { q[j][0] = z; q[j][1] = z; }
+                }
+#pragma unroll
+                for (uint32_t j = 0; j < kInFlight; ++j) {
+                    const uint32_t b = b0 + j * kWalkThreads;
+                    if (b >= b_end) break;
+                    const uint4 q0 = q[j][0], q1 = q[j][1];
+                    bytes = __dp4a(q0.x, 0x01010101u, bytes); bytes = __dp4a(q0.y, 0x01010101u, bytes);
+                    bytes = __dp4a(q0.z, 0x01010101u, bytes); bytes = __dp4a(q0.w, 0x01010101u, bytes);
+                    bytes = __dp4a(q1.x, 0x01010101u, bytes); bytes = __dp4a(q1.y, 0x01010101u, bytes);
+                    bytes = __dp4a(q1.z, 0x01010101u, bytes); bytes = __dp4a(q1.w, 0x01010101u, bytes);
+                    uint32_t tt = m_row ? __umulhi(b, m_row) : b, bx = b - tt * wrow;
+                    if ((int32_t)bx < 0) { bx += wrow; --tt; }
+                    uint32_t bz = m_byn ? __umulhi(tt, m_byn) : tt, by = tt - bz * byn;
+                    if ((int32_t)by < 0) { by += byn; --bz; }
+                    const uint32_t o = (2u * bz) * wslab + (4u * by) * wrow + bx;
+                    __stcs(dst + o, q0.x); __stcs(dst + (o + wrow), q0.y); __stcs(dst + (o + 2u * wrow), q0.z); __stcs(dst + (o + 3u * wrow), q0.w);
+                    const uint32_t o1 = o + wslab;
+                    __stcs(dst + o1, q1.x); __stcs(dst + (o1 + wrow), q1.y); __stcs(dst + (o1 + 2u * wrow), q1.z); __stcs(dst + (o1 + 3u * wrow), q1.w);
+                    if ((q0.x | q0.y | q0.z | q0.w | q1.x | q1.y | q1.z | q1.w) != 0u) { __stcg(src + 2u * b, z); __stcg(src + 2u * b + 1u, z); }
+                }
+            }
+            const unsigned long long wsum = (unsigned long long)__reduce_add_sync(kFullWarp, bytes & 0xFFFFu) +
+                                            ((unsigned long long)__reduce_add_sync(kFullWarp, bytes >> 16) << 16);
+            if (lane == 0) s_sum[warp] = wsum;
         }
-        const unsigned long long wsum = (unsigned long long)__reduce_add_sync(kFullWarp, bytes & 0xFFFFu) +
-                                        ((unsigned long long)__reduce_add_sync(kFullWarp, bytes >> 16) << 16);
-        if (lane == 0) s_sum[warp] = wsum;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long sum = 0;
-        for (uint32_t w = 0; w < kWarpsPerBlock; ++w) sum += s_sum[w];
-        if (sum) atomicAdd(&ctl->bytes[i][c & (kFrameStatSlots - 1u)], sum);
-        __threadfence();                                           // the zeros (of every thread: barrier above) are in place before the slot is released
-        s_last = (atomicAdd(&ctl->copy_done[i], 1u) == copiers - 1u) ? 1u : 0u;
-    }
-    __syncthreads();
-    if (s_last && warp == 0) {
-        // the instance is complete: samples added != byte sum of the volume means some byte carried (more than 255 hits
-        // in a voxel) -> flag 2, k_repair_packed recounts the instance in u32
-        __threadfence();
-        unsigned long long a = *(volatile unsigned long long*)&ctl->added[i][lane], y = *(volatile unsigned long long*)&ctl->bytes[i][lane];
-        for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(kFullWarp, a, o); y += __shfl_down_sync(kFullWarp, y, o); }
-        if (lane == 0) *I.ovf_flag = (a != y) ? 2u : 0u;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long sum = 0;
+            for (uint32_t w = 0; w < kWarpsPerBlock; ++w) sum += s_sum[w];
+            if (sum) atomicAdd(&ctl->bytes[t][c & (kFrameStatSlots - 1u)], sum);
+            __threadfence();                                       // the zeros (of every thread: barrier above) are in place before the slot is released
+            s_last = (atomicAdd(&ctl->copy_done[t], 1u) == copiers - 1u) ? 1u : 0u;
+        }
+        __syncthreads();
+        if (s_last && warp == 0) {
+            // instance t is complete: samples added != byte sum of the volume means some byte carried (more than 255
+            // hits in a voxel) -> flag 2, k_repair_packed recounts the instance in u32
+            __threadfence();
+            unsigned long long a = *(volatile unsigned long long*)&ctl->added[t][lane], y = *(volatile unsigned long long*)&ctl->bytes[t][lane];
+            for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(kFullWarp, a, o); y += __shfl_down_sync(kFullWarp, y, o); }
+            if (lane == 0) *T.ovf_flag = (a != y) ? 2u : 0u;
+        }
+        __syncthreads();                                           // s_sum / s_last are reused by the next role
     }
 }
 

@@ -372,6 +372,7 @@ BatchPlan fill_batch(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool verti
             I.n_tiles = (uint32_t)((items + per_item - 1) / per_item);
         }
         I.vps_magic = (uint32_t)((1ull << 32) / (uint64_t)(jobs[k].segs + 1u)) + 1u;
+        I.tile_step = kTileStride % (jobs[k].segs + 1u);
         plan.max_tiles[kind] = std::max(plan.max_tiles[kind], I.n_tiles);
     }
     return plan;
@@ -456,7 +457,7 @@ int launch_repair(vkhr_b200_ctx* ctx, uint32_t* scratch, cudaStream_t s) {
 }
 
 #ifndef VKHR_FRAME_COPIERS
-#define VKHR_FRAME_COPIERS 64u
+#define VKHR_FRAME_COPIERS 256u
 #endif
 // BRICK8 as ONE launch per batch: the frame kernel (kernels.cuh, k_frame) walks and copies out through a ring of
 // L2-resident scratch volumes; then the repair kernel looks at the verdict flags.  `small`: every grid <= 2^24 voxels.
@@ -489,8 +490,9 @@ int run_frame(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool small, cudaS
         fill_batch(ctx, jobs + first, m, false, true);
         FramePlan P{};
         P.ring = std::min(ring, m);
-        // copiers: few while other instances keep the machine busy (they hold CTA slots while they wait and copy), many
-        // for the last instance, whose copy-out is the tail of the call
+        // copiers: the last CTAs of instance i + 1 copy out instance i after their own walk (whose CTAs all started
+        // before them: nothing to wait for); the batch's last instance is copied out by its own last CTAs
+        if (P.ring < 2u && m > 1u) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "the frame kernel needs a ring of two scratch volumes");
         P.copiers = VKHR_FRAME_COPIERS;
         P.copiers_last = 256u;
         P.n_bricks = (uint32_t)(nv / 32);
@@ -506,6 +508,7 @@ int run_frame(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool small, cudaS
             ctx->batch.inst[k].ovf_flag = base + (size_t)k * (bm_words + kHdr);
             ctx->batch.inst[k].ovf_bitmap = base + (size_t)k * (bm_words + kHdr) + kHdr;
             ctx->batch.inst[k].counts = static_cast<uint32_t*>(ctx->counts.p);
+            ctx->batch.inst[k].brick = P.ring_base + (size_t)(k % P.ring) * P.slot_bytes;   // instance k counts in slot k mod ring
         }
         {
             PhaseMark mk(ctx, s, PH_WALK);
