@@ -149,6 +149,16 @@ struct SinkPacked8Brick {
         const uint32_t brick = ((uint32_t)(iz >> 1) * hb + (uint32_t)(iy >> 2)) * wb + (uint32_t)(ix >> 2);
         put_brick<SLOT>((uint32_t)ix, brick * 8u + ((uint32_t)(iz & 1) * 4u + (uint32_t)(iy & 3)));
     }
+    // the same voxel as ONE number, (brick word << 2) | byte -- below 2^24 on the grids of the int32-index walk (at most
+    // 2^24 voxels) -- so that another lane can add it (walk_interior_tile_dealt)
+    __device__ __forceinline__ uint32_t pack_xyz(int ix, int iy, int iz) const {
+        const uint32_t brick = ((uint32_t)(iz >> 1) * hb + (uint32_t)(iy >> 2)) * wb + (uint32_t)(ix >> 2);
+        return ((brick * 8u + ((uint32_t)(iz & 1) * 4u + (uint32_t)(iy & 3))) << 2) | ((uint32_t)ix & 3u);
+    }
+    __device__ __forceinline__ void put_packed(uint32_t a) { put_brick<0>(a, a >> 2); }
+    // a red that carries several samples of one word (`value` = the sum of their byte increments); `n` of them are this lane's own
+    __device__ __forceinline__ void put_packed_value(uint32_t a, uint32_t value, uint32_t n) { red_add_u32(words + (a >> 2), value); added += n; }
+    __device__ __forceinline__ void count(uint32_t n) { added += n; }
     template <int SLOT>
     __device__ __forceinline__ void put_linear(uint32_t lin) { put_brick<SLOT>(lin, brick_word_pow2(lin, wh & 0xFFu, wh >> 8)); }
     template <int SLOT>
@@ -214,6 +224,14 @@ template <> struct SinkOf<4> { using type = SinkPacked8Brick<true>;
 // the vertex stream and the reds.  blockIdx.y + first = instance.
 // MODE 0 = COUNT32, 1 = PACKED8, 3 = BRICK8 on small grids (EXACT = 3), 4 = BRICK8 on power-of-two grids of any size (EXACT = 4).
 // ---------------------------------------------------------------------------
+// The interior walk of a tile: 0 = one segment per lane (the default); 1 = the tile's samples dealt out again so that one
+// red instruction carries both samples of 16 consecutive segments; 2 = neighbour absorption (walk.cuh).  Both
+// alternatives were built to cut request packets and do (120 M -> 114 M / 98 M red sectors per crowd frame), both
+// are bit-exact on the whole GPU suite, and both are SLOWER (1.00 -> 1.08 / 1.09 ms): the extra shuffles and selects
+// cost more issue slots than the packets saved (profiles/r02_ac_*, r02_ad_*).
+#ifndef VKHR_WALK_DEALT
+#define VKHR_WALK_DEALT 0
+#endif
 constexpr uint32_t kTilesPerWarp = 8;
 constexpr uint32_t kWarpsPerBlock = kWalkThreads / 32;
 constexpr uint32_t kTileStride = 31;          // segments (= new vertices) per warp-tile
@@ -367,7 +385,13 @@ __device__ __forceinline__ void walk_range(const InstanceDev& I, const GridParam
             const float steps = fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz));   // no NaN here when the vote passes
             const bool ok = vertex_is_interior(g, px, py, pz) && (!active || steps < 2048.0f);
             if (__all_sync(kFullWarp, ok)) {
+#if VKHR_WALK_DEALT == 2
+                walk_interior_tile_absorb(active && steps > 0.0f, px, py, pz, dx, dy, dz, steps, sink);
+#elif VKHR_WALK_DEALT == 1
+                walk_interior_tile_dealt(active && steps > 0.0f, px, py, pz, dx, dy, dz, steps, sink);
+#else
                 if (active && steps > 0.0f) walk_interior_lane(px, py, pz, dx, dy, dz, steps, sink);
+#endif
                 walked = true;
             }
         }
@@ -484,6 +508,9 @@ constexpr uint32_t kFrameIndexedSegs = 2048;                    // segments per 
 #endif
 #ifndef VKHR_FRAME_STAGES
 #define VKHR_FRAME_STAGES 1
+#endif
+#ifndef VKHR_FRAME_INFLIGHT
+#define VKHR_FRAME_INFLIGHT 4                                   // bricks (2 x 16 bytes) a copier thread has in flight
 #endif
 constexpr uint32_t kFrameStages = VKHR_FRAME_STAGES;            // vertex stage buffers per warp
 constexpr uint32_t kFrameRanges = VKHR_FRAME_RANGES;            // warp-ranges a warp walks per item: the item's fixed costs (fence, report) are paid once
@@ -615,7 +642,7 @@ k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
             const uint32_t b_end = min((c + 1u) * per, P.n_bricks);
             // Four bricks per thread and round: ALL eight 16-byte loads are issued before the first of them is used
             // (as a plain unrolled loop each brick's loads stay behind the previous brick's stores to `src`).
-            constexpr uint32_t kInFlight = 4;
+            constexpr uint32_t kInFlight = VKHR_FRAME_INFLIGHT;
             for (uint32_t b0 = c * per + threadIdx.x; b0 < b_end; b0 += kInFlight * kWalkThreads) {
                 uint4 q[kInFlight][2];
 #pragma unroll

@@ -402,6 +402,114 @@ __device__ __forceinline__ void walk_interior_lane(float rx, float ry, float rz,
     }
 }
 
+// The interior walk of a whole tile with the samples DEALT OUT AGAIN before they are added (all 32 lanes call it).
+//
+// What a sample costs is its 32-byte request packet on the SM -> L2 path, and one warp instruction sends one packet per
+// distinct sector its lanes touch.  With one segment per lane, instruction k adds sample k of 31
+// consecutive segments -- points spread along two and a half strands: 0.57 sectors per sample in the brick layout.
+// Here every lane first computes the packed address (sink.pack_xyz) of its segment's first TWO samples; then two
+// instructions add them, each taking BOTH samples of 16 consecutive segments (lane j: sample j & 1 of segment
+// base + j / 2, fetched by shuffle): the same points, but an instruction's lanes now lie along one strand's length --
+// 0.34 sectors per sample on the bench's strands (tools/locality_stats.py), 40 % fewer packets.  Samples beyond the
+// second (segments longer than two voxels) are added by their own lane afterwards, as walk_interior_lane does.
+// The positions are the reference's: root, root + dir, (root + dir) + dir, ... accumulated in that order; `steps - k > 0`
+// with the exact float decrements of `while (steps-- > 0.0f)` (hair_style.cc:318) is `steps > k` for k = 1, 2.
+template <class Sink>
+__device__ __forceinline__ void walk_interior_tile_dealt(bool go, float rx, float ry, float rz, float dx, float dy, float dz,
+                                                         float steps, Sink& sink) {
+    constexpr uint32_t kNone = 0xFFFFFFFFu;                                   // (a packed sample is below 2^24)
+    uint32_t a0 = kNone, a1 = kNone;
+    bool more = false;
+    if (go) {
+        const float y = rcp_steps(steps);                                     // RN(1/steps)
+        dx = div_fast(dx, steps, y);
+        dy = div_fast(dy, steps, y);
+        dz = div_fast(dz, steps, y);
+        a0 = sink.pack_xyz(__float2int_rd(rx), __float2int_rd(ry), __float2int_rd(rz));
+        if (steps > 1.0f) {
+            rx = __fadd_rn(rx, dx);
+            ry = __fadd_rn(ry, dy);
+            rz = __fadd_rn(rz, dz);
+            a1 = sink.pack_xyz(__float2int_rd(rx), __float2int_rd(ry), __float2int_rd(rz));
+            more = steps > 2.0f;
+        }
+    }
+    __syncwarp();
+    const uint32_t lane = threadIdx.x & 31u, half = lane >> 1;
+    const bool second = (lane & 1u) != 0u;
+#pragma unroll
+    for (uint32_t base = 0; base < 32u; base += 16u) {
+        const uint32_t v0 = __shfl_sync(kFullWarp, a0, base + half), v1 = __shfl_sync(kFullWarp, a1, base + half);
+        const uint32_t a = second ? v1 : v0;
+        if (a != kNone) sink.put_packed(a);
+    }
+    if (__any_sync(kFullWarp, more)) {
+        if (more) {
+            steps = __fsub_rn(__fsub_rn(steps, 1.0f), 1.0f);
+            do {
+                rx = __fadd_rn(rx, dx);
+                ry = __fadd_rn(ry, dy);
+                rz = __fadd_rn(rz, dz);
+                sink.template put_xyz<0>(__float2int_rd(rx), __float2int_rd(ry), __float2int_rd(rz));
+                steps = __fsub_rn(steps, 1.0f);
+            } while (steps > 0.0f);
+        }
+        __syncwarp();
+    }
+}
+
+// The interior walk of a whole tile with NEIGHBOUR ABSORPTION (all 32 lanes call it).
+//
+// Lanes that add to the same 32-bit word in one warp instruction are serialised into separate packets, lanes that add
+// to different words of one sector share a packet (measured: profiles/README, round 2).  The second sample of segment
+// t and the first sample of segment t + 1 lie a quarter of a voxel apart -- the same word six times out of ten on the
+// bench's strands -- but sit in different instructions (sample 1 of lane t, sample 0 of lane t + 1) and cost a packet
+// each.  Here lane t + 1 adds its neighbour's second sample to its own first one (one red of 1 << 8 b0 + 1 << 8 b1)
+// whenever the words agree, and lane t drops it: 0.57 -> 0.46 packets per sample.  The byte-sum verdict is unaffected:
+// a red still raises the volume's byte sum by the number of samples it carries unless a byte carries out.
+template <class Sink>
+__device__ __forceinline__ void walk_interior_tile_absorb(bool go, float rx, float ry, float rz, float dx, float dy, float dz,
+                                                          float steps, Sink& sink) {
+    constexpr uint32_t kNone = 0xFFFFFFFFu;                                   // (a packed sample is below 2^24)
+    uint32_t a0 = kNone, a1 = kNone;
+    bool more = false;
+    if (go) {
+        const float y = rcp_steps(steps);                                     // RN(1/steps)
+        dx = div_fast(dx, steps, y);
+        dy = div_fast(dy, steps, y);
+        dz = div_fast(dz, steps, y);
+        a0 = sink.pack_xyz(__float2int_rd(rx), __float2int_rd(ry), __float2int_rd(rz));
+        if (steps > 1.0f) {
+            rx = __fadd_rn(rx, dx);
+            ry = __fadd_rn(ry, dy);
+            rz = __fadd_rn(rz, dz);
+            a1 = sink.pack_xyz(__float2int_rd(rx), __float2int_rd(ry), __float2int_rd(rz));
+            more = steps > 2.0f;
+        }
+    }
+    __syncwarp();
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t nxt0 = __shfl_down_sync(kFullWarp, a0, 1), prv1 = __shfl_up_sync(kFullWarp, a1, 1);
+    // the pair (second sample of lane t, first sample of lane t + 1): both lanes evaluate the same test
+    const bool give = lane != 31u && (a1 ^ nxt0) < 4u && (a1 | nxt0) < 0x80000000u;    // same word, both present
+    const bool take = lane != 0u && (prv1 ^ a0) < 4u && (prv1 | a0) < 0x80000000u;
+    if (a0 != kNone) sink.put_packed_value(a0, (1u << ((a0 & 3u) * 8u)) + (take ? 1u << ((prv1 & 3u) * 8u) : 0u), 1u);
+    if (a1 != kNone) { if (give) sink.count(1u); else sink.put_packed(a1); }
+    if (__any_sync(kFullWarp, more)) {
+        if (more) {
+            steps = __fsub_rn(__fsub_rn(steps, 1.0f), 1.0f);
+            do {
+                rx = __fadd_rn(rx, dx);
+                ry = __fadd_rn(ry, dy);
+                rz = __fadd_rn(rz, dz);
+                sink.template put_xyz<0>(__float2int_rd(rx), __float2int_rd(ry), __float2int_rd(rz));
+                steps = __fsub_rn(steps, 1.0f);
+            } while (steps > 0.0f);
+        }
+        __syncwarp();
+    }
+}
+
 // Vertex pair of segment `s`.  indices == nullptr => uniform strands of
 // `segs` segments: the pairs HairStyle::generate_indices (hair_style.cc:196-213)
 // would emit, without reading an index buffer.
