@@ -1,6 +1,7 @@
 """The CPU restatement (oracle/voxel_oracle.c) against the pins: golden vectors generated from the
 unmodified reference (tests/golden/make_golden.py) and, where the reference driver is available,
 the reference itself on fresh inputs.  No GPU involved."""
+import os
 import numpy as np
 import pytest
 
@@ -303,3 +304,47 @@ def test_port_at_the_baseline_sizes(port, golden, name):
     assert (_fnv(port, d), int(d.astype(np.int64).sum()), int(np.count_nonzero(d)), int((d == 255).sum())) == \
            (st["fnv"], st["sum"], st["nonzero"], st["saturated"])
     assert _fnv(port, port.normalize(d)) == e["normalize_segments"]["fnv"]
+
+
+# ---- the prefilter / ADSM restatement frozen against committed fixtures ------------------------------------------------
+def _prefilter_fixtures():
+    sys_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_prefilter_fixtures", os.path.join(sys_path, "make_prefilter_fixtures.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod, np.load(os.path.join(sys_path, "prefilter_fixtures.npz"))
+
+
+def test_prefilter_oracle_is_frozen_by_committed_fixtures(port):
+    """oracle/prefilter_oracle.c recomputes tests/golden/prefilter_fixtures.npz BIT FOR BIT (float32): the checker of the
+    CUDA prefilter / ADSM kernels cannot drift with them.  (Oracle-generated, not reference-held: rows f1 / f3 stay
+    "parity unpinned by the reference")"""
+    mod, fx = _prefilter_fixtures()
+    now = mod.compute(port)
+    assert sorted(now) == sorted(fx.files)
+    for k in fx.files:
+        assert now[k].dtype == fx[k].dtype and np.array_equal(now[k], fx[k]), k
+
+
+def test_prefilter_fixtures_hold_hand_computed_values():
+    """A single texel of density 255 in an empty 9^3 volume, by hand from the shader text:
+    AO, radius 0 (local_ambient_occlusion.glsl:9-30): all eight taps sit on the voxel's own centre, each min(1.0, 0.16), so
+        ao = (1 - 8 * 0.16 / 8)^10 = 0.84^10 at the texel, 1 everywhere else;
+    Gaussian of width 1: the identity, tau = 1 at the texel; opacity = (1 - 0.3)^(1 * 11) = 0.7^11 at the texel."""
+    _, fx = _prefilter_fixtures()
+    c = (4 * 9 + 4) * 9 + 4
+    ao = fx["single_voxel/ao3"]
+    assert abs(float(ao[c]) - 0.84 ** 10) <= 2e-6 * 0.84 ** 10 and np.all(np.delete(ao, c) == 1.0)
+    g = fx["single_voxel/gauss0"]
+    assert g[c] == 1.0 and np.all(np.delete(g, c) == 0.0)
+    op = fx["single_voxel/opacity0"]
+    assert abs(float(op[c]) - 0.7 ** 11) <= 2e-6 * 0.7 ** 11 and np.all(np.delete(op, c) == 1.0)
+    # AO, radius 2.5 (kernel_radius = 0.5, so the eight taps sit at +-2.5 texels on every axis): the centre voxel's taps
+    # fall between texels 1|2 and 6|7 -- weight 0 of texel 4 -- so it is unoccluded; voxel (6, 6, 6) has ONE tap at texel
+    # coordinate 3.5 on every axis: trilinear weight 0.5^3 = 0.125 of the texel, below the clamp of 0.16, so
+    # ao = (1 - 0.125 / 8)^10 = 0.984375^10
+    ao25 = fx["single_voxel/ao0"]
+    assert ao25[c] == 1.0
+    n = (6 * 9 + 6) * 9 + 6
+    assert abs(float(ao25[n]) - 0.984375 ** 10) <= 2e-6

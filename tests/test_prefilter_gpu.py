@@ -213,3 +213,24 @@ def test_adsm_device_resident_matches_host_api(vox):
     dev = vox.adsm_dev(torch.from_numpy(d).cuda(), W, H, D, [0, 0, 0], [4, 2, 1], [5, 6, 7])
     torch.cuda.synchronize()
     assert np.array_equal(dev.cpu().numpy(), host)
+
+
+def test_cuda_against_the_committed_fixtures(vox):
+    """The CUDA prefilter / ADSM against tests/golden/prefilter_fixtures.npz (frozen outputs of the restatement, see
+    tests/golden/make_prefilter_fixtures.py) -- no live oracle call on this path: 1e-6 relative."""
+    import importlib.util, os
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_prefilter_fixtures", os.path.join(g, "make_prefilter_fixtures.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    fx = np.load(os.path.join(g, "prefilter_fixtures.npz"))
+    for name, W, H, D, _, _ in mod.VOLUMES:
+        d = fx[f"{name}/densities"]
+        for k, (r, e, m) in enumerate(mod.AO_PARAMS):
+            _close(vox.prefilter(d, W, H, D, ao=True, ao_radius=r, ao_exponent=e, ao_max=m)["ao"], fx[f"{name}/ao{k}"], f"{name} ao{k}")
+        for k, w in enumerate(mod.GAUSS_WIDTHS):
+            _close(vox.prefilter(d, W, H, D, ao=False, gauss=True, gauss_width=w)["gauss"], fx[f"{name}/gauss{k}"], f"{name} gauss{k}")
+        for k, (a, t) in enumerate(mod.OPACITY_PARAMS):
+            _close(vox.prefilter(d, W, H, D, ao=False, opacity=True, strand_alpha=a, thickness=t)["opacity"], fx[f"{name}/opacity{k}"], f"{name} opacity{k}")
+        for k, (o, s, l, steps, a, t) in enumerate(mod.ADSM_CASES):
+            _close(vox.adsm(d, W, H, D, o, s, l, steps=steps, strand_alpha=a, thickness=t), fx[f"{name}/adsm{k}"], f"{name} adsm{k}")
