@@ -605,6 +605,28 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                "d2h_bytes_per_step": total * nvox, "steps": ke, "ms_per_step": dt / ke * 1e3,
                "api": "vkhr_b200_voxelize_segments_batch (host pointers, pinned; H2D / kernels / D2H of consecutive "
                       "instances pipelined on three streams), one call per rank per step", "host_affinity": numa}
+        if rank == 0 and world == 1:
+            # like for like with the reference call, which always builds the tangent volume too (hair_style.cc:331-339):
+            # densities AND tangents of a few instances, one vkhr_b200_voxelize_segments call each, pinned host buffers
+            try:
+                nt = min(I, 8)
+                td = torch.empty(nvox, dtype=torch.uint8).pin_memory()
+                tt = torch.empty((nvox, 4), dtype=torch.int8).pin_memory()
+                call = lambda k: vox.voxelize_segments(hv[k], None, aabbs[k][0], aabbs[k][1], W, W, W, segs_per_strand=segs,  # noqa: E731
+                                                       flags=flags, want_tangents=True, out=td.numpy(), tangents_out=tt.numpy())
+                call(0)
+                t0 = time.perf_counter()
+                for k in range(nt):
+                    call(k)
+                dtt = time.perf_counter() - t0
+                e2e["densities_and_tangents"] = {
+                    "value": n_seg * nt / dtt / 1e6, "unit": UNIT, "instances": nt, "ms_per_instance": dtt / nt * 1e3,
+                    "h2d_bytes_per_instance": V * 12, "d2h_bytes_per_instance": nvox * 5,
+                    "api": "vkhr_b200_voxelize_segments (host pointers, pinned), one call per instance, densities + int8x4 tangent "
+                           "volume -- what the reference's HairStyle::voxelize_segments returns; not pipelined across instances"}
+                del td, tt
+            except Exception as e:  # noqa: BLE001
+                e2e["densities_and_tangents"] = {"error": str(e)[:200]}
         # the frame that came back over PCIe must equal the device-resident one
         frame()
         torch.cuda.synchronize()

@@ -623,7 +623,7 @@ k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
         const uint32_t t = role == 0u ? i - 1u : i;                // the instance copied out
         const uint32_t copiers = min(items, role == 0u ? P.copiers : P.copiers_last);
         if (blockIdx.x + copiers < items) continue;                // not one of instance i's last `copiers` CTAs
-        const uint32_t c = blockIdx.x - (items - copiers);
+        const uint32_t c = blockIdx.x - (items - copiers);         // (the FIRST CTAs instead were measured: no gain, profiles/r02_ae_*)
         const InstanceDev& T = B.inst[t];
         frame_wait_ge(&ctl->walk_done[t], max(T.n_tiles, 1u));     // every walk CTA of instance t has reported (acquire)
         {

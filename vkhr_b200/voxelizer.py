@@ -91,20 +91,28 @@ class Voxelizer:
 
     # ---- host-pointer API (numpy) ------------------------------------------
     def voxelize_segments(self, vertices, indices, aabb_origin, aabb_size, W, H, D,
-                          segs_per_strand: int = 0, flags: int = 0, tangents=None, want_tangents: bool = False):
+                          segs_per_strand: int = 0, flags: int = 0, tangents=None, want_tangents: bool = False,
+                          out=None, tangents_out=None):
         """Replaces ``HairStyle::voxelize_segments`` (reference hair_style.cc:296-342); returns W*H*D uint8.
 
         ``want_tangents`` (or ``tangents`` given): also returns the int8 (W*H*D, 4) tangent volume
         (``Volume::tangents``); without ``tangents`` the tangent of a segment is normalize(tip - root).
+        ``out`` / ``tangents_out``: caller-owned result arrays (e.g. views of pinned memory) instead of fresh ones.
         """
         v = _np(vertices, np.float32).reshape(-1, 3)
         idx = None if indices is None else _np(indices, np.uint32).reshape(-1)
         tin = None if tangents is None else _np(tangents, np.float32).reshape(-1, 3)
         if tin is not None and tin.shape != v.shape:
             raise ValueError("tangents must have one row per vertex")
-        want = want_tangents or tin is not None
-        out = np.empty(int(W) * int(H) * int(D), dtype=np.uint8)
-        tout = np.empty((out.size, 4), dtype=np.int8) if want else None
+        want = want_tangents or tin is not None or tangents_out is not None
+        nvox = int(W) * int(H) * int(D)
+        if out is None:
+            out = np.empty(nvox, dtype=np.uint8)
+        elif out.dtype != np.uint8 or out.size != nvox or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous uint8 array of W*H*D")
+        tout = tangents_out if tangents_out is not None else (np.empty((nvox, 4), dtype=np.int8) if want else None)
+        if tout is not None and (tout.dtype != np.int8 or tout.size != 4 * nvox or not tout.flags.c_contiguous):
+            raise ValueError("tangents_out must be a contiguous int8 array of W*H*D x 4")
         rc = lib.vkhr_b200_voxelize_segments(self._h, _p(v), v.shape[0], _p(idx),
                                              0 if idx is None else idx.size, int(segs_per_strand), _p(tin),
                                              capi.vec3(aabb_origin), capi.vec3(aabb_size),
