@@ -11,6 +11,14 @@
 
 namespace vkhr_b200 {
 
+// Measurement builds only (tools/gpu_r2_ag.sh; never the product): the frame kernel without its reds / without its copy-out.
+#ifndef VKHR_PROBE_NO_RED
+#define VKHR_PROBE_NO_RED 0
+#endif
+#ifndef VKHR_PROBE_NO_COPY
+#define VKHR_PROBE_NO_COPY 0
+#endif
+
 constexpr int kWalkThreads = 256;
 #ifndef VKHR_WALK_MIN_CTAS
 #define VKHR_WALK_MIN_CTAS 5
@@ -140,6 +148,9 @@ struct SinkPacked8Brick {
     uint32_t added = 0;             // samples this lane added
     template <int SLOT>
     __device__ __forceinline__ void put_brick(uint32_t lin, uint32_t bword) {
+#if VKHR_PROBE_NO_RED          // measurement build (tools/): the walk with its address arithmetic but without the red itself
+        if (bword == 0xFFFFFFFFu)
+#endif
         red_add_u32(words + bword, 1u << ((lin & 3u) * 8u));
         ++added;
     }
@@ -232,13 +243,16 @@ template <> struct SinkOf<4> { using type = SinkPacked8Brick<true>;
 #ifndef VKHR_WALK_DEALT
 #define VKHR_WALK_DEALT 0
 #endif
-constexpr uint32_t kTilesPerWarp = 8;
+#ifndef VKHR_TILES_PER_WARP
+#define VKHR_TILES_PER_WARP 8                                    // a multiple of 4 (whole 16-byte units per range); 16 fits 48 KB of static shared memory with one stage
+#endif
+constexpr uint32_t kTilesPerWarp = VKHR_TILES_PER_WARP;
 constexpr uint32_t kWarpsPerBlock = kWalkThreads / 32;
 constexpr uint32_t kTileStride = 31;          // segments (= new vertices) per warp-tile
-constexpr uint32_t kRangeFloats = 3u * kTileStride * kTilesPerWarp;   // 744 floats = 2976 bytes (a multiple of 16)
+constexpr uint32_t kRangeFloats = 3u * kTileStride * kTilesPerWarp;   // 8 tiles: 744 floats = 2976 bytes (a multiple of 16)
 constexpr uint32_t kNeedFloats = kRangeFloats + 3u;                   // + the tip vertex of the range's last segment
 constexpr uint32_t kBulkBytes = ((kNeedFloats * 4u + 15u) / 16u) * 16u;   // 3008: what one bulk copy moves
-constexpr uint32_t kStageFloats = 752u;       // shared-memory slot of one warp (= kBulkBytes / 4; two per warp must fit 48 KB of static shared memory)
+constexpr uint32_t kStageFloats = kBulkBytes / 4u;   // shared-memory slot of one warp (752 floats for 8 tiles; two per warp must fit 48 KB of static shared memory)
 static_assert(kRangeFloats * 4u % 16u == 0 && kBulkBytes <= kStageFloats * 4u, "bulk copy geometry");
 
 // mbarrier + 1-D bulk copy (TMA unit, `cp.async.bulk`, SASS UBLKCP): global -> shared without passing
@@ -501,7 +515,7 @@ k_walk_indexed(const __grid_constant__ Batch B, uint32_t first) {
 constexpr uint32_t kFrameStatSlots = 32;
 constexpr uint32_t kFrameIndexedSegs = 2048;                    // segments per walk item of an indexed instance
 #ifndef VKHR_FRAME_RANGES
-#define VKHR_FRAME_RANGES 2
+#define VKHR_FRAME_RANGES 3
 #endif
 #ifndef VKHR_FRAME_MIN_CTAS
 #define VKHR_FRAME_MIN_CTAS 4
@@ -552,8 +566,8 @@ k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
     // gain -- 1.12 ms against 1.08 ms per crowd frame with one buffer, which leaves twice the L1; profiles/r02_m_*)
     __shared__ __align__(128) float s_stage[kFrameStages][kWarpsPerBlock][kStageFloats];
     __shared__ __align__(8) unsigned long long s_bar[kFrameStages][kWarpsPerBlock];
-    __shared__ unsigned long long s_sum[kWarpsPerBlock];
-    __shared__ uint32_t s_last;
+    __shared__ unsigned long long s_sum[kWarpsPerBlock];           // the walk's sample counts
+    __shared__ unsigned long long s_csum[kWarpsPerBlock];          // the copy-out's byte sums (thread 0 may still be reading s_sum)
     const uint32_t i = blockIdx.y;
     const InstanceDev& I = B.inst[i];
     const uint32_t items = max(I.n_tiles, 1u);                     // CTAs of this instance (one for an instance without segments: its copy-out)
@@ -601,7 +615,18 @@ k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
         const uint32_t added = __reduce_add_sync(kFullWarp, sink.added);
         if (lane == 0) s_sum[warp] = added;
     }
-    __syncthreads();
+    // A CTA that is going to copy out instance i - 1 (role 0 below) looks at that instance's counter NOW, every warp for
+    // itself as it comes off its walk: the round trip of the acquire load hides behind the wait for the CTA's slowest
+    // warp, and the barrier below doubles as the vote.  (Before: thread 0 polled after the barrier and seven warps
+    // waited for its round trip at a second barrier -- 7 % of all warp-time, profiles/r02_aa_*.)
+    bool ready = false;
+    if (i > 0u && blockIdx.x + min(items, P.copiers) >= items) {
+        uint32_t seen = 0;
+        if (lane == 0) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(&ctl->walk_done[i - 1u]) : "memory");
+        seen = __shfl_sync(kFullWarp, seen, 0);
+        ready = seen >= max(B.inst[i - 1u].n_tiles, 1u);
+    }
+    const bool all_ready = __syncthreads_and(ready) != 0;
     if (threadIdx.x == 0) {
         unsigned long long sum = 0;
         for (uint32_t w = 0; w < kWarpsPerBlock; ++w) sum += s_sum[w];
@@ -625,7 +650,11 @@ k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
         if (blockIdx.x + copiers < items) continue;                // not one of instance i's last `copiers` CTAs
         const uint32_t c = blockIdx.x - (items - copiers);         // (the FIRST CTAs instead were measured: no gain, profiles/r02_ae_*)
         const InstanceDev& T = B.inst[t];
-        frame_wait_ge(&ctl->walk_done[t], max(T.n_tiles, 1u));     // every walk CTA of instance t has reported (acquire)
+        if (!(role == 0u && all_ready))                            // (role 0: usually seen already, above)
+            frame_wait_ge(&ctl->walk_done[t], max(T.n_tiles, 1u)); // every walk CTA of instance t has reported (acquire)
+#if VKHR_PROBE_NO_COPY         // measurement build (tools/): the frame kernel without the copy-out's loads and stores
+        if (P.n_bricks == 0xFFFFFFFFu)
+#endif
         {
             const uint32_t wrow = T.grid.W >> 2, byn = T.grid.H >> 2;  // words (= bricks) per row, brick rows per slab
             const uint32_t wslab = wrow * T.grid.H;
@@ -673,26 +702,31 @@ k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
             }
             const unsigned long long wsum = (unsigned long long)__reduce_add_sync(kFullWarp, bytes & 0xFFFFu) +
                                             ((unsigned long long)__reduce_add_sync(kFullWarp, bytes >> 16) << 16);
-            if (lane == 0) s_sum[warp] = wsum;
+            if (lane == 0) s_csum[warp] = wsum;
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned long long sum = 0;
-            for (uint32_t w = 0; w < kWarpsPerBlock; ++w) sum += s_sum[w];
-            if (sum) atomicAdd(&ctl->bytes[t][c & (kFrameStatSlots - 1u)], sum);
-            __threadfence();                                       // the zeros (of every thread: barrier above) are in place before the slot is released
-            s_last = (atomicAdd(&ctl->copy_done[t], 1u) == copiers - 1u) ? 1u : 0u;
+        __syncthreads();                                           // every thread's stores are issued, s_csum is complete
+        if (warp == 0) {                                           // (the other warps are done: nothing below concerns them)
+            uint32_t last = 0;
+            if (lane == 0) {
+                unsigned long long sum = 0;
+                for (uint32_t w = 0; w < kWarpsPerBlock; ++w) sum += s_csum[w];
+                if (sum) atomicAdd(&ctl->bytes[t][c & (kFrameStatSlots - 1u)], sum);
+                __threadfence();                                   // the zeros (of every thread: barrier above) are in place before the slot is released
+                last = (atomicAdd(&ctl->copy_done[t], 1u) == copiers - 1u) ? 1u : 0u;
+            }
+            if (__shfl_sync(kFullWarp, last, 0)) {
+                // instance t is complete: samples added != byte sum of the volume means some byte carried (more than 255
+                // hits in a voxel) -> flag 2, k_repair_packed recounts the instance in u32
+                __threadfence();
+                unsigned long long a = *(volatile unsigned long long*)&ctl->added[t][lane], y = *(volatile unsigned long long*)&ctl->bytes[t][lane];
+                for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(kFullWarp, a, o); y += __shfl_down_sync(kFullWarp, y, o); }
+#if VKHR_PROBE_NO_RED || VKHR_PROBE_NO_COPY
+                a = y;                                             // (probe builds produce no volume: never send them to the repair kernel)
+#endif
+                if (lane == 0) *T.ovf_flag = (a != y) ? 2u : 0u;
+            }
         }
-        __syncthreads();
-        if (s_last && warp == 0) {
-            // instance t is complete: samples added != byte sum of the volume means some byte carried (more than 255
-            // hits in a voxel) -> flag 2, k_repair_packed recounts the instance in u32
-            __threadfence();
-            unsigned long long a = *(volatile unsigned long long*)&ctl->added[t][lane], y = *(volatile unsigned long long*)&ctl->bytes[t][lane];
-            for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(kFullWarp, a, o); y += __shfl_down_sync(kFullWarp, y, o); }
-            if (lane == 0) *T.ovf_flag = (a != y) ? 2u : 0u;
-        }
-        __syncthreads();                                           // s_sum / s_last are reused by the next role
+        if (role == 0u && i + 1u == n_inst) __syncthreads();       // s_csum is reused by role 1
     }
 }
 
