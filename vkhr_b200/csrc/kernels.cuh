@@ -253,7 +253,9 @@ constexpr uint32_t kRangeFloats = 3u * kTileStride * kTilesPerWarp;   // 8 tiles
 constexpr uint32_t kNeedFloats = kRangeFloats + 3u;                   // + the tip vertex of the range's last segment
 constexpr uint32_t kBulkBytes = ((kNeedFloats * 4u + 15u) / 16u) * 16u;   // 3008: what one bulk copy moves
 constexpr uint32_t kStageFloats = kBulkBytes / 4u;   // shared-memory slot of one warp (752 floats for 8 tiles; two per warp must fit 48 KB of static shared memory)
+constexpr uint32_t kStagePad = 96u;           // floats behind the last warp's slot: the tile loop fetches one tile ahead, also behind the last tile
 static_assert(kRangeFloats * 4u % 16u == 0 && kBulkBytes <= kStageFloats * 4u, "bulk copy geometry");
+static_assert(kRangeFloats + 3u * 32u <= kStageFloats + kStagePad, "the look-ahead fetch stays inside the padded stage");
 
 // mbarrier + 1-D bulk copy (TMA unit, `cp.async.bulk`, SASS UBLKCP): global -> shared without passing
 // through the LSU queue the reds occupy.
@@ -329,8 +331,10 @@ __device__ __forceinline__ bool stage_range(const InstanceDev& I, uint32_t range
 
 // walk_range: the walk of a staged range.  `parity`: the phase of `bar` the bulk copy completes (flipped here); the
 // sink is the caller's (it calls finish()).  All 32 lanes call this together.
-template <int EXACT, class Sink>
+template <int EXACT, bool FAST, class Sink>
 __device__ __forceinline__ void walk_range(const InstanceDev& I, const GridParams& g, uint32_t range, float* stage, uint32_t bar, bool bulk, uint32_t& parity, Sink& sink) {
+    // FAST (the caller's g.fast_div, warp-uniform, decided once per CTA instead of twice per tile): the FMA division
+    // applies to this instance's voxel sizes, which is what the unguarded interior walk needs
     // g: the caller's pin(I.grid) -- registers, not indexed constant loads, and loaded once per CTA, not once per range
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n_vertices = I.n_vertices;
@@ -374,7 +378,7 @@ __device__ __forceinline__ void walk_range(const InstanceDev& I, const GridParam
         tz = __shfl_down_sync(kFullWarp, pz, 1);
     };
     constexpr bool kInterior = EXACT == 3;                          // the unguarded interior walk exists for the int32-index brick sink
-    const bool fast_div = kInterior && g.fast_div != 0u;            // (uniform) the FMA division applies to this instance's voxel sizes
+    constexpr bool fast_div = kInterior && FAST;
     auto transform = [&]() {
         if (fast_div) {
             // unguarded: validated by vertex_is_interior on the RESULT (walk.cuh); a tile that fails the vote is redone below
@@ -388,13 +392,13 @@ __device__ __forceinline__ void walk_range(const InstanceDev& I, const GridParam
     };
     fetch();
     transform();
-    for (uint32_t k = n_tiles; k > 0u; --k) {
-        if (k > 1u) fetch();                                       // warp-uniform
+    for (uint32_t k = n_tiles;;) {
+        fetch();                                                   // (behind the last tile: up to 96 floats past the range -- the stage is padded)
         const bool active = sp1 != vps;
         sp1 += r_step;
         if (sp1 > vps) sp1 -= vps;
         bool walked = false;
-        if constexpr (kInterior) if (fast_div) {
+        if constexpr (fast_div) {
             const float dx = __fsub_rn(tx, px), dy = __fsub_rn(ty, py), dz = __fsub_rn(tz, pz);
             const float steps = fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz));   // no NaN here when the vote passes
             const bool ok = vertex_is_interior(g, px, py, pz) && (!active || steps < 2048.0f);
@@ -423,14 +427,16 @@ __device__ __forceinline__ void walk_range(const InstanceDev& I, const GridParam
         // behind the transform and runs its 19 instructions once for each half of the warp: 7 % of the frame kernel's
         // instructions, ncu source page of round 2.)
         __syncwarp();
-        if (k > 1u) transform();
+        if (--k == 0u) break;
+        transform();
     }
 }
 
 template <int MODE, int EXACT>
 __global__ void __launch_bounds__(kWalkThreads, VKHR_WALK_MIN_CTAS)
 k_walk_uniform(const __grid_constant__ Batch B, uint32_t first) {
-    __shared__ __align__(128) float s_stage[kWarpsPerBlock][kStageFloats];
+    __shared__ __align__(128) float s_stage_flat[kWarpsPerBlock * kStageFloats + kStagePad];
+    float (*s_stage)[kStageFloats] = reinterpret_cast<float (*)[kStageFloats]>(s_stage_flat);
     __shared__ __align__(8) unsigned long long s_bar[kWarpsPerBlock];
     const InstanceDev& I = B.inst[first + blockIdx.y];
     if (blockIdx.x >= I.n_tiles || I.kind != WK_UNIFORM) return;          // n_tiles counts CTAs
@@ -444,7 +450,8 @@ k_walk_uniform(const __grid_constant__ Batch B, uint32_t first) {
     const uint32_t range = blockIdx.x * kWarpsPerBlock + warp;     // this warp's range of kTilesPerWarp tiles
     const bool bulk = stage_range(I, range, s_stage[warp], bar);
     const GridParams g = pin(I.grid);
-    walk_range<EXACT>(I, g, range, s_stage[warp], bar, bulk, parity, sink);
+    if (g.fast_div) walk_range<EXACT, true>(I, g, range, s_stage[warp], bar, bulk, parity, sink);
+    else walk_range<EXACT, false>(I, g, range, s_stage[warp], bar, bulk, parity, sink);
     sink.finish();
 }
 
@@ -564,7 +571,8 @@ __global__ void __launch_bounds__(kWalkThreads, VKHR_FRAME_MIN_CTAS)
 k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
     // kFrameStages = 2: the vertices of a warp's next range are in flight while it walks the current one (measured: no
     // gain -- 1.12 ms against 1.08 ms per crowd frame with one buffer, which leaves twice the L1; profiles/r02_m_*)
-    __shared__ __align__(128) float s_stage[kFrameStages][kWarpsPerBlock][kStageFloats];
+    __shared__ __align__(128) float s_stage_flat[kFrameStages * kWarpsPerBlock * kStageFloats + kStagePad];
+    float (*s_stage)[kWarpsPerBlock][kStageFloats] = reinterpret_cast<float (*)[kWarpsPerBlock][kStageFloats]>(s_stage_flat);
     __shared__ __align__(8) unsigned long long s_bar[kFrameStages][kWarpsPerBlock];
     __shared__ unsigned long long s_sum[kWarpsPerBlock];           // the walk's sample counts
     __shared__ unsigned long long s_csum[kWarpsPerBlock];          // the copy-out's byte sums (thread 0 may still be reading s_sum)
@@ -596,13 +604,15 @@ k_frame(const __grid_constant__ Batch B, const __grid_constant__ FramePlan P) {
         if (i >= P.ring)                                           // the slot's previous tenant, instance i - ring, has been copied out
             frame_wait_ge(&ctl->copy_done[i - P.ring], min(max(B.inst[i - P.ring + 1u].n_tiles, 1u), P.copiers));   // by CTAs of the instance behind it
         if (uniform_item) {
-#pragma unroll
+            // (not unrolled: one copy of the walk per FAST instead of kFrameRanges -- the kernel is instruction-cache sized)
+#pragma unroll 1
             for (uint32_t rr = 0; rr < kFrameRanges; ++rr) {
                 const uint32_t b = kFrameStages > 1u ? (rr & 1u) : 0u, nb = kFrameStages > 1u ? (b ^ 1u) : 0u;
                 bool bulk_nxt = false;
                 if (kFrameStages > 1u && rr + 1u < kFrameRanges)   // (buffer nb was last read two ranges ago, by this warp)
                     bulk_nxt = stage_range(I, range + kWarpsPerBlock, s_stage[nb][warp], bar[nb]);
-                walk_range<EXACT>(I, g, range, s_stage[b][warp], bar[b], bulk, parity[b], sink);
+                if (g.fast_div) walk_range<EXACT, true>(I, g, range, s_stage[b][warp], bar[b], bulk, parity[b], sink);
+                else walk_range<EXACT, false>(I, g, range, s_stage[b][warp], bar[b], bulk, parity[b], sink);
                 __syncwarp();
                 range += kWarpsPerBlock;
                 if (kFrameStages == 1u && rr + 1u < kFrameRanges) bulk_nxt = stage_range(I, range, s_stage[0][warp], bar[0]);

@@ -515,6 +515,8 @@ int run_frame(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool small, cudaS
             const dim3 grid(max_items, m);
             if (small) k_frame<3, 3><<<grid, kWalkThreads, 0, s>>>(ctx->batch, P);
             else       k_frame<4, 4><<<grid, kWalkThreads, 0, s>>>(ctx->batch, P);
+            // (the ring as a persisting access-policy window of this launch was measured: same time, same L2 misses,
+            // profiles/r02_aj_*)
             ctx->launches++;
             CU_CHECK(ctx, cudaGetLastError());
         }
