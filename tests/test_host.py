@@ -257,3 +257,23 @@ def test_volume_save_writes_what_the_reference_writes(tmp_path, ref):
     assert vol.save(str(tmp_path / "no_such_dir" / "x.raw")) is False
     assert ref.volume_save(d, str(tmp_path / "no_such_dir" / "x.raw")) is False
     assert capi.lib.vkhr_b200_volume_save(None, None, 0) == capi.ERR_INVALID_ARGUMENT
+
+
+def test_copy_out_brick_coordinates_by_multiply_high():
+    """numpy restatement of the frame kernel's copy-out addressing (kernels.cuh, k_frame): brick number b ->
+    (bx, by, bz) with m = floor((2^32 - 1) / d) + 1 and one correction step, for every divisor a volume of the frame
+    kernel can have (W / 4, H / 4 < 65536) and brick numbers up to 2^23 -- against integer division."""
+    rng = np.random.default_rng(7)
+    ds = np.unique(np.concatenate([np.arange(1, 300), 2 ** np.arange(0, 16), 2 ** np.arange(1, 16) - 1, 2 ** np.arange(1, 16) + 1,
+                                   rng.integers(1, 65536, 500), [65535]])).astype(np.uint64)
+    ds = ds[ds < 65536]
+    b = np.concatenate([np.arange(0, 4096), rng.integers(0, 1 << 23, 20000), [(1 << 23) - 1, (1 << 20) - 1, 1 << 20]]).astype(np.uint64)
+    for d in ds:
+        m = np.uint64(0) if d == 1 else np.uint64(0xFFFFFFFF) // d + np.uint64(1)
+        assert m < (1 << 32)
+        q = b.copy() if d == 1 else (b * m) >> np.uint64(32)                   # __umulhi
+        r = (b.astype(np.int64) - (q * d).astype(np.int64))                    # 32-bit wrap == signed difference here
+        neg = r < 0
+        q = np.where(neg, q - np.uint64(1), q)
+        r = np.where(neg, r + np.int64(d), r)
+        assert np.array_equal(q, b // d) and np.array_equal(r.astype(np.uint64), b % d), int(d)
