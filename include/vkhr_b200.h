@@ -113,9 +113,10 @@ VKHR_B200_API uint64_t vkhr_b200_launch_count(const vkhr_b200_ctx* ctx);
  * (0 before the first call).  Introspection for tests and benchmarks; no reference counterpart. */
 VKHR_B200_API uint32_t vkhr_b200_last_strategy(const vkhr_b200_ctx* ctx);
 
-/* Bytes of BRICK8 scratch the frame kernel keeps in flight: a ring of floor(bytes / (W*H*D)) volumes (at least one, at
- * most eight), sized to stay resident in L2 beside the streams of strands and output volumes (default 48 MiB of the
- * B200's 126 MB).  Tuning knob; results do not depend on it. */
+/* Bytes of BRICK8 scratch the frame kernel keeps in flight: a ring of floor(bytes / (W*H*D)) volumes (at most eight;
+ * below two volumes the separate kernels run instead), sized to sit in L2 beside the streams of strands and output
+ * volumes (default 64 MiB of the B200's 126 MB: four 256^3 volumes; three and five were measured slower).  Tuning
+ * knob; results do not depend on it. */
 VKHR_B200_API int vkhr_b200_set_scratch_ring_bytes(vkhr_b200_ctx* ctx, size_t bytes);
 
 /* Per-phase device timing.  While enabled, every voxelize call records CUDA
