@@ -11,7 +11,7 @@
 
 namespace vkhr_b200 {
 
-// Measurement builds only (tools/gpu_r2_ag.sh; never the product): the frame kernel without its reds / without its copy-out.
+// Measurement builds only (tools/runs/gpu_r2_ag.sh; never the product): the frame kernel without its reds / without its copy-out.
 #ifndef VKHR_PROBE_NO_RED
 #define VKHR_PROBE_NO_RED 0
 #endif
