@@ -496,28 +496,31 @@ k_walk_indexed(const __grid_constant__ Batch B, uint32_t first) {
 // The grid is k_walk_uniform's: blockIdx.y = instance, blockIdx.x = walk item (8 warp-ranges of 8 tiles, kFrameRanges of
 // them in a row; 2048 segments of an indexed instance), so instances START in order.  A CTA walks its item, adds its
 // sample count to the instance's statistics and reports to the instance's counter (one fence, by one thread, behind the
-// CTA's barrier).  An instance's LAST `copiers` CTAs stay on: they wait until every CTA of the instance has reported
-// (they were the last to start, so few are still running) and then copy the instance's scratch volume out to the
+// CTA's barrier).  The last `copiers` CTAs of instance i + 1 then copy out instance i -- the scratch volume to the
 // caller's x-fastest volume, an equal share of the bricks each, zeroing behind themselves -- while every other CTA slot
-// of the machine is already walking the next instances.  The walk is bound by
-// its instructions, the copy-out by memory: side by side they fill both.  Instance i counts in scratch slot i mod
-// `ring`; a ring of four slots (64 MiB at 256^3) covers the window of instances in flight and stays largely resident
-// in the 126 MB L2, so the walk's reds, the copy-out's reads and the zeros behind it mostly stay off HBM.
+// of the machine walks on.  Every CTA of instance i was dispatched before them and has almost always reported by the
+// time they come off their own walk (each warp looks at the counter as it finishes; the CTA's report barrier is the
+// vote), so no CTA slot is held by a copier that waits.  Only the batch's last instance is copied out by its own last
+// `copiers_last` CTAs, which wait for its walk.  Instance i counts in scratch slot i mod `ring` (the pointer comes from
+// the host): a ring of four slots (64 MiB at 256^3) covers the window of instances in flight.
 //
-// Waiting: a copier waits for CTAs of its own instance (smaller block indices); a walk CTA of instance i waits (with
-// its vertex copy already in flight) for the copiers of instance i - ring (smaller block indices).  CTAs are dispatched in increasing linear block index (the order every spin-on-the-previous-block scheme
-// relies on -- serial split-K semaphores, decoupled look-back with block-index tickets), so whatever is waited for is
-// resident and running.  Waits are bounded: a lost dependency traps instead of hanging the device.  The verdict of the
-// fire-and-forget `red` walk (samples added == byte sum, see SinkPacked8Brick) is taken by an instance's last copier.
-// The control block of the NEXT call is zeroed here (two blocks alternate), so a frame is one launch (+ the repair
-// kernel's look at the flags).
+// Waiting: a copier waits for CTAs of the instance before its own; a walk CTA of instance i waits (with its vertex copy
+// already in flight) until instance i - ring has been copied out (by CTAs of instance i - ring + 1).  Everything waited
+// for has a smaller block index, and CTAs are dispatched in increasing linear block index (the order every
+// spin-on-the-previous-block scheme relies on -- serial split-K semaphores, decoupled look-back with block-index
+// tickets), so it is resident and running.  Waits are bounded: a lost dependency traps instead of hanging the device.
+// The verdict of the fire-and-forget `red` walk (samples added == byte sum, see SinkPacked8Brick) is taken by an
+// instance's last copier.  The control block of the NEXT call is zeroed here (two blocks alternate), so a frame is one
+// launch (+ the repair kernel's look at the flags).
 //
-// Three other forms were built and measured first (crowd frame, ms; separate kernels: 1.19): persistent CTAs drawing
-// CTA-wide items from one ordered ticket queue with the copy-out as queue items 1.27; the same with autonomous warps and
-// one item of look-ahead 2.1 (the tickets parked in look-ahead were the dependencies other warps span on); ticketed
-// one-item CTAs whose last finishers copy out 1.14-1.5 (a fifth of all warp-time at the barrier behind the ticket); this
-// grid with warp-wise reports and copiers 1.78 (a fence per warp: 15 % of all warp-time in the fence).
-// profiles/r02_b_*, r02_d_*, r02_e_*, r02_f_*, r02_g_*.
+// Forms built and measured before this one (crowd frame, ms; separate kernels: 1.19; this one: 0.98-1.01): persistent
+// CTAs drawing CTA-wide items from one ordered ticket queue with the copy-out as queue items 1.27; the same with
+// autonomous warps and one item of look-ahead 2.1 (the tickets parked in look-ahead were the dependencies other warps
+// span on); ticketed one-item CTAs whose last finishers copy out 1.14-1.5 (a fifth of all warp-time at the barrier behind
+// the ticket); this grid with warp-wise reports and copiers 1.78 (a fence per warp: 15 % of all warp-time in the fence);
+// this grid with an instance's OWN last 64 CTAs waiting for its walk and copying it out 1.03-1.08 (7 % of all warp-time
+// at that wait, and the copy-out paced the ring).  profiles/r02_b_* ... r02_h_*, r02_y_*, r02_aa_*; what bounds this
+// form: DESIGN.md 6.16.
 // ---------------------------------------------------------------------------
 constexpr uint32_t kFrameStatSlots = 32;
 constexpr uint32_t kFrameIndexedSegs = 2048;                    // segments per walk item of an indexed instance
@@ -543,11 +546,9 @@ struct FrameCtl {
 };
 struct FramePlan {
     uint32_t ring;                                              // scratch slots
-    uint32_t copiers;                                           // CTAs of an instance that copy it out (the last ones by block index)
+    uint32_t copiers;                                           // CTAs of instance i + 1 (its last ones by block index) that copy out instance i
     uint32_t n_bricks;
-    uint32_t copiers_last;                                      // ... of the batch's LAST instance: nothing walks beside its copy-out, so more hands
-    uint8_t* ring_base;
-    unsigned long long slot_bytes;
+    uint32_t copiers_last;                                      // CTAs of the batch's LAST instance that copy it out themselves (nobody comes behind it)
     FrameCtl* ctl;
     FrameCtl* ctl_next;
 };

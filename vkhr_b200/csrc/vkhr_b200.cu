@@ -498,8 +498,7 @@ int run_frame(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool small, cudaS
         P.n_bricks = (uint32_t)(nv / 32);
         uint32_t max_items = 1;
         for (uint32_t p = 0; p < m; ++p) max_items = std::max(max_items, ctx->batch.inst[p].n_tiles);
-        P.ring_base = static_cast<uint8_t*>(ctx->brick.p);
-        P.slot_bytes = nv;
+        uint8_t* const ring_base = static_cast<uint8_t*>(ctx->brick.p);
         FrameCtl* ctl = static_cast<FrameCtl*>(ctx->frame_ctl.p);
         P.ctl = ctl + (ctx->frame_calls & 1u);
         P.ctl_next = ctl + ((ctx->frame_calls + 1u) & 1u);
@@ -508,7 +507,7 @@ int run_frame(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool small, cudaS
             ctx->batch.inst[k].ovf_flag = base + (size_t)k * (bm_words + kHdr);
             ctx->batch.inst[k].ovf_bitmap = base + (size_t)k * (bm_words + kHdr) + kHdr;
             ctx->batch.inst[k].counts = static_cast<uint32_t*>(ctx->counts.p);
-            ctx->batch.inst[k].brick = P.ring_base + (size_t)(k % P.ring) * P.slot_bytes;   // instance k counts in slot k mod ring
+            ctx->batch.inst[k].brick = ring_base + (size_t)(k % P.ring) * nv;   // instance k counts in slot k mod ring
         }
         {
             PhaseMark mk(ctx, s, PH_WALK);
