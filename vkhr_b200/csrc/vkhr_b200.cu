@@ -163,6 +163,7 @@ struct vkhr_b200_ctx {
     Slot slots[kSlots];
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     int repair_blocks[2] = {0, 0};
+    int frame_slots[2] = {0, 0};  // CTAs of k_frame<3,3> / <4,4> the device holds at once (occupancy x SMs)
     DevBuf pf_occ;                // prefilter: occupancy cells + tile activity bytes
     DevBuf adsm_occ;              // ADSM coarse occupancy bits
     DevBuf adsm_table;            // the ADSM march's accumulated t sequence for `adsm_steps`
@@ -494,7 +495,18 @@ int run_frame(vkhr_b200_ctx* ctx, const Job* jobs, uint32_t n, bool small, cudaS
         // before them: nothing to wait for); the batch's last instance is copied out by its own last CTAs
         if (P.ring < 2u && m > 1u) return fail(ctx, VKHR_B200_ERR_INVALID_ARGUMENT, "the frame kernel needs a ring of two scratch volumes");
         P.copiers = VKHR_FRAME_COPIERS;
-        P.copiers_last = 256u;
+        // The last instance's own copiers are the one wait on LARGER block indices in the kernel (each waits for every CTA
+        // of its instance, the other copiers behind it included): all of them must fit on the device at once.  592 slots
+        // on a B200; half of what this device holds, on a smaller part.
+        int& slots = ctx->frame_slots[small ? 0 : 1];
+        if (slots == 0) {
+            int per_sm = 0;
+            if (small) CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame<3, 3>, kWalkThreads, 0));
+            else       CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame<4, 4>, kWalkThreads, 0));
+            if (per_sm < 1) return fail(ctx, VKHR_B200_ERR_CUDA, "frame kernel does not fit on an SM");
+            slots = per_sm * ctx->sm_count;
+        }
+        P.copiers_last = std::min<uint32_t>(256u, std::max<uint32_t>(1u, (uint32_t)slots / 2u));
         P.n_bricks = (uint32_t)(nv / 32);
         uint32_t max_items = 1;
         for (uint32_t p = 0; p < m; ++p) max_items = std::max(max_items, ctx->batch.inst[p].n_tiles);
