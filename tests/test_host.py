@@ -277,3 +277,68 @@ def test_copy_out_brick_coordinates_by_multiply_high():
         q = np.where(neg, q - np.uint64(1), q)
         r = np.where(neg, r + np.int64(d), r)
         assert np.array_equal(q, b // d) and np.array_equal(r.astype(np.uint64), b % d), int(d)
+
+
+def _simulate_frame_schedule(items, slots, ring, copiers, copiers_last, rng):
+    """The dependency structure of k_frame (kernels.cuh) as a model: CTAs are dispatched in linear block order
+    (instance-major) into `slots` resident places and leave when their last phase is done.  Phases of CTA (i, x):
+    [i >= ring: wait until instance i - ring is copied out] -> walk, report -> [one of the last min(items_i, copiers)
+    CTAs of i > 0: wait until every CTA of instance i - 1 has reported, copy, count] -> [last instance, one of its
+    last min(items, copiers_last) CTAs: wait for every CTA of its own instance, copy, count].  Phases complete in
+    random order (any interleaving the hardware could produce).  Returns True when every CTA finishes."""
+    n = len(items)
+    order = [(i, x) for i in range(n) for x in range(items[i])]
+    walk_done, copy_done = [0] * n, [0] * n
+    need_copies = [min(items[t + 1], copiers) if t + 1 < n else min(items[t], copiers_last) for t in range(n)]
+    resident, nxt, finished = {}, 0, 0            # (i, x) -> phase index
+    while finished < len(order):
+        while nxt < len(order) and len(resident) < slots:
+            resident[order[nxt]] = 0
+            nxt += 1
+        movable = []
+        for (i, x), ph in resident.items():
+            if ph == 0:                            # slot wait
+                ok = i < ring or copy_done[i - ring] >= need_copies[i - ring]
+            elif ph == 1:                          # walk + report: never blocks
+                ok = True
+            elif ph == 2:                          # role 0
+                mine = i > 0 and x + min(items[i], copiers) >= items[i]
+                ok = (not mine) or walk_done[i - 1] >= items[i - 1]
+            else:                                  # role 1
+                mine = i == n - 1 and x + min(items[i], copiers_last) >= items[i]
+                ok = (not mine) or walk_done[i] >= items[i]
+            if ok:
+                movable.append((i, x))
+        if not movable:
+            return False                           # every resident CTA waits and nothing else can be dispatched
+        i, x = movable[rng.integers(len(movable))]
+        ph = resident[(i, x)]
+        if ph == 1:
+            walk_done[i] += 1
+        elif ph == 2 and i > 0 and x + min(items[i], copiers) >= items[i]:
+            copy_done[i - 1] += 1
+        elif ph == 3 and i == n - 1 and x + min(items[i], copiers_last) >= items[i]:
+            copy_done[i] += 1
+        if ph == 3:
+            del resident[(i, x)]
+            finished += 1
+        else:
+            resident[(i, x)] = ph + 1
+    return all(copy_done[t] == need_copies[t] for t in range(n)) and all(walk_done[t] == items[t] for t in range(n))
+
+
+def test_frame_kernel_schedule_cannot_deadlock_in_the_model():
+    """Whatever the batch (ragged, instances of one item = no segments), the ring (>= 2 slots for a batch), the copier
+    counts and the interleaving: with in-order dispatch every wait of k_frame is on a smaller block index, except the
+    last instance's own copiers, which the host clamps to half the device's CTA slots (run_frame)."""
+    rng = np.random.default_rng(11)
+    for _ in range(300):
+        n = int(rng.integers(1, 9))
+        items = [int(rng.integers(1, 30)) for _ in range(n)]
+        slots = int(rng.integers(2, 40))
+        ring = int(rng.integers(2, 5)) if n > 1 else 1
+        copiers = int(rng.integers(1, 40))
+        copiers_last = max(1, min(int(rng.integers(1, 40)), slots // 2))          # the host's clamp
+        assert _simulate_frame_schedule(items, slots, min(ring, n), copiers, copiers_last, rng), (items, slots, ring, copiers, copiers_last)
+    # the clamp is what makes it so: more waiting copiers of the last instance than slots cannot finish
+    assert not _simulate_frame_schedule([20], 8, 1, 4, 16, np.random.default_rng(0))
