@@ -22,36 +22,6 @@ import numpy as np
 
 from harness import synth
 
-W = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-v, n, s = synth.shape("ponytail", seed=0x5EED, seg_len=0.5)
-lo, hi = synth.host_bounding_box(v)
-res = np.array([W, W, W], np.float32)
-vs = (hi - lo).astype(np.float32) / res
-P = ((v.reshape(-1, 3) - lo) / vs).astype(np.float32)             # vertices in voxel space, strand-major
-V, vps = P.shape[0], s + 1
-# the kernel's tiles: 31 vertices per warp-tile; lane t = vertex 31 * tile + t, idle when it ends a strand
-nt = (V - 1) // 31
-idx = np.arange(nt * 31).reshape(nt, 31)
-root, tip = P[idx], P[idx + 1]
-active = (idx % vps) != vps - 1
-d = tip - root
-steps = np.abs(d).max(axis=2)
-ns = np.ceil(steps).astype(np.int64) * active                      # samples of the lane's segment
-dirn = d / np.maximum(steps, 1e-30)[..., None]
-p = [root, root + dirn, root + dirn + dirn]                        # the first three samples (more are rare here)
-
-
-def word(q):
-    """Word index of a sample in the brick-ordered scratch (brick_word in walk.cuh); word >> 3 = sector."""
-    x = np.minimum(np.floor(q), res - 1).astype(np.int64)
-    brick = ((x[..., 2] >> 1) * (W // 4) + (x[..., 1] >> 2)) * (W // 4) + (x[..., 0] >> 2)
-    return brick * 8 + (x[..., 2] & 1) * 4 + (x[..., 1] & 3)
-
-
-w = [word(q) for q in p]
-total = int(ns.clip(max=3).sum())
-
-
 def count(keys, mask):
     """(packets, distinct sectors) summed over the rows (= warp instructions) of keys[mask]."""
     rows, L = keys.shape
@@ -71,40 +41,76 @@ def count(keys, mask):
     return int((mx * ok).sum()), int(ok.sum())
 
 
-def add(*parts):
-    return tuple(sum(x) for x in zip(*parts))
+
+def main():
+    W = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+    v, n, s = synth.shape("ponytail", seed=0x5EED, seg_len=0.5)
+    lo, hi = synth.host_bounding_box(v)
+    res = np.array([W, W, W], np.float32)
+    vs = (hi - lo).astype(np.float32) / res
+    P = ((v.reshape(-1, 3) - lo) / vs).astype(np.float32)             # vertices in voxel space, strand-major
+    V, vps = P.shape[0], s + 1
+    # the kernel's tiles: 31 vertices per warp-tile; lane t = vertex 31 * tile + t, idle when it ends a strand
+    nt = (V - 1) // 31
+    idx = np.arange(nt * 31).reshape(nt, 31)
+    root, tip = P[idx], P[idx + 1]
+    active = (idx % vps) != vps - 1
+    d = tip - root
+    steps = np.abs(d).max(axis=2)
+    ns = np.ceil(steps).astype(np.int64) * active                      # samples of the lane's segment
+    dirn = d / np.maximum(steps, 1e-30)[..., None]
+    p = [root, root + dirn, root + dirn + dirn]                        # the first three samples (more are rare here)
 
 
-out = {"W": W, "samples": total, "samples_per_segment": total / int(active.sum())}
-# (0) one segment per lane: instruction k = sample k of the tile's 31 lanes
-out["one_segment_per_lane"] = add(*[count(w[k], ns > k) for k in range(3)])
+    def word(q):
+        """Word index of a sample in the brick-ordered scratch (brick_word in walk.cuh); word >> 3 = sector."""
+        x = np.minimum(np.floor(q), res - 1).astype(np.int64)
+        brick = ((x[..., 2] >> 1) * (W // 4) + (x[..., 1] >> 2)) * (W // 4) + (x[..., 0] >> 2)
+        return brick * 8 + (x[..., 2] & 1) * 4 + (x[..., 1] & 3)
 
 
-# (1) dealt out again: an instruction carries both samples of 16 consecutive segments (lane j: sample j & 1 of segment j / 2)
-def dealt(a, b):
-    L = b - a
-    keys = np.empty((nt, 2 * L), np.int64); mask = np.empty((nt, 2 * L), bool)
-    keys[:, 0::2], keys[:, 1::2] = w[0][:, a:b], w[1][:, a:b]
-    mask[:, 0::2], mask[:, 1::2] = ns[:, a:b] > 0, ns[:, a:b] > 1
-    return keys, mask
+    w = [word(q) for q in p]
+    total = int(ns.clip(max=3).sum())
 
 
-out["dealt"] = add(count(*dealt(0, 16)), count(*dealt(16, 31)), count(w[2], ns > 2))
-# (1b) the same with runs of adjacent lanes on one word merged in software (what a match_any-style aggregation would add)
-merged = []
-for a, b in ((0, 16), (16, 31)):
-    keys, mask = dealt(a, b)
-    dup = np.zeros_like(mask); dup[:, 1:] = mask[:, 1:] & mask[:, :-1] & (keys[:, 1:] == keys[:, :-1])
-    merged.append(count(keys, mask & ~dup))
-out["dealt_and_adjacent_lanes_merged"] = add(*merged, count(w[2], ns > 2))
-# (2) neighbour absorption: the second sample of lane t joins the first sample of lane t + 1 when the words agree
-v0, v1 = ns > 0, ns > 1
-nxt_w = np.concatenate([w[0][:, 1:], np.full((nt, 1), -5)], axis=1)
-nxt_v = np.concatenate([v0[:, 1:], np.zeros((nt, 1), bool)], axis=1)
-absorbed = v1 & nxt_v & (w[1] == nxt_w)
-out["neighbour_absorption"] = add(count(w[0], v0), count(w[1], v1 & ~absorbed), count(w[2], ns > 2))
-out["share_of_second_samples_absorbed"] = float(absorbed.sum() / v1.sum())
-for k in ("one_segment_per_lane", "dealt", "dealt_and_adjacent_lanes_merged", "neighbour_absorption"):
-    pk, sec = out[k]
-    out[k] = {"packets_per_sample": pk / total, "distinct_sectors_per_sample": sec / total}
-print(json.dumps(out, indent=1))
+    def add(*parts):
+        return tuple(sum(x) for x in zip(*parts))
+
+
+    out = {"W": W, "samples": total, "samples_per_segment": total / int(active.sum())}
+    # (0) one segment per lane: instruction k = sample k of the tile's 31 lanes
+    out["one_segment_per_lane"] = add(*[count(w[k], ns > k) for k in range(3)])
+
+
+    # (1) dealt out again: an instruction carries both samples of 16 consecutive segments (lane j: sample j & 1 of segment j / 2)
+    def dealt(a, b):
+        L = b - a
+        keys = np.empty((nt, 2 * L), np.int64); mask = np.empty((nt, 2 * L), bool)
+        keys[:, 0::2], keys[:, 1::2] = w[0][:, a:b], w[1][:, a:b]
+        mask[:, 0::2], mask[:, 1::2] = ns[:, a:b] > 0, ns[:, a:b] > 1
+        return keys, mask
+
+
+    out["dealt"] = add(count(*dealt(0, 16)), count(*dealt(16, 31)), count(w[2], ns > 2))
+    # (1b) the same with runs of adjacent lanes on one word merged in software (what a match_any-style aggregation would add)
+    merged = []
+    for a, b in ((0, 16), (16, 31)):
+        keys, mask = dealt(a, b)
+        dup = np.zeros_like(mask); dup[:, 1:] = mask[:, 1:] & mask[:, :-1] & (keys[:, 1:] == keys[:, :-1])
+        merged.append(count(keys, mask & ~dup))
+    out["dealt_and_adjacent_lanes_merged"] = add(*merged, count(w[2], ns > 2))
+    # (2) neighbour absorption: the second sample of lane t joins the first sample of lane t + 1 when the words agree
+    v0, v1 = ns > 0, ns > 1
+    nxt_w = np.concatenate([w[0][:, 1:], np.full((nt, 1), -5)], axis=1)
+    nxt_v = np.concatenate([v0[:, 1:], np.zeros((nt, 1), bool)], axis=1)
+    absorbed = v1 & nxt_v & (w[1] == nxt_w)
+    out["neighbour_absorption"] = add(count(w[0], v0), count(w[1], v1 & ~absorbed), count(w[2], ns > 2))
+    out["share_of_second_samples_absorbed"] = float(absorbed.sum() / v1.sum())
+    for k in ("one_segment_per_lane", "dealt", "dealt_and_adjacent_lanes_merged", "neighbour_absorption"):
+        pk, sec = out[k]
+        out[k] = {"packets_per_sample": pk / total, "distinct_sectors_per_sample": sec / total}
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
